@@ -1,0 +1,186 @@
+/* jams_b200.h — C ABI of the B200-native llg-heun + exchange hot path for stonerlab/jams.
+ *
+ * This is the drop-in boundary ("Face 2"): a JAMS `Solver` subclass registered as
+ * module "llg-heun-b200-gpu"  calls these entry points instead of the
+ * cuSPARSE/cuBLAS/cuRAND path of `CUDAHeunLLGSolver`.  Every entry point names the reference
+ * interface it replaces (file:line relative to /root/reference/src/jams/).
+ *
+ * Conventions
+ *  - extern "C", opaque handle, plain pointers and sizes, int status (0 = JB_OK); no exceptions cross.
+ *  - units are JAMS internal units: time ps, field T, energy meV, moments meV/T (README.md:92-105).
+ *  - host arrays are caller-owned and in the REFERENCE's layout: per-site arrays of length N in
+ *    site order ((i*Ny + j)*Nz + k)*M + m (core/lattice.cc:622-657), vector fields N x 3 row-major
+ *    (globals::s, core/lattice.cc:688-694).  The library owns all device memory and keeps spins
+ *    in its own SoA/ghosted layout.
+ *  - `on_device != 0` means the pointer is a device pointer on the context's GPU (what
+ *    MultiArray::device_data() returns, containers/multiarray.h:239-253); otherwise host memory.
+ *  - one context per (process, GPU); calls on one context must come from one host thread at a
+ *    time; calls return after enqueueing work on the context's stream except those that hand
+ *    data back to the host, which synchronise.
+ *  - there is no CPU fallback: every compute entry point needs a CUDA device and fails with
+ *    JB_ERR_CUDA otherwise.
+ */
+#ifndef JAMS_B200_H
+#define JAMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define JB_API __attribute__((visibility("default")))
+#else
+#define JB_API
+#endif
+
+typedef struct jb_ctx jb_ctx;
+
+typedef enum jb_status {
+  JB_OK = 0,
+  JB_ERR_INVALID = 1,   /* bad argument / call order (jams::SanityException analogue) */
+  JB_ERR_CUDA = 2,      /* CUDA runtime/driver error (CHECK_CUDA_STATUS, cuda/cuda_common.h:43-77) */
+  JB_ERR_UNSUPPORTED = 3,
+  JB_ERR_PEER = 4       /* halo peer signalling timed out / peer mapping failed */
+} jb_status;
+
+/* Hamiltonian selector for jb_fields / jb_energies (Hamiltonian::create names, core/hamiltonian.cc:80-115) */
+typedef enum jb_term {
+  JB_TERM_EXCHANGE = 0,  /* "exchange"      hamiltonian/exchange.cc */
+  JB_TERM_UNIAXIAL = 1,  /* "uniaxial"      hamiltonian/uniaxial_anisotropy.cc */
+  JB_TERM_ZEEMAN = 2,    /* "zeeman"        hamiltonian/zeeman.cc */
+  JB_TERM_APPLIED = 3,   /* "applied-field" hamiltonian/applied_field.cc */
+  JB_TERM_TOTAL = 4      /* sum of the registered terms = globals::h after Solver::compute_fields */
+} jb_term;
+
+/* Lattice + slab description.  Replaces what the solver reads from globals::lattice
+ * (Lattice::size, is_periodic, num_basis_sites; core/lattice.h:54-153).
+ * The supercell has dims[0] x dims[1] x dims[2] unit cells of M motif sites.  This context owns
+ * the x-slab [x_begin, x_begin + nx_local) of it; single-GPU: x_begin = 0,
+ * nx_local = dims[0], n_ranks = 1.  N (local) = nx_local*dims[1]*dims[2]*M. */
+typedef struct jb_lattice_desc {
+  int32_t dims[3];
+  int32_t num_motif;      /* M */
+  int32_t periodic[3];    /* lattice.periodic (core/lattice.cc:413) */
+  int32_t x_begin;
+  int32_t nx_local;
+  int32_t rank;           /* position in the ring of slabs */
+  int32_t n_ranks;
+  int32_t device;         /* CUDA device ordinal, -1 = current device */
+} jb_lattice_desc;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Solver construction (core/jams++.cc:274; CUDAHeunLLGSolver::initialize, solvers/cuda_llg_heun.cu:21-62) */
+JB_API int jb_create(jb_ctx **ctx, const jb_lattice_desc *desc);
+JB_API void jb_destroy(jb_ctx *ctx);
+/* text of the last error on this context (or of a failed jb_create when ctx == NULL);
+ * the adapter rethrows it as std::runtime_error like cuda/cuda_common.h:43-77 */
+JB_API const char *jb_last_error(const jb_ctx *ctx);
+JB_API int jb_abi_version(void);
+
+/* ---- parameters ---------------------------------------------------------------------------- */
+/* globals::mus / gyro / alpha, N each (core/lattice.cc:703-713).  gyro already carries the
+ * Gilbert prefactor if the caller applied it (jams::gilbert_gyro_prefactor, core/lattice.cc:95-97). */
+JB_API int jb_set_materials(jb_ctx *ctx, const double *mus, const double *gyro, const double *alpha);
+
+/* Exchange, translation-invariant form: the processed interaction template of
+ * post_process_interactions (core/interactions.cc:292-347): entry n couples motif site motif_i[n]
+ * of cell (i,j,k) to motif site motif_j[n] of cell (i,j,k)+T3[3n..3n+2] with tensor J9[9n..] (row-major,
+ * meV, already multiplied by interaction_prefactor and the unit conversion, hamiltonian/exchange.cc:165).
+ * Boundary handling is Lattice::apply_boundary_conditions (core/lattice.cc:987-1007).
+ * Equivalent to the CSR that ExchangeHamiltonian builds (hamiltonian/exchange.cc:162-171) on a lattice
+ * without impurities. */
+JB_API int jb_set_exchange_template(jb_ctx *ctx, int32_t n, const int32_t *motif_i, const int32_t *motif_j,
+                             const int32_t *T3, const double *J9);
+
+/* Exchange, general form: the neighbour list itself, as
+ * ExchangeHamiltonian::neighbour_list() exposes it (hamiltonian/exchange.h:13,
+ * containers/interaction_list.h:45-47): pairs (i,j) in GLOBAL site ids with an index into the table
+ * of unique tensors (row-major 3x3, meV, already scaled).  Only pairs whose i lies in this
+ * context's slab are used.  Single-GPU only in this version (n_ranks == 1). */
+JB_API int jb_set_exchange_pairs(jb_ctx *ctx, int64_t n_pairs, const int32_t *i, const int32_t *j,
+                          const int32_t *value_id, int32_t n_values, const double *J9);
+
+/* UniaxialAnisotropyHamiltonian: power_ (2,4,6), magnitude_ (N, meV), axis_ (N x 3, unit vectors)
+ * (hamiltonian/uniaxial_anisotropy.h:30-32, .cc:89-114). */
+JB_API int jb_set_uniaxial(jb_ctx *ctx, int32_t power, const double *magnitude, const double *axis);
+
+/* ZeemanHamiltonian: dc_local_field_ (N x 3, already multiplied by mu_i, meV), optional
+ * ac_local_field_ (N x 3, meV) and ac_local_frequency_ (N, rad/ps = 2*pi*f) or NULL
+ * (hamiltonian/zeeman.cc:26-71). */
+JB_API int jb_set_zeeman(jb_ctx *ctx, const double *dc_local_field, const double *ac_local_field,
+                  const double *ac_local_frequency);
+
+/* AppliedFieldHamiltonian: homogeneous B(t) in Tesla; the field on site i is mu_i * B
+ * (hamiltonian/applied_field.cc:146-148).  Call again whenever B(t) changes. enable = 0 removes it. */
+JB_API int jb_set_applied_field(jb_ctx *ctx, const double B[3], int32_t enable);
+
+/* ---- state --------------------------------------------------------------------------------- */
+/* globals::s <-> device SoA.  s_aos is N(local) x 3 row-major (core/lattice.cc:688). */
+JB_API int jb_import_spins(jb_ctx *ctx, const double *s_aos, int32_t on_device);
+JB_API int jb_export_spins(jb_ctx *ctx, double *s_aos, int32_t on_device);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* nsteps calls of Solver::run (HeunLLGSolver::run, solvers/cpu_llg_heun.cc:45-148 /
+ * CUDAHeunLLGSolver::run, solvers/cuda_llg_heun.cu:64-122) fused into two kernels per step:
+ *   dt_ps           step_size_ (ps)
+ *   time_ps         solver time at the start of the first step (only AC Zeeman depends on it)
+ *   temperature_K   physics_module_->temperature() (core/solver.cc:94-97); 0 disables the thermostat
+ *   seed, first_step_index   key / counter of the Philox4x32-10 Langevin noise: the N(0,1) draw for
+ *                   (global site, component) at step index first_step_index + n depends on nothing
+ *                   else, so slab decompositions give identical trajectories
+ *   gilbert_prefactor  only enters sigma_i = sqrt(2 kB alpha_i / (mu_i gyro_i dt [1+alpha_i^2]))
+ *                   (solvers/cpu_llg_heun.cc:35-42, thermostats/cuda_thermostat_classical.cc:34-43) */
+JB_API int jb_step(jb_ctx *ctx, int32_t nsteps, double dt_ps, double time_ps, double temperature_K,
+            uint64_t seed, uint64_t first_step_index, int32_t gilbert_prefactor);
+
+/* Thermostat::device_data() equivalent (core/thermostat.h:22-34): the white-noise field
+ * xi_ij = sigma_i sqrt(T) n_ij in Tesla that jb_step uses at step `step_index`, N x 3.
+ * With normals_only != 0 the raw N(0,1) draws n_ij are returned instead. */
+JB_API int jb_noise(jb_ctx *ctx, double dt_ps, double temperature_K, uint64_t seed, uint64_t step_index,
+             int32_t gilbert_prefactor, int32_t normals_only, double *xi_aos, int32_t on_device);
+
+/* ---- Hamiltonian / Monitor surface ------------------------------------------------------------ */
+/* Hamiltonian::calculate_fields(time) (core/hamiltonian.h:27-42): field of one term (meV, NOT divided
+ * by mu) or JB_TERM_TOTAL (= globals::h after Solver::compute_fields, core/solver.cc:43-57), N x 3. */
+JB_API int jb_fields(jb_ctx *ctx, int32_t term, double time_ps, double *h_aos, int32_t on_device);
+
+/* Hamiltonian::calculate_energies / calculate_total_energy (core/hamiltonian.h:27-42):
+ * per-spin energies e (N, may be NULL; exchange: -s_i.(A s)_i, sparse_interaction.cc:79-84) and the
+ * total (exchange carries the factor 1/2, sparse_interaction.cc:86-100; this rank's slab only). */
+JB_API int jb_energies(jb_ctx *ctx, int32_t term, double time_ps, double *e, int32_t on_device, double *total);
+
+/* MagnetisationMonitor::update reduction (monitors/magnetisation.cc:88-100, helpers/spinops.cc:55-67):
+ * M4[4g..4g+3] = { sum_i mu_i s_i (x,y,z), sum_i mu_i } over the spins of group g in this slab.
+ * group_of_spin (N, values in [0,n_groups)) or NULL for a single group. */
+JB_API int jb_magnetisation(jb_ctx *ctx, int32_t n_groups, const int32_t *group_of_spin, double *M4);
+
+/* ---- multi-GPU halo plumbing (no reference counterpart) ------------------------- */
+/* Each rank exports one opaque handle blob (JB_HALO_HANDLE_BYTES) describing its device buffers;
+ * the host layer all-gathers the blobs (torch.distributed / MPI / files) and hands every rank the
+ * blobs of its ring neighbours.  After jb_halo_connect the stage kernels store boundary planes
+ * straight into the neighbours' ghost planes over NVLink (P2P stores) and signal with flags. */
+#define JB_HALO_HANDLE_BYTES 256
+JB_API int jb_halo_export_handle(jb_ctx *ctx, void *blob);
+JB_API int jb_halo_connect(jb_ctx *ctx, const void *blob_lo_neighbour, const void *blob_hi_neighbour);
+
+/* ---- introspection for benches and tests -------------------------------------------------------- */
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+JB_API int64_t jb_kernel_launches(const jb_ctx *ctx);
+/* device time in ms of the stage kernels of the most recent jb_step, measured with CUDA events on the
+ * context's stream; out2[0] = stage A total, out2[1] = stage B total.  Synchronises. */
+JB_API int jb_last_step_kernel_ms(jb_ctx *ctx, double *out2);
+/* block until all enqueued work of this context has finished */
+JB_API int jb_synchronize(jb_ctx *ctx);
+/* the cudaStream_t the context launches on (so callers can record events on it) */
+JB_API void *jb_stream(jb_ctx *ctx);
+/* tuning knobs (tile shape etc.); unknown keys return JB_ERR_INVALID */
+JB_API int jb_set_option(jb_ctx *ctx, const char *key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAMS_B200_H */

@@ -1,0 +1,927 @@
+// jb_capi.cu — host side of the C ABI declared in include/jams_b200.h.
+// Owns the context (device buffers, tables, TMA descriptors, halo peers) and sequences the kernels of
+// jb_kernels.cu.  No CPU compute path exists here: without a CUDA device every entry point fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "jb_internal.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr double kBoltzmannIU = 0.0861733326;  // meV/K, reference helpers/consts.h:32
+
+#define JB_FAIL(ctx, code, msg)          \
+  do {                                   \
+    (ctx)->err = (msg);                  \
+    return (code);                       \
+  } while (0)
+
+#define JB_CUDA(ctx, call)                                                                       \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorName(e_) + " - " + cudaGetErrorString(e_); \
+      return JB_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+struct Blob {  // contents of a JB_HALO_HANDLE_BYTES halo handle
+  uint32_t magic;
+  int32_t pid;
+  int32_t device;
+  int32_t rank;
+  int32_t nx, PY, PZ, M, gx;
+  uint64_t base_ptr;             // slab base in the exporting process
+  uint64_t off_S0[3], off_S1[3]; // byte offsets inside the slab
+  uint64_t off_flags;
+  cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(Blob) <= JB_HALO_HANDLE_BYTES, "halo blob too large");
+
+void free_dev(void *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void release_state(jb_ctx *c) {
+  if (c->slab) cudaFree(c->slab);
+  c->slab = nullptr;
+  for (int k = 0; k < 3; ++k) {
+    c->S0[k] = c->S1[k] = nullptr;
+    if (c->U[k]) cudaFree(c->U[k]);
+    c->U[k] = nullptr;
+  }
+  c->flags = nullptr;
+  c->state_allocated = false;
+  c->tmap_valid = false;
+}
+
+int ensure_scratch(jb_ctx *c, size_t bytes) {
+  if (c->d_scratch_bytes >= bytes) return JB_OK;
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  c->d_scratch = nullptr; c->d_scratch_bytes = 0;
+  JB_CUDA(c, cudaMalloc(&c->d_scratch, bytes));
+  c->d_scratch_bytes = bytes;
+  return JB_OK;
+}
+
+int ensure_aos(jb_ctx *c) {
+  const size_t bytes = (size_t)c->N * 3 * sizeof(double);
+  if (c->d_aos_bytes >= bytes) return JB_OK;
+  if (c->d_aos) cudaFree(c->d_aos);
+  c->d_aos = nullptr; c->d_aos_bytes = 0;
+  JB_CUDA(c, cudaMalloc(&c->d_aos, bytes));
+  c->d_aos_bytes = bytes;
+  return JB_OK;
+}
+
+// ---- geometry --------------------------------------------------------------------------------------
+void compute_geometry(jb_ctx *c, int gx, int gy, int gz) {
+  JbGeom &g = c->g;
+  g.nx = c->d.nx_local; g.Ny = c->d.dims[1]; g.Nz = c->d.dims[2]; g.M = c->d.num_motif;
+  g.gx = gx; g.gy = gy; g.gz = gz;
+  g.PX = g.nx + 2 * gx; g.PY = g.Ny + 2 * gy;
+  g.PZ = g.Nz + 2 * gz;
+  if (g.PZ & 1) g.PZ += 1;
+  g.sY = (long long)g.M * g.PZ;
+  g.sX = (long long)g.PY * g.sY;
+  g.elems = (long long)g.PX * g.sX;
+  for (int k = 0; k < 3; ++k) g.per[k] = c->d.periodic[k];
+  g.x_begin = c->d.x_begin; g.Nx_global = c->d.dims[0];
+  g.n_ranks = c->d.n_ranks; g.rank = c->d.rank;
+}
+
+int allocate_state(jb_ctx *c) {
+  release_state(c);
+  const JbGeom &g = c->g;
+  if (g.elems >= (1ll << 31)) JB_FAIL(c, JB_ERR_UNSUPPORTED, "slab too large for 32-bit in-box offsets; use more ranks");
+  const size_t comp = ((size_t)g.elems * sizeof(double) + 255) / 256 * 256;
+  const size_t total = 6 * comp + 256;
+  JB_CUDA(c, cudaMalloc(&c->slab, total));
+  c->slab_bytes = total;
+  JB_CUDA(c, cudaMemsetAsync(c->slab, 0, total, c->stream));
+  char *base = static_cast<char *>(c->slab);
+  for (int k = 0; k < 3; ++k) {
+    c->S0[k] = reinterpret_cast<double *>(base + (size_t)k * comp);
+    c->S1[k] = reinterpret_cast<double *>(base + (size_t)(3 + k) * comp);
+    JB_CUDA(c, cudaMalloc(&c->U[k], comp));
+    JB_CUDA(c, cudaMemsetAsync(c->U[k], 0, comp, c->stream));
+  }
+  c->flags = reinterpret_cast<unsigned long long *>(base + 6 * comp);
+  c->state_allocated = true;
+  c->tmap_valid = false;
+  c->halo_connected = false;
+  c->epoch = 0;
+  return JB_OK;
+}
+
+// ---- exchange template -> device tables -------------------------------------------------------------
+int build_template_tables(jb_ctx *c, int BZ_tile) {
+  const JbGeom &g = c->g;
+  const int n = (int)c->t_mi.size();
+  const int M = g.M;
+  // unique tensors
+  std::vector<std::array<double, 9>> uniq;
+  std::vector<int> jidx(n);
+  bool iso = true;
+  for (int k = 0; k < n; ++k) {
+    std::array<double, 9> J;
+    std::copy(c->t_J9.begin() + 9 * k, c->t_J9.begin() + 9 * k + 9, J.begin());
+    if (!(J[1] == 0 && J[2] == 0 && J[3] == 0 && J[5] == 0 && J[6] == 0 && J[7] == 0 && J[0] == J[4] && J[4] == J[8])) iso = false;
+    auto it = std::find(uniq.begin(), uniq.end(), J);
+    if (it == uniq.end()) { uniq.push_back(J); jidx[k] = (int)uniq.size() - 1; }
+    else jidx[k] = (int)(it - uniq.begin());
+  }
+  // per motif, ordered like the reference's CSR columns for an interior site: ascending neighbour
+  // site id = lexicographic (Tx, Ty, Tz, mj)  (interface/sparse_blas.h:22-25 sums in that order)
+  std::vector<int> order(n);
+  for (int k = 0; k < n; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (c->t_mi[a] != c->t_mi[b]) return c->t_mi[a] < c->t_mi[b];
+    for (int d = 0; d < 3; ++d) if (c->t_T[3 * a + d] != c->t_T[3 * b + d]) return c->t_T[3 * a + d] < c->t_T[3 * b + d];
+    return c->t_mj[a] < c->t_mj[b];
+  });
+  std::vector<JbNbr> glob(n), tile(n);
+  for (int m = 0; m <= M; ++m) c->nbr_begin[m] = 0;
+  for (int pos = 0; pos < n; ++pos) {
+    const int k = order[pos];
+    const int mi = c->t_mi[k], mj = c->t_mj[k];
+    const int Tx = c->t_T[3 * k], Ty = c->t_T[3 * k + 1], Tz = c->t_T[3 * k + 2];
+    if (pos > 0) {
+      const int q = order[pos - 1];
+      if (c->t_mi[q] == mi && c->t_mj[q] == mj && c->t_T[3 * q] == Tx && c->t_T[3 * q + 1] == Ty && c->t_T[3 * q + 2] == Tz)
+        JB_FAIL(c, JB_ERR_INVALID, "Multiple interactions for the same motif pair and translation in the exchange template");
+    }
+    JbNbr e{};
+    e.dx = Tx; e.jidx = jidx[k]; e.J = c->t_J9[9 * k];
+    e.delta = (Ty * M + (mj - mi)) * g.PZ + Tz;
+    glob[pos] = e;
+    e.delta = (Ty * M + (mj - mi)) * BZ_tile + Tz;
+    tile[pos] = e;
+    c->nbr_begin[mi + 1]++;
+  }
+  for (int m = 0; m < M; ++m) c->nbr_begin[m + 1] += c->nbr_begin[m];
+  c->iso = iso;
+  c->n_unique_J = (int)uniq.size();
+  if (c->d_nbr_global) cudaFree(c->d_nbr_global);
+  if (c->d_nbr_tile) cudaFree(c->d_nbr_tile);
+  if (c->d_Jtab) cudaFree(c->d_Jtab);
+  c->d_nbr_global = c->d_nbr_tile = nullptr; c->d_Jtab = nullptr;
+  if (n > 0) {
+    JB_CUDA(c, cudaMalloc(&c->d_nbr_global, n * sizeof(JbNbr)));
+    JB_CUDA(c, cudaMalloc(&c->d_nbr_tile, n * sizeof(JbNbr)));
+    JB_CUDA(c, cudaMalloc(&c->d_Jtab, uniq.size() * 9 * sizeof(double)));
+    JB_CUDA(c, cudaMemcpy(c->d_nbr_global, glob.data(), n * sizeof(JbNbr), cudaMemcpyHostToDevice));
+    JB_CUDA(c, cudaMemcpy(c->d_nbr_tile, tile.data(), n * sizeof(JbNbr), cudaMemcpyHostToDevice));
+    JB_CUDA(c, cudaMemcpy(c->d_Jtab, uniq.data(), uniq.size() * 9 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  c->tile_BZ_built = BZ_tile;
+  return JB_OK;
+}
+
+// ---- per-site parameters -> classes ------------------------------------------------------------------
+int build_classes(jb_ctx *c) {
+  if (!c->classes_dirty) return JB_OK;
+  const JbGeom &g = c->g;
+  const int N = c->N;
+  if ((int)c->h_mus.size() != N) JB_FAIL(c, JB_ERR_INVALID, "jb_set_materials has not been called");
+  std::map<std::array<double, 18>, int> seen;
+  c->h_classes.clear(); c->h_class_dc.clear(); c->h_class_ac.clear(); c->h_class_omega.clear();
+  std::vector<unsigned char> cls(N);
+  for (int i = 0; i < N; ++i) {
+    std::array<double, 18> key{};
+    key[0] = c->h_mus[i]; key[1] = c->h_gyro[i]; key[2] = c->h_alpha[i];
+    if (c->uni_power) { key[3] = c->h_K[i]; key[4] = c->h_axis[3 * i]; key[5] = c->h_axis[3 * i + 1]; key[6] = c->h_axis[3 * i + 2]; }
+    if (c->has_zeeman) { key[7] = c->h_dc[3 * i]; key[8] = c->h_dc[3 * i + 1]; key[9] = c->h_dc[3 * i + 2]; }
+    if (c->has_ac) { key[10] = c->h_ac[3 * i]; key[11] = c->h_ac[3 * i + 1]; key[12] = c->h_ac[3 * i + 2]; key[13] = c->h_omega[i]; }
+    auto it = seen.find(key);
+    int id;
+    if (it == seen.end()) {
+      id = (int)c->h_classes.size();
+      if (id >= JB_MAX_CLASSES) JB_FAIL(c, JB_ERR_UNSUPPORTED, "more than JB_MAX_CLASSES distinct per-site parameter sets");
+      seen.emplace(key, id);
+      JbClass k{};
+      k.mu = key[0]; k.inv_mu = (key[0] != 0.0) ? 1.0 / key[0] : 0.0;
+      k.mgyro = -key[1]; k.alpha = key[2];
+      k.K = key[3]; k.Kp = key[3] * c->uni_power; k.ax = key[4]; k.ay = key[5]; k.az = key[6];
+      k.power = (c->uni_power && key[3] != 0.0) ? c->uni_power : 0;
+      c->h_classes.push_back(k);
+      for (int d = 0; d < 3; ++d) { c->h_class_dc.push_back(key[7 + d]); c->h_class_ac.push_back(key[10 + d]); }
+      c->h_class_omega.push_back(key[13]);
+    } else {
+      id = it->second;
+    }
+    cls[i] = (unsigned char)id;
+  }
+  // motif-uniform?
+  c->motif_uniform = true;
+  for (int m = 0; m < g.M && m < JB_MAX_MOTIF; ++m) c->class_of_motif[m] = cls[m];
+  for (int i = 0; i < N && c->motif_uniform; ++i) if (cls[i] != cls[i % g.M]) c->motif_uniform = false;
+  if (c->d_site_class) cudaFree(c->d_site_class);
+  c->d_site_class = nullptr;
+  if (!c->motif_uniform) {
+    // reorder to interior layout order [x][y][m][z]
+    std::vector<unsigned char> lay(N);
+    long long q = 0;
+    for (int x = 0; x < g.nx; ++x) for (int y = 0; y < g.Ny; ++y) for (int m = 0; m < g.M; ++m) for (int z = 0; z < g.Nz; ++z)
+      lay[q++] = cls[(((long long)x * g.Ny + y) * g.Nz + z) * g.M + m];
+    JB_CUDA(c, cudaMalloc(&c->d_site_class, N));
+    JB_CUDA(c, cudaMemcpy(c->d_site_class, lay.data(), N, cudaMemcpyHostToDevice));
+  }
+  c->classes_dirty = false;
+  c->class_sig.clear();
+  return JB_OK;
+}
+
+// fill sigma and the constant field of `count` consecutive stage tables and upload them.
+//   which_f: JB_TERM_TOTAL (zeeman + applied), JB_TERM_ZEEMAN, JB_TERM_APPLIED, or -1 (none)
+int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, double T, int gilbert, int which_f) {
+  const int nc = (int)c->h_classes.size();
+  const size_t count = times.size();
+  // skip the upload (and its host/device synchronisation) when the table on the device is current
+  std::vector<double> sig = {dt, T, (double)gilbert, (double)which_f, c->applied_B[0], c->applied_B[1], c->applied_B[2],
+                             c->has_applied ? 1.0 : 0.0, (double)nc};
+  sig.insert(sig.end(), times.begin(), times.end());
+  if (c->d_classes && sig == c->class_sig) return JB_OK;
+  std::vector<JbClass> tab(nc * count);
+  for (size_t s = 0; s < count; ++s) {
+    for (int k = 0; k < nc; ++k) {
+      JbClass cl = c->h_classes[k];
+      const double gyro = -cl.mgyro;
+      if (T > 0.0 && dt > 0.0 && cl.mu != 0.0 && gyro != 0.0) {
+        double denominator = 1.0;
+        if (gilbert) denominator = 1.0 + cl.alpha * cl.alpha;
+        // solvers/cpu_llg_heun.cc:35-42 times sqrt(T) (:57-63)
+        cl.sigma = sqrt((2.0 * kBoltzmannIU * cl.alpha) / (cl.mu * gyro * dt * denominator)) * sqrt(T);
+      } else {
+        cl.sigma = 0.0;
+      }
+      double f[3] = {0, 0, 0};
+      if (which_f == JB_TERM_TOTAL || which_f == JB_TERM_ZEEMAN) {
+        for (int d = 0; d < 3; ++d) {
+          f[d] += c->has_zeeman ? c->h_class_dc[3 * k + d] : 0.0;
+          if (c->has_ac) f[d] += c->h_class_ac[3 * k + d] * cos(c->h_class_omega[k] * times[s]);  // zeeman.cc:126-130
+        }
+      }
+      if ((which_f == JB_TERM_TOTAL || which_f == JB_TERM_APPLIED) && c->has_applied) {
+        for (int d = 0; d < 3; ++d) f[d] += cl.mu * c->applied_B[d];  // applied_field.cc:146-148
+      }
+      cl.fx = f[0]; cl.fy = f[1]; cl.fz = f[2];
+      tab[s * nc + k] = cl;
+    }
+  }
+  const size_t bytes = tab.size() * sizeof(JbClass);
+  static_assert(sizeof(JbClass) % 8 == 0, "class size");
+  if (c->h_pinned_bytes < bytes) {
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    c->h_pinned = nullptr; c->h_pinned_bytes = 0;
+    JB_CUDA(c, cudaMallocHost(&c->h_pinned, bytes));
+    c->h_pinned_bytes = bytes;
+    if (c->d_classes) cudaFree(c->d_classes);
+    c->d_classes = nullptr;
+    JB_CUDA(c, cudaMalloc(&c->d_classes, bytes));
+  }
+  // the pinned buffer may still be in flight from a previous upload on this stream
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(c->h_pinned, tab.data(), bytes);
+  JB_CUDA(c, cudaMemcpyAsync(c->d_classes, c->h_pinned, bytes, cudaMemcpyHostToDevice, c->stream));
+  c->class_sig = sig;
+  return JB_OK;
+}
+
+void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
+  t.nbr_global = c->d_nbr_global; t.nbr_tile = c->d_nbr_tile; t.Jtab = c->d_Jtab;
+  t.classes = c->d_classes + (size_t)class_table_index * c->h_classes.size();
+  t.site_class = c->d_site_class;
+  for (int m = 0; m <= JB_MAX_MOTIF; ++m) t.nbr_begin[m] = (m <= c->g.M && c->has_template) ? c->nbr_begin[m] : 0;
+  for (int m = 0; m < JB_MAX_MOTIF; ++m) t.class_of_motif[m] = c->class_of_motif[m];
+  t.n_classes = (int)c->h_classes.size();
+  t.iso = c->iso ? 1 : 0;
+}
+
+// ---- tiling of the TMA kernel -------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Tiling { int TY, TZ, XC, BY, BZ, rows, slot_elems, R, n_yt, n_zt, n_ch, spt, threads; bool ok; };
+
+Tiling choose_tiling(jb_ctx *c) {
+  const JbGeom &g = c->g;
+  Tiling t{};
+  t.ok = false;
+  if (!c->has_template || !c->motif_uniform || g.gx > 3) return t;
+  t.threads = c->opt_threads;
+  t.R = c->opt_R ? c->opt_R : ((2 * g.gx + 2) <= 4 ? 4 : 8);
+  if (t.R < 2 * g.gx + 2 || t.R > JB_MAX_RING || (t.R & (t.R - 1))) return t;
+  int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
+  if (TZ > g.Nz) TZ = g.Nz;
+  int TY = c->opt_TY;
+  if (!TY) {
+    // aim for ~512-1024 in-plane sites per CTA while keeping two CTAs per SM in shared memory
+    TY = std::max(1, 512 / (TZ * g.M));
+    if (TY > g.Ny) TY = g.Ny;
+  }
+  for (;;) {
+    t.TY = TY; t.TZ = TZ;
+    t.BY = TY + 2 * g.gy; t.BZ = TZ + 2 * g.gz; if (t.BZ & 1) t.BZ++;
+    t.rows = t.BY * g.M;
+    t.slot_elems = (t.rows * t.BZ + 15) / 16 * 16;
+    const size_t smem = (size_t)t.R * 3 * t.slot_elems * 8;
+    if (smem <= 100 * 1024 || TY == 1 || c->opt_TY) break;
+    TY = std::max(1, TY / 2);
+  }
+  if (t.rows > 256 || t.BZ > 256) return t;
+  if ((size_t)t.R * 3 * t.slot_elems * 8 + 4096 > 220 * 1024) return t;
+  t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
+  const int Q = t.TY * g.M * t.TZ;
+  t.spt = (Q + t.threads - 1) / t.threads;
+  if (t.spt > 4) { t.threads = 512; t.spt = (Q + 511) / 512; }
+  if (t.spt > 4) return t;
+  int XC = c->opt_XC;
+  if (!XC) {
+    // enough CTAs for >= ~6 waves of 2 CTAs/SM, but chunks of at least 8 planes to amortise the x halo
+    const long long cols = (long long)t.n_yt * t.n_zt;
+    long long want_chunks = (148LL * 2 * 6 + cols - 1) / cols;
+    XC = (int)std::max<long long>(8, g.nx / std::max<long long>(1, want_chunks));
+    if (XC > g.nx) XC = g.nx;
+  }
+  t.XC = XC;
+  t.n_ch = (g.nx + XC - 1) / XC;
+  t.ok = true;
+  return t;
+}
+
+int build_tmaps(jb_ctx *c, const Tiling &t) {
+  if (c->tmap_valid && c->tmap_BY == t.BY && c->tmap_BZ == t.BZ) return JB_OK;
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    JB_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) JB_FAIL(c, JB_ERR_CUDA, "cuTensorMapEncodeTiled not available in this driver");
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const JbGeom &g = c->g;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.PZ, (cuuint64_t)g.PY * g.M, (cuuint64_t)g.PX};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.PZ * 8, (cuuint64_t)g.sX * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)t.BZ, (cuuint32_t)t.rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  for (int a = 0; a < 2; ++a) {
+    for (int k = 0; k < 3; ++k) {
+      double *base = a == 0 ? c->S0[k] : c->S1[k];
+      CUresult r = encode(&c->tmap[a][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) JB_FAIL(c, JB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    }
+  }
+  c->tmap_valid = true; c->tmap_BY = t.BY; c->tmap_BZ = t.BZ;
+  return JB_OK;
+}
+
+// make geometry, state, tables and classes consistent with the parameters set so far
+int ensure_ready(jb_ctx *c) {
+  JB_CUDA(c, cudaSetDevice(c->device));
+  int gx = 0, gy = 0, gz = 0;
+  if (c->has_template) {
+    for (size_t k = 0; k < c->t_mi.size(); ++k) {
+      gx = std::max(gx, std::abs(c->t_T[3 * k])); gy = std::max(gy, std::abs(c->t_T[3 * k + 1])); gz = std::max(gz, std::abs(c->t_T[3 * k + 2]));
+    }
+  }
+  const JbGeom &g = c->g;
+  const bool geom_changed = !c->state_allocated || gx != g.gx || gy != g.gy || gz != g.gz;
+  if (geom_changed) {
+    // the reference throws "Multiple interactions" when a periodic dimension is so short that two
+    // template entries reach the same site (core/interactions.cc:373-381); the ghost scheme needs
+    // the same condition
+    const int ext[3] = {c->d.dims[0], c->d.dims[1], c->d.dims[2]};
+    const int gg[3] = {gx, gy, gz};
+    for (int d = 0; d < 3; ++d) {
+      if (gg[d] > 0 && c->d.periodic[d] && ext[d] < 2 * gg[d] + 1)
+        JB_FAIL(c, JB_ERR_INVALID, "periodic dimension shorter than 2*range+1 of the exchange template (the reference reports 'Multiple interactions' here)");
+    }
+    if (gx > c->d.nx_local || (c->d.n_ranks == 1 && c->d.periodic[0] && gx > 0 && c->d.nx_local < 2 * gx))
+      JB_FAIL(c, JB_ERR_INVALID, "slab thinner than the x range of the exchange template");
+    std::vector<double> keep;
+    const bool had_state = c->state_allocated;
+    if (had_state) {  // re-layout: carry the spins over
+      int rc = ensure_aos(c); if (rc) return rc;
+      const double *src[3] = {c->S0[0], c->S0[1], c->S0[2]};
+      JB_CUDA(c, jbk_export(c->g, src, c->d_aos, c->stream)); c->launches++;
+      JB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    compute_geometry(c, gx, gy, gz);
+    int rc = allocate_state(c); if (rc) return rc;
+    if (had_state) {
+      double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
+      JB_CUDA(c, jbk_import(c->g, c->d_aos, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
+    }
+    c->tile_BZ_built = -1;
+    c->classes_dirty = true;
+  }
+  int rc = build_classes(c); if (rc) return rc;
+  if (c->has_template) {
+    Tiling t = choose_tiling(c);
+    const int BZ = t.ok ? t.BZ : 0;
+    if (c->tile_BZ_built != BZ) { rc = build_template_tables(c, BZ); if (rc) return rc; }
+  }
+  return JB_OK;
+}
+
+void record_event(jb_ctx *c, int kind) {
+  if (!c->opt_time_kernels) return;
+  if (c->ev_used >= c->ev.size()) {
+    if (c->ev.size() >= 16384) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    c->ev.push_back(e); c->ev_kind.push_back(0);
+  }
+  c->ev_kind[c->ev_used] = kind;
+  cudaEventRecord(c->ev[c->ev_used++], c->stream);
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int jb_abi_version(void) { return JB_ABI_VERSION; }
+
+const char *jb_last_error(const jb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int jb_create(jb_ctx **out, const jb_lattice_desc *desc) {
+  if (!out || !desc) { g_create_error = "null argument"; return JB_ERR_INVALID; }
+  *out = nullptr;
+  if (desc->dims[0] < 1 || desc->dims[1] < 1 || desc->dims[2] < 1 || desc->num_motif < 1 || desc->num_motif > JB_MAX_MOTIF) {
+    g_create_error = "invalid lattice dimensions or motif size"; return JB_ERR_INVALID;
+  }
+  if (desc->n_ranks < 1 || desc->rank < 0 || desc->rank >= desc->n_ranks || desc->nx_local < 1 || desc->x_begin < 0 ||
+      desc->x_begin + desc->nx_local > desc->dims[0]) {
+    g_create_error = "invalid slab description"; return JB_ERR_INVALID;
+  }
+  if (desc->n_ranks == 1 && (desc->x_begin != 0 || desc->nx_local != desc->dims[0])) {
+    g_create_error = "single-rank context must own the whole lattice"; return JB_ERR_INVALID;
+  }
+  const long long N = (long long)desc->nx_local * desc->dims[1] * desc->dims[2] * desc->num_motif;
+  if (N >= (1ll << 31)) { g_create_error = "more than 2^31 spins per context"; return JB_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (jams_b200 has no CPU fallback)";
+    return JB_ERR_CUDA;
+  }
+  int dev = desc->device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { g_create_error = "device ordinal out of range"; return JB_ERR_INVALID; }
+  jb_ctx *c = new jb_ctx;
+  c->d = *desc; c->device = dev; c->N = (int)N;
+  if ((e = cudaSetDevice(dev)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+    delete c; return JB_ERR_CUDA;
+  }
+  compute_geometry(c, 0, 0, 0);
+  *out = c;
+  return JB_OK;
+}
+
+void jb_destroy(jb_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->peer_lo_base) cudaIpcCloseMemHandle(c->peer_lo_base);
+  if (c->peer_hi_base && !c->same_peer) cudaIpcCloseMemHandle(c->peer_hi_base);
+  release_state(c);
+  void *p;
+  p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
+  p = c->d_nbr_global; free_dev(p); p = c->d_nbr_tile; free_dev(p); p = c->d_Jtab; free_dev(p);
+  p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
+  p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  for (auto ev : c->ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int jb_set_materials(jb_ctx *c, const double *mus, const double *gyro, const double *alpha) {
+  if (!c || !mus || !gyro || !alpha) return JB_ERR_INVALID;
+  c->h_mus.assign(mus, mus + c->N); c->h_gyro.assign(gyro, gyro + c->N); c->h_alpha.assign(alpha, alpha + c->N);
+  c->classes_dirty = true;
+  return JB_OK;
+}
+
+int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int32_t *mj, const int32_t *T3, const double *J9) {
+  if (!c || n < 0 || (n > 0 && (!mi || !mj || !T3 || !J9))) return JB_ERR_INVALID;
+  for (int k = 0; k < n; ++k) {
+    if (mi[k] < 0 || mi[k] >= c->d.num_motif || mj[k] < 0 || mj[k] >= c->d.num_motif) JB_FAIL(c, JB_ERR_INVALID, "motif index out of range in exchange template");
+  }
+  c->t_mi.assign(mi, mi + n); c->t_mj.assign(mj, mj + n); c->t_T.assign(T3, T3 + 3 * n); c->t_J9.assign(J9, J9 + 9 * (size_t)n);
+  c->has_template = n > 0;
+  c->has_pairs = false;
+  c->tile_BZ_built = -1;
+  return JB_OK;
+}
+
+int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const int32_t *pj, const int32_t *vid, int32_t n_values, const double *J9) {
+  if (!c || n_pairs < 0 || n_values < 0 || (n_pairs > 0 && (!pi || !pj || !vid || !J9))) return JB_ERR_INVALID;
+  if (c->d.n_ranks != 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_set_exchange_pairs is single-rank only in this version");
+  JB_CUDA(c, cudaSetDevice(c->device));
+  c->has_template = false; c->t_mi.clear(); c->t_mj.clear(); c->t_T.clear(); c->t_J9.clear();
+  c->has_pairs = false;
+  int rc = ensure_ready(c);  // geometry without ghosts
+  if (rc) return rc;
+  const JbGeom &g = c->g;
+  const int N = c->N;
+  std::vector<int> count(N, 0);
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    if (pi[p] < 0 || pi[p] >= N || pj[p] < 0 || pj[p] >= N || vid[p] < 0 || vid[p] >= n_values) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
+    count[pi[p]]++;
+  }
+  int width = 0;
+  for (int i = 0; i < N; ++i) width = std::max(width, count[i]);
+  auto layout_q = [&](int ref) {  // reference site id -> interior layout order q and ghosted index
+    const int m = ref % g.M; int r = ref / g.M; const int z = r % g.Nz; r /= g.Nz; const int y = r % g.Ny; const int x = r / g.Ny;
+    const long long q = (((long long)x * g.Ny + y) * g.M + m) * g.Nz + z;
+    const long long gi = ((long long)(x + g.gx) * g.PY + (y + g.gy)) * g.sY + (long long)m * g.PZ + (z + g.gz);
+    return std::make_pair(q, gi);
+  };
+  std::vector<int> idx((size_t)width * N, -1), val((size_t)width * N, 0), fill(N, 0);
+  for (int64_t p = 0; p < n_pairs; ++p) {  // pairs arrive sorted by {i,j}: ascending-j order is kept per row
+    const auto qi = layout_q(pi[p]);
+    const auto qj = layout_q(pj[p]);
+    const int e = fill[pi[p]]++;
+    idx[(size_t)e * N + qi.first] = (int)qj.second;
+    val[(size_t)e * N + qi.first] = vid[p];
+  }
+  bool iso = true;
+  for (int v = 0; v < n_values; ++v) {
+    const double *J = J9 + 9 * v;
+    if (!(J[1] == 0 && J[2] == 0 && J[3] == 0 && J[5] == 0 && J[6] == 0 && J[7] == 0 && J[0] == J[4] && J[4] == J[8])) iso = false;
+  }
+  void *p;
+  p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
+  c->d_ell_idx = c->d_ell_val = nullptr; c->d_pair_J = nullptr;
+  if (width > 0) {
+    JB_CUDA(c, cudaMalloc(&c->d_ell_idx, idx.size() * sizeof(int)));
+    JB_CUDA(c, cudaMalloc(&c->d_ell_val, val.size() * sizeof(int)));
+    JB_CUDA(c, cudaMalloc(&c->d_pair_J, (size_t)std::max(1, n_values) * 9 * sizeof(double)));
+    JB_CUDA(c, cudaMemcpy(c->d_ell_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    JB_CUDA(c, cudaMemcpy(c->d_ell_val, val.data(), val.size() * sizeof(int), cudaMemcpyHostToDevice));
+    JB_CUDA(c, cudaMemcpy(c->d_pair_J, J9, (size_t)n_values * 9 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  c->ell_width = width; c->n_pair_values = n_values; c->pairs_iso = iso; c->has_pairs = width > 0;
+  return JB_OK;
+}
+
+int jb_set_uniaxial(jb_ctx *c, int32_t power, const double *magnitude, const double *axis) {
+  if (!c) return JB_ERR_INVALID;
+  if (power == 0 || !magnitude) { c->uni_power = 0; c->h_K.clear(); c->h_axis.clear(); c->classes_dirty = true; return JB_OK; }
+  if (!(power == 2 || power == 4 || power == 6) || !axis) JB_FAIL(c, JB_ERR_INVALID, "Unsupported anisotropy power (K1,K2,K3 = 2,4,6)");
+  c->uni_power = power; c->h_K.assign(magnitude, magnitude + c->N); c->h_axis.assign(axis, axis + 3 * (size_t)c->N);
+  c->classes_dirty = true;
+  return JB_OK;
+}
+
+int jb_set_zeeman(jb_ctx *c, const double *dc, const double *ac, const double *omega) {
+  if (!c) return JB_ERR_INVALID;
+  if ((ac == nullptr) != (omega == nullptr)) JB_FAIL(c, JB_ERR_INVALID, "must have a field and a frequency");
+  c->has_zeeman = dc != nullptr;
+  if (dc) c->h_dc.assign(dc, dc + 3 * (size_t)c->N); else c->h_dc.clear();
+  c->has_ac = ac != nullptr;
+  if (ac) {
+    c->h_ac.assign(ac, ac + 3 * (size_t)c->N); c->h_omega.assign(omega, omega + c->N);
+    if (!dc) { c->h_dc.assign(3 * (size_t)c->N, 0.0); c->has_zeeman = true; }
+  } else { c->h_ac.clear(); c->h_omega.clear(); }
+  c->classes_dirty = true;
+  return JB_OK;
+}
+
+int jb_set_applied_field(jb_ctx *c, const double B[3], int32_t enable) {
+  if (!c || (enable && !B)) return JB_ERR_INVALID;
+  c->has_applied = enable != 0;
+  for (int d = 0; d < 3; ++d) c->applied_B[d] = enable ? B[d] : 0.0;
+  return JB_OK;
+}
+
+int jb_import_spins(jb_ctx *c, const double *s_aos, int32_t on_device) {
+  if (!c || !s_aos) return JB_ERR_INVALID;
+  int rc = ensure_ready(c); if (rc) return rc;
+  const double *src = s_aos;
+  if (!on_device) {
+    rc = ensure_aos(c); if (rc) return rc;
+    JB_CUDA(c, cudaMemcpyAsync(c->d_aos, s_aos, (size_t)c->N * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    src = c->d_aos;
+  }
+  double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  JB_CUDA(c, jbk_import(c->g, src, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
+  if (c->d.n_ranks > 1 && c->g.gx > 0) {
+    if (!c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: call jb_halo_connect before jb_import_spins");
+    // neighbours may still be reading my previous ghosts: exchange happens inside an epoch handshake
+    const double *s0[3] = {c->S0[0], c->S0[1], c->S0[2]};
+    double *lo[3] = {c->peer_lo_S0[0], c->peer_lo_S0[1], c->peer_lo_S0[2]};
+    double *hi[3] = {c->peer_hi_S0[0], c->peer_hi_S0[1], c->peer_hi_S0[2]};
+    JB_CUDA(c, jbk_push_x_ghosts(c->g, s0, lo, hi, c->stream)); c->launches++;
+    c->epoch++;
+    JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+  }
+  if (!on_device) JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return JB_OK;
+}
+
+int jb_export_spins(jb_ctx *c, double *s_aos, int32_t on_device) {
+  if (!c || !s_aos) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  JB_CUDA(c, cudaSetDevice(c->device));
+  const double *src[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  if (on_device) {
+    JB_CUDA(c, jbk_export(c->g, src, s_aos, c->stream)); c->launches++;
+    return JB_OK;
+  }
+  int rc = ensure_aos(c); if (rc) return rc;
+  JB_CUDA(c, jbk_export(c->g, src, c->d_aos, c->stream)); c->launches++;
+  JB_CUDA(c, cudaMemcpyAsync(s_aos, c->d_aos, (size_t)c->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return JB_OK;
+}
+
+int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint64_t seed, uint64_t first_step, int32_t gilbert) {
+  if (!c || nsteps < 0 || !(dt > 0.0) || T < 0.0) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  if (c->d.n_ranks > 1 && c->g.gx > 0 && !c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: jb_halo_connect has not been called");
+  const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
+
+  Tiling tl = choose_tiling(c);
+  const bool use_tma = c->opt_kernel == 1 && tl.ok && !c->has_pairs;
+  if (use_tma) { rc = build_tmaps(c, tl); if (rc) return rc; }
+
+  const int max_chunk = c->has_ac ? 2048 : nsteps;
+  for (int done = 0; done < nsteps;) {
+    const int chunk = std::min(nsteps - done, std::max(1, max_chunk));
+    std::vector<double> times;
+    if (c->has_ac) {
+      for (int n = 0; n < chunk; ++n) { const double t0 = time_ps + (done + n) * dt; times.push_back(t0); times.push_back(t0 + dt); }  // cpu_llg_heun.cc:46,103-104
+    } else {
+      times.push_back(time_ps);
+    }
+    rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
+
+    for (int n = 0; n < chunk; ++n) {
+      for (int stage = 0; stage < 2; ++stage) {
+        JbStageParams p{};
+        p.g = c->g;
+        fill_tables(c, p.t, c->has_ac ? 2 * n + stage : 0);
+        for (int k = 0; k < 3; ++k) {
+          p.in[k] = stage == 0 ? c->S0[k] : c->S1[k];
+          p.out[k] = stage == 0 ? c->S1[k] : c->S0[k];
+          p.u[k] = c->U[k];
+          if (multi) {
+            p.out_lo[k] = stage == 0 ? c->peer_lo_S1[k] : c->peer_lo_S0[k];
+            p.out_hi[k] = stage == 0 ? c->peer_hi_S1[k] : c->peer_hi_S0[k];
+          } else if (c->g.per[0] && c->g.gx > 0) {
+            p.out_lo[k] = p.out[k]; p.out_hi[k] = p.out[k];
+          } else {
+            p.out_lo[k] = nullptr; p.out_hi[k] = nullptr;
+          }
+        }
+        p.dt = dt; p.half_dt = 0.5 * dt;
+        p.seed = seed; p.step = first_step + (uint64_t)(done + n);
+        p.thermal = T > 0.0 ? 1 : 0;
+        if (multi) {
+          // ghosts I read were written by the neighbours' previous stage; the boxes I write into were
+          // last read by the neighbours' previous stage: both are covered by their last signal
+          JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++;
+        }
+        record_event(c, 2 * stage);
+        if (c->has_pairs) {
+          JB_CUDA(c, jbk_stage_pairs(p, c->d_ell_idx, c->d_ell_val, c->ell_width, c->d_pair_J, c->pairs_iso ? 1 : 0, stage, c->stream));
+        } else if (use_tma) {
+          p.TY = tl.TY; p.TZ = tl.TZ; p.XC = tl.XC; p.BY = tl.BY; p.BZ = tl.BZ; p.rows = tl.rows; p.slot_elems = tl.slot_elems;
+          p.R = tl.R; p.n_ytiles = tl.n_yt; p.n_ztiles = tl.n_zt; p.n_chunks = tl.n_ch; p.spt = tl.spt;
+          JB_CUDA(c, jbk_stage_tma(p, c->tmap[stage], stage, tl.threads, c->stream));
+        } else {
+          JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
+        }
+        c->launches++;
+        record_event(c, 2 * stage + 1);
+        if (multi) {
+          c->epoch++;
+          JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+        }
+      }
+    }
+    done += chunk;
+  }
+  return JB_OK;
+}
+
+int jb_noise(jb_ctx *c, double dt, double T, uint64_t seed, uint64_t step, int32_t gilbert, int32_t normals_only, double *xi, int32_t on_device) {
+  if (!c || !xi) return JB_ERR_INVALID;
+  int rc = ensure_ready(c); if (rc) return rc;
+  std::vector<double> times{0.0};
+  rc = upload_classes(c, times, dt, T, gilbert, -1); if (rc) return rc;
+  JbTables t; fill_tables(c, t, 0);
+  double *dst = xi;
+  if (!on_device) { rc = ensure_aos(c); if (rc) return rc; dst = c->d_aos; }
+  JB_CUDA(c, jbk_noise(c->g, t, seed, step, normals_only, dst, c->stream)); c->launches++;
+  if (!on_device) {
+    JB_CUDA(c, cudaMemcpyAsync(xi, dst, (size_t)c->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return JB_OK;
+}
+
+int jb_fields(jb_ctx *c, int32_t term, double time_ps, double *h_aos, int32_t on_device) {
+  if (!c || !h_aos || term < 0 || term > JB_TERM_TOTAL) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  std::vector<double> times{time_ps};
+  rc = upload_classes(c, times, 0.0, 0.0, 0, term); if (rc) return rc;
+  JbTables t; fill_tables(c, t, 0);
+  if (!c->has_template) t.nbr_global = nullptr;
+  double *dst = h_aos;
+  if (!on_device) { rc = ensure_aos(c); if (rc) return rc; dst = c->d_aos; }
+  const double *s[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  JB_CUDA(c, jbk_field(c->g, t, s, term, c->has_pairs ? c->d_ell_idx : nullptr, c->d_ell_val, c->ell_width, c->d_pair_J, c->pairs_iso ? 1 : 0, dst, c->stream));
+  c->launches++;
+  if (!on_device) {
+    JB_CUDA(c, cudaMemcpyAsync(h_aos, dst, (size_t)c->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return JB_OK;
+}
+
+int jb_energies(jb_ctx *c, int32_t term, double time_ps, double *e, int32_t on_device, double *total) {
+  if (!c || term < 0 || term >= JB_TERM_TOTAL) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  std::vector<double> times{time_ps};
+  rc = upload_classes(c, times, 0.0, 0.0, 0, term); if (rc) return rc;
+  JbTables t; fill_tables(c, t, 0);
+  if (!c->has_template) t.nbr_global = nullptr;
+  rc = ensure_scratch(c, (size_t)(c->N + 4096) * sizeof(double)); if (rc) return rc;
+  double *partial = c->d_scratch, *tot = c->d_scratch + 2048, *e_dev = nullptr;
+  if (e) e_dev = on_device ? e : c->d_scratch + 4096;
+  const double *s[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  JB_CUDA(c, jbk_energy(c->g, t, s, term, c->has_pairs ? c->d_ell_idx : nullptr, c->d_ell_val, c->ell_width, c->d_pair_J,
+                        c->pairs_iso ? 1 : 0, e_dev, partial, tot, c->stream));
+  c->launches += 2;
+  if (e && !on_device) JB_CUDA(c, cudaMemcpyAsync(e, e_dev, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  double host_total = 0.0;
+  JB_CUDA(c, cudaMemcpyAsync(&host_total, tot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (total) *total = host_total;
+  return JB_OK;
+}
+
+int jb_magnetisation(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin, double *M4) {
+  if (!c || !M4 || n_groups < 1) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  if (c->d_classes == nullptr) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
+  JbTables t; fill_tables(c, t, 0);
+  const size_t need = (size_t)(4096 + 4 * n_groups) * sizeof(double) + (group_of_spin ? (size_t)c->N * sizeof(int) : 0);
+  rc = ensure_scratch(c, need + 64); if (rc) return rc;
+  double *partial = c->d_scratch, *out4 = c->d_scratch + 4096;
+  int *d_groups = nullptr;
+  if (group_of_spin) {
+    d_groups = reinterpret_cast<int *>(c->d_scratch + 4096 + 4 * n_groups + 2);
+    JB_CUDA(c, cudaMemcpyAsync(d_groups, group_of_spin, (size_t)c->N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
+  const double *s[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  JB_CUDA(c, jbk_magnetisation(c->g, t, s, n_groups, d_groups, partial, out4, c->stream));
+  c->launches += 2 * n_groups;
+  JB_CUDA(c, cudaMemcpyAsync(M4, out4, (size_t)4 * n_groups * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return JB_OK;
+}
+
+// ---- halo plumbing ------------------------------------------------------------------------------------
+int jb_halo_export_handle(jb_ctx *c, void *blob_out) {
+  if (!c || !blob_out) return JB_ERR_INVALID;
+  int rc = ensure_ready(c); if (rc) return rc;
+  Blob b{};
+  b.magic = 0x4a42484cu;  // "JBHL"
+  b.pid = (int32_t)getpid(); b.device = c->device; b.rank = c->d.rank;
+  b.nx = c->g.nx; b.PY = c->g.PY; b.PZ = c->g.PZ; b.M = c->g.M; b.gx = c->g.gx;
+  b.base_ptr = (uint64_t)(uintptr_t)c->slab;
+  for (int k = 0; k < 3; ++k) {
+    b.off_S0[k] = (uint64_t)((char *)c->S0[k] - (char *)c->slab);
+    b.off_S1[k] = (uint64_t)((char *)c->S1[k] - (char *)c->slab);
+  }
+  b.off_flags = (uint64_t)((char *)c->flags - (char *)c->slab);
+  JB_CUDA(c, cudaIpcGetMemHandle(&b.ipc, c->slab));
+  memset(blob_out, 0, JB_HALO_HANDLE_BYTES);
+  memcpy(blob_out, &b, sizeof(b));
+  return JB_OK;
+}
+
+static int map_peer(jb_ctx *c, const Blob &b, void **base_out) {
+  if (b.magic != 0x4a42484cu) JB_FAIL(c, JB_ERR_PEER, "bad halo handle");
+  if (b.nx != c->g.nx || b.PY != c->g.PY || b.PZ != c->g.PZ || b.M != c->g.M || b.gx != c->g.gx)
+    JB_FAIL(c, JB_ERR_PEER, "neighbour slab has a different shape (equal slabs are required)");
+  if (b.pid == (int32_t)getpid()) {
+    // same process (several contexts driven by one host thread): plain pointers, peer access if needed
+    if (b.device != c->device) {
+      int can = 0;
+      JB_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, b.device));
+      if (!can) JB_FAIL(c, JB_ERR_PEER, "no peer access between the two devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) JB_CUDA(c, e);
+      cudaGetLastError();
+    }
+    *base_out = (void *)(uintptr_t)b.base_ptr;
+    return JB_OK;
+  }
+  void *p = nullptr;
+  JB_CUDA(c, cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+  *base_out = p;
+  return JB_OK;
+}
+
+int jb_halo_connect(jb_ctx *c, const void *blob_lo, const void *blob_hi) {
+  if (!c) return JB_ERR_INVALID;
+  int rc = ensure_ready(c); if (rc) return rc;
+  JB_CUDA(c, cudaSetDevice(c->device));
+  Blob lo{}, hi{};
+  void *lo_base = nullptr, *hi_base = nullptr;
+  bool lo_ipc = false, hi_ipc = false;
+  if (blob_lo) { memcpy(&lo, blob_lo, sizeof(Blob)); rc = map_peer(c, lo, &lo_base); if (rc) return rc; lo_ipc = lo.pid != (int32_t)getpid(); }
+  if (blob_hi) {
+    memcpy(&hi, blob_hi, sizeof(Blob));
+    if (blob_lo && lo.pid == hi.pid && lo.base_ptr == hi.base_ptr && lo.rank == hi.rank) { hi_base = lo_base; c->same_peer = true; }
+    else { rc = map_peer(c, hi, &hi_base); if (rc) return rc; hi_ipc = hi.pid != (int32_t)getpid(); }
+  }
+  for (int k = 0; k < 3; ++k) {
+    c->peer_lo_S0[k] = lo_base ? (double *)((char *)lo_base + lo.off_S0[k]) : nullptr;
+    c->peer_lo_S1[k] = lo_base ? (double *)((char *)lo_base + lo.off_S1[k]) : nullptr;
+    c->peer_hi_S0[k] = hi_base ? (double *)((char *)hi_base + hi.off_S0[k]) : nullptr;
+    c->peer_hi_S1[k] = hi_base ? (double *)((char *)hi_base + hi.off_S1[k]) : nullptr;
+  }
+  c->peer_lo_flags = lo_base ? (unsigned long long *)((char *)lo_base + lo.off_flags) : nullptr;
+  c->peer_hi_flags = hi_base ? (unsigned long long *)((char *)hi_base + hi.off_flags) : nullptr;
+  c->peer_lo_base = lo_ipc ? lo_base : nullptr;
+  c->peer_hi_base = (hi_ipc && !c->same_peer) ? hi_base : nullptr;
+  c->halo_connected = true;
+  return JB_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------------
+int64_t jb_kernel_launches(const jb_ctx *c) { return c ? c->launches : 0; }
+
+int jb_synchronize(jb_ctx *c) {
+  if (!c) return JB_ERR_INVALID;
+  JB_CUDA(c, cudaSetDevice(c->device));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->flags && c->d.n_ranks > 1) {
+    unsigned long long err = 0;
+    JB_CUDA(c, cudaMemcpy(&err, c->flags + 2, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) JB_FAIL(c, JB_ERR_PEER, "timed out waiting for a halo signal from a neighbour rank");
+  }
+  return JB_OK;
+}
+
+void *jb_stream(jb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int jb_last_step_kernel_ms(jb_ctx *c, double *out2) {
+  if (!c || !out2) return JB_ERR_INVALID;
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  out2[0] = out2[1] = 0.0;
+  for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+    float ms = 0.f;
+    JB_CUDA(c, cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]));
+    out2[c->ev_kind[i] / 2] += ms;
+  }
+  c->ev_used = 0;
+  return JB_OK;
+}
+
+int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
+  if (!c || !key) return JB_ERR_INVALID;
+  const std::string k(key);
+  if (k == "kernel") c->opt_kernel = (int)value;
+  else if (k == "tile_y") c->opt_TY = (int)value;
+  else if (k == "tile_z") c->opt_TZ = (int)value;
+  else if (k == "chunk_x") c->opt_XC = (int)value;
+  else if (k == "ring") c->opt_R = (int)value;
+  else if (k == "threads") c->opt_threads = (int)value;
+  else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; }
+  else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
+  c->tile_BZ_built = -1;
+  c->tmap_valid = false;
+  return JB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// jb_internal.h — context, device-side parameter blocks and launcher prototypes shared by
+// jb_capi.cu (host side of the C ABI) and jb_kernels.cu (sm_100a kernels).
+//
+// Device data layout (DESIGN.md "Data layout in HBM"):
+//   spins are stored SoA in double, one array per component, in a GHOSTED box
+//       index(xp, yp, m, zp) = ((xp * PY + yp) * M + m) * PZ + zp
+//   with xp = x + gx, yp = y + gy, zp = z + gz and ghost depths gx,gy,gz = max |T| of the exchange
+//   template along each axis.  z is the fastest index (lanes of a warp run along z), the motif index
+//   m sits between y and z so that a warp never mixes motif sites.  Ghost cells hold the periodic
+//   image (or zero across an open boundary: a zero spin contributes nothing to J.s), so the field
+//   gather has no boundary branches and a tile + halo is a plain box for TMA.
+//   The reference orders sites ((x*Ny + y)*Nz + z)*M + m (core/lattice.cc:622-657) in AoS N x 3;
+//   jb_import_spins / jb_export_spins translate.
+#ifndef JB_INTERNAL_H
+#define JB_INTERNAL_H
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "jams_b200.h"
+
+#define JB_MAX_MOTIF 32
+#define JB_MAX_CLASSES 255
+#define JB_MAX_RING 8
+
+// ---- geometry of the ghosted box ---------------------------------------------------------------
+struct JbGeom {
+  int nx, Ny, Nz, M;       // interior extent of this slab (cells) and motif size
+  int gx, gy, gz;          // ghost depth
+  int PX, PY, PZ;          // padded extent (PZ rounded up to even: 16-byte rows for TMA)
+  long long sY;            // stride of yp  = M * PZ
+  long long sX;            // stride of xp  = PY * M * PZ
+  long long elems;         // PX * sX
+  int per[3];              // periodic flags
+  int x_begin;             // global x of local x = 0
+  int Nx_global;
+  int n_ranks, rank;
+};
+
+// ---- per-class constants (a class = one distinct tuple of per-site parameters) -----------------
+// The reference keeps all of these as per-site arrays (globals::mus/gyro/alpha, uniaxial magnitude_/axis_,
+// zeeman dc_local_field_); they only ever take one value per material / motif position, so they are
+// de-duplicated on the host and cost 0 B of HBM traffic per spin.
+struct JbClass {
+  double inv_mu;      // 1 / mu_i
+  double mu;          // mu_i (for applied field and magnetisation)
+  double mgyro;       // -gyro_i
+  double alpha;
+  double sigma;       // sqrt(2 kB alpha / (mu gyro dt [1+alpha^2])) * sqrt(T)   (set per jb_step)
+  double Kp;          // K_i * power
+  double K;           // K_i
+  double ax, ay, az;  // anisotropy axis
+  double fx, fy, fz;  // constant field of this stage, meV: dc + ac*cos(omega t) + mu*B_applied
+  int power;          // 0 = no uniaxial term
+  int pad;
+};
+
+// one entry of the exchange template of a motif site, in ghosted-box terms
+struct JbNbr {
+  int delta;   // offset inside a plane: (dy*M + (mj - mi))*row + dz, with row = PZ (global) or BZ (smem tile)
+  int dx;      // plane offset
+  int jidx;    // index into the table of unique tensors
+  int pad;
+  double J;    // scalar coupling (isotropic case), meV
+};
+
+struct JbTables {
+  const JbNbr *nbr_global;     // entries with delta computed for the global ghosted box (row = PZ)
+  const JbNbr *nbr_tile;       // entries with delta computed for the smem tile (row = BZ)
+  const double *Jtab;          // n_unique x 9
+  const JbClass *classes;      // n_classes
+  const unsigned char *site_class;  // per-site class in interior [x][y][m][z] order, or nullptr (motif-uniform)
+  int nbr_begin[JB_MAX_MOTIF + 1];
+  int class_of_motif[JB_MAX_MOTIF];
+  int n_classes;
+  int iso;                     // all tensors are scalar multiples of the identity
+};
+
+// ---- parameter block of the fused stage kernels --------------------------------------------------
+struct JbStageParams {
+  JbGeom g;
+  JbTables t;
+  const double *in[3];   // spins read with neighbours (S0 in stage A, S1 in stage B)
+  double *out[3];        // spins written (S1 in stage A, S0 in stage B), own box
+  double *out_lo[3];     // box that receives the images of my low-x boundary planes (own box, a peer's, or null)
+  double *out_hi[3];     // ... of my high-x boundary planes
+  double *u[3];          // Heun intermediate u = s_n + dt/2 k1 (written in A, read in B), interior only used
+  double dt, half_dt;
+  unsigned long long seed, step;
+  int thermal;
+  // tiling of the TMA kernel
+  int TY, TZ, XC;        // tile extent in y, z and planes marched per CTA
+  int BY, BZ;            // tile + halo extent (BZ even)
+  int rows;              // BY * M
+  int slot_elems;        // rows * BZ rounded up to a multiple of 16 doubles (128 B)
+  int R;                 // ring slots (power of two)
+  int n_ytiles, n_ztiles, n_chunks;
+  int spt;               // in-plane sites per thread
+};
+
+struct jb_ctx {
+  jb_lattice_desc d{};
+  JbGeom g{};
+  int N = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // host copies of the caller's per-site parameters (kept to build classes lazily)
+  std::vector<double> h_mus, h_gyro, h_alpha;
+  std::vector<double> h_K, h_axis; int uni_power = 0;
+  std::vector<double> h_dc, h_ac, h_omega; bool has_zeeman = false, has_ac = false;
+  double applied_B[3] = {0, 0, 0}; bool has_applied = false;
+
+  // exchange template (host)
+  std::vector<int> t_mi, t_mj, t_T; std::vector<double> t_J9;
+  bool has_template = false;
+  // exchange pairs (host -> device ELL), general path
+  bool has_pairs = false;
+  int ell_width = 0;
+  int *d_ell_idx = nullptr;       // width x N (column-major: entry e of site q at e*N + q), ghosted index or -1
+  int *d_ell_val = nullptr;       // value ids
+  double *d_pair_J = nullptr;     // n_values x 9
+  int n_pair_values = 0;
+  bool pairs_iso = false;
+
+  // classes
+  bool classes_dirty = true;
+  std::vector<double> class_sig;            // what the device class table currently encodes
+  std::vector<JbClass> h_classes;          // without sigma / f (filled per launch)
+  std::vector<int> h_class_omega_id;       // index into per-class ac data
+  std::vector<double> h_class_dc, h_class_ac, h_class_omega;  // per class x3 / x3 / x1
+  std::vector<unsigned char> h_site_class; // interior [x][y][m][z] order
+  bool motif_uniform = true;
+  int class_of_motif[JB_MAX_MOTIF] = {0};
+
+  // device tables
+  JbNbr *d_nbr_global = nullptr, *d_nbr_tile = nullptr;
+  double *d_Jtab = nullptr;
+  JbClass *d_classes = nullptr;
+  unsigned char *d_site_class = nullptr;
+  int nbr_begin[JB_MAX_MOTIF + 1] = {0};
+  int n_unique_J = 0;
+  bool iso = true;
+  int tile_BZ_built = 0;  // BZ the tile table was built for
+
+  // state: ghosted SoA arrays
+  double *S0[3] = {nullptr, nullptr, nullptr};
+  double *S1[3] = {nullptr, nullptr, nullptr};
+  double *U[3] = {nullptr, nullptr, nullptr};
+  bool state_allocated = false;
+  double *d_aos = nullptr; size_t d_aos_bytes = 0;     // staging for host <-> device AoS
+  double *d_scratch = nullptr; size_t d_scratch_bytes = 0;  // per-spin scalars / reductions
+  double *h_pinned = nullptr; size_t h_pinned_bytes = 0;
+
+  // TMA descriptors for S0 and S1 components
+  CUtensorMap tmap[2][3];
+  bool tmap_valid = false;
+  int tmap_BY = 0, tmap_BZ = 0;
+
+  // options
+  int opt_kernel = 1;      // 0 = direct global gathers, 1 = TMA ring
+  int opt_TY = 0, opt_TZ = 0, opt_XC = 0, opt_R = 0, opt_threads = 256;  // 0 = heuristic
+  int opt_time_kernels = 0;
+
+  // halo peers
+  double *peer_lo_S0[3] = {nullptr, nullptr, nullptr}, *peer_lo_S1[3] = {nullptr, nullptr, nullptr};
+  double *peer_hi_S0[3] = {nullptr, nullptr, nullptr}, *peer_hi_S1[3] = {nullptr, nullptr, nullptr};
+  unsigned long long *flags = nullptr;           // [0] = written by lo neighbour, [1] = by hi neighbour, [2] = error
+  unsigned long long *peer_lo_flags = nullptr, *peer_hi_flags = nullptr;
+  void *peer_lo_base = nullptr, *peer_hi_base = nullptr;  // mapped IPC allocations
+  bool same_peer = false;
+  void *slab = nullptr; size_t slab_bytes = 0;   // single allocation holding S0,S1 and flags (one IPC handle)
+  unsigned long long epoch = 0;
+  bool halo_connected = false;
+
+  // bookkeeping
+  long long launches = 0;
+  std::vector<cudaEvent_t> ev; size_t ev_used = 0;
+  std::vector<int> ev_kind;
+};
+
+// ---- launchers implemented in jb_kernels.cu (all enqueue on `stream`) -----------------------------
+cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream);
+cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream);
+cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream);
+cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
+cudaError_t jbk_stage_tma(const JbStageParams &p, const CUtensorMap *tmaps3, int stage, int threads, cudaStream_t stream);
+cudaError_t jbk_stage_tma_smem_bytes(const JbStageParams &p, size_t *bytes);
+cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
+                            int iso, int stage, cudaStream_t stream);
+// term field (meV) into AoS N x 3 (device); term as jb_term; pairs path when ell_idx != nullptr
+cudaError_t jbk_field(const JbGeom &g, const JbTables &t, const double *const s[3], int term, const int *ell_idx,
+                      const int *ell_val, int width, const double *pairJ, int pairs_iso, double *h_aos, cudaStream_t stream);
+// per-spin energies (N, reference site order) and block-reduced total into total_out[0]; scratch >= 1024 doubles
+cudaError_t jbk_energy(const JbGeom &g, const JbTables &t, const double *const s[3], int term, const int *ell_idx,
+                       const int *ell_val, int width, const double *pairJ, int pairs_iso, double *e_out, double *scratch,
+                       double *total_out, cudaStream_t stream);
+// sum mu_i s_i and sum mu_i per group -> out4 (n_groups x 4, device); scratch >= 4*n_groups*1024 doubles
+cudaError_t jbk_magnetisation(const JbGeom &g, const JbTables &t, const double *const s[3], int n_groups,
+                              const int *group_of_spin, double *scratch, double *out4, cudaStream_t stream);
+cudaError_t jbk_noise(const JbGeom &g, const JbTables &t, unsigned long long seed, unsigned long long step,
+                      int normals_only, double *xi_aos, cudaStream_t stream);
+cudaError_t jbk_signal(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, unsigned long long epoch, cudaStream_t stream);
+cudaError_t jbk_wait(unsigned long long *flags, int wait_lo, int wait_hi, unsigned long long epoch, cudaStream_t stream);
+
+#endif  // JB_INTERNAL_H

@@ -1,0 +1,815 @@
+// jb_kernels.cu — hand-written sm_100a kernels of the llg-heun + exchange hot path.
+//
+// Replaces, fused into two launches per Heun step (SURVEY.md 2 "CUDA kernel / library-call inventory"):
+//   cusparseSpMV (containers/sparse_matrix.h:366-379), cuda_uniaxial_field_kernel
+//   (hamiltonian/cuda_uniaxial_anisotropy_kernel.cuh:14-26), the Zeeman D2D copy + ac kernel
+//   (hamiltonian/cuda_zeeman.cu:27-41), cudaMemcpy + cublasDaxpy field summation (cuda/cuda_solver.cc:11-26),
+//   curandGenerateNormalDouble + scale (thermostats/cuda_thermostat_classical.cc:47-56), the s -> s_old
+//   snapshot (solvers/cuda_llg_heun.cu:71-75) and cuda_heun_llg_kernelA/B (solvers/cuda_llg_heun_kernel.cuh:8-104).
+// The arithmetic follows the CPU solver (solvers/cpu_llg_heun.cc:45-148), see DESIGN.md.
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jb_internal.h"
+
+namespace {
+
+// =================================================================================================
+// small device helpers
+// =================================================================================================
+__device__ __forceinline__ long long gidx(const JbGeom &g, int xp, int yp, int m, int zp) {
+  return (long long)xp * g.sX + (long long)yp * g.sY + (long long)m * g.PZ + zp;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) counter-based generator, all in registers -------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Box-Muller in fp32 from two 32-bit words; the result is widened to double by the caller.
+// u in (0,1]: (x + 0.5) * 2^-32 is never 0, so the log is finite.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
+  const float u = __fmaf_rn((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  const float v = __fmul_rn((float)b, 2.3283064365386963e-10f);  // [0,1]
+  const float r = sqrtf(__fmul_rn(-2.0f, logf(u)));
+  float s, c;
+  sincospif(__fmul_rn(2.0f, v), &s, &c);
+  n0 = __fmul_rn(r, c);
+  n1 = __fmul_rn(r, s);
+}
+
+// three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
+// (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
+__device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step,
+                                             unsigned long long gsite, double &n0, double &n1, double &n2) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float a, b, c, d;
+  box_muller(r[0], r[1], a, b);
+  box_muller(r[2], r[3], c, d);
+  n0 = (double)a; n1 = (double)b; n2 = (double)c;
+}
+
+__device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
+  return (((unsigned long long)(g.x_begin + x) * g.Ny + y) * g.Nz + z) * g.M + m;
+}
+
+// ---- the per-spin physics ---------------------------------------------------------------------------
+// Adds the local terms to the exchange field, converts to Tesla, adds noise, evaluates the LLG right
+// hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and performs the
+// stage update:
+//   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
+//   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
+// unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
+template <int STAGE, bool THERMAL>
+__device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
+                                         double hx, double hy, double hz,
+                                         double n0, double n1, double n2, double dt, double half_dt,
+                                         double ux, double uy, double uz,
+                                         double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
+  if (c.power != 0) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163)
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    double pw = d;
+    if (c.power >= 4) pw = d * d * d;
+    if (c.power >= 6) pw = pw * d * d;
+    const double f = c.Kp * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  hx += c.fx; hy += c.fy; hz += c.fz;  // Zeeman dc + ac cos(wt) + applied field, meV
+  hx *= c.inv_mu; hy *= c.inv_mu; hz *= c.inv_mu;  // Tesla  (cpu_llg_heun.cc:68-82)
+  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
+
+  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;        // s x h
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;  // s x (s x h)
+  const double rx = c.mgyro * fma(c.alpha, bx_, ax_);
+  const double ry = c.mgyro * fma(c.alpha, by_, ay_);
+  const double rz = c.mgyro * fma(c.alpha, bz_, az_);
+
+  double px, py, pz;
+  if (STAGE == 0) {
+    vx = fma(half_dt, rx, sx); vy = fma(half_dt, ry, sy); vz = fma(half_dt, rz, sz);
+    px = fma(dt, rx, sx); py = fma(dt, ry, sy); pz = fma(dt, rz, sz);
+  } else {
+    px = fma(half_dt, rx, ux); py = fma(half_dt, ry, uy); pz = fma(half_dt, rz, uz);
+  }
+  const double n2_ = px * px + py * py + pz * pz;
+  // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged
+  const double inv = (n2_ > 4.930380657631324e-32) ? 1.0 / sqrt(n2_) : 1.0;
+  ox = px * inv; oy = py * inv; oz = pz * inv;
+}
+
+// store a freshly computed spin into its own cell and into every ghost image of that cell
+// (periodic images in y/z inside this box; x images into the lo/hi boxes, which are this box itself
+// on one GPU and the neighbours' boxes -- peer memory over NVLink -- on several)
+__device__ __forceinline__ void store_with_images(const JbStageParams &p, int x, int y, int m, int z,
+                                                  double vx, double vy, double vz) {
+  const JbGeom &g = p.g;
+  const long long i0 = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  p.out[0][i0] = vx; p.out[1][i0] = vy; p.out[2][i0] = vz;
+  const bool xb = (x < g.gx) | (x >= g.nx - g.gx);
+  const bool yb = g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy));
+  const bool zb = g.per[2] && ((z < g.gz) | (z >= g.Nz - g.gz));
+  if (!(xb | yb | zb)) return;
+
+  int yps[2], zps[2], ny = 1, nz = 1;
+  yps[0] = y + g.gy; zps[0] = z + g.gz;
+  if (yb) yps[ny++] = (y < g.gy) ? y + g.gy + g.Ny : y + g.gy - g.Ny;
+  if (zb) zps[nz++] = (z < g.gz) ? z + g.gz + g.Nz : z + g.gz - g.Nz;
+  // x targets: 0 = own, 1 = lo box, 2 = hi box
+  for (int xt = 0; xt < 3; ++xt) {
+    double *const *arr;
+    int xp;
+    if (xt == 0) { arr = p.out; xp = x + g.gx; }
+    else if (xt == 1) { if (!(x < g.gx) || p.out_lo[0] == nullptr) continue; arr = p.out_lo; xp = x + g.gx + g.nx; }
+    else { if (!(x >= g.nx - g.gx) || p.out_hi[0] == nullptr) continue; arr = p.out_hi; xp = x + g.gx - g.nx; }
+    for (int a = 0; a < ny; ++a) {
+      for (int b = 0; b < nz; ++b) {
+        if (xt == 0 && a == 0 && b == 0) continue;
+        const long long i = gidx(g, xp, yps[a], m, zps[b]);
+        arr[0][i] = vx; arr[1][i] = vy; arr[2][i] = vz;
+      }
+    }
+  }
+}
+
+// interior flat index q (layout order [x][y][m][z]) -> coordinates
+__device__ __forceinline__ void decode_site(const JbGeom &g, long long q, int &x, int &y, int &m, int &z) {
+  z = (int)(q % g.Nz); q /= g.Nz;
+  m = (int)(q % g.M); q /= g.M;
+  y = (int)(q % g.Ny);
+  x = (int)(q / g.Ny);
+}
+
+__device__ __forceinline__ long long ref_site_local(const JbGeom &g, int x, int y, int m, int z) {
+  return (((long long)x * g.Ny + y) * g.Nz + z) * g.M + m;
+}
+
+// =================================================================================================
+// import / export between the reference's AoS site order and the ghosted SoA box
+// =================================================================================================
+__global__ void import_kernel(const JbGeom g, const double *__restrict__ aos, double *__restrict__ dx,
+                              double *__restrict__ dy, double *__restrict__ dz, int fill_x_ghosts) {
+  const long long total = g.elems;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long r = t;
+    const int zp = (int)(r % g.PZ); r /= g.PZ;
+    const int m = (int)(r % g.M); r /= g.M;
+    const int yp = (int)(r % g.PY);
+    const int xp = (int)(r / g.PY);
+    int x = xp - g.gx, y = yp - g.gy, z = zp - g.gz;
+    bool ok = true;
+    if (x < 0 || x >= g.nx) {
+      // multi-rank: the x ghost planes belong to the neighbours (they push into them); do not touch
+      if (!fill_x_ghosts) continue;
+      if (g.per[0]) x = (x + g.nx) % g.nx; else ok = false;
+    }
+    if (y < 0 || y >= g.Ny) {
+      if (g.per[1] && yp < g.Ny + 2 * g.gy) y = (y + g.Ny) % g.Ny; else ok = false;
+    }
+    if (z < 0 || z >= g.Nz) {
+      if (g.per[2] && zp < g.Nz + 2 * g.gz) z = (z + g.Nz) % g.Nz; else ok = false;
+    }
+    double vx = 0.0, vy = 0.0, vz = 0.0;
+    if (ok) {
+      const long long s = ref_site_local(g, x, y, m, z);
+      vx = aos[3 * s]; vy = aos[3 * s + 1]; vz = aos[3 * s + 2];
+    }
+    dx[t] = vx; dy[t] = vy; dz[t] = vz;
+  }
+}
+
+__global__ void export_kernel(const JbGeom g, const double *__restrict__ sx, const double *__restrict__ sy,
+                              const double *__restrict__ sz, double *__restrict__ aos) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    int x, y, m, z;
+    decode_site(g, q, x, y, m, z);
+    const long long i = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const long long s = ref_site_local(g, x, y, m, z);
+    aos[3 * s] = sx[i]; aos[3 * s + 1] = sy[i]; aos[3 * s + 2] = sz[i];
+  }
+}
+
+// copy my gx lowest / highest interior planes (complete planes incl. their y/z ghosts) into the
+// neighbours' x ghost planes
+__global__ void push_x_ghosts_kernel(const JbGeom g, const double *__restrict__ s0, const double *__restrict__ s1,
+                                     const double *__restrict__ s2, double *lo0, double *lo1, double *lo2,
+                                     double *hi0, double *hi1, double *hi2) {
+  const long long plane = g.sX;
+  const long long total = plane * g.gx;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long k = t / plane, r = t % plane;
+    if (lo0) {  // my planes xp = gx + k  ->  lo neighbour's xp = gx + nx + k
+      const long long src = (g.gx + k) * plane + r, dst = (g.gx + g.nx + k) * plane + r;
+      lo0[dst] = s0[src]; lo1[dst] = s1[src]; lo2[dst] = s2[src];
+    }
+    if (hi0) {  // my planes xp = nx + k  ->  hi neighbour's xp = k
+      const long long src = (g.nx + k) * plane + r, dst = k * plane + r;
+      hi0[dst] = s0[src]; hi1[dst] = s1[src]; hi2[dst] = s2[src];
+    }
+  }
+}
+
+// =================================================================================================
+// stage kernel, variant 0: direct gathers from the ghosted box through L1/L2 (one thread per spin)
+// =================================================================================================
+template <int STAGE, bool THERMAL, bool ISO>
+__global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant__ JbStageParams p) {
+  const JbGeom &g = p.g;
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  int x, y, m, z;
+  decode_site(g, q, x, y, m, z);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const double *__restrict__ inx = p.in[0];
+  const double *__restrict__ iny = p.in[1];
+  const double *__restrict__ inz = p.in[2];
+  const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
+
+  double hx = 0.0, hy = 0.0, hz = 0.0;
+  const int nb = p.t.nbr_begin[m], ne = p.t.nbr_begin[m + 1];
+  for (int n = nb; n < ne; ++n) {
+    const JbNbr e = p.t.nbr_global[n];
+    const long long j = ic + (long long)e.dx * g.sX + e.delta;
+    const double jx = inx[j], jy = iny[j], jz = inz[j];
+    if (ISO) {
+      hx = fma(e.J, jx, hx); hy = fma(e.J, jy, hy); hz = fma(e.J, jz, hz);
+    } else {
+      const double *__restrict__ J = p.t.Jtab + 9 * e.jidx;
+      hx += J[0] * jx + J[1] * jy + J[2] * jz;
+      hy += J[3] * jx + J[4] * jy + J[5] * jz;
+      hz += J[6] * jx + J[7] * jy + J[8] * jz;
+    }
+  }
+  const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
+  const JbClass c = p.t.classes[ci];
+  double n0 = 0, n1 = 0, n2 = 0;
+  if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+  double ux = 0, uy = 0, uz = 0;
+  if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
+  double ox, oy, oz, vx, vy, vz;
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
+  store_with_images(p, x, y, m, z, ox, oy, oz);
+}
+
+// =================================================================================================
+// stage kernel, variant 1: TMA-fed shared-memory plane ring, marching along x
+// =================================================================================================
+// A CTA owns a (TY x TZ) column of cells (all M motif sites) and marches over XC consecutive x planes.
+// Each plane-with-halo is a 3-D TMA box {BZ, BY*M, 1} of the ghosted array per spin component, landed
+// in one of R ring slots; an mbarrier per slot carries the transaction count.  At any time the
+// 2*gx+1 planes the stencil needs are resident and R-(2gx+1) further planes are in flight.
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+#define JB_SPT_MAX 4
+
+template <int STAGE, bool THERMAL, bool ISO>
+__global__ void __launch_bounds__(512) stage_tma_kernel(const __grid_constant__ JbStageParams p,
+                                                        const __grid_constant__ CUtensorMap tmx,
+                                                        const __grid_constant__ CUtensorMap tmy,
+                                                        const __grid_constant__ CUtensorMap tmz) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const JbGeom &g = p.g;
+  const int R = p.R, Rm = p.R - 1;
+  const int slot_elems = p.slot_elems;
+  double *ring = reinterpret_cast<double *>(smem_raw);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)R * 3 * slot_elems);
+  JbNbr *s_nbr = reinterpret_cast<JbNbr *>(bars + JB_MAX_RING);
+  const int n_nbr = p.t.nbr_begin[g.M];
+
+  const int tid = threadIdx.x, NT = blockDim.x;
+  int b = blockIdx.x;
+  const int zt = b % p.n_ztiles; b /= p.n_ztiles;
+  const int yt = b % p.n_ytiles;
+  const int chunk = b / p.n_ytiles;
+  const int x0 = chunk * p.XC;
+  const int xc = min(p.XC, g.nx - x0);
+  const int y0 = yt * p.TY, z0 = zt * p.TZ;
+  const int n_planes = xc + 2 * g.gx;
+  const uint32_t box_bytes = (uint32_t)(p.rows * p.BZ * sizeof(double));
+
+  if (tid == 0) {
+    for (int s = 0; s < R; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int n = tid; n < n_nbr; n += NT) s_nbr[n] = p.t.nbr_tile[n];
+  __syncthreads();
+
+  auto issue = [&](int seq) {
+    const int slot = seq & Rm;
+    const uint32_t bar = smem_u32(&bars[slot]);
+    mbar_expect_tx(bar, 3 * box_bytes);
+    double *dst = ring + (size_t)slot * 3 * slot_elems;
+    tma_load_3d(smem_u32(dst), &tmx, z0, y0 * g.M, x0 + seq, bar);
+    tma_load_3d(smem_u32(dst + slot_elems), &tmy, z0, y0 * g.M, x0 + seq, bar);
+    tma_load_3d(smem_u32(dst + 2 * slot_elems), &tmz, z0, y0 * g.M, x0 + seq, bar);
+  };
+  if (tid == 0) {
+    const int pre = min(R, n_planes);
+    for (int seq = 0; seq < pre; ++seq) issue(seq);
+  }
+
+  // per-thread in-plane sites
+  const int Q = p.TY * g.M * p.TZ;
+  int s_off[JB_SPT_MAX];       // centre offset inside a slot component
+  int s_y[JB_SPT_MAX], s_z[JB_SPT_MAX], s_m[JB_SPT_MAX];
+  bool s_ok[JB_SPT_MAX];
+#pragma unroll
+  for (int k = 0; k < JB_SPT_MAX; ++k) {
+    const int q = tid + k * NT;
+    const int tz = q % p.TZ;
+    const int r = q / p.TZ;
+    const int m = r % g.M;
+    const int ty = r / g.M;
+    s_y[k] = y0 + ty; s_z[k] = z0 + tz; s_m[k] = m;
+    s_ok[k] = (k < p.spt) && (q < Q) && (s_y[k] < g.Ny) && (s_z[k] < g.Nz);
+    s_off[k] = ((ty + g.gy) * g.M + m) * p.BZ + tz + g.gz;
+  }
+
+  // wait for the first 2*gx planes; plane 2*gx + ix is waited for inside the loop
+  for (int seq = 0; seq < 2 * g.gx; ++seq) mbar_wait(smem_u32(&bars[seq & Rm]), (uint32_t)((seq / R) & 1));
+
+  for (int ix = 0; ix < xc; ++ix) {
+    {
+      const int seq = ix + 2 * g.gx;
+      mbar_wait(smem_u32(&bars[seq & Rm]), (uint32_t)((seq / R) & 1));
+    }
+    const int x = x0 + ix;
+    const int cseq = ix + g.gx;  // ring sequence number of the centre plane
+#pragma unroll
+    for (int k = 0; k < JB_SPT_MAX; ++k) {
+      if (!s_ok[k]) continue;
+      const int m = s_m[k];
+      const double *cp = ring + (size_t)(cseq & Rm) * 3 * slot_elems + s_off[k];
+      const double sx = cp[0], sy = cp[slot_elems], sz = cp[2 * slot_elems];
+      double hx = 0.0, hy = 0.0, hz = 0.0;
+      const int nb = p.t.nbr_begin[m], ne = p.t.nbr_begin[m + 1];
+#pragma unroll 2
+      for (int n = nb; n < ne; ++n) {
+        const JbNbr e = s_nbr[n];
+        const double *np_ = ring + (size_t)((cseq + e.dx) & Rm) * 3 * slot_elems + s_off[k] + e.delta;
+        const double jx = np_[0], jy = np_[slot_elems], jz = np_[2 * slot_elems];
+        if (ISO) {
+          hx = fma(e.J, jx, hx); hy = fma(e.J, jy, hy); hz = fma(e.J, jz, hz);
+        } else {
+          const double *__restrict__ J = p.t.Jtab + 9 * e.jidx;
+          hx += J[0] * jx + J[1] * jy + J[2] * jz;
+          hy += J[3] * jx + J[4] * jy + J[5] * jz;
+          hz += J[6] * jx + J[7] * jy + J[8] * jz;
+        }
+      }
+      const JbClass c = p.t.classes[p.t.class_of_motif[m]];
+      const int y = s_y[k], z = s_z[k];
+      double n0 = 0, n1 = 0, n2 = 0;
+      if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+      const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+      double ux = 0, uy = 0, uz = 0;
+      if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
+      double ox, oy, oz, vx, vy, vz;
+      llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
+      if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
+      store_with_images(p, x, y, m, z, ox, oy, oz);
+    }
+    __syncthreads();  // every thread is done with the oldest plane (sequence ix): its slot can be refilled
+    if (tid == 0 && ix + R < n_planes) issue(ix + R);
+  }
+}
+
+// =================================================================================================
+// stage kernel, variant 2: general neighbour list (ELL, explicit int32 indices)
+// =================================================================================================
+template <int STAGE, bool THERMAL, bool ISO>
+__global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant__ JbStageParams p,
+                                                          const int *__restrict__ ell_idx, const int *__restrict__ ell_val,
+                                                          int width, const double *__restrict__ pairJ) {
+  const JbGeom &g = p.g;
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  int x, y, m, z;
+  decode_site(g, q, x, y, m, z);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const double *__restrict__ inx = p.in[0];
+  const double *__restrict__ iny = p.in[1];
+  const double *__restrict__ inz = p.in[2];
+  const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
+  double hx = 0.0, hy = 0.0, hz = 0.0;
+  for (int e = 0; e < width; ++e) {
+    const int j = ell_idx[(long long)e * total + q];
+    if (j < 0) continue;
+    const double *__restrict__ J = pairJ + 9 * ell_val[(long long)e * total + q];
+    const double jx = inx[j], jy = iny[j], jz = inz[j];
+    if (ISO) {
+      hx = fma(J[0], jx, hx); hy = fma(J[0], jy, hy); hz = fma(J[0], jz, hz);
+    } else {
+      hx += J[0] * jx + J[1] * jy + J[2] * jz;
+      hy += J[3] * jx + J[4] * jy + J[5] * jz;
+      hz += J[6] * jx + J[7] * jy + J[8] * jz;
+    }
+  }
+  const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
+  const JbClass c = p.t.classes[ci];
+  double n0 = 0, n1 = 0, n2 = 0;
+  if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+  double ux = 0, uy = 0, uz = 0;
+  if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
+  double ox, oy, oz, vx, vy, vz;
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
+  p.out[0][ic] = ox; p.out[1][ic] = oy; p.out[2][ic] = oz;
+}
+
+// =================================================================================================
+// Hamiltonian / Monitor surface: fields, energies, magnetisation, noise
+// =================================================================================================
+__device__ __forceinline__ void exchange_field_site(const JbGeom &g, const JbTables &t, const double *__restrict__ inx,
+                                                    const double *__restrict__ iny, const double *__restrict__ inz,
+                                                    long long q, long long ic, int m, const int *__restrict__ ell_idx,
+                                                    const int *__restrict__ ell_val, int width,
+                                                    const double *__restrict__ pairJ, int pairs_iso, long long total,
+                                                    double &hx, double &hy, double &hz) {
+  hx = hy = hz = 0.0;
+  if (ell_idx) {
+    for (int e = 0; e < width; ++e) {
+      const int j = ell_idx[(long long)e * total + q];
+      if (j < 0) continue;
+      const double *__restrict__ J = pairJ + 9 * ell_val[(long long)e * total + q];
+      const double jx = inx[j], jy = iny[j], jz = inz[j];
+      if (pairs_iso) {
+        hx = fma(J[0], jx, hx); hy = fma(J[0], jy, hy); hz = fma(J[0], jz, hz);
+      } else {
+        hx += J[0] * jx + J[1] * jy + J[2] * jz;
+        hy += J[3] * jx + J[4] * jy + J[5] * jz;
+        hz += J[6] * jx + J[7] * jy + J[8] * jz;
+      }
+    }
+    return;
+  }
+  if (!t.nbr_global) return;
+  for (int n = t.nbr_begin[m]; n < t.nbr_begin[m + 1]; ++n) {
+    const JbNbr e = t.nbr_global[n];
+    const long long j = ic + (long long)e.dx * g.sX + e.delta;
+    const double jx = inx[j], jy = iny[j], jz = inz[j];
+    if (t.iso) {
+      hx = fma(e.J, jx, hx); hy = fma(e.J, jy, hy); hz = fma(e.J, jz, hz);
+    } else {
+      const double *__restrict__ J = t.Jtab + 9 * e.jidx;
+      hx += J[0] * jx + J[1] * jy + J[2] * jz;
+      hy += J[3] * jx + J[4] * jy + J[5] * jz;
+      hz += J[6] * jx + J[7] * jy + J[8] * jz;
+    }
+  }
+}
+
+__device__ __forceinline__ double ipow_even(double d, int power) {  // d^power for power in {2,4,6}
+  double d2 = d * d, r = d2;
+  if (power >= 4) r *= d2;
+  if (power >= 6) r *= d2;
+  return r;
+}
+
+__global__ void field_kernel(const JbGeom g, const JbTables t, const double *__restrict__ inx,
+                             const double *__restrict__ iny, const double *__restrict__ inz, int term,
+                             const int *__restrict__ ell_idx, const int *__restrict__ ell_val, int width,
+                             const double *__restrict__ pairJ, int pairs_iso, double *__restrict__ h_aos) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  int x, y, m, z;
+  decode_site(g, q, x, y, m, z);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  double hx = 0, hy = 0, hz = 0;
+  if (term == JB_TERM_EXCHANGE || term == JB_TERM_TOTAL)
+    exchange_field_site(g, t, inx, iny, inz, q, ic, m, ell_idx, ell_val, width, pairJ, pairs_iso, total, hx, hy, hz);
+  const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
+  const JbClass c = t.classes[ci];
+  if ((term == JB_TERM_UNIAXIAL || term == JB_TERM_TOTAL) && c.power != 0) {
+    const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    double pw = d;
+    if (c.power >= 4) pw = d * d * d;
+    if (c.power >= 6) pw = pw * d * d;
+    const double f = c.Kp * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  if (term == JB_TERM_ZEEMAN || term == JB_TERM_APPLIED || term == JB_TERM_TOTAL) { hx += c.fx; hy += c.fy; hz += c.fz; }
+  const long long s = ref_site_local(g, x, y, m, z);
+  h_aos[3 * s] = hx; h_aos[3 * s + 1] = hy; h_aos[3 * s + 2] = hz;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-level sum with warp shuffles; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double *sm) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) sm[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? sm[threadIdx.x] : 0.0;
+  if (w == 0) v = warp_sum(v);
+  __syncthreads();
+  return v;
+}
+
+// per-spin energy of one term; per-block partial sums to partial[blockIdx.x]
+__global__ void __launch_bounds__(256) energy_kernel(const JbGeom g, const JbTables t, const double *__restrict__ inx,
+                                                    const double *__restrict__ iny, const double *__restrict__ inz, int term,
+                                                    const int *__restrict__ ell_idx, const int *__restrict__ ell_val, int width,
+                                                    const double *__restrict__ pairJ, int pairs_iso,
+                                                    double *__restrict__ e_out, double *__restrict__ partial) {
+  __shared__ double sm[32];
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  double acc = 0.0;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    int x, y, m, z;
+    decode_site(g, q, x, y, m, z);
+    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
+    const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
+    const JbClass c = t.classes[ci];
+    double e = 0.0;
+    if (term == JB_TERM_EXCHANGE) {
+      double hx, hy, hz;
+      exchange_field_site(g, t, inx, iny, inz, q, ic, m, ell_idx, ell_val, width, pairJ, pairs_iso, total, hx, hy, hz);
+      e = -(sx * hx + sy * hy + sz * hz);  // sparse_interaction.cc:79-84
+    } else if (term == JB_TERM_UNIAXIAL) {
+      if (c.power != 0) {
+        const double d = c.ax * sx + c.ay * sy + c.az * sz;
+        e = -c.K * ipow_even(d, c.power);  // uniaxial_anisotropy.cc:126-133
+      }
+    } else {  // ZEEMAN / APPLIED: -s . f   (zeeman.cc:82-87, applied_field.cc:150+)
+      e = -(sx * c.fx + sy * c.fy + sz * c.fz);
+    }
+    if (e_out) e_out[ref_site_local(g, x, y, m, z)] = e;
+    acc += e;
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// deterministic final reduction of n partials (one block), scaled
+__global__ void __launch_bounds__(256) final_sum_kernel(const double *__restrict__ partial, int n, double scale, double *__restrict__ out) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+
+// sum_i mu_i s_i (x,y,z) and sum_i mu_i over the spins of one group; partial[(blockIdx.x*4 + c)]
+__global__ void __launch_bounds__(256) magnetisation_kernel(const JbGeom g, const JbTables t, const double *__restrict__ inx,
+                                                           const double *__restrict__ iny, const double *__restrict__ inz,
+                                                           const int *__restrict__ group_of_spin, int group,
+                                                           double *__restrict__ partial) {
+  __shared__ double sm[32];
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+    int x, y, m, z;
+    decode_site(g, q, x, y, m, z);
+    if (group_of_spin && group_of_spin[ref_site_local(g, x, y, m, z)] != group) continue;
+    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
+    const double mu = t.classes[ci].mu;
+    a0 = fma(mu, inx[ic], a0); a1 = fma(mu, iny[ic], a1); a2 = fma(mu, inz[ic], a2); a3 += mu;
+  }
+  a0 = block_sum(a0, sm); a1 = block_sum(a1, sm); a2 = block_sum(a2, sm); a3 = block_sum(a3, sm);
+  if (threadIdx.x == 0) {
+    partial[4 * blockIdx.x] = a0; partial[4 * blockIdx.x + 1] = a1; partial[4 * blockIdx.x + 2] = a2; partial[4 * blockIdx.x + 3] = a3;
+  }
+}
+
+__global__ void __launch_bounds__(256) final_sum4_kernel(const double *__restrict__ partial, int n, double *__restrict__ out4) {
+  __shared__ double sm[32];
+  for (int c = 0; c < 4; ++c) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[4 * i + c];
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) out4[c] = acc;
+  }
+}
+
+__global__ void noise_kernel(const JbGeom g, const JbTables t, unsigned long long seed, unsigned long long step,
+                             int normals_only, double *__restrict__ xi) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  int x, y, m, z;
+  decode_site(g, q, x, y, m, z);
+  double n0, n1, n2;
+  site_normals(seed, step, global_site(g, x, y, m, z), n0, n1, n2);
+  double sc = 1.0;
+  if (!normals_only) {
+    const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
+    sc = t.classes[ci].sigma;
+  }
+  const long long s = ref_site_local(g, x, y, m, z);
+  xi[3 * s] = sc * n0; xi[3 * s + 1] = sc * n1; xi[3 * s + 2] = sc * n2;
+}
+
+// ---- halo signalling: epoch flags in (peer) device memory -----------------------------------------
+__global__ void signal_kernel(unsigned long long *lo, unsigned long long *hi, unsigned long long epoch) {
+  __threadfence_system();
+  if (lo) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(lo), "l"(epoch) : "memory"); }
+  if (hi) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hi), "l"(epoch) : "memory"); }
+}
+
+__global__ void wait_kernel(unsigned long long *flags, int wait_lo, int wait_hi, unsigned long long epoch) {
+  const long long t0 = clock64();
+  const long long limit = 20000000000LL;  // ~10 s at 2 GHz: a dead peer must not hang the GPU
+  for (int w = 0; w < 2; ++w) {
+    if (!(w == 0 ? wait_lo : wait_hi)) continue;
+    unsigned long long v = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + w) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t0 > limit) { flags[2] = 1ull; return; }
+      __nanosleep(200);
+    }
+  }
+}
+
+template <typename K, typename... Args>
+cudaError_t launch1d(K kernel, long long total, int threads, cudaStream_t stream, Args... args) {
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks < 1) blocks = 1;
+  kernel<<<(unsigned)blocks, threads, 0, stream>>>(args...);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream) {
+  long long blocks = (g.elems + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  import_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, aos, dst[0], dst[1], dst[2], fill_x_ghosts ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  export_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, src[0], src[1], src[2], aos);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream) {
+  if (g.gx == 0) return cudaSuccess;
+  const long long total = g.sX * g.gx;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  push_x_ghosts_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, src[0], src[1], src[2], lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+  return cudaGetLastError();
+}
+
+#define JB_DISPATCH_STAGE(KERNEL, LAUNCH)                                            \
+  do {                                                                               \
+    const bool th = p.thermal != 0, iso = p.t.iso != 0;                              \
+    if (stage == 0) {                                                                \
+      if (th) { if (iso) { auto k = KERNEL<0, true, true>; LAUNCH; } else { auto k = KERNEL<0, true, false>; LAUNCH; } } \
+      else    { if (iso) { auto k = KERNEL<0, false, true>; LAUNCH; } else { auto k = KERNEL<0, false, false>; LAUNCH; } } \
+    } else {                                                                         \
+      if (th) { if (iso) { auto k = KERNEL<1, true, true>; LAUNCH; } else { auto k = KERNEL<1, true, false>; LAUNCH; } } \
+      else    { if (iso) { auto k = KERNEL<1, false, true>; LAUNCH; } else { auto k = KERNEL<1, false, false>; LAUNCH; } } \
+    }                                                                                \
+  } while (0)
+
+cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream) {
+  const long long total = (long long)p.g.nx * p.g.Ny * p.g.Nz * p.g.M;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  JB_DISPATCH_STAGE(stage_direct_kernel, (k<<<blocks, 256, 0, stream>>>(p)));
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_stage_tma_smem_bytes(const JbStageParams &p, size_t *bytes) {
+  const int n_nbr = p.t.nbr_begin[p.g.M];
+  *bytes = (size_t)p.R * 3 * p.slot_elems * sizeof(double) + JB_MAX_RING * sizeof(unsigned long long) +
+           (size_t)n_nbr * sizeof(JbNbr) + 128;
+  return cudaSuccess;
+}
+
+cudaError_t jbk_stage_tma(const JbStageParams &p, const CUtensorMap *tm, int stage, int threads, cudaStream_t stream) {
+  size_t smem = 0;
+  jbk_stage_tma_smem_bytes(p, &smem);
+  const unsigned blocks = (unsigned)(p.n_chunks * p.n_ytiles * p.n_ztiles);
+  cudaError_t err = cudaSuccess;
+  JB_DISPATCH_STAGE(stage_tma_kernel,
+                    (err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                     (err == cudaSuccess ? (void)(k<<<blocks, threads, smem, stream>>>(p, tm[0], tm[1], tm[2])) : (void)0)));
+  if (err != cudaSuccess) return err;
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
+                            int iso_pairs, int stage, cudaStream_t stream) {
+  const long long total = (long long)p.g.nx * p.g.Ny * p.g.Nz * p.g.M;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  JbStageParams q = p;
+  q.t.iso = iso_pairs;
+  {
+    const JbStageParams &p = q;
+    JB_DISPATCH_STAGE(stage_pairs_kernel, (k<<<blocks, 256, 0, stream>>>(p, ell_idx, ell_val, width, pairJ)));
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_field(const JbGeom &g, const JbTables &t, const double *const s[3], int term, const int *ell_idx,
+                      const int *ell_val, int width, const double *pairJ, int pairs_iso, double *h_aos, cudaStream_t stream) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  return launch1d(field_kernel, total, 256, stream, g, t, s[0], s[1], s[2], term, ell_idx, ell_val, width, pairJ, pairs_iso, h_aos);
+}
+
+cudaError_t jbk_energy(const JbGeom &g, const JbTables &t, const double *const s[3], int term, const int *ell_idx,
+                       const int *ell_val, int width, const double *pairJ, int pairs_iso, double *e_out, double *scratch,
+                       double *total_out, cudaStream_t stream) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  energy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, t, s[0], s[1], s[2], term, ell_idx, ell_val, width, pairJ, pairs_iso, e_out, scratch);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  final_sum_kernel<<<1, 256, 0, stream>>>(scratch, (int)blocks, term == JB_TERM_EXCHANGE ? 0.5 : 1.0, total_out);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_magnetisation(const JbGeom &g, const JbTables &t, const double *const s[3], int n_groups,
+                              const int *group_of_spin, double *scratch, double *out4, cudaStream_t stream) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  for (int grp = 0; grp < n_groups; ++grp) {
+    magnetisation_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, t, s[0], s[1], s[2], group_of_spin, grp, scratch);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    final_sum4_kernel<<<1, 256, 0, stream>>>(scratch, (int)blocks, out4 + 4 * grp);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t jbk_noise(const JbGeom &g, const JbTables &t, unsigned long long seed, unsigned long long step,
+                      int normals_only, double *xi_aos, cudaStream_t stream) {
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  return launch1d(noise_kernel, total, 256, stream, g, t, seed, step, normals_only, xi_aos);
+}
+
+cudaError_t jbk_signal(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, unsigned long long epoch, cudaStream_t stream) {
+  signal_kernel<<<1, 1, 0, stream>>>(peer_lo_flag, peer_hi_flag, epoch);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_wait(unsigned long long *flags, int wait_lo, int wait_hi, unsigned long long epoch, cudaStream_t stream) {
+  wait_kernel<<<1, 1, 0, stream>>>(flags, wait_lo, wait_hi, epoch);
+  return cudaGetLastError();
+}

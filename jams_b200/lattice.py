@@ -1,0 +1,355 @@
+"""Host-side lattice and interaction-template construction (pure integer / small float logic).
+
+Mirrors what JAMS does before the solver ever runs, so that the exchange template handed to
+``jb_set_exchange_template`` is exactly the one the reference would build:
+
+* site numbering ``((i*Ny + j)*Nz + k)*M + m``          — reference core/lattice.cc:622-657
+* boundary wrap / open-boundary rejection               — core/lattice.cc:987-1007
+* interaction template processing                        — core/interactions.cc:24-124,292-347
+* point-group expansion                                  — core/lattice.cc:1015-1035,1127-1153
+  (spglib is replaced by an explicit operation list; ``cubic_point_group()`` gives the 48 O_h
+  operations, sufficient for the sc / bcc / fcc cells of the BASELINE configs)
+* neighbour list                                          — core/interactions.cc:349-395
+
+Everything here is setup code; none of it is on the per-step path.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .consts import kBohrMagnetonIU, kGyromagneticRatioIU, kJoule2meV, ENERGY_UNITS
+
+LATTICE_TOLERANCE = 1e-4  # reference helpers/defaults.h:44
+
+
+# ---- tolerant comparisons (reference helpers/maths.h:16-46) -------------------------------------
+def approximately_equal(a: float, b: float, eps: float) -> bool:
+    if abs(a - b) <= eps:
+        return True
+    return abs(a - b) <= max(abs(a), abs(b)) * eps
+
+
+def approximately_zero(a: float, eps: float) -> bool:
+    return abs(a) <= eps
+
+
+def definately_greater_than(a: float, b: float, eps: float) -> bool:
+    return (a - b) > max(abs(a), abs(b)) * eps
+
+
+def definately_less_than(a: float, b: float, eps: float) -> bool:
+    return (b - a) > max(abs(a), abs(b)) * eps
+
+
+def vec_approximately_equal(a, b, eps) -> bool:
+    return all(approximately_equal(float(x), float(y), eps) for x, y in zip(a, b))
+
+
+def cubic_point_group():
+    """48 signed permutation matrices (fractional basis) with zero translations."""
+    rots = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1.0, -1.0), repeat=3):
+            R = np.zeros((3, 3))
+            for r in range(3):
+                R[r, perm[r]] = signs[r]
+            rots.append(R)
+    return np.array(rots), np.zeros((len(rots), 3))
+
+
+def normalise_fractional_coordinate(r, eps=LATTICE_TOLERANCE):
+    """reference core/lattice.cc:48-64"""
+    r = [float(v) for v in r]
+    for n in range(3):
+        if r[n] < 0.0:
+            r[n] = r[n] + 1.0
+        if approximately_equal(r[n], 1.0, eps):
+            r[n] = 0.0
+    return r
+
+
+def lattice_translation_vector(r_frac, tolerance):
+    """reference core/interactions.cc:58-76 (round to nearest even like std::nearbyint)"""
+    T = []
+    for n in range(3):
+        x = float(r_frac[n])
+        nearest = float(np.rint(x))
+        floored = math.floor(x)
+        T.append(nearest if approximately_zero(x - nearest, tolerance) else float(floored))
+    return T
+
+
+@dataclass
+class Material:
+    """reference containers/material.h:16-60 (moment in Bohr magnetons, gyro as a fraction of gamma_e)"""
+    name: str
+    moment: float
+    gyro: float = 1.0
+    alpha: float = 0.01
+    spin: tuple = (0.0, 0.0, 1.0)
+
+
+@dataclass
+class Lattice:
+    """Materials + unit cell + supercell (reference core/lattice.h)."""
+    materials: list
+    cell: np.ndarray                  # 3x3, columns are a, b, c (core/lattice.cc:356-367)
+    motif: list                       # [(material name, (fx, fy, fz)), ...]
+    dims: tuple
+    periodic: tuple = (True, True, True)
+    gilbert_prefactor: bool = False
+    symops: tuple | None = None       # (rotations (n,3,3) fractional, translations (n,3)); None = cubic O_h
+
+    def __post_init__(self):
+        self.cell = np.asarray(self.cell, dtype=np.float64).reshape(3, 3)
+        self.cell_inv = np.linalg.inv(self.cell)
+        self.material_index = {m.name: i for i, m in enumerate(self.materials)}
+        self.motif_material = np.array([self.material_index[name] for name, _ in self.motif], dtype=np.int32)
+        self.motif_frac = np.array([normalise_fractional_coordinate(p) for _, p in self.motif], dtype=np.float64)
+        self.dims = tuple(int(d) for d in self.dims)
+        self.periodic = tuple(bool(p) for p in self.periodic)
+        if self.symops is None:
+            self.symops = cubic_point_group()
+
+    # -- sizes
+    @property
+    def M(self):
+        return len(self.motif)
+
+    @property
+    def num_spins(self):
+        return self.dims[0] * self.dims[1] * self.dims[2] * self.M
+
+    def site_index(self, i, j, k, m):
+        return ((i * self.dims[1] + j) * self.dims[2] + k) * self.M + m
+
+    def apply_boundary_conditions(self, abc):
+        """reference core/lattice.cc:987-1007; returns wrapped cell or None if outside an open boundary"""
+        out = []
+        for l in range(3):
+            if not self.periodic[l] and (abc[l] < 0 or abc[l] >= self.dims[l]):
+                return None
+            out.append((abc[l] + self.dims[l]) % self.dims[l])
+        return out
+
+    # -- per-site arrays in reference site order for the slab x in [x0, x0 + nx)
+    def _tile(self, per_motif, x0=0, nx=None):
+        nx = self.dims[0] if nx is None else nx
+        cells = nx * self.dims[1] * self.dims[2]
+        return np.tile(np.asarray(per_motif), (cells,) + (1,) * (np.ndim(per_motif) - 1))
+
+    def site_material(self, x0=0, nx=None):
+        return self._tile(self.motif_material, x0, nx).astype(np.int32)
+
+    def site_motif(self, x0=0, nx=None):
+        return self._tile(np.arange(self.M, dtype=np.int32), x0, nx)
+
+    def mus(self, x0=0, nx=None):
+        """globals::mus = moment * mu_B (containers/material.h:32)"""
+        return self._tile([self.materials[t].moment * kBohrMagnetonIU for t in self.motif_material], x0, nx)
+
+    def alpha(self, x0=0, nx=None):
+        return self._tile([self.materials[t].alpha for t in self.motif_material], x0, nx)
+
+    def gyro(self, x0=0, nx=None):
+        """globals::gyro (containers/material.h:33, core/lattice.cc:91-97,709-713)"""
+        vals = []
+        for t in self.motif_material:
+            mat = self.materials[t]
+            g = mat.gyro * kGyromagneticRatioIU
+            if self.gilbert_prefactor:
+                g = g / (1.0 + mat.alpha * mat.alpha)
+            vals.append(g)
+        return self._tile(vals, x0, nx)
+
+    def positions(self, x0=0, nx=None):
+        """cartesian site positions in lattice constants (core/lattice.cc:751-756)"""
+        nx = self.dims[0] if nx is None else nx
+        ii, jj, kk, mm = np.meshgrid(np.arange(x0, x0 + nx), np.arange(self.dims[1]), np.arange(self.dims[2]),
+                                     np.arange(self.M), indexing="ij")
+        frac = self.motif_frac[mm.reshape(-1)] + np.stack([ii.reshape(-1), jj.reshape(-1), kk.reshape(-1)], axis=1)
+        return frac @ self.cell.T
+
+    def initial_spins(self, x0=0, nx=None, seed=None):
+        """material.spin normalised (core/lattice.cc:715-733), or seeded uniform-on-sphere spins (seed given)"""
+        nx = self.dims[0] if nx is None else nx
+        n = nx * self.dims[1] * self.dims[2] * self.M
+        if seed is None:
+            per = []
+            for t in self.motif_material:
+                s = np.asarray(self.materials[t].spin, dtype=np.float64)
+                nrm = np.sqrt(s @ s)
+                per.append(s / nrm if nrm > np.finfo(float).eps else s)
+            return self._tile(per, x0, nx)
+        # decomposition-independent: generate the whole lattice stream and slice (test / bench inputs only)
+        rng = np.random.default_rng(seed)
+        v = rng.standard_normal((self.num_spins, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        per_plane = self.dims[1] * self.dims[2] * self.M
+        return np.ascontiguousarray(v[x0 * per_plane:(x0 + nx) * per_plane])
+
+    # -- interaction template (core/interactions.cc:292-347)
+    def point_group_of_motif(self, m):
+        """reference core/lattice.cc:1127-1153"""
+        rots, trans = self.symops
+        out = []
+        p = self.motif_frac[m]
+        for R, t in zip(rots, trans):
+            if not all(approximately_zero(float(x), LATTICE_TOLERANCE) for x in t):
+                continue
+            new_position = normalise_fractional_coordinate(R @ p)
+            if vec_approximately_equal(p, new_position, LATTICE_TOLERANCE):
+                out.append(R)
+        return out
+
+    def expand_interactions(self, interactions, *, energy_units="joules", coordinate_format="cartesian", use_symops=True,
+                            energy_cutoff=0.0, radius_cutoff=100.0, distance_tolerance=LATTICE_TOLERANCE,
+                            interaction_prefactor=1.0):
+        """``interactions``: [(type_i, type_j, (rx,ry,rz), J)], type names (JAMS format) or 1-based motif
+        indices (KKR format); J scalar or 9 numbers in ``energy_units``.  Returns the processed template
+        dict(mi, mj, T, J9) with J9 in meV (scaled as hamiltonian/exchange.cc:165-167)."""
+        unit = ENERGY_UNITS[energy_units]
+        kkr = isinstance(interactions[0][0], (int, np.integer))
+        entries = []
+        for ti, tj, r, J in interactions:
+            r = np.asarray(r, dtype=np.float64)
+            if coordinate_format.lower() == "fractional":
+                r = self.cell @ r
+            J = np.asarray(J, dtype=np.float64)
+            J9 = (float(J) * np.eye(3)).reshape(9) if J.ndim == 0 else J.reshape(9)
+            if kkr:
+                entries.append(dict(mi=int(ti) - 1, mj=int(tj) - 1, r=r, J9=J9))
+            else:
+                entries.append(dict(ti=self.material_index[ti], tj=self.material_index[tj], r=r, J9=J9))
+        if not kkr:  # complete_interaction_unitcell_positions (:98-124)
+            new = []
+            for e in entries:
+                for i in range(self.M):
+                    if self.motif_material[i] != e["ti"]:
+                        continue
+                    q = self.cell_inv @ e["r"] + self.motif_frac[i]
+                    T = lattice_translation_vector(q, distance_tolerance)
+                    offset = q - np.asarray(T)
+                    partner = None
+                    for k in range(self.M):
+                        if vec_approximately_equal(self.motif_frac[k], offset, distance_tolerance):
+                            partner = k
+                            break
+                    if partner is None or self.motif_material[partner] != e["tj"]:
+                        continue
+                    new.append(dict(mi=i, mj=partner, r=e["r"], J9=e["J9"]))
+            entries = new
+        if use_symops:  # apply_symops (:24-37) + generate_symmetric_points (core/lattice.cc:1015-1035)
+            groups = [self.point_group_of_motif(m) for m in range(self.M)]
+            new = []
+            for e in entries:
+                r_frac = self.cell_inv @ e["r"]
+                pts = [e["r"]]
+                for R in groups[e["mi"]]:
+                    r_sym = self.cell @ (R @ r_frac)
+                    if not any(vec_approximately_equal(r_sym, v2, LATTICE_TOLERANCE) for v2 in pts):
+                        pts.append(r_sym)
+                for p in pts:
+                    new.append(dict(mi=e["mi"], mj=e["mj"], r=p, J9=e["J9"]))
+            entries = new
+        if energy_cutoff > 0.0:
+            entries = [e for e in entries if not definately_less_than(float(np.max(np.abs(e["J9"]))), energy_cutoff, np.finfo(float).eps)]
+        if radius_cutoff > 0.0:
+            entries = [e for e in entries if not definately_greater_than(float(np.sqrt(e["r"] @ e["r"])), radius_cutoff, LATTICE_TOLERANCE)]
+        mi, mj, Ts, J9s = [], [], [], []
+        for e in entries:
+            q = self.cell_inv @ e["r"] + self.motif_frac[e["mi"]] - self.motif_frac[e["mj"]]
+            T = lattice_translation_vector(q, distance_tolerance)
+            Jij = interaction_prefactor * unit * e["J9"]
+            # hamiltonian/exchange.cc:166: keep only if max_abs(Jij) > energy_cutoff * unit
+            if not (float(np.max(np.abs(Jij))) > energy_cutoff * unit):
+                continue
+            mi.append(e["mi"]); mj.append(e["mj"]); Ts.append([int(T[0]), int(T[1]), int(T[2])]); J9s.append(Jij)
+        return dict(mi=np.array(mi, np.int32), mj=np.array(mj, np.int32), T=np.array(Ts, np.int32).reshape(-1, 3),
+                    J9=np.array(J9s, np.float64).reshape(-1, 9))
+
+    def neighbour_list(self, template):
+        """neighbour_list_from_interactions (core/interactions.cc:349-395) for a lattice without impurities.
+        Returns (i, j, value_id, values9) in jams::InteractionList order (pairs sorted by {i,j}, values in
+        first-insertion order).  Vectorised over cells; raises on duplicate pairs like the reference."""
+        nx, ny, nz = self.dims
+        M = self.M
+        ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+        ii, jj, kk = ii.reshape(-1), jj.reshape(-1), kk.reshape(-1)
+        all_i, all_j, all_v = [], [], []
+        n_t = len(template["mi"])
+        first_pos = np.full(n_t, -1, np.int64)   # position of each entry's first insertion in generation order
+        for n in range(n_t):
+            d = [ii + template["T"][n, 0], jj + template["T"][n, 1], kk + template["T"][n, 2]]
+            ok = np.ones(ii.shape, bool)
+            for l, size in enumerate(self.dims):
+                if not self.periodic[l]:
+                    ok &= (d[l] >= 0) & (d[l] < size)
+                d[l] = (d[l] + size) % size
+            local = ((ii * ny + jj) * nz + kk) * M + int(template["mi"][n])
+            nbr = ((d[0] * ny + d[1]) * nz + d[2]) * M + int(template["mj"][n])
+            all_i.append(local[ok]); all_j.append(nbr[ok])
+            all_v.append(np.full(int(ok.sum()), n, np.int64))
+            if ok.any():
+                first_pos[n] = int(np.argmax(ok)) * n_t + n   # generation order: cell-major, entry-minor
+        if not all_i:
+            return (np.zeros(0, np.int32),) * 3 + (np.zeros((0, 9)),)
+        I = np.concatenate(all_i); Jn = np.concatenate(all_j); E = np.concatenate(all_v)
+        # unique values in first-insertion order (containers/unordered_vector_set.h:38-45)
+        values, value_of = [], {}
+        for n in sorted((n for n in range(n_t) if first_pos[n] >= 0), key=lambda n: first_pos[n]):
+            key = tuple(template["J9"][n])
+            if key not in value_of:
+                value_of[key] = len(values)
+                values.append(key)
+        vid_of_entry = np.array([value_of.get(tuple(template["J9"][n]), -1) for n in range(n_t)], np.int32)
+        order = np.lexsort((Jn, I))
+        I, Jn, V = I[order], Jn[order], vid_of_entry[E[order]]
+        dup = (I[1:] == I[:-1]) & (Jn[1:] == Jn[:-1])
+        if dup.any():
+            p = int(np.nonzero(dup)[0][0])
+            raise RuntimeError(f"Multiple interactions for sites {int(I[p])} and {int(Jn[p])}")
+        return I.astype(np.int32), Jn.astype(np.int32), V.astype(np.int32), np.array(values, np.float64).reshape(-1, 9)
+
+
+def bloch_domain_wall(positions, spins, width, center, normal=(1, 0, 0), domain=(0, 0, 1)):
+    """InitBlochDomainWall::execute (reference initializer/init_bloch_domain_wall.cc:10-32): rotate every spin
+    by the rotation that takes ``domain`` to m(x) = (0, sech(pi x/w), tanh(pi x/w))."""
+    normal = np.asarray(normal, float); normal = normal / np.linalg.norm(normal)
+    domain = np.asarray(domain, float); domain = domain / np.linalg.norm(domain)
+    out = np.empty_like(spins)
+    x = positions @ normal - center
+    my = 1.0 / np.cosh(np.pi * x / width)
+    mz = np.tanh(np.pi * x / width)
+    for i in range(len(spins)):
+        out[i] = rotation_matrix_between_vectors(domain, np.array([0.0, my[i], mz[i]])) @ spins[i]
+    return out
+
+
+def rotation_matrix_between_vectors(a, b):
+    """reference containers/mat3.h:334-366"""
+    def unit(v):
+        n = np.sqrt(v @ v)
+        return v if n <= np.finfo(float).eps else v / n
+
+    def ssc(v):
+        return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], dtype=np.float64)
+
+    ua, ub = unit(np.asarray(a, float)), unit(np.asarray(b, float))
+    c = float(ua @ ub)
+    if approximately_equal(c, 1.0, 1e-12):
+        return np.eye(3)
+    if approximately_equal(c, -1.0, 1e-12):
+        ortho = np.array([1.0, 0, 0]) if abs(ua[0]) < 0.9 else np.array([0, 1.0, 0])
+        axis = unit(np.cross(ua, ortho))
+        vx = ssc(unit(axis))
+        return np.eye(3) + math.sin(math.pi) * vx + ((1.0 - math.cos(math.pi)) * vx) @ vx
+    v = np.cross(ua, ub)
+    s = np.sqrt(v @ v)
+    vx = ssc(v)
+    k = (1.0 - c) / (s * s)
+    return np.eye(3) + vx + (k * vx) @ vx

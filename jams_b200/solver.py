@@ -1,0 +1,403 @@
+"""Host-side mirror of the JAMS plugin surface for the llg-heun hot path.
+
+Names, argument meaning and error behaviour follow the reference's classes so that code (and tests)
+written against JAMS read the same here:
+
+=========================  ==========================================================================
+reference                   here
+=========================  ==========================================================================
+``Solver``                  :class:`Solver` (core/solver.h:15-90): ``initialize``, ``run``, ``time``,
+                            ``iteration``, ``is_running``, ``register_hamiltonian``,
+                            ``register_monitor``, ``notify_monitors``, ``compute_fields``
+``CUDAHeunLLGSolver``       :class:`B200HeunLLGSolver`, module name ``"llg-heun-b200-gpu"``
+                            (solvers/cuda_llg_heun.cu:21-122; maths of solvers/cpu_llg_heun.cc:45-148)
+``Hamiltonian``             :class:`Hamiltonian` (core/hamiltonian.h:15-78): ``calculate_fields``,
+                            ``calculate_energies``, ``calculate_total_energy``
+``ExchangeHamiltonian``     :class:`ExchangeHamiltonian`      (hamiltonian/exchange.cc:12-172)
+``UniaxialAnisotropy...``   :class:`UniaxialAnisotropyHamiltonian` (hamiltonian/uniaxial_anisotropy.cc:79-115)
+``ZeemanHamiltonian``       :class:`ZeemanHamiltonian`        (hamiltonian/zeeman.cc:12-72)
+``AppliedFieldHamiltonian`` :class:`AppliedFieldHamiltonian`  (hamiltonian/applied_field.cc:84-148, static type)
+``Thermostat``              :class:`LangevinWhiteThermostat`  (thermostats/cuda_thermostat_classical.cc:22-56)
+``MagnetisationMonitor``    :class:`MagnetisationMonitor`     (monitors/magnetisation.cc:21-104)
+``EnergyMonitor``           :class:`EnergyMonitor`            (monitors/energy.cc:16-33)
+=========================  ==========================================================================
+
+All numerical work happens in ``libjams_b200.so`` through :mod:`jams_b200.capi`; this module only holds
+parameters and sequences calls (as the C++ adapter in INTEGRATION.md does inside JAMS itself).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+from .consts import ENERGY_UNITS, kBohrMagnetonIU
+from .lattice import Lattice
+
+
+class Hamiltonian:
+    """core/hamiltonian.h:15-78.  ``energy_units`` defaults to joules (helpers/defaults.h:25)."""
+    term = None
+    name = "hamiltonian"
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        self.settings = dict(settings)
+        self.lattice = lattice
+        unit_name = self.settings.get("unit_name", self.settings.get("energy_units", "joules"))
+        if unit_name not in ENERGY_UNITS:
+            raise RuntimeError(f"energy units: {unit_name} is not known")
+        self.input_energy_unit_conversion = ENERGY_UNITS[unit_name]
+        self.input_energy_unit_name = unit_name
+        self.solver = None
+
+    # push parameters for the slab [x0, x0+nx) into a context
+    def attach(self, ctx: capi.Context, x0: int, nx: int):
+        raise NotImplementedError
+
+    def calculate_fields(self, time: float):
+        """field_ of this term, N x 3, meV (not divided by mu)"""
+        return self.solver.ctx.fields(self.term, time)
+
+    def calculate_energies(self, time: float):
+        return self.solver.ctx.energies(self.term, time, per_spin=True)[0]
+
+    def calculate_total_energy(self, time: float):
+        return self.solver.ctx.energies(self.term, time, per_spin=False)[1]
+
+
+class ExchangeHamiltonian(Hamiltonian):
+    term = capi.TERM_EXCHANGE
+    name = "exchange"
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings, lattice)
+        s = self.settings
+        if "interactions" not in s:
+            raise RuntimeError("'exc_file' or 'interactions' settings are required")
+        self.template = lattice.expand_interactions(
+            s["interactions"], energy_units=self.input_energy_unit_name,
+            coordinate_format=s.get("coordinate_format", "cartesian"), use_symops=s.get("symops", True),
+            energy_cutoff=s.get("energy_cutoff", 0.0), radius_cutoff=s.get("radius_cutoff", 100.0),
+            distance_tolerance=s.get("distance_tolerance", 1e-4), interaction_prefactor=s.get("interaction_prefactor", 1.0))
+        self.use_pairs = bool(s.get("use_neighbour_list", False))
+        self._nbr = None
+
+    def neighbour_list(self):
+        if self._nbr is None:
+            self._nbr = self.lattice.neighbour_list(self.template)
+        return self._nbr
+
+    def attach(self, ctx, x0, nx):
+        if self.use_pairs:
+            i, j, v, vals = self.neighbour_list()
+            ctx.set_exchange_pairs(i, j, v, vals)
+        else:
+            t = self.template
+            ctx.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
+
+
+class UniaxialAnisotropyHamiltonian(Hamiltonian):
+    term = capi.TERM_UNIAXIAL
+    name = "uniaxial"
+    _POWER = {"K1": 2, "K2": 4, "K3": 6}
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings, lattice)
+        s = self.settings
+        for old in ("d2z", "d4z", "d6z", "K1", "K2", "K3"):
+            if old in s:
+                raise RuntimeError("UniaxialHamiltonian: anisotropy should only be specified for a single K1, K2 or K3.")
+        if s["order"] not in self._POWER:
+            raise RuntimeError("Unsupported anisotropy: " + str(s["order"]))
+        self.power = self._POWER[s["order"]]
+        M = lattice.M
+        self.motif_K = np.zeros(M)
+        self.motif_axis = np.zeros((M, 3))
+        for who, axis, energy in s["anisotropies"]:
+            axis = np.asarray(axis, dtype=np.float64)
+            axis = axis / np.sqrt(axis @ axis)  # normalize(), uniaxial_anisotropy.cc:65
+            for m in range(M):
+                if isinstance(who, (int, np.integer)):
+                    if who - 1 < 0 or who - 1 >= M:
+                        raise RuntimeError("uniaxial anisotropy motif position is invalid")
+                    hit = (m == who - 1)
+                else:
+                    if who not in lattice.material_index:
+                        raise RuntimeError("uniaxial anisotropy material is invalid")
+                    hit = lattice.motif_material[m] == lattice.material_index[who]
+                if hit:
+                    self.motif_K[m] = energy * self.input_energy_unit_conversion
+                    self.motif_axis[m] = axis
+
+    def site_arrays(self, x0=0, nx=None):
+        return self.lattice._tile(self.motif_K, x0, nx), self.lattice._tile(self.motif_axis, x0, nx)
+
+    def attach(self, ctx, x0, nx):
+        K, axis = self.site_arrays(x0, nx)
+        ctx.set_uniaxial(self.power, K, axis)
+
+
+class ZeemanHamiltonian(Hamiltonian):
+    term = capi.TERM_ZEEMAN
+    name = "zeeman"
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings, lattice)
+        s = self.settings
+        nmat = len(lattice.materials)
+        self.dc = np.zeros((nmat, 3))
+        if "dc_local_field" in s:
+            if len(s["dc_local_field"]) != nmat:
+                raise RuntimeError("dc_local_field: field must be specified for every material")
+            self.dc = np.asarray(s["dc_local_field"], dtype=np.float64).reshape(nmat, 3)
+        self.has_ac = ("ac_local_field" in s) or ("ac_local_frequency" in s)
+        if self.has_ac:
+            if not ("ac_local_field" in s and "ac_local_frequency" in s):
+                raise RuntimeError("ac_local_field: must have a field and a frequency")
+            if len(s["ac_local_field"]) != nmat or len(s["ac_local_frequency"]) != nmat:
+                raise RuntimeError("ac_local_frequency: must be specified for every material")
+            self.ac = np.asarray(s["ac_local_field"], dtype=np.float64).reshape(nmat, 3)
+            self.freq = 2.0 * np.pi * np.asarray(s["ac_local_frequency"], dtype=np.float64)
+
+    def site_arrays(self, x0=0, nx=None):
+        lat = self.lattice
+        mat = lat.site_material(x0, nx)
+        mus = lat.mus(x0, nx)
+        dc = self.dc[mat] * mus[:, None]                   # zeeman.cc:32-37
+        if self.has_ac:
+            return dc, self.ac[mat] * mus[:, None], self.freq[mat]
+        return dc, None, None
+
+    def attach(self, ctx, x0, nx):
+        ctx.set_zeeman(*self.site_arrays(x0, nx))
+
+
+class AppliedFieldHamiltonian(Hamiltonian):
+    term = capi.TERM_APPLIED
+    name = "applied-field-static"
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings, lattice)
+        kind = str(self.settings.get("type", "static")).lower()
+        if kind != "static":
+            raise RuntimeError("Unknown field pulse type " + kind + " (only 'static' is on the hot path)")
+        self.field = np.asarray(self.settings["field"], dtype=np.float64)
+
+    def attach(self, ctx, x0, nx):
+        ctx.set_applied_field(self.field, True)
+
+
+_HAMILTONIANS = {"exchange": ExchangeHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
+                 "zeeman": ZeemanHamiltonian, "applied-field": AppliedFieldHamiltonian}
+
+
+def create_hamiltonian(settings: dict, lattice: Lattice) -> Hamiltonian:
+    """Hamiltonian::create (core/hamiltonian.cc:80-115): dispatch on lower-cased ``module``"""
+    module = str(settings["module"]).lower()
+    if module not in _HAMILTONIANS:
+        raise RuntimeError("unknown hamiltonian " + module)
+    return _HAMILTONIANS[module](settings, lattice)
+
+
+class LangevinWhiteThermostat:
+    """thermostats/cuda_thermostat_classical.cc:22-56: xi_ij = sigma_i sqrt(T) n_ij (Tesla).  The draws come
+    from Philox4x32-10 keyed by (seed; global site, step) inside the stage kernels; this object only exposes
+    them (Thermostat::device_data) and carries the temperature."""
+
+    def __init__(self, solver, seed=0):
+        self.solver, self.seed, self.temperature = solver, int(seed), 0.0
+
+    def set_temperature(self, T):
+        self.temperature = float(T)
+
+    def noise(self, step=None):
+        s = self.solver
+        return s.ctx.noise(s.step_size, self.temperature, self.seed, s.iteration if step is None else step,
+                           s.lattice.gilbert_prefactor)
+
+
+class Monitor:
+    def __init__(self, settings: dict | None = None):
+        settings = settings or {}
+        self.output_step_freq = int(settings.get("output_steps", 100))  # helpers/defaults.h:28
+        self.records = []
+
+    def is_updating(self, iteration):  # core/monitor.cc
+        return iteration % self.output_step_freq == 0
+
+    def update(self, solver):
+        raise NotImplementedError
+
+
+class MagnetisationMonitor(Monitor):
+    """monitors/magnetisation.cc:21-104, grouping = materials (default) | positions | none"""
+
+    def __init__(self, settings=None, lattice: Lattice | None = None):
+        super().__init__(settings)
+        settings = settings or {}
+        self.grouping = str(settings.get("grouping", "materials")).lower()
+        if self.grouping not in ("none", "materials", "positions"):
+            raise RuntimeError("unknown magnetisation grouping: " + self.grouping)
+        self.normalize = bool(settings.get("normalize", True))
+
+    def groups(self, solver):
+        lat = solver.lattice
+        if self.grouping == "none":
+            return None, 1
+        if self.grouping == "materials":
+            return lat.site_material(solver.x0, solver.nx), len(lat.materials)
+        return lat.site_motif(solver.x0, solver.nx), lat.M
+
+    def update(self, solver):
+        g, ng = self.groups(solver)
+        M4 = solver.reduce_sum(solver.ctx.magnetisation(g, ng))
+        row = [solver.time, solver.temperature]
+        for n in range(ng):
+            mag = M4[n, :3]
+            factor = 1.0 / M4[n, 3] if self.normalize else 1.0 / kBohrMagnetonIU
+            row += [mag[0] * factor, mag[1] * factor, mag[2] * factor, float(np.sqrt(mag @ mag)) * factor]
+        self.records.append(row)
+        return row
+
+
+class EnergyMonitor(Monitor):
+    """monitors/energy.cc:22-33: one total per registered Hamiltonian, meV"""
+
+    def update(self, solver):
+        row = [solver.time] + [float(solver.reduce_sum(np.array([h.calculate_total_energy(solver.time)]))[0])
+                               for h in solver.hamiltonians]
+        self.records.append(row)
+        return row
+
+
+class Solver:
+    """core/solver.h:15-90"""
+    name = "solver"
+
+    def __init__(self):
+        self.iteration = 0
+        self.time = 0.0
+        self.step_size = 1.0
+        self.max_steps = 0
+        self.min_steps = 0
+        self.temperature = 0.0
+        self.hamiltonians = []
+        self.monitors = []
+
+    def is_cuda_solver(self):
+        return False
+
+    def is_running(self):
+        return self.iteration < self.max_steps
+
+    def register_hamiltonian(self, h: Hamiltonian):
+        h.solver = self
+        self.hamiltonians.append(h)
+
+    def register_monitor(self, m: Monitor):
+        self.monitors.append(m)
+
+    def notify_monitors(self):  # core/solver.cc:110-116
+        for m in self.monitors:
+            if m.is_updating(self.iteration):
+                m.update(self)
+
+
+class B200HeunLLGSolver(Solver):
+    """``module = "llg-heun-b200-gpu"``: drop-in alternative to ``llg-heun-gpu``.
+
+    settings keys (solvers/cuda_llg_heun.cu:23-37, solvers/cpu_llg_heun.cc:17-33): ``t_step``, ``t_max``,
+    ``t_min`` in seconds, ``gilbert_prefactor``; extras: ``seed`` (sim.seed), ``device``.
+    One instance drives one x-slab; ``comm`` (see :mod:`jams_b200.distributed`) supplies rank/world and the
+    halo-handle exchange when the lattice is split over several GPUs."""
+    name = "llg-heun-b200-gpu"
+
+    def __init__(self, settings: dict, lattice: Lattice, comm=None):
+        super().__init__()
+        self.lattice = lattice
+        self.comm = comm
+        self.rank = comm.rank if comm else 0
+        self.n_ranks = comm.world_size if comm else 1
+        from .distributed import slab_range
+        self.x0, self.nx = slab_range(lattice.dims[0], self.rank, self.n_ranks)
+        self.ctx = None
+        self._built = False
+        self._physics_dirty = False
+        self.initialize(settings)
+
+    def is_cuda_solver(self):
+        return True
+
+    def initialize(self, settings: dict):
+        self.step_size = float(settings["t_step"]) / 1e-12          # ps
+        t_max = float(settings["t_max"]) / 1e-12
+        t_min = float(settings.get("t_min", 0.0)) / 1e-12
+        self.max_steps = int(t_max / self.step_size)
+        self.min_steps = int(t_min / self.step_size)
+        self.lattice.gilbert_prefactor = bool(settings.get("gilbert_prefactor", self.lattice.gilbert_prefactor))
+        self.seed = int(settings.get("seed", 0))
+        self.thermostat = LangevinWhiteThermostat(self, self.seed)
+        lat = self.lattice
+        self.ctx = capi.Context(lat.dims, lat.M, lat.periodic, x_begin=self.x0, nx_local=self.nx,
+                                rank=self.rank, n_ranks=self.n_ranks, device=int(settings.get("device", -1)))
+        for key, val in settings.get("options", {}).items():
+            self.ctx.set_option(key, val)
+        self._spins0 = lat.initial_spins(self.x0, self.nx)
+
+    # Hamiltonians are registered after the solver exists (core/jams++.cc:274-288): build lazily
+    def _build(self):
+        if self._built:
+            return
+        lat, ctx = self.lattice, self.ctx
+        ctx.set_materials(lat.mus(self.x0, self.nx), lat.gyro(self.x0, self.nx), lat.alpha(self.x0, self.nx))
+        for h in self.hamiltonians:
+            h.attach(ctx, self.x0, self.nx)
+        if self.n_ranks > 1:
+            self.comm.connect_halos(ctx)
+        ctx.import_spins(self._spins0)
+        self._built = True
+
+    def set_spins(self, s_aos):
+        """globals::s = ... (local slab, N x 3)"""
+        self._spins0 = np.ascontiguousarray(s_aos, dtype=np.float64).reshape(-1, 3)
+        if self._built:
+            if self.n_ranks > 1:
+                self.comm.barrier(self.ctx)
+            self.ctx.import_spins(self._spins0)
+
+    def spins(self):
+        self._build()
+        return self.ctx.export_spins()
+
+    def set_temperature(self, T):
+        """physics_module_->temperature() is re-read every step (core/solver.cc:94-97)"""
+        self.temperature = float(T)
+        self.thermostat.set_temperature(T)
+
+    def run(self, nsteps: int = 1):
+        """``nsteps`` Heun steps (one in the reference's main loop, core/jams++.cc:341)"""
+        self._build()
+        self.ctx.step(nsteps, self.step_size, self.time, self.temperature, self.seed, self.iteration,
+                      self.lattice.gilbert_prefactor)
+        self.iteration += nsteps
+        self.time = self.iteration * self.step_size   # cpu_llg_heun.cc:146-147
+
+    def compute_fields(self):
+        """globals::h = sum_k field_k (core/solver.cc:43-57), N x 3 meV"""
+        self._build()
+        return self.ctx.fields(capi.TERM_TOTAL, self.time)
+
+    def notify_monitors(self):
+        self._build()
+        super().notify_monitors()
+
+    def reduce_sum(self, arr):
+        """all-reduce of monitor partial sums over slabs (no-op on one GPU)"""
+        return self.comm.allreduce_sum(arr) if self.comm and self.n_ranks > 1 else arr
+
+
+def create_solver(settings: dict, lattice: Lattice, comm=None) -> Solver:
+    """Solver::create (core/solver.cc:60-77)"""
+    module = str(settings["module"]).lower()
+    if module == "llg-heun-b200-gpu":
+        return B200HeunLLGSolver(settings, lattice, comm)
+    raise RuntimeError("unknown solver " + str(settings["module"]))

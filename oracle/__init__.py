@@ -1,0 +1,352 @@
+"""oracle — CPU checkers for the llg-heun + exchange hot path.  TEST INFRASTRUCTURE ONLY.
+
+Two libraries, one Python face:
+
+* ``libjams_oracle.so``  — self-contained restatement (``oracle/jams_oracle.cpp``), prefix ``jo_``.
+* ``_ref/libjams_ref.so`` — the reference's own header-only code compiled in place from
+  ``/root/reference/src`` (``oracle/ref_wrap.cpp``), prefix ``jref_``.  Exists only if it was built in a
+  container that has the reference tree; it then travels to the GPU box as a prebuilt file.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this package.  Nothing under ``jams_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libjams_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libjams_ref.so")
+
+_c_double_p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_c_int_p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool = True) -> None:
+    """Compile the checkers (``make -C oracle oracle [ref]``)."""
+    targets = ["oracle"] + (["ref"] if ref else [])
+    subprocess.run(["make", "-C", HERE, "--no-print-directory"] + targets, check=True, stdout=subprocess.DEVNULL)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class _Lib:
+    """ctypes face shared by both libraries (function names differ only by prefix)."""
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} missing; run `make -C oracle` (python -c 'import oracle; oracle.build()')")
+        self.path, self.prefix = path, prefix
+        self.lib = C.CDLL(path)
+        p = prefix
+        L = self.lib
+
+        def sig(name, restype, *argtypes):
+            f = getattr(L, p + name)
+            f.restype, f.argtypes = restype, list(argtypes)
+            return f
+
+        self.last_error = sig("last_error", C.c_char_p)
+        self.omp_threads = sig("omp_threads", C.c_int)
+        self.sim_create = sig("sim_create", C.c_void_p, C.c_int, _c_double_p, _c_double_p, _c_double_p)
+        self.sim_destroy = sig("sim_destroy", None, C.c_void_p)
+        self.sim_add_exchange = sig("sim_add_exchange", C.c_int, C.c_void_p, C.c_int64, _c_int_p, _c_int_p, _c_double_p, C.c_int)
+        self.sim_add_uniaxial = sig("sim_add_uniaxial", C.c_int, C.c_void_p, C.c_int, _c_double_p, _c_double_p)
+        self.sim_add_zeeman = sig("sim_add_zeeman", C.c_int, C.c_void_p, _c_double_p, C.c_void_p, C.c_void_p)
+        self.sim_exchange_nnz = sig("sim_exchange_nnz", C.c_int64, C.c_void_p, C.c_int)
+        self.sim_exchange_csr = sig("sim_exchange_csr", None, C.c_void_p, C.c_int, _c_int_p, _c_int_p, _c_double_p)
+        self.sim_set_spins = sig("sim_set_spins", None, C.c_void_p, _c_double_p)
+        self.sim_get_spins = sig("sim_get_spins", None, C.c_void_p, _c_double_p)
+        self.sim_get_h = sig("sim_get_h", None, C.c_void_p, _c_double_p)
+        self.sim_init_solver = sig("sim_init_solver", None, C.c_void_p, C.c_double, C.c_int, C.c_uint64)
+        self.sim_get_sigma = sig("sim_get_sigma", None, C.c_void_p, _c_double_p)
+        self.sim_set_temperature = sig("sim_set_temperature", None, C.c_void_p, C.c_double)
+        self.sim_time = sig("sim_time", C.c_double, C.c_void_p)
+        self.sim_run = sig("sim_run", None, C.c_void_p, C.c_int, C.c_void_p)
+        self.sim_term_fields = sig("sim_term_fields", None, C.c_void_p, C.c_int, C.c_double, _c_double_p)
+        self.sim_term_total_energy = sig("sim_term_total_energy", C.c_double, C.c_void_p, C.c_int, C.c_double)
+        self.rotation_matrix_between_vectors = sig("rotation_matrix_between_vectors", None, _c_double_p, _c_double_p, _c_double_p)
+
+    def error(self) -> str:
+        return (self.last_error() or b"").decode()
+
+
+_libs: dict[str, _Lib] = {}
+
+
+def restatement() -> _Lib:
+    if "jo" not in _libs:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        lib = _Lib(ORACLE_SO, "jo_")
+        L = lib.lib
+        L.jo_expand_template.restype = C.c_int64
+        L.jo_expand_template.argtypes = [
+            _c_double_p, C.c_int, _c_double_p, _c_int_p, C.c_int, C.c_int, C.c_int64, _c_int_p, _c_int_p,
+            _c_double_p, _c_double_p, C.c_int, C.c_int, _c_double_p, _c_double_p, C.c_double, C.c_double, C.c_double,
+            C.c_int64, _c_int_p, _c_int_p, _c_int_p, _c_double_p, _c_double_p]
+        L.jo_neighbour_list.restype = C.c_int64
+        L.jo_neighbour_list.argtypes = [
+            _c_int_p, _c_int_p, C.c_int, _c_int_p, C.c_int64, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p, _c_double_p,
+            C.c_int64, _c_int_p, _c_int_p, _c_int_p, C.c_int, C.POINTER(C.c_int), _c_double_p]
+        L.jo_init_bloch_domain_wall.restype = None
+        L.jo_init_bloch_domain_wall.argtypes = [C.c_int64, _c_double_p, C.c_double, C.c_double, _c_double_p, _c_double_p, _c_double_p]
+        L.jo_magnetisation.restype = None
+        L.jo_magnetisation.argtypes = [C.c_int64, _c_double_p, _c_double_p, C.c_int, _c_int_p, _c_double_p]
+        L.jo_spin_temperature.restype = C.c_double
+        L.jo_spin_temperature.argtypes = [C.c_int64, _c_double_p, _c_double_p]
+        L.jo_sim_term_energies.restype = None
+        L.jo_sim_term_energies.argtypes = [C.c_void_p, C.c_int, C.c_double, _c_double_p]
+        _libs["jo"] = lib
+    return _libs["jo"]
+
+
+def reference() -> _Lib:
+    """The reference-header build (raises FileNotFoundError where it was never built)."""
+    if "jref" not in _libs:
+        lib = _Lib(REF_SO, "jref_")
+        L = lib.lib
+        L.jref_interaction_list.restype = C.c_int
+        L.jref_interaction_list.argtypes = [C.c_int64, _c_int_p, _c_int_p, _c_double_p, _c_int_p, _c_int_p, _c_int_p,
+                                            C.POINTER(C.c_int), _c_double_p]
+        L.jref_unit_vector.restype = None
+        L.jref_unit_vector.argtypes = [_c_double_p, _c_double_p]
+        L.jref_llg_rhs.restype = None
+        L.jref_llg_rhs.argtypes = [_c_double_p, _c_double_p, C.c_double, C.c_double, _c_double_p]
+        L.jref_approximately_equal.restype = C.c_int
+        L.jref_approximately_equal.argtypes = [C.c_double, C.c_double, C.c_double]
+        L.jref_have_pcg.restype = C.c_int
+        _libs["jref"] = lib
+    return _libs["jref"]
+
+
+# ------------------------------------------------------------------------------------------------
+# lattice / interaction construction (restatement only; the reference's versions need spglib)
+# ------------------------------------------------------------------------------------------------
+def cubic_point_group():
+    """The 48 signed permutation matrices of O_h with zero translation.
+
+    Stands in for the spglib operation list the reference uses (core/lattice.cc:942-967) for the
+    cubic cells of the BASELINE configs."""
+    rots = []
+    for perm in itertools.permutations(range(3)):
+        for signs in itertools.product((1.0, -1.0), repeat=3):
+            R = np.zeros((3, 3))
+            for r in range(3):
+                R[r, perm[r]] = signs[r]
+            rots.append(R.reshape(9))
+    rots = np.array(rots)
+    return rots, np.zeros((len(rots), 3))
+
+
+def site_index(dims, M, i, j, k, m):
+    return ((i * dims[1] + j) * dims[2] + k) * M + m
+
+
+def expand_template(cell, motif_frac, motif_type, interactions, *, fmt="jams", frac_coords=False, use_symops=True,
+                    symops=None, energy_cutoff=0.0, radius_cutoff=100.0, distance_tolerance=1e-4):
+    """``post_process_interactions`` (core/interactions.cc:292-347).
+
+    interactions: list of (type_i, type_j, r[3], J) with J a scalar or 9 numbers, energies in input units."""
+    lib = restatement()
+    motif_frac = _f64(motif_frac, (-1, 3))
+    M = motif_frac.shape[0]
+    n_in = len(interactions)
+    ti = _i32([it[0] for it in interactions])
+    tj = _i32([it[1] for it in interactions])
+    r = _f64([it[2] for it in interactions], (n_in, 3))
+    J9 = np.zeros((n_in, 9))
+    for n, it in enumerate(interactions):
+        J = np.asarray(it[3], dtype=np.float64)
+        J9[n] = (J * np.eye(3)).reshape(9) if J.ndim == 0 else J.reshape(9)
+    if symops is None:
+        symops = cubic_point_group()
+    rot, trans = _f64(symops[0], (-1, 9)), _f64(symops[1], (-1, 3))
+    cap = max(64, n_in * M * (len(rot) + 1))
+    mi = np.zeros(cap, np.int32); mj = np.zeros(cap, np.int32); T = np.zeros((cap, 3), np.int32)
+    oJ = np.zeros((cap, 9)); orr = np.zeros((cap, 3))
+    n = lib.lib.jo_expand_template(_f64(cell, (9,)), M, motif_frac, _i32(motif_type), 0 if fmt == "jams" else 1,
+                                   int(frac_coords), n_in, ti, tj, r, J9, int(use_symops), len(rot), rot, trans,
+                                   float(energy_cutoff), float(radius_cutoff), float(distance_tolerance),
+                                   cap, mi, mj, T, oJ, orr)
+    if n < 0:
+        raise RuntimeError(lib.error())
+    return {"mi": mi[:n].copy(), "mj": mj[:n].copy(), "T": T[:n].copy(), "J9": oJ[:n].copy(), "r": orr[:n].copy()}
+
+
+def neighbour_list(dims, periodic, M, site_type, template, entry_type_i=None, entry_type_j=None, motif_type=None):
+    """``neighbour_list_from_interactions`` (core/interactions.cc:349-395) in InteractionList storage order.
+
+    Returns (i, j, value_id, values9)."""
+    lib = restatement()
+    dims = _i32(dims); periodic = _i32([int(bool(p)) for p in periodic])
+    n_t = len(template["mi"])
+    if entry_type_i is None:
+        mt = _i32(motif_type if motif_type is not None else np.zeros(M, np.int32))
+        entry_type_i = mt[template["mi"]]
+        entry_type_j = mt[template["mj"]]
+    N = int(np.prod(dims)) * M
+    cap = N * max(n_t, 1)
+    oi = np.zeros(cap, np.int32); oj = np.zeros(cap, np.int32); ov = np.zeros(cap, np.int32)
+    vals = np.zeros((max(n_t, 1), 9)); nv = C.c_int(0)
+    n = lib.lib.jo_neighbour_list(dims, periodic, M, _i32(site_type), n_t, _i32(template["mi"]), _i32(template["mj"]),
+                                  _i32(template["T"]).reshape(-1), _i32(entry_type_i), _i32(entry_type_j),
+                                  _f64(template["J9"], (-1,)), cap, oi, oj, ov, vals.shape[0], C.byref(nv), vals)
+    if n < 0:
+        raise RuntimeError(lib.error())
+    return oi[:n].copy(), oj[:n].copy(), ov[:n].copy(), vals[:nv.value].copy()
+
+
+def reference_interaction_list(i, j, J9_per_pair):
+    """Feed pairs (in generation order) through the reference's jams::InteractionList."""
+    lib = reference()
+    n = len(i)
+    oi = np.zeros(n, np.int32); oj = np.zeros(n, np.int32); ov = np.zeros(n, np.int32)
+    vals = np.zeros((max(n, 1), 9)); nv = C.c_int(0)
+    rc = lib.lib.jref_interaction_list(n, _i32(i), _i32(j), _f64(J9_per_pair, (-1,)), oi, oj, ov, C.byref(nv), vals)
+    if rc != 0:
+        raise RuntimeError(lib.error())
+    return oi, oj, ov, vals[:nv.value].copy()
+
+
+def init_bloch_domain_wall(positions, s_aos, width, center, normal=(1, 0, 0), domain=(0, 0, 1)):
+    lib = restatement()
+    s = _f64(s_aos, (-1, 3)).copy()
+    lib.lib.jo_init_bloch_domain_wall(len(s), _f64(positions, (-1, 3)), float(width), float(center),
+                                      _f64(normal, (3,)), _f64(domain, (3,)), s)
+    return s
+
+
+def magnetisation(s_aos, mus, group_of_spin=None, n_groups=1):
+    lib = restatement()
+    s = _f64(s_aos, (-1, 3))
+    g = _i32(group_of_spin if group_of_spin is not None else np.zeros(len(s), np.int32))
+    out = np.zeros((n_groups, 4))
+    lib.lib.jo_magnetisation(len(s), s, _f64(mus), n_groups, g, out)
+    return out
+
+
+def spin_temperature(s_aos, h_aos):
+    lib = restatement()
+    s = _f64(s_aos, (-1, 3))
+    return lib.lib.jo_spin_temperature(len(s), s, _f64(h_aos, (-1, 3)))
+
+
+class CpuSim:
+    """llg-heun-cpu on one of the two CPU libraries (``which`` = "restatement" | "reference")."""
+
+    def __init__(self, mus, gyro, alpha, which="restatement"):
+        self.L = restatement() if which == "restatement" else reference()
+        self.which = which
+        self.N = len(mus)
+        self.h = self.L.sim_create(self.N, _f64(mus), _f64(gyro), _f64(alpha))
+        self.n_terms = 0
+
+    def close(self):
+        if self.h:
+            self.L.sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.error())
+
+    def add_exchange(self, i, j, J9_per_pair, check_symmetric=True):
+        self._check(self.L.sim_add_exchange(self.h, len(i), _i32(i), _i32(j), _f64(J9_per_pair, (-1,)), int(check_symmetric)))
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_uniaxial(self, power, magnitude, axis):
+        self._check(self.L.sim_add_uniaxial(self.h, int(power), _f64(magnitude), _f64(axis, (-1,))))
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_zeeman(self, dc, ac=None, omega=None):
+        dc = _f64(dc, (-1,))
+        if ac is not None:
+            ac = _f64(ac, (-1,)); omega = _f64(omega)
+            rc = self.L.sim_add_zeeman(self.h, dc, ac.ctypes.data, omega.ctypes.data)
+        else:
+            rc = self.L.sim_add_zeeman(self.h, dc, None, None)
+        self._check(rc)
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def exchange_csr(self, term=0):
+        nnz = self.L.sim_exchange_nnz(self.h, term)
+        row = np.zeros(3 * self.N + 1, np.int32); col = np.zeros(nnz, np.int32); val = np.zeros(nnz)
+        self.L.sim_exchange_csr(self.h, term, row, col, val)
+        return row, col, val
+
+    def set_spins(self, s):
+        self.L.sim_set_spins(self.h, _f64(s, (-1,)))
+
+    def get_spins(self):
+        s = np.zeros(3 * self.N)
+        self.L.sim_get_spins(self.h, s)
+        return s.reshape(-1, 3)
+
+    def get_h(self):
+        s = np.zeros(3 * self.N)
+        self.L.sim_get_h(self.h, s)
+        return s.reshape(-1, 3)
+
+    def init_solver(self, dt_ps, gilbert_prefactor=False, seed=1):
+        self.L.sim_init_solver(self.h, float(dt_ps), int(gilbert_prefactor), int(seed))
+
+    def sigma(self):
+        s = np.zeros(self.N)
+        self.L.sim_get_sigma(self.h, s)
+        return s
+
+    def set_temperature(self, T):
+        self.L.sim_set_temperature(self.h, float(T))
+
+    def time(self):
+        return self.L.sim_time(self.h)
+
+    def run(self, nsteps=1, normals=None):
+        if normals is not None:
+            normals = _f64(normals, (-1,))
+            assert normals.size == nsteps * 3 * self.N
+            self.L.sim_run(self.h, int(nsteps), normals.ctypes.data)
+        else:
+            self.L.sim_run(self.h, int(nsteps), None)
+
+    def term_fields(self, term, time=0.0):
+        f = np.zeros(3 * self.N)
+        self.L.sim_term_fields(self.h, int(term), float(time), f)
+        return f.reshape(-1, 3)
+
+    def term_total_energy(self, term, time=0.0):
+        return self.L.sim_term_total_energy(self.h, int(term), float(time))
+
+    def term_energies(self, term, time=0.0):
+        assert self.which == "restatement"
+        e = np.zeros(self.N)
+        self.L.lib.jo_sim_term_energies(self.h, int(term), float(time), e)
+        return e

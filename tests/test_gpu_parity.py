@@ -1,0 +1,277 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the C ABI
+(jams_b200.capi -> libjams_b200.so), against the CPU oracle and the committed golden vectors.
+
+Tolerances: neighbour structure / import-export are bit-exact; fp64 fields agree to 1e-13 relative
+(different summation instruction mix: FMA on the GPU, separate mul+add in the reference build);
+T = 0 (and fixed-noise T > 0) trajectories agree to 1e-10 per spin component after N steps, the bar
+BASELINE.json states."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import build_cpu_sim, random_unit_spins
+from golden_cases import CASES
+from jams_b200 import capi, workloads as W
+from jams_b200.lattice import Lattice, Material
+from jams_b200.solver import create_hamiltonian
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TRAJ_TOL = 1e-10
+KERNELS = {"direct": dict(kernel=0), "tma": dict(kernel=1)}
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def make(workload, options=None, pairs=False, **kw):
+    w = dict(workload)
+    if pairs:
+        w["hamiltonians"] = [dict(h, use_neighbour_list=True) if h["module"] == "exchange" else h for h in w["hamiltonians"]]
+    return W.make_solver(w, options=options, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_extension_is_loaded_and_launches_kernels():
+    s = make(W.c3_sc(dims=(8, 8, 8)))
+    s.run(2)
+    s.ctx.synchronize()
+    assert s.ctx.kernel_launches() >= 5   # import + 2 stages x 2 steps
+    assert any("libjams_b200.so" in line for line in open("/proc/self/maps"))
+
+
+@pytest.mark.parametrize("dims,M,periodic", [((5, 4, 7), 1, (True, True, True)), ((3, 6, 9), 2, (False, True, False)),
+                                              ((8, 3, 33), 1, (True, False, True))])
+def test_import_export_round_trip_is_exact(dims, M, periodic):
+    motif = [("A", (0, 0, 0)), ("A", (0.5, 0.5, 0.5))][:M]
+    lat = Lattice([Material("A", 1.0)], np.eye(3), motif, dims, periodic=periodic)
+    w = dict(lattice=lat, hamiltonians=[dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 1e-21)])], temperature=0.0)
+    s = make(w)
+    x = random_unit_spins(lat.num_spins, 5)
+    s.set_spins(x)
+    assert np.array_equal(s.spins(), x)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("pairs", [False, True])
+def test_fields_and_energies_match_reference_golden(name, pairs):
+    case, g = CASES[name], gold(f"case_{name}.npz")
+    w = case["workload"]()
+    s = make(w, pairs=pairs)
+    s.set_spins(g["s0"])
+    total = np.zeros_like(g["s0"])
+    for h in s.hamiltonians:
+        key = h.settings["module"].lower()
+        ref_f = g["field_" + key]
+        f = h.calculate_fields(0.0)
+        scale = max(np.abs(ref_f).max(), 1e-300)
+        assert np.abs(f - ref_f).max() <= 1e-13 * scale, key
+        total += ref_f
+        e = h.calculate_total_energy(0.0)
+        assert abs(e - float(g["energy_" + key])) <= 1e-12 * max(abs(float(g["energy_" + key])), 1.0), key
+    assert np.abs(s.compute_fields() - total).max() <= 1e-13 * np.abs(total).max()
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if "T0" in n])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pairs"])
+def test_T0_trajectories_match_reference_golden(name, variant):
+    case, g = CASES[name], gold(f"case_{name}.npz")
+    w = case["workload"]()
+    s = make(w, options=KERNELS.get(variant), pairs=(variant == "pairs"))
+    assert abs(s.step_size - case["dt_ps"]) < 1e-18
+    s.set_spins(g["s0"])
+    s.run(case["steps"])
+    out = s.spins()
+    assert np.abs(out - g["s_final"]).max() <= TRAJ_TOL
+    assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14
+    assert abs(s.time - float(g["time_final"])) < 1e-15
+
+
+@pytest.mark.parametrize("variant", ["direct", "tma", "pairs"])
+def test_thermal_trajectory_matches_oracle_given_the_same_noise(variant):
+    """T > 0: the reference's CPU (pcg) and GPU (XORWOW) noise streams already differ, so parity is defined on the
+    integrator given identical noise: dump the Philox normals the kernels use and feed them to the oracle."""
+    case = CASES["bcc_T300"]
+    w = case["workload"]()
+    lat = w["lattice"]
+    steps, seed = 25, 1234
+    s = make(w, options=KERNELS.get(variant), pairs=(variant == "pairs"), seed=seed)
+    s0 = random_unit_spins(lat.num_spins, 8)
+    s.set_spins(s0)
+    normals = np.stack([s.ctx.noise(s.step_size, 300.0, seed, n, normals_only=True) for n in range(steps)])
+    sim = build_cpu_sim(w, dt_ps=case["dt_ps"])
+    sim.set_spins(s0)
+    # Thermostat::device_data: xi = sigma sqrt(T) n
+    xi = s.thermostat.noise(step=3)
+    assert np.abs(xi - normals[3] * (sim.sigma() * np.sqrt(300.0))[:, None]).max() <= 1e-12 * np.abs(xi).max()
+    sim.run(steps, normals)
+    s.run(steps)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+
+
+def test_golden_thermal_case_with_reference_normals_is_reproduced_by_oracle_and_statistics_of_gpu_noise():
+    """the Philox/Box-Muller draws are N(0,1): moments, tails, and independence across sites, components, steps"""
+    lat = Lattice([Material("A", 1.0)], np.eye(3), [("A", (0, 0, 0))], (32, 32, 32))
+    w = dict(lattice=lat, hamiltonians=[dict(module="zeeman", dc_local_field=[[0, 0, 1.0]])], temperature=10.0)
+    s = make(w, seed=7)
+    s.spins()
+    a = s.ctx.noise(1e-4, 10.0, 7, 0, normals_only=True)
+    b = s.ctx.noise(1e-4, 10.0, 7, 1, normals_only=True)
+    c = s.ctx.noise(1e-4, 10.0, 8, 0, normals_only=True)
+    n = a.size
+    for x in (a, b, c):
+        assert abs(x.mean()) < 5 / np.sqrt(n)
+        assert abs(x.var() - 1.0) < 5 * np.sqrt(2.0 / n)
+        assert abs((x ** 4).mean() - 3.0) < 5 * np.sqrt(96.0 / n)
+        assert abs((x ** 3).mean()) < 5 * np.sqrt(15.0 / n)
+        assert 3.5 < np.abs(x).max() < 6.7
+    for x, y in ((a[:, 0], a[:, 1]), (a[:, 0], a[:, 2]), (a[:, 1], a[:, 2]), (a.ravel(), b.ravel()), (a.ravel(), c.ravel()),
+                 (a[:-1, 0], a[1:, 0])):
+        assert abs(np.mean(x * y)) < 5 / np.sqrt(x.size)
+    assert not np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.array_equal(a, s.ctx.noise(1e-4, 10.0, 7, 0, normals_only=True))   # counter-based: reproducible
+
+
+def test_magnetisation_and_energy_monitors():
+    case = CASES["two_material_T0"]
+    w = case["workload"]()
+    lat = w["lattice"]
+    s = make(w)
+    x = random_unit_spins(lat.num_spins, 21)
+    s.set_spins(x)
+    from jams_b200.solver import EnergyMonitor, MagnetisationMonitor
+    mon = MagnetisationMonitor(dict(grouping="materials"), lat)
+    row = mon.update(s)
+    ref = oracle.magnetisation(x, lat.mus(), lat.site_material(), 2)
+    for gidx in range(2):
+        want = list(ref[gidx, :3] / ref[gidx, 3]) + [np.linalg.norm(ref[gidx, :3]) / ref[gidx, 3]]
+        assert np.allclose(row[2 + 4 * gidx: 6 + 4 * gidx], want, rtol=0, atol=1e-13)
+    sim = build_cpu_sim(w)
+    sim.set_spins(x)
+    erow = EnergyMonitor().update(s)
+    for k, h in enumerate(s.hamiltonians):
+        want = sim.term_total_energy(sim.terms[h.settings["module"].lower()], 0.0)
+        assert abs(erow[1 + k] - want) <= 1e-12 * max(abs(want), 1.0)
+        e = h.calculate_energies(0.0)
+        assert np.abs(e - sim.term_energies(sim.terms[h.settings["module"].lower()])).max() <= 1e-12 * max(np.abs(e).max(), 1.0)
+
+
+# ---- sizes beyond what the fixtures hold: oracle on the same seeded input, and size-independent properties ----
+@pytest.mark.parametrize("make_w,steps", [(lambda: W.c3_sc(dims=(20, 18, 70)), 30), (lambda: W.c2_bcc_fe(12, temperature=0.0), 30),
+                                          (lambda: W.c4_bcc_long_range(8), 10), (lambda: W.c1_bloch_wall((64, 16, 16)), 50)])
+def test_midsize_trajectories_match_oracle(make_w, steps):
+    w = make_w()
+    lat = w["lattice"]
+    s0 = w["spins"] if w.get("spins") is not None else random_unit_spins(lat.num_spins, 3)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    sim.run(steps)
+    want = sim.get_spins()
+    for variant in ("direct", "tma"):
+        s = make(w, options=KERNELS[variant])
+        s.set_spins(s0)
+        s.run(steps)
+        assert np.abs(s.spins() - want).max() <= TRAJ_TOL, variant
+
+
+@pytest.mark.parametrize("dims", [(7, 9, 37), (33, 5, 130), (4, 70, 3)])
+def test_partial_tiles_and_odd_sizes(dims):
+    w = W.c3_sc(dims=dims)
+    lat = w["lattice"]
+    s0 = random_unit_spins(lat.num_spins, 13)
+    res = {}
+    for variant in ("direct", "tma"):
+        s = make(w, options=KERNELS[variant])
+        s.set_spins(s0)
+        s.run(5)
+        res[variant] = s.spins()
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    sim.run(5)
+    assert np.abs(res["direct"] - sim.get_spins()).max() <= TRAJ_TOL
+    assert np.abs(res["tma"] - res["direct"]).max() <= 1e-14
+
+
+def test_full_size_properties_sc_128():
+    """size-independent properties at a size the oracle cannot run in seconds: norm conservation, the
+    ferromagnetic fixed point, energy dissipation at T = 0, and kernel-variant agreement"""
+    w = W.c3_sc(dims=(128, 128, 128))
+    lat = w["lattice"]
+    s = make(w, options=KERNELS["tma"])
+    s.set_spins(np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1)))
+    s.run(10)
+    assert np.array_equal(s.spins(), np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1)))
+    s0 = lat.initial_spins(seed=2)
+    s.set_spins(s0)
+    e0 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
+    s.run(40)
+    out = s.spins()
+    e1 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
+    assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14
+    assert e1 < e0
+    d = make(w, options=KERNELS["direct"])
+    d.set_spins(s0)
+    d.run(40)
+    assert np.abs(d.spins() - out).max() <= 1e-13
+
+
+@pytest.mark.parametrize("n_slabs", [2, 4])
+@pytest.mark.parametrize("periodic_x", [True, False])
+def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x):
+    """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
+    keyed by the global site so the result must equal the undecomposed run bit for bit"""
+    dims = (16, 6, 10)
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], dims,
+                  periodic=(periodic_x, True, True))
+    hs = dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 1.6e-21)])
+    h = create_hamiltonian(hs, lat)
+    t = h.template
+    s0 = lat.initial_spins(seed=17)
+    dt, T, seed, steps = 1e-4, 50.0, 99, 12
+
+    def new_ctx(rank, n):
+        nx = dims[0] // n
+        c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
+        c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
+        c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
+        return c
+
+    single = new_ctx(0, 1)
+    single.import_spins(s0)
+    single.step(steps, dt, 0.0, T, seed, 0)
+    want = single.export_spins()
+
+    ctxs = [new_ctx(r, n_slabs) for r in range(n_slabs)]
+    blobs = [c.halo_export_handle() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        lo = r - 1 if r > 0 else (n_slabs - 1 if periodic_x else None)
+        hi = r + 1 if r < n_slabs - 1 else (0 if periodic_x else None)
+        c.halo_connect(blobs[lo] if lo is not None else None, blobs[hi] if hi is not None else None)
+    per = lat.num_spins // n_slabs
+    for r, c in enumerate(ctxs):
+        c.import_spins(s0[r * per:(r + 1) * per])
+    for n in range(steps):
+        for c in ctxs:
+            c.step(1, dt, n * dt, T, seed, n)
+    got = np.concatenate([c.export_spins() for c in ctxs])
+    for c in ctxs:
+        c.synchronize()
+    assert np.array_equal(got, want)
+
+
+def test_error_behaviour_mirrors_the_reference():
+    # periodic dimension too short for the template: the reference throws "Multiple interactions"
+    lat = Lattice([Material("A", 1.0)], np.eye(3), [("A", (0, 0, 0))], (16, 2, 8))
+    w = dict(lattice=lat, hamiltonians=[dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 1e-21)])], temperature=0.0)
+    with pytest.raises(capi.JamsB200Error, match="Multiple interactions"):
+        make(w).run(1)
+    c = capi.Context((4, 4, 4))
+    with pytest.raises(capi.JamsB200Error, match="no spins"):
+        c.step(1, 1e-4)
+    with pytest.raises(RuntimeError, match="Unsupported anisotropy"):
+        create_hamiltonian(dict(module="uniaxial", order="K7", anisotropies=[]), lat)
+    with pytest.raises(RuntimeError, match="unknown hamiltonian"):
+        create_hamiltonian(dict(module="dipole-fft"), lat)

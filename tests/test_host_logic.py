@@ -1,0 +1,130 @@
+"""CPU tests of the host side: lattice / template construction bit-exact with the oracle, the C-ABI
+library loads and exports every declared symbol, the product refuses to run without a GPU, and the
+multi-rank plumbing works over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import oracle_exchange_pairs
+from jams_b200 import capi, workloads as W
+from jams_b200.distributed import ring_neighbours, slab_range
+from jams_b200.lattice import Lattice, Material
+from jams_b200.solver import create_hamiltonian
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sorted_template(t):
+    key = np.lexsort((t["T"][:, 2], t["T"][:, 1], t["T"][:, 0], t["mj"], t["mi"]))
+    return t["mi"][key], t["mj"][key], t["T"][key], t["J9"][key]
+
+
+@pytest.mark.parametrize("make", [lambda: W.c1_bloch_wall((16, 4, 4)), lambda: W.c2_bcc_fe(4), lambda: W.c3_sc(dims=(5, 4, 6)),
+                                  lambda: W.c4_bcc_long_range(6)])
+def test_template_and_neighbour_list_bit_exact_with_oracle(make):
+    w = make()
+    lat = w["lattice"]
+    hs = next(h for h in w["hamiltonians"] if h["module"] == "exchange")
+    h = create_hamiltonian(hs, lat)
+    oi, oj, oJ9, otmpl = oracle_exchange_pairs(lat, hs)
+    # processed template: same entries (order of symmetric copies is irrelevant, the list is kept sorted)
+    unit = h.input_energy_unit_conversion
+    a = _sorted_template(h.template)
+    b = _sorted_template(dict(mi=otmpl["mi"], mj=otmpl["mj"], T=otmpl["T"], J9=otmpl["J9"] * unit))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # neighbour list: identical pairs, order, and tensors
+    i, j, v, vals = h.neighbour_list()
+    assert np.array_equal(i, oi) and np.array_equal(j, oj) and np.array_equal(vals[v], oJ9)
+
+
+def test_c4_template_has_112_neighbours_per_site():
+    w = W.c4_bcc_long_range(6)
+    h = create_hamiltonian(w["hamiltonians"][0], w["lattice"])
+    assert np.array_equal(np.bincount(h.template["mi"]), [112, 112])
+
+
+def test_site_arrays_follow_reference_numbering():
+    lat = Lattice([Material("A", 2.0, alpha=0.05), Material("B", 1.0, alpha=0.2)], np.eye(3),
+                  [("A", (0, 0, 0)), ("B", (0.5, 0.5, 0.5))], (3, 4, 5))
+    assert lat.site_index(2, 3, 4, 1) == lat.num_spins - 1
+    assert np.array_equal(lat.site_material()[:4], [0, 1, 0, 1])
+    pos = lat.positions()
+    assert np.allclose(pos[lat.site_index(1, 2, 3, 1)], [1.5, 2.5, 3.5])
+    # slab slices are contiguous ranges of the global order
+    assert np.array_equal(lat.mus(1, 2), lat.mus()[1 * 40:3 * 40])
+    assert np.array_equal(lat.initial_spins(1, 2, seed=3), lat.initial_spins(seed=3)[40:120])
+
+
+def test_slab_and_ring_helpers():
+    assert slab_range(512, 3, 8) == (192, 64)
+    with pytest.raises(RuntimeError):
+        slab_range(10, 0, 4)
+    assert ring_neighbours(0, 4, True) == (3, 1) and ring_neighbours(0, 4, False) == (None, 1)
+    assert ring_neighbours(3, 4, False) == (2, None) and ring_neighbours(0, 1, True) == (None, None)
+    assert ring_neighbours(1, 2, True) == (0, 0)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "jams_b200.h")).read()
+    declared = set(re.findall(r"JB_API [^;]*?\b(jb_\w+)\(", header))
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+    lib = capi.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.jb_abi_version() == 1
+    # the library is the in-tree build, not something on the system path
+    assert os.path.dirname(capi.LIB_PATH) == os.path.join(ROOT, "jams_b200")
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.JamsB200Error, match="no CUDA device"):
+        capi.Context((4, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "jams_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "libjams_oracle" not in text and "libjams_ref" not in text, f
+
+
+GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from jams_b200.distributed import TorchComm, ring_neighbours, slab_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+comm = TorchComm(periodic_x=True)
+blobs = comm.all_gather_bytes(bytes([comm.rank]) * 256)
+assert [b[0] for b in blobs] == [0, 1] and all(len(b) == 256 for b in blobs)
+tot = comm.allreduce_sum(np.array([[1.0 + comm.rank, 2.0, 3.0, 4.0]]))
+assert tot.shape == (1, 4) and tot[0, 0] == 3.0 and tot[0, 3] == 8.0
+assert comm.allreduce_max(float(comm.rank)) == 1.0
+x0, nx = slab_range(8, comm.rank, comm.world_size)
+assert (x0, nx) == (4 * comm.rank, 4)
+assert ring_neighbours(comm.rank, 2, True) == (1 - comm.rank, 1 - comm.rank)
+comm.barrier()
+dist.destroy_process_group()
+print("ok", comm.rank)
+"""
+
+
+def test_gloo_world_size_2_plumbing(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
