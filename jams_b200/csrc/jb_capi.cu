@@ -917,7 +917,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "chunk_x") c->opt_XC = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
   else if (k == "threads") c->opt_threads = (int)value;
-  else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; }
+  else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
   c->tile_BZ_built = -1;
   c->tmap_valid = false;
