@@ -1,0 +1,133 @@
+// b200_llg_heun.cc — see b200_llg_heun.h.  Compiles only inside the JAMS source tree (needs libconfig++ and
+// the `globals` object graph); every citation is relative to src/jams/.
+#include "jams/solvers/b200_llg_heun.h"
+
+#if HAS_CUDA
+
+#include <stdexcept>
+#include <vector>
+
+#include "jams/common.h"
+#include "jams/core/globals.h"
+#include "jams/core/lattice.h"
+#include "jams/core/physics.h"
+#include "jams/core/thermostat.h"
+#include "jams/hamiltonian/exchange.h"
+#include "jams/hamiltonian/uniaxial_anisotropy.h"   // + `friend class B200HeunLLGSolver;`
+#include "jams/hamiltonian/zeeman.h"                // + `friend class B200HeunLLGSolver;`
+#include "jams/helpers/defaults.h"
+#include "jams/interface/config.h"
+
+namespace {
+// the library draws its own Philox noise; this thermostat only carries T so that Solver::update_thermostat()
+// (core/solver.cc:94-97) and monitors that ask thermostat()->temperature() keep working
+class PassThroughThermostat : public Thermostat {
+ public:
+  PassThroughThermostat(double timestep, int num_spins) : Thermostat(0.0, 0.0, timestep, num_spins) {}
+  void update() override {}
+};
+}  // namespace
+
+B200HeunLLGSolver::~B200HeunLLGSolver() { jb_destroy(ctx_); }
+
+void B200HeunLLGSolver::check(int status) const {
+  if (status != JB_OK) throw std::runtime_error(std::string("jams_b200: ") + jb_last_error(ctx_));
+}
+
+void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
+  // same keys and conversions as CUDAHeunLLGSolver::initialize (solvers/cuda_llg_heun.cu:21-37)
+  step_size_ = jams::config_required<double>(settings, "t_step") / 1e-12;
+  auto t_max = jams::config_required<double>(settings, "t_max") / 1e-12;
+  auto t_min = jams::config_optional<double>(settings, "t_min", 0.0) / 1e-12;
+  max_steps_ = static_cast<int>(t_max / step_size_);
+  min_steps_ = static_cast<int>(t_min / step_size_);
+  gilbert_prefactor_ = jams::config_optional<bool>(settings, "gilbert_prefactor", false);  // core/lattice.cc:696-697
+  seed_ = static_cast<std::uint64_t>(jams::config_optional<int>(globals::config->lookup("sim"), "seed", 0));
+  register_thermostat(new PassThroughThermostat(step_size_, globals::num_spins));
+
+  jb_lattice_desc d{};
+  for (int n = 0; n < 3; ++n) {
+    d.dims[n] = globals::lattice->size(n);
+    d.periodic[n] = globals::lattice->is_periodic(n);
+  }
+  d.num_motif = globals::lattice->num_basis_sites();
+  d.x_begin = 0; d.nx_local = d.dims[0]; d.rank = 0; d.n_ranks = 1; d.device = -1;
+  if (jb_create(&ctx_, &d) != JB_OK) throw std::runtime_error(std::string("jams_b200: ") + jb_last_error(nullptr));
+}
+
+void B200HeunLLGSolver::build() {
+  check(jb_set_materials(ctx_, globals::mus.data(), globals::gyro.data(), globals::alpha.data()));
+  for (auto &h : hamiltonians_) {
+    if (auto *ex = dynamic_cast<ExchangeHamiltonian *>(h.get())) {
+      // ExchangeHamiltonian::neighbour_list() (hamiltonian/exchange.h:13): sorted {i,j} pairs + unique tensors.
+      // The library recognises a translation-invariant list and switches to its template kernel.
+      const auto &nbr = ex->neighbour_list();
+      std::vector<int32_t> pi(nbr.size()), pj(nbr.size()), vid(nbr.size());
+      std::vector<double> J9;
+      std::vector<Mat3> uniq;
+      for (int n = 0; n < nbr.size(); ++n) {
+        const auto pr = nbr[n];
+        pi[n] = pr.first[0]; pj[n] = pr.first[1];
+        int v = 0;
+        for (; v < static_cast<int>(uniq.size()); ++v) if (uniq[v] == pr.second) break;
+        if (v == static_cast<int>(uniq.size())) {
+          uniq.push_back(pr.second);
+          for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) J9.push_back(pr.second[a][b]);
+        }
+        vid[n] = v;
+      }
+      check(jb_set_exchange_pairs(ctx_, nbr.size(), pi.data(), pj.data(), vid.data(), static_cast<int32_t>(uniq.size()), J9.data()));
+    } else if (auto *un = dynamic_cast<UniaxialAnisotropyHamiltonian *>(h.get())) {
+      check(jb_set_uniaxial(ctx_, un->power_, un->magnitude_.data(), un->axis_.data()));
+    } else if (auto *ze = dynamic_cast<ZeemanHamiltonian *>(h.get())) {
+      check(jb_set_zeeman(ctx_, ze->dc_local_field_.data(),
+                          ze->has_ac_local_field_ ? ze->ac_local_field_.data() : nullptr,
+                          ze->has_ac_local_field_ ? ze->ac_local_frequency_.data() : nullptr));
+    } else {
+      throw std::runtime_error("llg-heun-b200-gpu: hamiltonian '" + h->name() + "' is not fused; use llg-heun-gpu");
+    }
+  }
+  physics_rewrites_spins_ = (lowercase(jams::config_optional<std::string>(globals::config->lookup("physics"), "module", "empty")) == "pinned_boundaries");
+  import_spins();
+  built_ = true;
+}
+
+void B200HeunLLGSolver::import_spins() {
+  // const device pointer: does not dirty the host copy (containers/synced_memory.h:472-478)
+  check(jb_import_spins(ctx_, const_cast<const jams::MultiArray<double, 2> &>(globals::s).device_data(), /*on_device=*/1));
+  spins_exported_ = true;
+}
+
+void B200HeunLLGSolver::export_spins() {
+  if (spins_exported_) return;
+  check(jb_export_spins(ctx_, globals::s.device_data(), /*on_device=*/1));  // non-const: host copy becomes stale
+  check(jb_synchronize(ctx_));
+  spins_exported_ = true;
+}
+
+void B200HeunLLGSolver::run() {
+  if (!built_) build();
+  if (physics_rewrites_spins_) import_spins();       // physics/pinned_boundaries.cc:34-46 rotates spins between steps
+  update_thermostat();                               // T is re-read every step (core/solver.cc:94-97)
+  check(jb_step(ctx_, 1, step_size_, time_, thermostat_->temperature(), seed_, static_cast<std::uint64_t>(iteration_),
+                gilbert_prefactor_ ? 1 : 0));
+  spins_exported_ = false;
+  iteration_++;
+  time_ = iteration_ * step_size_;                   // solvers/cuda_llg_heun.cu:120-121
+}
+
+void B200HeunLLGSolver::notify_monitors() {
+  if (!built_) build();
+  bool any = false;
+  for (auto &m : monitors_) any = any || m->is_updating(iteration_);
+  if (!any) return;
+  export_spins();                                    // 48 B/spin, only on output steps
+  Solver::notify_monitors();                         // core/solver.cc:110-116
+}
+
+void B200HeunLLGSolver::compute_fields() {
+  if (!built_) build();
+  check(jb_fields(ctx_, JB_TERM_TOTAL, time_, globals::h.device_data(), /*on_device=*/1));
+}
+
+#endif  // HAS_CUDA

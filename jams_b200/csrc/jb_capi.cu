@@ -128,7 +128,7 @@ int allocate_state(jb_ctx *c) {
 }
 
 // ---- exchange template -> device tables -------------------------------------------------------------
-int build_template_tables(jb_ctx *c, int BZ_tile) {
+int build_template_tables(jb_ctx *c) {
   const JbGeom &g = c->g;
   const int n = (int)c->t_mi.size();
   const int M = g.M;
@@ -153,7 +153,9 @@ int build_template_tables(jb_ctx *c, int BZ_tile) {
     for (int d = 0; d < 3; ++d) if (c->t_T[3 * a + d] != c->t_T[3 * b + d]) return c->t_T[3 * a + d] < c->t_T[3 * b + d];
     return c->t_mj[a] < c->t_mj[b];
   });
-  std::vector<JbNbr> glob(n), tile(n);
+  std::vector<JbNbr> glob(n);
+  c->tile_order.assign(order.begin(), order.end());
+  c->tile_jidx = jidx;
   for (int m = 0; m <= M; ++m) c->nbr_begin[m] = 0;
   for (int pos = 0; pos < n; ++pos) {
     const int k = order[pos];
@@ -168,26 +170,22 @@ int build_template_tables(jb_ctx *c, int BZ_tile) {
     e.dx = Tx; e.jidx = jidx[k]; e.J = c->t_J9[9 * k];
     e.delta = (Ty * M + (mj - mi)) * g.PZ + Tz;
     glob[pos] = e;
-    e.delta = (Ty * M + (mj - mi)) * BZ_tile + Tz;
-    tile[pos] = e;
     c->nbr_begin[mi + 1]++;
   }
   for (int m = 0; m < M; ++m) c->nbr_begin[m + 1] += c->nbr_begin[m];
   c->iso = iso;
   c->n_unique_J = (int)uniq.size();
   if (c->d_nbr_global) cudaFree(c->d_nbr_global);
-  if (c->d_nbr_tile) cudaFree(c->d_nbr_tile);
   if (c->d_Jtab) cudaFree(c->d_Jtab);
-  c->d_nbr_global = c->d_nbr_tile = nullptr; c->d_Jtab = nullptr;
+  c->d_nbr_global = nullptr; c->d_Jtab = nullptr;
   if (n > 0) {
     JB_CUDA(c, cudaMalloc(&c->d_nbr_global, n * sizeof(JbNbr)));
-    JB_CUDA(c, cudaMalloc(&c->d_nbr_tile, n * sizeof(JbNbr)));
     JB_CUDA(c, cudaMalloc(&c->d_Jtab, uniq.size() * 9 * sizeof(double)));
     JB_CUDA(c, cudaMemcpy(c->d_nbr_global, glob.data(), n * sizeof(JbNbr), cudaMemcpyHostToDevice));
-    JB_CUDA(c, cudaMemcpy(c->d_nbr_tile, tile.data(), n * sizeof(JbNbr), cudaMemcpyHostToDevice));
     JB_CUDA(c, cudaMemcpy(c->d_Jtab, uniq.data(), uniq.size() * 9 * sizeof(double), cudaMemcpyHostToDevice));
   }
-  c->tile_BZ_built = BZ_tile;
+  c->tables_built = true;
+  c->tiling_valid = false;
   return JB_OK;
 }
 
@@ -282,6 +280,7 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
       tab[s * nc + k] = cl;
     }
   }
+  c->h_class_tab = tab;
   const size_t bytes = tab.size() * sizeof(JbClass);
   static_assert(sizeof(JbClass) % 8 == 0, "class size");
   if (c->h_pinned_bytes < bytes) {
@@ -302,7 +301,7 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
 }
 
 void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
-  t.nbr_global = c->d_nbr_global; t.nbr_tile = c->d_nbr_tile; t.Jtab = c->d_Jtab;
+  t.nbr_global = c->d_nbr_global; t.Jtab = c->d_Jtab;
   t.classes = c->d_classes + (size_t)class_table_index * c->h_classes.size();
   t.site_class = c->d_site_class;
   for (int m = 0; m <= JB_MAX_MOTIF; ++m) t.nbr_begin[m] = (m <= c->g.M && c->has_template) ? c->nbr_begin[m] : 0;
@@ -311,61 +310,127 @@ void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
   t.iso = c->iso ? 1 : 0;
 }
 
-// ---- tiling of the TMA kernel -------------------------------------------------------------------------
+// ---- tiling of the persistent TMA tile kernel ----------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct Tiling { int TY, TZ, XC, BY, BZ, rows, slot_elems, R, n_yt, n_zt, n_ch, spt, threads; bool ok; };
-
-Tiling choose_tiling(jb_ctx *c) {
+// shape of the tiles; grid size and x-chunking are decided per kernel variant in tile_launch_shape()
+void choose_tiling(jb_ctx *c) {
+  if (c->tiling_valid) return;
   const JbGeom &g = c->g;
-  Tiling t{};
-  t.ok = false;
-  if (!c->has_template || !c->motif_uniform || g.gx > 3) return t;
-  t.threads = c->opt_threads;
-  t.R = c->opt_R ? c->opt_R : ((2 * g.gx + 2) <= 4 ? 4 : 8);
-  if (t.R < 2 * g.gx + 2 || t.R > JB_MAX_RING || (t.R & (t.R - 1))) return t;
+  jb_ctx::Tiling t;
+  c->tiling = t;
+  c->tiling_valid = true;
+  c->tmap_valid = false;
+  const int n_nbr = (int)c->t_mi.size();
+  if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR ||
+      (int)c->h_classes.size() > JB_TILE_MAX_CLASSES)
+    return;
   int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
-  if (TZ > g.Nz) TZ = g.Nz;
-  int TY = c->opt_TY;
-  if (!TY) {
-    // aim for ~512-1024 in-plane sites per CTA while keeping two CTAs per SM in shared memory
-    TY = std::max(1, 512 / (TZ * g.M));
-    if (TY > g.Ny) TY = g.Ny;
-  }
+  TZ = std::max(1, std::min(TZ, g.Nz));
+  if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
+  int SPT = c->opt_SPT ? c->opt_SPT : 2;
+  int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / TZ);   // ~256 threads per CTA
+  TY = std::max(1, std::min(TY, g.Ny));
+  if (TY > 64) TY = 64;
+  while (SPT > 1 && (SPT > TY)) SPT /= 2;
+  if (!(SPT == 1 || SPT == 2 || SPT == 4)) return;
+  t.R = c->opt_R ? c->opt_R : 2 * g.gx + 3;
+  t.RU = c->opt_RU ? c->opt_RU : 3;
+  if (t.R < 2 * g.gx + 2 || t.R > 8 || t.RU < 2 || t.RU > 8) return;
   for (;;) {
-    t.TY = TY; t.TZ = TZ;
+    t.TY = TY; t.TZ = TZ; t.SPT = SPT;
     t.BY = TY + 2 * g.gy; t.BZ = TZ + 2 * g.gz; if (t.BZ & 1) t.BZ++;
-    t.rows = t.BY * g.M;
-    t.slot_elems = (t.rows * t.BZ + 15) / 16 * 16;
-    const size_t smem = (size_t)t.R * 3 * t.slot_elems * 8;
-    if (smem <= 100 * 1024 || TY == 1 || c->opt_TY) break;
-    TY = std::max(1, TY / 2);
+    // the u box spans the same z range as the spin box (incl. the z halo) so that its inner start coordinate is
+    // z0, a multiple of the (even) tile width: TMA faults on boxes whose first element is not 16-byte aligned
+    t.UZ = t.BZ;
+    t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
+    t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
+    t.threads = TZ * ((TY + SPT - 1) / SPT);
+    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 256 + (size_t)n_nbr * sizeof(JbTileNbr);
+    t.u_tma = c->opt_u_tma ? 1 : 0;
+    t.smem[1] = t.smem[0] + (t.u_tma ? (size_t)t.RU * 3 * t.slotU * 8 : 0);
+    // wanted: two CTAs per SM in stage B
+    if ((t.smem[1] <= 110 * 1024 && t.threads <= 512) || c->opt_TY || TY <= SPT) break;
+    TY = std::max(SPT, TY / 2);
   }
-  if (t.rows > 256 || t.BZ > 256) return t;
-  if ((size_t)t.R * 3 * t.slot_elems * 8 + 4096 > 220 * 1024) return t;
+  if (t.threads > 512 || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
+  if (t.smem[1] > 220 * 1024) return;
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
-  const int Q = t.TY * g.M * t.TZ;
-  t.spt = (Q + t.threads - 1) / t.threads;
-  if (t.spt > 4) { t.threads = 512; t.spt = (Q + 511) / 512; }
-  if (t.spt > 4) return t;
-  int XC = c->opt_XC;
-  if (!XC) {
-    // enough CTAs for >= ~6 waves of 2 CTAs/SM, but chunks of at least 8 planes to amortise the x halo
-    const long long cols = (long long)t.n_yt * t.n_zt;
-    long long want_chunks = (148LL * 2 * 6 + cols - 1) / cols;
-    XC = (int)std::max<long long>(8, g.nx / std::max<long long>(1, want_chunks));
-    if (XC > g.nx) XC = g.nx;
-  }
-  t.XC = XC;
-  t.n_ch = (g.nx + XC - 1) / XC;
+  t.n_cols = t.n_yt * t.n_zt;
   t.ok = true;
-  return t;
+  c->tiling = t;
+
+  // tile-relative neighbour table for the parameter bank, grouped by (motif, dx)
+  const int nd = 2 * g.gx + 1;
+  c->tile_nbr.assign(n_nbr, JbTileNbr{});
+  c->tile_nbr_begin.assign(g.M * nd + 1, 0);
+  for (int pos = 0; pos < n_nbr; ++pos) {
+    const int k = c->tile_order[pos];
+    const int mi = c->t_mi[k], mj = c->t_mj[k];
+    const int Tx = c->t_T[3 * k], Ty = c->t_T[3 * k + 1], Tz = c->t_T[3 * k + 2];
+    JbTileNbr e{};
+    e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
+    e.jidx = c->tile_jidx[k];
+    e.J = c->t_J9[9 * k];
+    c->tile_nbr[pos] = e;
+    c->tile_nbr_begin[mi * nd + (Tx + g.gx) + 1]++;
+  }
+  for (int q = 0; q < g.M * nd; ++q) c->tile_nbr_begin[q + 1] += c->tile_nbr_begin[q];
+  if (c->d_tile_nbr) cudaFree(c->d_tile_nbr);
+  c->d_tile_nbr = nullptr;
+  if (cudaMalloc(&c->d_tile_nbr, std::max(1, n_nbr) * sizeof(JbTileNbr)) != cudaSuccess ||
+      cudaMemcpy(c->d_tile_nbr, c->tile_nbr.data(), n_nbr * sizeof(JbTileNbr), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    c->tiling.ok = false;  // fall back to the direct kernel
+  }
 }
 
-int build_tmaps(jb_ctx *c, const Tiling &t) {
-  if (c->tmap_valid && c->tmap_BY == t.BY && c->tmap_BZ == t.BZ) return JB_OK;
+void fill_tile_params(jb_ctx *c, JbTileParams &p) {
+  const jb_ctx::Tiling &t = c->tiling;
+  p.g = c->g;
+  p.Jtab = c->d_Jtab;
+  p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
+  p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols; p.u_tma = t.u_tma;
+  for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
+  for (int m = 0; m < c->g.M; ++m) p.class_of_motif[m] = c->class_of_motif[m];
+  p.nbr = c->d_tile_nbr;
+  p.n_nbr = (int)c->tile_nbr.size();
+}
+
+// grid size (resident CTAs) and number of x-chunks for one kernel variant
+int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) {
+  jb_ctx::Tiling &t = c->tiling;
+  if (t.grid[stage][thermal] > 0) return JB_OK;
+  if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
+  int per_sm = 0;
+  JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
+  if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the tile kernel does not fit on an SM with this tiling");
+  if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
+  const int G = per_sm * c->num_sms;
+  const JbGeom &g = c->g;
+  int best_c = 1;
+  if (c->opt_chunks > 0) {
+    best_c = std::min(c->opt_chunks, g.nx);
+  } else {
+    // cost model: time ~ (items per CTA, rounded up) x (planes marched per item + load-only halo planes)
+    double best = 1e300;
+    for (int nc = 1; nc <= g.nx; ++nc) {
+      const long long items = (long long)nc * t.n_cols;
+      const long long per_cta = (items + G - 1) / G;
+      const int xc = (g.nx + nc - 1) / nc;
+      const double cost = (double)per_cta * (xc + 0.7 * 2 * g.gx + 0.3);
+      if (cost < best * 0.999) { best = cost; best_c = nc; }
+    }
+  }
+  t.n_chunks[stage][thermal] = best_c;
+  t.grid[stage][thermal] = (int)std::min<long long>(G, (long long)best_c * t.n_cols);
+  return JB_OK;
+}
+
+int build_tmaps(jb_ctx *c) {
+  if (c->tmap_valid) return JB_OK;
   static EncodeTiledFn encode = nullptr;
   if (!encode) {
     void *fn = nullptr;
@@ -375,20 +440,21 @@ int build_tmaps(jb_ctx *c, const Tiling &t) {
     encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   const JbGeom &g = c->g;
+  const jb_ctx::Tiling &t = c->tiling;
   const cuuint64_t dims[3] = {(cuuint64_t)g.PZ, (cuuint64_t)g.PY * g.M, (cuuint64_t)g.PX};
   const cuuint64_t strides[2] = {(cuuint64_t)g.PZ * 8, (cuuint64_t)g.sX * 8};
-  const cuuint32_t box[3] = {(cuuint32_t)t.BZ, (cuuint32_t)t.rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int a = 0; a < 2; ++a) {
+  for (int a = 0; a < 3; ++a) {
+    const cuuint32_t box[3] = {(cuuint32_t)(a < 2 ? t.BZ : t.UZ), (cuuint32_t)((a < 2 ? t.BY : t.TY) * g.M), 1};
     for (int k = 0; k < 3; ++k) {
-      double *base = a == 0 ? c->S0[k] : c->S1[k];
+      double *base = a == 0 ? c->S0[k] : (a == 1 ? c->S1[k] : c->U[k]);
       CUresult r = encode(&c->tmap[a][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) JB_FAIL(c, JB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     }
   }
-  c->tmap_valid = true; c->tmap_BY = t.BY; c->tmap_BZ = t.BZ;
+  c->tmap_valid = true;
   return JB_OK;
 }
 
@@ -429,15 +495,14 @@ int ensure_ready(jb_ctx *c) {
       double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
       JB_CUDA(c, jbk_import(c->g, c->d_aos, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
     }
-    c->tile_BZ_built = -1;
+    c->tables_built = false;
+    c->tiling_valid = false;
     c->classes_dirty = true;
   }
+  const bool classes_were_dirty = c->classes_dirty;
   int rc = build_classes(c); if (rc) return rc;
-  if (c->has_template) {
-    Tiling t = choose_tiling(c);
-    const int BZ = t.ok ? t.BZ : 0;
-    if (c->tile_BZ_built != BZ) { rc = build_template_tables(c, BZ); if (rc) return rc; }
-  }
+  if (classes_were_dirty) c->tiling_valid = false;
+  if (c->has_template && !c->tables_built) { rc = build_template_tables(c); if (rc) return rc; }
   return JB_OK;
 }
 
@@ -506,7 +571,7 @@ void jb_destroy(jb_ctx *c) {
   release_state(c);
   void *p;
   p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
-  p = c->d_nbr_global; free_dev(p); p = c->d_nbr_tile; free_dev(p); p = c->d_Jtab; free_dev(p);
+  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -530,7 +595,8 @@ int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int3
   c->t_mi.assign(mi, mi + n); c->t_mj.assign(mj, mj + n); c->t_T.assign(T3, T3 + 3 * n); c->t_J9.assign(J9, J9 + 9 * (size_t)n);
   c->has_template = n > 0;
   c->has_pairs = false;
-  c->tile_BZ_built = -1;
+  c->tables_built = false;
+  c->tiling_valid = false;
   return JB_OK;
 }
 
@@ -663,9 +729,15 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   if (c->d.n_ranks > 1 && c->g.gx > 0 && !c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: jb_halo_connect has not been called");
   const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
 
-  Tiling tl = choose_tiling(c);
-  const bool use_tma = c->opt_kernel == 1 && tl.ok && !c->has_pairs;
-  if (use_tma) { rc = build_tmaps(c, tl); if (rc) return rc; }
+  choose_tiling(c);
+  const bool use_tile = c->opt_kernel == 1 && c->tiling.ok && !c->has_pairs;
+  JbTileParams tp{};
+  if (use_tile) {
+    rc = build_tmaps(c); if (rc) return rc;
+    fill_tile_params(c, tp);
+    tp.dt = dt; tp.half_dt = 0.5 * dt; tp.seed = seed;
+  }
+  const int thermal = T > 0.0 ? 1 : 0;
 
   const int max_chunk = c->has_ac ? 2048 : nsteps;
   for (int done = 0; done < nsteps;) {
@@ -707,10 +779,17 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         record_event(c, 2 * stage);
         if (c->has_pairs) {
           JB_CUDA(c, jbk_stage_pairs(p, c->d_ell_idx, c->d_ell_val, c->ell_width, c->d_pair_J, c->pairs_iso ? 1 : 0, stage, c->stream));
-        } else if (use_tma) {
-          p.TY = tl.TY; p.TZ = tl.TZ; p.XC = tl.XC; p.BY = tl.BY; p.BZ = tl.BZ; p.rows = tl.rows; p.slot_elems = tl.slot_elems;
-          p.R = tl.R; p.n_ytiles = tl.n_yt; p.n_ztiles = tl.n_zt; p.n_chunks = tl.n_ch; p.spt = tl.spt;
-          JB_CUDA(c, jbk_stage_tma(p, c->tmap[stage], stage, tl.threads, c->stream));
+        } else if (use_tile) {
+          for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
+          tp.step = p.step;
+          const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
+          for (size_t k = 0; k < c->h_classes.size(); ++k) tp.cls[k] = cls[k];
+          rc = tile_launch_shape(c, tp, stage, thermal); if (rc) return rc;
+          tp.n_chunks = c->tiling.n_chunks[stage][thermal];
+          tp.n_items = tp.n_chunks * tp.n_cols;
+          const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[2][0], c->tmap[2][1], c->tmap[2][2]};
+          JB_CUDA(c, jbk_stage_tile(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
+                                    c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
         }
@@ -914,12 +993,15 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   if (k == "kernel") c->opt_kernel = (int)value;
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
-  else if (k == "chunk_x") c->opt_XC = (int)value;
+  else if (k == "spt") c->opt_SPT = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
-  else if (k == "threads") c->opt_threads = (int)value;
+  else if (k == "ring_u") c->opt_RU = (int)value;
+  else if (k == "chunks") c->opt_chunks = (int)value;
+  else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
+  else if (k == "u_tma") c->opt_u_tma = (int)value;
   else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
-  c->tile_BZ_built = -1;
+  c->tiling_valid = false;
   c->tmap_valid = false;
   return JB_OK;
 }

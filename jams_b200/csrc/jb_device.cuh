@@ -1,0 +1,169 @@
+// jb_device.cuh — device-side building blocks shared by the stage kernels (jb_kernels.cu, jb_stage_tile.cu):
+// ghosted-box indexing, the Philox4x32-10 Langevin noise, the per-spin LLG-Heun stage update and the
+// ghost-image stores.  Reference formulas are cited next to each piece (paths relative to
+// /root/reference/src/jams/).
+#ifndef JB_DEVICE_CUH
+#define JB_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "jb_internal.h"
+
+namespace jbdev {
+
+__device__ __forceinline__ long long gidx(const JbGeom &g, int xp, int yp, int m, int zp) {
+  return (long long)xp * g.sX + (long long)yp * g.sY + (long long)m * g.PZ + zp;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) counter-based generator, all in registers -------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Box-Muller in fp32 on the SFU (MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS); the result is widened to
+// double by the caller.  u = (a + 0.5) 2^-32 lies in (0,1], so the log is finite; |n| <= 6.8.
+// The approximate SFU functions have absolute errors ~1e-6 on their outputs, far below the statistical
+// resolution of any observable (the reference's two backends, pcg+std::normal_distribution on the CPU
+// and cuRAND XORWOW on the GPU, already differ stream for stream: SURVEY.md 8c).
+__device__ __forceinline__ float bm_radius(uint32_t a) {
+  const float u = __fmaf_rn((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
+  return r;
+}
+__device__ __forceinline__ void box_muller2(uint32_t a, uint32_t b, float &n0, float &n1) {
+  const float r = bm_radius(a);
+  const float ang = (float)b * 1.4629180792671596e-09f;  // 2 pi 2^-32 b
+  n0 = r * __cosf(ang);
+  n1 = r * __sinf(ang);
+}
+__device__ __forceinline__ float box_muller1(uint32_t a, uint32_t b) {
+  return bm_radius(a) * __cosf((float)b * 1.4629180792671596e-09f);
+}
+
+// three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
+// (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
+__device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step,
+                                             unsigned long long gsite, double &n0, double &n1, double &n2) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float a, b;
+  box_muller2(r[0], r[1], a, b);
+  const float c = box_muller1(r[2], r[3]);
+  n0 = (double)a; n1 = (double)b; n2 = (double)c;
+}
+
+__device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
+  return (((unsigned long long)(g.x_begin + x) * g.Ny + y) * g.Nz + z) * g.M + m;
+}
+
+// ---- the per-spin physics ---------------------------------------------------------------------------
+// Adds the local terms to the exchange field, converts to Tesla, adds noise, evaluates the LLG right
+// hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and performs the
+// stage update:
+//   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
+//   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
+// unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
+template <int STAGE, bool THERMAL>
+__device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
+                                         double hx, double hy, double hz,
+                                         double n0, double n1, double n2, double dt, double half_dt,
+                                         double ux, double uy, double uz,
+                                         double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
+  if (c.power != 0) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163)
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    double pw = d;
+    if (c.power >= 4) pw = d * d * d;
+    if (c.power >= 6) pw = pw * d * d;
+    const double f = c.Kp * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  hx += c.fx; hy += c.fy; hz += c.fz;  // Zeeman dc + ac cos(wt) + applied field, meV
+  hx *= c.inv_mu; hy *= c.inv_mu; hz *= c.inv_mu;  // Tesla  (cpu_llg_heun.cc:68-82)
+  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
+
+  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;        // s x h
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;  // s x (s x h)
+  const double rx = c.mgyro * fma(c.alpha, bx_, ax_);
+  const double ry = c.mgyro * fma(c.alpha, by_, ay_);
+  const double rz = c.mgyro * fma(c.alpha, bz_, az_);
+
+  double px, py, pz;
+  if (STAGE == 0) {
+    vx = fma(half_dt, rx, sx); vy = fma(half_dt, ry, sy); vz = fma(half_dt, rz, sz);
+    px = fma(dt, rx, sx); py = fma(dt, ry, sy); pz = fma(dt, rz, sz);
+  } else {
+    px = fma(half_dt, rx, ux); py = fma(half_dt, ry, uy); pz = fma(half_dt, rz, uz);
+  }
+  const double n2_ = px * px + py * py + pz * pz;
+  // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged.  rsqrt() is CUDA's IEEE-accurate
+  // (<= 1 ulp) double reciprocal square root: MUFU.RSQ64H seed + Newton steps, no fp64 divide.
+  const double inv = (n2_ > 4.930380657631324e-32) ? rsqrt(n2_) : 1.0;
+  ox = px * inv; oy = py * inv; oz = pz * inv;
+}
+
+// store the ghost images of a freshly computed spin (the value for its own cell has been stored by the
+// caller): periodic images in y/z inside this box; x images into the lo/hi boxes, which are this box
+// itself on one GPU and the neighbours' boxes -- peer memory over NVLink -- on several.
+// Only called for sites within a ghost depth of a face.
+struct JbOutBoxes {
+  double *out[3];
+  double *out_lo[3];
+  double *out_hi[3];
+};
+static __device__ __noinline__ void store_images(const JbGeom &g, const JbOutBoxes &o, int x, int y, int m, int z,
+                                          double vx, double vy, double vz) {
+  const bool yb = g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy));
+  const bool zb = g.per[2] && ((z < g.gz) | (z >= g.Nz - g.gz));
+  int yps[2], zps[2], ny = 1, nz = 1;
+  yps[0] = y + g.gy; zps[0] = z + g.gz;
+  if (yb) yps[ny++] = (y < g.gy) ? y + g.gy + g.Ny : y + g.gy - g.Ny;
+  if (zb) zps[nz++] = (z < g.gz) ? z + g.gz + g.Nz : z + g.gz - g.Nz;
+  // x targets: 0 = own, 1 = lo box, 2 = hi box
+  for (int xt = 0; xt < 3; ++xt) {
+    double *const *arr;
+    int xp;
+    if (xt == 0) { arr = o.out; xp = x + g.gx; }
+    else if (xt == 1) { if (!(x < g.gx) || o.out_lo[0] == nullptr) continue; arr = o.out_lo; xp = x + g.gx + g.nx; }
+    else { if (!(x >= g.nx - g.gx) || o.out_hi[0] == nullptr) continue; arr = o.out_hi; xp = x + g.gx - g.nx; }
+    for (int a = 0; a < ny; ++a) {
+      for (int b = 0; b < nz; ++b) {
+        if (xt == 0 && a == 0 && b == 0) continue;
+        const long long i = gidx(g, xp, yps[a], m, zps[b]);
+        arr[0][i] = vx; arr[1][i] = vy; arr[2][i] = vz;
+      }
+    }
+  }
+}
+
+// does a site need store_images()?
+__device__ __forceinline__ bool yz_image_needed(const JbGeom &g, int y, int z) {
+  return (g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy))) | (g.per[2] && ((z < g.gz) | (z >= g.Nz - g.gz)));
+}
+__device__ __forceinline__ bool x_image_needed(const JbGeom &g, int x) { return (x < g.gx) | (x >= g.nx - g.gx); }
+
+// ---- warp / block reductions (monitors) ------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace jbdev
+
+#endif  // JB_DEVICE_CUH

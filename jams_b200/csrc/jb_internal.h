@@ -61,7 +61,7 @@ struct JbClass {
 
 // one entry of the exchange template of a motif site, in ghosted-box terms
 struct JbNbr {
-  int delta;   // offset inside a plane: (dy*M + (mj - mi))*row + dz, with row = PZ (global) or BZ (smem tile)
+  int delta;   // offset inside a plane of the ghosted box: (dy*M + (mj - mi))*PZ + dz
   int dx;      // plane offset
   int jidx;    // index into the table of unique tensors
   int pad;
@@ -70,7 +70,6 @@ struct JbNbr {
 
 struct JbTables {
   const JbNbr *nbr_global;     // entries with delta computed for the global ghosted box (row = PZ)
-  const JbNbr *nbr_tile;       // entries with delta computed for the smem tile (row = BZ)
   const double *Jtab;          // n_unique x 9
   const JbClass *classes;      // n_classes
   const unsigned char *site_class;  // per-site class in interior [x][y][m][z] order, or nullptr (motif-uniform)
@@ -92,14 +91,42 @@ struct JbStageParams {
   double dt, half_dt;
   unsigned long long seed, step;
   int thermal;
-  // tiling of the TMA kernel
-  int TY, TZ, XC;        // tile extent in y, z and planes marched per CTA
+};
+
+// ---- parameter block of the persistent TMA tile kernel (jb_stage_tile.cu) ------------------------------
+// The per-class constants, the template's group offsets and the tiling live in the kernel parameter (constant)
+// bank (kept under the classic 4 KB limit together with the six tensor maps); the exchange template itself
+// (16 B per entry) is copied from global to shared memory once per resident CTA.  "Matrix" data therefore costs
+// 0 B of HBM traffic per spin (the reference streams 12 B per non-zero, containers/sparse_matrix.h:366-379).
+#define JB_TILE_MAX_NBR 1024
+#define JB_TILE_MAX_CLASSES 8
+#define JB_TILE_MAX_MOTIF 16
+#define JB_TILE_MAX_GX 3
+struct JbTileNbr {
+  int delta;   // offset inside a plane of the smem tile: (dy*M + (mj - mi))*BZ + dz
+  int jidx;    // index into the table of unique tensors (anisotropic exchange only)
+  double J;    // scalar coupling, meV
+};
+struct JbTileParams {
+  JbGeom g;
+  double *out[3];        // spins written (S1 in stage A, S0 in stage B), own box
+  double *out_lo[3];     // box that receives the images of my low-x boundary planes (own box, a peer's, or null)
+  double *out_hi[3];
+  double *u[3];          // Heun intermediate, written by stage A with plain stores (stage B reads it through TMA)
+  const double *Jtab;    // n_unique x 9 (anisotropic exchange only)
+  double dt, half_dt;
+  unsigned long long seed, step;
+  int TY, TZ, UZ;        // tile extent in y, z; UZ = inner extent of the U box (= BZ, see choose_tiling)
   int BY, BZ;            // tile + halo extent (BZ even)
-  int rows;              // BY * M
-  int slot_elems;        // rows * BZ rounded up to a multiple of 16 doubles (128 B)
-  int R;                 // ring slots (power of two)
-  int n_ytiles, n_ztiles, n_chunks;
-  int spt;               // in-plane sites per thread
+  int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
+  int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
+  int u_tma;             // stage B: u arrives through the TMA ring (1) or by plain global loads (0)
+  int n_yt, n_zt, n_cols, n_chunks, n_items;
+  int n_nbr;
+  const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
+  int nbr_begin[JB_TILE_MAX_MOTIF * (2 * JB_TILE_MAX_GX + 1) + 1];  // [m][dx + gx] -> first entry of nbr[]
+  int class_of_motif[JB_TILE_MAX_MOTIF];
+  JbClass cls[JB_TILE_MAX_CLASSES];
 };
 
 struct jb_ctx {
@@ -139,14 +166,31 @@ struct jb_ctx {
   int class_of_motif[JB_MAX_MOTIF] = {0};
 
   // device tables
-  JbNbr *d_nbr_global = nullptr, *d_nbr_tile = nullptr;
+  JbNbr *d_nbr_global = nullptr;
   double *d_Jtab = nullptr;
   JbClass *d_classes = nullptr;
   unsigned char *d_site_class = nullptr;
   int nbr_begin[JB_MAX_MOTIF + 1] = {0};
   int n_unique_J = 0;
   bool iso = true;
-  int tile_BZ_built = 0;  // BZ the tile table was built for
+  bool tables_built = false;
+
+  // tiling of the persistent TMA kernel (jb_capi.cu choose_tiling) and its parameter-bank tables
+  struct Tiling {
+    bool ok = false;
+    int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
+    int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, u_tma = 1;
+    size_t smem[2] = {0, 0};              // per stage
+    int grid[2][2] = {{0, 0}, {0, 0}};    // [stage][thermal], 0 = not determined yet
+    int n_chunks[2][2] = {{0, 0}, {0, 0}};
+  } tiling;
+  bool tiling_valid = false;
+  std::vector<int> tile_order, tile_jidx;   // template entries in table order / their unique-tensor ids
+  std::vector<JbClass> h_class_tab;         // host copy of the class table(s) last uploaded (parameter bank of the tile kernel)
+  std::vector<JbTileNbr> tile_nbr;
+  JbTileNbr *d_tile_nbr = nullptr;
+  std::vector<int> tile_nbr_begin;
+  int num_sms = 0;
 
   // state: ghosted SoA arrays
   double *S0[3] = {nullptr, nullptr, nullptr};
@@ -157,14 +201,14 @@ struct jb_ctx {
   double *d_scratch = nullptr; size_t d_scratch_bytes = 0;  // per-spin scalars / reductions
   double *h_pinned = nullptr; size_t h_pinned_bytes = 0;
 
-  // TMA descriptors for S0 and S1 components
-  CUtensorMap tmap[2][3];
+  // TMA descriptors: [0] = S0 x,y,z  [1] = S1 x,y,z (tile + halo boxes)  [2] = U x,y,z (tile boxes)
+  CUtensorMap tmap[3][3];
   bool tmap_valid = false;
-  int tmap_BY = 0, tmap_BZ = 0;
 
   // options
-  int opt_kernel = 1;      // 0 = direct global gathers, 1 = TMA ring
-  int opt_TY = 0, opt_TZ = 0, opt_XC = 0, opt_R = 0, opt_threads = 256;  // 0 = heuristic
+  int opt_kernel = 1;      // 0 = direct global gathers, 1 = persistent TMA tile kernel
+  int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
+  int opt_u_tma = 1;
   int opt_time_kernels = 0;
 
   // halo peers
@@ -189,8 +233,12 @@ cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3],
 cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream);
 cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream);
 cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
-cudaError_t jbk_stage_tma(const JbStageParams &p, const CUtensorMap *tmaps3, int stage, int threads, cudaStream_t stream);
-cudaError_t jbk_stage_tma_smem_bytes(const JbStageParams &p, size_t *bytes);
+// persistent TMA tile kernel: tmaps = {S.x, S.y, S.z, U.x, U.y, U.z}; spt in {1,2,4}; grid = number of CTAs
+cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
+                           int threads, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t jbk_stage_tile_smem_bytes(const JbTileParams &p, int stage, size_t *bytes);
+cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
+                                     size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
                             int iso, int stage, cudaStream_t stream);
 // term field (meV) into AoS N x 3 (device); term as jb_term; pairs path when ell_idx != nullptr

@@ -13,146 +13,33 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "jb_internal.h"
+#include "jb_device.cuh"
 
 namespace {
 
-// =================================================================================================
-// small device helpers
-// =================================================================================================
-__device__ __forceinline__ long long gidx(const JbGeom &g, int xp, int yp, int m, int zp) {
-  return (long long)xp * g.sX + (long long)yp * g.sY + (long long)m * g.PZ + zp;
-}
+using namespace jbdev;
 
-// ---- Philox4x32-10 (Salmon et al., SC'11) counter-based generator, all in registers -------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0;
-    const uint32_t n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += W0; k1 += W1;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// Box-Muller in fp32 from two 32-bit words; the result is widened to double by the caller.
-// u in (0,1]: (x + 0.5) * 2^-32 is never 0, so the log is finite.
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float &n0, float &n1) {
-  const float u = __fmaf_rn((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float v = __fmul_rn((float)b, 2.3283064365386963e-10f);  // [0,1]
-  const float r = sqrtf(__fmul_rn(-2.0f, logf(u)));
-  float s, c;
-  sincospif(__fmul_rn(2.0f, v), &s, &c);
-  n0 = __fmul_rn(r, c);
-  n1 = __fmul_rn(r, s);
-}
-
-// three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
-// (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
-__device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step,
-                                             unsigned long long gsite, double &n0, double &n1, double &n2) {
-  uint32_t r[4];
-  philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32),
-                (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  float a, b, c, d;
-  box_muller(r[0], r[1], a, b);
-  box_muller(r[2], r[3], c, d);
-  n0 = (double)a; n1 = (double)b; n2 = (double)c;
-}
-
-__device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
-  return (((unsigned long long)(g.x_begin + x) * g.Ny + y) * g.Nz + z) * g.M + m;
-}
-
-// ---- the per-spin physics ---------------------------------------------------------------------------
-// Adds the local terms to the exchange field, converts to Tesla, adds noise, evaluates the LLG right
-// hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and performs the
-// stage update:
-//   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
-//   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
-// unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
-template <int STAGE, bool THERMAL>
-__device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
-                                         double hx, double hy, double hz,
-                                         double n0, double n1, double n2, double dt, double half_dt,
-                                         double ux, double uy, double uz,
-                                         double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
-  if (c.power != 0) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163)
-    const double d = c.ax * sx + c.ay * sy + c.az * sz;
-    double pw = d;
-    if (c.power >= 4) pw = d * d * d;
-    if (c.power >= 6) pw = pw * d * d;
-    const double f = c.Kp * pw;
-    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
-  }
-  hx += c.fx; hy += c.fy; hz += c.fz;  // Zeeman dc + ac cos(wt) + applied field, meV
-  hx *= c.inv_mu; hy *= c.inv_mu; hz *= c.inv_mu;  // Tesla  (cpu_llg_heun.cc:68-82)
-  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
-
-  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;        // s x h
-  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;  // s x (s x h)
-  const double rx = c.mgyro * fma(c.alpha, bx_, ax_);
-  const double ry = c.mgyro * fma(c.alpha, by_, ay_);
-  const double rz = c.mgyro * fma(c.alpha, bz_, az_);
-
-  double px, py, pz;
-  if (STAGE == 0) {
-    vx = fma(half_dt, rx, sx); vy = fma(half_dt, ry, sy); vz = fma(half_dt, rz, sz);
-    px = fma(dt, rx, sx); py = fma(dt, ry, sy); pz = fma(dt, rz, sz);
-  } else {
-    px = fma(half_dt, rx, ux); py = fma(half_dt, ry, uy); pz = fma(half_dt, rz, uz);
-  }
-  const double n2_ = px * px + py * py + pz * pz;
-  // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged
-  const double inv = (n2_ > 4.930380657631324e-32) ? 1.0 / sqrt(n2_) : 1.0;
-  ox = px * inv; oy = py * inv; oz = pz * inv;
-}
-
-// store a freshly computed spin into its own cell and into every ghost image of that cell
-// (periodic images in y/z inside this box; x images into the lo/hi boxes, which are this box itself
-// on one GPU and the neighbours' boxes -- peer memory over NVLink -- on several)
+// own cell + ghost images (see jbdev::store_images)
 __device__ __forceinline__ void store_with_images(const JbStageParams &p, int x, int y, int m, int z,
                                                   double vx, double vy, double vz) {
   const JbGeom &g = p.g;
   const long long i0 = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
   p.out[0][i0] = vx; p.out[1][i0] = vy; p.out[2][i0] = vz;
-  const bool xb = (x < g.gx) | (x >= g.nx - g.gx);
-  const bool yb = g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy));
-  const bool zb = g.per[2] && ((z < g.gz) | (z >= g.Nz - g.gz));
-  if (!(xb | yb | zb)) return;
-
-  int yps[2], zps[2], ny = 1, nz = 1;
-  yps[0] = y + g.gy; zps[0] = z + g.gz;
-  if (yb) yps[ny++] = (y < g.gy) ? y + g.gy + g.Ny : y + g.gy - g.Ny;
-  if (zb) zps[nz++] = (z < g.gz) ? z + g.gz + g.Nz : z + g.gz - g.Nz;
-  // x targets: 0 = own, 1 = lo box, 2 = hi box
-  for (int xt = 0; xt < 3; ++xt) {
-    double *const *arr;
-    int xp;
-    if (xt == 0) { arr = p.out; xp = x + g.gx; }
-    else if (xt == 1) { if (!(x < g.gx) || p.out_lo[0] == nullptr) continue; arr = p.out_lo; xp = x + g.gx + g.nx; }
-    else { if (!(x >= g.nx - g.gx) || p.out_hi[0] == nullptr) continue; arr = p.out_hi; xp = x + g.gx - g.nx; }
-    for (int a = 0; a < ny; ++a) {
-      for (int b = 0; b < nz; ++b) {
-        if (xt == 0 && a == 0 && b == 0) continue;
-        const long long i = gidx(g, xp, yps[a], m, zps[b]);
-        arr[0][i] = vx; arr[1][i] = vy; arr[2][i] = vz;
-      }
-    }
-  }
+  if (!(x_image_needed(g, x) | yz_image_needed(g, y, z))) return;
+  JbOutBoxes o;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { o.out[c] = p.out[c]; o.out_lo[c] = p.out_lo[c]; o.out_hi[c] = p.out_hi[c]; }
+  store_images(g, o, x, y, m, z, vx, vy, vz);
 }
 
 // interior flat index q (layout order [x][y][m][z]) -> coordinates
-__device__ __forceinline__ void decode_site(const JbGeom &g, long long q, int &x, int &y, int &m, int &z) {
-  z = (int)(q % g.Nz); q /= g.Nz;
-  m = (int)(q % g.M); q /= g.M;
-  y = (int)(q % g.Ny);
-  x = (int)(q / g.Ny);
+__device__ __forceinline__ void decode_site(const JbGeom &g, long long q64, int &x, int &y, int &m, int &z) {
+  unsigned q = (unsigned)q64;  // N < 2^31 per context (jb_create): 32-bit divisions
+  const unsigned uz = (unsigned)g.Nz, um = (unsigned)g.M, uy = (unsigned)g.Ny;
+  unsigned t = q / uz; z = (int)(q - t * uz); q = t;
+  t = q / um; m = (int)(q - t * um); q = t;
+  t = q / uy; y = (int)(q - t * uy);
+  x = (int)t;
 }
 
 __device__ __forceinline__ long long ref_site_local(const JbGeom &g, int x, int y, int m, int z) {
@@ -267,153 +154,6 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
   llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
   store_with_images(p, x, y, m, z, ox, oy, oz);
-}
-
-// =================================================================================================
-// stage kernel, variant 1: TMA-fed shared-memory plane ring, marching along x
-// =================================================================================================
-// A CTA owns a (TY x TZ) column of cells (all M motif sites) and marches over XC consecutive x planes.
-// Each plane-with-halo is a 3-D TMA box {BZ, BY*M, 1} of the ghosted array per spin component, landed
-// in one of R ring slots; an mbarrier per slot carries the transaction count.  At any time the
-// 2*gx+1 planes the stencil needs are resident and R-(2gx+1) further planes are in flight.
-__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-
-#define JB_SPT_MAX 4
-
-template <int STAGE, bool THERMAL, bool ISO>
-__global__ void __launch_bounds__(512) stage_tma_kernel(const __grid_constant__ JbStageParams p,
-                                                        const __grid_constant__ CUtensorMap tmx,
-                                                        const __grid_constant__ CUtensorMap tmy,
-                                                        const __grid_constant__ CUtensorMap tmz) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const JbGeom &g = p.g;
-  const int R = p.R, Rm = p.R - 1;
-  const int slot_elems = p.slot_elems;
-  double *ring = reinterpret_cast<double *>(smem_raw);
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)R * 3 * slot_elems);
-  JbNbr *s_nbr = reinterpret_cast<JbNbr *>(bars + JB_MAX_RING);
-  const int n_nbr = p.t.nbr_begin[g.M];
-
-  const int tid = threadIdx.x, NT = blockDim.x;
-  int b = blockIdx.x;
-  const int zt = b % p.n_ztiles; b /= p.n_ztiles;
-  const int yt = b % p.n_ytiles;
-  const int chunk = b / p.n_ytiles;
-  const int x0 = chunk * p.XC;
-  const int xc = min(p.XC, g.nx - x0);
-  const int y0 = yt * p.TY, z0 = zt * p.TZ;
-  const int n_planes = xc + 2 * g.gx;
-  const uint32_t box_bytes = (uint32_t)(p.rows * p.BZ * sizeof(double));
-
-  if (tid == 0) {
-    for (int s = 0; s < R; ++s) mbar_init(smem_u32(&bars[s]), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int n = tid; n < n_nbr; n += NT) s_nbr[n] = p.t.nbr_tile[n];
-  __syncthreads();
-
-  auto issue = [&](int seq) {
-    const int slot = seq & Rm;
-    const uint32_t bar = smem_u32(&bars[slot]);
-    mbar_expect_tx(bar, 3 * box_bytes);
-    double *dst = ring + (size_t)slot * 3 * slot_elems;
-    tma_load_3d(smem_u32(dst), &tmx, z0, y0 * g.M, x0 + seq, bar);
-    tma_load_3d(smem_u32(dst + slot_elems), &tmy, z0, y0 * g.M, x0 + seq, bar);
-    tma_load_3d(smem_u32(dst + 2 * slot_elems), &tmz, z0, y0 * g.M, x0 + seq, bar);
-  };
-  if (tid == 0) {
-    const int pre = min(R, n_planes);
-    for (int seq = 0; seq < pre; ++seq) issue(seq);
-  }
-
-  // per-thread in-plane sites
-  const int Q = p.TY * g.M * p.TZ;
-  int s_off[JB_SPT_MAX];       // centre offset inside a slot component
-  int s_y[JB_SPT_MAX], s_z[JB_SPT_MAX], s_m[JB_SPT_MAX];
-  bool s_ok[JB_SPT_MAX];
-#pragma unroll
-  for (int k = 0; k < JB_SPT_MAX; ++k) {
-    const int q = tid + k * NT;
-    const int tz = q % p.TZ;
-    const int r = q / p.TZ;
-    const int m = r % g.M;
-    const int ty = r / g.M;
-    s_y[k] = y0 + ty; s_z[k] = z0 + tz; s_m[k] = m;
-    s_ok[k] = (k < p.spt) && (q < Q) && (s_y[k] < g.Ny) && (s_z[k] < g.Nz);
-    s_off[k] = ((ty + g.gy) * g.M + m) * p.BZ + tz + g.gz;
-  }
-
-  // wait for the first 2*gx planes; plane 2*gx + ix is waited for inside the loop
-  for (int seq = 0; seq < 2 * g.gx; ++seq) mbar_wait(smem_u32(&bars[seq & Rm]), (uint32_t)((seq / R) & 1));
-
-  for (int ix = 0; ix < xc; ++ix) {
-    {
-      const int seq = ix + 2 * g.gx;
-      mbar_wait(smem_u32(&bars[seq & Rm]), (uint32_t)((seq / R) & 1));
-    }
-    const int x = x0 + ix;
-    const int cseq = ix + g.gx;  // ring sequence number of the centre plane
-#pragma unroll
-    for (int k = 0; k < JB_SPT_MAX; ++k) {
-      if (!s_ok[k]) continue;
-      const int m = s_m[k];
-      const double *cp = ring + (size_t)(cseq & Rm) * 3 * slot_elems + s_off[k];
-      const double sx = cp[0], sy = cp[slot_elems], sz = cp[2 * slot_elems];
-      double hx = 0.0, hy = 0.0, hz = 0.0;
-      const int nb = p.t.nbr_begin[m], ne = p.t.nbr_begin[m + 1];
-#pragma unroll 2
-      for (int n = nb; n < ne; ++n) {
-        const JbNbr e = s_nbr[n];
-        const double *np_ = ring + (size_t)((cseq + e.dx) & Rm) * 3 * slot_elems + s_off[k] + e.delta;
-        const double jx = np_[0], jy = np_[slot_elems], jz = np_[2 * slot_elems];
-        if (ISO) {
-          hx = fma(e.J, jx, hx); hy = fma(e.J, jy, hy); hz = fma(e.J, jz, hz);
-        } else {
-          const double *__restrict__ J = p.t.Jtab + 9 * e.jidx;
-          hx += J[0] * jx + J[1] * jy + J[2] * jz;
-          hy += J[3] * jx + J[4] * jy + J[5] * jz;
-          hz += J[6] * jx + J[7] * jy + J[8] * jz;
-        }
-      }
-      const JbClass c = p.t.classes[p.t.class_of_motif[m]];
-      const int y = s_y[k], z = s_z[k];
-      double n0 = 0, n1 = 0, n2 = 0;
-      if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
-      const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
-      double ux = 0, uy = 0, uz = 0;
-      if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
-      double ox, oy, oz, vx, vy, vz;
-      llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
-      if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
-      store_with_images(p, x, y, m, z, ox, oy, oz);
-    }
-    __syncthreads();  // every thread is done with the oldest plane (sequence ix): its slot can be refilled
-    if (tid == 0 && ix + R < n_planes) issue(ix + R);
-  }
 }
 
 // =================================================================================================
@@ -536,12 +276,6 @@ __global__ void field_kernel(const JbGeom g, const JbTables t, const double *__r
   if (term == JB_TERM_ZEEMAN || term == JB_TERM_APPLIED || term == JB_TERM_TOTAL) { hx += c.fx; hy += c.fy; hz += c.fz; }
   const long long s = ref_site_local(g, x, y, m, z);
   h_aos[3 * s] = hx; h_aos[3 * s + 1] = hy; h_aos[3 * s + 2] = hz;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-  return v;
 }
 
 // block-level sum with warp shuffles; result valid in thread 0
@@ -728,25 +462,6 @@ cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t str
   const long long total = (long long)p.g.nx * p.g.Ny * p.g.Nz * p.g.M;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   JB_DISPATCH_STAGE(stage_direct_kernel, (k<<<blocks, 256, 0, stream>>>(p)));
-  return cudaGetLastError();
-}
-
-cudaError_t jbk_stage_tma_smem_bytes(const JbStageParams &p, size_t *bytes) {
-  const int n_nbr = p.t.nbr_begin[p.g.M];
-  *bytes = (size_t)p.R * 3 * p.slot_elems * sizeof(double) + JB_MAX_RING * sizeof(unsigned long long) +
-           (size_t)n_nbr * sizeof(JbNbr) + 128;
-  return cudaSuccess;
-}
-
-cudaError_t jbk_stage_tma(const JbStageParams &p, const CUtensorMap *tm, int stage, int threads, cudaStream_t stream) {
-  size_t smem = 0;
-  jbk_stage_tma_smem_bytes(p, &smem);
-  const unsigned blocks = (unsigned)(p.n_chunks * p.n_ytiles * p.n_ztiles);
-  cudaError_t err = cudaSuccess;
-  JB_DISPATCH_STAGE(stage_tma_kernel,
-                    (err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                     (err == cudaSuccess ? (void)(k<<<blocks, threads, smem, stream>>>(p, tm[0], tm[1], tm[2])) : (void)0)));
-  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 

@@ -55,12 +55,15 @@ class Hamiltonian:
 
     def calculate_fields(self, time: float):
         """field_ of this term, N x 3, meV (not divided by mu)"""
+        self.solver._build()
         return self.solver.ctx.fields(self.term, time)
 
     def calculate_energies(self, time: float):
+        self.solver._build()
         return self.solver.ctx.energies(self.term, time, per_spin=True)[0]
 
     def calculate_total_energy(self, time: float):
+        self.solver._build()
         return self.solver.ctx.energies(self.term, time, per_spin=False)[1]
 
 

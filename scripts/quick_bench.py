@@ -1,29 +1,60 @@
-"""Development helper: time the stage kernels for a few tilings (not the contract bench; see bench.py)."""
+"""Development helper: time the stage kernels for a few tilings (not the contract bench; see bench.py).
+    python scripts/quick_bench.py [n] [T]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import json
 import numpy as np
 from jams_b200 import workloads as W
 
-def run(dims, options, T=0.0, steps=20, label=""):
-    w = W.c3_sc(dims=dims, temperature=T)
-    s = W.make_solver(w, options=dict(options, time_kernels=1), random_spins_seed=1)
-    s.run(3); s.ctx.synchronize(); s.ctx.last_step_kernel_ms()
-    t0 = time.perf_counter(); s.run(steps); s.ctx.synchronize(); wall = time.perf_counter() - t0
-    ms = s.ctx.last_step_kernel_ms()
+PEAK = 6538.9e9
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] * 1e9
+except Exception:
+    pass
+
+
+def run(dims, options, T=0.0, steps=20, label="", make=W.c3_sc):
+    w = make(dims=dims, temperature=T) if make is W.c3_sc else make(dims, T)
+    try:
+        s = W.make_solver(w, options=dict(options, time_kernels=1), random_spins_seed=1)
+        s.run(3); s.ctx.synchronize(); s.ctx.last_step_kernel_ms()
+        t0 = time.perf_counter(); s.run(steps); s.ctx.synchronize(); wall = time.perf_counter() - t0
+        ms = s.ctx.last_step_kernel_ms()
+    except Exception as e:  # noqa: BLE001
+        print(f"{label:44s} FAILED: {e}", flush=True)
+        return
     N = w["lattice"].num_spins
     rate = N * steps / (ms.sum() * 1e-3)
-    print(f"{label:40s} dims={dims} T={T}: A {ms[0]/steps:.3f} ms  B {ms[1]/steps:.3f} ms  wall/step {wall/steps*1e3:.3f} ms "
-          f"-> {rate/1e9:.2f} G upd/s = {rate*144/6532.2e9*100:.1f}% of HBM roofline", flush=True)
+    print(f"{label:44s} T={T:5.0f}: A {ms[0]/steps:.3f} ms  B {ms[1]/steps:.3f} ms  wall/step {wall/steps*1e3:.3f} ms "
+          f"-> {rate/1e9:6.2f} G upd/s = {rate*144/PEAK*100:5.1f}% of HBM roofline", flush=True)
+    s.ctx.close()
+
+
+CONFIGS = [(8, 64, 2, 4, 2, 0), (8, 64, 2, 5, 3, 0), (8, 64, 1, 4, 2, 0), (4, 64, 1, 5, 3, 0), (4, 64, 2, 5, 3, 0),
+           (4, 64, 1, 6, 4, 0), (16, 64, 2, 4, 2, 0), (16, 64, 4, 4, 2, 0), (16, 64, 4, 5, 3, 0), (8, 128, 2, 4, 2, 0),
+           (4, 128, 1, 5, 3, 0), (8, 32, 1, 5, 3, 0), (16, 32, 2, 5, 3, 0), (8, 64, 4, 5, 3, 0), (8, 64, 4, 6, 4, 0),
+           (2, 128, 1, 6, 4, 0), (2, 64, 1, 6, 4, 0)]
 
 if __name__ == "__main__":
+    # every configuration runs in its own process: a CUDA error is sticky for the process that hit it
+    import subprocess
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        n, T = int(sys.argv[2]), float(sys.argv[3])
+        opts = json.loads(sys.argv[4])
+        run((n, n, n), opts, T=T, label=sys.argv[5])
+        sys.exit(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    dims = (n, n, n)
-    run(dims, dict(kernel=0), label="direct")
-    for TY, TZ, XC, R, thr in [(8, 64, 0, 4, 256), (8, 64, 16, 8, 256), (4, 64, 0, 4, 256), (16, 64, 0, 4, 512), (8, 128, 0, 4, 256),
-                               (16, 32, 0, 4, 256), (8, 64, 32, 4, 256), (8, 64, 8, 4, 256), (4, 128, 0, 8, 256)]:
-        try:
-            run(dims, dict(kernel=1, tile_y=TY, tile_z=TZ, chunk_x=XC, ring=R, threads=thr), label=f"tma TY={TY} TZ={TZ} XC={XC} R={R} thr={thr}")
-        except Exception as e:
-            print("failed", TY, TZ, XC, R, thr, e)
-    run(dims, dict(kernel=0), T=300.0, label="direct thermal")
-    run(dims, dict(kernel=1), T=300.0, label="tma thermal (default tiling)")
+    temps = [float(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.0, 100.0]
+    for T in temps:
+        jobs = [(dict(kernel=0), "direct"), (dict(kernel=1), "tile default"), (dict(kernel=1, u_tma=0), "tile default u_tma=0"),
+                (dict(kernel=1, u_tma=0, tile_y=8, tile_z=64, spt=2, ring=5), "tile 8x64 spt2 R5 u_tma=0"),
+                (dict(kernel=1, u_tma=0, tile_y=8, tile_z=64, spt=2, ring=6), "tile 8x64 spt2 R6 u_tma=0"),
+                (dict(kernel=1, u_tma=0, tile_y=16, tile_z=64, spt=2, ring=5), "tile 16x64 spt2 R5 u_tma=0")]
+        for TY, TZ, SPT, R, RU, cta in CONFIGS:
+            jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, ctas_per_sm=cta),
+                         f"tile TY={TY} TZ={TZ} SPT={SPT} R={R} RU={RU} cta={cta}"))
+        for opts, label in jobs:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(T), json.dumps(opts), label],
+                               capture_output=True, text=True, timeout=300)
+            out = (r.stdout or "").strip()
+            print(out if out else f"{label:44s} CRASHED rc={r.returncode}: {(r.stderr or '').strip()[-300:]}", flush=True)
