@@ -100,9 +100,23 @@ JB_API int jb_set_exchange_template(jb_ctx *ctx, int32_t n, const int32_t *motif
  * ExchangeHamiltonian::neighbour_list() exposes it (hamiltonian/exchange.h:13,
  * containers/interaction_list.h:45-47): pairs (i,j) in GLOBAL site ids with an index into the table
  * of unique tensors (row-major 3x3, meV, already scaled).  Only pairs whose i lies in this
- * context's slab are used.  Single-GPU only in this version (n_ranks == 1). */
+ * context's slab are used.  A translation-invariant list (jb_detect_exchange_template) is turned into the
+ * template form and runs on the TMA tile kernel, on any number of ranks; anything else is kept as an ELL table
+ * (explicit int32 indices), single-rank only in this version. */
 JB_API int jb_set_exchange_pairs(jb_ctx *ctx, int64_t n_pairs, const int32_t *i, const int32_t *j,
                           const int32_t *value_id, int32_t n_values, const double *J9);
+
+/* Host-only helper (needs no GPU): recognise a translation-invariant neighbour list.  Pairs are in GLOBAL site
+ * ids as for jb_set_exchange_pairs; only pairs whose i lies in the slab of `desc` are looked at.  On success
+ * *n_template is the number of template entries written to motif_i / motif_j / T3 (3 per entry) / J9_out (9 per
+ * entry), in the form jb_set_exchange_template takes; *n_template = -1 means the list is not translation
+ * invariant (impurities or vacancies, a periodic dimension shorter than 2*range+1, or more than `capacity`
+ * distinct entries) and the general ELL path has to be used.  jb_set_exchange_pairs calls this itself (option
+ * "detect_template", default 1), so an adapter can hand over ExchangeHamiltonian::neighbour_list() as it is
+ * and still get the template kernel. */
+JB_API int jb_detect_exchange_template(const jb_lattice_desc *desc, int64_t n_pairs, const int32_t *i, const int32_t *j,
+                                const int32_t *value_id, int32_t n_values, const double *J9, int32_t capacity,
+                                int32_t *n_template, int32_t *motif_i, int32_t *motif_j, int32_t *T3, double *J9_out);
 
 /* UniaxialAnisotropyHamiltonian: power_ (2,4,6), magnitude_ (N, meV), axis_ (N x 3, unit vectors)
  * (hamiltonian/uniaxial_anisotropy.h:30-32, .cc:89-114). */

@@ -40,6 +40,8 @@ SIGNATURES = {
     "jb_set_materials": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "jb_set_exchange_template": (C.c_int, [C.c_void_p, C.c_int32, _ip, _ip, _ip, _dp]),
     "jb_set_exchange_pairs": (C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, _ip, C.c_int32, _dp]),
+    "jb_detect_exchange_template": (C.c_int, [C.POINTER(LatticeDesc), C.c_int64, _ip, _ip, _ip, C.c_int32, _dp, C.c_int32,
+                                               C.POINTER(C.c_int32), _ip, _ip, _ip, _dp]),
     "jb_set_uniaxial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "jb_set_zeeman": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_set_applied_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
@@ -83,6 +85,30 @@ def _f64(a):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def detect_exchange_template(dims, num_motif, periodic, i, j, value_id, values9, x_begin=0, nx_local=None, capacity=1024):
+    """jb_detect_exchange_template: (mi, mj, T, J9) of a translation-invariant neighbour list, or None.  Host only."""
+    lib = load()
+    d = LatticeDesc()
+    d.dims[:] = [int(v) for v in dims]
+    d.num_motif = int(num_motif)
+    d.periodic[:] = [int(bool(v)) for v in periodic]
+    d.x_begin = int(x_begin)
+    d.nx_local = int(dims[0] if nx_local is None else nx_local)
+    d.rank, d.n_ranks, d.device = 0, 1, -1
+    i = np.ascontiguousarray(i, np.int32); j = np.ascontiguousarray(j, np.int32)
+    v = np.ascontiguousarray(value_id, np.int32); J = _f64(values9).reshape(-1)
+    mi = np.zeros(capacity, np.int32); mj = np.zeros(capacity, np.int32); T = np.zeros(3 * capacity, np.int32)
+    J9 = np.zeros(9 * capacity)
+    n = C.c_int32(-1)
+    rc = lib.jb_detect_exchange_template(C.byref(d), i.size, i, j, v, J.size // 9, J, capacity, C.byref(n), mi, mj, T, J9)
+    if rc != JB_OK:
+        raise JamsB200Error(rc, "jb_detect_exchange_template: invalid arguments")
+    if n.value < 0:
+        return None
+    k = n.value
+    return dict(mi=mi[:k].copy(), mj=mj[:k].copy(), T=T[:3 * k].reshape(k, 3).copy(), J9=J9[:9 * k].reshape(k, 9).copy())
 
 
 class Context:

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -11,6 +12,7 @@
 #include <array>
 #include <cmath>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -196,7 +198,7 @@ int build_classes(jb_ctx *c) {
   const int N = c->N;
   if ((int)c->h_mus.size() != N) JB_FAIL(c, JB_ERR_INVALID, "jb_set_materials has not been called");
   std::map<std::array<double, 18>, int> seen;
-  c->h_classes.clear(); c->h_class_dc.clear(); c->h_class_ac.clear(); c->h_class_omega.clear();
+  c->h_classes.clear(); c->h_class_dc.clear(); c->h_class_ac.clear(); c->h_class_omega.clear(); c->h_class_gyro.clear();
   std::vector<unsigned char> cls(N);
   for (int i = 0; i < N; ++i) {
     std::array<double, 18> key{};
@@ -212,7 +214,8 @@ int build_classes(jb_ctx *c) {
       seen.emplace(key, id);
       JbClass k{};
       k.mu = key[0]; k.inv_mu = (key[0] != 0.0) ? 1.0 / key[0] : 0.0;
-      k.mgyro = -key[1]; k.alpha = key[2];
+      k.alpha = key[2];
+      c->h_class_gyro.push_back(key[1]);
       k.K = key[3]; k.Kp = key[3] * c->uni_power; k.ax = key[4]; k.ay = key[5]; k.az = key[6];
       k.power = (c->uni_power && key[3] != 0.0) ? c->uni_power : 0;
       c->h_classes.push_back(k);
@@ -257,7 +260,7 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
   for (size_t s = 0; s < count; ++s) {
     for (int k = 0; k < nc; ++k) {
       JbClass cl = c->h_classes[k];
-      const double gyro = -cl.mgyro;
+      const double gyro = c->h_class_gyro[k];
       if (T > 0.0 && dt > 0.0 && cl.mu != 0.0 && gyro != 0.0) {
         double denominator = 1.0;
         if (gilbert) denominator = 1.0 + cl.alpha * cl.alpha;
@@ -277,6 +280,9 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
         for (int d = 0; d < 3; ++d) f[d] += cl.mu * c->applied_B[d];  // applied_field.cc:146-148
       }
       cl.fx = f[0]; cl.fy = f[1]; cl.fz = f[2];
+      cl.fTx = f[0] * cl.inv_mu; cl.fTy = f[1] * cl.inv_mu; cl.fTz = f[2] * cl.inv_mu;
+      cl.KpT = cl.Kp * cl.inv_mu;
+      cl.c_full = -gyro * dt; cl.c_half = -gyro * (0.5 * dt);
       tab[s * nc + k] = cl;
     }
   }
@@ -324,8 +330,7 @@ void choose_tiling(jb_ctx *c) {
   c->tiling_valid = true;
   c->tmap_valid = false;
   const int n_nbr = (int)c->t_mi.size();
-  if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR ||
-      (int)c->h_classes.size() > JB_TILE_MAX_CLASSES)
+  if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
   int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
   TZ = std::max(1, std::min(TZ, g.Nz));
@@ -335,9 +340,9 @@ void choose_tiling(jb_ctx *c) {
   TY = std::max(1, std::min(TY, g.Ny));
   if (TY > 64) TY = 64;
   while (SPT > 1 && (SPT > TY)) SPT /= 2;
-  if (!(SPT == 1 || SPT == 2 || SPT == 4)) return;
-  t.R = c->opt_R ? c->opt_R : 2 * g.gx + 3;
-  t.RU = c->opt_RU ? c->opt_RU : 3;
+  if (!(SPT == 1 || SPT == 2)) return;
+  t.R = c->opt_R ? c->opt_R : 2 * g.gx + 2;
+  t.RU = c->opt_RU ? c->opt_RU : 2;
   if (t.R < 2 * g.gx + 2 || t.R > 8 || t.RU < 2 || t.RU > 8) return;
   for (;;) {
     t.TY = TY; t.TZ = TZ; t.SPT = SPT;
@@ -348,40 +353,45 @@ void choose_tiling(jb_ctx *c) {
     t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
     t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
     t.threads = TZ * ((TY + SPT - 1) / SPT);
-    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 256 + (size_t)n_nbr * sizeof(JbTileNbr);
+    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 512 + (size_t)n_nbr * sizeof(JbTileNbr);
     t.u_tma = c->opt_u_tma ? 1 : 0;
     t.smem[1] = t.smem[0] + (t.u_tma ? (size_t)t.RU * 3 * t.slotU * 8 : 0);
     // wanted: two CTAs per SM in stage B
-    if ((t.smem[1] <= 110 * 1024 && t.threads <= 512) || c->opt_TY || TY <= SPT) break;
+    if ((t.smem[1] <= 110 * 1024 && t.threads <= (SPT == 1 ? 512 : 256)) || c->opt_TY || TY <= SPT) break;
     TY = std::max(SPT, TY / 2);
   }
-  if (t.threads > 512 || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
+  if (t.threads > (t.SPT == 1 ? 512 : 256) || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
   if (t.smem[1] > 220 * 1024) return;
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
   t.ok = true;
   c->tiling = t;
 
-  // tile-relative neighbour table for the parameter bank, grouped by (motif, dx)
-  const int nd = 2 * g.gx + 1;
+  // tile-relative neighbour table, per motif site in the reference's CSR column order; couplings in Tesla
   c->tile_nbr.assign(n_nbr, JbTileNbr{});
-  c->tile_nbr_begin.assign(g.M * nd + 1, 0);
+  c->tile_nbr_begin.assign(g.M + 1, 0);
+  std::vector<double> J9T(9 * (size_t)std::max(1, n_nbr));
   for (int pos = 0; pos < n_nbr; ++pos) {
     const int k = c->tile_order[pos];
     const int mi = c->t_mi[k], mj = c->t_mj[k];
     const int Tx = c->t_T[3 * k], Ty = c->t_T[3 * k + 1], Tz = c->t_T[3 * k + 2];
+    const double inv_mu = c->h_classes[c->class_of_motif[mi]].inv_mu;
     JbTileNbr e{};
     e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
-    e.jidx = c->tile_jidx[k];
-    e.J = c->t_J9[9 * k];
+    e.d = Tx + g.gx;
+    e.J = c->t_J9[9 * k] * inv_mu;
+    for (int q = 0; q < 9; ++q) J9T[9 * (size_t)pos + q] = c->t_J9[9 * (size_t)k + q] * inv_mu;
     c->tile_nbr[pos] = e;
-    c->tile_nbr_begin[mi * nd + (Tx + g.gx) + 1]++;
+    c->tile_nbr_begin[mi + 1]++;
   }
-  for (int q = 0; q < g.M * nd; ++q) c->tile_nbr_begin[q + 1] += c->tile_nbr_begin[q];
+  for (int q = 0; q < g.M; ++q) c->tile_nbr_begin[q + 1] += c->tile_nbr_begin[q];
   if (c->d_tile_nbr) cudaFree(c->d_tile_nbr);
-  c->d_tile_nbr = nullptr;
+  if (c->d_tile_J9T) cudaFree(c->d_tile_J9T);
+  c->d_tile_nbr = nullptr; c->d_tile_J9T = nullptr;
   if (cudaMalloc(&c->d_tile_nbr, std::max(1, n_nbr) * sizeof(JbTileNbr)) != cudaSuccess ||
-      cudaMemcpy(c->d_tile_nbr, c->tile_nbr.data(), n_nbr * sizeof(JbTileNbr), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaMemcpy(c->d_tile_nbr, c->tile_nbr.data(), n_nbr * sizeof(JbTileNbr), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&c->d_tile_J9T, J9T.size() * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(c->d_tile_J9T, J9T.data(), J9T.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
     c->tiling.ok = false;  // fall back to the direct kernel
   }
@@ -390,13 +400,19 @@ void choose_tiling(jb_ctx *c) {
 void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   const jb_ctx::Tiling &t = c->tiling;
   p.g = c->g;
-  p.Jtab = c->d_Jtab;
+  p.J9T = c->d_tile_J9T;
   p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols; p.u_tma = t.u_tma;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
-  for (int m = 0; m < c->g.M; ++m) p.class_of_motif[m] = c->class_of_motif[m];
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
+  p.producer_sleep_ns = c->opt_producer_sleep;
+  p.split_wait = c->opt_split_wait;
+  for (int m = 0; m < c->g.M; ++m) {
+    int n = c->tile_nbr_begin[m];
+    while (n < c->tile_nbr_begin[m + 1] && c->tile_nbr[n].d < 2 * c->g.gx) ++n;
+    p.nbr_split[m] = n;
+  }
 }
 
 // grid size (resident CTAs) and number of x-chunks for one kernel variant
@@ -426,6 +442,10 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   }
   t.n_chunks[stage][thermal] = best_c;
   t.grid[stage][thermal] = (int)std::min<long long>(G, (long long)best_c * t.n_cols);
+  if (c->opt_verbose)
+    fprintf(stderr, "jams_b200: tile kernel stage %d thermal %d: tile %dx%d (y,z) spt %d, %d consumer threads, ring %d/%d, smem %zu B, "
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.R, t.RU,
+            t.smem[stage], per_sm, t.grid[stage][thermal], best_c, t.n_cols);
   return JB_OK;
 }
 
@@ -571,7 +591,7 @@ void jb_destroy(jb_ctx *c) {
   release_state(c);
   void *p;
   p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
-  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p);
+  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -600,8 +620,85 @@ int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int3
   return JB_OK;
 }
 
+int jb_detect_exchange_template(const jb_lattice_desc *d, int64_t n_pairs, const int32_t *pi, const int32_t *pj,
+                                const int32_t *vid, int32_t n_values, const double *J9, int32_t capacity,
+                                int32_t *n_template, int32_t *motif_i, int32_t *motif_j, int32_t *T3, double *J9_out) {
+  if (!d || !n_template || n_pairs < 0 || capacity < 0 || (n_pairs > 0 && (!pi || !pj || !vid || !J9))) return JB_ERR_INVALID;
+  if (capacity > 0 && (!motif_i || !motif_j || !T3 || !J9_out)) return JB_ERR_INVALID;
+  *n_template = -1;
+  const int L[3] = {d->dims[0], d->dims[1], d->dims[2]};
+  const int M = d->num_motif;
+  if (L[0] < 1 || L[1] < 1 || L[2] < 1 || M < 1 || M > 255) return JB_ERR_INVALID;
+  const long long Ntot = (long long)L[0] * L[1] * L[2] * M;
+  struct Entry { int mi, mj, T[3], vid; long long count; int order; };
+  std::unordered_map<uint64_t, Entry> seen;
+  auto decode = [&](int s, int cell[3], int &m) {
+    m = s % M; int r = s / M; cell[2] = r % L[2]; r /= L[2]; cell[1] = r % L[1]; cell[0] = r / L[1];
+  };
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    if (pi[p] < 0 || pi[p] >= Ntot || pj[p] < 0 || pj[p] >= Ntot || vid[p] < 0 || vid[p] >= n_values) return JB_ERR_INVALID;
+    int ci[3], cj[3], mi, mj;
+    decode(pi[p], ci, mi);
+    if (ci[0] < d->x_begin || ci[0] >= d->x_begin + d->nx_local) continue;
+    decode(pj[p], cj, mj);
+    int T[3];
+    for (int k = 0; k < 3; ++k) {
+      int t = cj[k] - ci[k];
+      if (d->periodic[k]) {  // minimum image, t in (-L/2, L/2]
+        if (2 * t > L[k]) t -= L[k];
+        else if (2 * t <= -L[k]) t += L[k];
+      }
+      if (t < -127 || t > 127) return JB_OK;  // not a short-range template
+      T[k] = t;
+    }
+    const uint64_t key = ((uint64_t)mi << 32) | ((uint64_t)mj << 24) | ((uint64_t)(T[0] + 128) << 16) | ((uint64_t)(T[1] + 128) << 8) | (uint64_t)(T[2] + 128);
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      if ((int)seen.size() >= capacity) return JB_OK;
+      Entry e{mi, mj, {T[0], T[1], T[2]}, vid[p], 1, (int)seen.size()};
+      seen.emplace(key, e);
+    } else {
+      if (it->second.vid != vid[p] && memcmp(J9 + 9 * (size_t)it->second.vid, J9 + 9 * (size_t)vid[p], 9 * sizeof(double)) != 0) return JB_OK;
+      it->second.count++;
+    }
+  }
+  std::vector<Entry> entries(seen.size());
+  for (auto &kv : seen) entries[kv.second.order] = kv.second;
+  for (const Entry &e : entries) {
+    long long expect = 1;
+    for (int k = 0; k < 3; ++k) {
+      const int lo = k == 0 ? d->x_begin : 0, n = k == 0 ? d->nx_local : L[k];
+      if (d->periodic[k]) {
+        if (e.T[k] != 0 && L[k] < 2 * std::abs(e.T[k]) + 1) return JB_OK;  // images alias: the reference would have thrown
+        expect *= n;
+      } else {
+        long long cnt = 0;
+        for (int x = lo; x < lo + n; ++x) cnt += (x + e.T[k] >= 0 && x + e.T[k] < L[k]) ? 1 : 0;
+        expect *= cnt;
+      }
+    }
+    if (e.count != expect) return JB_OK;  // some cell lacks (or repeats) this neighbour: impurity / vacancy
+  }
+  for (size_t n = 0; n < entries.size(); ++n) {
+    motif_i[n] = entries[n].mi; motif_j[n] = entries[n].mj;
+    for (int k = 0; k < 3; ++k) T3[3 * n + k] = entries[n].T[k];
+    memcpy(J9_out + 9 * n, J9 + 9 * (size_t)entries[n].vid, 9 * sizeof(double));
+  }
+  *n_template = (int32_t)entries.size();
+  return JB_OK;
+}
+
 int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const int32_t *pj, const int32_t *vid, int32_t n_values, const double *J9) {
   if (!c || n_pairs < 0 || n_values < 0 || (n_pairs > 0 && (!pi || !pj || !vid || !J9))) return JB_ERR_INVALID;
+  if (c->opt_detect_template && n_pairs > 0) {
+    const int cap = JB_TILE_MAX_NBR;
+    std::vector<int32_t> mi(cap), mj(cap), T3(3 * cap);
+    std::vector<double> J9t(9 * (size_t)cap);
+    int32_t nt = -1;
+    int rc = jb_detect_exchange_template(&c->d, n_pairs, pi, pj, vid, n_values, J9, cap, &nt, mi.data(), mj.data(), T3.data(), J9t.data());
+    if (rc == JB_ERR_INVALID) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
+    if (nt > 0) return jb_set_exchange_template(c, nt, mi.data(), mj.data(), T3.data(), J9t.data());
+  }
   if (c->d.n_ranks != 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_set_exchange_pairs is single-rank only in this version");
   JB_CUDA(c, cudaSetDevice(c->device));
   c->has_template = false; c->t_mi.clear(); c->t_mj.clear(); c->t_T.clear(); c->t_J9.clear();
@@ -735,7 +832,10 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   if (use_tile) {
     rc = build_tmaps(c); if (rc) return rc;
     fill_tile_params(c, tp);
-    tp.dt = dt; tp.half_dt = 0.5 * dt; tp.seed = seed;
+    for (int r = 0; r < 10; ++r) {   // Philox4x32-10 key schedule (Salmon et al.)
+      tp.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+      tp.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
   }
   const int thermal = T > 0.0 ? 1 : 0;
 
@@ -768,7 +868,6 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
             p.out_lo[k] = nullptr; p.out_hi[k] = nullptr;
           }
         }
-        p.dt = dt; p.half_dt = 0.5 * dt;
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
         p.thermal = T > 0.0 ? 1 : 0;
         if (multi) {
@@ -783,7 +882,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
           tp.step = p.step;
           const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
-          for (size_t k = 0; k < c->h_classes.size(); ++k) tp.cls[k] = cls[k];
+          for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
           rc = tile_launch_shape(c, tp, stage, thermal); if (rc) return rc;
           tp.n_chunks = c->tiling.n_chunks[stage][thermal];
           tp.n_items = tp.n_chunks * tp.n_cols;
@@ -999,6 +1098,10 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "chunks") c->opt_chunks = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
   else if (k == "u_tma") c->opt_u_tma = (int)value;
+  else if (k == "producer_sleep") { c->opt_producer_sleep = (int)value; return JB_OK; }
+  else if (k == "split_wait") { c->opt_split_wait = (int)value; return JB_OK; }
+  else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
+  else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }
   else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
   c->tiling_valid = false;

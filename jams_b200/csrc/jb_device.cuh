@@ -55,6 +55,29 @@ __device__ __forceinline__ float box_muller1(uint32_t a, uint32_t b) {
   return bm_radius(a) * __cosf((float)b * 1.4629180792671596e-09f);
 }
 
+// the same generator with the 20 round keys precomputed (rk[2r] = k0 + r W0, rk[2r+1] = k1 + r W1): when rk lives
+// in the kernel-parameter bank the keys are constant-bank operands of the LOP3s and cost no instructions
+__device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const unsigned int *__restrict__ rk, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void normals_from_words(const uint32_t r[4], double &n0, double &n1, double &n2) {
+  float a, b;
+  box_muller2(r[0], r[1], a, b);
+  const float c = box_muller1(r[2], r[3]);
+  n0 = (double)a; n1 = (double)b; n2 = (double)c;
+}
+
 // three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
 // (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
 __device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step,
@@ -62,10 +85,13 @@ __device__ __forceinline__ void site_normals(unsigned long long seed, unsigned l
   uint32_t r[4];
   philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32),
                 (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  float a, b;
-  box_muller2(r[0], r[1], a, b);
-  const float c = box_muller1(r[2], r[3]);
-  n0 = (double)a; n1 = (double)b; n2 = (double)c;
+  normals_from_words(r, n0, n1, n2);
+}
+__device__ __forceinline__ void site_normals_rk(const unsigned int *__restrict__ rk, unsigned long long step,
+                                                unsigned long long gsite, double &n0, double &n1, double &n2) {
+  uint32_t r[4];
+  philox4x32_10_rk((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, r);
+  normals_from_words(r, n0, n1, n2);
 }
 
 __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
@@ -73,42 +99,39 @@ __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x
 }
 
 // ---- the per-spin physics ---------------------------------------------------------------------------
-// Adds the local terms to the exchange field, converts to Tesla, adds noise, evaluates the LLG right
-// hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and performs the
-// stage update:
+// Input: the spin s, the exchange + constant field h in TESLA (sum_j J_ij s_j / mu_i + f_i / mu_i), three
+// N(0,1) draws, and in the corrector the Heun intermediate u.  Adds the uniaxial field and the noise,
+// evaluates the LLG right hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and
+// performs the stage update with the step folded into the class constants c_full = -gyro dt, c_half = -gyro dt/2:
 //   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
 //   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
 // unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
 template <int STAGE, bool THERMAL>
 __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
                                          double hx, double hy, double hz,
-                                         double n0, double n1, double n2, double dt, double half_dt,
+                                         double n0, double n1, double n2,
                                          double ux, double uy, double uz,
                                          double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
-  if (c.power != 0) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163)
+  if (c.power != 0) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163), here / mu
     const double d = c.ax * sx + c.ay * sy + c.az * sz;
     double pw = d;
     if (c.power >= 4) pw = d * d * d;
     if (c.power >= 6) pw = pw * d * d;
-    const double f = c.Kp * pw;
+    const double f = c.KpT * pw;
     hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
   }
-  hx += c.fx; hy += c.fy; hz += c.fz;  // Zeeman dc + ac cos(wt) + applied field, meV
-  hx *= c.inv_mu; hy *= c.inv_mu; hz *= c.inv_mu;  // Tesla  (cpu_llg_heun.cc:68-82)
-  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
+  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }  // cpu_llg_heun.cc:68-82
 
   const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;        // s x h
   const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;  // s x (s x h)
-  const double rx = c.mgyro * fma(c.alpha, bx_, ax_);
-  const double ry = c.mgyro * fma(c.alpha, by_, ay_);
-  const double rz = c.mgyro * fma(c.alpha, bz_, az_);
+  const double tx = fma(c.alpha, bx_, ax_), ty = fma(c.alpha, by_, ay_), tz = fma(c.alpha, bz_, az_);  // rhs / -gyro
 
   double px, py, pz;
   if (STAGE == 0) {
-    vx = fma(half_dt, rx, sx); vy = fma(half_dt, ry, sy); vz = fma(half_dt, rz, sz);
-    px = fma(dt, rx, sx); py = fma(dt, ry, sy); pz = fma(dt, rz, sz);
+    vx = fma(c.c_half, tx, sx); vy = fma(c.c_half, ty, sy); vz = fma(c.c_half, tz, sz);
+    px = fma(c.c_full, tx, sx); py = fma(c.c_full, ty, sy); pz = fma(c.c_full, tz, sz);
   } else {
-    px = fma(half_dt, rx, ux); py = fma(half_dt, ry, uy); pz = fma(half_dt, rz, uz);
+    px = fma(c.c_half, tx, ux); py = fma(c.c_half, ty, uy); pz = fma(c.c_half, tz, uz);
   }
   const double n2_ = px * px + py * py + pz * pz;
   // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged.  rsqrt() is CUDA's IEEE-accurate

@@ -48,13 +48,16 @@ struct JbGeom {
 struct JbClass {
   double inv_mu;      // 1 / mu_i
   double mu;          // mu_i (for applied field and magnetisation)
-  double mgyro;       // -gyro_i
+  double c_full;      // -gyro_i * dt      (set per jb_step)
+  double c_half;      // -gyro_i * dt / 2
   double alpha;
   double sigma;       // sqrt(2 kB alpha / (mu gyro dt [1+alpha^2])) * sqrt(T)   (set per jb_step)
-  double Kp;          // K_i * power
-  double K;           // K_i
+  double Kp;          // K_i * power, meV
+  double K;           // K_i, meV
+  double KpT;         // K_i * power / mu_i, Tesla
   double ax, ay, az;  // anisotropy axis
   double fx, fy, fz;  // constant field of this stage, meV: dc + ac*cos(omega t) + mu*B_applied
+  double fTx, fTy, fTz;  // the same divided by mu_i, Tesla
   int power;          // 0 = no uniaxial term
   int pad;
 };
@@ -88,7 +91,6 @@ struct JbStageParams {
   double *out_lo[3];     // box that receives the images of my low-x boundary planes (own box, a peer's, or null)
   double *out_hi[3];     // ... of my high-x boundary planes
   double *u[3];          // Heun intermediate u = s_n + dt/2 k1 (written in A, read in B), interior only used
-  double dt, half_dt;
   unsigned long long seed, step;
   int thermal;
 };
@@ -102,10 +104,10 @@ struct JbStageParams {
 #define JB_TILE_MAX_CLASSES 8
 #define JB_TILE_MAX_MOTIF 16
 #define JB_TILE_MAX_GX 3
-struct JbTileNbr {
+struct __align__(16) JbTileNbr {
   int delta;   // offset inside a plane of the smem tile: (dy*M + (mj - mi))*BZ + dz
-  int jidx;    // index into the table of unique tensors (anisotropic exchange only)
-  double J;    // scalar coupling, meV
+  int d;       // dx + gx: which of the 2 gx + 1 resident planes
+  double J;    // scalar coupling divided by mu of the owning motif site: Tesla
 };
 struct JbTileParams {
   JbGeom g;
@@ -113,20 +115,23 @@ struct JbTileParams {
   double *out_lo[3];     // box that receives the images of my low-x boundary planes (own box, a peer's, or null)
   double *out_hi[3];
   double *u[3];          // Heun intermediate, written by stage A with plain stores (stage B reads it through TMA)
-  const double *Jtab;    // n_unique x 9 (anisotropic exchange only)
-  double dt, half_dt;
-  unsigned long long seed, step;
+  const double *J9T;     // n_nbr x 9: tensor of every template entry divided by mu_i, Tesla (anisotropic exchange only)
+  unsigned long long step;
+  unsigned int rk[20];   // Philox4x32-10 round keys of the seed (k0 + r W0, k1 + r W1)
   int TY, TZ, UZ;        // tile extent in y, z; UZ = inner extent of the U box (= BZ, see choose_tiling)
   int BY, BZ;            // tile + halo extent (BZ even)
   int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
   int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
   int u_tma;             // stage B: u arrives through the TMA ring (1) or by plain global loads (0)
+  int producer_sleep_ns; // back-off of the producer thread while a slot is still in use (0 = poll)
+  int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
+  int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
   int n_yt, n_zt, n_cols, n_chunks, n_items;
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
-  int nbr_begin[JB_TILE_MAX_MOTIF * (2 * JB_TILE_MAX_GX + 1) + 1];  // [m][dx + gx] -> first entry of nbr[]
-  int class_of_motif[JB_TILE_MAX_MOTIF];
-  JbClass cls[JB_TILE_MAX_CLASSES];
+  int nbr_begin[JB_TILE_MAX_MOTIF + 1];  // [m] -> first entry of nbr[]
+  JbClass cls[JB_TILE_MAX_MOTIF];   // constants of motif site m (already resolved through class_of_motif): for M == 1 a
+                                     // compile-time offset, i.e. constant-bank operands of the fp64 instructions
 };
 
 struct jb_ctx {
@@ -159,7 +164,7 @@ struct jb_ctx {
   bool classes_dirty = true;
   std::vector<double> class_sig;            // what the device class table currently encodes
   std::vector<JbClass> h_classes;          // without sigma / f (filled per launch)
-  std::vector<int> h_class_omega_id;       // index into per-class ac data
+  std::vector<double> h_class_gyro;        // gyro of every class
   std::vector<double> h_class_dc, h_class_ac, h_class_omega;  // per class x3 / x3 / x1
   std::vector<unsigned char> h_site_class; // interior [x][y][m][z] order
   bool motif_uniform = true;
@@ -189,6 +194,7 @@ struct jb_ctx {
   std::vector<JbClass> h_class_tab;         // host copy of the class table(s) last uploaded (parameter bank of the tile kernel)
   std::vector<JbTileNbr> tile_nbr;
   JbTileNbr *d_tile_nbr = nullptr;
+  double *d_tile_J9T = nullptr;
   std::vector<int> tile_nbr_begin;
   int num_sms = 0;
 
@@ -208,7 +214,8 @@ struct jb_ctx {
   // options
   int opt_kernel = 1;      // 0 = direct global gathers, 1 = persistent TMA tile kernel
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
-  int opt_u_tma = 1;
+  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 1, opt_verbose = 0;
+  int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
   int opt_time_kernels = 0;
 
   // halo peers
@@ -234,9 +241,9 @@ cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos,
 cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream);
 cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
 // persistent TMA tile kernel: tmaps = {S.x, S.y, S.z, U.x, U.y, U.z}; spt in {1,2,4}; grid = number of CTAs
+// `threads` counts the consumer threads; the launch adds one producer warp
 cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
-cudaError_t jbk_stage_tile_smem_bytes(const JbTileParams &p, int stage, size_t *bytes);
 cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,

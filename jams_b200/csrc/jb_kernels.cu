@@ -145,13 +145,14 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
     }
   }
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
-  const JbClass c = p.t.classes[ci];
+  const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
   if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
-  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, fma(hx, c.inv_mu, c.fTx), fma(hy, c.inv_mu, c.fTy), fma(hz, c.inv_mu, c.fTz), n0, n1, n2,
+                           ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
   store_with_images(p, x, y, m, z, ox, oy, oz);
 }
@@ -189,13 +190,14 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
     }
   }
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
-  const JbClass c = p.t.classes[ci];
+  const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
   if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
-  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, p.dt, p.half_dt, ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, fma(hx, c.inv_mu, c.fTx), fma(hy, c.inv_mu, c.fTy), fma(hz, c.inv_mu, c.fTz), n0, n1, n2,
+                           ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
   p.out[0][ic] = ox; p.out[1][ic] = oy; p.out[2][ic] = oz;
 }

@@ -16,8 +16,12 @@
 //    (cp.async.bulk.tensor) landing in a ring of R shared-memory slots, completion signalled on an mbarrier per
 //    slot.  The plane stream continues across item boundaries, so the pipeline never drains.  In stage B the
 //    Heun intermediate u of the centre plane arrives the same way in a second, shallower ring.
-//  * Each thread owns SPT y-sites x M motif sites of one z column; the exchange template, coupling constants
-//    and material classes are read from the kernel-parameter bank with uniform indices (no per-thread loads).
+//  * Warp specialisation: the last warp of the CTA is the TMA producer; the other warps are consumers and never
+//    meet at a CTA-wide barrier.  A "full" mbarrier per slot carries the TMA transaction count, an "empty"
+//    mbarrier per slot collects one arrival per consumer warp when the slot's plane is no longer needed.
+//  * Each consumer thread owns SPT y-sites x M motif sites of one z column.  The exchange template (16 B per
+//    entry, coupling already divided by mu) sits in shared memory, the class constants and Philox round keys
+//    in the kernel-parameter bank: no per-site global loads besides the spins themselves.
 //  * Results go straight from registers to global memory (256 B per warp and component); sites within a ghost
 //    depth of a face also store their periodic / neighbour-slab images (peer memory over NVLink).
 #include <cuda.h>
@@ -37,9 +41,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// wait with back-off: a polling loop would steal issue slots from the warps that have work
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
   uint32_t ok = 0;
-  while (!ok) {
+  for (;;) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -47,7 +52,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (ok) break;
+    if (ns) __nanosleep(ns);
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
@@ -68,93 +78,93 @@ __device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
   return it;
 }
 
-#define JB_TILE_BARS 8
+#define JB_TILE_BARS 8   // max ring depth; barrier block = {fullS, emptyS, fullU, emptyU} x JB_TILE_BARS
 
-template <int STAGE, bool THERMAL, bool ISO, int SPT>
-__global__ void __launch_bounds__(512) stage_tile_kernel(const __grid_constant__ CUtensorMap tS0,
-                                                         const __grid_constant__ CUtensorMap tS1,
-                                                         const __grid_constant__ CUtensorMap tS2,
-                                                         const __grid_constant__ CUtensorMap tU0,
-                                                         const __grid_constant__ CUtensorMap tU1,
-                                                         const __grid_constant__ CUtensorMap tU2,
-                                                         const __grid_constant__ JbTileParams p) {
+// MOTIF1: the lattice has one motif site (M == 1): no motif loop, class constants through the uniform datapath
+template <int STAGE, bool THERMAL, bool ISO, int SPT, bool MOTIF1>
+__global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_tile_kernel(const __grid_constant__ CUtensorMap tS0,
+                                                            const __grid_constant__ CUtensorMap tS1,
+                                                            const __grid_constant__ CUtensorMap tS2,
+                                                            const __grid_constant__ CUtensorMap tU0,
+                                                            const __grid_constant__ CUtensorMap tU1,
+                                                            const __grid_constant__ CUtensorMap tU2,
+                                                            const __grid_constant__ JbTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const JbGeom &g = p.g;
-  const int M = g.M, gx = g.gx, nd = 2 * g.gx + 1;
+  const int M = MOTIF1 ? 1 : g.M, gx = g.gx;
   const int R = p.R, RU = p.RU;
   const int slotS = p.slotS, slotU = p.slotU;
+  const bool use_u = (STAGE == 1) && p.u_tma;
   double *ringS = reinterpret_cast<double *>(smem_raw);
   double *ringU = ringS + (size_t)R * 3 * slotS;
-  unsigned long long *barS = reinterpret_cast<unsigned long long *>(ringU + ((STAGE == 1 && p.u_tma) ? (size_t)RU * 3 * slotU : 0));
-  unsigned long long *barU = barS + JB_TILE_BARS;
-  JbTileNbr *s_nbr = reinterpret_cast<JbTileNbr *>(barU + JB_TILE_BARS);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringU + (use_u ? (size_t)RU * 3 * slotU : 0));
+  unsigned long long *fullS = bars, *emptyS = bars + JB_TILE_BARS, *fullU = bars + 2 * JB_TILE_BARS, *emptyU = bars + 3 * JB_TILE_BARS;
+  JbTileNbr *s_nbr = reinterpret_cast<JbTileNbr *>(bars + 4 * JB_TILE_BARS);
 
   const int tid = threadIdx.x;
+  const int n_cw = (blockDim.x >> 5) - 1;          // consumer warps; warp n_cw is the producer
   const int G = gridDim.x, bid = blockIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) mbar_init(smem_u32(&barS[s]), 1);
-    if (STAGE == 1) for (int s = 0; s < JB_TILE_BARS; ++s) mbar_init(smem_u32(&barU[s]), 1);
+    for (int s = 0; s < JB_TILE_BARS; ++s) {
+      mbar_init(smem_u32(&fullS[s]), 1); mbar_init(smem_u32(&emptyS[s]), n_cw);
+      mbar_init(smem_u32(&fullU[s]), 1); mbar_init(smem_u32(&emptyU[s]), n_cw);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int n = tid; n < p.n_nbr; n += blockDim.x) s_nbr[n] = p.nbr[n];
   __syncthreads();
 
-  // ---- producer (thread 0): the stream of S planes (and U planes) of this CTA's items ------------------
-  const uint32_t bytesS = (uint32_t)(p.BY * M * p.BZ * sizeof(double));
-  const uint32_t bytesU = (uint32_t)(p.TY * M * p.UZ * sizeof(double));   // UZ = BZ: see jb_capi.cu choose_tiling
-  int ps_item = bid, ps_j = 0, ps_slot = 0, issuedS = 0;
-  int pu_item = bid, pu_i = 0, pu_slot = 0, issuedU = 0;
-  ItemGeom ps_g = item_geom(p, bid < p.n_items ? bid : 0), pu_g = ps_g;
-  int freedS = 0, freedU = 0;
-
-  auto produce = [&]() {
-    while (issuedS < freedS + R && ps_item < p.n_items) {
-      const uint32_t bar = smem_u32(&barS[ps_slot]);
-      double *dst = ringS + (size_t)ps_slot * 3 * slotS;
-      mbar_expect_tx(bar, 3 * bytesS);
-      tma_load_3d(smem_u32(dst), &tS0, ps_g.z0, ps_g.y0 * M, ps_g.x0 + ps_j, bar);
-      tma_load_3d(smem_u32(dst + slotS), &tS1, ps_g.z0, ps_g.y0 * M, ps_g.x0 + ps_j, bar);
-      tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, ps_g.z0, ps_g.y0 * M, ps_g.x0 + ps_j, bar);
-      ps_slot = (ps_slot + 1 == R) ? 0 : ps_slot + 1;
-      ++issuedS;
-      if (++ps_j == ps_g.xc + 2 * gx) {
-        ps_j = 0; ps_item += G;
-        if (ps_item < p.n_items) ps_g = item_geom(p, ps_item);
-      }
-    }
-    if (STAGE == 1 && p.u_tma) {
-      while (issuedU < freedU + RU && pu_item < p.n_items) {
-        const uint32_t bar = smem_u32(&barU[pu_slot]);
-        double *dst = ringU + (size_t)pu_slot * 3 * slotU;
-        mbar_expect_tx(bar, 3 * bytesU);
-        const int c0 = pu_g.z0, c1 = (pu_g.y0 + g.gy) * M, c2 = pu_g.x0 + pu_i + gx;  // inner start kept 16-byte aligned
-        tma_load_3d(smem_u32(dst), &tU0, c0, c1, c2, bar);
-        tma_load_3d(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar);
-        tma_load_3d(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar);
-        pu_slot = (pu_slot + 1 == RU) ? 0 : pu_slot + 1;
-        ++issuedU;
-        if (++pu_i == pu_g.xc) {
-          pu_i = 0; pu_item += G;
-          if (pu_item < p.n_items) pu_g = item_geom(p, pu_item);
+  // =========================== producer warp: the stream of S planes and u planes ===========================
+  if ((tid >> 5) == n_cw) {
+    if ((tid & 31) != 0) return;
+    const uint32_t bytesS = (uint32_t)(p.BY * M * p.BZ * sizeof(double));
+    const uint32_t bytesU = (uint32_t)(p.TY * M * p.UZ * sizeof(double));   // UZ = BZ: see jb_capi.cu choose_tiling
+    int slot = 0, uslot = 0;
+    uint32_t pe = 0xffffffffu, pue = 0xffffffffu;   // parity to wait for on each empty barrier (first pass: passes at once)
+    for (int item = bid; item < p.n_items; item += G) {
+      const ItemGeom it = item_geom(p, item);
+      const int np = it.xc + 2 * gx;
+      for (int j = 0; j < np; ++j) {
+        {
+          mbar_wait_backoff(smem_u32(&emptyS[slot]), (pe >> slot) & 1u, p.producer_sleep_ns);
+          pe ^= 1u << slot;
+          const uint32_t bar = smem_u32(&fullS[slot]);
+          double *dst = ringS + (size_t)slot * 3 * slotS;
+          mbar_expect_tx(bar, 3 * bytesS);
+          tma_load_3d(smem_u32(dst), &tS0, it.z0, it.y0 * M, it.x0 + j, bar);
+          tma_load_3d(smem_u32(dst + slotS), &tS1, it.z0, it.y0 * M, it.x0 + j, bar);
+          tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, it.z0, it.y0 * M, it.x0 + j, bar);
+          slot = (slot + 1 == R) ? 0 : slot + 1;
+        }
+        if (use_u && j >= 2 * gx) {   // the u plane of step i = j - 2 gx is needed together with S plane j
+          mbar_wait_backoff(smem_u32(&emptyU[uslot]), (pue >> uslot) & 1u, p.producer_sleep_ns);
+          pue ^= 1u << uslot;
+          const uint32_t bar = smem_u32(&fullU[uslot]);
+          double *dst = ringU + (size_t)uslot * 3 * slotU;
+          mbar_expect_tx(bar, 3 * bytesU);
+          const int c0 = it.z0, c1 = (it.y0 + g.gy) * M, c2 = it.x0 + (j - 2 * gx) + gx;  // inner start kept 16-byte aligned
+          tma_load_3d(smem_u32(dst), &tU0, c0, c1, c2, bar);
+          tma_load_3d(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar);
+          tma_load_3d(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar);
+          uslot = (uslot + 1 == RU) ? 0 : uslot + 1;
         }
       }
     }
-  };
-  if (tid == 0) produce();
+    return;
+  }
 
-  // ---- consumer: every thread owns SPT y-sites x M motif sites of one z column of the tile ---------------
+  // =========================== consumers: SPT y-sites x M motif sites of one z column each ===========================
   const int tz = tid % p.TZ, tyg = tid / p.TZ;
-  const int ty0 = tyg * SPT;
+  const bool padding = tyg * SPT >= p.TY;            // threads that only fill up the last consumer warp
+  const int ty0 = padding ? 0 : tyg * SPT;
   const int soff = ((ty0 + g.gy) * M) * p.BZ + tz + g.gz;   // centre of (k = 0, m = 0) inside a slot component
   const int uoff = (ty0 * M) * p.UZ + tz + g.gz;
   const int kS = M * p.BZ, kU = M * p.UZ, kG = M * g.PZ;    // strides between the thread's consecutive y sites
-  const unsigned long long kSite = (unsigned long long)g.Nz * M;
+  const unsigned int kSite = (unsigned int)g.Nz * M;
   const unsigned long long planeSites = (unsigned long long)g.Ny * g.Nz * M;
-
-  JbOutBoxes boxes;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { boxes.out[c] = p.out[c]; boxes.out_lo[c] = p.out_lo[c]; boxes.out_hi[c] = p.out_hi[c]; }
+  const bool lane0 = (tid & 31) == 0;
+  const int slot3 = 3 * slotS;
 
   int cslotS = 0, cslotU = 0;
   uint32_t phS = 0, phU = 0;
@@ -163,63 +173,70 @@ __global__ void __launch_bounds__(512) stage_tile_kernel(const __grid_constant__
   for (int item = bid; item < p.n_items; item += G) {
     const ItemGeom it = item_geom(p, item);
     const int z = it.z0 + tz;
-    bool ok[SPT], img[SPT];
+    unsigned okm = 0, imgm = 0;
 #pragma unroll
     for (int k = 0; k < SPT; ++k) {
       const int y = it.y0 + ty0 + k;
-      ok[k] = (ty0 + k < p.TY) && (y < g.Ny) && (z < g.Nz);
-      img[k] = yz_image_needed(g, y, z);
+      if (!padding && (ty0 + k < p.TY) && (y < g.Ny) && (z < g.Nz)) okm |= 1u << k;
+      if (yz_image_needed(g, y, z)) imgm |= 1u << k;
     }
     int ic = (int)gidx(g, it.x0 + gx, it.y0 + ty0 + g.gy, 0, z + g.gz);   // g.elems < 2^31 (jb_capi.cu allocate_state)
     unsigned long long gs = global_site(g, it.x0, it.y0 + ty0, 0, z);
 
     for (int j = 0; j < 2 * gx; ++j) {
       const int s = wrapS(cslotS + j);
-      mbar_wait(smem_u32(&barS[s]), (phS >> s) & 1u);
+      mbar_wait_backoff(smem_u32(&fullS[s]), (phS >> s) & 1u, 40);
       phS ^= 1u << s;
     }
 
     for (int i = 0; i < it.xc; ++i) {
-      {
+      bool newest_ready = false;   // has this thread waited for S plane i + 2 gx yet?
+      auto wait_newest = [&]() {
         const int s = wrapS(cslotS + 2 * gx);
-        mbar_wait(smem_u32(&barS[s]), (phS >> s) & 1u);
+        mbar_wait_backoff(smem_u32(&fullS[s]), (phS >> s) & 1u, 20);
         phS ^= 1u << s;
-      }
-      if (STAGE == 1 && p.u_tma) {
-        mbar_wait(smem_u32(&barU[cslotU]), (phU >> cslotU) & 1u);
+        newest_ready = true;
+      };
+      if (!p.split_wait) wait_newest();
+      if (use_u) {
+        mbar_wait_backoff(smem_u32(&fullU[cslotU]), (phU >> cslotU) & 1u, 40);
         phU ^= 1u << cslotU;
       }
       const int x = it.x0 + i;
       const bool xb = x_image_needed(g, x);
-      const double *cplane = ringS + (size_t)wrapS(cslotS + gx) * 3 * slotS + soff;
       const double *uplane = ringU + (size_t)cslotU * 3 * slotU + uoff;
 
+#pragma unroll 1
       for (int m = 0; m < M; ++m) {
+        const JbClass &c = p.cls[MOTIF1 ? 0 : m];
+        const double *base = ringS + soff + m * p.BZ;
+        const double *cplane = base + wrapS(cslotS + gx) * slot3;
         double sx[SPT], sy[SPT], sz[SPT], hx[SPT], hy[SPT], hz[SPT];
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
-          const double *cp = cplane + m * p.BZ + k * kS;
+          const double *cp = cplane + k * kS;
           sx[k] = cp[0]; sy[k] = cp[slotS]; sz[k] = cp[2 * slotS];
-          hx[k] = 0.0; hy[k] = 0.0; hz[k] = 0.0;
+          hx[k] = c.fTx; hy[k] = c.fTy; hz[k] = c.fTz;   // constant field (Zeeman dc + ac cos wt + applied), Tesla
         }
-        // exchange field: entries are grouped by dx, inside a group in the reference's CSR column order
-        // (ascending neighbour site id, interface/sparse_blas.h:22-25)
-        for (int d = 0; d < nd; ++d) {
-          const double *pl = ringS + (size_t)wrapS(cslotS + d) * 3 * slotS + soff + m * p.BZ;
-          const int nb = p.nbr_begin[m * nd + d], ne = p.nbr_begin[m * nd + d + 1];
-          for (int n = nb; n < ne; ++n) {
-            const JbTileNbr e = s_nbr[n];
-            const double *q = pl + e.delta;
+        // exchange field in Tesla; entries in the reference's CSR column order (interface/sparse_blas.h:22-25)
+        const int nb = p.nbr_begin[MOTIF1 ? 0 : m], ne = p.nbr_begin[(MOTIF1 ? 0 : m) + 1];
+        const int nsplit = newest_ready ? nb : p.nbr_split[MOTIF1 ? 0 : m];   // entries [nsplit, ne) read the newest plane
+        auto gather = [&](int n0, int n1) {
+#pragma unroll 2
+          for (int n = n0; n < n1; ++n) {
+            const int4 raw = *reinterpret_cast<const int4 *>(&s_nbr[n]);   // one LDS.128: {delta, d, J}
+            struct { int delta, d; double J; } e = {raw.x, raw.y, __hiloint2double(raw.w, raw.z)};
+            const int t = cslotS + e.d - R;
+            const double *q = base + (t < 0 ? t + R : t) * slot3 + e.delta;
             if (ISO) {
-              const double J = e.J;
 #pragma unroll
               for (int k = 0; k < SPT; ++k) {
-                hx[k] = fma(J, q[k * kS], hx[k]);
-                hy[k] = fma(J, q[slotS + k * kS], hy[k]);
-                hz[k] = fma(J, q[2 * slotS + k * kS], hz[k]);
+                hx[k] = fma(e.J, q[k * kS], hx[k]);
+                hy[k] = fma(e.J, q[slotS + k * kS], hy[k]);
+                hz[k] = fma(e.J, q[2 * slotS + k * kS], hz[k]);
               }
             } else {
-              const double *__restrict__ J = p.Jtab + 9 * e.jidx;
+              const double *__restrict__ J = p.J9T + 9 * n;
               const double J0 = J[0], J1 = J[1], J2 = J[2], J3 = J[3], J4 = J[4], J5 = J[5], J6 = J[6], J7 = J[7], J8 = J[8];
 #pragma unroll
               for (int k = 0; k < SPT; ++k) {
@@ -230,15 +247,17 @@ __global__ void __launch_bounds__(512) stage_tile_kernel(const __grid_constant__
               }
             }
           }
-        }
-        const JbClass &c = p.cls[p.class_of_motif[m]];
+        };
+        gather(nb, nsplit);
+        if (!newest_ready) wait_newest();
+        gather(nsplit, ne);
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
-          if (!ok[k]) continue;
+          if (!((okm >> k) & 1u)) continue;
           double n0 = 0, n1 = 0, n2 = 0;
-          if (THERMAL) site_normals(p.seed, p.step, gs + k * kSite + m, n0, n1, n2);
-          double ux = 0, uy = 0, uz = 0;
+          if (THERMAL) site_normals_rk(p.rk, p.step, gs + k * kSite + m, n0, n1, n2);
           const int idx = ic + m * g.PZ + k * kG;
+          double ux = 0, uy = 0, uz = 0;
           if (STAGE == 1) {
             if (p.u_tma) {
               const double *up = uplane + m * p.UZ + k * kU;
@@ -248,30 +267,40 @@ __global__ void __launch_bounds__(512) stage_tile_kernel(const __grid_constant__
             }
           }
           double ox, oy, oz, vx, vy, vz;
-          llg_site<STAGE, THERMAL>(c, sx[k], sy[k], sz[k], hx[k], hy[k], hz[k], n0, n1, n2, p.dt, p.half_dt, ux, uy, uz,
-                                   ox, oy, oz, vx, vy, vz);
+          llg_site<STAGE, THERMAL>(c, sx[k], sy[k], sz[k], hx[k], hy[k], hz[k], n0, n1, n2, ux, uy, uz, ox, oy, oz, vx, vy, vz);
           if (STAGE == 0) { p.u[0][idx] = vx; p.u[1][idx] = vy; p.u[2][idx] = vz; }
           p.out[0][idx] = ox; p.out[1][idx] = oy; p.out[2][idx] = oz;
-          if (img[k] | xb) store_images(g, boxes, x, it.y0 + ty0 + k, m, z, ox, oy, oz);
+          if (((imgm >> k) & 1u) | xb) {
+            JbOutBoxes boxes;
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) { boxes.out[cc] = p.out[cc]; boxes.out_lo[cc] = p.out_lo[cc]; boxes.out_hi[cc] = p.out_hi[cc]; }
+            store_images(g, boxes, x, it.y0 + ty0 + k, m, z, ox, oy, oz);
+          }
         }
       }
-      __syncthreads();  // every thread is done with the oldest S plane and the U plane: their slots can be refilled
+      // this warp is done with the oldest S plane (and the u plane): one arrival per warp on their empty barriers
+      __syncwarp();
+      if (lane0) {
+        mbar_arrive(smem_u32(&emptyS[cslotS]));
+        if (i == it.xc - 1) for (int j = 1; j <= 2 * gx; ++j) mbar_arrive(smem_u32(&emptyS[wrapS(cslotS + j)]));
+        if (use_u) mbar_arrive(smem_u32(&emptyU[cslotU]));
+      }
       cslotS = wrapS(cslotS + 1);
-      ++freedS;
-      if (i == it.xc - 1) { cslotS = wrapS(cslotS + 2 * gx); freedS += 2 * gx; }
-      if (STAGE == 1) { cslotU = (cslotU + 1 == RU) ? 0 : cslotU + 1; ++freedU; }
+      if (i == it.xc - 1) cslotS = wrapS(cslotS + 2 * gx);
+      if (use_u) cslotU = (cslotU + 1 == RU) ? 0 : cslotU + 1;
       ic += (int)g.sX;
       gs += planeSites;
-      if (tid == 0) produce();
     }
   }
 }
 
 template <typename F>
-cudaError_t with_kernel(int stage, int thermal, int iso, int spt, F &&f) {
-#define JB_TILE_CASE(ST, TH, IS, SP) \
-  if (stage == ST && thermal == TH && iso == IS && spt == SP) return f(stage_tile_kernel<ST, (TH != 0), (IS != 0), SP>);
-#define JB_TILE_CASES_SPT(ST, TH, IS) JB_TILE_CASE(ST, TH, IS, 1) JB_TILE_CASE(ST, TH, IS, 2) JB_TILE_CASE(ST, TH, IS, 4)
+cudaError_t with_kernel(int stage, int thermal, int iso, int spt, int motif1, F &&f) {
+#define JB_TILE_CASE(ST, TH, IS, SP, M1) \
+  if (stage == ST && thermal == TH && iso == IS && spt == SP && motif1 == M1) \
+    return f(stage_tile_kernel<ST, (TH != 0), (IS != 0), SP, (M1 != 0)>);
+#define JB_TILE_CASES_SPT(ST, TH, IS) \
+  JB_TILE_CASE(ST, TH, IS, 1, 0) JB_TILE_CASE(ST, TH, IS, 2, 0) JB_TILE_CASE(ST, TH, IS, 1, 1) JB_TILE_CASE(ST, TH, IS, 2, 1)
   JB_TILE_CASES_SPT(0, 0, 0) JB_TILE_CASES_SPT(0, 0, 1) JB_TILE_CASES_SPT(0, 1, 0) JB_TILE_CASES_SPT(0, 1, 1)
   JB_TILE_CASES_SPT(1, 0, 0) JB_TILE_CASES_SPT(1, 0, 1) JB_TILE_CASES_SPT(1, 1, 0) JB_TILE_CASES_SPT(1, 1, 1)
 #undef JB_TILE_CASES_SPT
@@ -281,28 +310,23 @@ cudaError_t with_kernel(int stage, int thermal, int iso, int spt, F &&f) {
 
 }  // namespace
 
-cudaError_t jbk_stage_tile_smem_bytes(const JbTileParams &p, int stage, size_t *bytes) {
-  *bytes = ((size_t)p.R * 3 * p.slotS + ((stage == 1 && p.u_tma) ? (size_t)p.RU * 3 * p.slotU : 0)) * sizeof(double) +
-           2 * JB_TILE_BARS * sizeof(unsigned long long) + (size_t)p.n_nbr * sizeof(JbTileNbr) + 128;
-  return cudaSuccess;
-}
-
 cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
                                      size_t smem_bytes, int *blocks_per_sm) {
-  (void)p;
-  return with_kernel(stage, thermal, iso, spt, [&](auto k) -> cudaError_t {
+  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32, smem_bytes);
   });
 }
 
 cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int iso, int spt,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream) {
-  return with_kernel(stage, thermal, iso, spt, [&](auto k) -> cudaError_t {
+  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    k<<<grid, threads, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    err = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return err;
+    k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     return cudaGetLastError();
   });
 }

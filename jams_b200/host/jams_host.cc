@@ -1,0 +1,760 @@
+// jams_host.cc — see jams_host.h.  Setup-time logic only (integers, small float geometry, file formats); the
+// per-step numerics are in libjams_b200.so.  Citations are relative to /root/reference/src/jams/.
+#include "jams_host.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <random>
+#include <sstream>
+
+namespace jams_b200 {
+
+namespace {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPi = 2.0 * kPi;
+constexpr double kmRyd2meV = 13.605693123;
+constexpr double kBoltzmannIU = 0.0861733326;
+constexpr double kHBarIU = 0.6582119569;
+constexpr double kElectronGFactor = 2.0023193043625;
+constexpr double kGyroIU = kElectronGFactor * kBohrMagnetonIU / kHBarIU;   // helpers/consts.h:31
+
+std::string lowercase(std::string s) { for (auto &c : s) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c))); return s; }
+
+// ---- tolerant comparisons (helpers/maths.h:16-46) ----------------------------------------------------------
+bool approximately_equal(double a, double b, double eps) {
+  if (std::abs(a - b) <= eps) return true;
+  return std::abs(a - b) <= std::max(std::abs(a), std::abs(b)) * eps;
+}
+bool approximately_zero(double a, double eps) { return std::abs(a) <= eps; }
+bool definately_greater_than(double a, double b, double eps) { return (a - b) > std::max(std::abs(a), std::abs(b)) * eps; }
+bool definately_less_than(double a, double b, double eps) { return (b - a) > std::max(std::abs(a), std::abs(b)) * eps; }
+bool vec_approximately_equal(const Vec3 &a, const Vec3 &b, double eps) {
+  return approximately_equal(a[0], b[0], eps) && approximately_equal(a[1], b[1], eps) && approximately_equal(a[2], b[2], eps);
+}
+
+Vec3 matvec(const Mat3 &A, const Vec3 &v) {
+  return {{A[0][0] * v[0] + A[0][1] * v[1] + A[0][2] * v[2], A[1][0] * v[0] + A[1][1] * v[1] + A[1][2] * v[2],
+           A[2][0] * v[0] + A[2][1] * v[1] + A[2][2] * v[2]}};
+}
+Mat3 matmul(const Mat3 &A, const Mat3 &B) {
+  Mat3 C{};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
+  return C;
+}
+double dot(const Vec3 &a, const Vec3 &b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+Vec3 cross(const Vec3 &a, const Vec3 &b) { return {{a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]}}; }
+double norm(const Vec3 &a) { return std::sqrt(dot(a, a)); }
+Vec3 unit_vector(const Vec3 &a) {   // containers/vec3.h:276-283
+  const double n = norm(a);
+  if (n <= DBL_EPSILON) return a;
+  return {{a[0] / n, a[1] / n, a[2] / n}};
+}
+Mat3 identity() { return {{{{1, 0, 0}}, {{0, 1, 0}}, {{0, 0, 1}}}}; }
+
+Mat3 inverse(const Mat3 &m) {   // 3x3 cofactor inverse (the reference uses LAPACK dgetri, containers/mat3.h:233-262; results are
+                                // only used through 1e-4 tolerance snaps)
+  const double det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+                     m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  if (det == 0.0) throw std::runtime_error("unit cell matrix is singular");
+  Mat3 r{};
+  r[0][0] = (m[1][1] * m[2][2] - m[1][2] * m[2][1]) / det; r[0][1] = (m[0][2] * m[2][1] - m[0][1] * m[2][2]) / det; r[0][2] = (m[0][1] * m[1][2] - m[0][2] * m[1][1]) / det;
+  r[1][0] = (m[1][2] * m[2][0] - m[1][0] * m[2][2]) / det; r[1][1] = (m[0][0] * m[2][2] - m[0][2] * m[2][0]) / det; r[1][2] = (m[0][2] * m[1][0] - m[0][0] * m[1][2]) / det;
+  r[2][0] = (m[1][0] * m[2][1] - m[1][1] * m[2][0]) / det; r[2][1] = (m[0][1] * m[2][0] - m[0][0] * m[2][1]) / det; r[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) / det;
+  return r;
+}
+
+Vec3 read_vec3(const Setting &s) {
+  if (s.length() != 3) throw ConfigError("setting '" + s.name() + "' must have 3 components");
+  return {{s[0].as_double(), s[1].as_double(), s[2].as_double()}};
+}
+
+Vec3 normalise_fractional_coordinate(Vec3 r) {   // core/lattice.cc:48-64
+  for (int n = 0; n < 3; ++n) {
+    if (r[n] < 0.0) r[n] = r[n] + 1.0;
+    if (approximately_equal(r[n], 1.0, kLatticeTolerance)) r[n] = 0.0;
+  }
+  return r;
+}
+
+Vec3 lattice_translation_vector(const Vec3 &q, double tolerance) {   // core/interactions.cc:58-76
+  Vec3 T;
+  for (int n = 0; n < 3; ++n) {
+    const double nearest = std::nearbyint(q[n]);
+    T[n] = approximately_zero(q[n] - nearest, tolerance) ? nearest : std::floor(q[n]);
+  }
+  return T;
+}
+
+Mat3 rotation_matrix_between_vectors(const Vec3 &a, const Vec3 &b) {   // containers/mat3.h:334-366
+  auto ssc = [](const Vec3 &v) -> Mat3 { return {{{{0, -v[2], v[1]}}, {{v[2], 0, -v[0]}}, {{-v[1], v[0], 0}}}}; };
+  const Vec3 ua = unit_vector(a), ub = unit_vector(b);
+  const double c = dot(ua, ub);
+  Mat3 R = identity();
+  if (approximately_equal(c, 1.0, 1e-12)) return R;
+  if (approximately_equal(c, -1.0, 1e-12)) {
+    const Vec3 ortho = std::abs(ua[0]) < 0.9 ? Vec3{{1, 0, 0}} : Vec3{{0, 1, 0}};
+    const Mat3 vx = ssc(unit_vector(unit_vector(cross(ua, ortho))));
+    Mat3 k1 = vx;
+    for (auto &row : k1) for (auto &x : row) x *= (1.0 - std::cos(kPi));
+    const Mat3 vx2 = matmul(k1, vx);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] += std::sin(kPi) * vx[i][j] + vx2[i][j];
+    return R;
+  }
+  const Vec3 v = cross(ua, ub);
+  const double s = norm(v);
+  const Mat3 vx = ssc(v);
+  Mat3 kvx = vx;
+  const double k = (1.0 - c) / (s * s);
+  for (auto &row : kvx) for (auto &x : row) x *= k;
+  const Mat3 vx2 = matmul(kvx, vx);
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] += vx[i][j] + vx2[i][j];
+  return R;
+}
+
+std::vector<Mat3> cubic_point_group() {   // the 48 signed permutation matrices of O_h (fractional basis, zero translations)
+  std::vector<Mat3> rots;
+  int perm[3] = {0, 1, 2};
+  do {
+    for (int s0 = 0; s0 < 2; ++s0) for (int s1 = 0; s1 < 2; ++s1) for (int s2 = 0; s2 < 2; ++s2) {
+      const double sg[3] = {s0 ? -1.0 : 1.0, s1 ? -1.0 : 1.0, s2 ? -1.0 : 1.0};
+      Mat3 R{};
+      for (int r = 0; r < 3; ++r) R[r][perm[r]] = sg[r];
+      rots.push_back(R);
+    }
+  } while (std::next_permutation(perm, perm + 3));
+  return rots;
+}
+
+// jams::fmt::sci / decimal (helpers/output.h:32-42)
+std::ostream &fmt_sci(std::ostream &os) { return os << std::setprecision(8) << std::setw(16) << std::scientific << std::right; }
+std::ostream &fmt_decimal(std::ostream &os) { return os << std::setprecision(6) << std::setw(16) << std::fixed << std::right; }
+
+}  // namespace
+
+double energy_unit_conversion(const std::string &name) {
+  static const std::map<std::string, double> table = {
+      {"joules", kJoule2meV}, {"J", kJoule2meV}, {"milli_electron_volts", 1.0}, {"meV", 1.0}, {"milli_rydbergs", kmRyd2meV},
+      {"mRyd", kmRyd2meV}, {"rydbergs", kmRyd2meV * 1e3}, {"Ryd", kmRyd2meV * 1e3}, {"Kelvin", kBoltzmannIU}, {"K", kBoltzmannIU}};
+  auto it = table.find(name);
+  if (it == table.end()) throw std::runtime_error("energy units: " + name + " is not known");
+  return it->second;
+}
+
+// =====================================================================================================
+// Lattice
+// =====================================================================================================
+Lattice::Lattice(const Setting &config) {
+  // materials (core/lattice.cc:337-352, containers/material.h:28-60)
+  const Setting &mats = config.required("materials");
+  for (int i = 0; i < mats.length(); ++i) {
+    const Setting &cfg = mats[i];
+    Material m;
+    m.name = cfg.required("name").as_string();
+    m.moment = cfg.required("moment").as_double() * kBohrMagnetonIU;
+    m.gyro = cfg.get("gyro", 1.0) * kGyroIU;
+    m.alpha = cfg.get("alpha", 0.01);
+    if (const Setting *sp = cfg.find("spin")) {
+      if (sp->is_array()) {
+        if (sp->length() == 3) m.spin = read_vec3(*sp);
+        else if (sp->length() == 2) {
+          const double theta = (*sp)[0].as_double() * kPi / 180.0, phi = (*sp)[1].as_double() * kPi / 180.0;
+          m.spin = {{std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)}};
+        } else throw std::runtime_error("spin setting array is not length 2 or 3");
+      } else if (sp->is_string() && lowercase(sp->as_string()) == "random") {
+        m.randomize = true;
+      }
+    }
+    if (material_exists(m.name)) throw std::runtime_error("the material " + m.name + " is specified twice in the configuration");
+    materials.push_back(m);
+  }
+
+  // unit cell (core/lattice.cc:354-410)
+  const Setting &uc = config.required("unitcell");
+  const Setting &basis = uc.required("basis");
+  if (basis.length() != 3) throw ConfigError("unitcell.basis must be a 3x3 matrix");
+  for (int r = 0; r < 3; ++r) { const Vec3 row = read_vec3(basis[r]); for (int c = 0; c < 3; ++c) cell[r][c] = row[c]; }
+  lattice_parameter = uc.required("parameter").as_double();
+  if (lattice_parameter < 0.0) throw std::runtime_error("lattice parameter cannot be negative");
+  if (lattice_parameter == 0.0) throw std::runtime_error("lattice parameter cannot be zero");
+  cell_inv = inverse(cell);
+
+  // lattice (core/lattice.cc:411-427)
+  const Setting &lat = config.required("lattice");
+  const Setting &size = lat.required("size");
+  if (size.length() != 3) throw ConfigError("lattice.size must have 3 components");
+  for (int n = 0; n < 3; ++n) dims[n] = static_cast<int>(size[n].as_int());
+  if (const Setting *p = lat.find("periodic")) for (int n = 0; n < 3; ++n) periodic[n] = (*p)[n].as_bool();
+  if (lat.exists("impurities")) throw std::runtime_error("lattice.impurities is not supported by the llg-heun-b200-gpu host layer");
+  if (lat.exists("global_rotation") || lat.exists("orientation_axis")) throw std::runtime_error("lattice rotations are not supported by the llg-heun-b200-gpu host layer");
+
+  // motif (core/lattice.cc:286-310, 429-470)
+  const std::string fmt_name = uc.get("coordinate_format", "FRACTIONAL");
+  bool cartesian = false;
+  { std::string up = fmt_name; for (auto &c : up) c = static_cast<char>(std::toupper(static_cast<unsigned char>(c)));
+    if (up == "CARTESIAN") cartesian = true; else if (up != "FRACTIONAL") throw std::runtime_error("Unknown coordinate format for atom positions in unit cell"); }
+  const Setting &pos = uc.required("positions");
+  if (!pos.is_list()) throw std::runtime_error("unitcell.positions must be a list (position files are not supported here)");
+  for (int i = 0; i < pos.length(); ++i) {
+    const std::string mat = pos[i][0].as_string();
+    Vec3 p = read_vec3(pos[i][1]);
+    if (cartesian) p = matvec(cell_inv, p);
+    if (!material_exists(mat)) throw std::runtime_error("material " + mat + " in the motif is not defined in the configuration");
+    motif_material.push_back(material_index(mat));
+    motif_frac.push_back(normalise_fractional_coordinate(p));
+  }
+  M = static_cast<int>(motif_frac.size());
+  if (M < 1) throw std::runtime_error("unit cell has no motif positions");
+  const long long n = 1LL * dims[0] * dims[1] * dims[2] * M;
+  if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || n >= (1LL << 31)) throw std::runtime_error("invalid lattice size");
+  num_spins = static_cast<int>(n);
+
+  if (const Setting *solver = config.find("solver")) gilbert_prefactor = solver->get("gilbert_prefactor", false);   // core/lattice.cc:696-697
+  rotations = cubic_point_group();
+}
+
+int Lattice::material_index(const std::string &name) const {
+  for (size_t i = 0; i < materials.size(); ++i) if (materials[i].name == name) return static_cast<int>(i);
+  throw std::runtime_error("material " + name + " does not exist");
+}
+bool Lattice::material_exists(const std::string &name) const {
+  for (const auto &m : materials) if (m.name == name) return true;
+  return false;
+}
+
+std::vector<int32_t> Lattice::site_material() const {
+  std::vector<int32_t> v(num_spins);
+  for (int i = 0; i < num_spins; ++i) v[i] = motif_material[i % M];
+  return v;
+}
+std::vector<int32_t> Lattice::site_motif() const {
+  std::vector<int32_t> v(num_spins);
+  for (int i = 0; i < num_spins; ++i) v[i] = i % M;
+  return v;
+}
+std::vector<double> Lattice::mus() const {
+  std::vector<double> v(num_spins);
+  for (int i = 0; i < num_spins; ++i) v[i] = materials[motif_material[i % M]].moment;
+  return v;
+}
+std::vector<double> Lattice::alpha() const {
+  std::vector<double> v(num_spins);
+  for (int i = 0; i < num_spins; ++i) v[i] = materials[motif_material[i % M]].alpha;
+  return v;
+}
+std::vector<double> Lattice::gyro() const {   // core/lattice.cc:91-97,709-713
+  std::vector<double> v(num_spins);
+  for (int i = 0; i < num_spins; ++i) {
+    const Material &m = materials[motif_material[i % M]];
+    v[i] = gilbert_prefactor ? m.gyro / (1.0 + m.alpha * m.alpha) : m.gyro;
+  }
+  return v;
+}
+std::vector<double> Lattice::positions() const {   // core/lattice.cc:622-657,751-756
+  std::vector<double> p(3 * static_cast<size_t>(num_spins));
+  size_t s = 0;
+  for (int i = 0; i < dims[0]; ++i) for (int j = 0; j < dims[1]; ++j) for (int k = 0; k < dims[2]; ++k) for (int m = 0; m < M; ++m) {
+    const Vec3 f = {{motif_frac[m][0] + i, motif_frac[m][1] + j, motif_frac[m][2] + k}};
+    const Vec3 r = matvec(cell, f);
+    p[3 * s] = r[0]; p[3 * s + 1] = r[1]; p[3 * s + 2] = r[2];
+    ++s;
+  }
+  return p;
+}
+std::vector<double> Lattice::initial_spins(uint64_t seed) const {   // core/lattice.cc:703-733
+  std::vector<double> s(3 * static_cast<size_t>(num_spins));
+  std::mt19937_64 rng(seed);   // the reference seeds pcg32 from std::random_device here: "random" spins are unpinned by design
+  std::normal_distribution<double> nd;
+  for (int i = 0; i < num_spins; ++i) {
+    const Material &m = materials[motif_material[i % M]];
+    Vec3 spin = m.spin;
+    if (m.randomize) spin = {{nd(rng), nd(rng), nd(rng)}};
+    if (m.moment == 0.0) spin = {{0, 0, 0}};   // vacancies
+    spin = unit_vector(spin);
+    for (int n = 0; n < 3; ++n) s[3 * static_cast<size_t>(i) + n] = spin[n];
+  }
+  return s;
+}
+
+std::vector<Mat3> Lattice::point_group_of_motif(int m) const {   // core/lattice.cc:1127-1153
+  std::vector<Mat3> out;
+  for (const Mat3 &R : rotations) {
+    const Vec3 np = normalise_fractional_coordinate(matvec(R, motif_frac[m]));
+    if (vec_approximately_equal(motif_frac[m], np, kLatticeTolerance)) out.push_back(R);
+  }
+  return out;
+}
+
+InteractionTemplate Lattice::expand_interactions(const std::vector<InteractionInput> &interactions, double unit, bool fractional,
+                                                 bool use_symops, double energy_cutoff, double radius_cutoff,
+                                                 double distance_tolerance, double prefactor) const {
+  struct Entry { int mi, mj; Vec3 r; std::array<double, 9> J9; };
+  std::vector<Entry> entries;
+  for (const auto &in : interactions) {
+    Vec3 r = in.r;
+    if (fractional) r = matvec(cell, r);
+    if (in.by_motif) {
+      if (in.motif_i < 0 || in.motif_i >= M || in.motif_j < 0 || in.motif_j >= M) throw std::runtime_error("interaction motif position is invalid");
+      entries.push_back({in.motif_i, in.motif_j, r, in.J9});
+    } else {   // complete_interaction_unitcell_positions (core/interactions.cc:98-124)
+      const int ti = material_index(in.type_i), tj = material_index(in.type_j);
+      for (int i = 0; i < M; ++i) {
+        if (motif_material[i] != ti) continue;
+        const Vec3 qf = matvec(cell_inv, r);
+        const Vec3 q = {{qf[0] + motif_frac[i][0], qf[1] + motif_frac[i][1], qf[2] + motif_frac[i][2]}};
+        const Vec3 T = lattice_translation_vector(q, distance_tolerance);
+        const Vec3 offset = {{q[0] - T[0], q[1] - T[1], q[2] - T[2]}};
+        int partner = -1;
+        for (int k = 0; k < M; ++k) if (vec_approximately_equal(motif_frac[k], offset, distance_tolerance)) { partner = k; break; }
+        if (partner < 0 || motif_material[partner] != tj) continue;
+        entries.push_back({i, partner, r, in.J9});
+      }
+    }
+  }
+  if (use_symops) {   // apply_symops (core/interactions.cc:24-37) + generate_symmetric_points (core/lattice.cc:1015-1035)
+    std::vector<std::vector<Mat3>> groups(M);
+    for (int m = 0; m < M; ++m) groups[m] = point_group_of_motif(m);
+    std::vector<Entry> expanded;
+    for (const Entry &e : entries) {
+      const Vec3 rf = matvec(cell_inv, e.r);
+      std::vector<Vec3> pts{e.r};
+      for (const Mat3 &R : groups[e.mi]) {
+        const Vec3 rs = matvec(cell, matvec(R, rf));
+        bool seen = false;
+        for (const Vec3 &p : pts) if (vec_approximately_equal(rs, p, kLatticeTolerance)) { seen = true; break; }
+        if (!seen) pts.push_back(rs);
+      }
+      for (const Vec3 &p : pts) expanded.push_back({e.mi, e.mj, p, e.J9});
+    }
+    entries.swap(expanded);
+  }
+  auto max_abs = [](const std::array<double, 9> &J) { double m = 0; for (double x : J) m = std::max(m, std::abs(x)); return m; };
+  if (energy_cutoff > 0.0) {   // core/interactions.cc:322-326
+    std::vector<Entry> kept;
+    for (const Entry &e : entries) if (!definately_less_than(max_abs(e.J9), energy_cutoff, DBL_EPSILON)) kept.push_back(e);
+    entries.swap(kept);
+  }
+  if (radius_cutoff > 0.0) {   // :327-330
+    std::vector<Entry> kept;
+    for (const Entry &e : entries) if (!definately_greater_than(norm(e.r), radius_cutoff, kLatticeTolerance)) kept.push_back(e);
+    entries.swap(kept);
+  }
+  InteractionTemplate t;
+  for (const Entry &e : entries) {   // :333-345 and hamiltonian/exchange.cc:162-169
+    const Vec3 qf = matvec(cell_inv, e.r);
+    const Vec3 q = {{qf[0] + motif_frac[e.mi][0] - motif_frac[e.mj][0], qf[1] + motif_frac[e.mi][1] - motif_frac[e.mj][1],
+                     qf[2] + motif_frac[e.mi][2] - motif_frac[e.mj][2]}};
+    const Vec3 T = lattice_translation_vector(q, distance_tolerance);
+    std::array<double, 9> Jij;
+    for (int k = 0; k < 9; ++k) Jij[k] = prefactor * unit * e.J9[k];
+    if (!(max_abs(Jij) > energy_cutoff * unit)) continue;
+    t.mi.push_back(e.mi); t.mj.push_back(e.mj);
+    for (int k = 0; k < 3; ++k) t.T3.push_back(static_cast<int32_t>(T[k]));
+    t.J9.insert(t.J9.end(), Jij.begin(), Jij.end());
+  }
+  return t;
+}
+
+NeighbourList Lattice::neighbour_list(const InteractionTemplate &t) const {   // core/interactions.cc:349-395
+  struct Pair { int32_t i, j, entry; long long order; };
+  std::vector<Pair> pairs;
+  const int nt = t.size();
+  pairs.reserve(static_cast<size_t>(dims[0]) * dims[1] * dims[2] * nt);
+  long long order = 0;
+  for (int i = 0; i < dims[0]; ++i) for (int j = 0; j < dims[1]; ++j) for (int k = 0; k < dims[2]; ++k) {
+    for (int n = 0; n < nt; ++n, ++order) {
+      int c[3] = {i + t.T3[3 * n], j + t.T3[3 * n + 1], k + t.T3[3 * n + 2]};
+      bool ok = true;
+      for (int l = 0; l < 3; ++l) {   // Lattice::apply_boundary_conditions (core/lattice.cc:987-1007)
+        if (!periodic[l] && (c[l] < 0 || c[l] >= dims[l])) { ok = false; break; }
+        c[l] = (c[l] + dims[l]) % dims[l];
+      }
+      if (!ok) continue;
+      pairs.push_back({site_index(i, j, k, t.mi[n]), site_index(c[0], c[1], c[2], t.mj[n]), n, order});
+    }
+  }
+  // unique values in first-insertion order (containers/unordered_vector_set.h:38-45)
+  NeighbourList nl;
+  std::vector<int> value_of_entry(nt, -1);
+  {
+    std::vector<char> used(nt, 0);
+    std::vector<long long> first(nt, -1);
+    for (const Pair &p : pairs) if (first[p.entry] < 0) first[p.entry] = p.order;
+    std::vector<int> by_first;
+    for (int n = 0; n < nt; ++n) if (first[n] >= 0) by_first.push_back(n);
+    std::sort(by_first.begin(), by_first.end(), [&](int a, int b) { return first[a] < first[b]; });
+    for (int n : by_first) {
+      int found = -1;
+      for (size_t v = 0; v < nl.values9.size() / 9; ++v) if (std::memcmp(&nl.values9[9 * v], &t.J9[9 * static_cast<size_t>(n)], 9 * sizeof(double)) == 0) { found = static_cast<int>(v); break; }
+      if (found < 0) { found = static_cast<int>(nl.values9.size() / 9); nl.values9.insert(nl.values9.end(), t.J9.begin() + 9 * n, t.J9.begin() + 9 * n + 9); }
+      value_of_entry[n] = found;
+    }
+  }
+  std::sort(pairs.begin(), pairs.end(), [](const Pair &a, const Pair &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });   // jams::VectorSet keeps {i,j} sorted
+  for (size_t p = 1; p < pairs.size(); ++p)
+    if (pairs[p].i == pairs[p - 1].i && pairs[p].j == pairs[p - 1].j)
+      throw std::runtime_error("Multiple interactions for sites " + std::to_string(pairs[p].i) + " and " + std::to_string(pairs[p].j));   // :373-381
+  nl.i.reserve(pairs.size()); nl.j.reserve(pairs.size()); nl.value_id.reserve(pairs.size());
+  for (const Pair &p : pairs) { nl.i.push_back(p.i); nl.j.push_back(p.j); nl.value_id.push_back(value_of_entry[p.entry]); }
+  return nl;
+}
+
+// =====================================================================================================
+// Hamiltonians
+// =====================================================================================================
+Hamiltonian::Hamiltonian(const Setting &settings, const Lattice &lattice) : lattice_(lattice) {   // core/hamiltonian.cc:117-147
+  name_ = lowercase(settings.required("module").as_string());
+  input_energy_unit_name_ = settings.get("energy_units", "joules");   // helpers/defaults.h:25
+  if (settings.exists("unit_name")) input_energy_unit_name_ = settings.get("unit_name", "joules");
+  input_energy_unit_conversion_ = energy_unit_conversion(input_energy_unit_name_);
+}
+
+Hamiltonian *Hamiltonian::create(const Setting &settings, const Lattice &lattice) {   // core/hamiltonian.cc:80-115
+  const std::string module = lowercase(settings.required("module").as_string());
+  if (module == "exchange") return new ExchangeHamiltonian(settings, lattice);
+  if (module == "uniaxial") return new UniaxialAnisotropyHamiltonian(settings, lattice);
+  if (module == "zeeman") return new ZeemanHamiltonian(settings, lattice);
+  if (module == "applied-field") return new AppliedFieldHamiltonian(settings, lattice);
+  throw std::runtime_error("unknown hamiltonian " + module + " (not on the llg-heun-b200-gpu path)");
+}
+
+ExchangeHamiltonian::ExchangeHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
+  const bool use_symops = s.get("symops", true);
+  const double energy_cutoff = s.get("energy_cutoff", 0.0), radius_cutoff = s.get("radius_cutoff", 100.0);
+  const double distance_tolerance = s.get("distance_tolerance", kLatticeTolerance), prefactor = s.get("interaction_prefactor", 1.0);
+  const std::string coord = lowercase(s.get("coordinate_format", "cartesian"));
+  if (coord != "cartesian" && coord != "fractional") throw std::runtime_error("Unknown coordinate format for exchange interactions");
+  if (!s.exists("interactions")) {
+    if (s.exists("exc_file")) throw std::runtime_error("exc_file is not supported by this host layer yet: inline the table as 'interactions'");
+    throw std::runtime_error("'exc_file' or 'interactions' settings are required");
+  }
+  const Setting &list = s["interactions"];
+  if (!list.is_list() || list.length() < 1) throw std::runtime_error("exchange settings must be a list");
+  // discover_interaction_setting_format (core/interactions.cc:172-203)
+  if (list[0][0].is_number() != list[0][1].is_number()) throw std::runtime_error("interaction type format is incorrect");
+  const bool kkr = list[0][0].is_number();
+  if (!list[0][2].is_array()) throw std::runtime_error("interaction vector format is incorrect");
+  const bool scalar = list[0][3].is_number();
+  if (!scalar && !(list[0][3].is_array() && list[0][3].length() == 9)) throw std::runtime_error("interaction energy format is incorrect");
+  std::vector<InteractionInput> inputs;
+  for (int i = 0; i < list.length(); ++i) {   // interactions_from_settings (:254-289)
+    InteractionInput in;
+    in.by_motif = kkr;
+    if (kkr) { in.motif_i = static_cast<int>(list[i][0].as_int()) - 1; in.motif_j = static_cast<int>(list[i][1].as_int()) - 1; }
+    else { in.type_i = list[i][0].as_string(); in.type_j = list[i][1].as_string(); }
+    in.r = read_vec3(list[i][2]);
+    in.J9.fill(0.0);
+    if (scalar) { const double J = list[i][3].as_double(); in.J9[0] = in.J9[4] = in.J9[8] = J; }
+    else for (int k = 0; k < 9; ++k) in.J9[k] = list[i][3][k].as_double();
+    inputs.push_back(in);
+  }
+  template_ = lattice.expand_interactions(inputs, input_energy_unit_conversion_, coord == "fractional", use_symops, energy_cutoff,
+                                          radius_cutoff, distance_tolerance, prefactor);
+}
+
+UniaxialAnisotropyHamiltonian::UniaxialAnisotropyHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
+  for (const char *old : {"d2z", "d4z", "d6z", "K1", "K2", "K3"})
+    if (s.exists(old)) throw std::runtime_error("UniaxialHamiltonian: anisotropy should only be specified for a single K1, K2 or K3.");
+  const std::string order = s.required("order").as_string();
+  if (order == "K1") power_ = 2; else if (order == "K2") power_ = 4; else if (order == "K3") power_ = 6;
+  else throw std::runtime_error("Unsupported anisotropy: " + order);
+  const int N = lattice.num_spins;
+  magnitude_.assign(N, 0.0); axis_.assign(3 * static_cast<size_t>(N), 0.0);
+  const Setting &list = s.required("anisotropies");
+  for (int a = 0; a < list.length(); ++a) {   // hamiltonian/uniaxial_anisotropy.cc:40-70,89-114
+    const Setting &e = list[a];
+    int motif_position = -1, material = -1;
+    if (e[0].is_number()) {
+      motif_position = static_cast<int>(e[0].as_int()) - 1;
+      if (motif_position < 0 || motif_position >= lattice.M) throw std::runtime_error("uniaxial anisotropy motif position is invalid");
+    } else {
+      if (!lattice.material_exists(e[0].as_string())) throw std::runtime_error("uniaxial anisotropy material is invalid");
+      material = lattice.material_index(e[0].as_string());
+    }
+    Vec3 axis = read_vec3(e[1]);
+    const double n = norm(axis);
+    axis = {{axis[0] / n, axis[1] / n, axis[2] / n}};   // normalize()
+    const double energy = e[2].as_double();
+    for (int i = 0; i < N; ++i) {
+      if ((motif_position >= 0 && i % lattice.M == motif_position) || (material >= 0 && lattice.motif_material[i % lattice.M] == material)) {
+        magnitude_[i] = energy * input_energy_unit_conversion_;
+        for (int k = 0; k < 3; ++k) axis_[3 * static_cast<size_t>(i) + k] = axis[k];
+      }
+    }
+  }
+}
+
+ZeemanHamiltonian::ZeemanHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {   // hamiltonian/zeeman.cc:12-72
+  const int N = lattice.num_spins, nmat = static_cast<int>(lattice.materials.size());
+  const std::vector<double> mus = lattice.mus();
+  dc_local_field_.assign(3 * static_cast<size_t>(N), 0.0);
+  if (const Setting *dc = s.find("dc_local_field")) {
+    if (dc->length() != nmat) throw std::runtime_error("dc_local_field: field must be specified for every material");
+    for (int i = 0; i < N; ++i) for (int k = 0; k < 3; ++k)
+      dc_local_field_[3 * static_cast<size_t>(i) + k] = (*dc)[lattice.motif_material[i % lattice.M]][k].as_double() * mus[i];
+  }
+  if (s.exists("ac_local_field") || s.exists("ac_local_frequency")) {
+    if (!(s.exists("ac_local_field") && s.exists("ac_local_frequency"))) throw std::runtime_error("ac_local_field: must have a field and a frequency");
+    const Setting &f = s["ac_local_field"], &w = s["ac_local_frequency"];
+    if (w.length() != nmat || f.length() != nmat) throw std::runtime_error("ac_local_frequency: must be specified for every material");
+    has_ac_local_field_ = true;
+    ac_local_field_.assign(3 * static_cast<size_t>(N), 0.0); ac_local_frequency_.assign(N, 0.0);
+    for (int i = 0; i < N; ++i) {
+      const int mat = lattice.motif_material[i % lattice.M];
+      for (int k = 0; k < 3; ++k) ac_local_field_[3 * static_cast<size_t>(i) + k] = f[mat][k].as_double() * mus[i];
+      ac_local_frequency_[i] = kTwoPi * w[mat].as_double();
+    }
+  }
+}
+
+AppliedFieldHamiltonian::AppliedFieldHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
+  const std::string type = lowercase(s.get("type", "static"));
+  if (type != "static") throw std::runtime_error("Unknown field pulse type " + type + " (only 'static' is on the hot path)");
+  field_ = read_vec3(s.required("field"));
+}
+
+// =====================================================================================================
+// Physics, Monitors
+// =====================================================================================================
+Physics::Physics(const Setting *s) {   // core/physics.cc: temperature / applied_field of the `physics` group
+  if (!s) return;
+  const std::string module = lowercase(s->get("module", "empty"));
+  if (module != "empty") throw std::runtime_error("physics module '" + module + "' is not supported by the llg-heun-b200-gpu host layer");
+  temperature_ = s->get("temperature", 0.0);
+  if (const Setting *f = s->find("applied_field")) applied_field_ = read_vec3(*f);
+}
+
+Monitor::Monitor(const Setting &settings) { output_step_freq_ = settings.get("output_steps", 100); }
+
+Monitor *Monitor::create(const Setting &settings, const Lattice &lattice, const std::string &prefix) {   // core/monitor.cc
+  const std::string module = lowercase(settings.required("module").as_string());
+  if (module == "magnetisation") return new MagnetisationMonitor(settings, lattice, prefix + "mag.tsv");
+  if (module == "energy") return new EnergyMonitor(settings, prefix + "eng.tsv");
+  throw std::runtime_error("unknown monitor " + module + " (not supported by the llg-heun-b200-gpu host layer)");
+}
+
+MagnetisationMonitor::MagnetisationMonitor(const Setting &settings, const Lattice &lattice, const std::string &filename)
+    : Monitor(settings), lattice_(lattice), tsv_file_(filename) {
+  const std::string g = lowercase(settings.get("grouping", "materials"));
+  if (g == "none") { grouping_ = Grouping::NONE; n_groups_ = 1; }
+  else if (g == "materials") { grouping_ = Grouping::MATERIALS; n_groups_ = static_cast<int>(lattice.materials.size()); group_of_spin_ = lattice.site_material(); }
+  else if (g == "positions") { grouping_ = Grouping::POSITIONS; n_groups_ = lattice.M; group_of_spin_ = lattice.site_motif(); }
+  else throw std::runtime_error("unknown magnetisation grouping: " + g);
+  normalize_ = settings.get("normalize", true);
+  if (!tsv_file_) throw std::runtime_error("cannot open " + filename);
+  tsv_file_.setf(std::ios::right);
+  tsv_file_ << tsv_header();
+}
+
+std::string MagnetisationMonitor::tsv_header() const {   // monitors/magnetisation.cc:106-141
+  std::stringstream ss;
+  ss.width(12);
+  for (const char *h : {"time", "T", "hx", "hy", "hz"}) ss << fmt_sci << h;
+  if (grouping_ == Grouping::NONE) {
+    for (const char *n : {"mx", "my", "mz", "m"}) ss << fmt_decimal << n;
+  } else if (grouping_ == Grouping::MATERIALS) {
+    for (const auto &m : lattice_.materials) for (const char *suf : {"_mx", "_my", "_mz", "_m"}) ss << fmt_decimal << m.name + suf;
+  } else {
+    for (int i = 0; i < lattice_.M; ++i)
+      for (const char *suf : {"_mx", "_my", "_mz", "_m"}) ss << fmt_sci << std::to_string(i + 1) + "_" + lattice_.materials[lattice_.motif_material[i]].name + suf;
+  }
+  ss << std::endl;
+  return ss.str();
+}
+
+void MagnetisationMonitor::update(B200HeunLLGSolver &solver) {   // monitors/magnetisation.cc:77-104
+  std::vector<double> M4(4 * static_cast<size_t>(n_groups_));
+  solver.check(jb_magnetisation(solver.ctx(), n_groups_, group_of_spin_.empty() ? nullptr : group_of_spin_.data(), M4.data()));
+  tsv_file_.width(12);
+  tsv_file_ << fmt_sci << solver.time();
+  tsv_file_ << fmt_sci << solver.physics()->temperature();
+  for (int i = 0; i < 3; ++i) tsv_file_ << fmt_sci << solver.physics()->applied_field(i);
+  for (int n = 0; n < n_groups_; ++n) {
+    const double *m = &M4[4 * static_cast<size_t>(n)];
+    const double factor = normalize_ ? 1.0 / m[3] : 1.0 / kBohrMagnetonIU;
+    tsv_file_ << fmt_sci << m[0] * factor << fmt_sci << m[1] * factor << fmt_sci << m[2] * factor
+              << fmt_sci << std::sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) * factor;
+  }
+  tsv_file_ << std::endl;
+}
+
+EnergyMonitor::EnergyMonitor(const Setting &settings, const std::string &filename) : Monitor(settings), filename_(filename), tsv_file_(filename) {
+  if (!tsv_file_) throw std::runtime_error("cannot open " + filename);
+  tsv_file_.setf(std::ios::right);
+}
+
+void EnergyMonitor::update(B200HeunLLGSolver &solver) {   // monitors/energy.cc:22-46
+  if (!header_written_) {   // the reference writes the header in the constructor from globals::solver->hamiltonians()
+    std::stringstream ss;
+    ss.width(12);
+    ss << "time\t";
+    for (auto &h : solver.hamiltonians()) ss << h->name() << "_E_meV\t";
+    ss << std::endl;
+    tsv_file_ << ss.str();
+    header_written_ = true;
+  }
+  tsv_file_.width(12);
+  tsv_file_ << std::scientific << solver.time() << "\t";
+  for (auto &h : solver.hamiltonians()) tsv_file_ << std::scientific << std::setprecision(15) << h->calculate_total_energy(solver.time()) << "\t";
+  tsv_file_ << std::endl;
+}
+
+// =====================================================================================================
+// Solver
+// =====================================================================================================
+B200HeunLLGSolver::B200HeunLLGSolver(const Setting &settings, const Lattice &lattice, uint64_t seed) : lattice_(lattice), seed_(seed) {
+  // solvers/cuda_llg_heun.cu:21-37
+  step_size_ = settings.required("t_step").as_double() / 1e-12;
+  const double t_max = settings.required("t_max").as_double() / 1e-12;
+  const double t_min = settings.get("t_min", 0.0) / 1e-12;
+  max_steps_ = static_cast<int>(t_max / step_size_);
+  min_steps_ = static_cast<int>(t_min / step_size_);
+  jb_lattice_desc d{};
+  for (int n = 0; n < 3; ++n) { d.dims[n] = lattice.dims[n]; d.periodic[n] = lattice.periodic[n] ? 1 : 0; }
+  d.num_motif = lattice.M; d.x_begin = 0; d.nx_local = lattice.dims[0]; d.rank = 0; d.n_ranks = 1;
+  d.device = settings.get("device", -1);
+  if (jb_create(&ctx_, &d) != JB_OK) throw std::runtime_error(std::string("jams_b200: ") + jb_last_error(nullptr));
+  spins0_ = lattice.initial_spins(seed);
+  physics_.reset(new Physics(nullptr));
+}
+
+B200HeunLLGSolver::~B200HeunLLGSolver() { jb_destroy(ctx_); }
+
+void B200HeunLLGSolver::check(int status) const {
+  if (status != JB_OK) throw std::runtime_error(std::string("jams_b200: ") + jb_last_error(ctx_));
+}
+
+void B200HeunLLGSolver::register_hamiltonian(Hamiltonian *h) {
+  h->solver = this;
+  hamiltonians_.emplace_back(h);
+}
+
+void B200HeunLLGSolver::build() {   // Hamiltonians are registered after the solver exists (core/jams++.cc:274-288)
+  if (built_) return;
+  const std::vector<double> mus = lattice_.mus(), gyro = lattice_.gyro(), alpha = lattice_.alpha();
+  check(jb_set_materials(ctx_, mus.data(), gyro.data(), alpha.data()));
+  for (auto &h : hamiltonians_) h->attach(ctx_);
+  check(jb_import_spins(ctx_, spins0_.data(), 0));
+  built_ = true;
+}
+
+void B200HeunLLGSolver::set_spins(const std::vector<double> &s) {
+  if (s.size() != 3 * static_cast<size_t>(lattice_.num_spins)) throw std::runtime_error("set_spins: wrong array size");
+  spins0_ = s;
+  if (built_) check(jb_import_spins(ctx_, spins0_.data(), 0));
+}
+
+std::vector<double> B200HeunLLGSolver::spins() {
+  build();
+  std::vector<double> s(3 * static_cast<size_t>(lattice_.num_spins));
+  check(jb_export_spins(ctx_, s.data(), 0));
+  return s;
+}
+
+void B200HeunLLGSolver::run_steps(int n) {
+  build();
+  check(jb_step(ctx_, n, step_size_, time_, physics_->temperature(), seed_, static_cast<uint64_t>(iteration_), lattice_.gilbert_prefactor ? 1 : 0));
+  iteration_ += n;
+  time_ = iteration_ * step_size_;   // solvers/cuda_llg_heun.cu:120-121
+}
+
+void B200HeunLLGSolver::run() { run_steps(1); }
+
+void B200HeunLLGSolver::notify_monitors() {
+  build();
+  for (auto &m : monitors_) if (m->is_updating(iteration_)) m->update(*this);
+}
+
+std::vector<double> B200HeunLLGSolver::compute_fields() {
+  build();
+  std::vector<double> h(3 * static_cast<size_t>(lattice_.num_spins));
+  check(jb_fields(ctx_, JB_TERM_TOTAL, time_, h.data(), 0));
+  return h;
+}
+
+std::vector<double> Hamiltonian::calculate_fields(double time) {
+  std::vector<double> h(3 * static_cast<size_t>(lattice_.num_spins));
+  solver->check(jb_fields(solver->ctx(), term(), time, h.data(), 0));
+  return h;
+}
+std::vector<double> Hamiltonian::calculate_energies(double time) {
+  std::vector<double> e(lattice_.num_spins);
+  double total = 0.0;
+  solver->check(jb_energies(solver->ctx(), term(), time, e.data(), 0, &total));
+  return e;
+}
+double Hamiltonian::calculate_total_energy(double time) {
+  double total = 0.0;
+  solver->check(jb_energies(solver->ctx(), term(), time, nullptr, 0, &total));
+  return total;
+}
+
+void ExchangeHamiltonian::attach(jb_ctx *ctx) {
+  solver->check(jb_set_exchange_template(ctx, template_.size(), template_.mi.data(), template_.mj.data(), template_.T3.data(), template_.J9.data()));
+}
+void UniaxialAnisotropyHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_uniaxial(ctx, power_, magnitude_.data(), axis_.data())); }
+void ZeemanHamiltonian::attach(jb_ctx *ctx) {
+  solver->check(jb_set_zeeman(ctx, dc_local_field_.data(), has_ac_local_field_ ? ac_local_field_.data() : nullptr,
+                              has_ac_local_field_ ? ac_local_frequency_.data() : nullptr));
+}
+void AppliedFieldHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_applied_field(ctx, field_.data(), 1)); }
+
+// =====================================================================================================
+// Simulation (core/jams++.cc:231-377)
+// =====================================================================================================
+Simulation::Simulation(const std::vector<std::string> &config_args, const std::string &name, const std::string &output_dir) {
+  config_ = parse_config_strings(config_args);
+  prefix_ = output_dir;
+  if (!prefix_.empty() && prefix_.back() != '/') prefix_ += '/';
+  prefix_ += name + "_";   // jams::output::full_path_filename (helpers/output.cc:38-41)
+  uint64_t seed = 0;
+  if (const Setting *sim = config_->find("sim")) seed = static_cast<uint64_t>(sim->get("seed", 0LL));
+  lattice_.reset(new Lattice(*config_));
+  const Setting &solver_settings = config_->required("solver");
+  const std::string module = lowercase(solver_settings.required("module").as_string());
+  if (module != "llg-heun-b200-gpu" && module != "llg-heun-gpu" && module != "llg-heun-cpu")   // Solver::create (core/solver.cc:60-77)
+    throw std::runtime_error("unknown solver " + solver_settings["module"].as_string() + " (this host layer provides the llg-heun path only)");
+  solver_.reset(new B200HeunLLGSolver(solver_settings, *lattice_, seed));
+  solver_->register_physics_module(new Physics(config_->find("physics")));
+  if (!config_->exists("hamiltonians")) throw std::runtime_error("No hamiltonians group in config");
+  const Setting &hams = (*config_)["hamiltonians"];
+  for (int i = 0; i < hams.length(); ++i) solver_->register_hamiltonian(Hamiltonian::create(hams[i], *lattice_));
+  if (const Setting *mons = config_->find("monitors"))
+    for (int i = 0; i < mons->length(); ++i) solver_->register_monitor(Monitor::create((*mons)[i], *lattice_, prefix_));
+  if (const Setting *init = config_->find("initializer")) run_initializer(*init);
+}
+
+void Simulation::run_initializer(const Setting &s) {   // initializer/init_dispatcher + init_bloch_domain_wall.cc:10-32
+  const std::string module = lowercase(s.required("module").as_string());
+  if (module != "bloch_domain_wall") throw std::runtime_error("unknown initializer " + module);
+  const double width = s.required("width").as_double(), center = s.required("center").as_double();
+  Vec3 normal{{1, 0, 0}}, domain{{0, 0, 1}};
+  if (const Setting *n = s.find("normal")) normal = read_vec3(*n);
+  if (const Setting *d = s.find("domain")) domain = read_vec3(*d);
+  { const double n = norm(normal); for (auto &x : normal) x /= n; }
+  { const double n = norm(domain); for (auto &x : domain) x /= n; }
+  std::vector<double> spins = lattice_->initial_spins(0);
+  const std::vector<double> pos = lattice_->positions();
+  for (int i = 0; i < lattice_->num_spins; ++i) {
+    const Vec3 r = {{pos[3 * static_cast<size_t>(i)], pos[3 * static_cast<size_t>(i) + 1], pos[3 * static_cast<size_t>(i) + 2]}};
+    const double x = dot(r, normal) - center;
+    const Vec3 m = {{0.0, 1.0 / std::cosh(kPi * x / width), std::tanh(kPi * x / width)}};
+    const Vec3 spin = {{spins[3 * static_cast<size_t>(i)], spins[3 * static_cast<size_t>(i) + 1], spins[3 * static_cast<size_t>(i) + 2]}};
+    const Vec3 out = matvec(rotation_matrix_between_vectors(domain, m), spin);
+    for (int n = 0; n < 3; ++n) spins[3 * static_cast<size_t>(i) + n] = out[n];
+  }
+  solver_->set_spins(spins);
+}
+
+void Simulation::run() {   // run_simulation (core/jams++.cc:326-377)
+  while (solver_->is_running()) {
+    solver_->notify_monitors();
+    solver_->run();
+  }
+}
+
+}  // namespace jams_b200

@@ -214,6 +214,7 @@ class LangevinWhiteThermostat:
 
     def noise(self, step=None):
         s = self.solver
+        s._build()
         return s.ctx.noise(s.step_size, self.temperature, self.seed, s.iteration if step is None else step,
                            s.lattice.gilbert_prefactor)
 
@@ -251,6 +252,7 @@ class MagnetisationMonitor(Monitor):
         return lat.site_motif(solver.x0, solver.nx), lat.M
 
     def update(self, solver):
+        solver._build()
         g, ng = self.groups(solver)
         M4 = solver.reduce_sum(solver.ctx.magnetisation(g, ng))
         row = [solver.time, solver.temperature]
@@ -366,6 +368,8 @@ class B200HeunLLGSolver(Solver):
             if self.n_ranks > 1:
                 self.comm.barrier(self.ctx)
             self.ctx.import_spins(self._spins0)
+        elif self.hamiltonians:
+            self._build()     # Hamiltonians are registered: the device structures can be built now
 
     def spins(self):
         self._build()

@@ -30,10 +30,10 @@ def run(dims, options, T=0.0, steps=20, label="", make=W.c3_sc):
     s.ctx.close()
 
 
-CONFIGS = [(8, 64, 2, 4, 2, 0), (8, 64, 2, 5, 3, 0), (8, 64, 1, 4, 2, 0), (4, 64, 1, 5, 3, 0), (4, 64, 2, 5, 3, 0),
-           (4, 64, 1, 6, 4, 0), (16, 64, 2, 4, 2, 0), (16, 64, 4, 4, 2, 0), (16, 64, 4, 5, 3, 0), (8, 128, 2, 4, 2, 0),
-           (4, 128, 1, 5, 3, 0), (8, 32, 1, 5, 3, 0), (16, 32, 2, 5, 3, 0), (8, 64, 4, 5, 3, 0), (8, 64, 4, 6, 4, 0),
-           (2, 128, 1, 6, 4, 0), (2, 64, 1, 6, 4, 0)]
+# (TY, TZ, SPT, R, RU, u_tma)
+CONFIGS = [(8, 64, 1, 4, 2, 1), (8, 64, 1, 5, 2, 1), (4, 128, 1, 4, 2, 1), (4, 128, 1, 5, 2, 1), (2, 128, 1, 4, 2, 1), (2, 128, 1, 6, 3, 1),
+           (4, 64, 1, 4, 2, 1), (4, 64, 1, 6, 3, 1), (8, 64, 2, 4, 2, 1)]
+EXTRA = [dict(), dict(split_wait=0), dict(producer_sleep=100), dict(split_wait=0, producer_sleep=100)]
 
 if __name__ == "__main__":
     # every configuration runs in its own process: a CUDA error is sticky for the process that hit it
@@ -46,15 +46,16 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     temps = [float(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.0, 100.0]
     for T in temps:
-        jobs = [(dict(kernel=0), "direct"), (dict(kernel=1), "tile default"), (dict(kernel=1, u_tma=0), "tile default u_tma=0"),
-                (dict(kernel=1, u_tma=0, tile_y=8, tile_z=64, spt=2, ring=5), "tile 8x64 spt2 R5 u_tma=0"),
-                (dict(kernel=1, u_tma=0, tile_y=8, tile_z=64, spt=2, ring=6), "tile 8x64 spt2 R6 u_tma=0"),
-                (dict(kernel=1, u_tma=0, tile_y=16, tile_z=64, spt=2, ring=5), "tile 16x64 spt2 R5 u_tma=0")]
-        for TY, TZ, SPT, R, RU, cta in CONFIGS:
-            jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, ctas_per_sm=cta),
-                         f"tile TY={TY} TZ={TZ} SPT={SPT} R={R} RU={RU} cta={cta}"))
+        jobs = [(dict(kernel=0), "direct"), (dict(kernel=1), "tile default")]
+        for TY, TZ, SPT, R, RU, ut in CONFIGS:
+            for ex in (EXTRA if (TY, TZ, SPT) in ((8, 64, 1), (4, 128, 1)) else EXTRA[:1]):
+                jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, u_tma=ut, verbose=1, **ex),
+                             f"tile TY={TY} TZ={TZ} SPT={SPT} R={R} RU={RU} {ex}"))
         for opts, label in jobs:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(T), json.dumps(opts), label],
                                capture_output=True, text=True, timeout=300)
             out = (r.stdout or "").strip()
+            for line in (r.stderr or "").splitlines():
+                if line.startswith("jams_b200:"):
+                    print("    " + line, flush=True)
             print(out if out else f"{label:44s} CRASHED rc={r.returncode}: {(r.stderr or '').strip()[-300:]}", flush=True)

@@ -1,0 +1,133 @@
+"""The C++ host layer (jams_b200/host/: libconfig-grammar front end, Lattice, Hamiltonians, Solver, Monitors, `jams-b200`)
+against the Python mirror that the oracle parity tests validated: same config file -> same lattice arrays, the same
+exchange template bit for bit, and on the GPU the same trajectory and JAMS-format monitor files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from jams_b200 import host, workloads as W
+from jams_b200.solver import create_hamiltonian
+
+FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "bloch_wall_small.cfg")
+PATCH_B200 = 'solver : { module = "llg-heun-b200-gpu"; };'
+
+
+def _sorted_template(t):
+    key = np.lexsort((t["T"][:, 2], t["T"][:, 1], t["T"][:, 0], t["mj"], t["mi"]))
+    return t["mi"][key], t["mj"][key], t["T"][key], t["J9"][key]
+
+
+def test_config_grammar_and_types():
+    d = host.config_to_dict("""
+        # hash comment
+        a = 1; b : 2.5, c = "str" "ing";   /* block
+        comment */ d = true; e = FALSE; f = 0x1F; g = 12345678901L; h = 1e-23; i = -3;
+        grp : { x = [1, 2, 3]; y = ( "A", [0.5, 1], { k = 1; } ); empty = (); };
+        list = ( (1, 2.0, "three"), [1.0, 2] )
+    """)
+    assert d["a"] == 1 and d["b"] == 2.5 and d["c"] == "string" and d["d"] is True and d["e"] is False
+    assert d["f"] == 31 and d["g"] == 12345678901 and d["h"] == 1e-23 and d["i"] == -3
+    assert d["grp"] == {"x": [1, 2, 3], "y": ["A", [0.5, 1], {"k": 1}], "empty": []}
+    assert d["list"] == [[1, 2.0, "three"], [1.0, 2]]
+    for bad in ("a = ;", "a = 1; a = 2;", "x = [1, \"s\"];", "g = { a = 1;", 's = "unterminated'):
+        with pytest.raises(host.HostError):
+            host.config_to_dict(bad)
+
+
+def test_config_patches_merge_left_to_right_like_jams():
+    """core/jams++.cc:48-84 + interface/config.cc:12-145: scalars are replaced, missing settings added, lists patched by position"""
+    d = host.config_to_dict(FIXTURE, 'solver : { module = "llg-heun-b200-gpu"; t_max = 2e-15; }; physics : { temperature = 30.0; };',
+                            'lattice : { size = [8, 8, 8]; }; hamiltonians = ( { order = "K2"; } ); sim : { seed = 7; };')
+    assert d["solver"] == {"t_step": 1e-16, "module": "llg-heun-b200-gpu", "t_max": 2e-15}
+    assert d["physics"]["temperature"] == 30.0 and d["sim"]["seed"] == 7
+    assert d["lattice"] == {"size": [8, 8, 8], "periodic": [False, True, True]}
+    assert d["hamiltonians"][0]["order"] == "K2" and d["hamiltonians"][0]["module"] == "uniaxial" and d["hamiltonians"][1]["module"] == "exchange"
+    assert d["materials"][0]["name"] == "A"
+
+
+def test_cpp_lattice_and_template_equal_the_python_mirror_bit_for_bit():
+    w = W.c1_bloch_wall((32, 4, 4))
+    lat = w["lattice"]
+    la = host.lattice_arrays(FIXTURE)
+    assert la["num_spins"] == lat.num_spins and la["M"] == lat.M and la["dims"] == lat.dims and la["periodic"] == lat.periodic
+    assert np.array_equal(la["mus"], lat.mus()) and np.array_equal(la["gyro"], lat.gyro()) and np.array_equal(la["alpha"], lat.alpha())
+    assert np.array_equal(la["spins"], lat.initial_spins()) and np.array_equal(la["positions"], lat.positions())
+    h = create_hamiltonian(w["hamiltonians"][1], lat)
+    t = host.exchange_template(FIXTURE, ham_index=1)
+    for x, y in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    assert t["n_pairs"] == len(h.neighbour_list()[0])
+
+
+BCC_CFG = """
+materials = ( { name = "Fe"; moment = 2.2; alpha = 0.1; }, { name = "Co"; moment = 1.7; alpha = 0.05; gyro = 1.1; spin = [90.0, 0.0]; } );
+unitcell : { parameter = 2.87e-10; basis = ([1.0,0,0],[0,1.0,0],[0,0,1.0]); positions = ( ("Fe", [0,0,0]), ("Co", [0.5,0.5,0.5]) ); };
+lattice : { size = [6, 5, 4]; periodic = [true, true, false]; };
+hamiltonians = ( { module = "exchange"; energy_units = "meV"; energy_cutoff = 0.5;
+                   interactions = ( ("Fe","Co",[0.5,0.5,0.5], [20.0,0,0, 0,20.0,0, 0,0,20.0]), ("Co","Fe",[0.5,0.5,0.5], [20.0,0,0, 0,20.0,0, 0,0,20.0]),
+                                    ("Fe","Fe",[1.0,0,0], [10.0,0,0, 0,10.0,0, 0,0,10.0]), ("Co","Co",[1.0,0,0], [8.0,0.1,0, -0.1,8.0,0, 0,0,7.5]),
+                                    ("Fe","Fe",[1.0,1.0,0], [0.4,0,0, 0,0.4,0, 0,0,0.4]) ); } );
+solver : { module = "llg-heun-b200-gpu"; t_step = 1e-16; t_max = 1e-15; gilbert_prefactor = true; };
+"""
+
+
+def test_two_material_bcc_template_with_cutoffs_and_tensors():
+    from jams_b200.lattice import Lattice, Material
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, gyro=1.1, alpha=0.05, spin=(1.0, 0.0, 0.0))], np.eye(3),
+                  [("Fe", (0, 0, 0)), ("Co", (0.5, 0.5, 0.5))], (6, 5, 4), periodic=(True, True, False), gilbert_prefactor=True)
+    inter = [("Fe", "Co", [0.5, 0.5, 0.5], 20.0), ("Co", "Fe", [0.5, 0.5, 0.5], 20.0), ("Fe", "Fe", [1.0, 0, 0], 10.0),
+             ("Co", "Co", [1.0, 0, 0], [8.0, 0.1, 0, -0.1, 8.0, 0, 0, 0, 7.5]), ("Fe", "Fe", [1.0, 1.0, 0], 0.4)]
+    h = create_hamiltonian(dict(module="exchange", energy_units="meV", energy_cutoff=0.5, interactions=inter), lat)
+    t = host.exchange_template(BCC_CFG, ham_index=0)
+    for x, y in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    assert t["n_pairs"] == len(h.neighbour_list()[0])
+    la = host.lattice_arrays(BCC_CFG)
+    assert np.array_equal(la["mus"], lat.mus()) and np.array_equal(la["gyro"], lat.gyro()) and np.array_equal(la["alpha"], lat.alpha())
+    assert np.allclose(la["spins"], lat.initial_spins(), rtol=0, atol=1e-16)   # spherical-angle spin setting
+    assert np.array_equal(la["positions"], lat.positions())
+
+
+def test_known_neighbour_count_sc_8_cubed():
+    """sc 8^3 NN with symmetry operations -> 8*8*8*6 interactions (reference src/jams/test/interactions.h:241-252)"""
+    t = host.exchange_template(FIXTURE, "lattice : { size = [8, 8, 8]; periodic = [true, true, true]; };", ham_index=1)
+    assert len(t["mi"]) == 6 and t["n_pairs"] == 8 * 8 * 8 * 6
+    assert np.allclose(t["J9"][:, [0, 4, 8]], 3.5e-21 * 6.24150907e21) and np.all(t["J9"][:, [1, 2, 3, 5, 6, 7]] == 0)
+
+
+def test_error_behaviour_mirrors_the_reference():
+    with pytest.raises(host.HostError, match="unknown solver"):
+        host.run(FIXTURE, 'solver : { module = "llg-rk4-gpu"; };', num_spins=512)
+    with pytest.raises(host.HostError, match="energy units"):
+        host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { energy_units = "furlongs"; } );', ham_index=1)
+    with pytest.raises(host.HostError, match="Multiple interactions"):   # core/interactions.cc:373-381
+        host.exchange_template(FIXTURE, "lattice : { size = [32, 1, 4]; };", ham_index=1)
+    with pytest.raises(host.HostError, match="required setting 'moment'"):
+        host.lattice_arrays('materials = ( { name = "A"; } ); unitcell : { parameter = 1e-10; basis = ([1.0,0,0],[0,1.0,0],[0,0,1.0]); positions = (("A",[0,0,0])); }; lattice : { size = [1,1,1]; };')
+
+
+@pytest.mark.gpu
+def test_cpp_simulation_equals_python_mirror_and_writes_jams_monitor_files(tmp_path):
+    """the same config through the C++ Simulation (C++ lattice/template/initializer/main loop) and through the Python mirror"""
+    steps = 40
+    got, done = host.run(FIXTURE, PATCH_B200, name="wall", output_dir=str(tmp_path))
+    assert done == steps
+    w = W.c1_bloch_wall((32, 4, 4))
+    from jams_b200.lattice import bloch_domain_wall
+    lat = w["lattice"]
+    w["spins"] = bloch_domain_wall(lat.positions(), lat.initial_spins(), width=8.0, center=16.0)
+    s = W.make_solver(w)
+    s.run(steps)
+    assert np.array_equal(got, s.spins())
+    mag = open(tmp_path / "wall_mag.tsv").read().splitlines()
+    assert mag[0].split() == ["time", "T", "hx", "hy", "hz", "A_mx", "A_my", "A_mz", "A_m"]
+    assert len(mag) == 1 + 4 and all(len(line) == 16 * 9 for line in mag[1:])     # jams::fmt::sci columns, steps 0,10,20,30
+    assert float(mag[2].split()[0]) == pytest.approx(10 * 1e-4)
+    eng = open(tmp_path / "wall_eng.tsv").read().splitlines()
+    assert eng[0].split() == ["time", "uniaxial_E_meV", "exchange_E_meV"] and len(eng) == 1 + 2
+    # the command-line driver runs the same thing
+    r = subprocess.run([host.EXE_PATH, "--name", "cli", "--output", str(tmp_path), FIXTURE, PATCH_B200], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "cli_mag.tsv").read() == open(tmp_path / "wall_mag.tsv").read()

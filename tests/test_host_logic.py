@@ -44,6 +44,34 @@ def test_template_and_neighbour_list_bit_exact_with_oracle(make):
     assert np.array_equal(i, oi) and np.array_equal(j, oj) and np.array_equal(vals[v], oJ9)
 
 
+@pytest.mark.parametrize("make", [lambda: W.c1_bloch_wall((16, 4, 4)), lambda: W.c2_bcc_fe(4), lambda: W.c3_sc(dims=(5, 4, 6)),
+                                  lambda: W.c4_bcc_long_range(6)])
+def test_translation_invariant_neighbour_list_is_recognised(make):
+    """jb_detect_exchange_template (host only): ExchangeHamiltonian::neighbour_list() -> the template it came from"""
+    from jams_b200 import capi
+    w = make()
+    lat = w["lattice"]
+    h = create_hamiltonian(next(hs for hs in w["hamiltonians"] if hs["module"] == "exchange"), lat)
+    i, j, v, vals = h.neighbour_list()
+    t = capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i, j, v, vals)
+    assert t is not None
+    for x, y in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    # a slab sees the same template from the global list
+    nx = lat.dims[0] // 2
+    t2 = capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i, j, v, vals, x_begin=nx, nx_local=lat.dims[0] - nx)
+    for x, y in zip(_sorted_template(t2), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    # a vacancy (one pair missing), a changed coupling, or too small a capacity: not a template
+    keep = np.ones(i.size, bool); keep[i.size // 3] = False
+    assert capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i[keep], j[keep], v[keep], vals) is None
+    vals2 = np.concatenate([vals, vals[:1] * 1.5]); v2 = v.copy(); v2[i.size // 2] = len(vals)
+    assert capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i, j, v2, vals2) is None
+    assert capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i, j, v, vals, capacity=2) is None
+    with pytest.raises(capi.JamsB200Error):
+        capi.detect_exchange_template(lat.dims, lat.M, lat.periodic, i, j + lat.num_spins, v, vals)
+
+
 def test_c4_template_has_112_neighbours_per_site():
     w = W.c4_bcc_long_range(6)
     h = create_hamiltonian(w["hamiltonians"][0], w["lattice"])
