@@ -95,8 +95,8 @@ void compute_geometry(jb_ctx *c, int gx, int gy, int gz) {
   g.nx = c->d.nx_local; g.Ny = c->d.dims[1]; g.Nz = c->d.dims[2]; g.M = c->d.num_motif;
   g.gx = gx; g.gy = gy; g.gz = gz;
   g.PX = g.nx + 2 * gx; g.PY = g.Ny + 2 * gy;
-  g.PZ = g.Nz + 2 * gz;
-  if (g.PZ & 1) g.PZ += 1;
+  g.oz = 16;
+  g.PZ = (g.oz + g.Nz + gz + 15) / 16 * 16;
   g.sY = (long long)g.M * g.PZ;
   g.sX = (long long)g.PY * g.sY;
   g.elems = (long long)g.PX * g.sX;
@@ -335,8 +335,9 @@ void choose_tiling(jb_ctx *c) {
   int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
   TZ = std::max(1, std::min(TZ, g.Nz));
   if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
-  int SPT = c->opt_SPT ? c->opt_SPT : 2;
-  int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / TZ);   // ~256 threads per CTA
+  int SPT = c->opt_SPT ? c->opt_SPT : 1;
+  // consumer threads per CTA: <= 480 (+ the producer warp = 512 threads at 64 registers, two CTAs per SM) for SPT 1, 256 for SPT 2
+  int TY = c->opt_TY ? c->opt_TY : std::max(SPT, ((SPT == 1 ? 480 : 256) * SPT) / TZ);
   TY = std::max(1, std::min(TY, g.Ny));
   if (TY > 64) TY = 64;
   while (SPT > 1 && (SPT > TY)) SPT /= 2;
@@ -346,21 +347,20 @@ void choose_tiling(jb_ctx *c) {
   if (t.R < 2 * g.gx + 2 || t.R > 8 || t.RU < 2 || t.RU > 8) return;
   for (;;) {
     t.TY = TY; t.TZ = TZ; t.SPT = SPT;
-    t.BY = TY + 2 * g.gy; t.BZ = TZ + 2 * g.gz; if (t.BZ & 1) t.BZ++;
-    // the u box spans the same z range as the spin box (incl. the z halo) so that its inner start coordinate is
-    // z0, a multiple of the (even) tile width: TMA faults on boxes whose first element is not 16-byte aligned
-    t.UZ = t.BZ;
+    t.gzb = (g.gz + 1) & ~1;
+    t.BY = TY + 2 * g.gy; t.BZ = TZ + 2 * t.gzb; if (t.BZ & 1) t.BZ++;
+    t.UZ = (TZ + 1) & ~1;
     t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
     t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
     t.threads = TZ * ((TY + SPT - 1) / SPT);
-    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 512 + (size_t)n_nbr * sizeof(JbTileNbr);
+    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 512 + (size_t)t.R * n_nbr * sizeof(JbTileNbr);
     t.u_tma = c->opt_u_tma ? 1 : 0;
     t.smem[1] = t.smem[0] + (t.u_tma ? (size_t)t.RU * 3 * t.slotU * 8 : 0);
     // wanted: two CTAs per SM in stage B
-    if ((t.smem[1] <= 110 * 1024 && t.threads <= (SPT == 1 ? 512 : 256)) || c->opt_TY || TY <= SPT) break;
+    if ((t.smem[1] <= 110 * 1024 && t.threads <= (SPT == 1 ? 480 : 256)) || c->opt_TY || TY <= SPT) break;
     TY = std::max(SPT, TY / 2);
   }
-  if (t.threads > (t.SPT == 1 ? 512 : 256) || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
+  if (t.threads > (t.SPT == 1 ? 480 : 256) || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
   if (t.smem[1] > 220 * 1024) return;
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
@@ -401,13 +401,16 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   const jb_ctx::Tiling &t = c->tiling;
   p.g = c->g;
   p.J9T = c->d_tile_J9T;
-  p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
+  p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols; p.u_tma = t.u_tma;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
   p.producer_sleep_ns = c->opt_producer_sleep;
   p.split_wait = c->opt_split_wait;
+  p.debug_skip = c->opt_debug_skip;
+  p.early_release = c->opt_early_release;
+  p.store_hint = c->opt_store_hint;
   for (int m = 0; m < c->g.M; ++m) {
     int n = c->tile_nbr_begin[m];
     while (n < c->tile_nbr_begin[m + 1] && c->tile_nbr[n].d < 2 * c->g.gx) ++n;
@@ -717,7 +720,7 @@ int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const i
   auto layout_q = [&](int ref) {  // reference site id -> interior layout order q and ghosted index
     const int m = ref % g.M; int r = ref / g.M; const int z = r % g.Nz; r /= g.Nz; const int y = r % g.Ny; const int x = r / g.Ny;
     const long long q = (((long long)x * g.Ny + y) * g.M + m) * g.Nz + z;
-    const long long gi = ((long long)(x + g.gx) * g.PY + (y + g.gy)) * g.sY + (long long)m * g.PZ + (z + g.gz);
+    const long long gi = ((long long)(x + g.gx) * g.PY + (y + g.gy)) * g.sY + (long long)m * g.PZ + (z + g.oz);
     return std::make_pair(q, gi);
   };
   std::vector<int> idx((size_t)width * N, -1), val((size_t)width * N, 0), fill(N, 0);
@@ -1101,6 +1104,9 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "producer_sleep") { c->opt_producer_sleep = (int)value; return JB_OK; }
   else if (k == "split_wait") { c->opt_split_wait = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
+  else if (k == "debug_skip") { c->opt_debug_skip = (int)value; return JB_OK; }
+  else if (k == "early_release") { c->opt_early_release = (int)value; return JB_OK; }
+  else if (k == "store_hint") { c->opt_store_hint = (int)value; return JB_OK; }
   else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }
   else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);

@@ -149,14 +149,14 @@ struct JbOutBoxes {
   double *out_lo[3];
   double *out_hi[3];
 };
-static __device__ __noinline__ void store_images(const JbGeom &g, const JbOutBoxes &o, int x, int y, int m, int z,
-                                          double vx, double vy, double vz) {
+__device__ __forceinline__ void store_images_inline(const JbGeom &g, const JbOutBoxes &o, int x, int y, int m, int z,
+                                                    double vx, double vy, double vz) {
   const bool yb = g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy));
   const bool zb = g.per[2] && ((z < g.gz) | (z >= g.Nz - g.gz));
   int yps[2], zps[2], ny = 1, nz = 1;
-  yps[0] = y + g.gy; zps[0] = z + g.gz;
+  yps[0] = y + g.gy; zps[0] = z + g.oz;
   if (yb) yps[ny++] = (y < g.gy) ? y + g.gy + g.Ny : y + g.gy - g.Ny;
-  if (zb) zps[nz++] = (z < g.gz) ? z + g.gz + g.Nz : z + g.gz - g.Nz;
+  if (zb) zps[nz++] = (z < g.gz) ? z + g.oz + g.Nz : z + g.oz - g.Nz;
   // x targets: 0 = own, 1 = lo box, 2 = hi box
   for (int xt = 0; xt < 3; ++xt) {
     double *const *arr;
@@ -172,6 +172,11 @@ static __device__ __noinline__ void store_images(const JbGeom &g, const JbOutBox
       }
     }
   }
+}
+
+static __device__ __noinline__ void store_images(const JbGeom &g, const JbOutBoxes &o, int x, int y, int m, int z,
+                                                  double vx, double vy, double vz) {
+  store_images_inline(g, o, x, y, m, z, vx, vy, vz);
 }
 
 // does a site need store_images()?

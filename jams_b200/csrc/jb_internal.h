@@ -4,8 +4,9 @@
 // Device data layout (DESIGN.md "Data layout in HBM"):
 //   spins are stored SoA in double, one array per component, in a GHOSTED box
 //       index(xp, yp, m, zp) = ((xp * PY + yp) * M + m) * PZ + zp
-//   with xp = x + gx, yp = y + gy, zp = z + gz and ghost depths gx,gy,gz = max |T| of the exchange
-//   template along each axis.  z is the fastest index (lanes of a warp run along z), the motif index
+//   with xp = x + gx, yp = y + gy, zp = z + oz and ghost depths gx,gy,gz = max |T| of the exchange
+//   template along each axis.  oz = 16 >= gz: warp-wide stores of 32 consecutive z hit two full 128-byte lines, and
+//   TMA boxes start on even columns (a box whose first element is not 16-byte aligned faults).  z is the fastest index (lanes of a warp run along z), the motif index
 //   m sits between y and z so that a warp never mixes motif sites.  Ghost cells hold the periodic
 //   image (or zero across an open boundary: a zero spin contributes nothing to J.s), so the field
 //   gather has no boundary branches and a tile + halo is a plain box for TMA.
@@ -31,7 +32,8 @@
 struct JbGeom {
   int nx, Ny, Nz, M;       // interior extent of this slab (cells) and motif size
   int gx, gy, gz;          // ghost depth
-  int PX, PY, PZ;          // padded extent (PZ rounded up to even: 16-byte rows for TMA)
+  int oz;                  // column of z = 0 inside a row: a multiple of 16 doubles, so interior rows start on a 128-byte line
+  int PX, PY, PZ;          // padded extent (PZ a multiple of 16: every row starts on a 128-byte line)
   long long sY;            // stride of yp  = M * PZ
   long long sX;            // stride of xp  = PY * M * PZ
   long long elems;         // PX * sX
@@ -118,12 +120,15 @@ struct JbTileParams {
   const double *J9T;     // n_nbr x 9: tensor of every template entry divided by mu_i, Tesla (anisotropic exchange only)
   unsigned long long step;
   unsigned int rk[20];   // Philox4x32-10 round keys of the seed (k0 + r W0, k1 + r W1)
-  int TY, TZ, UZ;        // tile extent in y, z; UZ = inner extent of the U box (= BZ, see choose_tiling)
-  int BY, BZ;            // tile + halo extent (BZ even)
+  int TY, TZ, UZ;        // tile extent in y, z; UZ = TZ rounded up to even = inner extent of the u box
+  int BY, BZ, gzb;       // tile + halo extent; gzb = gz rounded up to even = z halo of the box (BZ = TZ + 2 gzb)
   int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
   int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
   int u_tma;             // stage B: u arrives through the TMA ring (1) or by plain global loads (0)
   int producer_sleep_ns; // back-off of the producer thread while a slot is still in use (0 = poll)
+  int early_release;     // hand the oldest S slot back to the producer right after the gathers instead of at the end of the plane
+  int store_hint;        // 0 = default stores, 1 = st.global.cs (streaming), 2 = st.global.wt
+  int debug_skip;        // timing experiments only: 1 = no compute (TMA pipeline alone), 2 = no stores
   int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
   int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
   int n_yt, n_zt, n_cols, n_chunks, n_items;
@@ -183,7 +188,7 @@ struct jb_ctx {
   // tiling of the persistent TMA kernel (jb_capi.cu choose_tiling) and its parameter-bank tables
   struct Tiling {
     bool ok = false;
-    int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
+    int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
     int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, u_tma = 1;
     size_t smem[2] = {0, 0};              // per stage
     int grid[2][2] = {{0, 0}, {0, 0}};    // [stage][thermal], 0 = not determined yet
@@ -214,7 +219,7 @@ struct jb_ctx {
   // options
   int opt_kernel = 1;      // 0 = direct global gathers, 1 = persistent TMA tile kernel
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
-  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 1, opt_verbose = 0;
+  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0;
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
   int opt_time_kernels = 0;
 

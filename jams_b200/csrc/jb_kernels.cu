@@ -23,7 +23,7 @@ using namespace jbdev;
 __device__ __forceinline__ void store_with_images(const JbStageParams &p, int x, int y, int m, int z,
                                                   double vx, double vy, double vz) {
   const JbGeom &g = p.g;
-  const long long i0 = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const long long i0 = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
   p.out[0][i0] = vx; p.out[1][i0] = vy; p.out[2][i0] = vz;
   if (!(x_image_needed(g, x) | yz_image_needed(g, y, z))) return;
   JbOutBoxes o;
@@ -58,7 +58,7 @@ __global__ void import_kernel(const JbGeom g, const double *__restrict__ aos, do
     const int m = (int)(r % g.M); r /= g.M;
     const int yp = (int)(r % g.PY);
     const int xp = (int)(r / g.PY);
-    int x = xp - g.gx, y = yp - g.gy, z = zp - g.gz;
+    int x = xp - g.gx, y = yp - g.gy, z = zp - g.oz;
     bool ok = true;
     if (x < 0 || x >= g.nx) {
       // multi-rank: the x ghost planes belong to the neighbours (they push into them); do not touch
@@ -69,7 +69,7 @@ __global__ void import_kernel(const JbGeom g, const double *__restrict__ aos, do
       if (g.per[1] && yp < g.Ny + 2 * g.gy) y = (y + g.Ny) % g.Ny; else ok = false;
     }
     if (z < 0 || z >= g.Nz) {
-      if (g.per[2] && zp < g.Nz + 2 * g.gz) z = (z + g.Nz) % g.Nz; else ok = false;
+      if (g.per[2] && z >= -g.gz && z < g.Nz + g.gz) z = (z + g.Nz) % g.Nz; else ok = false;   // padding columns stay 0
     }
     double vx = 0.0, vy = 0.0, vz = 0.0;
     if (ok) {
@@ -86,7 +86,7 @@ __global__ void export_kernel(const JbGeom g, const double *__restrict__ sx, con
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
     int x, y, m, z;
     decode_site(g, q, x, y, m, z);
-    const long long i = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const long long i = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
     const long long s = ref_site_local(g, x, y, m, z);
     aos[3 * s] = sx[i]; aos[3 * s + 1] = sy[i]; aos[3 * s + 2] = sz[i];
   }
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
   if (q >= total) return;
   int x, y, m, z;
   decode_site(g, q, x, y, m, z);
-  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
   const double *__restrict__ inx = p.in[0];
   const double *__restrict__ iny = p.in[1];
   const double *__restrict__ inz = p.in[2];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
   if (q >= total) return;
   int x, y, m, z;
   decode_site(g, q, x, y, m, z);
-  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
   const double *__restrict__ inx = p.in[0];
   const double *__restrict__ iny = p.in[1];
   const double *__restrict__ inz = p.in[2];
@@ -260,7 +260,7 @@ __global__ void field_kernel(const JbGeom g, const JbTables t, const double *__r
   if (q >= total) return;
   int x, y, m, z;
   decode_site(g, q, x, y, m, z);
-  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
   double hx = 0, hy = 0, hz = 0;
   if (term == JB_TERM_EXCHANGE || term == JB_TERM_TOTAL)
     exchange_field_site(g, t, inx, iny, inz, q, ic, m, ell_idx, ell_val, width, pairJ, pairs_iso, total, hx, hy, hz);
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(256) energy_kernel(const JbGeom g, const JbTab
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
     int x, y, m, z;
     decode_site(g, q, x, y, m, z);
-    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
     const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
     const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
     const JbClass c = t.classes[ci];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) magnetisation_kernel(const JbGeom g, cons
     int x, y, m, z;
     decode_site(g, q, x, y, m, z);
     if (group_of_spin && group_of_spin[ref_site_local(g, x, y, m, z)] != group) continue;
-    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.gz);
+    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
     const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
     const double mu = t.classes[ci].mu;
     a0 = fma(mu, inx[ic], a0); a1 = fma(mu, iny[ic], a1); a2 = fma(mu, inz[ic], a2); a3 += mu;

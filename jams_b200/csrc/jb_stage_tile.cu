@@ -66,6 +66,15 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
       : "memory");
 }
 
+// ghost images of a boundary site (rare path, out of line).  The parameter block is __grid_constant__, so its address
+// can be handed over without a local copy: no stack frame in the hot kernel.
+__device__ __noinline__ void tile_store_images(const JbTileParams &p, int x, int y, int m, int z, double vx, double vy, double vz) {
+  JbOutBoxes boxes;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { boxes.out[c] = p.out[c]; boxes.out_lo[c] = p.out_lo[c]; boxes.out_hi[c] = p.out_hi[c]; }
+  store_images_inline(p.g, boxes, x, y, m, z, vx, vy, vz);
+}
+
 struct ItemGeom { int y0, z0, x0, xc; };
 
 __device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
@@ -82,7 +91,7 @@ __device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
 
 // MOTIF1: the lattice has one motif site (M == 1): no motif loop, class constants through the uniform datapath
 template <int STAGE, bool THERMAL, bool ISO, int SPT, bool MOTIF1>
-__global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_tile_kernel(const __grid_constant__ CUtensorMap tS0,
+__global__ void __launch_bounds__(SPT == 1 ? 512 : 288, SPT == 1 ? 2 : 3) stage_tile_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
                                                             const __grid_constant__ CUtensorMap tS2,
                                                             const __grid_constant__ CUtensorMap tU0,
@@ -112,19 +121,37 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int n = tid; n < p.n_nbr; n += blockDim.x) s_nbr[n] = p.nbr[n];
+  // per ring phase c (= slot of the oldest resident plane) and template entry n: byte offset of the neighbour
+  // relative to the thread's own site in slot 0, and the coupling -> one LDS.128 and one add per neighbour
+  for (int idx = tid; idx < R * p.n_nbr; idx += blockDim.x) {
+    const int c = idx / p.n_nbr, n = idx - c * p.n_nbr;
+    const JbTileNbr e = p.nbr[n];
+    int t = c + e.d;
+    if (t >= R) t -= R;
+    JbTileNbr o;
+    o.delta = (t * 3 * slotS + e.delta) * (int)sizeof(double);
+    o.d = e.d;
+    o.J = e.J;
+    s_nbr[idx] = o;
+  }
   __syncthreads();
 
   // =========================== producer warp: the stream of S planes and u planes ===========================
-  if ((tid >> 5) == n_cw) {
-    if ((tid & 31) != 0) return;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the producer's TMA operands in
+  // uniform registers (no per-lane election loops around UTMALDG)
+  const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  if (warp_idx == n_cw) {
+    uint32_t elected = 0;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+    if (!elected) return;
     const uint32_t bytesS = (uint32_t)(p.BY * M * p.BZ * sizeof(double));
-    const uint32_t bytesU = (uint32_t)(p.TY * M * p.UZ * sizeof(double));   // UZ = BZ: see jb_capi.cu choose_tiling
+    const uint32_t bytesU = (uint32_t)(p.TY * M * p.UZ * sizeof(double));
     int slot = 0, uslot = 0;
     uint32_t pe = 0xffffffffu, pue = 0xffffffffu;   // parity to wait for on each empty barrier (first pass: passes at once)
     for (int item = bid; item < p.n_items; item += G) {
       const ItemGeom it = item_geom(p, item);
       const int np = it.xc + 2 * gx;
+      const int zs = it.z0 + g.oz - p.gzb;   // first column of the spin box: even, i.e. 16-byte aligned (TMA requirement)
       for (int j = 0; j < np; ++j) {
         {
           mbar_wait_backoff(smem_u32(&emptyS[slot]), (pe >> slot) & 1u, p.producer_sleep_ns);
@@ -132,9 +159,9 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
           const uint32_t bar = smem_u32(&fullS[slot]);
           double *dst = ringS + (size_t)slot * 3 * slotS;
           mbar_expect_tx(bar, 3 * bytesS);
-          tma_load_3d(smem_u32(dst), &tS0, it.z0, it.y0 * M, it.x0 + j, bar);
-          tma_load_3d(smem_u32(dst + slotS), &tS1, it.z0, it.y0 * M, it.x0 + j, bar);
-          tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, it.z0, it.y0 * M, it.x0 + j, bar);
+          tma_load_3d(smem_u32(dst), &tS0, zs, it.y0 * M, it.x0 + j, bar);
+          tma_load_3d(smem_u32(dst + slotS), &tS1, zs, it.y0 * M, it.x0 + j, bar);
+          tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, zs, it.y0 * M, it.x0 + j, bar);
           slot = (slot + 1 == R) ? 0 : slot + 1;
         }
         if (use_u && j >= 2 * gx) {   // the u plane of step i = j - 2 gx is needed together with S plane j
@@ -143,7 +170,7 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
           const uint32_t bar = smem_u32(&fullU[uslot]);
           double *dst = ringU + (size_t)uslot * 3 * slotU;
           mbar_expect_tx(bar, 3 * bytesU);
-          const int c0 = it.z0, c1 = (it.y0 + g.gy) * M, c2 = it.x0 + (j - 2 * gx) + gx;  // inner start kept 16-byte aligned
+          const int c0 = it.z0 + g.oz, c1 = (it.y0 + g.gy) * M, c2 = it.x0 + (j - 2 * gx) + gx;   // oz, z0 even: aligned
           tma_load_3d(smem_u32(dst), &tU0, c0, c1, c2, bar);
           tma_load_3d(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar);
           tma_load_3d(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar);
@@ -158,8 +185,8 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
   const int tz = tid % p.TZ, tyg = tid / p.TZ;
   const bool padding = tyg * SPT >= p.TY;            // threads that only fill up the last consumer warp
   const int ty0 = padding ? 0 : tyg * SPT;
-  const int soff = ((ty0 + g.gy) * M) * p.BZ + tz + g.gz;   // centre of (k = 0, m = 0) inside a slot component
-  const int uoff = (ty0 * M) * p.UZ + tz + g.gz;
+  const int soff = ((ty0 + g.gy) * M) * p.BZ + tz + p.gzb;   // centre of (k = 0, m = 0) inside a slot component
+  const int uoff = (ty0 * M) * p.UZ + tz;
   const int kS = M * p.BZ, kU = M * p.UZ, kG = M * g.PZ;    // strides between the thread's consecutive y sites
   const unsigned int kSite = (unsigned int)g.Nz * M;
   const unsigned long long planeSites = (unsigned long long)g.Ny * g.Nz * M;
@@ -180,7 +207,7 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
       if (!padding && (ty0 + k < p.TY) && (y < g.Ny) && (z < g.Nz)) okm |= 1u << k;
       if (yz_image_needed(g, y, z)) imgm |= 1u << k;
     }
-    int ic = (int)gidx(g, it.x0 + gx, it.y0 + ty0 + g.gy, 0, z + g.gz);   // g.elems < 2^31 (jb_capi.cu allocate_state)
+    int ic = (int)gidx(g, it.x0 + gx, it.y0 + ty0 + g.gy, 0, z + g.oz);   // g.elems < 2^31 (jb_capi.cu allocate_state)
     unsigned long long gs = global_site(g, it.x0, it.y0 + ty0, 0, z);
 
     for (int j = 0; j < 2 * gx; ++j) {
@@ -206,6 +233,8 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
       const bool xb = x_image_needed(g, x);
       const double *uplane = ringU + (size_t)cslotU * 3 * slotU + uoff;
 
+      if (p.debug_skip & 1) { if (!newest_ready) wait_newest(); }   // timing experiments: data movement only
+      else
 #pragma unroll 1
       for (int m = 0; m < M; ++m) {
         const JbClass &c = p.cls[MOTIF1 ? 0 : m];
@@ -221,13 +250,13 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
         // exchange field in Tesla; entries in the reference's CSR column order (interface/sparse_blas.h:22-25)
         const int nb = p.nbr_begin[MOTIF1 ? 0 : m], ne = p.nbr_begin[(MOTIF1 ? 0 : m) + 1];
         const int nsplit = newest_ready ? nb : p.nbr_split[MOTIF1 ? 0 : m];   // entries [nsplit, ne) read the newest plane
+        const JbTileNbr *tab = s_nbr + cslotS * p.n_nbr;
         auto gather = [&](int n0, int n1) {
 #pragma unroll 2
           for (int n = n0; n < n1; ++n) {
-            const int4 raw = *reinterpret_cast<const int4 *>(&s_nbr[n]);   // one LDS.128: {delta, d, J}
-            struct { int delta, d; double J; } e = {raw.x, raw.y, __hiloint2double(raw.w, raw.z)};
-            const int t = cslotS + e.d - R;
-            const double *q = base + (t < 0 ? t + R : t) * slot3 + e.delta;
+            const int4 raw = *reinterpret_cast<const int4 *>(&tab[n]);   // one LDS.128: {byte offset, d, J}
+            struct { int off, d; double J; } e = {raw.x, raw.y, __hiloint2double(raw.w, raw.z)};
+            const double *q = reinterpret_cast<const double *>(reinterpret_cast<const char *>(base) + e.off);
             if (ISO) {
 #pragma unroll
               for (int k = 0; k < SPT; ++k) {
@@ -251,6 +280,15 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
         gather(nb, nsplit);
         if (!newest_ready) wait_newest();
         gather(nsplit, ne);
+        // early release: the oldest S plane (at the end of an item: all resident planes) is only read by the gathers
+        // above, so its slot can go back to the producer while this warp still does the per-site physics
+        if (p.early_release && m == M - 1) {
+          __syncwarp();
+          if (lane0) {
+            mbar_arrive(smem_u32(&emptyS[cslotS]));
+            if (i == it.xc - 1) for (int j = 1; j <= 2 * gx; ++j) mbar_arrive(smem_u32(&emptyS[wrapS(cslotS + j)]));
+          }
+        }
 #pragma unroll
         for (int k = 0; k < SPT; ++k) {
           if (!((okm >> k) & 1u)) continue;
@@ -268,21 +306,27 @@ __global__ void __launch_bounds__(SPT == 1 ? 576 : 288, SPT == 1 ? 2 : 3) stage_
           }
           double ox, oy, oz, vx, vy, vz;
           llg_site<STAGE, THERMAL>(c, sx[k], sy[k], sz[k], hx[k], hy[k], hz[k], n0, n1, n2, ux, uy, uz, ox, oy, oz, vx, vy, vz);
-          if (STAGE == 0) { p.u[0][idx] = vx; p.u[1][idx] = vy; p.u[2][idx] = vz; }
-          p.out[0][idx] = ox; p.out[1][idx] = oy; p.out[2][idx] = oz;
-          if (((imgm >> k) & 1u) | xb) {
-            JbOutBoxes boxes;
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) { boxes.out[cc] = p.out[cc]; boxes.out_lo[cc] = p.out_lo[cc]; boxes.out_hi[cc] = p.out_hi[cc]; }
-            store_images(g, boxes, x, it.y0 + ty0 + k, m, z, ox, oy, oz);
+          if (p.debug_skip & 2) { if (ox + oy + oz + vx + vy + vz == 1.2345e300) p.out[0][idx] = ox; continue; }   // timing experiments: no stores
+          if (p.store_hint == 1) {        // streaming (evict-first) stores: the results are not read again by this launch
+            if (STAGE == 0) { __stcs(&p.u[0][idx], vx); __stcs(&p.u[1][idx], vy); __stcs(&p.u[2][idx], vz); }
+            __stcs(&p.out[0][idx], ox); __stcs(&p.out[1][idx], oy); __stcs(&p.out[2][idx], oz);
+          } else if (p.store_hint == 2) { // write-through
+            if (STAGE == 0) { __stwt(&p.u[0][idx], vx); __stwt(&p.u[1][idx], vy); __stwt(&p.u[2][idx], vz); }
+            __stwt(&p.out[0][idx], ox); __stwt(&p.out[1][idx], oy); __stwt(&p.out[2][idx], oz);
+          } else {
+            if (STAGE == 0) { p.u[0][idx] = vx; p.u[1][idx] = vy; p.u[2][idx] = vz; }
+            p.out[0][idx] = ox; p.out[1][idx] = oy; p.out[2][idx] = oz;
           }
+          if (((imgm >> k) & 1u) | xb) tile_store_images(p, x, it.y0 + ty0 + k, m, z, ox, oy, oz);
         }
       }
       // this warp is done with the oldest S plane (and the u plane): one arrival per warp on their empty barriers
       __syncwarp();
       if (lane0) {
-        mbar_arrive(smem_u32(&emptyS[cslotS]));
-        if (i == it.xc - 1) for (int j = 1; j <= 2 * gx; ++j) mbar_arrive(smem_u32(&emptyS[wrapS(cslotS + j)]));
+        if (!p.early_release || (p.debug_skip & 1)) {
+          mbar_arrive(smem_u32(&emptyS[cslotS]));
+          if (i == it.xc - 1) for (int j = 1; j <= 2 * gx; ++j) mbar_arrive(smem_u32(&emptyS[wrapS(cslotS + j)]));
+        }
         if (use_u) mbar_arrive(smem_u32(&emptyU[cslotU]));
       }
       cslotS = wrapS(cslotS + 1);
@@ -323,8 +367,6 @@ cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tm, int sta
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream) {
   return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (err != cudaSuccess) return err;
-    err = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return err;
     k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     return cudaGetLastError();

@@ -77,7 +77,7 @@ def exchange_template(*args: str, ham_index: int, capacity: int = 4096):
     return dict(mi=mi[:k].copy(), mj=mj[:k].copy(), T=T[:3 * k].reshape(k, 3).copy(), J9=J9[:9 * k].reshape(k, 9).copy(), n_pairs=pairs.value)
 
 
-def run(*args: str, name="jams", output_dir=".", max_steps=0, num_spins=None):
+def run(*args: str, name="jams", output_dir=".", max_steps=-1, num_spins=None):
     """run a configuration on the GPU through the C++ Simulation; returns (final spins N x 3, steps done)"""
     lib = load()
     a, n = _args(args)

@@ -71,14 +71,14 @@ __attribute__((visibility("default"))) int jbh_exchange_template(const char *con
 }
 
 // run a configuration to completion on the GPU (writes <output_dir>/<name>_mag.tsv etc.); returns the final spins (N x 3)
-// if `spins_out` is not NULL and `max_steps_override` > 0 stops after that many steps
+// if `spins_out` is not NULL; `max_steps_override` >= 0 stops after that many steps (negative: run to t_max)
 __attribute__((visibility("default"))) int jbh_run(const char *const *args, int n, const char *name, const char *output_dir, int max_steps_override,
                                                    double *spins_out, int *steps_done) {
   try {
     Simulation sim(split_args(args, n), name, output_dir);
     B200HeunLLGSolver &s = sim.solver();
     int steps = 0;
-    while (s.is_running() && (max_steps_override <= 0 || steps < max_steps_override)) {
+    while (s.is_running() && (max_steps_override < 0 || steps < max_steps_override)) {
       s.notify_monitors();
       s.run();
       ++steps;

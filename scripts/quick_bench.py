@@ -31,9 +31,9 @@ def run(dims, options, T=0.0, steps=20, label="", make=W.c3_sc):
 
 
 # (TY, TZ, SPT, R, RU, u_tma)
-CONFIGS = [(8, 64, 1, 4, 2, 1), (8, 64, 1, 5, 2, 1), (4, 128, 1, 4, 2, 1), (4, 128, 1, 5, 2, 1), (2, 128, 1, 4, 2, 1), (2, 128, 1, 6, 3, 1),
-           (4, 64, 1, 4, 2, 1), (4, 64, 1, 6, 3, 1), (8, 64, 2, 4, 2, 1)]
-EXTRA = [dict(), dict(split_wait=0), dict(producer_sleep=100), dict(split_wait=0, producer_sleep=100)]
+CONFIGS = [(7, 64, 1, 4, 2, 1), (7, 64, 1, 5, 2, 1), (7, 64, 1, 5, 2, 0), (7, 64, 1, 6, 2, 0), (6, 64, 1, 5, 2, 1), (6, 64, 1, 6, 2, 1), (3, 128, 1, 4, 2, 1),
+           (3, 128, 1, 5, 2, 1), (15, 32, 1, 4, 2, 1), (15, 32, 1, 5, 2, 1), (4, 64, 1, 6, 3, 1), (4, 64, 1, 8, 3, 1)]
+EXTRA = [dict()]
 
 if __name__ == "__main__":
     # every configuration runs in its own process: a CUDA error is sticky for the process that hit it
@@ -48,8 +48,8 @@ if __name__ == "__main__":
     for T in temps:
         jobs = [(dict(kernel=0), "direct"), (dict(kernel=1), "tile default")]
         for TY, TZ, SPT, R, RU, ut in CONFIGS:
-            for ex in (EXTRA if (TY, TZ, SPT) in ((8, 64, 1), (4, 128, 1)) else EXTRA[:1]):
-                jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, u_tma=ut, verbose=1, **ex),
+            for ex in EXTRA:
+                jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, **dict(dict(u_tma=ut), **ex)),
                              f"tile TY={TY} TZ={TZ} SPT={SPT} R={R} RU={RU} {ex}"))
         for opts, label in jobs:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(T), json.dumps(opts), label],
