@@ -332,6 +332,50 @@ void choose_tiling(jb_ctx *c) {
   const int n_nbr = (int)c->t_mi.size();
   if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
+  const bool pair = c->opt_kernel == 2;
+  t.pair = pair ? 1 : 0;
+  if (pair) {
+    // pair kernel: a thread owns the sites (z, z + 1); consumer threads = ceil(TZ / 2) x ceil(TY / SPT), 256 by default
+    // so that two CTAs share an SM, and the rest of the shared memory goes into ring depth (loads in flight)
+    int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : g.Nz);
+    TZ = std::max(1, std::min(TZ, g.Nz));
+    if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
+    const int HZ = (TZ + 1) / 2;
+    int SPT = c->opt_SPT ? c->opt_SPT : 1;
+    if (!(SPT == 1 || SPT == 2)) return;
+    int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / HZ);
+    TY = std::max(1, std::min(TY, std::min(g.Ny, 64)));
+    if (SPT > TY) SPT = 1;
+    const size_t budget = c->opt_ctas_per_sm == 1 ? 220 * 1024 : 113 * 1024;   // per CTA
+    for (;;) {
+      t.TY = TY; t.TZ = TZ; t.SPT = SPT;
+      t.gzb = (g.gz + 1) & ~1;
+      t.BY = TY + 2 * g.gy; t.BZ = ((TZ + 1) & ~1) + 2 * t.gzb;
+      t.UZ = (TZ + 1) & ~1;
+      t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
+      t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
+      t.threads = HZ * ((TY + SPT - 1) / SPT);
+      t.u_tma = 1;
+      t.RU = c->opt_RU ? c->opt_RU : 2;
+      const size_t slot_bytes = (size_t)3 * t.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
+      const size_t u_bytes = (size_t)t.RU * 3 * t.slotU * 8;
+      const int rmin = 2 * g.gx + 2;
+      for (int st = 0; st < 2; ++st) {
+        const size_t fixed = 512 + (st == 1 ? u_bytes : 0);
+        int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
+        R = std::min(R, JB_PAIR_MAX_RING);
+        if (!c->opt_R) R = std::min(R, 2 * g.gx + 1 + 4);   // more than four planes in flight per CTA buys nothing
+        t.Rs[st] = R;
+        t.smem[st] = fixed + (size_t)R * slot_bytes;
+      }
+      t.R = t.Rs[1];
+      if ((t.Rs[0] >= rmin && t.Rs[1] >= rmin && t.threads <= 512) || c->opt_TY || TY <= SPT) break;
+      TY = std::max(SPT, TY / 2);
+    }
+    if (t.Rs[0] < 2 * g.gx + 2 || t.Rs[1] < 2 * g.gx + 2 || t.RU < 2 || t.RU > JB_PAIR_MAX_RING || t.threads > 512) return;
+    if (t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;   // TMA box extents
+    if (t.smem[0] > 220 * 1024 || t.smem[1] > 220 * 1024) return;
+  } else {
   int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
   TZ = std::max(1, std::min(TZ, g.Nz));
   if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
@@ -362,6 +406,8 @@ void choose_tiling(jb_ctx *c) {
   }
   if (t.threads > (t.SPT == 1 ? 480 : 256) || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
   if (t.smem[1] > 220 * 1024) return;
+  t.Rs[0] = t.Rs[1] = t.R;
+  }
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
   t.ok = true;
@@ -371,11 +417,21 @@ void choose_tiling(jb_ctx *c) {
   c->tile_nbr.assign(n_nbr, JbTileNbr{});
   c->tile_nbr_begin.assign(g.M + 1, 0);
   std::vector<double> J9T(9 * (size_t)std::max(1, n_nbr));
+  // pair kernel: within a motif site the entries with an even z offset come first (their neighbour pair is 16-byte
+  // aligned in shared memory), then the odd ones; both groups keep the CSR column order
+  std::vector<int> order(c->tile_order.begin(), c->tile_order.end());
+  if (t.pair)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+      if (c->t_mi[a] != c->t_mi[b]) return c->t_mi[a] < c->t_mi[b];
+      return (c->t_T[3 * a + 2] & 1) < (c->t_T[3 * b + 2] & 1);
+    });
+  c->tile_nbr_odd.assign(g.M + 1, 0);
   for (int pos = 0; pos < n_nbr; ++pos) {
-    const int k = c->tile_order[pos];
+    const int k = order[pos];
     const int mi = c->t_mi[k], mj = c->t_mj[k];
     const int Tx = c->t_T[3 * k], Ty = c->t_T[3 * k + 1], Tz = c->t_T[3 * k + 2];
     const double inv_mu = c->h_classes[c->class_of_motif[mi]].inv_mu;
+    if (!(Tz & 1)) c->tile_nbr_odd[mi]++;   // number of even entries for now
     JbTileNbr e{};
     e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
     e.d = Tx + g.gx;
@@ -385,6 +441,7 @@ void choose_tiling(jb_ctx *c) {
     c->tile_nbr_begin[mi + 1]++;
   }
   for (int q = 0; q < g.M; ++q) c->tile_nbr_begin[q + 1] += c->tile_nbr_begin[q];
+  for (int q = 0; q < g.M; ++q) c->tile_nbr_odd[q] += c->tile_nbr_begin[q];   // -> first odd entry
   if (c->d_tile_nbr) cudaFree(c->d_tile_nbr);
   if (c->d_tile_J9T) cudaFree(c->d_tile_J9T);
   c->d_tile_nbr = nullptr; c->d_tile_J9T = nullptr;
@@ -404,6 +461,7 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols; p.u_tma = t.u_tma;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
+  for (int q = 0; q < c->g.M; ++q) p.nbr_odd[q] = t.pair ? c->tile_nbr_odd[q] : c->tile_nbr_begin[q + 1];
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
   p.producer_sleep_ns = c->opt_producer_sleep;
@@ -424,7 +482,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   if (t.grid[stage][thermal] > 0) return JB_OK;
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
-  JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
+  if (t.pair) JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
+  else JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the tile kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
   const int G = per_sm * c->num_sms;
@@ -446,8 +505,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   t.n_chunks[stage][thermal] = best_c;
   t.grid[stage][thermal] = (int)std::min<long long>(G, (long long)best_c * t.n_cols);
   if (c->opt_verbose)
-    fprintf(stderr, "jams_b200: tile kernel stage %d thermal %d: tile %dx%d (y,z) spt %d, %d consumer threads, ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.R, t.RU,
+    fprintf(stderr, "jams_b200: %s kernel stage %d thermal %d: tile %dx%d (y,z) spt %d, %d consumer threads, ring %d/%d, smem %zu B, "
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", t.pair ? "pair" : "tile", stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.Rs[stage], t.RU,
             t.smem[stage], per_sm, t.grid[stage][thermal], best_c, t.n_cols);
   return JB_OK;
 }
@@ -830,7 +889,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
 
   choose_tiling(c);
-  const bool use_tile = c->opt_kernel == 1 && c->tiling.ok && !c->has_pairs;
+  const bool use_tile = (c->opt_kernel == 1 || c->opt_kernel == 2) && c->tiling.ok && !c->has_pairs;
   JbTileParams tp{};
   if (use_tile) {
     rc = build_tmaps(c); if (rc) return rc;
@@ -886,12 +945,17 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           tp.step = p.step;
           const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
           for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
+          tp.R = c->tiling.Rs[stage];
           rc = tile_launch_shape(c, tp, stage, thermal); if (rc) return rc;
           tp.n_chunks = c->tiling.n_chunks[stage][thermal];
           tp.n_items = tp.n_chunks * tp.n_cols;
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[2][0], c->tmap[2][1], c->tmap[2][2]};
-          JB_CUDA(c, jbk_stage_tile(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
-                                    c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
+          if (c->tiling.pair)
+            JB_CUDA(c, jbk_stage_pair(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
+                                      c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
+          else
+            JB_CUDA(c, jbk_stage_tile(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
+                                      c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
         }

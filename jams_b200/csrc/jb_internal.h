@@ -106,6 +106,7 @@ struct JbStageParams {
 #define JB_TILE_MAX_CLASSES 8
 #define JB_TILE_MAX_MOTIF 16
 #define JB_TILE_MAX_GX 3
+#define JB_PAIR_MAX_RING 12   // ring depth limit of the pair kernel (jb_stage_pair.cu)
 struct __align__(16) JbTileNbr {
   int delta;   // offset inside a plane of the smem tile: (dy*M + (mj - mi))*BZ + dz
   int d;       // dx + gx: which of the 2 gx + 1 resident planes
@@ -131,6 +132,7 @@ struct JbTileParams {
   int debug_skip;        // timing experiments only: 1 = no compute (TMA pipeline alone), 2 = no stores
   int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
   int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
+  int nbr_odd[JB_TILE_MAX_MOTIF];    // pair kernel: [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
   int n_yt, n_zt, n_cols, n_chunks, n_items;
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
@@ -189,6 +191,8 @@ struct jb_ctx {
   struct Tiling {
     bool ok = false;
     int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
+    int pair = 0;                         // 1 = pair kernel (jb_stage_pair.cu): a thread owns two z-adjacent sites
+    int Rs[2] = {0, 0};                   // ring depth per stage (the pair kernel spends the shared memory stage B needs for u on a deeper ring in stage A)
     int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, u_tma = 1;
     size_t smem[2] = {0, 0};              // per stage
     int grid[2][2] = {{0, 0}, {0, 0}};    // [stage][thermal], 0 = not determined yet
@@ -200,7 +204,7 @@ struct jb_ctx {
   std::vector<JbTileNbr> tile_nbr;
   JbTileNbr *d_tile_nbr = nullptr;
   double *d_tile_J9T = nullptr;
-  std::vector<int> tile_nbr_begin;
+  std::vector<int> tile_nbr_begin, tile_nbr_odd;
   int num_sms = 0;
 
   // state: ghosted SoA arrays
@@ -217,7 +221,7 @@ struct jb_ctx {
   bool tmap_valid = false;
 
   // options
-  int opt_kernel = 1;      // 0 = direct global gathers, 1 = persistent TMA tile kernel
+  int opt_kernel = 2;      // 0 = direct global gathers, 1 = persistent TMA tile kernel (one site per thread), 2 = pair kernel
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
   int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0;
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
@@ -250,6 +254,11 @@ cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t str
 cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
+                                     size_t smem_bytes, int *blocks_per_sm);
+// pair kernel (jb_stage_pair.cu): same contract; `threads` = consumer threads = ceil(TZ/2) x ceil(TY/spt)
+cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
+                           int threads, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
                             int iso, int stage, cudaStream_t stream);
