@@ -366,7 +366,7 @@ void choose_tiling(jb_ctx *c) {
         R = std::min(R, JB_PAIR_MAX_RING);
         if (!c->opt_R) R = std::min(R, 2 * g.gx + 1 + 4);   // more than four planes in flight per CTA buys nothing
         t.Rs[st] = R;
-        t.smem[st] = fixed + (size_t)R * slot_bytes;
+        t.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
       }
       t.R = t.Rs[1];
       if ((t.Rs[0] >= rmin && t.Rs[1] >= rmin && t.threads <= 512) || c->opt_TY || TY <= SPT) break;
@@ -1165,6 +1165,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "chunks") c->opt_chunks = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
   else if (k == "u_tma") c->opt_u_tma = (int)value;
+  else if (k == "smem_pad") c->opt_smem_pad = (int)value;   // experiments: unused dynamic shared memory (KB) per CTA
   else if (k == "producer_sleep") { c->opt_producer_sleep = (int)value; return JB_OK; }
   else if (k == "split_wait") { c->opt_split_wait = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }

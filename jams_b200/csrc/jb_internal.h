@@ -224,6 +224,7 @@ struct jb_ctx {
   int opt_kernel = 2;      // 0 = direct global gathers, 1 = persistent TMA tile kernel (one site per thread), 2 = pair kernel
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
   int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0;
+  int opt_smem_pad = 0;
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
   int opt_time_kernels = 0;
 

@@ -35,7 +35,10 @@ CONFIGS = [(7, 64, 1, 4, 2, 1), (7, 64, 1, 5, 2, 1), (7, 64, 1, 5, 2, 0), (7, 64
            (3, 128, 1, 5, 2, 1), (15, 32, 1, 4, 2, 1), (15, 32, 1, 5, 2, 1), (4, 64, 1, 6, 3, 1), (4, 64, 1, 8, 3, 1)]
 EXTRA = [dict()]
 # pair kernel: (TY, TZ, SPT, R, RU, ctas_per_sm); 0 = heuristic
-PAIR_CONFIGS = [(8, 64, 1, 4, 2, 0), (8, 64, 1, 5, 2, 0), (8, 64, 1, 0, 3, 0), (16, 64, 1, 0, 2, 1), (16, 64, 1, 6, 3, 1), (4, 128, 1, 0, 2, 0),
+PAIR_EXTRA = []   # (label, options) appended by the caller through JB_QB_EXTRA (json list)
+if os.environ.get("JB_QB_EXTRA"):
+    PAIR_EXTRA = [(str(o), o) for o in json.loads(os.environ["JB_QB_EXTRA"])]
+PAIR_CONFIGS = [] if os.environ.get("JB_QB_EXTRA") else [(8, 64, 1, 4, 2, 0), (8, 64, 1, 5, 2, 0), (8, 64, 1, 0, 3, 0), (16, 64, 1, 0, 2, 1), (16, 64, 1, 6, 3, 1), (4, 128, 1, 0, 2, 0),
                 (8, 128, 1, 0, 2, 1), (16, 64, 2, 0, 2, 1), (8, 64, 2, 0, 2, 0), (16, 32, 1, 0, 2, 0)]
 
 if __name__ == "__main__":
@@ -49,10 +52,12 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     temps = [float(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.0, 100.0]
     for T in temps:
-        jobs = [(dict(kernel=1, verbose=1), "tile (one site per thread) default"), (dict(kernel=2, verbose=1), "pair default")]
+        jobs = [(dict(kernel=2, verbose=1), "pair default")] if os.environ.get("JB_QB_EXTRA") else [(dict(kernel=1, verbose=1), "tile (one site per thread) default"), (dict(kernel=2, verbose=1), "pair default")]
         for TY, TZ, SPT, R, RU, cps in PAIR_CONFIGS:
             jobs.append((dict(kernel=2, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, ctas_per_sm=cps, verbose=1),
                          f"pair TY={TY} TZ={TZ} SPT={SPT} R={R} RU={RU} ctas={cps}"))
+        for label, o in PAIR_EXTRA:
+            jobs.append((dict(dict(kernel=2, verbose=1), **o), "pair " + label))
         for TY, TZ, SPT, R, RU, ut in (CONFIGS if os.environ.get("JB_QB_TILE") else []):
             for ex in EXTRA:
                 jobs.append((dict(kernel=1, tile_y=TY, tile_z=TZ, spt=SPT, ring=R, ring_u=RU, **dict(dict(u_tma=ut), **ex)),

@@ -120,7 +120,7 @@ def test_cpp_simulation_equals_python_mirror_and_writes_jams_monitor_files(tmp_p
     w["spins"] = bloch_domain_wall(lat.positions(), lat.initial_spins(), width=8.0, center=16.0)
     # the initializer's rotation matrices are built by different code (C++ here, numpy there): agreement to rounding
     init, zero = host.run(FIXTURE, PATCH_B200, name="init", output_dir=str(tmp_path), max_steps=0)
-    assert zero == 0 and np.abs(init - w["spins"]).max() <= 4e-16
+    assert zero == 0 and np.abs(init - w["spins"]).max() <= 1e-15
     s = W.make_solver(w)
     s.set_spins(init)
     s.run(steps)
