@@ -95,8 +95,14 @@ void compute_geometry(jb_ctx *c, int gx, int gy, int gz) {
   g.nx = c->d.nx_local; g.Ny = c->d.dims[1]; g.Nz = c->d.dims[2]; g.M = c->d.num_motif;
   g.gx = gx; g.gy = gy; g.gz = gz;
   g.PX = g.nx + 2 * gx; g.PY = g.Ny + 2 * gy;
-  g.oz = 16;
-  g.PZ = (g.oz + g.Nz + gz + 15) / 16 * 16;
+  // row layout: [oz pad/ghost columns][Nz interior][gz ghost + pad up to a multiple of `oz`].  oz = 16 starts every interior run on a
+  // 128-byte line; smaller values (8: 64-byte DRAM atoms, 4: 32-byte sectors) shorten the unused gap between the runs
+  // of consecutive rows, which is what the DRAM efficiency of the stage kernels turned out to depend on (profiles/README.md)
+  int oz = (c->opt_oz == 4 || c->opt_oz == 8 || c->opt_oz == 16) ? c->opt_oz : 16;
+  const int need = std::max(4, ((2 * gz + 3) / 4) * 4);   // TMA boxes start up to 2 * ceil_even(gz) columns left of the interior
+  while (oz < need) oz *= 2;
+  g.oz = oz;
+  g.PZ = (g.oz + g.Nz + gz + oz - 1) / oz * oz;
   g.sY = (long long)g.M * g.PZ;
   g.sX = (long long)g.PY * g.sY;
   g.elems = (long long)g.PX * g.sX;
@@ -332,12 +338,57 @@ void choose_tiling(jb_ctx *c) {
   const int n_nbr = (int)c->t_mi.size();
   if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
-  const bool pair = c->opt_kernel == 2;
+  const bool fused = c->opt_kernel == 3 && c->fused_geometry && g.gx == 2 * c->reach[0] && c->reach[0] == 1;
+  const bool pair = c->opt_kernel >= 2;
   t.pair = pair ? 1 : 0;
-  if (pair) {
+  if (fused) {
+    // fused step kernel: one CTA per SM; the s_n ring (TMA) and four s* planes share the SM's shared memory.  Tile
+    // candidates in order of preference (less redundant predictor work first); a thread owns the pair (z, z + 1) of
+    // every motif site of one (y) row, consumer threads <= 256.
+    const int rx = c->reach[0], ry = c->reach[1], rz = c->reach[2];
+    const int cand[][2] = {{8, 64}, {4, 64}, {8, 32}, {4, 32}, {8, 16}, {4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}};
+    const size_t budget = 220 * 1024;
+    bool found = false;
+    for (const auto &cd : cand) {
+      int TY = c->opt_TY ? c->opt_TY : cd[0], TZ = c->opt_TZ ? c->opt_TZ : cd[1];
+      TY = std::max(1, std::min(TY, g.Ny));
+      TZ = std::max(1, std::min(TZ, g.Nz));
+      if (TZ < g.Nz && (TZ & 1)) TZ++;
+      const int HZ = (TZ + 1) / 2;
+      t.TY = TY; t.TZ = TZ; t.SPT = 1;
+      t.e1z = rz > 0 ? 2 : 0; t.e2z = rz > 0 ? 4 : 0;
+      t.gzb = t.e2z;
+      t.BY = TY + 4 * ry; t.BZ = 2 * HZ + 2 * t.e2z;
+      t.UZ = 2 * HZ;
+      t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
+      t.slotU = 16;
+      t.threads = HZ * TY;
+      t.u_tma = 0; t.RU = 2;
+      const int n_ct = (t.threads + 31) / 32 * 32;
+      const int n_halo = 2 * ry * g.M * (HZ + t.e1z) + TY * g.M * t.e1z;
+      const size_t slot_bytes = (size_t)3 * t.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);
+      const size_t fixed = 512 + 4 * slot_bytes;   // four s* planes + their entry-table phases + barriers
+      int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
+      R = std::min(R, JB_PAIR_MAX_RING);
+      if (!c->opt_R) R = std::min(R, 2 * rx + 1 + 3);
+      t.R = t.Rs[0] = t.Rs[1] = R;
+      t.smem[0] = t.smem[1] = fixed + (size_t)R * slot_bytes;
+      t.halo_warps = (n_halo + 31) / 32;
+      const bool fits = R >= 2 * rx + 2 && t.smem[0] <= budget && n_ct + 32 * t.halo_warps + 32 <= 384 &&
+                        t.BY * g.M <= 256 && t.BZ <= 256 && g.oz >= t.e2z;
+      if (fits) { found = true; break; }
+      if (c->opt_TY && c->opt_TZ) break;
+    }
+    if (found) t.fused = 1;
+    for (const JbClass &cl : c->h_classes) if (cl.power != 0) t.uni = 1;
+  }
+  if (t.fused) {
+    // shape chosen above
+  } else if (pair) {
     // pair kernel: a thread owns the sites (z, z + 1); consumer threads = ceil(TZ / 2) x ceil(TY / SPT), 256 by default
     // so that two CTAs share an SM, and the rest of the shared memory goes into ring depth (loads in flight)
-    int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : g.Nz);
+    // long contiguous runs along z serve DRAM best (measured: 4 x 128 beats 8 x 64 beats 16 x 32, profiles/README.md)
+    int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 128 ? 128 : g.Nz);
     TZ = std::max(1, std::min(TZ, g.Nz));
     if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
     const int HZ = (TZ + 1) / 2;
@@ -364,7 +415,9 @@ void choose_tiling(jb_ctx *c) {
         const size_t fixed = 512 + (st == 1 ? u_bytes : 0);
         int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
         R = std::min(R, JB_PAIR_MAX_RING);
-        if (!c->opt_R) R = std::min(R, 2 * g.gx + 1 + 4);   // more than four planes in flight per CTA buys nothing
+        // one plane in flight per CTA is the measured optimum: with the stores in the mix, more outstanding plane loads
+        // lower the DRAM efficiency (ring 5 / 6: -8 % / -15 %, profiles/README.md r01f)
+        if (!c->opt_R) R = std::min(R, 2 * g.gx + 2);
         t.Rs[st] = R;
         t.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
       }
@@ -434,7 +487,7 @@ void choose_tiling(jb_ctx *c) {
     if (!(Tz & 1)) c->tile_nbr_odd[mi]++;   // number of even entries for now
     JbTileNbr e{};
     e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
-    e.d = Tx + g.gx;
+    e.d = Tx + (t.fused ? c->reach[0] : g.gx);
     e.J = c->t_J9[9 * k] * inv_mu;
     for (int q = 0; q < 9; ++q) J9T[9 * (size_t)pos + q] = c->t_J9[9 * (size_t)k + q] * inv_mu;
     c->tile_nbr[pos] = e;
@@ -464,11 +517,13 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   for (int q = 0; q < c->g.M; ++q) p.nbr_odd[q] = t.pair ? c->tile_nbr_odd[q] : c->tile_nbr_begin[q + 1];
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
+  p.rx = c->reach[0]; p.ry = c->reach[1]; p.rz = c->reach[2]; p.e1z = t.e1z; p.e2z = t.e2z;
   p.producer_sleep_ns = c->opt_producer_sleep;
   p.split_wait = c->opt_split_wait;
   p.debug_skip = c->opt_debug_skip;
   p.early_release = c->opt_early_release;
   p.store_hint = c->opt_store_hint;
+  p.load_hint = c->opt_load_hint;
   for (int m = 0; m < c->g.M; ++m) {
     int n = c->tile_nbr_begin[m];
     while (n < c->tile_nbr_begin[m + 1] && c->tile_nbr[n].d < 2 * c->g.gx) ++n;
@@ -482,7 +537,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   if (t.grid[stage][thermal] > 0) return JB_OK;
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
-  if (t.pair) JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
+  if (t.fused) JB_CUDA(c, jbk_step_fused_occupancy(p, thermal, c->iso ? 1 : 0, t.uni, t.threads, t.halo_warps, t.smem[stage], &per_sm));
+  else if (t.pair) JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
   else JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the tile kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
@@ -498,7 +554,9 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
       const long long items = (long long)nc * t.n_cols;
       const long long per_cta = (items + G - 1) / G;
       const int xc = (g.nx + nc - 1) / nc;
-      const double cost = (double)per_cta * (xc + 0.7 * 2 * g.gx + 0.3);
+      // planes marched per item + what an item costs on top: halo planes that are only loaded (two-launch kernels) or
+      // the extra predictor planes of the fused kernel
+      const double cost = (double)per_cta * (xc + (t.fused ? 2.0 * c->reach[0] + 0.6 : 0.7 * 2 * g.gx + 0.3));
       if (cost < best * 0.999) { best = cost; best_c = nc; }
     }
   }
@@ -506,7 +564,7 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   t.grid[stage][thermal] = (int)std::min<long long>(G, (long long)best_c * t.n_cols);
   if (c->opt_verbose)
     fprintf(stderr, "jams_b200: %s kernel stage %d thermal %d: tile %dx%d (y,z) spt %d, %d consumer threads, ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", t.pair ? "pair" : "tile", stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.Rs[stage], t.RU,
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", t.fused ? "fused step" : (t.pair ? "pair" : "tile"), stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.Rs[stage], t.RU,
             t.smem[stage], per_sm, t.grid[stage][thermal], best_c, t.n_cols);
   return JB_OK;
 }
@@ -550,18 +608,30 @@ int ensure_ready(jb_ctx *c) {
     }
   }
   const JbGeom &g = c->g;
-  const bool geom_changed = !c->state_allocated || gx != g.gx || gy != g.gy || gz != g.gz;
+  // the fused step kernel (jb_step_fused.cu) needs ghost zones twice as deep as the template reaches; it handles reach 1
+  // along x, reach <= 1 along y and z and motifs of one or two sites.  A periodic axis must then be at least 2 x ghost
+  // depth long (no site may sit on both faces) and the slab at least a ghost depth thick.
+  const int reach[3] = {gx, gy, gz};
+  bool fused = c->opt_kernel == 3 && c->has_template && !c->has_pairs && gx == 1 && gy <= 1 && gz <= 1 && c->d.num_motif <= 2;
+  {
+    const int ext[3] = {c->d.dims[0], c->d.dims[1], c->d.dims[2]};
+    for (int d = 0; d < 3; ++d) if (reach[d] > 0 && c->d.periodic[d] && ext[d] < 4 * reach[d]) fused = false;
+    if (c->d.nx_local < 2 * gx || (c->d.n_ranks == 1 && c->d.periodic[0] && c->d.nx_local < 4 * gx)) fused = false;
+  }
+  if (fused) { gx *= 2; gy *= 2; gz *= 2; }
+  const bool geom_changed = !c->state_allocated || gx != g.gx || gy != g.gy || gz != g.gz || c->state_relayout;
+  c->state_relayout = false;
   if (geom_changed) {
     // the reference throws "Multiple interactions" when a periodic dimension is so short that two
     // template entries reach the same site (core/interactions.cc:373-381); the ghost scheme needs
     // the same condition
     const int ext[3] = {c->d.dims[0], c->d.dims[1], c->d.dims[2]};
-    const int gg[3] = {gx, gy, gz};
+    const int gg[3] = {reach[0], reach[1], reach[2]};
     for (int d = 0; d < 3; ++d) {
       if (gg[d] > 0 && c->d.periodic[d] && ext[d] < 2 * gg[d] + 1)
         JB_FAIL(c, JB_ERR_INVALID, "periodic dimension shorter than 2*range+1 of the exchange template (the reference reports 'Multiple interactions' here)");
     }
-    if (gx > c->d.nx_local || (c->d.n_ranks == 1 && c->d.periodic[0] && gx > 0 && c->d.nx_local < 2 * gx))
+    if (reach[0] > c->d.nx_local || (c->d.n_ranks == 1 && c->d.periodic[0] && reach[0] > 0 && c->d.nx_local < 2 * reach[0]))
       JB_FAIL(c, JB_ERR_INVALID, "slab thinner than the x range of the exchange template");
     std::vector<double> keep;
     const bool had_state = c->state_allocated;
@@ -572,6 +642,7 @@ int ensure_ready(jb_ctx *c) {
       JB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     compute_geometry(c, gx, gy, gz);
+    c->fused_geometry = fused;
     int rc = allocate_state(c); if (rc) return rc;
     if (had_state) {
       double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
@@ -581,6 +652,7 @@ int ensure_ready(jb_ctx *c) {
     c->tiling_valid = false;
     c->classes_dirty = true;
   }
+  for (int d = 0; d < 3; ++d) c->reach[d] = reach[d];
   const bool classes_were_dirty = c->classes_dirty;
   int rc = build_classes(c); if (rc) return rc;
   if (classes_were_dirty) c->tiling_valid = false;
@@ -889,7 +961,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
 
   choose_tiling(c);
-  const bool use_tile = (c->opt_kernel == 1 || c->opt_kernel == 2) && c->tiling.ok && !c->has_pairs;
+  const bool use_tile = c->opt_kernel >= 1 && c->tiling.ok && !c->has_pairs;
   JbTileParams tp{};
   if (use_tile) {
     rc = build_tmaps(c); if (rc) return rc;
@@ -912,7 +984,46 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
     }
     rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
 
-    for (int n = 0; n < chunk; ++n) {
+    for (int n = 0; n < chunk && use_tile && c->tiling.fused; ++n) {
+      // ---- fused step kernel: one launch per Heun step, reads S0 (s_n) and writes S1 (s_{n+1}); then the roles swap ----
+      for (int k = 0; k < 3; ++k) {
+        tp.out[k] = c->S1[k]; tp.u[k] = nullptr;
+        if (multi) { tp.out_lo[k] = c->peer_lo_S1[k]; tp.out_hi[k] = c->peer_hi_S1[k]; }
+        else if (c->g.per[0] && c->g.gx > 0) { tp.out_lo[k] = c->S1[k]; tp.out_hi[k] = c->S1[k]; }
+        else { tp.out_lo[k] = nullptr; tp.out_hi[k] = nullptr; }
+      }
+      tp.step = first_step + (uint64_t)(done + n);
+      const size_t nc = c->h_classes.size();
+      const JbClass *cls0 = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n : 0) * nc;       // fields at t      (cpu_llg_heun.cc:66)
+      const JbClass *cls1 = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + 1 : 0) * nc;   // fields at t + dt (:103-106)
+      for (int m = 0; m < c->g.M; ++m) {
+        tp.cls[m] = cls0[c->class_of_motif[m]];
+        const JbClass &b = cls1[c->class_of_motif[m]];
+        tp.fT1[m][0] = b.fTx; tp.fT1[m][1] = b.fTy; tp.fT1[m][2] = b.fTz;
+      }
+      tp.R = c->tiling.Rs[0];
+      rc = tile_launch_shape(c, tp, 0, thermal); if (rc) return rc;
+      tp.n_chunks = c->tiling.n_chunks[0][thermal];
+      tp.n_items = tp.n_chunks * tp.n_cols;
+      if (multi) { JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++; }
+      record_event(c, 0);
+      const CUtensorMap tm[3] = {c->tmap[0][0], c->tmap[0][1], c->tmap[0][2]};
+      JB_CUDA(c, jbk_step_fused(tp, tm, thermal, c->iso ? 1 : 0, c->tiling.uni, c->tiling.threads, c->tiling.halo_warps, c->tiling.grid[0][thermal],
+                                c->tiling.smem[0], c->stream));
+      c->launches++;
+      record_event(c, 1);
+      if (multi) {
+        c->epoch++;
+        JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+      }
+      for (int k = 0; k < 3; ++k) {   // s_{n+1} becomes the current state
+        std::swap(c->S0[k], c->S1[k]);
+        std::swap(c->tmap[0][k], c->tmap[1][k]);
+        std::swap(c->peer_lo_S0[k], c->peer_lo_S1[k]);
+        std::swap(c->peer_hi_S0[k], c->peer_hi_S1[k]);
+      }
+    }
+    for (int n = 0; n < chunk && !(use_tile && c->tiling.fused); ++n) {
       for (int stage = 0; stage < 2; ++stage) {
         JbStageParams p{};
         p.g = c->g;
@@ -950,6 +1061,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           tp.n_chunks = c->tiling.n_chunks[stage][thermal];
           tp.n_items = tp.n_chunks * tp.n_cols;
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[2][0], c->tmap[2][1], c->tmap[2][2]};
+          tp.reverse_items = (c->tiling.pair && stage == 1 && c->opt_reverse_b) ? 1 : 0;
           if (c->tiling.pair)
             JB_CUDA(c, jbk_stage_pair(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
                                       c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
@@ -1165,13 +1277,16 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "chunks") c->opt_chunks = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
   else if (k == "u_tma") c->opt_u_tma = (int)value;
-  else if (k == "smem_pad") c->opt_smem_pad = (int)value;   // experiments: unused dynamic shared memory (KB) per CTA
+  else if (k == "smem_pad") c->opt_smem_pad = (int)value;
+  else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }   // experiments: unused dynamic shared memory (KB) per CTA
   else if (k == "producer_sleep") { c->opt_producer_sleep = (int)value; return JB_OK; }
   else if (k == "split_wait") { c->opt_split_wait = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
   else if (k == "debug_skip") { c->opt_debug_skip = (int)value; return JB_OK; }
   else if (k == "early_release") { c->opt_early_release = (int)value; return JB_OK; }
   else if (k == "store_hint") { c->opt_store_hint = (int)value; return JB_OK; }
+  else if (k == "load_hint") { c->opt_load_hint = (int)value; return JB_OK; }
+  else if (k == "reverse_b") { c->opt_reverse_b = (int)value; return JB_OK; }
   else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }
   else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);

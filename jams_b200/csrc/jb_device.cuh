@@ -77,6 +77,9 @@ __device__ __forceinline__ void normals_from_words(const uint32_t r[4], double &
   const float c = box_muller1(r[2], r[3]);
   n0 = (double)a; n1 = (double)b; n2 = (double)c;
 }
+// the same three draws left in fp32 (they are exact fp32 values; widening later gives identical doubles)
+__device__ __forceinline__ void site_normals_rk_f(const unsigned int *__restrict__ rk, unsigned long long step,
+                                                  unsigned long long gsite, float &n0, float &n1, float &n2);
 
 // three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
 // (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
@@ -92,6 +95,14 @@ __device__ __forceinline__ void site_normals_rk(const unsigned int *__restrict__
   uint32_t r[4];
   philox4x32_10_rk((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, r);
   normals_from_words(r, n0, n1, n2);
+}
+
+__device__ __forceinline__ void site_normals_rk_f(const unsigned int *__restrict__ rk, unsigned long long step,
+                                                  unsigned long long gsite, float &n0, float &n1, float &n2) {
+  uint32_t r[4];
+  philox4x32_10_rk((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, r);
+  box_muller2(r[0], r[1], n0, n1);
+  n2 = box_muller1(r[2], r[3]);
 }
 
 __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
@@ -137,6 +148,50 @@ __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy,
   // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged.  rsqrt() is CUDA's IEEE-accurate
   // (<= 1 ulp) double reciprocal square root: MUFU.RSQ64H seed + Newton steps, no fp64 divide.
   const double inv = (n2_ > 4.930380657631324e-32) ? rsqrt(n2_) : 1.0;
+  ox = px * inv; oy = py * inv; oz = pz * inv;
+}
+
+// branch-free variant for kernels that interleave several independent site updates in one basic block
+// (jb_step_fused.cu): UNI selects the uniaxial term at compile time, the reciprocal square root is the hardware
+// seed (MUFU.RSQ64H, ~2^-23) refined by one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (the same scheme
+// CUDA's rsqrt() uses, <= 1 ulp) without the special-case branch: x = p.p is either > DBL_EPSILON^2 and far from
+// overflow (|p| ~ 1) or the result is discarded by the select.
+__device__ __forceinline__ double rsqrt_nobranch(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  const double q = fma(e, 0.375, 0.5);
+  return fma(q, e * y, y);
+}
+template <int STAGE, bool THERMAL, bool UNI>
+__device__ __forceinline__ void llg_site_nb(const JbClass &c, double sx, double sy, double sz,
+                                            double hx, double hy, double hz,
+                                            double n0, double n1, double n2,
+                                            double ux, double uy, double uz,
+                                            double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
+  if (UNI) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163), here / mu; KpT = 0 when the class has none
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    const double d2 = d * d;
+    double pw = d;
+    pw = (c.power >= 4) ? pw * d2 : pw;
+    pw = (c.power >= 6) ? pw * d2 : pw;
+    const double f = c.KpT * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
+  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;
+  const double tx = fma(c.alpha, bx_, ax_), ty = fma(c.alpha, by_, ay_), tz = fma(c.alpha, bz_, az_);
+  double px, py, pz;
+  if (STAGE == 0) {
+    vx = fma(c.c_half, tx, sx); vy = fma(c.c_half, ty, sy); vz = fma(c.c_half, tz, sz);
+    px = fma(c.c_full, tx, sx); py = fma(c.c_full, ty, sy); pz = fma(c.c_full, tz, sz);
+  } else {
+    px = fma(c.c_half, tx, ux); py = fma(c.c_half, ty, uy); pz = fma(c.c_half, tz, uz);
+  }
+  const double n2_ = px * px + py * py + pz * pz;
+  const double r = rsqrt_nobranch(n2_);
+  const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;   // |p| <= DBL_EPSILON: unchanged (containers/vec3.h:276-283)
   ox = px * inv; oy = py * inv; oz = pz * inv;
 }
 

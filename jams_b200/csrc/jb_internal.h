@@ -5,7 +5,8 @@
 //   spins are stored SoA in double, one array per component, in a GHOSTED box
 //       index(xp, yp, m, zp) = ((xp * PY + yp) * M + m) * PZ + zp
 //   with xp = x + gx, yp = y + gy, zp = z + oz and ghost depths gx,gy,gz = max |T| of the exchange
-//   template along each axis.  oz = 16 >= gz: warp-wide stores of 32 consecutive z hit two full 128-byte lines, and
+//   template along each axis (twice that for the fused step kernel).  oz (4 by default; 8 / 16 selectable) >= gz keeps every
+//   interior run on a 32-byte sector boundary (all stores write whole sectors) with the shortest possible gap between rows, and
 //   TMA boxes start on even columns (a box whose first element is not 16-byte aligned faults).  z is the fastest index (lanes of a warp run along z), the motif index
 //   m sits between y and z so that a warp never mixes motif sites.  Ghost cells hold the periodic
 //   image (or zero across an open boundary: a zero spin contributes nothing to J.s), so the field
@@ -32,8 +33,8 @@
 struct JbGeom {
   int nx, Ny, Nz, M;       // interior extent of this slab (cells) and motif size
   int gx, gy, gz;          // ghost depth
-  int oz;                  // column of z = 0 inside a row: a multiple of 16 doubles, so interior rows start on a 128-byte line
-  int PX, PY, PZ;          // padded extent (PZ a multiple of 16: every row starts on a 128-byte line)
+  int oz;                  // column of z = 0 inside a row: 4, 8 or 16 doubles (interior rows start on a sector / DRAM atom / L2 line)
+  int PX, PY, PZ;          // padded extent (PZ a multiple of oz)
   long long sY;            // stride of yp  = M * PZ
   long long sX;            // stride of xp  = PY * M * PZ
   long long elems;         // PX * sX
@@ -128,11 +129,17 @@ struct JbTileParams {
   int u_tma;             // stage B: u arrives through the TMA ring (1) or by plain global loads (0)
   int producer_sleep_ns; // back-off of the producer thread while a slot is still in use (0 = poll)
   int early_release;     // hand the oldest S slot back to the producer right after the gathers instead of at the end of the plane
-  int store_hint;        // 0 = default stores, 1 = st.global.cs (streaming), 2 = st.global.wt
+  int store_hint;        // 0 = default stores, 1 = st.global.cs (streaming), 2 = st.global.wt, 3 / 4 = L2 evict_first / evict_last policy (pair kernel)
+  int reverse_items;     // walk the work items from the last to the first (stage B: the data stage A wrote last is still in L2)
+  int load_hint;         // pair kernel, TMA loads: 0 = none, 1 = evict_first on u, 2 = + evict_last on S, 3 = evict_first on both
   int debug_skip;        // timing experiments only: 1 = no compute (TMA pipeline alone), 2 = no stores
   int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
   int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
   int nbr_odd[JB_TILE_MAX_MOTIF];    // pair kernel: [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
+  // fused step kernel (jb_step_fused.cu): reach of the exchange template per axis (the ghost depths g.gx.. are twice
+  // that), z halo (even) of the s* extent / of the s_n tile, constant field of the corrector stage (time t + dt), Tesla
+  int rx, ry, rz, e1z, e2z;
+  double fT1[JB_TILE_MAX_MOTIF][3];
   int n_yt, n_zt, n_cols, n_chunks, n_items;
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
@@ -192,6 +199,8 @@ struct jb_ctx {
     bool ok = false;
     int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
     int pair = 0;                         // 1 = pair kernel (jb_stage_pair.cu): a thread owns two z-adjacent sites
+    int fused = 0;                        // 1 = fused step kernel (jb_step_fused.cu): predictor + corrector in one launch
+    int e1z = 0, e2z = 0, halo_warps = 0, uni = 0;
     int Rs[2] = {0, 0};                   // ring depth per stage (the pair kernel spends the shared memory stage B needs for u on a deeper ring in stage A)
     int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, u_tma = 1;
     size_t smem[2] = {0, 0};              // per stage
@@ -221,10 +230,15 @@ struct jb_ctx {
   bool tmap_valid = false;
 
   // options
-  int opt_kernel = 2;      // 0 = direct global gathers, 1 = persistent TMA tile kernel (one site per thread), 2 = pair kernel
+  int opt_kernel = 2;      // 0 = direct global gathers, 1 = persistent TMA tile kernel (one site per thread), 2 = pair kernel (default),
+                           // 3 = fused step kernel where the template allows it (else 2)
+  int reach[3] = {0, 0, 0};   // max |T| of the exchange template per axis
+  bool fused_geometry = false; // ghost depths are 2 x reach (what the fused step kernel needs)
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
-  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0;
+  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0, opt_load_hint = 0, opt_reverse_b = 0;
   int opt_smem_pad = 0;
+  int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows
+  bool state_relayout = false; // an option that changes the box layout was set: re-layout at the next ensure_ready
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
   int opt_time_kernels = 0;
 
@@ -256,6 +270,11 @@ cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
+// fused step kernel (jb_step_fused.cu): tmaps3 = {S_in.x, S_in.y, S_in.z}; one launch = one Heun step
+cudaError_t jbk_step_fused(const JbTileParams &p, const CUtensorMap *tmaps3, int thermal, int iso, int uni, int threads, int halo_warps,
+                           int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t jbk_step_fused_occupancy(const JbTileParams &p, int thermal, int iso, int uni, int threads, int halo_warps, size_t smem_bytes,
+                                     int *blocks_per_sm);
 // pair kernel (jb_stage_pair.cu): same contract; `threads` = consumer threads = ceil(TZ/2) x ceil(TY/spt)
 cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);

@@ -43,15 +43,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // try_wait suspends the warp in hardware for a bounded time, so the loop around it costs almost no issue slots
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // the suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
+  // returning after a short default time-out: a spinning try_wait + branch pair showed up as 18 % of all issued
+  // instructions in the T = 100 K profile (profiles/README.md r01g)
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "JB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra JB_DONE;\n\t"
       "bra JB_WAIT;\n\t"
       "JB_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -81,6 +84,26 @@ __device__ __forceinline__ int4 lds_entry(uint32_t a) {
 }
 __device__ __forceinline__ void stg128(double *ptr, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
+}
+// store with a cache hint (experiments on how the write-back stream reaches DRAM): 1 = streaming (.cs), 2 = write-through
+// (.wt), 3 = L2 evict_first policy, 4 = L2 evict_last policy; pol = the createpolicy value for 3 / 4
+__device__ __forceinline__ void stg128_hint(double *ptr, double a, double b, int hint, unsigned long long pol) {
+  if (hint == 1) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
+  else if (hint == 2) asm volatile("st.global.wt.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
+  else if (hint >= 3) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
+  else stg128(ptr, a, b);
+}
+__device__ __forceinline__ unsigned long long make_policy(int kind) {   // 0 evict_first, 1 evict_last
+  unsigned long long pol;
+  if (kind == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar, unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
+      : "memory");
 }
 
 // ghost images of a boundary site, general case (x / y faces and their edges; rare, out of line).  The parameter
@@ -163,7 +186,10 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
     const uint32_t bytesU = (uint32_t)(p.TY * M * p.UZ * sizeof(double));
     int slot = 0, uslot = 0;
     uint32_t pe = 0xffffffffu, pue = 0xffffffffu;   // parity to wait for on each empty barrier (first pass: passes at once)
-    for (int item = bid; item < p.n_items; item += G) {
+    const int lh = p.load_hint;    // experiments: 0 = none, 1 = evict_first on u, 2 = evict_first on u and evict_last on S, 3 = evict_first on both
+    const unsigned long long polF = make_policy(0), polL = make_policy(1);
+    for (int item0 = bid; item0 < p.n_items; item0 += G) {
+      const int item = p.reverse_items ? p.n_items - 1 - item0 : item0;
       const ItemGeom it = item_geom(p, item);
       const int np = it.xc + 2 * gx;
       const int zs = it.z0 + g.oz - p.gzb;   // first column of the spin box: even, i.e. 16-byte aligned (TMA requirement)
@@ -174,9 +200,16 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
           const uint32_t bar = smem_u32(&fullS[slot]);
           double *dst = ringS + (size_t)slot * 3 * slotS;
           mbar_expect_tx(bar, 3 * bytesS);
-          tma_load_3d(smem_u32(dst), &tS0, zs, it.y0 * M, it.x0 + j, bar);
-          tma_load_3d(smem_u32(dst + slotS), &tS1, zs, it.y0 * M, it.x0 + j, bar);
-          tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, zs, it.y0 * M, it.x0 + j, bar);
+          if (lh >= 2) {
+            const unsigned long long pol = lh == 2 ? polL : polF;
+            tma_load_3d_hint(smem_u32(dst), &tS0, zs, it.y0 * M, it.x0 + j, bar, pol);
+            tma_load_3d_hint(smem_u32(dst + slotS), &tS1, zs, it.y0 * M, it.x0 + j, bar, pol);
+            tma_load_3d_hint(smem_u32(dst + 2 * slotS), &tS2, zs, it.y0 * M, it.x0 + j, bar, pol);
+          } else {
+            tma_load_3d(smem_u32(dst), &tS0, zs, it.y0 * M, it.x0 + j, bar);
+            tma_load_3d(smem_u32(dst + slotS), &tS1, zs, it.y0 * M, it.x0 + j, bar);
+            tma_load_3d(smem_u32(dst + 2 * slotS), &tS2, zs, it.y0 * M, it.x0 + j, bar);
+          }
           slot = (slot + 1 == R) ? 0 : slot + 1;
         }
         if (STAGE == 1 && j >= 2 * gx) {   // the u plane of step i = j - 2 gx is needed together with S plane j
@@ -186,9 +219,15 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
           double *dst = ringU + (size_t)uslot * 3 * slotU;
           mbar_expect_tx(bar, 3 * bytesU);
           const int c0 = it.z0 + g.oz, c1 = (it.y0 + g.gy) * M, c2 = it.x0 + (j - 2 * gx) + gx;   // oz, z0 even: aligned
-          tma_load_3d(smem_u32(dst), &tU0, c0, c1, c2, bar);
-          tma_load_3d(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar);
-          tma_load_3d(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar);
+          if (lh >= 1) {   // u is read exactly once
+            tma_load_3d_hint(smem_u32(dst), &tU0, c0, c1, c2, bar, polF);
+            tma_load_3d_hint(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar, polF);
+            tma_load_3d_hint(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar, polF);
+          } else {
+            tma_load_3d(smem_u32(dst), &tU0, c0, c1, c2, bar);
+            tma_load_3d(smem_u32(dst + slotU), &tU1, c0, c1, c2, bar);
+            tma_load_3d(smem_u32(dst + 2 * slotU), &tU2, c0, c1, c2, bar);
+          }
           uslot = (uslot + 1 == RU) ? 0 : uslot + 1;
         }
       }
@@ -219,8 +258,11 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
   int cslotS = 0, cslotU = 0;
   uint32_t phS = 0, phU = 0;
   auto wrapS = [&](int a) { return a >= R ? a - R : a; };
+  const int sh = p.store_hint;
+  const unsigned long long spol = make_policy(sh == 4 ? 1 : 0);
 
-  for (int item = bid; item < p.n_items; item += G) {
+  for (int item0 = bid; item0 < p.n_items; item0 += G) {
+    const int item = p.reverse_items ? p.n_items - 1 - item0 : item0;   // see jb_capi.cu: stage B walks the lattice backwards
     const ItemGeom it = item_geom(p, item);
     const int z = it.z0 + 2 * zp;                         // first site of the pair; the second is z + 1
     unsigned ok0 = 0, ok1 = 0, ygen = 0;                  // per y row k: site z valid, site z + 1 valid, y-face row
@@ -279,7 +321,8 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
         // exchange field in Tesla.  Entries of a motif site: first those with an even z offset (the neighbour pair
         // is 16-byte aligned: LDS.128), then the odd ones (two LDS.64); within each group in the reference's CSR
         // column order (interface/sparse_blas.h:22-25)
-        const int nb = p.nbr_begin[MOTIF1 ? 0 : m], no = p.nbr_odd[MOTIF1 ? 0 : m], ne = p.nbr_begin[(MOTIF1 ? 0 : m) + 1];
+        int nb = p.nbr_begin[MOTIF1 ? 0 : m], no = p.nbr_odd[MOTIF1 ? 0 : m], ne = p.nbr_begin[(MOTIF1 ? 0 : m) + 1];
+        if (p.debug_skip & 4) no = ne = nb;   // timing experiments: no neighbour gathers
         const uint32_t base = own + mo;
 #pragma unroll 2
         for (int n = nb; n < no; ++n) {
@@ -358,18 +401,28 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
             site_normals_rk(p.rk, p.step, site + M, nb0, nb1, nb2);   // z + 1: the next site id but M - 1
           }
           double2 ox, oy, oz, vx, vy, vz;
+          if (p.debug_skip & 8) {   // timing experiments: no per-site physics, the pipeline only moves data
+            ox = make_double2(sx[k].x + ux.x, sx[k].y + ux.y); oy = make_double2(sy[k].x + uy.x, sy[k].y + uy.y); oz = make_double2(sz[k].x + uz.x, sz[k].y + uz.y);
+            vx = hx[k]; vy = hy[k]; vz = hz[k];
+          } else {
           llg_site<STAGE, THERMAL>(c, sx[k].x, sy[k].x, sz[k].x, hx[k].x, hy[k].x, hz[k].x, na0, na1, na2, ux.x, uy.x, uz.x,
                                    ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
           llg_site<STAGE, THERMAL>(c, sx[k].y, sy[k].y, sz[k].y, hx[k].y, hy[k].y, hz[k].y, nb0, nb1, nb2, ux.y, uy.y, uz.y,
                                    ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
+          }
           if (p.debug_skip & 2) {   // timing experiments: no stores
             if (ox.x + oy.x + oz.x + vx.x + vy.x + vz.x + ox.y + oy.y + oz.y + vx.y + vy.y + vz.y == 1.2345e300) p.out[0][0] = ox.x;
             continue;
           }
           const int idx = ic + m * g.PZ + k * kG;
           if ((ok1 >> k) & 1u) {          // both sites: 16-byte stores
-            if (STAGE == 0) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
-            stg128(&p.out[0][idx], ox.x, ox.y); stg128(&p.out[1][idx], oy.x, oy.y); stg128(&p.out[2][idx], oz.x, oz.y);
+            if (sh == 0) {
+              if (STAGE == 0) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
+              stg128(&p.out[0][idx], ox.x, ox.y); stg128(&p.out[1][idx], oy.x, oy.y); stg128(&p.out[2][idx], oz.x, oz.y);
+            } else {
+              if (STAGE == 0) { stg128_hint(&p.u[0][idx], vx.x, vx.y, sh, spol); stg128_hint(&p.u[1][idx], vy.x, vy.y, sh, spol); stg128_hint(&p.u[2][idx], vz.x, vz.y, sh, spol); }
+              stg128_hint(&p.out[0][idx], ox.x, ox.y, sh, spol); stg128_hint(&p.out[1][idx], oy.x, oy.y, sh, spol); stg128_hint(&p.out[2][idx], oz.x, oz.y, sh, spol);
+            }
           } else if ((ok0 >> k) & 1u) {   // odd Nz: the last pair of a row holds one site
             if (STAGE == 0) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
             p.out[0][idx] = ox.x; p.out[1][idx] = oy.x; p.out[2][idx] = oz.x;

@@ -47,7 +47,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         n, T = int(sys.argv[2]), float(sys.argv[3])
         opts = json.loads(sys.argv[4])
-        run((n, n, n), opts, T=T, label=sys.argv[5])
+        dims = tuple(int(v) for v in os.environ["JB_QB_DIMS"].split("x")) if os.environ.get("JB_QB_DIMS") else (n, n, n)
+        run(dims, opts, T=T, label=sys.argv[5])
         sys.exit(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     temps = [float(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0.0, 100.0]

@@ -20,7 +20,8 @@ from jams_b200.solver import create_hamiltonian
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TRAJ_TOL = 1e-10
-KERNELS = {"direct": dict(kernel=0), "tma": dict(kernel=1), "pair": dict(kernel=2), "pair_spt2": dict(kernel=2, spt=2)}
+KERNELS = {"direct": dict(kernel=0), "tma": dict(kernel=1), "pair": dict(kernel=2), "pair_spt2": dict(kernel=2, spt=2),
+           "fused": dict(kernel=3), "fused_small_tile": dict(kernel=3, tile_y=4, tile_z=32, ring=4)}
 
 
 def gold(name):
@@ -43,7 +44,7 @@ def test_extension_is_loaded_and_launches_kernels():
     s = make(W.c3_sc(dims=(8, 8, 8)))
     s.run(2)
     s.ctx.synchronize()
-    assert s.ctx.kernel_launches() >= 5   # import + 2 stages x 2 steps
+    assert s.ctx.kernel_launches() >= 3   # import + 2 fused steps (or 2 stages x 2 steps)
     assert any("libjams_b200.so" in line for line in open("/proc/self/maps"))
 
 
@@ -80,7 +81,7 @@ def test_fields_and_energies_match_reference_golden(name, pairs):
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if "T0" in n])
-@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "pairs", "pairs_auto"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile", "pairs", "pairs_auto"])
 def test_T0_trajectories_match_reference_golden(name, variant):
     case, g = CASES[name], gold(f"case_{name}.npz")
     w = case["workload"]()
@@ -94,7 +95,7 @@ def test_T0_trajectories_match_reference_golden(name, variant):
     assert abs(s.time - float(g["time_final"])) < 1e-15
 
 
-@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "pairs"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile", "pairs"])
 def test_thermal_trajectory_matches_oracle_given_the_same_noise(variant):
     """T > 0: the reference's CPU (pcg) and GPU (XORWOW) noise streams already differ, so parity is defined on the
     integrator given identical noise: dump the Philox normals the kernels use and feed them to the oracle."""
@@ -174,20 +175,20 @@ def test_midsize_trajectories_match_oracle(make_w, steps):
     sim.set_spins(s0)
     sim.run(steps)
     want = sim.get_spins()
-    for variant in ("direct", "tma", "pair", "pair_spt2"):
+    for variant in ("direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile"):
         s = make(w, options=KERNELS[variant])
         s.set_spins(s0)
         s.run(steps)
         assert np.abs(s.spins() - want).max() <= TRAJ_TOL, variant
 
 
-@pytest.mark.parametrize("dims", [(7, 9, 37), (33, 5, 130), (4, 70, 3), (5, 3, 64), (6, 19, 66)])
+@pytest.mark.parametrize("dims", [(7, 9, 37), (33, 5, 130), (4, 70, 3), (5, 3, 64), (6, 19, 66), (9, 4, 4), (40, 10, 6)])
 def test_partial_tiles_and_odd_sizes(dims):
     w = W.c3_sc(dims=dims)
     lat = w["lattice"]
     s0 = random_unit_spins(lat.num_spins, 13)
     res = {}
-    for variant in ("direct", "tma", "pair", "pair_spt2"):
+    for variant in ("direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile"):
         s = make(w, options=KERNELS[variant])
         s.set_spins(s0)
         s.run(5)
@@ -199,6 +200,8 @@ def test_partial_tiles_and_odd_sizes(dims):
     assert np.abs(res["tma"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["pair"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["pair_spt2"] - res["direct"]).max() <= 1e-14
+    assert np.abs(res["fused"] - res["direct"]).max() <= 1e-14
+    assert np.abs(res["fused_small_tile"] - res["direct"]).max() <= 1e-14
 
 
 def test_full_size_properties_sc_128():
@@ -206,7 +209,7 @@ def test_full_size_properties_sc_128():
     ferromagnetic fixed point, energy dissipation at T = 0, and kernel-variant agreement"""
     w = W.c3_sc(dims=(128, 128, 128))
     lat = w["lattice"]
-    s = make(w, options=KERNELS["pair"])
+    s = make(w, options=KERNELS["fused"])
     s.set_spins(np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1)))
     s.run(10)
     assert np.array_equal(s.spins(), np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1)))
@@ -218,7 +221,7 @@ def test_full_size_properties_sc_128():
     e1 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
     assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14
     assert e1 < e0
-    for variant in ("direct", "tma"):
+    for variant in ("direct", "tma", "pair"):
         d = make(w, options=KERNELS[variant])
         d.set_spins(s0)
         d.run(40)
