@@ -422,10 +422,10 @@ void choose_tiling(jb_ctx *c) {
         t.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
       }
       t.R = t.Rs[1];
-      if ((t.Rs[0] >= rmin && t.Rs[1] >= rmin && t.threads <= 512) || c->opt_TY || TY <= SPT) break;
+      if ((t.Rs[0] >= rmin && t.Rs[1] >= rmin && t.threads <= 256) || TY <= SPT) break;
       TY = std::max(SPT, TY / 2);
     }
-    if (t.Rs[0] < 2 * g.gx + 2 || t.Rs[1] < 2 * g.gx + 2 || t.RU < 2 || t.RU > JB_PAIR_MAX_RING || t.threads > 512) return;
+    if (t.Rs[0] < 2 * g.gx + 2 || t.Rs[1] < 2 * g.gx + 2 || t.RU < 2 || t.RU > JB_PAIR_MAX_RING || t.threads > 256) return;   // the kernel is compiled for <= 288 threads
     if (t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;   // TMA box extents
     if (t.smem[0] > 220 * 1024 || t.smem[1] > 220 * 1024) return;
   } else {

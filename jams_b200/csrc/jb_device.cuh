@@ -117,6 +117,16 @@ __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x
 //   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
 //   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
 // unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
+// reciprocal square root without the special-case branch of CUDA's rsqrt(): hardware seed (MUFU.RSQ64H, ~2^-23) refined by
+// one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (<= 1 ulp).  x = p.p is either > DBL_EPSILON^2 and far from
+// overflow (|p| ~ 1) or the result is discarded by the caller's select.
+__device__ __forceinline__ double rsqrt_nobranch(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);
+  const double q = fma(e, 0.375, 0.5);
+  return fma(q, e * y, y);
+}
 template <int STAGE, bool THERMAL>
 __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
                                          double hx, double hy, double hz,
@@ -145,24 +155,14 @@ __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy,
     px = fma(c.c_half, tx, ux); py = fma(c.c_half, ty, uy); pz = fma(c.c_half, tz, uz);
   }
   const double n2_ = px * px + py * py + pz * pz;
-  // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged.  rsqrt() is CUDA's IEEE-accurate
-  // (<= 1 ulp) double reciprocal square root: MUFU.RSQ64H seed + Newton steps, no fp64 divide.
-  const double inv = (n2_ > 4.930380657631324e-32) ? rsqrt(n2_) : 1.0;
+  // |p| <= DBL_EPSILON  <=>  p.p <= DBL_EPSILON^2 : leave unchanged (select, no branch; no fp64 divide or sqrt).
+  const double r = rsqrt_nobranch(n2_);
+  const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;
   ox = px * inv; oy = py * inv; oz = pz * inv;
 }
 
 // branch-free variant for kernels that interleave several independent site updates in one basic block
-// (jb_step_fused.cu): UNI selects the uniaxial term at compile time, the reciprocal square root is the hardware
-// seed (MUFU.RSQ64H, ~2^-23) refined by one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (the same scheme
-// CUDA's rsqrt() uses, <= 1 ulp) without the special-case branch: x = p.p is either > DBL_EPSILON^2 and far from
-// overflow (|p| ~ 1) or the result is discarded by the select.
-__device__ __forceinline__ double rsqrt_nobranch(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x * y, y, 1.0);
-  const double q = fma(e, 0.375, 0.5);
-  return fma(q, e * y, y);
-}
+// (jb_step_fused.cu): UNI selects the uniaxial term at compile time.
 template <int STAGE, bool THERMAL, bool UNI>
 __device__ __forceinline__ void llg_site_nb(const JbClass &c, double sx, double sy, double sz,
                                             double hx, double hy, double hz,

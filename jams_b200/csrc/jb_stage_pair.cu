@@ -28,111 +28,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "jb_device.cuh"
+#include "jb_tma.cuh"
 
 namespace {
 
 using namespace jbdev;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// try_wait suspends the warp in hardware for a bounded time, so the loop around it costs almost no issue slots
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  // the suspend-time hint lets the hardware park the warp until the phase completes (or the hint expires) instead of
-  // returning after a short default time-out: a spinning try_wait + branch pair showed up as 18 % of all issued
-  // instructions in the T = 100 K profile (profiles/README.md r01g)
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "JB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-      "@P1 bra JB_DONE;\n\t"
-      "bra JB_WAIT;\n\t"
-      "JB_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity), "r"(0x989680)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-// shared-memory loads by 32-bit shared address: always LDS (never a generic LD), 16 or 8 bytes per lane
-__device__ __forceinline__ double2 lds128(uint32_t a) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ double lds64(uint32_t a) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ int4 lds_entry(uint32_t a) {
-  int4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void stg128(double *ptr, double a, double b) {
-  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
-}
-// store with a cache hint (experiments on how the write-back stream reaches DRAM): 1 = streaming (.cs), 2 = write-through
-// (.wt), 3 = L2 evict_first policy, 4 = L2 evict_last policy; pol = the createpolicy value for 3 / 4
-__device__ __forceinline__ void stg128_hint(double *ptr, double a, double b, int hint, unsigned long long pol) {
-  if (hint == 1) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
-  else if (hint == 2) asm volatile("st.global.wt.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
-  else if (hint >= 3) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
-  else stg128(ptr, a, b);
-}
-__device__ __forceinline__ unsigned long long make_policy(int kind) {   // 0 evict_first, 1 evict_last
-  unsigned long long pol;
-  if (kind == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar, unsigned long long pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
-      : "memory");
-}
-
-// ghost images of a boundary site, general case (x / y faces and their edges; rare, out of line).  The parameter
-// block is __grid_constant__, so its address can be handed over without a local copy: no stack frame in the kernel.
-__device__ __noinline__ void pair_store_images(const JbTileParams &p, int x, int y, int m, int z, double vx, double vy, double vz) {
-  JbOutBoxes boxes;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { boxes.out[c] = p.out[c]; boxes.out_lo[c] = p.out_lo[c]; boxes.out_hi[c] = p.out_hi[c]; }
-  store_images_inline(p.g, boxes, x, y, m, z, vx, vy, vz);
-}
-
-struct ItemGeom { int y0, z0, x0, xc; };
-
-__device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
-  ItemGeom it;
-  const int chunk = item / p.n_cols, col = item - chunk * p.n_cols;
-  const int yt = col / p.n_zt, zt = col - yt * p.n_zt;
-  it.y0 = yt * p.TY; it.z0 = zt * p.TZ;
-  it.x0 = (int)(((long long)chunk * p.g.nx) / p.n_chunks);
-  it.xc = (int)(((long long)(chunk + 1) * p.g.nx) / p.n_chunks) - it.x0;
-  return it;
-}
-
 // barrier block = {fullS, emptyS, fullU, emptyU} x JB_PAIR_BARS
 #define JB_PAIR_BARS JB_PAIR_MAX_RING
 
 // SPT: y sites per thread (x 2 z sites).  MOTIF1: one motif site, class constants through the constant bank.
+// 288 threads x 2 CTAs = 18 warps per SM = 5 per scheduler: 16384 / 5 -> at most 96 registers per thread (ptxas picks that
+// from the launch bounds; 104-112 registers silently drop the kernel to one CTA per SM: measured 0.32 instead of 0.24 ms)
 template <int STAGE, bool THERMAL, bool ISO, int SPT, bool MOTIF1>
-__global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
+__global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
                                                             const __grid_constant__ CUtensorMap tS2,
                                                             const __grid_constant__ CUtensorMap tU0,
@@ -432,8 +341,8 @@ __global__ void __launch_bounds__(544, 1) stage_pair_kernel(const __grid_constan
             if (zsh0 != 0 && ((ok0 >> k) & 1u)) { p.out[0][idx + zsh0] = ox.x; p.out[1][idx + zsh0] = oy.x; p.out[2][idx + zsh0] = oz.x; }
             if (zsh1 != 0 && ((ok1 >> k) & 1u)) { p.out[0][idx + 1 + zsh1] = ox.y; p.out[1][idx + 1 + zsh1] = oy.y; p.out[2][idx + 1 + zsh1] = oz.y; }
           } else {
-            if ((ok0 >> k) & 1u) pair_store_images(p, x, it.y0 + ty0 + k, m, z, ox.x, oy.x, oz.x);
-            if ((ok1 >> k) & 1u) pair_store_images(p, x, it.y0 + ty0 + k, m, z + 1, ox.y, oy.y, oz.y);
+            if ((ok0 >> k) & 1u) tile_store_images(p, x, it.y0 + ty0 + k, m, z, ox.x, oy.x, oz.x);
+            if ((ok1 >> k) & 1u) tile_store_images(p, x, it.y0 + ty0 + k, m, z + 1, ox.y, oy.y, oz.y);
           }
         }
       }

@@ -28,64 +28,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "jb_device.cuh"
+#include "jb_tma.cuh"
 
 namespace {
 
 using namespace jbdev;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// wait with back-off: a polling loop would steal issue slots from the warps that have work
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  uint32_t ok = 0;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (ns) __nanosleep(ns);
-  }
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
-
-// ghost images of a boundary site (rare path, out of line).  The parameter block is __grid_constant__, so its address
-// can be handed over without a local copy: no stack frame in the hot kernel.
-__device__ __noinline__ void tile_store_images(const JbTileParams &p, int x, int y, int m, int z, double vx, double vy, double vz) {
-  JbOutBoxes boxes;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { boxes.out[c] = p.out[c]; boxes.out_lo[c] = p.out_lo[c]; boxes.out_hi[c] = p.out_hi[c]; }
-  store_images_inline(p.g, boxes, x, y, m, z, vx, vy, vz);
-}
-
-struct ItemGeom { int y0, z0, x0, xc; };
-
-__device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
-  ItemGeom it;
-  const int chunk = item / p.n_cols, col = item - chunk * p.n_cols;
-  const int yt = col / p.n_zt, zt = col - yt * p.n_zt;
-  it.y0 = yt * p.TY; it.z0 = zt * p.TZ;
-  it.x0 = (int)(((long long)chunk * p.g.nx) / p.n_chunks);
-  it.xc = (int)(((long long)(chunk + 1) * p.g.nx) / p.n_chunks) - it.x0;
-  return it;
-}
 
 #define JB_TILE_BARS 8   // max ring depth; barrier block = {fullS, emptyS, fullU, emptyU} x JB_TILE_BARS
 

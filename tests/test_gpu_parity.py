@@ -230,7 +230,8 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
     dims = (16, 6, 10)
@@ -245,6 +246,7 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     def new_ctx(rank, n):
         nx = dims[0] // n
         c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
+        c.set_option("kernel", kernel)   # 2: two launches per step, two halo exchanges; 3: fused step, one exchange two planes deep
         c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
         c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
         return c
