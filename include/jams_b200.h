@@ -151,6 +151,15 @@ JB_API int jb_export_spins(jb_ctx *ctx, double *s_aos, int32_t on_device);
 JB_API int jb_step(jb_ctx *ctx, int32_t nsteps, double dt_ps, double time_ps, double temperature_K,
             uint64_t seed, uint64_t first_step_index, int32_t gilbert_prefactor);
 
+/* nsteps calls of CudaRK4BaseSolver::run with CUDALLGRK4Solver::function_kernel (module "llg-rk4-gpu":
+ * solvers/cuda_rk4_base.cu:50-108, solvers/cuda_llg_rk4.cu:17-34, cuda_llg_rk4_kernel.cuh:11-58,
+ * cuda_rk4_base_kernel.cuh:1-19, cuda/cuda_spin_ops.cu:4-17): classical RK4 on the LLG right hand side with one
+ * white-noise draw per step, unnormalised intermediate states and a normalisation after the combination.  Four
+ * launches per step, each fusing the field evaluation, k_i, the next stage input and the running sum of the k's.
+ * Arguments as jb_step.  One slab (n_ranks == 1) and a translation-invariant exchange template only. */
+JB_API int jb_step_rk4(jb_ctx *ctx, int32_t nsteps, double dt_ps, double time_ps, double temperature_K,
+                uint64_t seed, uint64_t first_step_index, int32_t gilbert_prefactor);
+
 /* Thermostat::device_data() equivalent (core/thermostat.h:22-34): the white-noise field
  * xi_ij = sigma_i sqrt(T) n_ij in Tesla that jb_step uses at step `step_index`, N x 3.
  * With normals_only != 0 the raw N(0,1) draws n_ij are returned instead. */

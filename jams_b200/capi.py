@@ -48,6 +48,7 @@ SIGNATURES = {
     "jb_import_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_export_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
+    "jb_step_rk4": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
     "jb_noise": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "jb_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32]),
     "jb_energies": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
@@ -211,6 +212,10 @@ class Context:
     def step(self, nsteps, dt_ps, time_ps=0.0, temperature=0.0, seed=0, first_step=0, gilbert_prefactor=False):
         self._ck(self.lib.jb_step(self.h, int(nsteps), float(dt_ps), float(time_ps), float(temperature),
                                   int(seed), int(first_step), int(gilbert_prefactor)))
+
+    def step_rk4(self, nsteps, dt_ps, time_ps=0.0, temperature=0.0, seed=0, first_step=0, gilbert_prefactor=False):
+        self._ck(self.lib.jb_step_rk4(self.h, int(nsteps), float(dt_ps), float(time_ps), float(temperature),
+                                      int(seed), int(first_step), int(gilbert_prefactor)))
 
     def noise(self, dt_ps, temperature, seed, step, gilbert_prefactor=False, normals_only=False):
         out = np.empty((self.N, 3))

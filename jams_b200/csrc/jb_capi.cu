@@ -64,6 +64,8 @@ void release_state(jb_ctx *c) {
     c->S0[k] = c->S1[k] = nullptr;
     if (c->U[k]) cudaFree(c->U[k]);
     c->U[k] = nullptr;
+    if (c->V[k]) cudaFree(c->V[k]);
+    c->V[k] = nullptr;
   }
   c->flags = nullptr;
   c->state_allocated = false;
@@ -289,6 +291,7 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
       cl.fTx = f[0] * cl.inv_mu; cl.fTy = f[1] * cl.inv_mu; cl.fTz = f[2] * cl.inv_mu;
       cl.KpT = cl.Kp * cl.inv_mu;
       cl.c_full = -gyro * dt; cl.c_half = -gyro * (0.5 * dt);
+      cl.gyro = gyro;
       tab[s * nc + k] = cl;
     }
   }
@@ -1077,6 +1080,56 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           c->epoch++;
           JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
         }
+      }
+    }
+    done += chunk;
+  }
+  return JB_OK;
+}
+
+
+int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint64_t seed, uint64_t first_step, int32_t gilbert) {
+  if (!c || nsteps < 0 || !(dt > 0.0) || T < 0.0) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  if (c->d.n_ranks > 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 runs on one slab only in this version (the second stage-input box is not peer-mapped)");
+  if (c->has_pairs) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 needs a translation-invariant exchange template (jb_set_exchange_template, or jb_set_exchange_pairs with template detection)");
+  if (!c->V[0]) {   // second stage-input box, ghosts included (zero across open boundaries like the other boxes)
+    const size_t comp = ((size_t)c->g.elems * sizeof(double) + 255) / 256 * 256;
+    for (int k = 0; k < 3; ++k) {
+      JB_CUDA(c, cudaMalloc(&c->V[k], comp));
+      JB_CUDA(c, cudaMemsetAsync(c->V[k], 0, comp, c->stream));
+    }
+  }
+  const bool periodic_x = c->g.per[0] && c->g.gx > 0;
+  for (int done = 0; done < nsteps;) {
+    const int chunk = c->has_ac ? std::min(nsteps - done, 1024) : nsteps - done;
+    std::vector<double> times;
+    if (c->has_ac) {   // fields at t0, t0 + dt/2 (k2 and k3), t0 + dt (cuda_rk4_base.cu:70-71,78-79,86-87)
+      for (int n = 0; n < chunk; ++n) { const double t0 = time_ps + (done + n) * dt; times.push_back(t0); times.push_back(t0 + 0.5 * dt); times.push_back(t0 + dt); }
+    } else {
+      times.push_back(time_ps);
+    }
+    rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
+    for (int n = 0; n < chunk; ++n) {
+      for (int stage = 0; stage < 4; ++stage) {
+        JbStageParams p{};
+        p.g = c->g;
+        const int tsel = stage == 0 ? 0 : (stage == 3 ? 2 : 1);
+        fill_tables(c, p.t, c->has_ac ? 3 * n + tsel : 0);
+        double *const *in = stage == 0 ? c->S0 : (stage == 2 ? c->V : c->S1);          // S0 -> S1 -> V -> S1 -> S0
+        double *const *out = stage == 0 ? c->S1 : (stage == 1 ? c->V : (stage == 2 ? c->S1 : c->S0));
+        for (int k = 0; k < 3; ++k) {
+          p.in[k] = in[k]; p.out[k] = out[k]; p.u[k] = c->U[k]; p.s_old[k] = c->S0[k];
+          p.out_lo[k] = periodic_x ? out[k] : nullptr; p.out_hi[k] = periodic_x ? out[k] : nullptr;
+        }
+        p.seed = seed; p.step = first_step + (uint64_t)(done + n);
+        p.thermal = T > 0.0 ? 1 : 0;
+        p.dt = dt;
+        record_event(c, 0);
+        JB_CUDA(c, jbk_rk4_stage_direct(p, stage, c->stream));
+        c->launches++;
+        record_event(c, 1);
       }
     }
     done += chunk;

@@ -63,6 +63,7 @@ struct JbClass {
   double fTx, fTy, fTz;  // the same divided by mu_i, Tesla
   int power;          // 0 = no uniaxial term
   int pad;
+  double gyro;        // gyro_i (rad / ps / T): the RK4 stages need k = -gyro (...) without the step folded in
 };
 
 // one entry of the exchange template of a motif site, in ghosted-box terms
@@ -96,6 +97,10 @@ struct JbStageParams {
   double *u[3];          // Heun intermediate u = s_n + dt/2 k1 (written in A, read in B), interior only used
   unsigned long long seed, step;
   int thermal;
+  // RK4 (jb_step_rk4): the state at the start of the step (own site only), the step, and where the running sum
+  // k1 + 2 k2 + 2 k3 lives is `u`
+  const double *s_old[3];
+  double dt;
 };
 
 // ---- parameter block of the persistent TMA tile kernel (jb_stage_tile.cu) ------------------------------
@@ -220,6 +225,7 @@ struct jb_ctx {
   double *S0[3] = {nullptr, nullptr, nullptr};
   double *S1[3] = {nullptr, nullptr, nullptr};
   double *U[3] = {nullptr, nullptr, nullptr};
+  double *V[3] = {nullptr, nullptr, nullptr};     // second stage-input box of the RK4 solver (allocated on first use)
   bool state_allocated = false;
   double *d_aos = nullptr; size_t d_aos_bytes = 0;     // staging for host <-> device AoS
   double *d_scratch = nullptr; size_t d_scratch_bytes = 0;  // per-spin scalars / reductions
@@ -264,6 +270,9 @@ cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3],
 cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream);
 cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream);
 cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
+// one of the four RK4 stages (stage 0..3), direct gathers: in = stage input (with neighbours), out = next stage input
+// (stages 0-2) or the new spins (stage 3), u = running sum of the k's, s_old = spins at the start of the step
+cudaError_t jbk_rk4_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
 // persistent TMA tile kernel: tmaps = {S.x, S.y, S.z, U.x, U.y, U.z}; spt in {1,2,4}; grid = number of CTAs
 // `threads` counts the consumer threads; the launch adds one producer warp
 cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,

@@ -157,6 +157,90 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
   store_with_images(p, x, y, m, z, ox, oy, oz);
 }
 
+
+// =================================================================================================
+// RK4-LLG (llg-rk4-gpu: solvers/cuda_rk4_base.cu:50-108, cuda_llg_rk4_kernel.cuh:11-58), one launch per stage.
+// The reference runs per stage: field kernels + field sum, cuda_llg_rk4_kernel (k_i), cublasDcopy + cublasDaxpy
+// (next stage input) and keeps k1..k4 as four N x 3 arrays; here a stage launch evaluates the fields, k_i, the next
+// stage input y = s_old + a_i dt k_i (not normalised, as in the reference) and the running sum k1 + 2 k2 + 2 k3 in one
+// pass; the last stage applies cuda_rk4_combination_kernel (cuda_rk4_base_kernel.cuh:16) and the normalisation
+// (cuda/cuda_spin_ops.cu:4-17, here with the zero-length guard of Vec3 unit_vector).
+//   HBM bytes per spin: 72 + 120 + 120 + 96 = 408 per step (reference: > 2.5 kB).
+// =================================================================================================
+template <int STAGE, bool THERMAL, bool ISO>
+__global__ void __launch_bounds__(256) rk4_direct_kernel(const __grid_constant__ JbStageParams p) {
+  const JbGeom &g = p.g;
+  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= total) return;
+  int x, y, m, z;
+  decode_site(g, q, x, y, m, z);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
+  const double *__restrict__ inx = p.in[0];
+  const double *__restrict__ iny = p.in[1];
+  const double *__restrict__ inz = p.in[2];
+  const double sx = inx[ic], sy = iny[ic], sz = inz[ic];
+
+  double hx = 0.0, hy = 0.0, hz = 0.0;
+  const int nb = p.t.nbr_begin[m], ne = p.t.nbr_begin[m + 1];
+  for (int n = nb; n < ne; ++n) {
+    const JbNbr e = p.t.nbr_global[n];
+    const long long j = ic + (long long)e.dx * g.sX + e.delta;
+    const double jx = inx[j], jy = iny[j], jz = inz[j];
+    if (ISO) {
+      hx = fma(e.J, jx, hx); hy = fma(e.J, jy, hy); hz = fma(e.J, jz, hz);
+    } else {
+      const double *__restrict__ J = p.t.Jtab + 9 * e.jidx;
+      hx += J[0] * jx + J[1] * jy + J[2] * jz;
+      hy += J[3] * jx + J[4] * jy + J[5] * jz;
+      hz += J[6] * jx + J[7] * jy + J[8] * jz;
+    }
+  }
+  const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
+  const JbClass &c = p.t.classes[ci];
+  hx = fma(hx, c.inv_mu, c.fTx); hy = fma(hy, c.inv_mu, c.fTy); hz = fma(hz, c.inv_mu, c.fTz);   // Tesla
+  if (c.power != 0) {  // uniaxial (uniaxial_anisotropy.cc:155-163), here / mu
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    double pw = d;
+    if (c.power >= 4) pw = d * d * d;
+    if (c.power >= 6) pw = pw * d * d;
+    const double f = c.KpT * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  if (THERMAL) {   // one draw per step, all four stages (cuda_rk4_base.cu:65)
+    double n0, n1, n2;
+    site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+    hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz);
+  }
+  // cuda_llg_rk4_kernel.cuh:36-56
+  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;
+  const double mg = -c.gyro;
+  const double kx = mg * (ax_ + c.alpha * bx_), ky = mg * (ay_ + c.alpha * by_), kz = mg * (az_ + c.alpha * bz_);
+
+  double ox, oy, oz;
+  if (STAGE == 0) {          // y1 = s_old + dt/2 k1 ; sum = k1
+    const double a = 0.5 * p.dt;
+    ox = sx + a * kx; oy = sy + a * ky; oz = sz + a * kz;
+    p.u[0][ic] = kx; p.u[1][ic] = ky; p.u[2][ic] = kz;
+  } else {
+    const double s0x = p.s_old[0][ic], s0y = p.s_old[1][ic], s0z = p.s_old[2][ic];
+    const double ux = p.u[0][ic], uy = p.u[1][ic], uz = p.u[2][ic];
+    if (STAGE == 1 || STAGE == 2) {   // y = s_old + a dt k ; sum += 2 k
+      const double a = (STAGE == 1) ? 0.5 * p.dt : p.dt;
+      ox = s0x + a * kx; oy = s0y + a * ky; oz = s0z + a * kz;
+      p.u[0][ic] = ux + 2 * kx; p.u[1][ic] = uy + 2 * ky; p.u[2][ic] = uz + 2 * kz;
+    } else {                          // s = unit(s_old + dt (k1 + 2 k2 + 2 k3 + k4) / 6)
+      const double vx = s0x + p.dt * (ux + kx) / 6.0, vy = s0y + p.dt * (uy + ky) / 6.0, vz = s0z + p.dt * (uz + kz) / 6.0;
+      const double n2_ = vx * vx + vy * vy + vz * vz;
+      const double r = rsqrt_nobranch(n2_);
+      const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;
+      ox = vx * inv; oy = vy * inv; oz = vz * inv;
+    }
+  }
+  store_with_images(p, x, y, m, z, ox, oy, oz);
+}
+
 // =================================================================================================
 // stage kernel, variant 2: general neighbour list (ELL, explicit int32 indices)
 // =================================================================================================
@@ -464,6 +548,21 @@ cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t str
   const long long total = (long long)p.g.nx * p.g.Ny * p.g.Nz * p.g.M;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   JB_DISPATCH_STAGE(stage_direct_kernel, (k<<<blocks, 256, 0, stream>>>(p)));
+  return cudaGetLastError();
+}
+
+
+cudaError_t jbk_rk4_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream) {
+  const long long total = (long long)p.g.nx * p.g.Ny * p.g.Nz * p.g.M;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  const bool th = p.thermal != 0, iso = p.t.iso != 0;
+#define JB_RK4_CASE(ST) \
+  if (stage == ST) { \
+    if (th) { if (iso) rk4_direct_kernel<ST, true, true><<<blocks, 256, 0, stream>>>(p); else rk4_direct_kernel<ST, true, false><<<blocks, 256, 0, stream>>>(p); } \
+    else    { if (iso) rk4_direct_kernel<ST, false, true><<<blocks, 256, 0, stream>>>(p); else rk4_direct_kernel<ST, false, false><<<blocks, 256, 0, stream>>>(p); } \
+  }
+  JB_RK4_CASE(0) JB_RK4_CASE(1) JB_RK4_CASE(2) JB_RK4_CASE(3)
+#undef JB_RK4_CASE
   return cudaGetLastError();
 }
 

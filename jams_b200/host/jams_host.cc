@@ -607,7 +607,8 @@ void EnergyMonitor::update(B200HeunLLGSolver &solver) {   // monitors/energy.cc:
 // Solver
 // =====================================================================================================
 B200HeunLLGSolver::B200HeunLLGSolver(const Setting &settings, const Lattice &lattice, uint64_t seed) : lattice_(lattice), seed_(seed) {
-  // solvers/cuda_llg_heun.cu:21-37
+  // solvers/cuda_llg_heun.cu:21-37 / solvers/cuda_rk4_base.cu:10-29 (same keys)
+  rk4_ = lowercase(settings.required("module").as_string()).find("rk4") != std::string::npos;
   step_size_ = settings.required("t_step").as_double() / 1e-12;
   const double t_max = settings.required("t_max").as_double() / 1e-12;
   const double t_min = settings.get("t_min", 0.0) / 1e-12;
@@ -657,7 +658,8 @@ std::vector<double> B200HeunLLGSolver::spins() {
 
 void B200HeunLLGSolver::run_steps(int n) {
   build();
-  check(jb_step(ctx_, n, step_size_, time_, physics_->temperature(), seed_, static_cast<uint64_t>(iteration_), lattice_.gilbert_prefactor ? 1 : 0));
+  check((rk4_ ? jb_step_rk4 : jb_step)(ctx_, n, step_size_, time_, physics_->temperature(), seed_, static_cast<uint64_t>(iteration_),
+                                       lattice_.gilbert_prefactor ? 1 : 0));
   iteration_ += n;
   time_ = iteration_ * step_size_;   // solvers/cuda_llg_heun.cu:120-121
 }
@@ -716,8 +718,9 @@ Simulation::Simulation(const std::vector<std::string> &config_args, const std::s
   lattice_.reset(new Lattice(*config_));
   const Setting &solver_settings = config_->required("solver");
   const std::string module = lowercase(solver_settings.required("module").as_string());
-  if (module != "llg-heun-b200-gpu" && module != "llg-heun-gpu" && module != "llg-heun-cpu")   // Solver::create (core/solver.cc:60-77)
-    throw std::runtime_error("unknown solver " + solver_settings["module"].as_string() + " (this host layer provides the llg-heun path only)");
+  if (module != "llg-heun-b200-gpu" && module != "llg-heun-gpu" && module != "llg-heun-cpu" &&
+      module != "llg-rk4-b200-gpu" && module != "llg-rk4-gpu")   // Solver::create (core/solver.cc:60-77)
+    throw std::runtime_error("unknown solver " + solver_settings["module"].as_string() + " (this host layer provides the llg-heun and llg-rk4 paths only)");
   solver_.reset(new B200HeunLLGSolver(solver_settings, *lattice_, seed));
   solver_->register_physics_module(new Physics(config_->find("physics")));
   if (!config_->exists("hamiltonians")) throw std::runtime_error("No hamiltonians group in config");

@@ -234,7 +234,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
   B200HeunLLGSolver(const Setting &settings, const Lattice &lattice, uint64_t seed);
   ~B200HeunLLGSolver();
 
-  std::string name() const { return "llg-heun-b200-gpu"; }
+  std::string name() const { return rk4_ ? "llg-rk4-b200-gpu" : "llg-heun-b200-gpu"; }
   bool is_cuda_solver() const { return true; }
   bool is_running() const { return iteration_ < max_steps_; }
   int iteration() const { return iteration_; }
@@ -250,7 +250,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
 
   void set_spins(const std::vector<double> &s_aos);   // globals::s = ...
   std::vector<double> spins();                         // globals::s
-  void run();                                          // one Heun step (core/jams++.cc:341)
+  void run();                                          // one Heun (or RK4) step (core/jams++.cc:341)
   void run_steps(int n);                               // n steps without returning to the host in between
   void notify_monitors();                              // core/solver.cc:110-116
   std::vector<double> compute_fields();                // globals::h = sum_k field_k
@@ -265,6 +265,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
   const Lattice &lattice_;
   jb_ctx *ctx_ = nullptr;
   bool built_ = false;
+  bool rk4_ = false;      // module "llg-rk4-b200-gpu" / "llg-rk4-gpu": CudaRK4BaseSolver::run (solvers/cuda_rk4_base.cu:50-108)
   int iteration_ = 0, max_steps_ = 0, min_steps_ = 0;
   double time_ = 0.0, step_size_ = 1.0;
   uint64_t seed_ = 0;

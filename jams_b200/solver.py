@@ -402,9 +402,27 @@ class B200HeunLLGSolver(Solver):
         return self.comm.allreduce_sum(arr) if self.comm and self.n_ranks > 1 else arr
 
 
+class B200RK4LLGSolver(B200HeunLLGSolver):
+    """``module = "llg-rk4-b200-gpu"``: drop-in alternative to ``llg-rk4-gpu`` (CudaRK4BaseSolver + CUDALLGRK4Solver,
+    solvers/cuda_rk4_base.cu:10-108, solvers/cuda_llg_rk4.cu:17-34).  Same settings keys as the Heun solver
+    (cuda_rk4_base.cu:12-29); the shipped example runs this integrator with a ten times larger ``t_step``
+    (examples/bloch_domain_wall/bloch_domain_wall.cfg:75-81)."""
+    name = "llg-rk4-b200-gpu"
+
+    def run(self, nsteps: int = 1):
+        """``nsteps`` RK4 steps (cuda_rk4_base.cu:50-108)"""
+        self._build()
+        self.ctx.step_rk4(nsteps, self.step_size, self.time, self.temperature, self.seed, self.iteration,
+                          self.lattice.gilbert_prefactor)
+        self.iteration += nsteps
+        self.time = self.iteration * self.step_size   # cuda_rk4_base.cu:105-106
+
+
 def create_solver(settings: dict, lattice: Lattice, comm=None) -> Solver:
     """Solver::create (core/solver.cc:60-77)"""
     module = str(settings["module"]).lower()
     if module == "llg-heun-b200-gpu":
         return B200HeunLLGSolver(settings, lattice, comm)
+    if module == "llg-rk4-b200-gpu":
+        return B200RK4LLGSolver(settings, lattice, comm)
     raise RuntimeError("unknown solver " + str(settings["module"]))

@@ -113,6 +113,8 @@ def restatement() -> _Lib:
         L.jo_magnetisation.argtypes = [C.c_int64, _c_double_p, _c_double_p, C.c_int, _c_int_p, _c_double_p]
         L.jo_spin_temperature.restype = C.c_double
         L.jo_spin_temperature.argtypes = [C.c_int64, _c_double_p, _c_double_p]
+        L.jo_sim_run_rk4.restype = None
+        L.jo_sim_run_rk4.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.jo_sim_term_energies.restype = None
         L.jo_sim_term_energies.argtypes = [C.c_void_p, C.c_int, C.c_double, _c_double_p]
         _libs["jo"] = lib
@@ -336,6 +338,18 @@ class CpuSim:
             self.L.sim_run(self.h, int(nsteps), normals.ctypes.data)
         else:
             self.L.sim_run(self.h, int(nsteps), None)
+
+    def run_rk4(self, nsteps=1, normals=None):
+        """CudaRK4BaseSolver::run restated on the host (restatement library only: the reference has no CPU RK4)"""
+        fn = getattr(self.L.lib, self.L.prefix + "sim_run_rk4", None)
+        if fn is None:
+            raise RuntimeError("run_rk4 exists in the restatement library only")
+        if normals is not None:
+            normals = _f64(normals, (-1,))
+            assert normals.size == nsteps * 3 * self.N
+            fn(C.c_void_p(self.h), int(nsteps), C.c_void_p(normals.ctypes.data))
+        else:
+            fn(C.c_void_p(self.h), int(nsteps), None)
 
     def term_fields(self, term, time=0.0):
         f = np.zeros(3 * self.N)

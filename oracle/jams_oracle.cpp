@@ -561,6 +561,68 @@ void heun_run(Sim &sim, const double *normals) {
   sim.time = sim.iteration * sim.dt;
 }
 
+// CudaRK4BaseSolver::run (solvers/cuda_rk4_base.cu:50-108) with CUDALLGRK4Solver::function_kernel
+// (solvers/cuda_llg_rk4.cu:17-29, cuda_llg_rk4_kernel.cuh:11-58) and post_step = normalise_spins_cuda
+// (cuda/cuda_spin_ops.cu:4-17).  The reference has no CPU RK4 solver: this is the CUDA solver's arithmetic on the
+// host.  One noise draw per step (update_thermostat, :65) serves all four stages; the intermediate states
+// s_old + a k are NOT normalised; the fields of k2/k3 are evaluated at t0 + dt/2, those of k4 at t0 + dt.
+// Deviation: cuda_normalise_spins_kernel has no zero-length guard (a vacancy would become NaN); here, as in
+// Vec3 unit_vector (containers/vec3.h:276-283), vectors of length <= DBL_EPSILON are left unchanged.
+void rk4_function(Sim &sim, std::vector<double> &k) {
+  const int N = sim.N;
+  compute_fields(sim);   // cuda_llg_rk4.cu:18
+#pragma omp parallel for
+  for (int i = 0; i < N; ++i) {   // cuda_llg_rk4_kernel.cuh:25-57
+    V3 h, s;
+    for (int n = 0; n < 3; ++n) h[n] = ((sim.h[3 * i + n] / sim.mus[i]) + sim.w[3 * i + n]);
+    for (int n = 0; n < 3; ++n) s[n] = sim.s[3 * i + n];
+    const V3 sxh = {(s[1] * h[2] - s[2] * h[1]), (s[2] * h[0] - s[0] * h[2]), (s[0] * h[1] - s[1] * h[0])};
+    const V3 sxsxh = {(s[1] * sxh[2] - s[2] * sxh[1]), (s[2] * sxh[0] - s[0] * sxh[2]), (s[0] * sxh[1] - s[1] * sxh[0])};
+    for (int n = 0; n < 3; ++n) k[3 * i + n] = -sim.gyro[i] * (sxh[n] + sim.alpha[i] * sxsxh[n]);
+  }
+}
+
+void rk4_run(Sim &sim, const double *normals) {
+  const int N = sim.N;
+  const double t0 = sim.time;
+  sim.s_old = sim.s;   // :54-58
+  // update_thermostat (:65): CudaThermostatClassical::update (thermostats/cuda_thermostat_classical.cc:47-56)
+  if (sim.temperature > 0.0) {
+    if (normals) std::copy(normals, normals + 3 * N, sim.w.begin());
+    else { std::normal_distribution<> nd; for (auto &x : sim.w) x = nd(sim.rng); }
+    const double sqrt_temperature = sqrt(sim.temperature);
+    for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) sim.w[3 * i + j] = sim.w[3 * i + j] * sim.sigma[i] * sqrt_temperature;
+  } else {
+    std::fill(sim.w.begin(), sim.w.end(), 0.0);
+  }
+  std::vector<double> k1(3 * N), k2(3 * N), k3(3 * N), k4(3 * N);
+  auto axpy_from_old = [&](double a, const std::vector<double> &k) {   // cublasDcopy + cublasDaxpy (:73-74, :81-82, :89-90)
+    for (int n = 0; n < 3 * N; ++n) sim.s[n] = sim.s_old[n] + a * k[n];
+  };
+  rk4_function(sim, k1);                         // :68
+  sim.time = t0 + 0.5 * sim.dt;                  // :70-71
+  axpy_from_old(0.5 * sim.dt, k1);
+  rk4_function(sim, k2);                         // :76
+  sim.time = t0 + 0.5 * sim.dt;                  // :78-79
+  axpy_from_old(0.5 * sim.dt, k2);
+  rk4_function(sim, k3);                         // :84
+  sim.time = t0 + sim.dt;                        // :86-87
+  axpy_from_old(sim.dt, k3);
+  rk4_function(sim, k4);                         // :92
+  for (int i = 0; i < N; ++i) {
+    V3 v;
+    for (int n = 0; n < 3; ++n) {                // cuda_rk4_base_kernel.cuh:16: s_old + dt * (k1 + 2 k2 + 2 k3 + k4) / 6.0
+      const int q = 3 * i + n;
+      v[n] = sim.s_old[q] + sim.dt * (k1[q] + 2 * k2[q] + 2 * k3[q] + k4[q]) / 6.0;
+    }
+    const double n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];   // cuda_spin_ops.cu:9-15: s * rsqrt(s.s)
+    const double r = (n2 > DBL_EPSILON * DBL_EPSILON) ? 1.0 / sqrt(n2) : 1.0;
+    for (int n = 0; n < 3; ++n) sim.s[3 * i + n] = v[n] * r;
+  }
+  sim.iteration++;                               // :105-106
+  sim.time = sim.iteration * sim.dt;
+}
+
 }  // namespace
 
 extern "C" {
@@ -685,6 +747,11 @@ void jo_sim_init_solver(void *p, double step_size_ps, int use_gilbert_prefactor,
 void jo_sim_get_sigma(void *p, double *sigma) { auto *sim = static_cast<Sim *>(p); std::copy(sim->sigma.begin(), sim->sigma.end(), sigma); }
 void jo_sim_set_temperature(void *p, double T) { static_cast<Sim *>(p)->temperature = T; }
 double jo_sim_time(void *p) { return static_cast<Sim *>(p)->time; }
+
+void jo_sim_run_rk4(void *p, int nsteps, const double *normals) {
+  auto *sim = static_cast<Sim *>(p);
+  for (int n = 0; n < nsteps; ++n) rk4_run(*sim, normals ? normals + std::size_t(n) * 3 * sim->N : nullptr);
+}
 
 void jo_sim_run(void *p, int nsteps, const double *normals) {
   auto *sim = static_cast<Sim *>(p);

@@ -287,3 +287,77 @@ def test_error_behaviour_mirrors_the_reference():
         create_hamiltonian(dict(module="uniaxial", order="K7", anisotropies=[]), lat)
     with pytest.raises(RuntimeError, match="unknown hamiltonian"):
         create_hamiltonian(dict(module="dipole-fft"), lat)
+
+
+# ---- RK4-LLG: jb_step_rk4 against the restatement of CudaRK4BaseSolver::run ----
+def _rk4_solver(w, **kw):
+    from jams_b200.solver import create_solver
+    lat = w["lattice"]
+    s = create_solver(dict(module="llg-rk4-b200-gpu", t_step=W.T_STEP, t_max=1e-9, seed=kw.get("seed", 0), options=kw.get("options", {})), lat)
+    for h in w["hamiltonians"]:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    s.set_temperature(w.get("temperature", 0.0))
+    return s
+
+
+@pytest.mark.parametrize("make_w,steps", [(lambda: W.c3_sc(dims=(12, 9, 20)), 40), (lambda: W.c2_bcc_fe(6, temperature=0.0), 30),
+                                          (lambda: W.c1_bloch_wall((32, 6, 6)), 40), (lambda: W.c4_bcc_long_range(8), 8)])
+def test_rk4_T0_trajectories_match_oracle(make_w, steps):
+    w = make_w()
+    if "sc 12" in w["name"] or w["name"].startswith("C3"):
+        w["hamiltonians"].append(dict(module="uniaxial", order="K2", anisotropies=[("A", [0.0, 0.6, 0.8], 2e-23)]))
+    lat = w["lattice"]
+    s0 = w["spins"] if w.get("spins") is not None else random_unit_spins(lat.num_spins, 21)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    sim.run_rk4(steps)
+    s = _rk4_solver(w)
+    s.set_spins(s0)
+    s.run(steps)
+    got = s.spins()
+    assert np.abs(got - sim.get_spins()).max() <= TRAJ_TOL
+    assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() < 1e-14
+    # a Heun step afterwards continues from the RK4 state (shared device state)
+    s.ctx.step(3, s.step_size, s.time, 0.0, 0, s.iteration)
+    sim.run(3)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+
+
+def test_rk4_thermal_trajectory_matches_oracle_given_the_same_noise_and_ac_field():
+    """one noise draw per step for all four stages (cuda_rk4_base.cu:65); AC Zeeman field evaluated at t0, t0 + dt/2, t0 + dt"""
+    lat = Lattice([Material("A", 2.0, alpha=0.05)], np.eye(3), [("A", (0, 0, 0))], (8, 7, 10))
+    w = dict(name="sc ac", lattice=lat, temperature=40.0, spins=None,
+             hamiltonians=[dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 3.5e-21)]),
+                           dict(module="zeeman", dc_local_field=[[0.0, 0.0, 0.5]], ac_local_field=[[2.0, 0.0, 0.0]], ac_local_frequency=[0.5])])
+    steps, seed = 20, 4321
+    s = _rk4_solver(w, seed=seed)
+    s0 = random_unit_spins(lat.num_spins, 9)
+    s.set_spins(s0)
+    normals = np.stack([s.ctx.noise(s.step_size, 40.0, seed, n, normals_only=True) for n in range(steps)])
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    sim.run_rk4(steps, normals)
+    s.run(steps)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+
+
+def test_rk4_full_size_properties_and_fixed_point():
+    w = W.c3_sc(dims=(96, 96, 96))
+    lat = w["lattice"]
+    s = _rk4_solver(w)
+    up = np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1))
+    s.set_spins(up)
+    s.run(5)
+    assert np.array_equal(s.spins(), up)
+    s0 = lat.initial_spins(seed=2)
+    s.set_spins(s0)
+    e0 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
+    s.run(20)
+    out = s.spins()
+    e1 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
+    assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14 and e1 < e0
+    # Heun from the same start stays within its own (second-order) error of the RK4 trajectory
+    h = make(w)
+    h.set_spins(s0)
+    h.run(20)
+    assert np.abs(h.spins() - out).max() < 1e-4

@@ -99,7 +99,7 @@ def test_known_neighbour_count_sc_8_cubed():
 
 def test_error_behaviour_mirrors_the_reference():
     with pytest.raises(host.HostError, match="unknown solver"):
-        host.run(FIXTURE, 'solver : { module = "llg-rk4-gpu"; };', num_spins=512)
+        host.run(FIXTURE, 'solver : { module = "monte-carlo-metropolis-cpu"; };', num_spins=512)
     with pytest.raises(host.HostError, match="energy units"):
         host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { energy_units = "furlongs"; } );', ham_index=1)
     with pytest.raises(host.HostError, match="Multiple interactions"):   # core/interactions.cc:373-381
