@@ -181,6 +181,20 @@ JB_API int jb_energies(jb_ctx *ctx, int32_t term, double time_ps, double *e, int
  * group_of_spin (N, values in [0,n_groups)) or NULL for a single group. */
 JB_API int jb_magnetisation(jb_ctx *ctx, int32_t n_groups, const int32_t *group_of_spin, double *M4);
 
+/* ---- physics hooks that rewrite spins on the device ------------------------------------------ */
+/* PinnedBoundariesPhysics (physics/pinned_boundaries.cc:12-46) keeps the magnetisation direction of an edge region by
+ * rotating its spins every iteration.  A region is a list of local site ids (reference order, what
+ * PinnedBoundary::indices holds); up to JB_MAX_REGIONS of them.
+ *   jb_region_moment  M4 = {sum mu_i s_i (x,y,z), sum mu_i} over the region
+ *                     (jams::vector_field_indexed_scale_and_reduce_cuda / jams::sum_spins_moments, helpers/spinops.cc:55-67)
+ *   jb_rotate_region  s_i <- R s_i, R row-major 3x3 (jams::rotate_spins_cuda, cuda/cuda_spin_ops.cu:29-60), ghost images
+ *                     refreshed.  The adapter computes R = rotation_matrix_between_vectors(M, pinned_magnetisation)
+ *                     (containers/mat3.h:334-366) between the two calls; with several slabs it all-reduces M first. */
+#define JB_MAX_REGIONS 8
+JB_API int jb_set_region(jb_ctx *ctx, int32_t region, int32_t n_sites, const int32_t *site_index);
+JB_API int jb_region_moment(jb_ctx *ctx, int32_t region, double *M4);
+JB_API int jb_rotate_region(jb_ctx *ctx, int32_t region, const double *R9);
+
 /* ---- multi-GPU halo plumbing (no reference counterpart) ------------------------- */
 /* Each rank exports one opaque handle blob (JB_HALO_HANDLE_BYTES) describing its device buffers;
  * the host layer all-gathers the blobs (torch.distributed / MPI / files) and hands every rank the

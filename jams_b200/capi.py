@@ -48,6 +48,9 @@ SIGNATURES = {
     "jb_import_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_export_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
+    "jb_set_region": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "jb_region_moment": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "jb_rotate_region": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "jb_step_rk4": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
     "jb_noise": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "jb_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32]),
@@ -212,6 +215,20 @@ class Context:
     def step(self, nsteps, dt_ps, time_ps=0.0, temperature=0.0, seed=0, first_step=0, gilbert_prefactor=False):
         self._ck(self.lib.jb_step(self.h, int(nsteps), float(dt_ps), float(time_ps), float(temperature),
                                   int(seed), int(first_step), int(gilbert_prefactor)))
+
+    # ---- physics hooks (PinnedBoundariesPhysics)
+    def set_region(self, region, site_index):
+        idx = np.ascontiguousarray(site_index, dtype=np.int32)
+        self._ck(self.lib.jb_set_region(self.h, int(region), int(idx.size), _ptr(idx)))
+
+    def region_moment(self, region):
+        out = np.zeros(4)
+        self._ck(self.lib.jb_region_moment(self.h, int(region), _ptr(out)))
+        return out
+
+    def rotate_region(self, region, R):
+        R = np.ascontiguousarray(R, dtype=np.float64).reshape(9)
+        self._ck(self.lib.jb_rotate_region(self.h, int(region), _ptr(R)))
 
     def step_rk4(self, nsteps, dt_ps, time_ps=0.0, temperature=0.0, seed=0, first_step=0, gilbert_prefactor=False):
         self._ck(self.lib.jb_step_rk4(self.h, int(nsteps), float(dt_ps), float(time_ps), float(temperature),

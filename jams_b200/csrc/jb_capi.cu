@@ -731,6 +731,7 @@ void jb_destroy(jb_ctx *c) {
   p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
+  for (int r = 0; r < JB_MAX_REGIONS; ++r) { p = c->d_region[r]; free_dev(p); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto ev : c->ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1215,6 +1216,55 @@ int jb_magnetisation(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin, 
   c->launches += 2 * n_groups;
   JB_CUDA(c, cudaMemcpyAsync(M4, out4, (size_t)4 * n_groups * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return JB_OK;
+}
+
+
+// ---- physics hooks: regions of spins (PinnedBoundariesPhysics, physics/pinned_boundaries.cc:12-46) --------------
+int jb_set_region(jb_ctx *c, int32_t region, int32_t n, const int32_t *sites) {
+  if (!c || region < 0 || region >= JB_MAX_REGIONS || n < 0 || (n > 0 && !sites)) return JB_ERR_INVALID;
+  for (int k = 0; k < n; ++k) if (sites[k] < 0 || sites[k] >= c->N) JB_FAIL(c, JB_ERR_INVALID, "jb_set_region: site index out of range");
+  JB_CUDA(c, cudaSetDevice(c->device));
+  if (c->d_region[region]) { JB_CUDA(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_region[region]); c->d_region[region] = nullptr; }
+  c->region_n[region] = n;
+  if (n > 0) {
+    JB_CUDA(c, cudaMalloc(&c->d_region[region], (size_t)n * sizeof(int)));
+    JB_CUDA(c, cudaMemcpy(c->d_region[region], sites, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return JB_OK;
+}
+
+int jb_region_moment(jb_ctx *c, int32_t region, double *M4) {
+  if (!c || !M4 || region < 0 || region >= JB_MAX_REGIONS) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  if (c->d_classes == nullptr) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
+  if (c->region_n[region] == 0) { M4[0] = M4[1] = M4[2] = M4[3] = 0.0; return JB_OK; }
+  JbTables t; fill_tables(c, t, 0);
+  rc = ensure_scratch(c, (size_t)(4096 + 8) * sizeof(double)); if (rc) return rc;
+  double *partial = c->d_scratch, *out4 = c->d_scratch + 4096;
+  const double *s[3] = {c->S0[0], c->S0[1], c->S0[2]};
+  JB_CUDA(c, jbk_region_moment(c->g, t, s, c->d_region[region], c->region_n[region], partial, out4, c->stream));
+  c->launches += 2;
+  JB_CUDA(c, cudaMemcpyAsync(M4, out4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return JB_OK;
+}
+
+int jb_rotate_region(jb_ctx *c, int32_t region, const double *R9) {
+  if (!c || !R9 || region < 0 || region >= JB_MAX_REGIONS) return JB_ERR_INVALID;
+  if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
+  int rc = ensure_ready(c); if (rc) return rc;
+  const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
+  if (multi && !c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: jb_halo_connect has not been called");
+  double *lo[3], *hi[3];
+  for (int k = 0; k < 3; ++k) {
+    if (multi) { lo[k] = c->peer_lo_S0[k]; hi[k] = c->peer_hi_S0[k]; }
+    else if (c->g.per[0] && c->g.gx > 0) { lo[k] = c->S0[k]; hi[k] = c->S0[k]; }
+    else { lo[k] = nullptr; hi[k] = nullptr; }
+  }
+  JB_CUDA(c, jbk_region_rotate(c->g, c->S0, lo, hi, c->d_region[region], c->region_n[region], R9, c->stream));
+  c->launches++;
   return JB_OK;
 }
 

@@ -259,6 +259,9 @@ struct jb_ctx {
   unsigned long long epoch = 0;
   bool halo_connected = false;
 
+  // regions of spins (jb_set_region): device copies of the site lists
+  int *d_region[JB_MAX_REGIONS] = {nullptr}; int region_n[JB_MAX_REGIONS] = {0};
+
   // bookkeeping
   long long launches = 0;
   std::vector<cudaEvent_t> ev; size_t ev_used = 0;
@@ -301,6 +304,12 @@ cudaError_t jbk_energy(const JbGeom &g, const JbTables &t, const double *const s
 // sum mu_i s_i and sum mu_i per group -> out4 (n_groups x 4, device); scratch >= 4*n_groups*1024 doubles
 cudaError_t jbk_magnetisation(const JbGeom &g, const JbTables &t, const double *const s[3], int n_groups,
                               const int *group_of_spin, double *scratch, double *out4, cudaStream_t stream);
+// sum mu_i s_i and sum mu_i over the sites of a region -> out4 (device); scratch >= 4 * 1024 doubles
+cudaError_t jbk_region_moment(const JbGeom &g, const JbTables &t, const double *const s[3], const int *sites, int n,
+                              double *scratch, double *out4, cudaStream_t stream);
+// s_i <- R s_i for the sites of a region, ghost images included (lo / hi: boxes that receive the x images, or null)
+cudaError_t jbk_region_rotate(const JbGeom &g, double *const s[3], double *const lo[3], double *const hi[3], const int *sites, int n,
+                              const double R9[9], cudaStream_t stream);
 cudaError_t jbk_noise(const JbGeom &g, const JbTables &t, unsigned long long seed, unsigned long long step,
                       int normals_only, double *xi_aos, cudaStream_t stream);
 cudaError_t jbk_signal(unsigned long long *peer_lo_flag, unsigned long long *peer_hi_flag, unsigned long long epoch, cudaStream_t stream);

@@ -455,6 +455,58 @@ __global__ void __launch_bounds__(256) final_sum4_kernel(const double *__restric
   }
 }
 
+
+// =================================================================================================
+// region operations for PinnedBoundariesPhysics::update (physics/pinned_boundaries.cc:34-46): the moment of a set of
+// spins, sum mu_i s_i (jams::vector_field_indexed_scale_and_reduce_cuda, cuda/cuda_array_reduction.cu:432-470), and the
+// rotation of that set, s_i <- R s_i (cuda_rotate_spins_kernel, cuda/cuda_spin_ops.cu:29-43).  `sites` holds local site
+// ids in the reference order ((x Ny + y) Nz + z) M + m.
+// =================================================================================================
+__device__ __forceinline__ void decode_ref_site(const JbGeom &g, int site, int &x, int &y, int &m, int &z) {
+  unsigned q = (unsigned)site;
+  const unsigned um = (unsigned)g.M, uz = (unsigned)g.Nz, uy = (unsigned)g.Ny;
+  unsigned t = q / um; m = (int)(q - t * um); q = t;
+  t = q / uz; z = (int)(q - t * uz); q = t;
+  t = q / uy; y = (int)(q - t * uy);
+  x = (int)t;
+}
+
+__global__ void __launch_bounds__(256) region_moment_kernel(const JbGeom g, const JbTables t, const double *__restrict__ inx,
+                                                           const double *__restrict__ iny, const double *__restrict__ inz,
+                                                           const int *__restrict__ sites, int n, double *__restrict__ partial) {
+  __shared__ double sm[32];
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    int x, y, m, z;
+    decode_ref_site(g, sites[k], x, y, m, z);
+    const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
+    const long long q = (((long long)x * g.Ny + y) * g.M + m) * g.Nz + z;   // interior layout order [x][y][m][z]
+    const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
+    const double mu = t.classes[ci].mu;
+    a0 = fma(mu, inx[ic], a0); a1 = fma(mu, iny[ic], a1); a2 = fma(mu, inz[ic], a2); a3 += mu;
+  }
+  a0 = block_sum(a0, sm); a1 = block_sum(a1, sm); a2 = block_sum(a2, sm); a3 = block_sum(a3, sm);
+  if (threadIdx.x == 0) {
+    partial[4 * blockIdx.x] = a0; partial[4 * blockIdx.x + 1] = a1; partial[4 * blockIdx.x + 2] = a2; partial[4 * blockIdx.x + 3] = a3;
+  }
+}
+
+struct JbRot { double r[9]; };
+
+__global__ void __launch_bounds__(128) region_rotate_kernel(const JbGeom g, const JbOutBoxes o, const int *__restrict__ sites, int n, const JbRot R) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int x, y, m, z;
+  decode_ref_site(g, sites[k], x, y, m, z);
+  const long long ic = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
+  const double s0 = o.out[0][ic], s1 = o.out[1][ic], s2 = o.out[2][ic];
+  const double vx = R.r[0] * s0 + R.r[1] * s1 + R.r[2] * s2;   // cuda_spin_ops.cu:38-40
+  const double vy = R.r[3] * s0 + R.r[4] * s1 + R.r[5] * s2;
+  const double vz = R.r[6] * s0 + R.r[7] * s1 + R.r[8] * s2;
+  o.out[0][ic] = vx; o.out[1][ic] = vy; o.out[2][ic] = vz;
+  if (x_image_needed(g, x) | yz_image_needed(g, y, z)) store_images(g, o, x, y, m, z, vx, vy, vz);
+}
+
 __global__ void noise_kernel(const JbGeom g, const JbTables t, unsigned long long seed, unsigned long long step,
                              int normals_only, double *__restrict__ xi) {
   const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
@@ -612,6 +664,30 @@ cudaError_t jbk_magnetisation(const JbGeom &g, const JbTables &t, const double *
     if (err != cudaSuccess) return err;
   }
   return cudaSuccess;
+}
+
+
+cudaError_t jbk_region_moment(const JbGeom &g, const JbTables &t, const double *const s[3], const int *sites, int n,
+                              double *scratch, double *out4, cudaStream_t stream) {
+  int blocks = (n + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  region_moment_kernel<<<blocks, 256, 0, stream>>>(g, t, s[0], s[1], s[2], sites, n, scratch);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  final_sum4_kernel<<<1, 256, 0, stream>>>(scratch, blocks, out4);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_region_rotate(const JbGeom &g, double *const s[3], double *const lo[3], double *const hi[3], const int *sites, int n,
+                              const double R9[9], cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  JbOutBoxes o;
+  for (int c = 0; c < 3; ++c) { o.out[c] = s[c]; o.out_lo[c] = lo[c]; o.out_hi[c] = hi[c]; }
+  JbRot R;
+  for (int k = 0; k < 9; ++k) R.r[k] = R9[k];
+  region_rotate_kernel<<<(n + 127) / 128, 128, 0, stream>>>(g, o, sites, n, R);
+  return cudaGetLastError();
 }
 
 cudaError_t jbk_noise(const JbGeom &g, const JbTables &t, unsigned long long seed, unsigned long long step,

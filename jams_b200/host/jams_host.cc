@@ -523,9 +523,47 @@ AppliedFieldHamiltonian::AppliedFieldHamiltonian(const Setting &s, const Lattice
 Physics::Physics(const Setting *s) {   // core/physics.cc: temperature / applied_field of the `physics` group
   if (!s) return;
   const std::string module = lowercase(s->get("module", "empty"));
-  if (module != "empty") throw std::runtime_error("physics module '" + module + "' is not supported by the llg-heun-b200-gpu host layer");
+  if (module != "empty" && module != "pinned_boundaries")
+    throw std::runtime_error("physics module '" + module + "' is not supported by the llg-heun-b200-gpu host layer");
   temperature_ = s->get("temperature", 0.0);
   if (const Setting *f = s->find("applied_field")) applied_field_ = read_vec3(*f);
+  if (module == "pinned_boundaries") {   // physics/pinned_boundaries.cc:12-31, pinned_boundaries.h:86-107
+    const char *names[6] = {"left", "right", "front", "back", "bottom", "top"};
+    for (int k = 0; k < 6; ++k) {
+      const std::string name = names[k];
+      const Setting *m = s->find(name + "_pinned_magnetisation");
+      if (!m) continue;
+      boundaries_.push_back({k / 2, (k % 2) == 1, s->get(name + "_pinned_cells", 1), read_vec3(*m)});
+    }
+  }
+}
+
+void Physics::update(B200HeunLLGSolver &solver) {   // physics/pinned_boundaries.cc:34-46
+  if (boundaries_.empty()) return;
+  const Lattice &lat = solver.lattice();
+  jb_ctx *ctx = solver.ctx();
+  if (!regions_set_) {
+    for (size_t r = 0; r < boundaries_.size(); ++r) {
+      const PinnedBoundary &b = boundaries_[r];
+      std::vector<int32_t> sites;
+      for (int x = 0; x < lat.dims[0]; ++x) for (int y = 0; y < lat.dims[1]; ++y) for (int z = 0; z < lat.dims[2]; ++z) {
+        const int cell[3] = {x, y, z};
+        const bool in = b.upper ? cell[b.dim] >= lat.dims[b.dim] - b.cells : cell[b.dim] < b.cells;
+        if (!in) continue;
+        for (int m = 0; m < lat.M; ++m) sites.push_back(((x * lat.dims[1] + y) * lat.dims[2] + z) * lat.M + m);
+      }
+      solver.check(jb_set_region(ctx, static_cast<int32_t>(r), static_cast<int32_t>(sites.size()), sites.data()));
+    }
+    regions_set_ = true;
+  }
+  for (size_t r = 0; r < boundaries_.size(); ++r) {
+    double M4[4];
+    solver.check(jb_region_moment(ctx, static_cast<int32_t>(r), M4));
+    const Mat3 R = rotation_matrix_between_vectors(Vec3{{M4[0], M4[1], M4[2]}}, boundaries_[r].magnetisation);
+    double R9[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R9[3 * i + j] = R[i][j];
+    solver.check(jb_rotate_region(ctx, static_cast<int32_t>(r), R9));
+  }
 }
 
 Monitor::Monitor(const Setting &settings) { output_step_freq_ = settings.get("output_steps", 100); }
@@ -722,7 +760,7 @@ Simulation::Simulation(const std::vector<std::string> &config_args, const std::s
       module != "llg-rk4-b200-gpu" && module != "llg-rk4-gpu")   // Solver::create (core/solver.cc:60-77)
     throw std::runtime_error("unknown solver " + solver_settings["module"].as_string() + " (this host layer provides the llg-heun and llg-rk4 paths only)");
   solver_.reset(new B200HeunLLGSolver(solver_settings, *lattice_, seed));
-  solver_->register_physics_module(new Physics(config_->find("physics")));
+  solver_->register_physics_module(new Physics(config_->find("physics")));   // Physics::create (core/physics.cc:79-126): empty, pinned_boundaries
   if (!config_->exists("hamiltonians")) throw std::runtime_error("No hamiltonians group in config");
   const Setting &hams = (*config_)["hamiltonians"];
   for (int i = 0; i < hams.length(); ++i) solver_->register_hamiltonian(Hamiltonian::create(hams[i], *lattice_));
@@ -755,6 +793,7 @@ void Simulation::run_initializer(const Setting &s) {   // initializer/init_dispa
 
 void Simulation::run() {   // run_simulation (core/jams++.cc:326-377)
   while (solver_->is_running()) {
+    solver_->update_physics_module();
     solver_->notify_monitors();
     solver_->run();
   }

@@ -181,14 +181,23 @@ class AppliedFieldHamiltonian : public Hamiltonian {   // hamiltonian/applied_fi
   Vec3 field_{{0, 0, 0}};
 };
 
-class Physics {   // core/physics.h:14-40 + physics/empty.h: constant temperature and applied field from `physics`
+class B200HeunLLGSolver;
+
+// core/physics.h:14-40 + physics/empty.h: constant temperature and applied field from `physics`;
+// module "pinned_boundaries" (physics/pinned_boundaries.{h,cc}): every iteration the spins of each edge region are rotated
+// on the device so that the region's moment points along the pinned direction (jb_region_moment / jb_rotate_region)
+class Physics {
  public:
   explicit Physics(const Setting *settings);
   double temperature() const { return temperature_; }
   double applied_field(int i) const { return applied_field_[i]; }
+  void update(B200HeunLLGSolver &solver);   // Physics::update, once per iteration before the monitors (core/jams++.cc:334)
  private:
+  struct PinnedBoundary { int dim; bool upper; int cells; Vec3 magnetisation; };
   double temperature_ = 0.0;
   Vec3 applied_field_{{0, 0, 0}};
+  std::vector<PinnedBoundary> boundaries_;
+  bool regions_set_ = false;
 };
 
 class Solver;
@@ -244,6 +253,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
   const Physics *physics() const { return physics_.get(); }
 
   void register_physics_module(Physics *p) { physics_.reset(p); }
+  void update_physics_module() { physics_->update(*this); }   // core/solver.cc:99-108
   void register_hamiltonian(Hamiltonian *h);
   void register_monitor(Monitor *m) { monitors_.emplace_back(m); }
   std::vector<std::unique_ptr<Hamiltonian>> &hamiltonians() { return hamiltonians_; }

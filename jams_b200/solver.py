@@ -274,6 +274,75 @@ class EnergyMonitor(Monitor):
         return row
 
 
+class Physics:
+    """core/physics.h:14-40 with physics/empty.h: constant ``temperature`` and ``applied_field`` from the ``physics`` group"""
+
+    def __init__(self, settings: dict | None = None):
+        settings = settings or {}
+        self.temperature = float(settings.get("temperature", 0.0))
+        self.applied_field = np.asarray(settings.get("applied_field", [0.0, 0.0, 0.0]), dtype=np.float64)
+
+    def update(self, solver):   # Physics::update(iterations, time, dt), called once per iteration (core/jams++.cc:334)
+        pass
+
+
+class PinnedBoundariesPhysics(Physics):
+    """``physics.module = "pinned_boundaries"`` (physics/pinned_boundaries.{h,cc}): every iteration the spins of each edge
+    region are rotated so that the region's moment sum mu_i s_i points along the pinned direction.  Regions: ``left/right``
+    (a), ``front/back`` (b), ``bottom/top`` (c), ``<name>_pinned_cells`` unit cells deep (default 1)
+    (pinned_boundaries.h:86-107).  The reduction and the rotation run on the device (``jb_region_moment``,
+    ``jb_rotate_region``); the 3x3 rotation is built here from the (all-reduced) moment like the reference does
+    (``rotation_matrix_between_vectors``, containers/mat3.h:334-366)."""
+    NAMES = {"left": (0, False), "right": (0, True), "front": (1, False), "back": (1, True), "bottom": (2, False), "top": (2, True)}
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings)
+        self.lattice = lattice
+        self.boundaries = []   # (name, dim, upper, n_cells, pinned magnetisation)
+        for name, (dim, upper) in self.NAMES.items():
+            if name + "_pinned_magnetisation" not in settings:
+                continue
+            m = np.asarray(settings[name + "_pinned_magnetisation"], dtype=np.float64)
+            self.boundaries.append((name, dim, upper, int(settings.get(name + "_pinned_cells", 1)), m))
+        self._attached = None
+
+    def region_sites(self, dim, upper, n, x0, nx):
+        """local site ids (reference order) of the spins whose cell offset lies in the region (pinned_boundaries.cc:21-27)"""
+        lat = self.lattice
+        Nx, Ny, Nz = lat.dims
+        x, y, z, m = np.meshgrid(np.arange(x0, x0 + nx), np.arange(Ny), np.arange(Nz), np.arange(lat.M), indexing="ij")
+        cell = (x, y, z)[dim]
+        size = lat.dims[dim]
+        mask = (cell >= size - n) if upper else (cell < n)
+        local = (((x - x0) * Ny + y) * Nz + z) * lat.M + m
+        return local[mask].astype(np.int32)
+
+    def attach(self, solver):
+        if self._attached is solver:
+            return
+        for r, (name, dim, upper, n, m) in enumerate(self.boundaries):
+            solver.ctx.set_region(r, self.region_sites(dim, upper, n, solver.x0, solver.nx))
+        self._attached = solver
+
+    def update(self, solver):
+        from .lattice import rotation_matrix_between_vectors
+        solver._build()
+        self.attach(solver)
+        for r, (name, dim, upper, n, target) in enumerate(self.boundaries):
+            mag = solver.reduce_sum(solver.ctx.region_moment(r))[:3]
+            solver.ctx.rotate_region(r, rotation_matrix_between_vectors(mag, target))
+
+
+def create_physics(settings: dict | None, lattice: Lattice) -> Physics:
+    """Physics::create (core/physics.cc:79-126), the modules on this path"""
+    module = str((settings or {}).get("module", "empty")).lower()
+    if module == "empty":
+        return Physics(settings)
+    if module == "pinned_boundaries":
+        return PinnedBoundariesPhysics(settings, lattice)
+    raise RuntimeError("unknown physics module " + module)
+
+
 class Solver:
     """core/solver.h:15-90"""
     name = "solver"
@@ -287,6 +356,17 @@ class Solver:
         self.temperature = 0.0
         self.hamiltonians = []
         self.monitors = []
+        self.physics = Physics()
+
+    def register_physics_module(self, p: Physics):   # core/solver.h:47
+        self.physics = p
+        self.set_temperature(p.temperature)
+
+    def set_temperature(self, T):
+        self.temperature = float(T)
+
+    def update_physics_module(self):   # core/solver.cc:99-108, called before notify_monitors and run (core/jams++.cc:334)
+        self.physics.update(self)
 
     def is_cuda_solver(self):
         return False

@@ -246,6 +246,26 @@ def magnetisation(s_aos, mus, group_of_spin=None, n_groups=1):
     return out
 
 
+def pin_region(s_aos, mus, indices, target):
+    """PinnedBoundariesPhysics::update for one boundary on the host path (physics/pinned_boundaries.cc:41-44):
+    mag = jams::sum_spins_moments(s, mus, indices) (helpers/spinops.cc:55-67: plain loop over the indices),
+    R = rotation_matrix_between_vectors(mag, target) (containers/mat3.h:334-366, the oracle's restatement),
+    jams::rotate_spins(s, R, indices) (helpers/spinops.cc: s_i <- R s_i).  Returns the new N x 3 array."""
+    s = np.array(_f64(s_aos, (-1, 3)), copy=True)
+    mus = _f64(mus)
+    mag = np.zeros(3)
+    for i in indices:            # same accumulation order as the reference loop
+        mag += mus[i] * s[i]
+    R = np.zeros(9)
+    restatement().rotation_matrix_between_vectors(np.ascontiguousarray(mag), _f64(target), R)
+    R = R.reshape(3, 3)
+    for i in indices:
+        v = s[i]
+        s[i] = [R[0, 0] * v[0] + R[0, 1] * v[1] + R[0, 2] * v[2], R[1, 0] * v[0] + R[1, 1] * v[1] + R[1, 2] * v[2],
+                R[2, 0] * v[0] + R[2, 1] * v[1] + R[2, 2] * v[2]]
+    return s
+
+
 def spin_temperature(s_aos, h_aos):
     lib = restatement()
     s = _f64(s_aos, (-1, 3))

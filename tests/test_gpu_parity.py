@@ -361,3 +361,42 @@ def test_rk4_full_size_properties_and_fixed_point():
     h.set_spins(s0)
     h.run(20)
     assert np.abs(h.spins() - out).max() < 1e-4
+
+
+# ---- physics hook on the device: pinned_boundaries, i.e. the shipped example's own set-up ----
+@pytest.mark.parametrize("module", ["llg-rk4-b200-gpu", "llg-heun-b200-gpu"])
+def test_pinned_boundaries_with_the_bloch_wall_example_matches_oracle(module):
+    """examples/bloch_domain_wall as shipped (bloch_domain_wall.cfg:75-81,132-139): RK4 + pinned_boundaries, here at T = 0 on a
+    smaller box; every iteration: update_physics_module (rotate the two edge regions), then run (core/jams++.cc:334-341)"""
+    from jams_b200.solver import create_solver, create_physics
+    w = W.c1_bloch_wall((32, 6, 5))
+    lat = w["lattice"]
+    phys = dict(module="pinned_boundaries", left_pinned_magnetisation=[0.0, 0.0, -1.0], right_pinned_magnetisation=[0.0, 0.0, 1.0],
+                left_pinned_cells=3, right_pinned_cells=2)
+    s = create_solver(dict(module=module, t_step=W.T_STEP, t_max=1e-9), lat)
+    for h in w["hamiltonians"]:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    p = create_physics(phys, lat)
+    s.register_physics_module(p)
+    s0 = random_unit_spins(lat.num_spins, 31) * 0.2 + w["spins"]      # a disturbed wall, so the rotations are not the identity
+    s0 /= np.linalg.norm(s0, axis=1, keepdims=True)
+    s.set_spins(s0)
+    sim = build_cpu_sim(w)
+    cur = s0.copy()
+    left = p.region_sites(0, False, 3, 0, lat.dims[0]); right = p.region_sites(0, True, 2, 0, lat.dims[0])
+    assert len(left) == 3 * 6 * 5 and len(right) == 2 * 6 * 5
+    steps = 15
+    for n in range(steps):
+        s.update_physics_module()
+        s.run(1)
+        cur = oracle.pin_region(cur, lat.mus(), left, [0.0, 0.0, -1.0])
+        cur = oracle.pin_region(cur, lat.mus(), right, [0.0, 0.0, 1.0])
+        sim.set_spins(cur)
+        (sim.run_rk4 if "rk4" in module else sim.run)(1)
+        cur = sim.get_spins()
+    got = s.spins()
+    assert np.abs(got - cur).max() <= TRAJ_TOL
+    # the device reduction equals the host loop
+    m4 = s.ctx.region_moment(0)
+    want = (lat.mus()[left, None] * got[left]).sum(axis=0)
+    assert np.abs(m4[:3] - want).max() <= 1e-12 * np.abs(want).max() and abs(m4[3] - lat.mus()[left].sum()) <= 1e-12 * m4[3]

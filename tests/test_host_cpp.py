@@ -135,3 +135,33 @@ def test_cpp_simulation_equals_python_mirror_and_writes_jams_monitor_files(tmp_p
     r = subprocess.run([host.EXE_PATH, "--name", "cli", "--output", str(tmp_path), FIXTURE, PATCH_B200], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert open(tmp_path / "cli_mag.tsv").read() == open(tmp_path / "wall_mag.tsv").read()
+
+
+@pytest.mark.gpu
+def test_cpp_simulation_runs_the_shipped_example_setup_rk4_with_pinned_boundaries(tmp_path):
+    """examples/bloch_domain_wall as shipped: solver llg-rk4-gpu + physics pinned_boundaries (bloch_domain_wall.cfg:75-81,132-139),
+    through the C++ Simulation and through the Python mirror (main loop order of core/jams++.cc:333-341)"""
+    from jams_b200.solver import create_solver, create_hamiltonian, create_physics
+    from jams_b200.lattice import bloch_domain_wall
+    patch = ('solver : { module = "llg-rk4-b200-gpu"; t_step = 5e-16; t_max = 1.5e-14; }; '
+             'physics : { module = "pinned_boundaries"; temperature = 0.0; left_pinned_magnetisation = [0.0, 0.0, -1.0]; '
+             'right_pinned_magnetisation = [0.0, 0.0, 1.0]; left_pinned_cells = 2; right_pinned_cells = 3; };')
+    got, done = host.run(FIXTURE, patch, name="pinned", output_dir=str(tmp_path))
+    assert done == 30
+    w = W.c1_bloch_wall((32, 4, 4))
+    lat = w["lattice"]
+    init = bloch_domain_wall(lat.positions(), lat.initial_spins(), width=8.0, center=16.0)
+    s = create_solver(dict(module="llg-rk4-b200-gpu", t_step=5e-16, t_max=1.5e-14), lat)
+    for h in w["hamiltonians"]:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    s.register_physics_module(create_physics(dict(module="pinned_boundaries", left_pinned_magnetisation=[0.0, 0.0, -1.0],
+                                                  right_pinned_magnetisation=[0.0, 0.0, 1.0], left_pinned_cells=2, right_pinned_cells=3), lat))
+    s.set_spins(init)
+    while s.is_running():
+        s.update_physics_module()
+        s.run(1)
+    assert s.iteration == 30
+    assert np.abs(got - s.spins()).max() <= 1e-12
+    # the pinned regions point where they were told to
+    m = got.reshape(32, 4, 4, 3)
+    assert m[:2, ..., 2].mean() < -0.9 and m[-3:, ..., 2].mean() > 0.9

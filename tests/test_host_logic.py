@@ -156,3 +156,23 @@ def test_gloo_world_size_2_plumbing(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_pinned_boundary_regions_follow_the_reference_predicates():
+    """physics/pinned_boundaries.h:86-107: lower boundary cell[dim] < n, upper boundary cell[dim] >= size[dim] - n;
+    indices in the reference site order, per slab when the lattice is split along x"""
+    from jams_b200.lattice import Lattice, Material
+    from jams_b200.solver import PinnedBoundariesPhysics
+    lat = Lattice([Material("A", 1.0)], np.eye(3), [("A", (0, 0, 0)), ("A", (0.5, 0.5, 0.5))], (8, 3, 4), periodic=(False, True, True))
+    p = PinnedBoundariesPhysics(dict(module="pinned_boundaries", left_pinned_magnetisation=[0, 0, -1], top_pinned_magnetisation=[1, 0, 0],
+                                     left_pinned_cells=2), lat)
+    assert [b[0] for b in p.boundaries] == ["left", "top"] and p.boundaries[0][3] == 2 and p.boundaries[1][3] == 1
+    left = p.region_sites(0, False, 2, 0, 8)
+    assert len(left) == 2 * 3 * 4 * 2 and left.max() == 2 * 3 * 4 * 2 - 1          # the first two x planes are the first sites
+    top = p.region_sites(2, True, 1, 0, 8)
+    z = (top // lat.M) % 4
+    assert len(top) == 8 * 3 * 2 and np.all(z == 3)
+    # slab 1 of 2 (x in [4, 8)): the left region is empty, the right one is the last plane of the slab in local numbering
+    assert len(p.region_sites(0, False, 2, 4, 4)) == 0
+    right = p.region_sites(0, True, 1, 4, 4)
+    assert len(right) == 3 * 4 * 2 and right.min() == 3 * 3 * 4 * 2
