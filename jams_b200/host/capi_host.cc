@@ -78,7 +78,8 @@ __attribute__((visibility("default"))) int jbh_run(const char *const *args, int 
     Simulation sim(split_args(args, n), name, output_dir);
     B200HeunLLGSolver &s = sim.solver();
     int steps = 0;
-    while (s.is_running() && (max_steps_override < 0 || steps < max_steps_override)) {
+    while (s.is_running() && (max_steps_override < 0 || steps < max_steps_override)) {   // core/jams++.cc:333-341
+      s.update_physics_module();
       s.notify_monitors();
       s.run();
       ++steps;
