@@ -388,49 +388,67 @@ void choose_tiling(jb_ctx *c) {
   if (t.fused) {
     // shape chosen above
   } else if (pair) {
-    // pair kernel: a thread owns the sites (z, z + 1); consumer threads = ceil(TZ / 2) x ceil(TY / SPT), 256 by default
-    // so that two CTAs share an SM, and the rest of the shared memory goes into ring depth (loads in flight)
-    // long contiguous runs along z serve DRAM best (measured: 4 x 128 beats 8 x 64 beats 16 x 32, profiles/README.md)
-    int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 128 ? 128 : g.Nz);
-    TZ = std::max(1, std::min(TZ, g.Nz));
-    if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
-    const int HZ = (TZ + 1) / 2;
+    // pair kernel: a thread owns the sites (z, z + 1) of every motif site of its y rows; consumer threads =
+    // ceil(TZ / 2) x ceil(TY / SPT) <= 256 so that two CTAs share an SM.  Tile choice: among z extents 128 / 64 / 32 (long
+    // contiguous runs along z serve DRAM best: 4 x 128 beats 8 x 64 beats 16 x 32 on C3, profiles/README.md) take, for
+    // each, the tallest tile whose rings fit the shared-memory budget, and keep the candidate with the most sites per
+    // plane (a shorter z extent only if it brings 1.5 x the sites).  Motifs with several sites multiply the slot size, so they end up with shorter tiles
+    // (bcc: 4 x 64) instead of degenerate one-row tiles.
     int SPT = c->opt_SPT ? c->opt_SPT : 1;
     if (!(SPT == 1 || SPT == 2)) return;
-    int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / HZ);
-    TY = std::max(1, std::min(TY, std::min(g.Ny, 64)));
-    if (SPT > TY) SPT = 1;
     const size_t budget = c->opt_ctas_per_sm == 1 ? 220 * 1024 : 113 * 1024;   // per CTA
-    for (;;) {
-      t.TY = TY; t.TZ = TZ; t.SPT = SPT;
-      t.gzb = (g.gz + 1) & ~1;
-      t.BY = TY + 2 * g.gy; t.BZ = ((TZ + 1) & ~1) + 2 * t.gzb;
-      t.UZ = (TZ + 1) & ~1;
-      t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
-      t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
-      t.threads = HZ * ((TY + SPT - 1) / SPT);
-      t.u_tma = 1;
-      t.RU = c->opt_RU ? c->opt_RU : 2;
-      const size_t slot_bytes = (size_t)3 * t.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
-      const size_t u_bytes = (size_t)t.RU * 3 * t.slotU * 8;
-      const int rmin = 2 * g.gx + 2;
+    const int rmin = 2 * g.gx + 2;
+    auto shape = [&](int TY, int TZ, jb_ctx::Tiling &q) -> bool {   // fills q; true if the tile fits
+      const int HZ = (TZ + 1) / 2;
+      q.TY = TY; q.TZ = TZ; q.SPT = (SPT > TY) ? 1 : SPT;
+      q.gzb = (g.gz + 1) & ~1;
+      q.BY = TY + 2 * g.gy; q.BZ = ((TZ + 1) & ~1) + 2 * q.gzb;
+      q.UZ = (TZ + 1) & ~1;
+      q.slotS = (q.BY * g.M * q.BZ + 15) / 16 * 16;
+      q.slotU = (q.TY * g.M * q.UZ + 15) / 16 * 16;
+      q.threads = HZ * ((TY + q.SPT - 1) / q.SPT);
+      q.u_tma = 1;
+      q.RU = c->opt_RU ? c->opt_RU : 2;
+      const size_t slot_bytes = (size_t)3 * q.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
+      const size_t u_bytes = (size_t)q.RU * 3 * q.slotU * 8;
       for (int st = 0; st < 2; ++st) {
         const size_t fixed = 512 + (st == 1 ? u_bytes : 0);
         int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
         R = std::min(R, JB_PAIR_MAX_RING);
         // one plane in flight per CTA is the measured optimum: with the stores in the mix, more outstanding plane loads
         // lower the DRAM efficiency (ring 5 / 6: -8 % / -15 %, profiles/README.md r01f)
-        if (!c->opt_R) R = std::min(R, 2 * g.gx + 2);
-        t.Rs[st] = R;
-        t.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
+        if (!c->opt_R) R = std::min(R, rmin);
+        q.Rs[st] = R;
+        q.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
       }
-      t.R = t.Rs[1];
-      if ((t.Rs[0] >= rmin && t.Rs[1] >= rmin && t.threads <= 256) || TY <= SPT) break;
-      TY = std::max(SPT, TY / 2);
+      q.R = q.Rs[1];
+      return q.Rs[0] >= rmin && q.Rs[1] >= rmin && q.threads <= 256 && q.smem[0] <= 220 * 1024 && q.smem[1] <= 220 * 1024 &&
+             q.BY * g.M <= 256 && q.BZ <= 256 && q.UZ <= 256 && q.TY * g.M <= 256 && q.RU >= 2 && q.RU <= JB_PAIR_MAX_RING;
+    };
+    bool found = false;
+    long long best_sites = -1;
+    const int zc[3] = {128, 64, 32};
+    int prev_TZ = -1;
+    for (int k = 0; k < 3; ++k) {
+      int TZ = c->opt_TZ ? c->opt_TZ : std::min(zc[k], g.Nz);
+      TZ = std::max(1, std::min(TZ, g.Nz));
+      if (TZ == prev_TZ) continue;   // the lattice is narrower than this candidate: already tried
+      prev_TZ = TZ;
+      if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
+      const int HZ = (TZ + 1) / 2;
+      int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / HZ);
+      TY = std::max(1, std::min(TY, std::min(g.Ny, 64)));
+      jb_ctx::Tiling q = t;
+      bool ok = false;
+      for (; TY >= 1; TY = c->opt_TY ? 0 : TY - 1) { if (shape(TY, TZ, q)) { ok = true; break; } }
+      if (ok) {
+        const long long sites = (long long)q.TY * q.TZ * g.M;
+        if (2 * sites > 3 * best_sites) { best_sites = sites;   // a shorter z extent must bring 1.5 x the sites per plane
+          const int pair_flag = t.pair; t = q; t.pair = pair_flag; found = true; }
+      }
+      if (c->opt_TZ) break;   // fixed by the caller
     }
-    if (t.Rs[0] < 2 * g.gx + 2 || t.Rs[1] < 2 * g.gx + 2 || t.RU < 2 || t.RU > JB_PAIR_MAX_RING || t.threads > 256) return;   // the kernel is compiled for <= 288 threads
-    if (t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;   // TMA box extents
-    if (t.smem[0] > 220 * 1024 || t.smem[1] > 220 * 1024) return;
+    if (!found) return;
   } else {
   int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
   TZ = std::max(1, std::min(TZ, g.Nz));
