@@ -443,3 +443,47 @@ def test_thermal_equilibrium_statistics_match_the_reference_arithmetic_and_the_t
     assert abs(ge - ce) <= 0.006 * abs(ce), (ge, ce)
     assert abs(gt - ct) <= 0.02 * T and abs(gt - T) <= 0.03 * T, (gt, ct, T)
     assert 0.0 < gm < 1.0
+
+
+# ---- edge cases: vacancies, no exchange at all, empty step counts, sizes beyond one slab ----
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "fused"])
+def test_vacancies_stay_zero_and_do_not_act_on_their_neighbours(variant):
+    """zero-length spins (vacancies) are left unchanged by unit_vector (containers/vec3.h:276-283) and add nothing to J.s"""
+    w = W.c3_sc(dims=(10, 8, 12), temperature=0.0)
+    w["hamiltonians"].append(dict(module="uniaxial", order="K1", anisotropies=[("A", [0.0, 0.0, 1.0], 1e-22)]))
+    lat = w["lattice"]
+    s0 = random_unit_spins(lat.num_spins, 5)
+    holes = np.random.default_rng(3).choice(lat.num_spins, lat.num_spins // 10, replace=False)
+    s0[holes] = 0.0
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    sim.run(25)
+    s = make(w, options=KERNELS[variant])
+    s.set_spins(s0)
+    s.run(25)
+    got = s.spins()
+    assert np.array_equal(got[holes], np.zeros((len(holes), 3)))
+    assert np.abs(got - sim.get_spins()).max() <= TRAJ_TOL
+
+
+def test_zeeman_only_single_spin_precession_and_empty_step_count():
+    """no exchange Hamiltonian at all (no template): one spin in a field precesses at gamma B; nsteps = 0 is a no-op"""
+    from jams_b200.consts import kGyromagneticRatioIU
+    lat = Lattice([Material("A", 1.0, alpha=0.0)], np.eye(3), [("A", (0, 0, 0))], (1, 1, 1), periodic=(False, False, False))
+    w = dict(name="one spin", lattice=lat, hamiltonians=[dict(module="zeeman", dc_local_field=[[0.0, 0.0, 10.0]])], temperature=0.0, spins=None)
+    s = make(w)
+    s.set_spins(np.array([[1.0, 0.0, 0.0]]))
+    s.run(0)
+    assert np.array_equal(s.spins(), [[1.0, 0.0, 0.0]])
+    s.run(1000)
+    phi = kGyromagneticRatioIU * 10.0 * 1000 * 1e-4
+    out = s.spins()[0]
+    assert abs(out[2]) < 1e-12 and abs(out[0] - np.cos(phi)) < 1e-6 and abs(out[1] - np.sin(phi)) < 1e-6
+
+
+def test_a_lattice_too_large_for_one_slab_is_refused_not_truncated():
+    """the reference throws when nnz overflows int32 (containers/sparse_matrix_builder.h:265-269, sc 512^3 already does);
+    here the limit is 2^31 box elements per slab and the message says what to do"""
+    with pytest.raises(capi.JamsB200Error, match="more ranks|too large|2\\^31"):
+        c = capi.Context((1400, 1300, 1300))
+        c.set_materials(np.ones(1), np.ones(1), np.ones(1))
