@@ -1071,7 +1071,9 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           }
         }
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
-        p.thermal = T > 0.0 ? 1 : 0;
+        // the corrector needs no noise: the predictor folds the noise part of its right-hand side into u (jb_device.cuh)
+        const int th = stage == 0 ? thermal : 0;
+        p.thermal = th;
         if (multi) {
           // ghosts I read were written by the neighbours' previous stage; the boxes I write into were
           // last read by the neighbours' previous stage: both are covered by their last signal
@@ -1086,17 +1088,17 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
           for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
           tp.R = c->tiling.Rs[stage];
-          rc = tile_launch_shape(c, tp, stage, thermal); if (rc) return rc;
-          tp.n_chunks = c->tiling.n_chunks[stage][thermal];
+          rc = tile_launch_shape(c, tp, stage, th); if (rc) return rc;
+          tp.n_chunks = c->tiling.n_chunks[stage][th];
           tp.n_items = tp.n_chunks * tp.n_cols;
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[2][0], c->tmap[2][1], c->tmap[2][2]};
           tp.reverse_items = (c->tiling.pair && stage == 1 && c->opt_reverse_b) ? 1 : 0;
           if (c->tiling.pair)
-            JB_CUDA(c, jbk_stage_pair(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
-                                      c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
+            JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
+                                      c->tiling.grid[stage][th], c->tiling.smem[stage], c->stream));
           else
-            JB_CUDA(c, jbk_stage_tile(tp, tm, stage, thermal, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
-                                      c->tiling.grid[stage][thermal], c->tiling.smem[stage], c->stream));
+            JB_CUDA(c, jbk_stage_tile(tp, tm, stage, th, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
+                                      c->tiling.grid[stage][th], c->tiling.smem[stage], c->stream));
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
         }

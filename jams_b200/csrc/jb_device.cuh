@@ -114,9 +114,26 @@ __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x
 // N(0,1) draws, and in the corrector the Heun intermediate u.  Adds the uniaxial field and the noise,
 // evaluates the LLG right hand side  rhs = -gyro ( s x h + alpha s x (s x h) )  (cpu_llg_heun.cc:89,130) and
 // performs the stage update with the step folded into the class constants c_full = -gyro dt, c_half = -gyro dt/2:
-//   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)
+//   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)   [+ the noise part of rhs*, see corrector_noise_part]
 //   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
+//   (stage 1 is always instantiated with THERMAL = false: the predictor has already put the noise part of rhs* into u)
 // unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
+// The LLG right-hand side is linear in the field: rhs(s*, H* + xi) = rhs(s*, H*) + rhs(s*, xi), and rhs(s*, xi) needs only
+// the site's own predictor spin s* and its own noise draw -- both at hand at the end of the predictor.  So the predictor
+// folds dt/2 rhs(s*, xi) into the Heun intermediate it writes anyway (u' = s + dt/2 k1 + dt/2 rhs(s*, xi)) and the
+// corrector, s' = unit(u' + dt/2 rhs(s*, H*)), needs no noise at all: the second Philox / Box-Muller evaluation per site
+// and step (about a quarter of the corrector's instructions at T > 0) disappears.  Same draw for both stages as in the
+// reference (solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64,108-114); the result differs by rounding only.
+__device__ __forceinline__ void corrector_noise_part(const JbClass &c, double sx, double sy, double sz, double n0, double n1, double n2,
+                                                     double &vx, double &vy, double &vz) {
+  const double xx = c.sigma * n0, xy = c.sigma * n1, xz = c.sigma * n2;
+  const double ax_ = sy * xz - sz * xy, ay_ = sz * xx - sx * xz, az_ = sx * xy - sy * xx;        // s* x xi
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;  // s* x (s* x xi)
+  vx = fma(c.c_half, fma(c.alpha, bx_, ax_), vx);
+  vy = fma(c.c_half, fma(c.alpha, by_, ay_), vy);
+  vz = fma(c.c_half, fma(c.alpha, bz_, az_), vz);
+}
+
 // reciprocal square root without the special-case branch of CUDA's rsqrt(): hardware seed (MUFU.RSQ64H, ~2^-23) refined by
 // one third-order step y (1 + e/2 + 3 e^2/8), e = 1 - x y^2 (<= 1 ulp).  x = p.p is either > DBL_EPSILON^2 and far from
 // overflow (|p| ~ 1) or the result is discarded by the caller's select.
@@ -159,6 +176,7 @@ __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy,
   const double r = rsqrt_nobranch(n2_);
   const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;
   ox = px * inv; oy = py * inv; oz = pz * inv;
+  if (STAGE == 0 && THERMAL) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
 }
 
 // branch-free variant for kernels that interleave several independent site updates in one basic block
@@ -193,6 +211,7 @@ __device__ __forceinline__ void llg_site_nb(const JbClass &c, double sx, double 
   const double r = rsqrt_nobranch(n2_);
   const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;   // |p| <= DBL_EPSILON: unchanged (containers/vec3.h:276-283)
   ox = px * inv; oy = py * inv; oz = pz * inv;
+  if (STAGE == 0 && THERMAL) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
 }
 
 // store the ghost images of a freshly computed spin (the value for its own cell has been stored by the

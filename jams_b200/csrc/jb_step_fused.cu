@@ -124,10 +124,9 @@ __device__ __forceinline__ void corrector_pair(const JbTileParams &p, const JbCl
   double2 hx = make_double2(p.fT1[mm][0], p.fT1[mm][0]), hy = make_double2(p.fT1[mm][1], p.fT1[mm][1]), hz = make_double2(p.fT1[mm][2], p.fT1[mm][2]);   // constant field at t + dt
   gather_pair<ISO>(ringP + off, tab, p.nbr_begin[mm], p.nbr_odd[mm], p.nbr_begin[mm + 1], cs8, p.J9T, hx, hy, hz);
   double2 vx, vy, vz;
-  llg_site_nb<1, THERMAL, UNI>(c, sx.x, sy.x, sz.x, hx.x, hy.x, hz.x, (double)nz.a0, (double)nz.a1, (double)nz.a2, ux.x, uy.x, uz.x,
-                               ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
-  llg_site_nb<1, THERMAL, UNI>(c, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, (double)nz.b0, (double)nz.b1, (double)nz.b2, ux.y, uy.y, uz.y,
-                               ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
+  (void)nz;   // the predictor has folded the noise part of this right-hand side into u (jb_device.cuh: corrector_noise_part)
+  llg_site_nb<1, false, UNI>(c, sx.x, sy.x, sz.x, hx.x, hy.x, hz.x, 0.0, 0.0, 0.0, ux.x, uy.x, uz.x, ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
+  llg_site_nb<1, false, UNI>(c, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, 0.0, 0.0, 0.0, ux.y, uy.y, uz.y, ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
 }
 
 // corrector of plane x_b and predictor of plane x_b + 2 rx + 1 ... of the SAME thread in one basic block: the two are
@@ -186,12 +185,13 @@ __device__ __forceinline__ void fused_ab_pair(const JbTileParams &p, const JbCla
   const double zero = 0.0;
   llg_site_nb<0, THERMAL, UNI>(c, sxA.x, syA.x, szA.x, hxA.x, hyA.x, hzA.x, (double)nz_n.a0, (double)nz_n.a1, (double)nz_n.a2, zero, zero, zero,
                                sA_x.x, sA_y.x, sA_z.x, ux_n.x, uy_n.x, uz_n.x);
-  llg_site_nb<1, THERMAL, UNI>(c, sxB.x, syB.x, szB.x, hxB.x, hyB.x, hzB.x, (double)nz_o.a0, (double)nz_o.a1, (double)nz_o.a2, ux_o.x, uy_o.x, uz_o.x,
-                               ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
+  (void)nz_o;   // the noise part of the corrector's right-hand side is already in u (jb_device.cuh: corrector_noise_part)
+  llg_site_nb<1, false, UNI>(c, sxB.x, syB.x, szB.x, hxB.x, hyB.x, hzB.x, 0.0, 0.0, 0.0, ux_o.x, uy_o.x, uz_o.x,
+                             ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
   llg_site_nb<0, THERMAL, UNI>(c, sxA.y, syA.y, szA.y, hxA.y, hyA.y, hzA.y, (double)nz_n.b0, (double)nz_n.b1, (double)nz_n.b2, zero, zero, zero,
                                sA_x.y, sA_y.y, sA_z.y, ux_n.y, uy_n.y, uz_n.y);
-  llg_site_nb<1, THERMAL, UNI>(c, sxB.y, syB.y, szB.y, hxB.y, hyB.y, hzB.y, (double)nz_o.b0, (double)nz_o.b1, (double)nz_o.b2, ux_o.y, uy_o.y, uz_o.y,
-                               ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
+  llg_site_nb<1, false, UNI>(c, sxB.y, syB.y, szB.y, hxB.y, hyB.y, hzB.y, 0.0, 0.0, 0.0, ux_o.y, uy_o.y, uz_o.y,
+                             ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
   sts128(dstP + off, sA_x.x, sA_x.y); sts128(dstP + off + cs8, sA_y.x, sA_y.y); sts128(dstP + off + 2 * cs8, sA_z.x, sA_z.y);
 }
 
