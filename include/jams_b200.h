@@ -156,7 +156,8 @@ JB_API int jb_step(jb_ctx *ctx, int32_t nsteps, double dt_ps, double time_ps, do
  * cuda_rk4_base_kernel.cuh:1-19, cuda/cuda_spin_ops.cu:4-17): classical RK4 on the LLG right hand side with one
  * white-noise draw per step, unnormalised intermediate states and a normalisation after the combination.  Four
  * launches per step, each fusing the field evaluation, k_i, the next stage input and the running sum of the k's.
- * Arguments as jb_step.  One slab (n_ranks == 1) and a translation-invariant exchange template only. */
+ * Arguments as jb_step; slab-decomposed runs exchange halos once per stage like jb_step.  Needs a translation-invariant
+ * exchange template. */
 JB_API int jb_step_rk4(jb_ctx *ctx, int32_t nsteps, double dt_ps, double time_ps, double temperature_K,
                 uint64_t seed, uint64_t first_step_index, int32_t gilbert_prefactor);
 

@@ -46,7 +46,7 @@ struct Blob {  // contents of a JB_HALO_HANDLE_BYTES halo handle
   int32_t rank;
   int32_t nx, PY, PZ, M, gx;
   uint64_t base_ptr;             // slab base in the exporting process
-  uint64_t off_S0[3], off_S1[3]; // byte offsets inside the slab
+  uint64_t off_S0[3], off_S1[3], off_V[3]; // byte offsets inside the slab
   uint64_t off_flags;
   cudaIpcMemHandle_t ipc;
 };
@@ -64,8 +64,7 @@ void release_state(jb_ctx *c) {
     c->S0[k] = c->S1[k] = nullptr;
     if (c->U[k]) cudaFree(c->U[k]);
     c->U[k] = nullptr;
-    if (c->V[k]) cudaFree(c->V[k]);
-    c->V[k] = nullptr;
+    c->V[k] = nullptr;   // part of the slab
   }
   c->flags = nullptr;
   c->state_allocated = false;
@@ -118,7 +117,7 @@ int allocate_state(jb_ctx *c) {
   const JbGeom &g = c->g;
   if (g.elems >= (1ll << 31)) JB_FAIL(c, JB_ERR_UNSUPPORTED, "slab too large for 32-bit in-box offsets; use more ranks");
   const size_t comp = ((size_t)g.elems * sizeof(double) + 255) / 256 * 256;
-  const size_t total = 6 * comp + 256;
+  const size_t total = 9 * comp + 256;   // S0, S1, V (every box a neighbour slab stores into) + the halo flags: one IPC handle
   JB_CUDA(c, cudaMalloc(&c->slab, total));
   c->slab_bytes = total;
   JB_CUDA(c, cudaMemsetAsync(c->slab, 0, total, c->stream));
@@ -126,10 +125,11 @@ int allocate_state(jb_ctx *c) {
   for (int k = 0; k < 3; ++k) {
     c->S0[k] = reinterpret_cast<double *>(base + (size_t)k * comp);
     c->S1[k] = reinterpret_cast<double *>(base + (size_t)(3 + k) * comp);
+    c->V[k] = reinterpret_cast<double *>(base + (size_t)(6 + k) * comp);
     JB_CUDA(c, cudaMalloc(&c->U[k], comp));
     JB_CUDA(c, cudaMemsetAsync(c->U[k], 0, comp, c->stream));
   }
-  c->flags = reinterpret_cast<unsigned long long *>(base + 6 * comp);
+  c->flags = reinterpret_cast<unsigned long long *>(base + 9 * comp);
   c->state_allocated = true;
   c->tmap_valid = false;
   c->halo_connected = false;
@@ -1120,15 +1120,9 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
   if (!c || nsteps < 0 || !(dt > 0.0) || T < 0.0) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
-  if (c->d.n_ranks > 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 runs on one slab only in this version (the second stage-input box is not peer-mapped)");
+  const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
+  if (multi && !c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: jb_halo_connect has not been called");
   if (c->has_pairs) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 needs a translation-invariant exchange template (jb_set_exchange_template, or jb_set_exchange_pairs with template detection)");
-  if (!c->V[0]) {   // second stage-input box, ghosts included (zero across open boundaries like the other boxes)
-    const size_t comp = ((size_t)c->g.elems * sizeof(double) + 255) / 256 * 256;
-    for (int k = 0; k < 3; ++k) {
-      JB_CUDA(c, cudaMalloc(&c->V[k], comp));
-      JB_CUDA(c, cudaMemsetAsync(c->V[k], 0, comp, c->stream));
-    }
-  }
   const bool periodic_x = c->g.per[0] && c->g.gx > 0;
   for (int done = 0; done < nsteps;) {
     const int chunk = c->has_ac ? std::min(nsteps - done, 1024) : nsteps - done;
@@ -1147,17 +1141,27 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
         fill_tables(c, p.t, c->has_ac ? 3 * n + tsel : 0);
         double *const *in = stage == 0 ? c->S0 : (stage == 2 ? c->V : c->S1);          // S0 -> S1 -> V -> S1 -> S0
         double *const *out = stage == 0 ? c->S1 : (stage == 1 ? c->V : (stage == 2 ? c->S1 : c->S0));
+        double *const *plo = stage == 0 ? c->peer_lo_S1 : (stage == 1 ? c->peer_lo_V : (stage == 2 ? c->peer_lo_S1 : c->peer_lo_S0));
+        double *const *phi = stage == 0 ? c->peer_hi_S1 : (stage == 1 ? c->peer_hi_V : (stage == 2 ? c->peer_hi_S1 : c->peer_hi_S0));
         for (int k = 0; k < 3; ++k) {
           p.in[k] = in[k]; p.out[k] = out[k]; p.u[k] = c->U[k]; p.s_old[k] = c->S0[k];
-          p.out_lo[k] = periodic_x ? out[k] : nullptr; p.out_hi[k] = periodic_x ? out[k] : nullptr;
+          if (multi) { p.out_lo[k] = plo[k]; p.out_hi[k] = phi[k]; }
+          else { p.out_lo[k] = periodic_x ? out[k] : nullptr; p.out_hi[k] = periodic_x ? out[k] : nullptr; }
         }
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
         p.thermal = T > 0.0 ? 1 : 0;
         p.dt = dt;
+        if (multi) {   // as in jb_step: the neighbours' previous stage wrote the ghosts this stage reads and read the boxes it writes
+          JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++;
+        }
         record_event(c, 0);
         JB_CUDA(c, jbk_rk4_stage_direct(p, stage, c->stream));
         c->launches++;
         record_event(c, 1);
+        if (multi) {
+          c->epoch++;
+          JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+        }
       }
     }
     done += chunk;
@@ -1307,6 +1311,7 @@ int jb_halo_export_handle(jb_ctx *c, void *blob_out) {
   for (int k = 0; k < 3; ++k) {
     b.off_S0[k] = (uint64_t)((char *)c->S0[k] - (char *)c->slab);
     b.off_S1[k] = (uint64_t)((char *)c->S1[k] - (char *)c->slab);
+    b.off_V[k] = (uint64_t)((char *)c->V[k] - (char *)c->slab);
   }
   b.off_flags = (uint64_t)((char *)c->flags - (char *)c->slab);
   JB_CUDA(c, cudaIpcGetMemHandle(&b.ipc, c->slab));
@@ -1356,6 +1361,8 @@ int jb_halo_connect(jb_ctx *c, const void *blob_lo, const void *blob_hi) {
     c->peer_lo_S1[k] = lo_base ? (double *)((char *)lo_base + lo.off_S1[k]) : nullptr;
     c->peer_hi_S0[k] = hi_base ? (double *)((char *)hi_base + hi.off_S0[k]) : nullptr;
     c->peer_hi_S1[k] = hi_base ? (double *)((char *)hi_base + hi.off_S1[k]) : nullptr;
+    c->peer_lo_V[k] = lo_base ? (double *)((char *)lo_base + lo.off_V[k]) : nullptr;
+    c->peer_hi_V[k] = hi_base ? (double *)((char *)hi_base + hi.off_V[k]) : nullptr;
   }
   c->peer_lo_flags = lo_base ? (unsigned long long *)((char *)lo_base + lo.off_flags) : nullptr;
   c->peer_hi_flags = hi_base ? (unsigned long long *)((char *)hi_base + hi.off_flags) : nullptr;

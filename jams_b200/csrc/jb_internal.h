@@ -225,7 +225,7 @@ struct jb_ctx {
   double *S0[3] = {nullptr, nullptr, nullptr};
   double *S1[3] = {nullptr, nullptr, nullptr};
   double *U[3] = {nullptr, nullptr, nullptr};
-  double *V[3] = {nullptr, nullptr, nullptr};     // second stage-input box of the RK4 solver (allocated on first use)
+  double *V[3] = {nullptr, nullptr, nullptr};     // second stage-input box of the RK4 solver (in the slab, so neighbours can store into it)
   bool state_allocated = false;
   double *d_aos = nullptr; size_t d_aos_bytes = 0;     // staging for host <-> device AoS
   double *d_scratch = nullptr; size_t d_scratch_bytes = 0;  // per-spin scalars / reductions
@@ -251,6 +251,7 @@ struct jb_ctx {
   // halo peers
   double *peer_lo_S0[3] = {nullptr, nullptr, nullptr}, *peer_lo_S1[3] = {nullptr, nullptr, nullptr};
   double *peer_hi_S0[3] = {nullptr, nullptr, nullptr}, *peer_hi_S1[3] = {nullptr, nullptr, nullptr};
+  double *peer_lo_V[3] = {nullptr, nullptr, nullptr}, *peer_hi_V[3] = {nullptr, nullptr, nullptr};
   unsigned long long *flags = nullptr;           // [0] = written by lo neighbour, [1] = by hi neighbour, [2] = error
   unsigned long long *peer_lo_flags = nullptr, *peer_hi_flags = nullptr;
   void *peer_lo_base = nullptr, *peer_hi_base = nullptr;  // mapped IPC allocations

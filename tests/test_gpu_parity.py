@@ -230,7 +230,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", [2, 3])
+@pytest.mark.parametrize("kernel", [2, 3, "rk4"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -246,14 +246,16 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     def new_ctx(rank, n):
         nx = dims[0] // n
         c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
-        c.set_option("kernel", kernel)   # 2: two launches per step, two halo exchanges; 3: fused step, one exchange two planes deep
+        if kernel != "rk4":
+            c.set_option("kernel", kernel)   # 2: two launches per step, two halo exchanges; 3: fused step, one exchange two planes deep
         c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
         c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
         return c
 
+    step = (lambda c, *a: c.step_rk4(*a)) if kernel == "rk4" else (lambda c, *a: c.step(*a))   # RK4: four exchanges per step
     single = new_ctx(0, 1)
     single.import_spins(s0)
-    single.step(steps, dt, 0.0, T, seed, 0)
+    step(single, steps, dt, 0.0, T, seed, 0)
     want = single.export_spins()
 
     ctxs = [new_ctx(r, n_slabs) for r in range(n_slabs)]
@@ -267,7 +269,7 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
         c.import_spins(s0[r * per:(r + 1) * per])
     for n in range(steps):
         for c in ctxs:
-            c.step(1, dt, n * dt, T, seed, n)
+            step(c, 1, dt, n * dt, T, seed, n)
     got = np.concatenate([c.export_spins() for c in ctxs])
     for c in ctxs:
         c.synchronize()
