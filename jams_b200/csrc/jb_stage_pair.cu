@@ -200,6 +200,13 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
     }
 
     for (int i = 0; i < it.xc; ++i) {
+      // the noise of this plane's sites depends on nothing but (site, step): evaluate it BEFORE waiting for the plane, so
+      // the Philox / Box-Muller instructions fill the time the warp would otherwise spend parked at the full barrier
+      float fa0 = 0.f, fa1 = 0.f, fa2 = 0.f, fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;
+      if (THERMAL && MOTIF1 && SPT == 1) {
+        site_normals_rk_f(p.rk, p.step, gs, fa0, fa1, fa2);
+        site_normals_rk_f(p.rk, p.step, gs + 1, fb0, fb1, fb2);   // M == 1: the site at z + 1 is the next id
+      }
       {
         const int s = wrapS(cslotS + 2 * gx);
         mbar_wait(smem_u32(&fullS[s]), (phS >> s) & 1u);
@@ -305,9 +312,13 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
           }
           double na0 = 0, na1 = 0, na2 = 0, nb0 = 0, nb1 = 0, nb2 = 0;
           if (THERMAL) {
-            const unsigned long long site = gs + k * kSite + m;
-            site_normals_rk(p.rk, p.step, site, na0, na1, na2);
-            site_normals_rk(p.rk, p.step, site + M, nb0, nb1, nb2);   // z + 1: the next site id but M - 1
+            if (MOTIF1 && SPT == 1) {   // drawn before the barrier wait
+              na0 = (double)fa0; na1 = (double)fa1; na2 = (double)fa2; nb0 = (double)fb0; nb1 = (double)fb1; nb2 = (double)fb2;
+            } else {
+              const unsigned long long site = gs + k * kSite + m;
+              site_normals_rk(p.rk, p.step, site, na0, na1, na2);
+              site_normals_rk(p.rk, p.step, site + M, nb0, nb1, nb2);   // z + 1: the next site id but M - 1
+            }
           }
           double2 ox, oy, oz, vx, vy, vz;
           if (p.debug_skip & 8) {   // timing experiments: no per-site physics, the pipeline only moves data
