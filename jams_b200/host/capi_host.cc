@@ -84,6 +84,7 @@ __attribute__((visibility("default"))) int jbh_run(const char *const *args, int 
       s.run();
       ++steps;
     }
+    s.post_process_monitors();   // core/jams++.cc:360-362
     if (steps_done) *steps_done = steps;
     if (spins_out) { const std::vector<double> sp = s.spins(); std::memcpy(spins_out, sp.data(), sp.size() * sizeof(double)); }
     return 0;

@@ -189,6 +189,7 @@ Lattice::Lattice(const Setting &config) {
   if (size.length() != 3) throw ConfigError("lattice.size must have 3 components");
   for (int n = 0; n < 3; ++n) dims[n] = static_cast<int>(size[n].as_int());
   if (const Setting *p = lat.find("periodic")) for (int n = 0; n < 3; ++n) periodic[n] = (*p)[n].as_bool();
+  if (const Setting *sf = lat.find("spins")) spins_file = sf->as_string();
   if (lat.exists("impurities")) throw std::runtime_error("lattice.impurities is not supported by the llg-heun-b200-gpu host layer");
   if (lat.exists("global_rotation") || lat.exists("orientation_axis")) throw std::runtime_error("lattice rotations are not supported by the llg-heun-b200-gpu host layer");
 
@@ -265,7 +266,28 @@ std::vector<double> Lattice::positions() const {   // core/lattice.cc:622-657,75
   }
   return p;
 }
-std::vector<double> Lattice::initial_spins(uint64_t seed) const {   // core/lattice.cc:703-733
+// load_array_from_tsv_file (helpers/load.h:21-47): whitespace-separated numbers, empty lines and lines starting with '#' or '//'
+// skipped (helpers/utils.h:115-127), the element count must match
+static std::vector<double> load_spins_tsv(const std::string &file_name, size_t expected) {
+  if (file_name.size() > 3 && file_name.substr(file_name.size() - 3) == ".h5")
+    throw std::runtime_error("lattice.spins: HDF5 is not available in this build; give the whitespace-separated text form (helpers/load.h:21-61)");
+  std::ifstream f(file_name);
+  if (!f.is_open()) throw std::runtime_error("failed to open file: " + file_name);
+  std::vector<double> out;
+  out.reserve(expected);
+  for (std::string line; std::getline(f, line);) {
+    const size_t a = line.find_first_not_of(" \t\r");
+    if (a == std::string::npos || line[a] == '#' || (line[a] == '/' && a + 1 < line.size() && line[a + 1] == '/')) continue;
+    std::stringstream is(line);
+    for (double v; is >> v;) out.push_back(v);
+  }
+  if (out.size() != expected)
+    throw std::runtime_error("loading array from file: '" + file_name + "' expected size: " + std::to_string(expected) + " actual size: " + std::to_string(out.size()));
+  return out;
+}
+
+std::vector<double> Lattice::initial_spins(uint64_t seed) const {   // core/lattice.cc:703-748
+  if (!spins_file.empty()) return load_spins_tsv(spins_file, 3 * static_cast<size_t>(num_spins));
   std::vector<double> s(3 * static_cast<size_t>(num_spins));
   std::mt19937_64 rng(seed);   // the reference seeds pcg32 from std::random_device here: "random" spins are unpinned by design
   std::normal_distribution<double> nd;
@@ -572,6 +594,7 @@ Monitor *Monitor::create(const Setting &settings, const Lattice &lattice, const 
   const std::string module = lowercase(settings.required("module").as_string());
   if (module == "magnetisation") return new MagnetisationMonitor(settings, lattice, prefix + "mag.tsv");
   if (module == "energy") return new EnergyMonitor(settings, prefix + "eng.tsv");
+  if (module == "hdf5" || module == "spins-tsv") return new SpinsTsvMonitor(settings, prefix);
   throw std::runtime_error("unknown monitor " + module + " (not supported by the llg-heun-b200-gpu host layer)");
 }
 
@@ -709,6 +732,31 @@ void B200HeunLLGSolver::notify_monitors() {
   for (auto &m : monitors_) if (m->is_updating(iteration_)) m->update(*this);
 }
 
+void B200HeunLLGSolver::post_process_monitors() {
+  for (auto &m : monitors_) m->post_process();
+}
+
+void SpinsTsvMonitor::write(const std::string &filename, const std::vector<double> &s, int iteration, double time) {
+  std::ofstream f(filename);
+  if (!f) throw std::runtime_error("cannot open " + filename);
+  f << "# spins " << s.size() / 3 << " x 3   iteration " << iteration << "   time_ps " << std::setprecision(17) << time << "\n";
+  f << std::setprecision(17);
+  for (size_t i = 0; i + 2 < s.size(); i += 3) f << s[i] << ' ' << s[i + 1] << ' ' << s[i + 2] << '\n';
+}
+
+void SpinsTsvMonitor::update(B200HeunLLGSolver &solver) {   // monitors/hdf5.cc:64-78: <name>_NNNNNNN
+  last_ = solver.spins(); last_iteration_ = solver.iteration(); last_time_ = solver.time();
+  char num[16];
+  std::snprintf(num, sizeof(num), "%07d", last_iteration_);
+  write(prefix_ + num + ".tsv", last_, last_iteration_, last_time_);
+  final_from_ = &solver;
+}
+
+void SpinsTsvMonitor::post_process() {   // monitors/hdf5.cc:52: <name>_final
+  if (!final_from_) return;
+  write(prefix_ + "final.tsv", final_from_->spins(), final_from_->iteration(), final_from_->time());
+}
+
 std::vector<double> B200HeunLLGSolver::compute_fields() {
   build();
   std::vector<double> h(3 * static_cast<size_t>(lattice_.num_spins));
@@ -797,6 +845,7 @@ void Simulation::run() {   // run_simulation (core/jams++.cc:326-377)
     solver_->notify_monitors();
     solver_->run();
   }
+  solver_->post_process_monitors();
 }
 
 }  // namespace jams_b200

@@ -103,7 +103,9 @@ class Lattice {
 
   // per-site arrays in reference site order (globals::mus/gyro/alpha/s/positions, core/lattice.cc:688-756)
   std::vector<double> mus() const, gyro() const, alpha() const;
-  std::vector<double> initial_spins(uint64_t seed) const;   // N x 3; "random" materials use a seeded uniform-on-sphere draw
+  std::vector<double> initial_spins(uint64_t seed) const;   // N x 3; "random" materials use a seeded uniform-on-sphere draw;
+                                                            // lattice.spins = "file" replaces them (core/lattice.cc:738-748)
+  std::string spins_file;                                   // lattice.spins
   std::vector<double> positions() const;                    // N x 3, lattice constants
   std::vector<int32_t> site_material() const, site_motif() const;
 
@@ -228,6 +230,26 @@ class MagnetisationMonitor : public Monitor {   // monitors/magnetisation.cc:21-
   std::ofstream tsv_file_;
 };
 
+// Spin snapshots for checkpoint / restart.  The reference's `hdf5` monitor writes <name>_NNNNNNN.h5 every output_steps and
+// <name>_final.h5 in post_process with the dataset /spins (N x 3 f64; monitors/hdf5.cc:28-52,64-78,94-150) and restarts through
+// lattice.spins = "file" (core/lattice.cc:738-748).  HDF5 is not available to this build, so module "hdf5" (alias
+// "spins-tsv") writes the same snapshots as whitespace-separated text, <name>_NNNNNNN.tsv / <name>_final.tsv -- the format the
+// reference's loader accepts for any extension other than .h5 (helpers/load.h:21-61): one spin per line, 17 significant digits
+// (round-trips exactly), '#' comment header.
+class SpinsTsvMonitor : public Monitor {
+ public:
+  SpinsTsvMonitor(const Setting &settings, const std::string &prefix) : Monitor(settings), prefix_(prefix) {}
+  void update(B200HeunLLGSolver &solver) override;
+  void post_process() override;
+  static void write(const std::string &filename, const std::vector<double> &s_aos, int iteration, double time);
+ private:
+  std::string prefix_;
+  std::vector<double> last_;
+  int last_iteration_ = 0;
+  double last_time_ = 0.0;
+  B200HeunLLGSolver *final_from_ = nullptr;   // the final snapshot is taken from the solver that was last seen
+};
+
 class EnergyMonitor : public Monitor {   // monitors/energy.cc:16-46
  public:
   EnergyMonitor(const Setting &settings, const std::string &filename);
@@ -263,6 +285,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
   void run();                                          // one Heun (or RK4) step (core/jams++.cc:341)
   void run_steps(int n);                               // n steps without returning to the host in between
   void notify_monitors();                              // core/solver.cc:110-116
+  void post_process_monitors();                        // core/jams++.cc:360-362
   std::vector<double> compute_fields();                // globals::h = sum_k field_k
 
   jb_ctx *ctx() { build(); return ctx_; }

@@ -330,6 +330,38 @@ def bloch_domain_wall(positions, spins, width, center, normal=(1, 0, 0), domain=
     return out
 
 
+def load_spins_tsv(path, num_spins):
+    """``lattice.spins = "file"`` through the text route of the reference's loader (core/lattice.cc:738-748,
+    helpers/load.h:21-61): whitespace-separated numbers, empty lines and lines starting with ``#`` or ``//`` skipped,
+    the element count must match.  Returns N x 3."""
+    if str(path).endswith(".h5"):
+        raise RuntimeError("lattice.spins: HDF5 is not available in this build; give the whitespace-separated text form")
+    vals = []
+    try:
+        fh = open(path)
+    except OSError:
+        raise RuntimeError("failed to open file: " + str(path))
+    with fh:
+        for line in fh:
+            t = line.strip()
+            if not t or t.startswith("#") or t.startswith("//"):
+                continue
+            vals.extend(float(v) for v in t.split())
+    if len(vals) != 3 * num_spins:
+        raise RuntimeError(f"loading array from file: '{path}' expected size: {3 * num_spins} actual size: {len(vals)}")
+    return np.asarray(vals, dtype=np.float64).reshape(num_spins, 3)
+
+
+def write_spins_tsv(path, s_aos, iteration=0, time_ps=0.0):
+    """the snapshot format of the C++ host's ``hdf5`` / ``spins-tsv`` monitor stand-in (jams_b200/host/jams_host.h):
+    one spin per line, 17 significant digits (round-trips exactly), ``#`` header"""
+    s = np.asarray(s_aos, dtype=np.float64).reshape(-1, 3)
+    with open(path, "w") as fh:
+        fh.write(f"# spins {len(s)} x 3   iteration {iteration}   time_ps {time_ps:.17g}\n")
+        for row in s:
+            fh.write("%.17g %.17g %.17g\n" % tuple(row))
+
+
 def rotation_matrix_between_vectors(a, b):
     """reference containers/mat3.h:334-366"""
     def unit(v):

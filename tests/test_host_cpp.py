@@ -165,3 +165,51 @@ def test_cpp_simulation_runs_the_shipped_example_setup_rk4_with_pinned_boundarie
     # the pinned regions point where they were told to
     m = got.reshape(32, 4, 4, 3)
     assert m[:2, ..., 2].mean() < -0.9 and m[-3:, ..., 2].mean() > 0.9
+
+
+def test_lattice_spins_file_is_read_like_the_reference_loader(tmp_path):
+    """lattice.spins = "file" (core/lattice.cc:738-748) through the text route of load_array_from_file (helpers/load.h:21-61):
+    whitespace separated, empty lines and '#' / '//' comment lines skipped, the element count must match"""
+    base = host.lattice_arrays(FIXTURE)
+    N = base["num_spins"]
+    rng = np.random.default_rng(5)
+    s = rng.standard_normal((N, 3)); s /= np.linalg.norm(s, axis=1, keepdims=True)
+    f = tmp_path / "state.tsv"
+    with open(f, "w") as fh:
+        fh.write("# spins\n\n// another comment\n")
+        for k, row in enumerate(s):
+            fh.write(("%.17g\t%.17g %.17g\n" % tuple(row)) if k % 2 else ("  %.17g %.17g %.17g  \n" % tuple(row)))
+    got = host.lattice_arrays(FIXTURE, 'lattice : { spins = "%s"; };' % f)
+    assert np.array_equal(got["spins"], s)
+    with open(f, "a") as fh:
+        fh.write("1.0 0.0\n")
+    with pytest.raises(host.HostError, match="expected size"):
+        host.lattice_arrays(FIXTURE, 'lattice : { spins = "%s"; };' % f)
+    with pytest.raises(host.HostError, match="failed to open file"):
+        host.lattice_arrays(FIXTURE, 'lattice : { spins = "%s"; };' % (tmp_path / "missing.tsv"))
+    with pytest.raises(host.HostError, match="HDF5 is not available"):
+        host.lattice_arrays(FIXTURE, 'lattice : { spins = "state.h5"; };')
+
+
+@pytest.mark.gpu
+def test_checkpoint_and_restart_through_the_spin_snapshot_monitor(tmp_path):
+    """the reference's checkpoint / resume idiom (monitors/hdf5.cc + lattice.spins): a run that stops after 20 steps,
+    writes <name>_final, and is resumed from that file reproduces the uninterrupted 40-step run bit for bit (T = 0)"""
+    import re
+    cfg = tmp_path / "noinit.cfg"   # the fixture without its initializer group (a resumed run must not re-initialise) and random initial spins
+    text = re.sub(r"initializer\s*:\s*\{.*?\};", "", open(FIXTURE).read(), flags=re.S)
+    open(cfg, "w").write(text.replace("spin      = [0.0, 0.0, 1.0];", 'spin      = "random";') + "\nsim : { seed = 7; };\n")
+    cfg = str(cfg)
+    mon = 'monitors = ( { module = "hdf5"; output_steps = 10; } ); '
+    full, n = host.run(cfg, PATCH_B200 + mon, name="full", output_dir=str(tmp_path))
+    assert n == 40 and np.abs(full - host.lattice_arrays(cfg)["spins"]).max() > 1e-6     # something happened
+    half, n = host.run(cfg, PATCH_B200 + mon + 'solver : { t_max = 2e-15; };', name="half", output_dir=str(tmp_path))
+    assert n == 20
+    for k in (0, 10):
+        assert (tmp_path / ("half_%07d.tsv" % k)).exists()
+    final = np.loadtxt(tmp_path / "half_final.tsv")
+    assert np.array_equal(final, half)
+    rest, n = host.run(cfg, PATCH_B200 + 'solver : { t_max = 2e-15; }; lattice : { spins = "%s"; };' % (tmp_path / "half_final.tsv"),
+                       name="rest", output_dir=str(tmp_path))
+    assert n == 20
+    assert np.array_equal(rest, full)

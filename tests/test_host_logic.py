@@ -176,3 +176,15 @@ def test_pinned_boundary_regions_follow_the_reference_predicates():
     assert len(p.region_sites(0, False, 2, 4, 4)) == 0
     right = p.region_sites(0, True, 1, 4, 4)
     assert len(right) == 3 * 4 * 2 and right.min() == 3 * 3 * 4 * 2
+
+
+def test_spin_snapshot_text_format_round_trips_exactly(tmp_path):
+    from jams_b200.lattice import load_spins_tsv, write_spins_tsv
+    s = np.random.default_rng(1).standard_normal((37, 3))
+    s /= np.linalg.norm(s, axis=1, keepdims=True)
+    write_spins_tsv(tmp_path / "a.tsv", s, iteration=12, time_ps=1.2e-3)
+    assert np.array_equal(load_spins_tsv(tmp_path / "a.tsv", 37), s)
+    with pytest.raises(RuntimeError, match="expected size"):
+        load_spins_tsv(tmp_path / "a.tsv", 36)
+    with pytest.raises(RuntimeError, match="failed to open file"):
+        load_spins_tsv(tmp_path / "nope.tsv", 37)
