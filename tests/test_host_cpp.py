@@ -201,15 +201,15 @@ def test_checkpoint_and_restart_through_the_spin_snapshot_monitor(tmp_path):
     open(cfg, "w").write(text.replace("spin      = [0.0, 0.0, 1.0];", 'spin      = "random";') + "\nsim : { seed = 7; };\n")
     cfg = str(cfg)
     mon = 'monitors = ( { module = "hdf5"; output_steps = 10; } ); '
-    full, n = host.run(cfg, PATCH_B200 + mon, name="full", output_dir=str(tmp_path))
+    full, n = host.run(cfg, PATCH_B200, mon, name="full", output_dir=str(tmp_path))
     assert n == 40 and np.abs(full - host.lattice_arrays(cfg)["spins"]).max() > 1e-6     # something happened
-    half, n = host.run(cfg, PATCH_B200 + mon + 'solver : { t_max = 2e-15; };', name="half", output_dir=str(tmp_path))
+    half, n = host.run(cfg, PATCH_B200, mon, 'solver : { t_max = 2e-15; };', name="half", output_dir=str(tmp_path))
     assert n == 20
     for k in (0, 10):
         assert (tmp_path / ("half_%07d.tsv" % k)).exists()
     final = np.loadtxt(tmp_path / "half_final.tsv")
     assert np.array_equal(final, half)
-    rest, n = host.run(cfg, PATCH_B200 + 'solver : { t_max = 2e-15; }; lattice : { spins = "%s"; };' % (tmp_path / "half_final.tsv"),
+    rest, n = host.run(cfg, PATCH_B200, 'solver : { t_max = 2e-15; }; lattice : { spins = "%s"; };' % (tmp_path / "half_final.tsv"),
                        name="rest", output_dir=str(tmp_path))
     assert n == 20
     assert np.array_equal(rest, full)
