@@ -251,11 +251,16 @@ def run_b200(args):
         dom = 0
     else:
         dom = int(np.argmax(stage_ms))
-        ach = BYTES_PER_STAGE * n_local / (stage_ms[dom] * 1e-3) / 1e9
+        # the pair kernel's T = 0 default stores no Heun intermediate (option recover_u): its predictor moves 48 B per spin
+        recover = TEMPERATURE == 0.0 and (args.kernel is None or args.kernel == 2)
+        stage_bytes = 48.0 if (recover and dom == 0) else BYTES_PER_STAGE
+        ach = stage_bytes * n_local / (stage_ms[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": ["stage A (predictor)", "stage B (corrector)"][dom], "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
-                    "algorithmic_bytes_per_launch": BYTES_PER_STAGE * n_local,
+                    "algorithmic_bytes_per_launch": stage_bytes * n_local,
                     "stage_ms": [float(stage_ms[0]), float(stage_ms[1])],
+                    "data_flow": ("recover_u: stage A moves 48 B and stage B 72 B per spin (120 B per update); step_frac is quoted against SURVEY 8d's 144 B per update model"
+                                  if recover else "store u: 72 B per spin and stage (144 B per update)"),
                     "step_frac": BYTES_PER_UPDATE * n_local / ((stage_ms[0] + stage_ms[1]) * 1e-3) / 1e9 / peak}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(traffic_file):
@@ -321,9 +326,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel", type=int, default=None, help="0 = direct gathers, 1 = TMA plane ring, 2 = pair kernel (two launches per step), 3 = fused step kernel (default)")
+    ap.add_argument("--temperature", type=float, default=None, help="thermostat temperature of the workload in K (default 100; 0 = the deterministic T = 0 variant, a profile artefact and not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=10)
     args = ap.parse_args()
+    if args.temperature is not None:
+        global TEMPERATURE
+        TEMPERATURE = float(args.temperature)
     if args.impl == "reference":
         run_reference(args)
     else:

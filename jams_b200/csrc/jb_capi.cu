@@ -411,8 +411,10 @@ void choose_tiling(jb_ctx *c) {
       q.RU = c->opt_RU ? c->opt_RU : 2;
       const size_t slot_bytes = (size_t)3 * q.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
       const size_t u_bytes = (size_t)q.RU * 3 * q.slotU * 8;
+      // noise ring of the noise warp (one-site motifs, SPT 1): two slots of three fp32 per site of the tile
+      const size_t n_bytes = (g.M == 1 && q.SPT == 1 && c->opt_noise_warp) ? (size_t)2 * 3 * q.slotU * 4 : 0;
       for (int st = 0; st < 2; ++st) {
-        const size_t fixed = 512 + (st == 1 ? u_bytes : 0);
+        const size_t fixed = 512 + (st == 1 ? u_bytes : 0) + n_bytes;
         int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
         R = std::min(R, JB_PAIR_MAX_RING);
         // one plane in flight per CTA is the measured optimum: with the stores in the mix, more outstanding plane loads
@@ -612,10 +614,10 @@ int build_tmaps(jb_ctx *c) {
   const cuuint64_t dims[3] = {(cuuint64_t)g.PZ, (cuuint64_t)g.PY * g.M, (cuuint64_t)g.PX};
   const cuuint64_t strides[2] = {(cuuint64_t)g.PZ * 8, (cuuint64_t)g.sX * 8};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int a = 0; a < 3; ++a) {
+  for (int a = 0; a < 5; ++a) {
     const cuuint32_t box[3] = {(cuuint32_t)(a < 2 ? t.BZ : t.UZ), (cuuint32_t)((a < 2 ? t.BY : t.TY) * g.M), 1};
     for (int k = 0; k < 3; ++k) {
-      double *base = a == 0 ? c->S0[k] : (a == 1 ? c->S1[k] : c->U[k]);
+      double *base = a == 0 || a == 3 ? c->S0[k] : (a == 1 || a == 4 ? c->S1[k] : c->U[k]);
       CUresult r = encode(&c->tmap[a][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1048,6 +1050,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
       for (int k = 0; k < 3; ++k) {   // s_{n+1} becomes the current state
         std::swap(c->S0[k], c->S1[k]);
         std::swap(c->tmap[0][k], c->tmap[1][k]);
+        std::swap(c->tmap[3][k], c->tmap[4][k]);
         std::swap(c->peer_lo_S0[k], c->peer_lo_S1[k]);
         std::swap(c->peer_hi_S0[k], c->peer_hi_S1[k]);
       }
@@ -1072,7 +1075,10 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         }
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
         // the corrector needs no noise: the predictor folds the noise part of its right-hand side into u (jb_device.cuh)
-        const int th = stage == 0 ? thermal : 0;
+        // (with recover_u the pair kernel stores no u, and its corrector draws the noise itself)
+        // (option recover_u: 2 = where it is measured faster, i.e. at T = 0 -- at T > 0 the second noise draw costs what the 24 B save)
+        const bool recu = use_tile && c->tiling.pair && !c->has_pairs && (c->opt_recover_u == 1 || (c->opt_recover_u == 2 && !thermal));
+        const int th = (stage == 0 || recu) ? thermal : 0;
         p.thermal = th;
         if (multi) {
           // ghosts I read were written by the neighbours' previous stage; the boxes I write into were
@@ -1085,13 +1091,16 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         } else if (use_tile) {
           for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
           tp.step = p.step;
+          tp.recover_u = recu ? 1 : 0;
+          tp.noise_warp = (c->tiling.pair && c->g.M == 1 && c->tiling.SPT == 1) ? c->opt_noise_warp : 0;
           const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
           for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
           tp.R = c->tiling.Rs[stage];
           rc = tile_launch_shape(c, tp, stage, th); if (rc) return rc;
           tp.n_chunks = c->tiling.n_chunks[stage][th];
           tp.n_items = tp.n_chunks * tp.n_cols;
-          const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[2][0], c->tmap[2][1], c->tmap[2][2]};
+          const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
+          const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
           tp.reverse_items = (c->tiling.pair && stage == 1 && c->opt_reverse_b) ? 1 : 0;
           if (c->tiling.pair)
             JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
@@ -1406,6 +1415,8 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   if (!c || !key) return JB_ERR_INVALID;
   const std::string k(key);
   if (k == "kernel") c->opt_kernel = (int)value;
+  else if (k == "recover_u") c->opt_recover_u = (int)value;
+  else if (k == "noise_warp") c->opt_noise_warp = (int)value;
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
   else if (k == "spt") c->opt_SPT = (int)value;

@@ -144,6 +144,17 @@ __device__ __forceinline__ double rsqrt_nobranch(double x) {
   const double q = fma(e, 0.375, 0.5);
   return fma(q, e * y, y);
 }
+// Heun intermediate from the predictor spin (pair kernel, option recover_u): k1 is perpendicular to s, so
+// s + dt k1 = lambda s* with lambda = (s.s) / (s*.s) and u = s + dt/2 k1 = (s + lambda s*) / 2.  In: (ux,uy,uz) = s_n,
+// (px,py,pz) = s*; out: (ux,uy,uz) = u.  A vacancy (s = s* = 0) keeps u = 0.  1 / (s*.s) = rsqrt^2 (s*.s > 0 always: it is
+// (s.s) / lambda), <= 3 ulp, i.e. the same 1e-16 absolute error a stored u carries.
+__device__ __forceinline__ void recover_u(double px, double py, double pz, double &ux, double &uy, double &uz) {
+  const double d = fma(px, ux, fma(py, uy, pz * uz));
+  const double nn = fma(ux, ux, fma(uy, uy, uz * uz));
+  const double r = rsqrt_nobranch(d);
+  const double hl = (d > 4.930380657631324e-32) ? 0.5 * nn * r * r : 0.0;   // lambda / 2
+  ux = fma(hl, px, 0.5 * ux); uy = fma(hl, py, 0.5 * uy); uz = fma(hl, pz, 0.5 * uz);
+}
 template <int STAGE, bool THERMAL>
 __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
                                          double hx, double hy, double hz,

@@ -138,6 +138,9 @@ struct JbTileParams {
   int reverse_items;     // walk the work items from the last to the first (stage B: the data stage A wrote last is still in L2)
   int load_hint;         // pair kernel, TMA loads: 0 = none, 1 = evict_first on u, 2 = + evict_last on S, 3 = evict_first on both
   int debug_skip;        // timing experiments only: 1 = no compute (TMA pipeline alone), 2 = no stores
+  int noise_warp;        // pair kernel, one-site motifs at T > 0: 0 = every consumer thread draws its own noise, 1 = a dedicated warp draws it one
+                         // plane ahead into a shared-memory ring, 2 = that warp draws the odd-z site of every pair only
+  int recover_u;         // pair kernel: the Heun intermediate is rebuilt from s_n and s* instead of stored (120 B per update)
   int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
   int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
   int nbr_odd[JB_TILE_MAX_MOTIF];    // pair kernel: [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
@@ -232,7 +235,8 @@ struct jb_ctx {
   double *h_pinned = nullptr; size_t h_pinned_bytes = 0;
 
   // TMA descriptors: [0] = S0 x,y,z  [1] = S1 x,y,z (tile + halo boxes)  [2] = U x,y,z (tile boxes)
-  CUtensorMap tmap[3][3];
+  // [3] = S0, [4] = S1 with the tile box of U (pair kernel, recover_u: the corrector reads the site's own s_n)
+  CUtensorMap tmap[5][3];
   bool tmap_valid = false;
 
   // options
@@ -243,6 +247,8 @@ struct jb_ctx {
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
   int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0, opt_load_hint = 0, opt_reverse_b = 0;
   int opt_smem_pad = 0;
+  int opt_noise_warp = 0;     // pair kernel: see JbTileParams::noise_warp
+  int opt_recover_u = 2;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B), 2 = 1 at T = 0, 0 at T > 0
   int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows
   bool state_relayout = false; // an option that changes the box layout was set: re-layout at the next ensure_ready
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template

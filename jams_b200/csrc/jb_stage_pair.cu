@@ -40,8 +40,20 @@ using namespace jbdev;
 // SPT: y sites per thread (x 2 z sites).  MOTIF1: one motif site, class constants through the constant bank.
 // 288 threads x 2 CTAs = 18 warps per SM = 5 per scheduler: 16384 / 5 -> at most 96 registers per thread (ptxas picks that
 // from the launch bounds; 104-112 registers silently drop the kernel to one CTA per SM: measured 0.32 instead of 0.24 ms)
-template <int STAGE, bool THERMAL, bool ISO, int SPT, bool MOTIF1>
-__global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
+//
+// RECU ("recover u", option `recover_u`): the Heun intermediate is not stored at all.  k1 is perpendicular
+// to s_n, so s_n + dt k1 = lambda s* with lambda = (s_n.s_n) / (s*.s_n), hence u = s_n + dt/2 k1 = (s_n + lambda s*) / 2:
+// the predictor writes only s* (48 instead of 72 B per site), the corrector reads the site's own s_n through the ring that
+// otherwise carries u (same tile box, tensor map over the S box), rebuilds u in registers and writes s_{n+1} in place
+// (72 B) -- 120 instead of 144 B of HBM traffic per spin-update.  The corrector then draws the site's noise itself
+// (THERMAL instantiation), as the reference does (solvers/cuda_llg_heun.cu:79: one draw per step, used by both stages).
+//
+// Noise warp (option `noise_warp`, THERMAL && MOTIF1 && SPT == 1): the Philox / Box-Muller evaluation -- 30 % of a consumer
+// warp's instructions at T > 0, all of them on its critical path -- moves to one more specialised warp that runs ahead of the
+// consumers and leaves the draws of a plane (3 fp32 per site: they are exact fp32 values) in a two-slot shared-memory ring
+// with its own full / empty mbarriers.  1 = all draws; 2 = the odd-z site of every pair (the consumer draws the even one).
+template <int STAGE, bool THERMAL, bool ISO, int SPT, bool MOTIF1, bool RECU>
+__global__ void __launch_bounds__(320, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
                                                             const __grid_constant__ CUtensorMap tS2,
                                                             const __grid_constant__ CUtensorMap tU0,
@@ -55,12 +67,16 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
   const int slotS = p.slotS, slotU = p.slotU;
   double *ringS = reinterpret_cast<double *>(smem_raw);
   double *ringU = ringS + (size_t)R * 3 * slotS;
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringU + (STAGE == 1 ? (size_t)RU * 3 * slotU : 0));
+  constexpr bool NOISEW = THERMAL && MOTIF1 && SPT == 1;
+  const int nw = NOISEW ? p.noise_warp : 0;        // 0 = consumers draw their own noise, 1 / 2 = a noise warp draws all / half of it
+  float *ringN = reinterpret_cast<float *>(ringU + (STAGE == 1 ? (size_t)RU * 3 * slotU : 0));   // 2 slots x 3 components x slotU floats
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringN + (nw ? 2 * 3 * slotU : 0));
   unsigned long long *fullS = bars, *emptyS = bars + JB_PAIR_BARS, *fullU = bars + 2 * JB_PAIR_BARS, *emptyU = bars + 3 * JB_PAIR_BARS;
-  JbTileNbr *s_nbr = reinterpret_cast<JbTileNbr *>(bars + 4 * JB_PAIR_BARS);
+  unsigned long long *fullN = bars + 4 * JB_PAIR_BARS, *emptyN = fullN + 2;
+  JbTileNbr *s_nbr = reinterpret_cast<JbTileNbr *>(bars + 4 * JB_PAIR_BARS + 4);
 
   const int tid = threadIdx.x;
-  const int n_cw = (blockDim.x >> 5) - 1;          // consumer warps; warp n_cw is the producer
+  const int n_cw = (blockDim.x >> 5) - 1 - (nw ? 1 : 0);   // consumer warps; warp n_cw is the producer, warp n_cw + 1 the noise warp
   const int G = gridDim.x, bid = blockIdx.x;
 
   if (tid == 0) {
@@ -68,6 +84,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
       mbar_init(smem_u32(&fullS[s]), 1); mbar_init(smem_u32(&emptyS[s]), n_cw);
       mbar_init(smem_u32(&fullU[s]), 1); mbar_init(smem_u32(&emptyU[s]), n_cw);
     }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&fullN[s]), 1); mbar_init(smem_u32(&emptyN[s]), n_cw); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // per ring phase c (= slot of the oldest resident plane) and template entry n: byte offset of the neighbour
@@ -144,6 +161,39 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
     return;
   }
 
+  // =========================== noise warp: the draws of every plane, one plane ahead of the consumers ===========================
+  if (NOISEW && nw && warp_idx == n_cw + 1) {
+    const int lane = tid & 31;
+    const int nq = nw == 2 ? p.TY * (p.UZ >> 1) : p.TY * p.UZ;   // work units per plane: odd-z sites, or all sites
+    int nslot = 0;
+    uint32_t pne = 0xffffffffu;
+    for (int item0 = bid; item0 < p.n_items; item0 += G) {
+      const int item = p.reverse_items ? p.n_items - 1 - item0 : item0;
+      const ItemGeom it = item_geom(p, item);
+      unsigned long long gs0 = global_site(g, it.x0, it.y0, 0, it.z0);   // M == 1
+      for (int i = 0; i < it.xc; ++i) {
+        mbar_wait(smem_u32(&emptyN[nslot]), (pne >> nslot) & 1u);
+        pne ^= 1u << nslot;
+        float *dst = ringN + (size_t)nslot * 3 * slotU;
+#pragma unroll 2
+        for (int q = lane; q < nq; q += 32) {
+          const int sidx = nw == 2 ? 2 * q + 1 : q;          // site of the tile: row ty, column zt
+          const int ty = sidx / p.UZ, zt = sidx - ty * p.UZ;
+          if (it.y0 + ty < g.Ny && it.z0 + zt < g.Nz) {
+            float a, b, c;
+            site_normals_rk_f(p.rk, p.step, gs0 + (unsigned long long)ty * g.Nz + zt, a, b, c);
+            dst[sidx] = a; dst[slotU + sidx] = b; dst[2 * slotU + sidx] = c;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&fullN[nslot]));
+        nslot ^= 1;
+        gs0 += (unsigned long long)g.Ny * g.Nz;
+      }
+    }
+    return;
+  }
+
   // =========================== consumers: SPT y rows x M motif sites x one z pair each ===========================
   const int HZ = (p.TZ + 1) >> 1;                        // pairs per tile row
   const int zp = tid % HZ, tyg = tid / HZ;
@@ -164,8 +214,9 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
   const unsigned long long planeSites = (unsigned long long)g.Ny * g.Nz * M;
   const bool lane0 = (tid & 31) == 0;
 
-  int cslotS = 0, cslotU = 0;
-  uint32_t phS = 0, phU = 0;
+  int cslotS = 0, cslotU = 0, cslotN = 0;
+  uint32_t phS = 0, phU = 0, phN = 0;
+  const uint32_t nown = smem_u32(ringN) + (uint32_t)(ty0 * p.UZ + 2 * zp) * 4u;   // own pair's draws in slot 0 of the noise ring
   auto wrapS = [&](int a) { return a >= R ? a - R : a; };
   const int sh = p.store_hint;
   const unsigned long long spol = make_policy(sh == 4 ? 1 : 0);
@@ -203,7 +254,18 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
       // the noise of this plane's sites depends on nothing but (site, step): evaluate it BEFORE waiting for the plane, so
       // the Philox / Box-Muller instructions fill the time the warp would otherwise spend parked at the full barrier
       float fa0 = 0.f, fa1 = 0.f, fa2 = 0.f, fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;
-      if (THERMAL && MOTIF1 && SPT == 1) {
+      if (NOISEW && nw) {
+        mbar_wait(smem_u32(&fullN[cslotN]), (phN >> cslotN) & 1u);
+        phN ^= 1u << cslotN;
+        const uint32_t na = nown + (uint32_t)cslotN * 3u * (uint32_t)slotU * 4u;
+        const float2 v0 = lds_f2(na), v1 = lds_f2(na + (uint32_t)slotU * 4u), v2 = lds_f2(na + 2u * (uint32_t)slotU * 4u);
+        __syncwarp();
+        if (lane0) mbar_arrive(smem_u32(&emptyN[cslotN]));
+        cslotN ^= 1;
+        fb0 = v0.y; fb1 = v1.y; fb2 = v2.y;
+        if (nw == 2) site_normals_rk_f(p.rk, p.step, gs, fa0, fa1, fa2);
+        else { fa0 = v0.x; fa1 = v1.x; fa2 = v2.x; }
+      } else if (THERMAL && MOTIF1 && SPT == 1) {
         site_normals_rk_f(p.rk, p.step, gs, fa0, fa1, fa2);
         site_normals_rk_f(p.rk, p.step, gs + 1, fb0, fb1, fb2);   // M == 1: the site at z + 1 is the next id
       }
@@ -309,6 +371,10 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
           if (STAGE == 1) {
             const uint32_t ua = uplane + (uint32_t)(m * p.UZ) * 8u + k * kU8;
             ux = lds128(ua); uy = lds128(ua + cu8); uz = lds128(ua + 2 * cu8);
+            if (RECU) {   // the ring delivered s_n: rebuild u = (s_n + lambda s*) / 2
+              recover_u(sx[k].x, sy[k].x, sz[k].x, ux.x, uy.x, uz.x);
+              recover_u(sx[k].y, sy[k].y, sz[k].y, ux.y, uy.y, uz.y);
+            }
           }
           double na0 = 0, na1 = 0, na2 = 0, nb0 = 0, nb1 = 0, nb2 = 0;
           if (THERMAL) {
@@ -337,14 +403,14 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
           const int idx = ic + m * g.PZ + k * kG;
           if ((ok1 >> k) & 1u) {          // both sites: 16-byte stores
             if (sh == 0) {
-              if (STAGE == 0) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
+              if (STAGE == 0 && !RECU) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
               stg128(&p.out[0][idx], ox.x, ox.y); stg128(&p.out[1][idx], oy.x, oy.y); stg128(&p.out[2][idx], oz.x, oz.y);
             } else {
-              if (STAGE == 0) { stg128_hint(&p.u[0][idx], vx.x, vx.y, sh, spol); stg128_hint(&p.u[1][idx], vy.x, vy.y, sh, spol); stg128_hint(&p.u[2][idx], vz.x, vz.y, sh, spol); }
+              if (STAGE == 0 && !RECU) { stg128_hint(&p.u[0][idx], vx.x, vx.y, sh, spol); stg128_hint(&p.u[1][idx], vy.x, vy.y, sh, spol); stg128_hint(&p.u[2][idx], vz.x, vz.y, sh, spol); }
               stg128_hint(&p.out[0][idx], ox.x, ox.y, sh, spol); stg128_hint(&p.out[1][idx], oy.x, oy.y, sh, spol); stg128_hint(&p.out[2][idx], oz.x, oz.y, sh, spol);
             }
           } else if ((ok0 >> k) & 1u) {   // odd Nz: the last pair of a row holds one site
-            if (STAGE == 0) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
+            if (STAGE == 0 && !RECU) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
             p.out[0][idx] = ox.x; p.out[1][idx] = oy.x; p.out[2][idx] = oz.x;
           }
           if (!(xb | ((ygen >> k) & 1u))) {
@@ -376,12 +442,13 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
 }
 
 template <typename F>
-cudaError_t with_kernel(int stage, int thermal, int iso, int spt, int motif1, F &&f) {
-#define JB_PAIR_CASE(ST, TH, IS, SP, M1) \
-  if (stage == ST && thermal == TH && iso == IS && spt == SP && motif1 == M1) \
-    return f(stage_pair_kernel<ST, (TH != 0), (IS != 0), SP, (M1 != 0)>);
+cudaError_t with_kernel(int stage, int thermal, int iso, int spt, int motif1, int recu, F &&f) {
+#define JB_PAIR_CASE(ST, TH, IS, SP, M1, RU_) \
+  if (stage == ST && thermal == TH && iso == IS && spt == SP && motif1 == M1 && recu == RU_) \
+    return f(stage_pair_kernel<ST, (TH != 0), (IS != 0), SP, (M1 != 0), (RU_ != 0)>);
 #define JB_PAIR_CASES_SPT(ST, TH, IS) \
-  JB_PAIR_CASE(ST, TH, IS, 1, 0) JB_PAIR_CASE(ST, TH, IS, 2, 0) JB_PAIR_CASE(ST, TH, IS, 1, 1) JB_PAIR_CASE(ST, TH, IS, 2, 1)
+  JB_PAIR_CASE(ST, TH, IS, 1, 0, 0) JB_PAIR_CASE(ST, TH, IS, 2, 0, 0) JB_PAIR_CASE(ST, TH, IS, 1, 1, 0) JB_PAIR_CASE(ST, TH, IS, 2, 1, 0) \
+  JB_PAIR_CASE(ST, TH, IS, 1, 0, 1) JB_PAIR_CASE(ST, TH, IS, 2, 0, 1) JB_PAIR_CASE(ST, TH, IS, 1, 1, 1) JB_PAIR_CASE(ST, TH, IS, 2, 1, 1)
   JB_PAIR_CASES_SPT(0, 0, 0) JB_PAIR_CASES_SPT(0, 0, 1) JB_PAIR_CASES_SPT(0, 1, 0) JB_PAIR_CASES_SPT(0, 1, 1)
   JB_PAIR_CASES_SPT(1, 0, 0) JB_PAIR_CASES_SPT(1, 0, 1) JB_PAIR_CASES_SPT(1, 1, 0) JB_PAIR_CASES_SPT(1, 1, 1)
 #undef JB_PAIR_CASES_SPT
@@ -391,21 +458,24 @@ cudaError_t with_kernel(int stage, int thermal, int iso, int spt, int motif1, F 
 
 }  // namespace
 
+// the kernel's NOISEW condition, host side
+static bool noise_warp_on(const JbTileParams &p, int thermal, int spt) { return p.noise_warp != 0 && thermal != 0 && p.g.M == 1 && spt == 1; }
+
 cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
                                      size_t smem_bytes, int *blocks_per_sm) {
-  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
+  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, p.recover_u ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32, smem_bytes);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32 + (noise_warp_on(p, thermal, spt) ? 32 : 0), smem_bytes);
   });
 }
 
 cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int iso, int spt,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream) {
-  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
+  return with_kernel(stage, thermal, iso, spt, p.g.M == 1 ? 1 : 0, p.recover_u ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
-    k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    k<<<grid, ((threads + 31) & ~31) + 32 + (noise_warp_on(p, thermal, spt) ? 32 : 0), smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     return cudaGetLastError();
   });
 }

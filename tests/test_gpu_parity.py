@@ -21,6 +21,10 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TRAJ_TOL = 1e-10
 KERNELS = {"direct": dict(kernel=0), "tma": dict(kernel=1), "pair": dict(kernel=2), "pair_spt2": dict(kernel=2, spt=2),
+           # recover_u = 1: the pair kernel rebuilds the Heun intermediate from s_n and s* (120 B per update); 0: stores it (144 B);
+           # default (2): 1 at T = 0, 0 at T > 0
+           "pair_store_u": dict(kernel=2, recover_u=0), "pair_spt2_store_u": dict(kernel=2, spt=2, recover_u=0),
+           "pair_recover_u": dict(kernel=2, recover_u=1), "pair_spt2_recover_u": dict(kernel=2, spt=2, recover_u=1),
            "fused": dict(kernel=3), "fused_small_tile": dict(kernel=3, tile_y=4, tile_z=32, ring=4)}
 
 
@@ -81,7 +85,7 @@ def test_fields_and_energies_match_reference_golden(name, pairs):
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if "T0" in n])
-@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile", "pairs", "pairs_auto"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "pair_store_u", "pair_spt2_store_u", "fused", "fused_small_tile", "pairs", "pairs_auto"])
 def test_T0_trajectories_match_reference_golden(name, variant):
     case, g = CASES[name], gold(f"case_{name}.npz")
     w = case["workload"]()
@@ -95,7 +99,7 @@ def test_T0_trajectories_match_reference_golden(name, variant):
     assert abs(s.time - float(g["time_final"])) < 1e-15
 
 
-@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile", "pairs"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_spt2", "pair_store_u", "pair_recover_u", "pair_spt2_recover_u", "fused", "fused_small_tile", "pairs"])
 def test_thermal_trajectory_matches_oracle_given_the_same_noise(variant):
     """T > 0: the reference's CPU (pcg) and GPU (XORWOW) noise streams already differ, so parity is defined on the
     integrator given identical noise: dump the Philox normals the kernels use and feed them to the oracle."""
@@ -175,7 +179,7 @@ def test_midsize_trajectories_match_oracle(make_w, steps):
     sim.set_spins(s0)
     sim.run(steps)
     want = sim.get_spins()
-    for variant in ("direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile"):
+    for variant in ("direct", "tma", "pair", "pair_spt2", "pair_store_u", "fused", "fused_small_tile"):
         s = make(w, options=KERNELS[variant])
         s.set_spins(s0)
         s.run(steps)
@@ -188,7 +192,7 @@ def test_partial_tiles_and_odd_sizes(dims):
     lat = w["lattice"]
     s0 = random_unit_spins(lat.num_spins, 13)
     res = {}
-    for variant in ("direct", "tma", "pair", "pair_spt2", "fused", "fused_small_tile"):
+    for variant in ("direct", "tma", "pair", "pair_spt2", "pair_store_u", "fused", "fused_small_tile"):
         s = make(w, options=KERNELS[variant])
         s.set_spins(s0)
         s.run(5)
@@ -200,6 +204,7 @@ def test_partial_tiles_and_odd_sizes(dims):
     assert np.abs(res["tma"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["pair"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["pair_spt2"] - res["direct"]).max() <= 1e-14
+    assert np.abs(res["pair_store_u"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["fused"] - res["direct"]).max() <= 1e-14
     assert np.abs(res["fused_small_tile"] - res["direct"]).max() <= 1e-14
 
@@ -221,7 +226,7 @@ def test_full_size_properties_sc_128():
     e1 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
     assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14
     assert e1 < e0
-    for variant in ("direct", "tma", "pair"):
+    for variant in ("direct", "tma", "pair", "pair_store_u"):
         d = make(w, options=KERNELS[variant])
         d.set_spins(s0)
         d.run(40)
@@ -230,7 +235,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", [2, 3, "rk4"])
+@pytest.mark.parametrize("kernel", ["2r", "2u", 3, "rk4"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -247,7 +252,8 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
         nx = dims[0] // n
         c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
         if kernel != "rk4":
-            c.set_option("kernel", kernel)   # 2: two launches per step, two halo exchanges; 3: fused step, one exchange two planes deep
+            c.set_option("kernel", 2 if kernel in ("2u", "2r") else kernel)
+            c.set_option("recover_u", 0 if kernel == "2u" else 1)   # 2: two launches per step, two halo exchanges; 3: fused step, one exchange two planes deep
         c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
         c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
         return c
@@ -448,7 +454,7 @@ def test_thermal_equilibrium_statistics_match_the_reference_arithmetic_and_the_t
 
 
 # ---- edge cases: vacancies, no exchange at all, empty step counts, sizes beyond one slab ----
-@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "fused"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_store_u", "fused"])
 def test_vacancies_stay_zero_and_do_not_act_on_their_neighbours(variant):
     """zero-length spins (vacancies) are left unchanged by unit_vector (containers/vec3.h:276-283) and add nothing to J.s"""
     w = W.c3_sc(dims=(10, 8, 12), temperature=0.0)
