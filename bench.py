@@ -236,6 +236,7 @@ def run_b200(args):
 
     peak, peak_src = hbm_peak()
     fused = bool(stage_ms[1] == 0.0)     # fused step kernel: one launch per Heun step (jb_step_fused.cu)
+    recover = False
     if fused:
         # the roofline figure is 144 B per spin-update (the two-stage data flow: s, s*, u).  The fused kernel
         # keeps s* and u on the SM and moves 48 B per update (24 B read + 24 B written), so its fraction of the 144 B
@@ -265,7 +266,8 @@ def run_b200(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("step_fused" if fused else ["stage_A", "stage_B"][dom])
+            key = "step_fused" if fused else ["stage_A", "stage_B"][dom] + ("_recover_u" if recover else "")
+            roofline["traffic"] = json.load(open(traffic_file)).get(key)
         except Exception:  # noqa: BLE001
             pass
 
