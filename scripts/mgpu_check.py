@@ -20,12 +20,15 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for name, make, periodic_x, T, steps in (("bcc NN+NNN periodic T=50", lambda: W.c2_bcc_fe(8 * world, temperature=50.0), True, 50.0, 12),
-                                             ("sc open-x wall T=0", lambda: W.c1_bloch_wall((16 * world, 8, 40)), False, 0.0, 15)):
+    # the T = 0 cases run the pair kernel's recover_u data flow (no stored Heun intermediate, corrector in place); the last case forces it at T > 0
+    for name, make, periodic_x, T, steps, opts in (("bcc NN+NNN periodic T=50", lambda: W.c2_bcc_fe(8 * world, temperature=50.0), True, 50.0, 12, None),
+                                                   ("sc open-x wall T=0", lambda: W.c1_bloch_wall((16 * world, 8, 40)), False, 0.0, 15, None),
+                                                   ("sc periodic T=0", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=0.0), True, 0.0, 15, None),
+                                                   ("sc periodic T=30 recover_u", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(recover_u=1))):
         w = make()
         lat = w["lattice"]
         comm = TorchComm(periodic_x=periodic_x, device=f"cuda:{local}")
-        s = W.make_solver(w, comm=comm, seed=77, device=local)
+        s = W.make_solver(w, comm=comm, seed=77, device=local, options=opts)
         s0 = w["spins"] if w.get("spins") is not None else lat.initial_spins(seed=5)
         per = lat.num_spins // world
         s.set_spins(s0[rank * per:(rank + 1) * per])
@@ -37,7 +40,7 @@ def main():
         comm.barrier(s.ctx)
         if rank == 0:
             got = torch.cat(parts).cpu().numpy()
-            single = W.make_solver(w, seed=77, device=local)
+            single = W.make_solver(w, seed=77, device=local, options=opts)
             single.set_spins(s0)
             single.run(steps)
             want = single.spins()
