@@ -444,35 +444,84 @@ Hamiltonian *Hamiltonian::create(const Setting &settings, const Lattice &lattice
   throw std::runtime_error("unknown hamiltonian " + module + " (not on the llg-heun-b200-gpu path)");
 }
 
+// exc_file: discover_interaction_file_format + interactions_from_file (core/interactions.cc:126-171,205-252).  Empty lines and
+// lines starting with '#' or '//' are skipped (helpers/utils.h:115-126); the first data line fixes the format: 6 columns =
+// scalar J, 14 = 3x3 tensor; first two columns material names (JAMS) or 1-based motif indices (KKR)
+static std::vector<InteractionInput> read_interaction_file(const std::string &path) {
+  std::ifstream file(path);
+  if (file.fail()) throw std::runtime_error(path + ": failed to open file");
+  auto is_comment = [](const std::string &line) {
+    std::stringstream ss(line);
+    char a = 0, b = 0;
+    ss >> a; ss >> b;
+    return (!ss) || a == '#' || (a == '/' && b == '/');
+  };
+  auto is_int = [](const std::string &t) { return t.find_first_not_of("0123456789") == std::string::npos; };
+  std::vector<std::string> lines;
+  for (std::string line; std::getline(file, line);) lines.push_back(line);
+  int ncols = 0, kkr = -1;
+  for (const std::string &line : lines) {
+    if (is_comment(line)) continue;
+    std::stringstream is(line);
+    std::vector<std::string> tok;
+    for (std::string t; is >> t;) tok.push_back(t);
+    if (tok.size() != 6 && tok.size() != 14) throw std::runtime_error("interaction file has an incorrect number of columns");
+    ncols = static_cast<int>(tok.size());
+    if (is_int(tok[0]) != is_int(tok[1])) break;
+    kkr = is_int(tok[0]) ? 1 : 0;
+    break;
+  }
+  if (kkr < 0) throw std::runtime_error("failed to discover interaction file format");
+  std::vector<InteractionInput> out;
+  int line_number = 0;
+  for (const std::string &line : lines) {
+    if (is_comment(line)) continue;
+    std::stringstream is(line);
+    InteractionInput in;
+    in.by_motif = kkr == 1;
+    if (kkr) { is >> in.motif_i >> in.motif_j; in.motif_i--; in.motif_j--; }
+    else is >> in.type_i >> in.type_j;
+    is >> in.r[0] >> in.r[1] >> in.r[2];
+    in.J9.fill(0.0);
+    if (ncols == 6) { double J = 0; is >> J; in.J9[0] = in.J9[4] = in.J9[8] = J; }
+    else for (int k = 0; k < 9; ++k) is >> in.J9[k];
+    if (is.bad() || is.fail()) throw std::runtime_error("failed to read line " + std::to_string(line_number) + " of interaction file");
+    out.push_back(in);
+  }
+  return out;
+}
+
 ExchangeHamiltonian::ExchangeHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
   const bool use_symops = s.get("symops", true);
   const double energy_cutoff = s.get("energy_cutoff", 0.0), radius_cutoff = s.get("radius_cutoff", 100.0);
   const double distance_tolerance = s.get("distance_tolerance", kLatticeTolerance), prefactor = s.get("interaction_prefactor", 1.0);
   const std::string coord = lowercase(s.get("coordinate_format", "cartesian"));
   if (coord != "cartesian" && coord != "fractional") throw std::runtime_error("Unknown coordinate format for exchange interactions");
-  if (!s.exists("interactions")) {
-    if (s.exists("exc_file")) throw std::runtime_error("exc_file is not supported by this host layer yet: inline the table as 'interactions'");
-    throw std::runtime_error("'exc_file' or 'interactions' settings are required");
-  }
-  const Setting &list = s["interactions"];
-  if (!list.is_list() || list.length() < 1) throw std::runtime_error("exchange settings must be a list");
-  // discover_interaction_setting_format (core/interactions.cc:172-203)
-  if (list[0][0].is_number() != list[0][1].is_number()) throw std::runtime_error("interaction type format is incorrect");
-  const bool kkr = list[0][0].is_number();
-  if (!list[0][2].is_array()) throw std::runtime_error("interaction vector format is incorrect");
-  const bool scalar = list[0][3].is_number();
-  if (!scalar && !(list[0][3].is_array() && list[0][3].length() == 9)) throw std::runtime_error("interaction energy format is incorrect");
   std::vector<InteractionInput> inputs;
-  for (int i = 0; i < list.length(); ++i) {   // interactions_from_settings (:254-289)
-    InteractionInput in;
-    in.by_motif = kkr;
-    if (kkr) { in.motif_i = static_cast<int>(list[i][0].as_int()) - 1; in.motif_j = static_cast<int>(list[i][1].as_int()) - 1; }
-    else { in.type_i = list[i][0].as_string(); in.type_j = list[i][1].as_string(); }
-    in.r = read_vec3(list[i][2]);
-    in.J9.fill(0.0);
-    if (scalar) { const double J = list[i][3].as_double(); in.J9[0] = in.J9[4] = in.J9[8] = J; }
-    else for (int k = 0; k < 9; ++k) in.J9[k] = list[i][3][k].as_double();
-    inputs.push_back(in);
+  if (s.exists("exc_file")) {   // kept by the reference for backwards compatibility; wins over 'interactions' (hamiltonian/exchange.cc:118-145)
+    inputs = read_interaction_file(s["exc_file"].as_string());
+  } else if (s.exists("interactions")) {
+    const Setting &list = s["interactions"];
+    if (!list.is_list() || list.length() < 1) throw std::runtime_error("exchange settings must be a list");
+    // discover_interaction_setting_format (core/interactions.cc:172-203)
+    if (list[0][0].is_number() != list[0][1].is_number()) throw std::runtime_error("interaction type format is incorrect");
+    const bool kkr = list[0][0].is_number();
+    if (!list[0][2].is_array()) throw std::runtime_error("interaction vector format is incorrect");
+    const bool scalar = list[0][3].is_number();
+    if (!scalar && !(list[0][3].is_array() && list[0][3].length() == 9)) throw std::runtime_error("interaction energy format is incorrect");
+    for (int i = 0; i < list.length(); ++i) {   // interactions_from_settings (:254-289)
+      InteractionInput in;
+      in.by_motif = kkr;
+      if (kkr) { in.motif_i = static_cast<int>(list[i][0].as_int()) - 1; in.motif_j = static_cast<int>(list[i][1].as_int()) - 1; }
+      else { in.type_i = list[i][0].as_string(); in.type_j = list[i][1].as_string(); }
+      in.r = read_vec3(list[i][2]);
+      in.J9.fill(0.0);
+      if (scalar) { const double J = list[i][3].as_double(); in.J9[0] = in.J9[4] = in.J9[8] = J; }
+      else for (int k = 0; k < 9; ++k) in.J9[k] = list[i][3][k].as_double();
+      inputs.push_back(in);
+    }
+  } else {
+    throw std::runtime_error("'exc_file' or 'interactions' settings are required");
   }
   template_ = lattice.expand_interactions(inputs, input_energy_unit_conversion_, coord == "fractional", use_symops, energy_cutoff,
                                           radius_cutoff, distance_tolerance, prefactor);
@@ -542,13 +591,52 @@ AppliedFieldHamiltonian::AppliedFieldHamiltonian(const Setting &s, const Lattice
 // =====================================================================================================
 // Physics, Monitors
 // =====================================================================================================
-Physics::Physics(const Setting *s) {   // core/physics.cc: temperature / applied_field of the `physics` group
+Physics::Physics(const Setting *s, const Setting *sim, const std::string &prefix) {   // core/physics.cc: temperature / applied_field of the `physics` group
   if (!s) return;
   const std::string module = lowercase(s->get("module", "empty"));
-  if (module != "empty" && module != "pinned_boundaries")
+  if (module != "empty" && module != "pinned_boundaries" && module != "field-cool" && module != "two-temperature-model")
     throw std::runtime_error("physics module '" + module + "' is not supported by the llg-heun-b200-gpu host layer");
   temperature_ = s->get("temperature", 0.0);
   if (const Setting *f = s->find("applied_field")) applied_field_ = read_vec3(*f);
+  output_step_freq_ = s->get("output_steps", 100);
+  if (module == "field-cool") {   // physics/field_cool.cc:9-54
+    field_cool_ = true;
+    init_temp_ = s->required("InitialTemperature").as_double();
+    final_temp_ = s->required("FinalTemperature").as_double();
+    integration_time_step_ = sim ? sim->get("t_step", 0.0) : 0.0;   // globals::config->lookup("sim.t_step"), as written in the file
+    init_field_ = read_vec3(s->required("InitialField"));
+    final_field_ = read_vec3(s->required("FinalField"));
+    cool_time_ = s->required("CoolTime").as_double();
+    for (int i = 0; i < 3; ++i) applied_field_[i] += init_field_[i];
+    if (s->exists("TSteps")) {
+      t_steps_ = s->get("TSteps", 1);
+      delta_T_ = (init_temp_ - final_temp_) / t_steps_;
+      t_plateau_ = cool_time_ / t_steps_;
+      t_eq_ = sim ? sim->get("t_eq", 0.0) : 0.0;
+      step_toggle_ = true;
+    }
+    temperature_ = init_temp_;
+  }
+  if (module == "two-temperature-model") {   // physics/two_temperature_model.cc:14-60
+    ttm_ = true;
+    phonon_temp_ = s->required("InitialTemperature").as_double();
+    electron_temp_ = sink_temp_ = phonon_temp_;
+    if (const Setting *pulses = s->find("laserPulses")) {
+      for (int i = 0; i < pulses->length(); ++i) {
+        const Setting &q = (*pulses)[i];
+        pulse_width_.push_back(q.required("width").as_double());
+        pulse_fluence_.push_back(1.152e20 * q.required("fluence").as_double());   // pumpPower (two_temperature_model.h:23)
+        pulse_start_.push_back(q.required("t_start").as_double());
+      }
+    }
+    Ce_ = s->get("Ce", Ce_); Cl_ = s->get("Cl", Cl_); G_ = s->get("Gep", G_); Gsink_ = s->get("Gps", Gsink_);
+    reversing_field_ = read_vec3(s->required("ReversingField"));
+    if (!s->exists("temperature")) temperature_ = electron_temp_;
+    if (!prefix.empty()) {
+      ttm_file_.open(prefix + "ttm.tsv");
+      ttm_file_ << std::setprecision(8) << "# t [s]\tT_el [K]\tT_ph [K]\tLaser [arb/]\n";
+    }
+  }
   if (module == "pinned_boundaries") {   // physics/pinned_boundaries.cc:12-31, pinned_boundaries.h:86-107
     const char *names[6] = {"left", "right", "front", "back", "bottom", "top"};
     for (int k = 0; k < 6; ++k) {
@@ -560,7 +648,34 @@ Physics::Physics(const Setting *s) {   // core/physics.cc: temperature / applied
   }
 }
 
-void Physics::update(B200HeunLLGSolver &solver) {   // physics/pinned_boundaries.cc:34-46
+void Physics::update(B200HeunLLGSolver &solver) {   // physics/pinned_boundaries.cc:34-46, field_cool.cc:56-78, two_temperature_model.cc:66-96
+  const double time = solver.time();
+  if (field_cool_ && time > t_eq_) {
+    if (step_toggle_) {
+      const int count = static_cast<int>((time - t_eq_) / t_plateau_);
+      if (count < t_steps_ + 1) temperature_ = init_temp_ - count * delta_T_;
+    } else if (time < cool_time_) {
+      for (int i = 0; i < 3; ++i) applied_field_[i] += ((final_field_[i] - init_field_[i]) * integration_time_step_) / cool_time_;
+      temperature_ += ((final_temp_ - init_temp_) * integration_time_step_) / cool_time_;
+    }
+  }
+  if (ttm_) {
+    const double dt = solver.time_step();
+    applied_field_ = reversing_field_;
+    double pump = 0.0;
+    for (size_t i = 0; i < pulse_fluence_.size(); ++i) {
+      const double rel = time - pulse_start_[i];
+      if (rel > 0.0 && rel <= 10 * pulse_width_[i]) {
+        const double a = (rel - 3 * pulse_width_[i]) / pulse_width_[i];
+        pump += pulse_fluence_[i] * std::exp(-a * a);
+      }
+    }
+    electron_temp_ = electron_temp_ + ((-G_ * (electron_temp_ - phonon_temp_) + pump) * dt) / (Ce_ * electron_temp_);
+    phonon_temp_ = phonon_temp_ + ((G_ * (electron_temp_ - phonon_temp_) - Gsink_ * (phonon_temp_ - sink_temp_)) * dt) / Cl_;
+    temperature_ = electron_temp_;
+    if (ttm_file_.is_open() && solver.iteration() % output_step_freq_ == 0)
+      ttm_file_ << time << "\t" << electron_temp_ << "\t" << phonon_temp_ << "\t" << pump << "\n";
+  }
   if (boundaries_.empty()) return;
   const Lattice &lat = solver.lattice();
   jb_ctx *ctx = solver.ctx();
@@ -808,7 +923,7 @@ Simulation::Simulation(const std::vector<std::string> &config_args, const std::s
       module != "llg-rk4-b200-gpu" && module != "llg-rk4-gpu")   // Solver::create (core/solver.cc:60-77)
     throw std::runtime_error("unknown solver " + solver_settings["module"].as_string() + " (this host layer provides the llg-heun and llg-rk4 paths only)");
   solver_.reset(new B200HeunLLGSolver(solver_settings, *lattice_, seed));
-  solver_->register_physics_module(new Physics(config_->find("physics")));   // Physics::create (core/physics.cc:79-126): empty, pinned_boundaries
+  solver_->register_physics_module(new Physics(config_->find("physics"), config_->find("sim"), prefix_));   // Physics::create (core/physics.cc:79-126): empty, pinned_boundaries, field-cool, two-temperature-model
   if (!config_->exists("hamiltonians")) throw std::runtime_error("No hamiltonians group in config");
   const Setting &hams = (*config_)["hamiltonians"];
   for (int i = 0; i < hams.length(); ++i) solver_->register_hamiltonian(Hamiltonian::create(hams[i], *lattice_));

@@ -187,10 +187,13 @@ class B200HeunLLGSolver;
 
 // core/physics.h:14-40 + physics/empty.h: constant temperature and applied field from `physics`;
 // module "pinned_boundaries" (physics/pinned_boundaries.{h,cc}): every iteration the spins of each edge region are rotated
-// on the device so that the region's moment points along the pinned direction (jb_region_moment / jb_rotate_region)
+// on the device so that the region's moment points along the pinned direction (jb_region_moment / jb_rotate_region);
+// modules "field-cool" (physics/field_cool.cc:9-78) and "two-temperature-model" (physics/two_temperature_model.cc:14-96):
+// temperature ramps, host arithmetic only -- the solver hands physics()->temperature() to jb_step every iteration
+// (core/solver.cc:94-97)
 class Physics {
  public:
-  explicit Physics(const Setting *settings);
+  explicit Physics(const Setting *settings, const Setting *sim = nullptr, const std::string &output_prefix = "");
   double temperature() const { return temperature_; }
   double applied_field(int i) const { return applied_field_[i]; }
   void update(B200HeunLLGSolver &solver);   // Physics::update, once per iteration before the monitors (core/jams++.cc:334)
@@ -200,6 +203,18 @@ class Physics {
   Vec3 applied_field_{{0, 0, 0}};
   std::vector<PinnedBoundary> boundaries_;
   bool regions_set_ = false;
+  // field-cool
+  bool field_cool_ = false, step_toggle_ = false;
+  double init_temp_ = 0, final_temp_ = 0, cool_time_ = 0, integration_time_step_ = 0, t_eq_ = 0, delta_T_ = 0, t_plateau_ = 0;
+  int t_steps_ = 0;
+  Vec3 init_field_{{0, 0, 0}}, final_field_{{0, 0, 0}};
+  // two-temperature model
+  bool ttm_ = false;
+  std::vector<double> pulse_width_, pulse_fluence_, pulse_start_;
+  double electron_temp_ = 0, phonon_temp_ = 0, sink_temp_ = 0, Ce_ = 7.0e2, Cl_ = 3.0e6, G_ = 17.0e17, Gsink_ = 17.0e14;
+  Vec3 reversing_field_{{0, 0, 0}};
+  int output_step_freq_ = 100;
+  std::ofstream ttm_file_;
 };
 
 class Solver;

@@ -93,6 +93,54 @@ class Material:
     spin: tuple = (0.0, 0.0, 1.0)
 
 
+def read_interaction_file(path):
+    """``exc_file`` (hamiltonian/exchange.cc:118-133): the text table of discover_interaction_file_format /
+    interactions_from_file (core/interactions.cc:126-171,205-252).  Lines that are empty or start with ``#`` / ``//`` are
+    skipped (helpers/utils.h:115-126); the first data line fixes the format for the whole file: 6 columns = scalar J,
+    14 columns = 3x3 tensor (row-major), anything else is an error; the first two columns are material names (JAMS
+    format) or 1-based motif indices (KKR format, both must be unsigned integers).  Returns the list that the
+    ``interactions`` setting would hold."""
+    def is_comment(line):
+        t = line.split()
+        return (not t) or t[0][0] == "#" or t[0][:2] == "//"
+
+    def is_int(tok):   # string_is_int (helpers/utils.h:158-160)
+        return all(ch in "0123456789" for ch in tok)
+
+    try:
+        lines = open(path).read().splitlines()
+    except OSError:
+        raise RuntimeError(f"{path}: failed to open file")
+    ncols, kkr = None, None
+    for line in lines:
+        if is_comment(line):
+            continue
+        tok = line.split()
+        if len(tok) not in (6, 14):
+            raise RuntimeError("interaction file has an incorrect number of columns")
+        ncols = len(tok)
+        if is_int(tok[0]) != is_int(tok[1]):
+            break
+        kkr = is_int(tok[0])
+        break
+    if kkr is None:
+        raise RuntimeError("failed to discover interaction file format")
+    out = []
+    for n, line in enumerate(lines):
+        if is_comment(line):
+            continue
+        tok = line.split()
+        try:
+            ti, tj = (int(tok[0]), int(tok[1])) if kkr else (tok[0], tok[1])
+            nums = [float(v) for v in tok[2:ncols]]
+            if len(nums) != ncols - 2:
+                raise ValueError
+        except (ValueError, IndexError):
+            raise RuntimeError(f"failed to read line {n} of interaction file")
+        out.append((ti, tj, nums[:3], nums[3] if ncols == 6 else nums[3:12]))
+    return out
+
+
 @dataclass
 class Lattice:
     """Materials + unit cell + supercell (reference core/lattice.h)."""

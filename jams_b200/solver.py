@@ -74,10 +74,15 @@ class ExchangeHamiltonian(Hamiltonian):
     def __init__(self, settings: dict, lattice: Lattice):
         super().__init__(settings, lattice)
         s = self.settings
-        if "interactions" not in s:
+        if "exc_file" in s:          # kept by the reference for backwards compatibility; wins over 'interactions' (exchange.cc:118-145)
+            from .lattice import read_interaction_file
+            interactions = read_interaction_file(s["exc_file"])
+        elif "interactions" in s:
+            interactions = s["interactions"]
+        else:
             raise RuntimeError("'exc_file' or 'interactions' settings are required")
         self.template = lattice.expand_interactions(
-            s["interactions"], energy_units=self.input_energy_unit_name,
+            interactions, energy_units=self.input_energy_unit_name,
             coordinate_format=s.get("coordinate_format", "cartesian"), use_symops=s.get("symops", True),
             energy_cutoff=s.get("energy_cutoff", 0.0), radius_cutoff=s.get("radius_cutoff", 100.0),
             distance_tolerance=s.get("distance_tolerance", 1e-4), interaction_prefactor=s.get("interaction_prefactor", 1.0))
@@ -333,13 +338,97 @@ class PinnedBoundariesPhysics(Physics):
             solver.ctx.rotate_region(r, rotation_matrix_between_vectors(mag, target))
 
 
-def create_physics(settings: dict | None, lattice: Lattice) -> Physics:
+class FieldCoolPhysics(Physics):
+    """``physics.module = "field-cool"`` (physics/field_cool.{h,cc}): temperature (and the reported applied field) ramp from
+    ``InitialTemperature`` / ``InitialField`` to ``FinalTemperature`` / ``FinalField`` over ``CoolTime`` -- continuously
+    (per-iteration increments, field_cool.cc:64-76) or, with ``TSteps``, in that many plateaus after ``sim.t_eq``
+    (:58-63).  The solver re-reads the temperature every step (core/solver.cc:94-97).  Restated literally, including the
+    reference's mixed units: ``time`` arrives in ps (core/solver.cc:85-87) while ``CoolTime``, ``sim.t_eq`` and
+    ``sim.t_step`` are used as written in the config file."""
+
+    def __init__(self, settings: dict, sim: dict | None = None):
+        super().__init__(settings)
+        sim = sim or {}
+        self.init_temp = float(settings["InitialTemperature"])
+        self.final_temp = float(settings["FinalTemperature"])
+        self.integration_time_step = float(sim.get("t_step", settings.get("t_step", 0.0)))   # globals::config->lookup("sim.t_step")
+        self.init_field = np.asarray(settings["InitialField"], dtype=np.float64)
+        self.final_field = np.asarray(settings["FinalField"], dtype=np.float64)
+        self.cool_time = float(settings["CoolTime"])
+        self.applied_field = self.applied_field + self.init_field        # field_cool.cc:37-39
+        self.t_eq = 0.0
+        self.step_toggle = "TSteps" in settings
+        if self.step_toggle:                                             # :41-49
+            self.n_steps = int(settings["TSteps"])
+            self.delta_t = (self.init_temp - self.final_temp) / self.n_steps
+            self.t_plateau = self.cool_time / self.n_steps
+            self.t_eq = float(sim.get("t_eq", 0.0))
+        self.temperature = self.init_temp
+
+    def update(self, solver):
+        time = solver.time
+        if not time > self.t_eq:
+            return
+        if self.step_toggle:
+            count = int((time - self.t_eq) / self.t_plateau)
+            if count < self.n_steps + 1:
+                self.temperature = self.init_temp - count * self.delta_t
+        elif time < self.cool_time:
+            self.applied_field = self.applied_field + (self.final_field - self.init_field) * self.integration_time_step / self.cool_time
+            self.temperature += (self.final_temp - self.init_temp) * self.integration_time_step / self.cool_time
+
+
+class TTMPhysics(Physics):
+    """``physics.module = "two-temperature-model"`` (physics/two_temperature_model.{h,cc}): electron and phonon temperatures
+    driven by Gaussian laser pulses, forward Euler with the solver's step (two_temperature_model.cc:66-95); the thermostat
+    follows the electron temperature.  ``records`` holds what the reference writes to ``ttm.tsv`` (:91-94)."""
+
+    def __init__(self, settings: dict, output_steps: int | None = None):
+        super().__init__(settings)
+        self.phonon_temp = float(settings["InitialTemperature"])
+        self.electron_temp = self.phonon_temp
+        self.sink_temp = self.phonon_temp
+        pulses = settings.get("laserPulses", [])
+        self.pulse_width = np.array([float(q["width"]) for q in pulses])
+        self.pulse_fluence = np.array([1.152e20 * float(q["fluence"]) for q in pulses])    # pumpPower, two_temperature_model.h:23
+        self.pulse_start = np.array([float(q["t_start"]) for q in pulses])
+        self.Ce = float(settings.get("Ce", 7.0e2))
+        self.Cl = float(settings.get("Cl", 3.0e6))
+        self.G = float(settings.get("Gep", 17.0e17))
+        self.Gsink = float(settings.get("Gps", 17.0e14))
+        self.reversing_field = np.asarray(settings["ReversingField"], dtype=np.float64)
+        self.output_steps = int(output_steps if output_steps is not None else settings.get("output_steps", 100))
+        self.pump_temp = 0.0
+        self.temperature = self.electron_temp if "temperature" not in settings else self.temperature
+        self.records = []
+
+    def update(self, solver):
+        time, dt = solver.time, solver.step_size
+        self.applied_field = self.reversing_field.copy()
+        pump = 0.0
+        for w, f, t0 in zip(self.pulse_width, self.pulse_fluence, self.pulse_start):
+            rel = time - t0
+            if 0.0 < rel <= 10 * w:
+                pump += f * np.exp(-((rel - 3 * w) / w) ** 2)
+        self.pump_temp = pump
+        self.electron_temp = self.electron_temp + ((-self.G * (self.electron_temp - self.phonon_temp) + pump) * dt) / (self.Ce * self.electron_temp)
+        self.phonon_temp = self.phonon_temp + ((self.G * (self.electron_temp - self.phonon_temp) - self.Gsink * (self.phonon_temp - self.sink_temp)) * dt) / self.Cl
+        self.temperature = self.electron_temp
+        if solver.iteration % self.output_steps == 0:
+            self.records.append((time, self.electron_temp, self.phonon_temp, pump))
+
+
+def create_physics(settings: dict | None, lattice: Lattice, sim: dict | None = None) -> Physics:
     """Physics::create (core/physics.cc:79-126), the modules on this path"""
     module = str((settings or {}).get("module", "empty")).lower()
     if module == "empty":
         return Physics(settings)
     if module == "pinned_boundaries":
         return PinnedBoundariesPhysics(settings, lattice)
+    if module == "field-cool":
+        return FieldCoolPhysics(settings, sim)
+    if module == "two-temperature-model":
+        return TTMPhysics(settings)
     raise RuntimeError("unknown physics module " + module)
 
 
@@ -365,8 +454,10 @@ class Solver:
     def set_temperature(self, T):
         self.temperature = float(T)
 
-    def update_physics_module(self):   # core/solver.cc:99-108, called before notify_monitors and run (core/jams++.cc:334)
+    def update_physics_module(self):   # core/solver.cc:85-87, called before notify_monitors and run (core/jams++.cc:334)
         self.physics.update(self)
+        if self.physics.temperature != self.temperature:   # update_thermostat re-reads it every step (core/solver.cc:94-97)
+            self.set_temperature(self.physics.temperature)
 
     def is_cuda_solver(self):
         return False

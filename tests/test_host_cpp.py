@@ -213,3 +213,99 @@ def test_checkpoint_and_restart_through_the_spin_snapshot_monitor(tmp_path):
                        name="rest", output_dir=str(tmp_path))
     assert n == 20
     assert np.array_equal(rest, full)
+
+
+@pytest.mark.gpu
+def test_cpp_simulation_with_temperature_ramp_physics_equals_python_mirror(tmp_path):
+    """physics.module = "field-cool" and "two-temperature-model" (physics/field_cool.cc, two_temperature_model.cc): the C++
+    Simulation hands physics()->temperature() to jb_step every iteration (core/solver.cc:94-97); the magnetisation monitor's T
+    column (monitors/magnetisation.cc:83) shows the ramp, and the trajectory equals the Python mirror's main loop bit for bit
+    (same Philox noise: seed and step index are the same)"""
+    from jams_b200.solver import create_solver, create_hamiltonian, create_physics
+    from jams_b200.lattice import bloch_domain_wall
+    cases = {
+        "cool": (dict(module="field-cool", InitialTemperature=40.0, FinalTemperature=10.0, InitialField=[0.0, 0.0, 0.5], FinalField=[0.0, 0.0, 0.0], CoolTime=0.003),
+                 'physics : { module = "field-cool"; InitialTemperature = 40.0; FinalTemperature = 10.0; InitialField = [0.0, 0.0, 0.5]; '
+                 'FinalField = [0.0, 0.0, 0.0]; CoolTime = 0.003; };'),
+        "ttm": (dict(module="two-temperature-model", InitialTemperature=20.0, ReversingField=[0.0, 0.0, -0.1], Ce=700.0, Cl=3.0e6, Gep=1.7e6, Gps=1.7e3,
+                     laserPulses=[dict(width=0.0005, fluence=4.0e-9, t_start=0.0002)]),
+                'physics : { module = "two-temperature-model"; InitialTemperature = 20.0; ReversingField = [0.0, 0.0, -0.1]; Ce = 700.0; Cl = 3.0e6; '
+                'Gep = 1.7e6; Gps = 1.7e3; laserPulses = ( { width = 0.0005; fluence = 4.0e-9; t_start = 0.0002; } ); };'),
+    }
+    w = W.c1_bloch_wall((32, 4, 4))
+    lat = w["lattice"]
+    init = bloch_domain_wall(lat.positions(), lat.initial_spins(), width=8.0, center=16.0)
+    for name, (py_cfg, patch) in cases.items():
+        got, done = host.run(FIXTURE, PATCH_B200, patch, 'sim : { seed = 11; t_step = 1e-4; }; monitors = ( { module = "magnetisation"; output_steps = 5; } );',
+                             name=name, output_dir=str(tmp_path))
+        assert done == 40
+        s = create_solver(dict(module="llg-heun-b200-gpu", t_step=1e-16, t_max=4e-15, seed=11), lat)
+        for h in w["hamiltonians"]:
+            s.register_hamiltonian(create_hamiltonian(h, lat))
+        s.register_physics_module(create_physics(py_cfg, lat, dict(t_step=1e-4)))   # sim.t_step as written: field_cool.cc uses it next to times in ps
+        s.set_spins(init)
+        temps = []
+        while s.is_running():
+            s.update_physics_module()
+            temps.append(s.temperature)
+            s.run(1)
+        assert len(set(temps)) > 5 and max(temps) - min(temps) > 1.0   # the temperature really moves
+        assert np.array_equal(got, s.spins()), name
+        rows = [line.split() for line in open(tmp_path / (name + "_mag.tsv")).read().splitlines()[1:]]
+        assert len(rows) == 8
+        for k, r in enumerate(rows):                                  # monitor steps 0, 5, ..., 35: T and the reported applied field
+            assert float(r[1]) == pytest.approx(temps[5 * k], rel=1e-7)
+    assert (tmp_path / "ttm_ttm.tsv").exists() and len(open(tmp_path / "ttm_ttm.tsv").read().splitlines()) >= 2
+
+
+def test_exc_file_gives_the_same_template_as_inline_interactions(tmp_path):
+    """exc_file (hamiltonian/exchange.cc:118-133; core/interactions.cc:126-171,205-252) in the C++ host and the Python mirror:
+    JAMS format (material names) with scalar J, KKR format (1-based motif indices) with a 3x3 tensor, comments and blank
+    lines, and the reference's error behaviour"""
+    from jams_b200.lattice import read_interaction_file
+    f = tmp_path / "wall.exc"
+    f.write_text("# J between nearest neighbours\n\n// (joules)\nA A 1.0 0.0 0.0 3.5e-21\n")
+    inline = host.exchange_template(FIXTURE, ham_index=1)
+    from_file = host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { exc_file = "%s"; } );' % f, ham_index=1)
+    for x, y in zip(_sorted_template(from_file), _sorted_template(inline)):
+        assert np.array_equal(x, y)
+    assert read_interaction_file(str(f)) == [("A", "A", [1.0, 0.0, 0.0], 3.5e-21)]
+    w = W.c1_bloch_wall((32, 4, 4))
+    hs = dict(w["hamiltonians"][1]); hs.pop("interactions"); hs["exc_file"] = str(f)
+    py = create_hamiltonian(hs, w["lattice"]).template
+    for x, y in zip(_sorted_template(py), _sorted_template(inline)):
+        assert np.array_equal(x, y)
+    # KKR + tensor: 14 columns
+    t9 = [1e-21, 2e-22, 0.0, -2e-22, 1e-21, 0.0, 0.0, 0.0, 1.5e-21]
+    g = tmp_path / "kkr.exc"
+    g.write_text("1 1  1.0 0.0 0.0  " + " ".join(repr(v) for v in t9) + "\n")
+    # (a config of its own: a patch cannot turn the fixture's scalar entry into an array in place)
+    text = open(FIXTURE).read()
+    line = 'interactions = (("A", "A", [ 1.0, 0.0, 0.0], 3.5e-21));'
+    assert line in text
+    extra = " symops = false; check_sparse_matrix_symmetry = false;"
+    cfg_file, cfg_inline = tmp_path / "tens_file.cfg", tmp_path / "tens_inline.cfg"
+    cfg_file.write_text(text.replace(line, 'exc_file = "%s";' % g + extra))
+    cfg_inline.write_text(text.replace(line, "interactions = ( (1, 1, [1.0, 0.0, 0.0], [%s]) );" % ", ".join(repr(v) for v in t9) + extra))
+    tens_file = host.exchange_template(str(cfg_file), ham_index=1)
+    tens_inline = host.exchange_template(str(cfg_inline), ham_index=1)
+    assert len(tens_file["mi"]) == 1 and np.array_equal(tens_file["J9"][0], np.array(t9) * 6.24150907e21)
+    for x, y in zip(_sorted_template(tens_file), _sorted_template(tens_inline)):
+        assert np.array_equal(x, y)
+    assert read_interaction_file(str(g)) == [(1, 1, [1.0, 0.0, 0.0], t9)]
+    # errors (core/interactions.cc:143,168,240; exchange.cc:122-124)
+    bad = tmp_path / "bad.exc"
+    bad.write_text("A A 1.0 0.0 0.0\n")
+    for reader in (lambda p: host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { exc_file = "%s"; } );' % p, ham_index=1), lambda p: read_interaction_file(str(p))):
+        with pytest.raises((host.HostError, RuntimeError), match="incorrect number of columns"):
+            reader(bad)
+        with pytest.raises((host.HostError, RuntimeError), match="failed to open file"):
+            reader(tmp_path / "missing.exc")
+    bad.write_text("# only comments\n\n")
+    with pytest.raises(host.HostError, match="failed to discover interaction file format"):
+        host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { exc_file = "%s"; } );' % bad, ham_index=1)
+    bad.write_text("A A 1.0 0.0 0.0 3.5e-21\nA A 0.0 1.0 zero 3.5e-21\n")
+    with pytest.raises(host.HostError, match="failed to read line"):
+        host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { exc_file = "%s"; } );' % bad, ham_index=1)
+    with pytest.raises(RuntimeError, match="failed to read line"):
+        read_interaction_file(str(bad))

@@ -188,3 +188,70 @@ def test_spin_snapshot_text_format_round_trips_exactly(tmp_path):
         load_spins_tsv(tmp_path / "a.tsv", 36)
     with pytest.raises(RuntimeError, match="failed to open file"):
         load_spins_tsv(tmp_path / "nope.tsv", 37)
+
+
+# ---- physics modules that ramp the temperature (core/solver.cc:94-97 re-reads T every step) ----
+class _Clock:
+    """what Physics::update gets from the solver: iteration, time (ps) and the step (core/solver.cc:85-87)"""
+    def __init__(self, dt):
+        self.iteration, self.time, self.step_size = 0, 0.0, dt
+
+    def tick(self):
+        self.iteration += 1
+        self.time = self.iteration * self.step_size
+
+
+def test_field_cool_physics_ramps_like_the_reference():
+    """physics/field_cool.cc:56-78: continuous mode adds (final - init) * sim.t_step / CoolTime per iteration while
+    t_eq < time < CoolTime; TSteps mode holds plateaus of CoolTime / TSteps after sim.t_eq"""
+    from jams_b200.solver import create_physics
+    clk = _Clock(1e-4)
+    p = create_physics(dict(module="field-cool", InitialTemperature=300.0, FinalTemperature=100.0, InitialField=[0.0, 0.0, 1.0],
+                            FinalField=[0.0, 0.0, 0.0], CoolTime=0.01, applied_field=[0.5, 0.0, 0.0]), None, dict(t_step=1e-4))
+    assert p.temperature == 300.0 and np.array_equal(p.applied_field, [0.5, 0.0, 1.0])
+    temps = []
+    for _ in range(150):
+        p.update(clk)          # main loop order: update_physics_module, then run (core/jams++.cc:334-341)
+        temps.append(p.temperature)
+        clk.tick()
+    want, T = [], 300.0
+    for n in range(150):
+        t = n * 1e-4
+        if t > 0.0 and t < 0.01:
+            T += (100.0 - 300.0) * 1e-4 / 0.01
+        want.append(T)
+    assert temps == want and abs(temps[-1] - 102.0) < 1e-9      # 99 increments: time = 0 is not > t_eq, time = CoolTime is not < CoolTime
+    assert abs(p.applied_field[2] - 0.01) < 1e-12 and p.applied_field[0] == 0.5
+    clk = _Clock(1e-4)
+    q = create_physics(dict(module="field-cool", InitialTemperature=300.0, FinalTemperature=100.0, InitialField=[0, 0, 0],
+                            FinalField=[0, 0, 0], CoolTime=0.01, TSteps=4), None, dict(t_step=1e-4, t_eq=0.002))
+    seen = []
+    for _ in range(200):
+        q.update(clk)
+        seen.append(q.temperature)
+        clk.tick()
+    assert seen[:21] == [300.0] * 21                           # time <= t_eq
+    assert seen[46] == 300.0 - 1 * 50.0 and seen[71] == 300.0 - 2 * 50.0 and seen[199] == 100.0
+    assert sorted(set(seen), reverse=True) == [300.0, 250.0, 200.0, 150.0, 100.0]
+
+
+def test_two_temperature_model_physics_follows_the_reference_recursion():
+    """physics/two_temperature_model.cc:66-95 (forward Euler with the solver's step; the thermostat follows T_electron)"""
+    from jams_b200.solver import create_physics
+    cfg = dict(module="two-temperature-model", InitialTemperature=300.0, ReversingField=[0.0, 0.0, -0.2], Ce=700.0, Cl=3.0e6,
+               Gep=1.7e6, Gps=1.7e3, output_steps=10, laserPulses=[dict(width=0.05, fluence=4.0e-11, t_start=0.01), dict(width=0.02, fluence=1.0e-11, t_start=0.3)])
+    p = create_physics(cfg, None)
+    clk = _Clock(1e-3)
+    Te = Tp = Ts = 300.0
+    for _ in range(800):
+        p.update(clk)
+        pump = 0.0
+        for w, f, t0 in ((0.05, 1.152e20 * 4.0e-11, 0.01), (0.02, 1.152e20 * 1.0e-11, 0.3)):
+            rel = clk.time - t0
+            if 0.0 < rel <= 10 * w:
+                pump += f * np.exp(-((rel - 3 * w) / w) ** 2)
+        Te = Te + ((-1.7e6 * (Te - Tp) + pump) * 1e-3) / (700.0 * Te)
+        Tp = Tp + ((1.7e6 * (Te - Tp) - 1.7e3 * (Tp - Ts)) * 1e-3) / 3.0e6
+        assert p.temperature == Te and p.phonon_temp == Tp
+        clk.tick()
+    assert max(r[1] for r in p.records) > 320.0 and len(p.records) == 80 and np.array_equal(p.applied_field, [0.0, 0.0, -0.2])
