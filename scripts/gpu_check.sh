@@ -1,3 +1,5 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu32.log; tail -6 gpurun_out/pytest_gpu32.log
-timeout 900 python scripts/other_configs.py > gpurun_out/other_configs32.log 2>&1; cat gpurun_out/other_configs32.log
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu52.log; tail -6 gpurun_out/pytest_gpu52.log
+timeout 900 python scripts/other_configs.py > gpurun_out/other_configs52.log 2>&1; cat gpurun_out/other_configs52.log
+export JB_QB_EXTRA='[{"recover_u":0},{"recover_u":1}]'
+timeout 600 python scripts/quick_bench.py 256 0,100 > gpurun_out/quick_bench52.log 2>&1; grep -v "^    jams" gpurun_out/quick_bench52.log
