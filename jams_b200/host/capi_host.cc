@@ -59,7 +59,10 @@ __attribute__((visibility("default"))) int jbh_exchange_template(const char *con
   try {
     auto cfg = parse_config_strings(split_args(args, n));
     Lattice lat(*cfg);
-    ExchangeHamiltonian h((*cfg)["hamiltonians"][ham_index], lat);
+    std::unique_ptr<Hamiltonian> ham(Hamiltonian::create((*cfg)["hamiltonians"][ham_index], lat));   // exchange or exchange-functional
+    ExchangeHamiltonian *hp = dynamic_cast<ExchangeHamiltonian *>(ham.get());
+    if (!hp) { g_error = "hamiltonian " + std::to_string(ham_index) + " is not an exchange hamiltonian"; return 1; }
+    ExchangeHamiltonian &h = *hp;
     const InteractionTemplate &t = h.interaction_template();
     *n_entries = t.size();
     if (t.size() > capacity) { g_error = "template capacity too small"; return 2; }

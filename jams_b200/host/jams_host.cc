@@ -6,7 +6,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <iomanip>
+#include <map>
 #include <iostream>
 #include <random>
 #include <sstream>
@@ -438,6 +440,7 @@ Hamiltonian::Hamiltonian(const Setting &settings, const Lattice &lattice) : latt
 Hamiltonian *Hamiltonian::create(const Setting &settings, const Lattice &lattice) {   // core/hamiltonian.cc:80-115
   const std::string module = lowercase(settings.required("module").as_string());
   if (module == "exchange") return new ExchangeHamiltonian(settings, lattice);
+  if (module == "exchange-functional") return new ExchangeFunctionalHamiltonian(settings, lattice);
   if (module == "uniaxial") return new UniaxialAnisotropyHamiltonian(settings, lattice);
   if (module == "zeeman") return new ZeemanHamiltonian(settings, lattice);
   if (module == "applied-field") return new AppliedFieldHamiltonian(settings, lattice);
@@ -525,6 +528,122 @@ ExchangeHamiltonian::ExchangeHamiltonian(const Setting &s, const Lattice &lattic
   }
   template_ = lattice.expand_interactions(inputs, input_energy_unit_conversion_, coord == "fractional", use_symops, energy_cutoff,
                                           radius_cutoff, distance_tolerance, prefactor);
+}
+
+// ---- exchange-functional (hamiltonian/exchange_functional.cc) -------------------------------------------------------
+double Lattice::max_interaction_radius() const {
+  Vec3 a[3];
+  for (int k = 0; k < 3; ++k) a[k] = {{cell[0][k] * dims[k], cell[1][k] * dims[k], cell[2][k] * dims[k]}};
+  auto add = [](const Vec3 &u, const Vec3 &v, double sv) { return Vec3{{u[0] + sv * v[0], u[1] + sv * v[1], u[2] + sv * v[2]}}; };
+  auto height = [](const Vec3 &u, const Vec3 &v, const Vec3 &w) { return std::abs(dot(cross(u, v), w)) / norm(cross(u, v)); };   // parallelepiped_height
+  auto pheight = [](const Vec3 &u, const Vec3 &v) { return norm(cross(u, v)) / norm(u); };                                       // parallelogram_height
+  const int np = (periodic[0] ? 1 : 0) + (periodic[1] ? 1 : 0) + (periodic[2] ? 1 : 0);
+  if (np == 3) return 0.5 * std::min({height(a[0], a[1], a[2]), height(a[2], a[0], a[1]), height(a[1], a[2], a[0])});
+  if (np == 2) {
+    const int k0 = periodic[0] ? 0 : 1, k1 = periodic[2] ? 2 : 1;
+    return 0.5 * std::min(pheight(a[k0], a[k1]), pheight(a[k1], a[k0]));
+  }
+  if (np == 1) return 0.5 * norm(a[periodic[0] ? 0 : (periodic[1] ? 1 : 2)]);
+  const Vec3 s01 = add(a[0], a[1], 1.0);
+  return std::max({norm(add(s01, a[2], 1.0)), norm(add(add(a[1], a[0], -1.0), a[2], 1.0)), norm(add(add(a[0], a[1], -1.0), a[2], 1.0)), norm(add(s01, a[2], -1.0))});
+}
+
+ExchangeFunctionalHamiltonian::ExchangeFunctionalHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  const double tol = kLatticeTolerance, E = input_energy_unit_conversion_;
+  const std::string dunit = s.get("distance_units", "lattice_constants");   // core/hamiltonian.cc:140-155
+  double D = 1.0;
+  if (dunit == "nanometers") D = 1e-9 / lattice.lattice_parameter;
+  else if (dunit == "angstroms") D = 1e-10 / lattice.lattice_parameter;
+  else if (dunit != "lattice_constants") throw std::runtime_error("distance units: " + dunit + " is not known");
+  if (!s.exists("interactions")) throw std::runtime_error("no 'interactions' setting in ExchangeFunctional hamiltonian");
+  using Fn = std::function<double(const Vec3 &)>;
+  std::map<std::pair<std::string, std::string>, std::pair<double, Fn>> functionals;
+  double rmax = 0.0;
+  const Setting &list = s["interactions"];
+  for (int n = 0; n < list.length(); ++n) {   // exchange_functional.cc:118-188
+    const Setting &e = list[n];
+    if (e.length() < 4) throw std::runtime_error("interaction requires at least 4 elements");
+    const std::string ti = e[0].as_string(), tj = e[1].as_string(), name = e[2].as_string();
+    const double rc = D * e[3].as_double();
+    for (const std::string &t : {ti, tj}) if (!lattice.material_exists(t)) throw std::runtime_error("material " + t + " does not exist in config");
+    if ((0.0 - rc) > std::abs(rc) * tol) throw std::runtime_error("cutoff radius cannot be negative");
+    if (functionals.count({ti, tj})) throw std::runtime_error("Interaction between types \"" + ti + "\" and \"" + tj + "\" is defined more than once.");
+    if (rc > lattice.max_interaction_radius())
+      throw std::runtime_error("cutoff radius " + std::to_string(rc) + " is larger than the maximum cutoff radius " + std::to_string(lattice.max_interaction_radius()));
+    rmax = std::max(rmax, rc);
+    std::vector<double> p;
+    for (int k = 4; k < e.length(); ++k) {
+      if (e[k].is_aggregate()) { for (int l = 0; l < e[k].length(); ++l) { if (!e[k][l].is_number()) throw std::runtime_error("functional parameter must be numeric"); p.push_back(e[k][l].as_double()); } }
+      else { if (!e[k].is_number()) throw std::runtime_error("functional parameter must be numeric"); p.push_back(e[k].as_double()); }
+    }
+    // validate_functional_params + functional_from_params (:13-88,358-416)
+    const std::map<std::string, int> npar = {{"rkky", 3}, {"exponential", 3}, {"gaussian", 3}, {"gaussian_multi", 9}, {"kaneyoshi", 3}, {"c3z", 14}, {"step", 2}};
+    if (!npar.count(name)) throw std::runtime_error("unknown exchange functional: " + name);
+    if (static_cast<int>(p.size()) != npar.at(name))
+      throw std::runtime_error("exchange functional '" + name + "' expects " + std::to_string(npar.at(name)) + " parameters, got " + std::to_string(p.size()));
+    auto non_zero = [&](size_t i, const char *pn) { if (std::abs(p[i]) <= tol) throw std::runtime_error("exchange functional '" + name + "' requires non-zero parameter '" + pn + "'"); };
+    auto positive = [&](size_t i, const char *pn) { if (!((p[i] - 0.0) > std::abs(p[i]) * tol)) throw std::runtime_error("exchange functional '" + name + "' requires positive parameter '" + pn + "'"); };
+    auto gauss = [](double r, double J0, double r0, double sg) { return J0 * std::exp(-(r - r0) * (r - r0) / (2 * sg * sg)); };
+    Fn fn;
+    if (name == "step") { const double J0 = E * p[0], rcut = D * p[1]; fn = [=](const Vec3 &r) { const double x = norm(r); return (x - rcut) < std::max(std::abs(x), std::abs(rcut)) * tol ? J0 : 0.0; }; }
+    else if (name == "exponential") { non_zero(2, "sigma"); const double J0 = E * p[0], r0 = D * p[1], sg = D * p[2]; fn = [=](const Vec3 &r) { return J0 * std::exp(-(norm(r) - r0) / sg); }; }
+    else if (name == "gaussian") { non_zero(2, "sigma"); const double J0 = E * p[0], r0 = D * p[1], sg = D * p[2]; fn = [=](const Vec3 &r) { return gauss(norm(r), J0, r0, sg); }; }
+    else if (name == "gaussian_multi") {
+      non_zero(2, "sigma0"); non_zero(5, "sigma1"); non_zero(8, "sigma2");
+      const std::vector<double> q = p;
+      fn = [=](const Vec3 &r) { double sum = 0; for (int k = 0; k < 3; ++k) sum += gauss(norm(r), E * q[3 * k], D * q[3 * k + 1], D * q[3 * k + 2]); return sum; };
+    }
+    else if (name == "kaneyoshi") { non_zero(2, "sigma"); const double J0 = E * p[0], r0 = D * p[1], sg = D * p[2];
+      fn = [=](const Vec3 &r) { const double x = norm(r) - r0; return J0 * x * x * std::exp(-x * x / (2 * sg * sg)); }; }
+    else if (name == "rkky") { non_zero(2, "k_F"); const double J0 = E * p[0], r0 = D * p[1], kF = p[2];
+      fn = [=](const Vec3 &r) { const double kr = 2 * kF * (norm(r) - r0);
+        if (std::abs(kr) <= tol) throw std::runtime_error("exchange functional rkky is singular for k_F*(r-r0) = 0");
+        return -J0 * (kr * std::cos(kr) - std::sin(kr)) / (kr * kr * kr * kr); }; }
+    else {   // c3z (:310-356)
+      positive(10, "l0"); positive(11, "l1s"); positive(12, "l1c");
+      const Vec3 qs1{{p[0] / D, p[1] / D, p[2] / D}}, qc1{{p[3] / D, p[4] / D, p[5] / D}};
+      const double J0 = E * p[6], J1s = E * p[7], J1c = E * p[8], d0 = D * p[9], l0 = D * p[10], l1s = D * p[11], l1c = D * p[12], rstar = D * p[13];
+      fn = [=](const Vec3 &rij) {
+        const double r = norm(rij);
+        const Vec3 rpar{{rij[0], rij[1], 0.0}};
+        double ssum = 0, csum = 0;
+        for (int k = 0; k < 3; ++k) {
+          const double t = 2 * kPi * k / 3.0, c = std::cos(t), sn = std::sin(t);
+          const Vec3 qs{{c * qs1[0] - sn * qs1[1], sn * qs1[0] + c * qs1[1], qs1[2]}}, qc{{c * qc1[0] - sn * qc1[1], sn * qc1[0] + c * qc1[1], qc1[2]}};
+          ssum += std::sin(dot(qs, rpar)); csum += std::cos(dot(qc, rpar));
+        }
+        return J0 * std::exp(-std::abs(r - d0) / l0) + J1s * std::exp(-std::abs(r - rstar) / l1s) * ssum + J1c * std::exp(-std::abs(r - rstar) / l1c) * csum;
+      };
+    }
+    functionals[{ti, tj}] = {rc, fn};
+  }
+  // the near-tree walk of :206-243 as a translation-invariant template
+  const Vec3 c0{{lattice.cell[0][0], lattice.cell[1][0], lattice.cell[2][0]}}, c1{{lattice.cell[0][1], lattice.cell[1][1], lattice.cell[2][1]}},
+             c2{{lattice.cell[0][2], lattice.cell[1][2], lattice.cell[2][2]}};
+  const Vec3 cols[3] = {c0, c1, c2};
+  const double vol = std::abs(dot(cross(c0, c1), c2));
+  int nmax[3];
+  for (int k = 0; k < 3; ++k) nmax[k] = static_cast<int>(std::ceil(rmax * (1 + tol) / (vol / norm(cross(cols[(k + 1) % 3], cols[(k + 2) % 3]))))) + 1;
+  for (int mi = 0; mi < lattice.M; ++mi) {
+    const Vec3 ri = matvec(lattice.cell, lattice.motif_frac[mi]);
+    for (int mj = 0; mj < lattice.M; ++mj) {
+      const auto it = functionals.find({lattice.materials[lattice.motif_material[mi]].name, lattice.materials[lattice.motif_material[mj]].name});
+      if (it == functionals.end()) continue;
+      const double rc = it->second.first;
+      for (int tx = -nmax[0]; tx <= nmax[0]; ++tx) for (int ty = -nmax[1]; ty <= nmax[1]; ++ty) for (int tz = -nmax[2]; tz <= nmax[2]; ++tz) {
+        if (mi == mj && tx == 0 && ty == 0 && tz == 0) continue;   // no self interaction (:213-215)
+        const Vec3 f{{lattice.motif_frac[mj][0] + tx, lattice.motif_frac[mj][1] + ty, lattice.motif_frac[mj][2] + tz}};
+        const Vec3 rj = matvec(lattice.cell, f);
+        const Vec3 rij{{rj[0] - ri[0], rj[1] - ri[1], rj[2] - ri[2]}};
+        const double r = norm(rij);
+        if (!((r - rc) < std::max(std::abs(r), std::abs(rc)) * tol)) continue;   // less_than_approx_equal (helpers/maths.h:37-40)
+        const double J = it->second.second(rij);
+        template_.mi.push_back(mi); template_.mj.push_back(mj);
+        template_.T3.push_back(tx); template_.T3.push_back(ty); template_.T3.push_back(tz);
+        for (int k = 0; k < 9; ++k) template_.J9.push_back((k % 4 == 0) ? J : 0.0);
+      }
+    }
+  }
 }
 
 UniaxialAnisotropyHamiltonian::UniaxialAnisotropyHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {

@@ -100,6 +100,7 @@ class Lattice {
   int material_index(const std::string &name) const;   // throws if unknown
   bool material_exists(const std::string &name) const;
   int site_index(int i, int j, int k, int m) const { return ((i * dims[1] + j) * dims[2] + k) * M + m; }
+  double max_interaction_radius() const;   // Lattice::max_interaction_radius (core/lattice.cc:1009-1011,1155-1200), lattice parameters
 
   // per-site arrays in reference site order (globals::mus/gyro/alpha/s/positions, core/lattice.cc:688-756)
   std::vector<double> mus() const, gyro() const, alpha() const;
@@ -150,8 +151,19 @@ class ExchangeHamiltonian : public Hamiltonian {   // hamiltonian/exchange.cc:12
   void attach(jb_ctx *ctx) override;
   const InteractionTemplate &interaction_template() const { return template_; }
   NeighbourList neighbour_list() const { return lattice_.neighbour_list(template_); }
- private:
+ protected:
+  struct NoParse {};
+  ExchangeHamiltonian(const Setting &settings, const Lattice &lattice, NoParse) : Hamiltonian(settings, lattice) {}
   InteractionTemplate template_;
+};
+
+// hamiltonian/exchange_functional.{h,cc}: isotropic J(r_ij) from a closed form inside a cutoff radius per ordered material pair
+// (step, exponential, gaussian, gaussian_multi, kaneyoshi, rkky, c3z).  The reference fills the same scalar CSR matrix as
+// `exchange` through a near-tree walk over the supercell; on a lattice without impurities that list is translation invariant,
+// so it is generated as a template for the same kernels.
+class ExchangeFunctionalHamiltonian : public ExchangeHamiltonian {
+ public:
+  ExchangeFunctionalHamiltonian(const Setting &settings, const Lattice &lattice);
 };
 
 class UniaxialAnisotropyHamiltonian : public Hamiltonian {   // hamiltonian/uniaxial_anisotropy.cc:79-172

@@ -320,6 +320,62 @@ class Lattice:
         return dict(mi=np.array(mi, np.int32), mj=np.array(mj, np.int32), T=np.array(Ts, np.int32).reshape(-1, 3),
                     J9=np.array(J9s, np.float64).reshape(-1, 9))
 
+    # -- exchange-functional: J(r_ij) within a cutoff (hamiltonian/exchange_functional.cc:94-252)
+    def max_interaction_radius(self):
+        """Lattice::max_interaction_radius / jams::maximum_interaction_length (core/lattice.cc:1009-1011,1155-1200), in lattice
+        parameters: inradius of the supercell over the periodic directions, longest body diagonal for an open system"""
+        a = [self.cell[:, k] * self.dims[k] for k in range(3)]
+        per = self.periodic
+        height = lambda u, v, w: abs(np.dot(np.cross(u, v), w)) / np.linalg.norm(np.cross(u, v))   # noqa: E731  parallelepiped_height
+        pheight = lambda u, v: np.linalg.norm(np.cross(u, v)) / np.linalg.norm(u)                   # noqa: E731  parallelogram_height
+        if all(per):
+            return 0.5 * min(height(a[0], a[1], a[2]), height(a[2], a[0], a[1]), height(a[1], a[2], a[0]))
+        if sum(per) == 2:
+            u, v = [a[k] for k in range(3) if per[k]]
+            return 0.5 * min(pheight(u, v), pheight(v, u))
+        if sum(per) == 1:
+            return 0.5 * np.linalg.norm(a[per.index(True)])
+        return max(np.linalg.norm(a[0] + a[1] + a[2]), np.linalg.norm(-a[0] + a[1] + a[2]), np.linalg.norm(a[0] - a[1] + a[2]),
+                   np.linalg.norm(a[0] + a[1] - a[2]))
+
+    def functional_template(self, functionals, tolerance=LATTICE_TOLERANCE):
+        """``functionals``: {(material i, material j): (r_cutoff, J(r_ij) -> meV)} with lengths in lattice parameters.  The
+        reference walks every site's neighbours inside the largest cutoff through a near-tree over the supercell and inserts
+        J(r_ij) for each ordered pair (i, j != i) whose material pair has a functional and whose distance is within that
+        pair's cutoff (less_than_approx_equal, relative tolerance 1e-4; exchange_functional.cc:206-243).  On a lattice
+        without impurities that list is translation invariant, so it is generated here as a template (motif i, motif j,
+        cell offset T, J) -- the form the kernels consume."""
+        if not functionals:
+            return dict(mi=np.zeros(0, np.int32), mj=np.zeros(0, np.int32), T=np.zeros((0, 3), np.int32), J9=np.zeros((0, 9)))
+        rmax = max(rc for rc, _ in functionals.values())
+        # cells that can hold a neighbour within rmax: |T_k| <= rmax / (distance between the lattice planes normal to a_k) + 1
+        vol = abs(np.linalg.det(self.cell))
+        nmax = []
+        for k in range(3):
+            u, v = self.cell[:, (k + 1) % 3], self.cell[:, (k + 2) % 3]
+            nmax.append(int(np.ceil(rmax * (1 + tolerance) / (vol / np.linalg.norm(np.cross(u, v))))) + 1)
+        names = [m.name for m in self.materials]
+        mi_l, mj_l, T_l, J_l = [], [], [], []
+        for mi in range(self.M):
+            ri = self.cell @ self.motif_frac[mi]
+            for mj in range(self.M):
+                key = (names[self.motif_material[mi]], names[self.motif_material[mj]])
+                if key not in functionals:
+                    continue
+                rc, fn = functionals[key]
+                for tx in range(-nmax[0], nmax[0] + 1):
+                    for ty in range(-nmax[1], nmax[1] + 1):
+                        for tz in range(-nmax[2], nmax[2] + 1):
+                            if mi == mj and tx == 0 and ty == 0 and tz == 0:
+                                continue   # no self interaction (exchange_functional.cc:213-215)
+                            rij = self.cell @ (self.motif_frac[mj] + np.array([tx, ty, tz], dtype=np.float64)) - ri
+                            r = float(np.linalg.norm(rij))
+                            if (r - rc) < max(abs(r), abs(rc)) * tolerance:   # less_than_approx_equal (helpers/maths.h:37-40)
+                                J = float(fn(rij))
+                                mi_l.append(mi); mj_l.append(mj); T_l.append((tx, ty, tz)); J_l.append(J * np.eye(3).reshape(9))
+        return dict(mi=np.array(mi_l, np.int32), mj=np.array(mj_l, np.int32), T=np.array(T_l, np.int32).reshape(-1, 3),
+                    J9=np.array(J_l, np.float64).reshape(-1, 9))
+
     def neighbour_list(self, template):
         """neighbour_list_from_interactions (core/interactions.cc:349-395) for a lattice without impurities.
         Returns (i, j, value_id, values9) in jams::InteractionList order (pairs sorted by {i,j}, values in

@@ -103,6 +103,112 @@ class ExchangeHamiltonian(Hamiltonian):
             ctx.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
 
 
+class ExchangeFunctionalHamiltonian(ExchangeHamiltonian):
+    """``module = "exchange-functional"`` (hamiltonian/exchange_functional.{h,cc}): isotropic exchange J(r_ij) from a closed
+    form inside a cutoff radius, one entry per ordered material pair:
+    ``interactions = ( (type_i, type_j, functional, r_cutoff, params...), ... )`` with functionals ``step`` (J0, r_cut),
+    ``exponential`` / ``gaussian`` / ``kaneyoshi`` (J0, r0, sigma), ``gaussian_multi`` (three such triples), ``rkky``
+    (J0, r0, k_F) and ``c3z`` (14 parameters); energies in ``energy_units``, lengths in ``distance_units``
+    (lattice_constants | nanometers | angstroms, core/hamiltonian.cc:140-155).  The reference fills the same scalar CSR
+    matrix as ``exchange`` (SparseInteractionHamiltonian); here the list becomes an exchange template for the same kernels."""
+    name = "exchange-functional"
+    _NPAR = {"rkky": 3, "exponential": 3, "gaussian": 3, "gaussian_multi": 9, "kaneyoshi": 3, "c3z": 14, "step": 2}
+
+    def __init__(self, settings: dict, lattice: Lattice, lattice_parameter: float | None = None):
+        Hamiltonian.__init__(self, settings, lattice)
+        s = self.settings
+        dunit = s.get("distance_units", "lattice_constants")
+        a = lattice_parameter if lattice_parameter is not None else s.get("lattice_parameter", getattr(lattice, "parameter", None))
+        conv = {"lattice_constants": 1.0}
+        if a:
+            conv.update(nanometers=1e-9 / float(a), angstroms=1e-10 / float(a))
+        if dunit not in conv:
+            raise RuntimeError(f"distance units: {dunit} is not known")
+        self.input_distance_unit_conversion = conv[dunit]
+        if "interactions" not in s:
+            raise RuntimeError("no 'interactions' setting in ExchangeFunctional hamiltonian")
+        functionals, rmax = {}, 0.0
+        for entry in s["interactions"]:
+            if len(entry) < 4:
+                raise RuntimeError("interaction requires at least 4 elements")
+            ti, tj, fname = str(entry[0]), str(entry[1]), str(entry[2])
+            rc = self.input_distance_unit_conversion * float(entry[3])
+            for t in (ti, tj):
+                if t not in lattice.material_index:
+                    raise RuntimeError(f"material {t} does not exist in config")
+            if rc < 0.0 and (0.0 - rc) > abs(rc) * 1e-4:
+                raise RuntimeError("cutoff radius cannot be negative")
+            if (ti, tj) in functionals:
+                raise RuntimeError(f'Interaction between types "{ti}" and "{tj}" is defined more than once.')
+            if rc > lattice.max_interaction_radius():
+                raise RuntimeError(f"cutoff radius {rc:f} is larger than the maximum cutoff radius {lattice.max_interaction_radius():f}")
+            params = []
+            for v in entry[4:]:
+                params.extend([float(x) for x in v] if isinstance(v, (list, tuple, np.ndarray)) else [float(v)])
+            functionals[(ti, tj)] = (rc, self._functional(fname, params))
+        self.template = lattice.functional_template(functionals)
+        self.use_pairs = bool(s.get("use_neighbour_list", False))
+        self._nbr = None
+
+    def _functional(self, name, p):
+        """validate_functional_params + functional_from_params (exchange_functional.cc:13-88,358-416)"""
+        if name not in self._NPAR:
+            raise RuntimeError("unknown exchange functional: " + name)
+        if len(p) != self._NPAR[name]:
+            raise RuntimeError(f"exchange functional '{name}' expects {self._NPAR[name]} parameters, got {len(p)}")
+        E, D, tol = self.input_energy_unit_conversion, self.input_distance_unit_conversion, 1e-4
+        nonzero = {"rkky": [(2, "k_F")], "exponential": [(2, "sigma")], "gaussian": [(2, "sigma")], "kaneyoshi": [(2, "sigma")],
+                   "gaussian_multi": [(2, "sigma0"), (5, "sigma1"), (8, "sigma2")]}.get(name, [])
+        for idx, pname in nonzero:
+            if abs(p[idx]) <= tol:
+                raise RuntimeError(f"exchange functional '{name}' requires non-zero parameter '{pname}'")
+        if name == "c3z":
+            for idx, pname in ((10, "l0"), (11, "l1s"), (12, "l1c")):
+                if not (p[idx] - 0.0) > abs(p[idx]) * tol:
+                    raise RuntimeError(f"exchange functional 'c3z' requires positive parameter '{pname}'")
+        norm = np.linalg.norm
+        gauss = lambda r, J0, r0, sg: J0 * np.exp(-(r - r0) ** 2 / (2 * sg ** 2))   # noqa: E731
+        if name == "step":
+            J0, rc = E * p[0], D * p[1]
+            return lambda rij: J0 if (norm(rij) - rc) < max(abs(norm(rij)), abs(rc)) * tol else 0.0
+        if name == "exponential":
+            J0, r0, sg = E * p[0], D * p[1], D * p[2]
+            return lambda rij: J0 * np.exp(-(norm(rij) - r0) / sg)
+        if name == "gaussian":
+            J0, r0, sg = E * p[0], D * p[1], D * p[2]
+            return lambda rij: gauss(norm(rij), J0, r0, sg)
+        if name == "gaussian_multi":
+            q = [(E * p[3 * k], D * p[3 * k + 1], D * p[3 * k + 2]) for k in range(3)]
+            return lambda rij: sum(gauss(norm(rij), *t) for t in q)
+        if name == "kaneyoshi":
+            J0, r0, sg = E * p[0], D * p[1], D * p[2]
+            return lambda rij: J0 * (norm(rij) - r0) ** 2 * np.exp(-(norm(rij) - r0) ** 2 / (2 * sg ** 2))
+        if name == "rkky":
+            J0, r0, kF = E * p[0], D * p[1], p[2]
+
+            def rkky(rij):
+                kr = 2 * kF * (norm(rij) - r0)
+                if abs(kr) <= tol:
+                    raise RuntimeError("exchange functional rkky is singular for k_F*(r-r0) = 0")
+                return -J0 * (kr * np.cos(kr) - np.sin(kr)) / kr ** 4
+            return rkky
+        # c3z (exchange_functional.cc:310-356)
+        qs1, qc1 = np.array(p[0:3]) / D, np.array(p[3:6]) / D
+        J0, J1s, J1c = E * p[6], E * p[7], E * p[8]
+        d0, l0, l1s, l1c, rstar = (D * v for v in p[9:14])
+
+        def rotz(t):
+            return np.array([[np.cos(t), -np.sin(t), 0.0], [np.sin(t), np.cos(t), 0.0], [0.0, 0.0, 1.0]])
+
+        def c3z(rij):
+            r = norm(rij)
+            rpar = np.array([rij[0], rij[1], 0.0])
+            ssum = sum(np.sin(np.dot(rotz(t) @ qs1, rpar)) for t in (0.0, 2 * np.pi / 3, 4 * np.pi / 3))
+            csum = sum(np.cos(np.dot(rotz(t) @ qc1, rpar)) for t in (0.0, 2 * np.pi / 3, 4 * np.pi / 3))
+            return J0 * np.exp(-abs(r - d0) / l0) + J1s * np.exp(-abs(r - rstar) / l1s) * ssum + J1c * np.exp(-abs(r - rstar) / l1c) * csum
+        return c3z
+
+
 class UniaxialAnisotropyHamiltonian(Hamiltonian):
     term = capi.TERM_UNIAXIAL
     name = "uniaxial"
@@ -194,7 +300,7 @@ class AppliedFieldHamiltonian(Hamiltonian):
         ctx.set_applied_field(self.field, True)
 
 
-_HAMILTONIANS = {"exchange": ExchangeHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
+_HAMILTONIANS = {"exchange": ExchangeHamiltonian, "exchange-functional": ExchangeFunctionalHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
                  "zeeman": ZeemanHamiltonian, "applied-field": AppliedFieldHamiltonian}
 
 

@@ -34,6 +34,34 @@ def oracle_exchange_pairs(lat, settings):
     return i[keep], j[keep], J9[keep], tmpl
 
 
+def brute_force_functional_pairs(lat, functionals, tol=1e-4):
+    """what ExchangeFunctionalHamiltonian's near-tree walk produces (hamiltonian/exchange_functional.cc:206-243), by brute force:
+    every ordered pair of sites (i, j != i) whose minimum-image distance is within the cutoff of its material pair.
+    ``functionals``: {(name_i, name_j): (r_cutoff, J(r_ij) in meV)}; lengths in lattice parameters.  Returns i, j, J9."""
+    pos = lat.positions()
+    names = [m.name for m in lat.materials]
+    mat = lat.site_material()
+    A = [lat.cell[:, k] * lat.dims[k] for k in range(3)]
+    shifts = [sx * A[0] * lat.periodic[0] + sy * A[1] * lat.periodic[1] + sz * A[2] * lat.periodic[2]
+              for sx in (-1, 0, 1) for sy in (-1, 0, 1) for sz in (-1, 0, 1)]
+    shifts = np.unique(np.array(shifts), axis=0)
+    I, J, V = [], [], []
+    for i in range(lat.num_spins):
+        for j in range(lat.num_spins):
+            if i == j:
+                continue
+            key = (names[mat[i]], names[mat[j]])
+            if key not in functionals:
+                continue
+            rc, fn = functionals[key]
+            for sh in shifts:
+                rij = pos[j] + sh - pos[i]
+                r = np.linalg.norm(rij)
+                if (r - rc) < max(abs(r), abs(rc)) * tol:
+                    I.append(i); J.append(j); V.append(float(fn(rij)) * np.eye(3).reshape(9))
+    return np.array(I, np.int32), np.array(J, np.int32), np.array(V).reshape(-1, 9)
+
+
 def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
     lat = workload["lattice"]
     sim = oracle.CpuSim(lat.mus(), lat.gyro(), lat.alpha(), which)
@@ -42,6 +70,9 @@ def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
         module = hs["module"].lower()
         if module == "exchange":
             i, j, J9, _ = oracle_exchange_pairs(lat, hs)
+            terms[module] = sim.add_exchange(i, j, J9)
+        elif module == "exchange-functional":
+            i, j, J9 = workload["functional_pairs"]   # brute-force list built by the test (brute_force_functional_pairs)
             terms[module] = sim.add_exchange(i, j, J9)
         elif module == "uniaxial":
             h = create_hamiltonian(hs, lat)   # parameter parsing only (no numerics)

@@ -37,7 +37,7 @@ def make(workload, options=None, pairs=False, **kw):
     over and let the library recognise the template (what the JAMS adapter does)"""
     w = dict(workload)
     if pairs:
-        w["hamiltonians"] = [dict(h, use_neighbour_list=True) if h["module"] == "exchange" else h for h in w["hamiltonians"]]
+        w["hamiltonians"] = [dict(h, use_neighbour_list=True) if h["module"] in ("exchange", "exchange-functional") else h for h in w["hamiltonians"]]
         if pairs != "auto":
             options = dict(options or {}, detect_template=0)
     return W.make_solver(w, options=options, **kw)
@@ -495,3 +495,31 @@ def test_a_lattice_too_large_for_one_slab_is_refused_not_truncated():
     with pytest.raises(capi.JamsB200Error, match="more ranks|too large|2\\^31"):
         c = capi.Context((1400, 1300, 1300))
         c.set_materials(np.ones(1), np.ones(1), np.ones(1))
+
+
+# ---- exchange-functional: another producer of the same scalar CSR matrix (hamiltonian/exchange_functional.cc) ----
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_store_u", "fused", "pairs", "pairs_auto"])
+def test_exchange_functional_fields_energy_and_trajectory_match_oracle(variant):
+    """two-material bcc lattice (periodic x and z, open y), J(r) from gaussian / exponential / rkky forms inside cutoffs: the
+    oracle integrates with the pair list of a brute-force minimum-image search, the GPU path with the template built by
+    the host layer (long range: 32 neighbours per Co site, ghost depth 1)"""
+    from test_host_logic import _functional_case
+    from helpers import brute_force_functional_pairs
+    lat, settings, fns = _functional_case()
+    w = dict(name="functional", lattice=lat, hamiltonians=[settings, dict(module="zeeman", dc_local_field=[[0.0, 0.0, 0.5], [0.0, 0.3, 0.0]])],
+             temperature=0.0, spins=None, functional_pairs=brute_force_functional_pairs(lat, fns))
+    s0 = random_unit_spins(lat.num_spins, 21)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    s = make(w, options=KERNELS.get(variant), pairs={"pairs": True, "pairs_auto": "auto"}.get(variant, False))
+    s.set_spins(s0)
+    h = s.hamiltonians[0]
+    f = h.calculate_fields(0.0)
+    want_f = sim.term_fields(sim.terms["exchange-functional"], 0.0)
+    assert np.abs(f - want_f).max() <= 1e-13 * np.abs(want_f).max()
+    e = h.calculate_total_energy(0.0)
+    want_e = sim.term_total_energy(sim.terms["exchange-functional"], 0.0)
+    assert abs(e - want_e) <= 1e-12 * abs(want_e)
+    sim.run(30)
+    s.run(30)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL

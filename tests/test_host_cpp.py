@@ -309,3 +309,38 @@ def test_exc_file_gives_the_same_template_as_inline_interactions(tmp_path):
         host.exchange_template(FIXTURE, 'hamiltonians = ( {}, { exc_file = "%s"; } );' % bad, ham_index=1)
     with pytest.raises(RuntimeError, match="failed to read line"):
         read_interaction_file(str(bad))
+
+
+def test_exchange_functional_template_cpp_equals_python(tmp_path):
+    """module = "exchange-functional" (hamiltonian/exchange_functional.cc) in the C++ host against the Python mirror (which
+    tests/test_host_logic.py checks against a brute-force pair search): same template entries, couplings to rounding"""
+    cfg = tmp_path / "functional.cfg"
+    cfg.write_text("""
+materials = ( { name = "Fe"; moment = 2.2; alpha = 0.1; spin = [0.0, 0.0, 1.0]; }, { name = "Co"; moment = 1.7; alpha = 0.05; spin = [0.0, 0.0, 1.0]; } );
+unitcell : { parameter = 0.2866e-9; basis = ([1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]); positions = (("Fe", [0.0, 0.0, 0.0]), ("Co", [0.5, 0.5, 0.5])); };
+lattice : { size = [5, 4, 6]; periodic = [true, false, true]; };
+hamiltonians = ( { module = "exchange-functional"; energy_units = "meV"; distance_units = "angstroms";
+    interactions = ( ("Fe", "Fe", "gaussian", 2.894, 12.0, 2.866, 0.86), ("Fe", "Co", "exponential", 2.58, 20.0, 2.29, 0.72),
+                     ("Co", "Fe", "exponential", 2.58, 20.0, 2.29, 0.72), ("Co", "Co", "rkky", 4.16, 3.0, 0.57, [1.3]) ); } );
+solver : { module = "llg-heun-b200-gpu"; t_step = 1e-16; t_max = 1e-15; };
+""")
+    from jams_b200.lattice import Lattice, Material
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05)], np.eye(3), [("Fe", (0, 0, 0)), ("Co", (0.5, 0.5, 0.5))], (5, 4, 6),
+                  periodic=(True, False, True))
+    a = 0.2866e-9
+    py = create_hamiltonian(dict(module="exchange-functional", energy_units="meV", distance_units="angstroms", lattice_parameter=a,
+                                 interactions=[("Fe", "Fe", "gaussian", 2.894, 12.0, 2.866, 0.86), ("Fe", "Co", "exponential", 2.58, 20.0, 2.29, 0.72),
+                                               ("Co", "Fe", "exponential", 2.58, 20.0, 2.29, 0.72), ("Co", "Co", "rkky", 4.16, 3.0, 0.57, [1.3])]), lat).template
+    cpp = host.exchange_template(str(cfg), ham_index=0)
+    a_, b_ = _sorted_template(cpp), _sorted_template(py)
+    assert len(a_[0]) == len(b_[0]) == 6 + 8 + 8 + 18
+    for k in range(3):
+        assert np.array_equal(a_[k], b_[k])
+    assert np.abs(a_[3] - b_[3]).max() <= 1e-13 * np.abs(b_[3]).max()
+    assert cpp["n_pairs"] == len(create_hamiltonian(dict(module="exchange-functional", energy_units="meV", distance_units="angstroms", lattice_parameter=a,
+                                                         interactions=[("Fe", "Fe", "gaussian", 2.894, 12.0, 2.866, 0.86), ("Fe", "Co", "exponential", 2.58, 20.0, 2.29, 0.72),
+                                                                       ("Co", "Fe", "exponential", 2.58, 20.0, 2.29, 0.72), ("Co", "Co", "rkky", 4.16, 3.0, 0.57, [1.3])]), lat).neighbour_list()[0])
+    with pytest.raises(host.HostError, match="unknown exchange functional"):
+        host.exchange_template(str(cfg), 'hamiltonians = ( { interactions = ( ("Fe", "Fe", "sinc", 2.894, 12.0, 2.866, 0.86) ); } );', ham_index=0)
+    with pytest.raises(host.HostError, match="larger than the maximum cutoff radius"):
+        host.exchange_template(str(cfg), 'hamiltonians = ( { interactions = ( ("Fe", "Fe", "gaussian", 28.0, 12.0, 2.866, 0.86) ); } );', ham_index=0)

@@ -255,3 +255,48 @@ def test_two_temperature_model_physics_follows_the_reference_recursion():
         assert p.temperature == Te and p.phonon_temp == Tp
         clk.tick()
     assert max(r[1] for r in p.records) > 320.0 and len(p.records) == 80 and np.array_equal(p.applied_field, [0.0, 0.0, -0.2])
+
+
+# ---- exchange-functional (another producer of the same scalar CSR matrix) ----
+def _functional_case():
+    from jams_b200.lattice import Lattice, Material
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05)], np.eye(3), [("Fe", (0, 0, 0)), ("Co", (0.5, 0.5, 0.5))], (5, 4, 6),
+                  periodic=(True, False, True))
+    settings = dict(module="exchange-functional", energy_units="meV",
+                    interactions=[("Fe", "Fe", "gaussian", 1.01, 12.0, 1.0, 0.3), ("Fe", "Co", "exponential", 0.9, 20.0, 0.8, 0.25),
+                                  ("Co", "Fe", "exponential", 0.9, 20.0, 0.8, 0.25), ("Co", "Co", "rkky", 1.45, 3.0, 0.2, [1.3])])
+    fns = {("Fe", "Fe"): (1.01, lambda r: 12.0 * np.exp(-(np.linalg.norm(r) - 1.0) ** 2 / (2 * 0.3 ** 2))),
+           ("Fe", "Co"): (0.9, lambda r: 20.0 * np.exp(-(np.linalg.norm(r) - 0.8) / 0.25)),
+           ("Co", "Fe"): (0.9, lambda r: 20.0 * np.exp(-(np.linalg.norm(r) - 0.8) / 0.25)),
+           ("Co", "Co"): (1.45, lambda r: -3.0 * ((2 * 1.3 * (np.linalg.norm(r) - 0.2)) * np.cos(2 * 1.3 * (np.linalg.norm(r) - 0.2)) - np.sin(2 * 1.3 * (np.linalg.norm(r) - 0.2)))
+                                 / (2 * 1.3 * (np.linalg.norm(r) - 0.2)) ** 4)}
+    return lat, settings, fns
+
+
+def test_exchange_functional_template_equals_a_brute_force_pair_search():
+    """hamiltonian/exchange_functional.cc:206-243: every ordered pair within its material pair's cutoff gets J(r_ij); the
+    template route (what the kernels consume) must give the same list as a brute-force minimum-image search over all pairs"""
+    from helpers import brute_force_functional_pairs
+    from jams_b200.solver import create_hamiltonian
+    lat, settings, fns = _functional_case()
+    h = create_hamiltonian(settings, lat)
+    i, j, v, vals = h.neighbour_list()
+    bi, bj, bJ = brute_force_functional_pairs(lat, fns)
+    got = {(int(a), int(b)): vals[c][0] for a, b, c in zip(i, j, v)}
+    want = {(int(a), int(b)): J9[0] for a, b, J9 in zip(bi, bj, bJ)}
+    assert len(i) == len(bi) == len(got) and set(got) == set(want)
+    assert max(abs(got[k] - want[k]) for k in got) <= 1e-13 * max(abs(x) for x in want.values())
+    # Fe-Fe: 6 neighbours at 1.0 (4 across the open y faces for boundary cells), Fe-Co: 8 at 0.866, Co-Co: 6 + 12 (1.0, 1.414)
+    counts = np.bincount(i, minlength=lat.num_spins)
+    inner = lat.site_index(2, 1, 3, 0), lat.site_index(2, 1, 3, 1)
+    assert counts[inner[0]] == 6 + 8 and counts[inner[1]] == 8 + 6 + 12
+    # reference error behaviour (exchange_functional.cc:13-88,118-160)
+    for bad, msg in ((dict(settings, interactions=[("Fe", "Fe", "gaussian", 1.0, 1.0, 1.0)]), "expects 3 parameters"),
+                     (dict(settings, interactions=[("Fe", "Fe", "sinc", 1.0, 1.0)]), "unknown exchange functional"),
+                     (dict(settings, interactions=[("Fe", "Fe", "gaussian", 1.0, 1.0, 1.0, 0.0)]), "non-zero parameter 'sigma'"),
+                     (dict(settings, interactions=[("Fe", "Ni", "step", 1.0, 1.0, 1.0)]), "does not exist"),
+                     (dict(settings, interactions=[("Fe", "Fe", "step", 1.0, 1.0, 1.0), ("Fe", "Fe", "step", 1.0, 1.0, 1.0)]), "defined more than once"),
+                     (dict(settings, interactions=[("Fe", "Fe", "step", 9.0, 1.0, 9.0)]), "larger than the maximum cutoff radius"),
+                     (dict(settings, distance_units="furlongs"), "distance units")):
+        with pytest.raises(RuntimeError, match=msg):
+            create_hamiltonian(bad, lat)
