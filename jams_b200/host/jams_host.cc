@@ -441,6 +441,7 @@ Hamiltonian *Hamiltonian::create(const Setting &settings, const Lattice &lattice
   const std::string module = lowercase(settings.required("module").as_string());
   if (module == "exchange") return new ExchangeHamiltonian(settings, lattice);
   if (module == "exchange-functional") return new ExchangeFunctionalHamiltonian(settings, lattice);
+  if (module == "exchange-neartree") return new ExchangeNeartreeHamiltonian(settings, lattice);
   if (module == "uniaxial") return new UniaxialAnisotropyHamiltonian(settings, lattice);
   if (module == "zeeman") return new ZeemanHamiltonian(settings, lattice);
   if (module == "applied-field") return new AppliedFieldHamiltonian(settings, lattice);
@@ -643,6 +644,70 @@ ExchangeFunctionalHamiltonian::ExchangeFunctionalHamiltonian(const Setting &s, c
         for (int k = 0; k < 9; ++k) template_.J9.push_back((k % 4 == 0) ? J : 0.0);
       }
     }
+  }
+}
+
+// ---- exchange-neartree (hamiltonian/exchange_neartree.cc:14-156) ----------------------------------------------------
+ExchangeNeartreeHamiltonian::ExchangeNeartreeHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  const double E = input_energy_unit_conversion_;
+  const std::string dunit = s.get("distance_units", "lattice_constants");
+  double D = 1.0;
+  if (dunit == "nanometers") D = 1e-9 / lattice.lattice_parameter;
+  else if (dunit == "angstroms") D = 1e-10 / lattice.lattice_parameter;
+  else if (dunit != "lattice_constants") throw std::runtime_error("distance units: " + dunit + " is not known");
+  const double energy_cutoff = s.get("energy_cutoff", 1e-26) * E, shell_width = s.get("shell_width", 1e-3) * D;
+  for (int i = 0; i < lattice.M; ++i) for (int j = i + 1; j < lattice.M; ++j) {   // :43-56
+    const Vec3 d{{lattice.motif_frac[i][0] - lattice.motif_frac[j][0], lattice.motif_frac[i][1] - lattice.motif_frac[j][1], lattice.motif_frac[i][2] - lattice.motif_frac[j][2]}};
+    if (norm(d) < shell_width)
+      throw std::runtime_error("Atoms " + std::to_string(i) + " and " + std::to_string(j) + " in the unit cell are close together than the shell_width");
+  }
+  if (!s.exists("interactions")) throw std::runtime_error("no 'interactions' setting in ExchangeNeartree hamiltonian");
+  struct Shell { int A, B; double radius, J; };
+  std::vector<Shell> shells;
+  double max_radius = 0.0;
+  const Setting &list = s["interactions"];
+  for (int n = 0; n < list.length(); ++n) {   // :64-89
+    const std::string ta = list[n][0].as_string(), tb = list[n][1].as_string();
+    for (const std::string &t : {ta, tb})
+      if (!lattice.material_exists(t)) throw std::runtime_error("exchange neartree interaction " + std::to_string(n) + ": material " + t + " does not exist in the config");
+    const double radius = list[n][2].as_double() * D, J = list[n][3].as_double() * E;
+    max_radius = std::max(max_radius, radius);
+    const int A = lattice.material_index(ta), B = lattice.material_index(tb);
+    shells.push_back({A, B, radius, J});
+    if (A != B) shells.push_back({B, A, radius, J});
+  }
+  if (shells.empty()) return;
+  // InteractionNearTree::shell -> NearTree::in_annulus (containers/neartree.h:359-376) with epsilon = shell_width / 10, as a template
+  const double eps = shell_width / 10.0;
+  auto gt = [&](double a, double b) { return (a - b) > std::max(std::abs(a), std::abs(b)) * eps; };   // definately_greater_than
+  const Vec3 c0{{lattice.cell[0][0], lattice.cell[1][0], lattice.cell[2][0]}}, c1{{lattice.cell[0][1], lattice.cell[1][1], lattice.cell[2][1]}},
+             c2{{lattice.cell[0][2], lattice.cell[1][2], lattice.cell[2][2]}};
+  const Vec3 cols[3] = {c0, c1, c2};
+  const double vol = std::abs(dot(cross(c0, c1), c2)), rmax = (max_radius + shell_width) * (1 + eps);
+  int nmax[3];
+  for (int k = 0; k < 3; ++k) nmax[k] = static_cast<int>(std::ceil(rmax / (vol / norm(cross(cols[(k + 1) % 3], cols[(k + 2) % 3]))))) + 1;
+  for (int mi = 0; mi < lattice.M; ++mi) {
+    const Vec3 ri = matvec(lattice.cell, lattice.motif_frac[mi]);
+    for (int mj = 0; mj < lattice.M; ++mj)
+      for (int tx = -nmax[0]; tx <= nmax[0]; ++tx) for (int ty = -nmax[1]; ty <= nmax[1]; ++ty) for (int tz = -nmax[2]; tz <= nmax[2]; ++tz) {
+        if (mi == mj && tx == 0 && ty == 0 && tz == 0) continue;   // :119-121
+        const Vec3 f{{lattice.motif_frac[mj][0] + tx, lattice.motif_frac[mj][1] + ty, lattice.motif_frac[mj][2] + tz}};
+        const Vec3 rj = matvec(lattice.cell, f);
+        const double r = norm(Vec3{{rj[0] - ri[0], rj[1] - ri[1], rj[2] - ri[2]}});
+        bool seen = false;
+        for (const Shell &sh : shells) {
+          if (lattice.motif_material[mi] != sh.A || lattice.motif_material[mj] != sh.B) continue;
+          const double inner = sh.radius - 0.5 * shell_width, outer = sh.radius + 0.5 * shell_width;
+          if (gt(r, outer) || !gt(r, inner)) continue;
+          if (seen) throw std::runtime_error("multiple interactions between spins of motif positions " + std::to_string(mi) + " and " + std::to_string(mj));
+          seen = true;
+          if (std::abs(sh.J) > energy_cutoff) {
+            template_.mi.push_back(mi); template_.mj.push_back(mj);
+            template_.T3.push_back(tx); template_.T3.push_back(ty); template_.T3.push_back(tz);
+            for (int k = 0; k < 9; ++k) template_.J9.push_back((k % 4 == 0) ? sh.J : 0.0);
+          }
+        }
+      }
   }
 }
 

@@ -166,6 +166,13 @@ class ExchangeFunctionalHamiltonian : public ExchangeHamiltonian {
   ExchangeFunctionalHamiltonian(const Setting &settings, const Lattice &lattice);
 };
 
+// hamiltonian/exchange_neartree.{h,cc}: isotropic exchange by distance shells, interactions = ((A, B, radius, J), ...): every A site
+// couples with J to the B sites at distance radius -+ shell_width / 2 (mirrored entry for A != B), |J| <= energy_cutoff dropped
+class ExchangeNeartreeHamiltonian : public ExchangeHamiltonian {
+ public:
+  ExchangeNeartreeHamiltonian(const Setting &settings, const Lattice &lattice);
+};
+
 class UniaxialAnisotropyHamiltonian : public Hamiltonian {   // hamiltonian/uniaxial_anisotropy.cc:79-172
  public:
   UniaxialAnisotropyHamiltonian(const Setting &settings, const Lattice &lattice);

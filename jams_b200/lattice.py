@@ -348,31 +348,60 @@ class Lattice:
         if not functionals:
             return dict(mi=np.zeros(0, np.int32), mj=np.zeros(0, np.int32), T=np.zeros((0, 3), np.int32), J9=np.zeros((0, 9)))
         rmax = max(rc for rc, _ in functionals.values())
-        # cells that can hold a neighbour within rmax: |T_k| <= rmax / (distance between the lattice planes normal to a_k) + 1
+        names = [m.name for m in self.materials]
+        mi_l, mj_l, T_l, J_l = [], [], [], []
+        for mi, mj, T, rij, r in self.motif_pairs_within(rmax * (1 + tolerance)):
+            key = (names[self.motif_material[mi]], names[self.motif_material[mj]])
+            if key not in functionals:
+                continue
+            rc, fn = functionals[key]
+            if (r - rc) < max(abs(r), abs(rc)) * tolerance:   # less_than_approx_equal (helpers/maths.h:37-40)
+                mi_l.append(mi); mj_l.append(mj); T_l.append(T); J_l.append(float(fn(rij)) * np.eye(3).reshape(9))
+        return dict(mi=np.array(mi_l, np.int32), mj=np.array(mj_l, np.int32), T=np.array(T_l, np.int32).reshape(-1, 3),
+                    J9=np.array(J_l, np.float64).reshape(-1, 9))
+
+    def motif_pairs_within(self, radius):
+        """every (motif i, motif j, cell offset T != self) with |r_ij| possibly <= radius: yields (mi, mj, T, r_ij, |r_ij|), lengths
+        in lattice parameters.  |T_k| <= radius / (spacing of the lattice planes normal to a_k) + 1 covers the sphere."""
         vol = abs(np.linalg.det(self.cell))
         nmax = []
         for k in range(3):
             u, v = self.cell[:, (k + 1) % 3], self.cell[:, (k + 2) % 3]
-            nmax.append(int(np.ceil(rmax * (1 + tolerance) / (vol / np.linalg.norm(np.cross(u, v))))) + 1)
-        names = [m.name for m in self.materials]
-        mi_l, mj_l, T_l, J_l = [], [], [], []
+            nmax.append(int(np.ceil(radius / (vol / np.linalg.norm(np.cross(u, v))))) + 1)
         for mi in range(self.M):
             ri = self.cell @ self.motif_frac[mi]
             for mj in range(self.M):
-                key = (names[self.motif_material[mi]], names[self.motif_material[mj]])
-                if key not in functionals:
-                    continue
-                rc, fn = functionals[key]
                 for tx in range(-nmax[0], nmax[0] + 1):
                     for ty in range(-nmax[1], nmax[1] + 1):
                         for tz in range(-nmax[2], nmax[2] + 1):
                             if mi == mj and tx == 0 and ty == 0 and tz == 0:
-                                continue   # no self interaction (exchange_functional.cc:213-215)
+                                continue   # no self interaction (exchange_functional.cc:213-215, exchange_neartree.cc:119-121)
                             rij = self.cell @ (self.motif_frac[mj] + np.array([tx, ty, tz], dtype=np.float64)) - ri
-                            r = float(np.linalg.norm(rij))
-                            if (r - rc) < max(abs(r), abs(rc)) * tolerance:   # less_than_approx_equal (helpers/maths.h:37-40)
-                                J = float(fn(rij))
-                                mi_l.append(mi); mj_l.append(mj); T_l.append((tx, ty, tz)); J_l.append(J * np.eye(3).reshape(9))
+                            yield mi, mj, (tx, ty, tz), rij, float(np.linalg.norm(rij))
+
+    def shell_template(self, shells, shell_width, energy_cutoff):
+        """exchange-neartree (hamiltonian/exchange_neartree.cc:100-128): ``shells`` = [(material id A, material id B, radius, J meV)]
+        (already mirrored for A != B).  A site of material A couples with J to every site of material B whose distance lies in
+        the annulus radius -+ shell_width / 2 (InteractionNearTree::shell -> NearTree::in_annulus, containers/neartree.h:359-376,
+        relative tolerance shell_width / 10); a pair reached twice is an error; |J| <= energy_cutoff is dropped."""
+        if not shells:
+            return dict(mi=np.zeros(0, np.int32), mj=np.zeros(0, np.int32), T=np.zeros((0, 3), np.int32), J9=np.zeros((0, 9)))
+        eps = shell_width / 10.0
+        gt = lambda a, b: (a - b) > max(abs(a), abs(b)) * eps   # noqa: E731  definately_greater_than
+        rmax = max(sh[2] for sh in shells) + shell_width
+        seen, mi_l, mj_l, T_l, J_l = set(), [], [], [], []
+        for mi, mj, T, rij, r in self.motif_pairs_within(rmax * (1 + eps)):
+            for A, B, radius, J in shells:
+                if self.motif_material[mi] != A or self.motif_material[mj] != B:
+                    continue
+                inner, outer = radius - 0.5 * shell_width, radius + 0.5 * shell_width
+                if gt(r, outer) or not gt(r, inner):
+                    continue
+                if (mi, mj, T) in seen:
+                    raise RuntimeError(f"multiple interactions between spins of motif positions {mi} and {mj}")
+                seen.add((mi, mj, T))
+                if abs(J) > energy_cutoff:
+                    mi_l.append(mi); mj_l.append(mj); T_l.append(T); J_l.append(J * np.eye(3).reshape(9))
         return dict(mi=np.array(mi_l, np.int32), mj=np.array(mj_l, np.int32), T=np.array(T_l, np.int32).reshape(-1, 3),
                     J9=np.array(J_l, np.float64).reshape(-1, 9))
 

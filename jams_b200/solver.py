@@ -209,6 +209,48 @@ class ExchangeFunctionalHamiltonian(ExchangeHamiltonian):
         return c3z
 
 
+class ExchangeNeartreeHamiltonian(ExchangeHamiltonian):
+    """``module = "exchange-neartree"`` (hamiltonian/exchange_neartree.{h,cc}): isotropic exchange by distance shells,
+    ``interactions = ( (material A, material B, radius, J), ... )``: every A site couples with J to the B sites at distance
+    radius -+ ``shell_width`` / 2 (default 1e-3), and the mirrored entry is added for A != B (:78-88); couplings with
+    |J| <= ``energy_cutoff`` (default 1e-26 in the input units) are dropped (:123-126).  Same scalar CSR matrix as ``exchange``
+    in the reference; here a template for the same kernels."""
+    name = "exchange-neartree"
+
+    def __init__(self, settings: dict, lattice: Lattice, lattice_parameter: float | None = None):
+        Hamiltonian.__init__(self, settings, lattice)
+        s = self.settings
+        dunit = s.get("distance_units", "lattice_constants")
+        a = lattice_parameter if lattice_parameter is not None else s.get("lattice_parameter", getattr(lattice, "parameter", None))
+        conv = {"lattice_constants": 1.0}
+        if a:
+            conv.update(nanometers=1e-9 / float(a), angstroms=1e-10 / float(a))
+        if dunit not in conv:
+            raise RuntimeError(f"distance units: {dunit} is not known")
+        D, E = conv[dunit], self.input_energy_unit_conversion
+        energy_cutoff = float(s.get("energy_cutoff", 1e-26)) * E
+        shell_width = float(s.get("shell_width", 1e-3)) * D
+        for i in range(lattice.M):             # exchange_neartree.cc:43-56
+            for j in range(i + 1, lattice.M):
+                d = float(np.linalg.norm(lattice.motif_frac[i] - lattice.motif_frac[j]))
+                if d < shell_width:
+                    raise RuntimeError(f"Atoms {i} and {j} in the unit cell are close together ({d}) than the shell_width ({shell_width}).")
+        if "interactions" not in s:
+            raise RuntimeError("no 'interactions' setting in ExchangeNeartree hamiltonian")
+        shells = []
+        for n, (ta, tb, radius, J) in enumerate(s["interactions"]):
+            for t in (ta, tb):
+                if t not in lattice.material_index:
+                    raise RuntimeError(f"exchange neartree interaction {n}: material {t} does not exist in the config")
+            A, B = lattice.material_index[ta], lattice.material_index[tb]
+            shells.append((A, B, float(radius) * D, float(J) * E))
+            if A != B:
+                shells.append((B, A, float(radius) * D, float(J) * E))
+        self.template = lattice.shell_template(shells, shell_width, energy_cutoff)
+        self.use_pairs = bool(s.get("use_neighbour_list", False))
+        self._nbr = None
+
+
 class UniaxialAnisotropyHamiltonian(Hamiltonian):
     term = capi.TERM_UNIAXIAL
     name = "uniaxial"
@@ -300,7 +342,8 @@ class AppliedFieldHamiltonian(Hamiltonian):
         ctx.set_applied_field(self.field, True)
 
 
-_HAMILTONIANS = {"exchange": ExchangeHamiltonian, "exchange-functional": ExchangeFunctionalHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
+_HAMILTONIANS = {"exchange": ExchangeHamiltonian, "exchange-functional": ExchangeFunctionalHamiltonian,
+                 "exchange-neartree": ExchangeNeartreeHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
                  "zeeman": ZeemanHamiltonian, "applied-field": AppliedFieldHamiltonian}
 
 
