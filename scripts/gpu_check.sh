@@ -1,6 +1,7 @@
 set -x
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu52.log; tail -6 gpurun_out/pytest_gpu52.log
-timeout 900 python scripts/other_configs.py > gpurun_out/other_configs52.log 2>&1; cat gpurun_out/other_configs52.log
-export JB_QB_EXTRA='[{"recover_u":0},{"recover_u":1}]'
-timeout 600 python scripts/quick_bench.py 256 0,100 > gpurun_out/quick_bench52.log 2>&1; grep -v "^    jams" gpurun_out/quick_bench52.log
-timeout 600 python bench.py --strong --steps 50 --warmup 3 --no-cpu > gpurun_out/bench_strong_1gpu.json 2> gpurun_out/bench_strong_1gpu.err; cut -c1-900 gpurun_out/bench_strong_1gpu.json; tail -2 gpurun_out/bench_strong_1gpu.err
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/pytest_gpu53.log; tail -6 gpurun_out/pytest_gpu53.log
+timeout 600 python bench.py --strong --steps 50 --warmup 3 --no-cpu --temperature 0 > gpurun_out/bench_strong_1gpu_T0.json 2> gpurun_out/bench_strong_1gpu_T0.err; cut -c1-400 gpurun_out/bench_strong_1gpu_T0.json; tail -2 gpurun_out/bench_strong_1gpu_T0.err
+python -c "
+import json
+for f in ('bench_strong_1gpu_T0.json',):
+    d=json.load(open('gpurun_out/'+f)); print(f, d['value'], d['ms_per_step'], d['roofline']['stage_ms'], d['roofline']['step_frac'])"
