@@ -131,6 +131,16 @@ JB_API int jb_set_zeeman(jb_ctx *ctx, const double *dc_local_field, const double
 /* AppliedFieldHamiltonian: homogeneous B(t) in Tesla; the field on site i is mu_i * B
  * (hamiltonian/applied_field.cc:146-148).  Call again whenever B(t) changes. enable = 0 removes it. */
 JB_API int jb_set_applied_field(jb_ctx *ctx, const double B[3], int32_t enable);
+/* The same Hamiltonian with a time-dependent amplitude, B(t) = B g(t) (TimeDependentField subclasses,
+ * hamiltonian/applied_field.cc:10-82): JB_FIELD_STATIC g = 1; JB_FIELD_SINC g = sinc(pi f_bw (t - t0));
+ * JB_FIELD_SINC_COS g = sinc(pi f_bw (t - t0)) cos(2 pi f_c (t - t0)); t0 in ps, f_bw and f_c in THz (the reference converts
+ * its config values the same way, :37-38,66-68).  The stage kernels see g at the stage's time (predictor t, corrector t + dt,
+ * cpu_llg_heun.cc:46,103-104), jb_fields / jb_energies at the time they are given. */
+#define JB_FIELD_STATIC 0
+#define JB_FIELD_SINC 1
+#define JB_FIELD_SINC_COS 2
+JB_API int jb_set_applied_field_pulse(jb_ctx *ctx, const double B[3], int32_t type, double time_center_ps,
+                                      double freq_bandwidth_THz, double freq_center_THz);
 
 /* ---- state --------------------------------------------------------------------------------- */
 /* globals::s <-> device SoA.  s_aos is N(local) x 3 row-major (core/lattice.cc:688). */

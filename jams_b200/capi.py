@@ -45,6 +45,7 @@ SIGNATURES = {
     "jb_set_uniaxial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "jb_set_zeeman": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_set_applied_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "jb_set_applied_field_pulse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double]),
     "jb_import_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_export_spins": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
@@ -190,6 +191,14 @@ class Context:
     def set_applied_field(self, B, enable=True):
         B = _f64(B if B is not None else [0, 0, 0])
         self._ck(self.lib.jb_set_applied_field(self.h, _ptr(B), int(enable)))
+
+    FIELD_TYPES = {"static": 0, "sinc": 1, "sinc-cos": 2}
+
+    def set_applied_field_pulse(self, B, kind, time_center_ps=0.0, freq_bandwidth_THz=0.0, freq_center_THz=0.0):
+        """B(t) = B g(t): static, sinc or sinc-cos amplitude (hamiltonian/applied_field.cc:10-82)"""
+        B = _f64(B)
+        self._ck(self.lib.jb_set_applied_field_pulse(self.h, _ptr(B), self.FIELD_TYPES[kind], float(time_center_ps),
+                                                     float(freq_bandwidth_THz), float(freq_center_THz)))
 
     def set_option(self, key, value):
         self._ck(self.lib.jb_set_option(self.h, key.encode(), int(value)))

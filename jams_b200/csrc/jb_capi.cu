@@ -254,6 +254,19 @@ int build_classes(jb_ctx *c) {
   return JB_OK;
 }
 
+// does the constant field of a stage depend on the stage's time? (Zeeman ac term, applied-field pulse)
+static bool time_dependent(const jb_ctx *c) { return c->has_ac || (c->has_applied && c->applied_type != JB_FIELD_STATIC); }
+
+// g(t) of the applied field (hamiltonian/applied_field.cc:18-19,41-43,70-73; sinc: helpers/maths.h:441-446)
+static double applied_amplitude(const jb_ctx *c, double t) {
+  if (c->applied_type == JB_FIELD_STATIC) return 1.0;
+  const double kPi = 3.14159265358979323846;
+  const double x = kPi * c->applied_fbw * (t - c->applied_t0);
+  const double sinc = x == 0.0 ? 1.0 : sin(x) / x;
+  if (c->applied_type == JB_FIELD_SINC) return sinc;
+  return sinc * cos(2.0 * kPi * c->applied_fc * (t - c->applied_t0));
+}
+
 // fill sigma and the constant field of `count` consecutive stage tables and upload them.
 //   which_f: JB_TERM_TOTAL (zeeman + applied), JB_TERM_ZEEMAN, JB_TERM_APPLIED, or -1 (none)
 int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, double T, int gilbert, int which_f) {
@@ -261,7 +274,7 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
   const size_t count = times.size();
   // skip the upload (and its host/device synchronisation) when the table on the device is current
   std::vector<double> sig = {dt, T, (double)gilbert, (double)which_f, c->applied_B[0], c->applied_B[1], c->applied_B[2],
-                             c->has_applied ? 1.0 : 0.0, (double)nc};
+                             c->has_applied ? 1.0 : 0.0, (double)nc, (double)c->applied_type, c->applied_t0, c->applied_fbw, c->applied_fc};
   sig.insert(sig.end(), times.begin(), times.end());
   if (c->d_classes && sig == c->class_sig) return JB_OK;
   std::vector<JbClass> tab(nc * count);
@@ -285,7 +298,8 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
         }
       }
       if ((which_f == JB_TERM_TOTAL || which_f == JB_TERM_APPLIED) && c->has_applied) {
-        for (int d = 0; d < 3; ++d) f[d] += cl.mu * c->applied_B[d];  // applied_field.cc:146-148
+        const double amp = applied_amplitude(c, times[s]);
+        for (int d = 0; d < 3; ++d) f[d] += cl.mu * (c->applied_B[d] * amp);  // applied_field.cc:146-148
       }
       cl.fx = f[0]; cl.fy = f[1]; cl.fz = f[2];
       cl.fTx = f[0] * cl.inv_mu; cl.fTy = f[1] * cl.inv_mu; cl.fTz = f[2] * cl.inv_mu;
@@ -939,7 +953,17 @@ int jb_set_zeeman(jb_ctx *c, const double *dc, const double *ac, const double *o
 int jb_set_applied_field(jb_ctx *c, const double B[3], int32_t enable) {
   if (!c || (enable && !B)) return JB_ERR_INVALID;
   c->has_applied = enable != 0;
+  c->applied_type = JB_FIELD_STATIC;
   for (int d = 0; d < 3; ++d) c->applied_B[d] = enable ? B[d] : 0.0;
+  return JB_OK;
+}
+
+int jb_set_applied_field_pulse(jb_ctx *c, const double B[3], int32_t type, double t0, double fbw, double fc) {
+  if (!c || !B) return JB_ERR_INVALID;
+  if (type != JB_FIELD_STATIC && type != JB_FIELD_SINC && type != JB_FIELD_SINC_COS) JB_FAIL(c, JB_ERR_INVALID, "unknown field pulse type");
+  c->has_applied = true;
+  c->applied_type = type; c->applied_t0 = t0; c->applied_fbw = fbw; c->applied_fc = fc;
+  for (int d = 0; d < 3; ++d) c->applied_B[d] = B[d];
   return JB_OK;
 }
 
@@ -1004,11 +1028,11 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   }
   const int thermal = T > 0.0 ? 1 : 0;
 
-  const int max_chunk = c->has_ac ? 2048 : nsteps;
+  const int max_chunk = time_dependent(c) ? 2048 : nsteps;
   for (int done = 0; done < nsteps;) {
     const int chunk = std::min(nsteps - done, std::max(1, max_chunk));
     std::vector<double> times;
-    if (c->has_ac) {
+    if (time_dependent(c)) {
       for (int n = 0; n < chunk; ++n) { const double t0 = time_ps + (done + n) * dt; times.push_back(t0); times.push_back(t0 + dt); }  // cpu_llg_heun.cc:46,103-104
     } else {
       times.push_back(time_ps);
@@ -1025,8 +1049,8 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
       }
       tp.step = first_step + (uint64_t)(done + n);
       const size_t nc = c->h_classes.size();
-      const JbClass *cls0 = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n : 0) * nc;       // fields at t      (cpu_llg_heun.cc:66)
-      const JbClass *cls1 = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + 1 : 0) * nc;   // fields at t + dt (:103-106)
+      const JbClass *cls0 = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n : 0) * nc;       // fields at t      (cpu_llg_heun.cc:66)
+      const JbClass *cls1 = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n + 1 : 0) * nc;   // fields at t + dt (:103-106)
       for (int m = 0; m < c->g.M; ++m) {
         tp.cls[m] = cls0[c->class_of_motif[m]];
         const JbClass &b = cls1[c->class_of_motif[m]];
@@ -1059,7 +1083,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
       for (int stage = 0; stage < 2; ++stage) {
         JbStageParams p{};
         p.g = c->g;
-        fill_tables(c, p.t, c->has_ac ? 2 * n + stage : 0);
+        fill_tables(c, p.t, time_dependent(c) ? 2 * n + stage : 0);
         for (int k = 0; k < 3; ++k) {
           p.in[k] = stage == 0 ? c->S0[k] : c->S1[k];
           p.out[k] = stage == 0 ? c->S1[k] : c->S0[k];
@@ -1093,7 +1117,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           tp.step = p.step;
           tp.recover_u = recu ? 1 : 0;
           tp.noise_warp = (c->tiling.pair && c->g.M == 1 && c->tiling.SPT == 1) ? c->opt_noise_warp : 0;
-          const JbClass *cls = c->h_class_tab.data() + (size_t)(c->has_ac ? 2 * n + stage : 0) * c->h_classes.size();
+          const JbClass *cls = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n + stage : 0) * c->h_classes.size();
           for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
           tp.R = c->tiling.Rs[stage];
           rc = tile_launch_shape(c, tp, stage, th); if (rc) return rc;
@@ -1134,9 +1158,9 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
   if (c->has_pairs) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 needs a translation-invariant exchange template (jb_set_exchange_template, or jb_set_exchange_pairs with template detection)");
   const bool periodic_x = c->g.per[0] && c->g.gx > 0;
   for (int done = 0; done < nsteps;) {
-    const int chunk = c->has_ac ? std::min(nsteps - done, 1024) : nsteps - done;
+    const int chunk = time_dependent(c) ? std::min(nsteps - done, 1024) : nsteps - done;
     std::vector<double> times;
-    if (c->has_ac) {   // fields at t0, t0 + dt/2 (k2 and k3), t0 + dt (cuda_rk4_base.cu:70-71,78-79,86-87)
+    if (time_dependent(c)) {   // fields at t0, t0 + dt/2 (k2 and k3), t0 + dt (cuda_rk4_base.cu:70-71,78-79,86-87)
       for (int n = 0; n < chunk; ++n) { const double t0 = time_ps + (done + n) * dt; times.push_back(t0); times.push_back(t0 + 0.5 * dt); times.push_back(t0 + dt); }
     } else {
       times.push_back(time_ps);
@@ -1147,7 +1171,7 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
         JbStageParams p{};
         p.g = c->g;
         const int tsel = stage == 0 ? 0 : (stage == 3 ? 2 : 1);
-        fill_tables(c, p.t, c->has_ac ? 3 * n + tsel : 0);
+        fill_tables(c, p.t, time_dependent(c) ? 3 * n + tsel : 0);
         double *const *in = stage == 0 ? c->S0 : (stage == 2 ? c->V : c->S1);          // S0 -> S1 -> V -> S1 -> S0
         double *const *out = stage == 0 ? c->S1 : (stage == 1 ? c->V : (stage == 2 ? c->S1 : c->S0));
         double *const *plo = stage == 0 ? c->peer_lo_S1 : (stage == 1 ? c->peer_lo_V : (stage == 2 ? c->peer_lo_S1 : c->peer_lo_S0));

@@ -169,6 +169,7 @@ struct jb_ctx {
   std::vector<double> h_K, h_axis; int uni_power = 0;
   std::vector<double> h_dc, h_ac, h_omega; bool has_zeeman = false, has_ac = false;
   double applied_B[3] = {0, 0, 0}; bool has_applied = false;
+  int applied_type = 0; double applied_t0 = 0.0, applied_fbw = 0.0, applied_fc = 0.0;   // jb_set_applied_field_pulse
 
   // exchange template (host)
   std::vector<int> t_mi, t_mj, t_T; std::vector<double> t_J9;

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(320, 2) stage_pair_kernel(const __grid_constan
       mbar_init(smem_u32(&fullS[s]), 1); mbar_init(smem_u32(&emptyS[s]), n_cw);
       mbar_init(smem_u32(&fullU[s]), 1); mbar_init(smem_u32(&emptyU[s]), n_cw);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&fullN[s]), 1); mbar_init(smem_u32(&emptyN[s]), n_cw); }
+    // noise ring: every thread that wrote (read) a slot arrives itself, so each access is ordered by its own release
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&fullN[s]), 32); mbar_init(smem_u32(&emptyN[s]), 32 * n_cw); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // per ring phase c (= slot of the oldest resident plane) and template entry n: byte offset of the neighbour
@@ -185,8 +186,7 @@ __global__ void __launch_bounds__(320, 2) stage_pair_kernel(const __grid_constan
             dst[sidx] = a; dst[slotU + sidx] = b; dst[2 * slotU + sidx] = c;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&fullN[nslot]));
+        mbar_arrive(smem_u32(&fullN[nslot]));
         nslot ^= 1;
         gs0 += (unsigned long long)g.Ny * g.Nz;
       }
@@ -259,8 +259,7 @@ __global__ void __launch_bounds__(320, 2) stage_pair_kernel(const __grid_constan
         phN ^= 1u << cslotN;
         const uint32_t na = nown + (uint32_t)cslotN * 3u * (uint32_t)slotU * 4u;
         const float2 v0 = lds_f2(na), v1 = lds_f2(na + (uint32_t)slotU * 4u), v2 = lds_f2(na + 2u * (uint32_t)slotU * 4u);
-        __syncwarp();
-        if (lane0) mbar_arrive(smem_u32(&emptyN[cslotN]));
+        mbar_arrive(smem_u32(&emptyN[cslotN]));
         cslotN ^= 1;
         fb0 = v0.y; fb1 = v1.y; fb2 = v2.y;
         if (nw == 2) site_normals_rk_f(p.rk, p.step, gs, fa0, fa1, fa2);

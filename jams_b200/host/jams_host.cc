@@ -768,8 +768,17 @@ ZeemanHamiltonian::ZeemanHamiltonian(const Setting &s, const Lattice &lattice) :
 
 AppliedFieldHamiltonian::AppliedFieldHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
   const std::string type = lowercase(s.get("type", "static"));
-  if (type != "static") throw std::runtime_error("Unknown field pulse type " + type + " (only 'static' is on the hot path)");
+  if (type == "static") type_ = JB_FIELD_STATIC;
+  else if (type == "sinc") type_ = JB_FIELD_SINC;
+  else if (type == "sinc-cos") type_ = JB_FIELD_SINC_COS;
+  else throw std::runtime_error("Unknown field pulse type " + type);
   field_ = read_vec3(s.required("field"));
+  if (type_ != JB_FIELD_STATIC) {
+    time_center_ = s.required("time_center").as_double() / 1e-12;
+    freq_bandwidth_ = s.required("freq_bandwidth").as_double() / 1e12;
+    if (type_ == JB_FIELD_SINC_COS) freq_center_ = s.required("freq_center").as_double() / 1e12;
+  }
+  name_ += "-" + type;
 }
 
 // =====================================================================================================
@@ -1088,7 +1097,10 @@ void ZeemanHamiltonian::attach(jb_ctx *ctx) {
   solver->check(jb_set_zeeman(ctx, dc_local_field_.data(), has_ac_local_field_ ? ac_local_field_.data() : nullptr,
                               has_ac_local_field_ ? ac_local_frequency_.data() : nullptr));
 }
-void AppliedFieldHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_applied_field(ctx, field_.data(), 1)); }
+void AppliedFieldHamiltonian::attach(jb_ctx *ctx) {
+  if (type_ == JB_FIELD_STATIC) solver->check(jb_set_applied_field(ctx, field_.data(), 1));
+  else solver->check(jb_set_applied_field_pulse(ctx, field_.data(), type_, time_center_, freq_bandwidth_, freq_center_));
+}
 
 // =====================================================================================================
 // Simulation (core/jams++.cc:231-377)

@@ -193,13 +193,15 @@ class ZeemanHamiltonian : public Hamiltonian {   // hamiltonian/zeeman.cc:12-132
   bool has_ac_local_field_ = false;
 };
 
-class AppliedFieldHamiltonian : public Hamiltonian {   // hamiltonian/applied_field.cc:84-148 (type "static")
+class AppliedFieldHamiltonian : public Hamiltonian {   // hamiltonian/applied_field.cc:10-148 (types static, sinc, sinc-cos)
  public:
   AppliedFieldHamiltonian(const Setting &settings, const Lattice &lattice);
   int term() const override { return JB_TERM_APPLIED; }
   void attach(jb_ctx *ctx) override;
  private:
   Vec3 field_{{0, 0, 0}};
+  int type_ = JB_FIELD_STATIC;
+  double time_center_ = 0.0, freq_bandwidth_ = 0.0, freq_center_ = 0.0;   // ps, THz (applied_field.cc:37-38,66-68)
 };
 
 class B200HeunLLGSolver;

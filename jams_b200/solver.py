@@ -328,18 +328,29 @@ class ZeemanHamiltonian(Hamiltonian):
 
 
 class AppliedFieldHamiltonian(Hamiltonian):
+    """``module = "applied-field"`` (hamiltonian/applied_field.{h,cc}): homogeneous B(t) = ``field`` x g(t), the field on site i is
+    mu_i B(t).  ``type``: ``static`` (default, g = 1), ``sinc`` (g = sinc(pi f_bw (t - t0))), ``sinc-cos`` (... x cos(2 pi f_c (t - t0)));
+    ``time_center`` in seconds, ``freq_bandwidth`` / ``freq_center`` in Hz (converted to ps / THz like applied_field.cc:37-38,66-68)."""
     term = capi.TERM_APPLIED
     name = "applied-field-static"
 
     def __init__(self, settings: dict, lattice: Lattice):
         super().__init__(settings, lattice)
         kind = str(self.settings.get("type", "static")).lower()
-        if kind != "static":
-            raise RuntimeError("Unknown field pulse type " + kind + " (only 'static' is on the hot path)")
+        if kind not in ("static", "sinc", "sinc-cos"):
+            raise RuntimeError("Unknown field pulse type " + kind)
+        self.kind = kind
+        self.name = "applied-field-" + kind
         self.field = np.asarray(self.settings["field"], dtype=np.float64)
+        self.time_center = float(self.settings["time_center"]) / 1e-12 if kind != "static" else 0.0
+        self.freq_bandwidth = float(self.settings["freq_bandwidth"]) / 1e12 if kind != "static" else 0.0
+        self.freq_center = float(self.settings["freq_center"]) / 1e12 if kind == "sinc-cos" else 0.0
 
     def attach(self, ctx, x0, nx):
-        ctx.set_applied_field(self.field, True)
+        if self.kind == "static":
+            ctx.set_applied_field(self.field, True)
+        else:
+            ctx.set_applied_field_pulse(self.field, self.kind, self.time_center, self.freq_bandwidth, self.freq_center)
 
 
 _HAMILTONIANS = {"exchange": ExchangeHamiltonian, "exchange-functional": ExchangeFunctionalHamiltonian,

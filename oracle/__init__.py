@@ -59,8 +59,12 @@ class _Lib:
         p = prefix
         L = self.lib
 
-        def sig(name, restype, *argtypes):
-            f = getattr(L, p + name)
+        def sig(name, restype, *argtypes, optional=False):
+            f = getattr(L, p + name, None)
+            if f is None:
+                if optional:
+                    return None      # the reference-header build (oracle/_ref) has no such entry
+                raise AttributeError(p + name)
             f.restype, f.argtypes = restype, list(argtypes)
             return f
 
@@ -71,6 +75,7 @@ class _Lib:
         self.sim_add_exchange = sig("sim_add_exchange", C.c_int, C.c_void_p, C.c_int64, _c_int_p, _c_int_p, _c_double_p, C.c_int)
         self.sim_add_uniaxial = sig("sim_add_uniaxial", C.c_int, C.c_void_p, C.c_int, _c_double_p, _c_double_p)
         self.sim_add_zeeman = sig("sim_add_zeeman", C.c_int, C.c_void_p, _c_double_p, C.c_void_p, C.c_void_p)
+        self.sim_add_applied_field = sig("sim_add_applied_field", C.c_int, C.c_void_p, _c_double_p, C.c_int, C.c_double, C.c_double, C.c_double, optional=True)
         self.sim_exchange_nnz = sig("sim_exchange_nnz", C.c_int64, C.c_void_p, C.c_int)
         self.sim_exchange_csr = sig("sim_exchange_csr", None, C.c_void_p, C.c_int, _c_int_p, _c_int_p, _c_double_p)
         self.sim_set_spins = sig("sim_set_spins", None, C.c_void_p, _c_double_p)
@@ -314,6 +319,16 @@ class CpuSim:
             rc = self.L.sim_add_zeeman(self.h, dc, ac.ctypes.data, omega.ctypes.data)
         else:
             rc = self.L.sim_add_zeeman(self.h, dc, None, None)
+        self._check(rc)
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_applied_field(self, B, kind="static", time_center_ps=0.0, freq_bandwidth_THz=0.0, freq_center_THz=0.0):
+        """AppliedFieldHamiltonian (hamiltonian/applied_field.cc): mu_i B g(t); restatement only"""
+        if getattr(self.L, "sim_add_applied_field", None) is None:
+            raise RuntimeError("this oracle build has no applied-field term")
+        rc = self.L.sim_add_applied_field(self.h, _f64(B, (3,)), {"static": 0, "sinc": 1, "sinc-cos": 2}[kind], float(time_center_ps),
+                                          float(freq_bandwidth_THz), float(freq_center_THz))
         self._check(rc)
         self.n_terms += 1
         return self.n_terms - 1

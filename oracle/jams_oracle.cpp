@@ -437,7 +437,7 @@ void jo_init_bloch_domain_wall(int64_t N, const double *positions, double width,
 namespace {
 
 struct Term {
-  enum Kind { EXCHANGE, UNIAXIAL, ZEEMAN } kind;
+  enum Kind { EXCHANGE, UNIAXIAL, ZEEMAN, APPLIED } kind;
   std::vector<double> field;  // N x 3 (Hamiltonian::field_, core/hamiltonian.h)
   // exchange CSR (containers/sparse_matrix.h:270-275)
   std::vector<int> row, col;
@@ -448,7 +448,22 @@ struct Term {
   // zeeman
   std::vector<double> dc, ac, omega;
   bool has_ac = false;
+  // applied field B(t) = B g(t) (hamiltonian/applied_field.cc:10-82): 0 static, 1 sinc, 2 sinc-cos; t0 in ps, frequencies in THz
+  double B[3] = {0, 0, 0};
+  int pulse_type = 0;
+  double t0 = 0, fbw = 0, fc = 0;
 };
+
+// TimeDependentField::field(time) (applied_field.cc:18-19,41-43,70-73); sinc: helpers/maths.h:441-446
+inline V3 applied_b(const Term &t, double time) {
+  const double kPi = 3.14159265358979323846, kTwoPi = 2.0 * kPi;
+  if (t.pulse_type == 0) return {t.B[0], t.B[1], t.B[2]};
+  const double x = kPi * t.fbw * (time - t.t0);
+  const double sinc = (x == 0.0) ? 1.0 : sin(x) / x;
+  if (t.pulse_type == 1) return {t.B[0] * sinc, t.B[1] * sinc, t.B[2] * sinc};
+  const double c = cos(kTwoPi * t.fc * (time - t.t0));
+  return {t.B[0] * sinc * c, t.B[1] * sinc * c, t.B[2] * sinc * c};
+}
 
 struct Sim {
   int N = 0;
@@ -488,6 +503,11 @@ void calculate_fields(Sim &sim, Term &t, double time) {
         if (t.has_ac) for (int j = 0; j < 3; ++j) t.field[3 * i + j] += t.ac[3 * i + j] * cos(t.omega[i] * time);
       }
       break;
+    case Term::APPLIED: {  // hamiltonian/applied_field.cc:137-148: field_(i, j) = mus(i) * B(t)[j]
+      const V3 b = applied_b(t, time);
+      for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) t.field[3 * i + j] = sim.mus[i] * b[j];
+      break;
+    }
   }
 }
 
@@ -720,6 +740,17 @@ int jo_sim_add_zeeman(void *p, const double *dc, const double *ac, const double 
   return 0;
 }
 
+int jo_sim_add_applied_field(void *p, const double *B, int type, double t0_ps, double fbw_THz, double fc_THz) {
+  auto *sim = static_cast<Sim *>(p);
+  if (type < 0 || type > 2) return 1;
+  Term t; t.kind = Term::APPLIED;
+  t.field.assign(3 * sim->N, 0.0);
+  for (int j = 0; j < 3; ++j) t.B[j] = B[j];
+  t.pulse_type = type; t.t0 = t0_ps; t.fbw = fbw_THz; t.fc = fc_THz;
+  sim->terms.push_back(std::move(t));
+  return 0;
+}
+
 int64_t jo_sim_exchange_nnz(void *p, int term) { return int64_t(static_cast<Sim *>(p)->terms.at(term).val.size()); }
 void jo_sim_exchange_csr(void *p, int term, int *row, int *col, double *val) {
   auto &t = static_cast<Sim *>(p)->terms.at(term);
@@ -797,6 +828,14 @@ double jo_sim_term_total_energy(void *p, int term, double time) {
         e_total += -dot(s_i, field);
       }
       return e_total;
+    case Term::APPLIED: {  // applied_field.cc:121-128,150-155
+      const V3 b = applied_b(t, time);
+      for (int i = 0; i < N; ++i) {
+        const V3 field = {sim->mus[i] * b[0], sim->mus[i] * b[1], sim->mus[i] * b[2]};
+        e_total += -(sim->s[3 * i] * field[0] + sim->s[3 * i + 1] * field[1] + sim->s[3 * i + 2] * field[2]);
+      }
+      return e_total;
+    }
   }
   return 0.0;
 }
@@ -821,6 +860,11 @@ void jo_sim_term_energies(void *p, int term, double time, double *e) {
         V3 field = {t.dc[3 * i], t.dc[3 * i + 1], t.dc[3 * i + 2]};
         if (t.has_ac) for (int j = 0; j < 3; ++j) field[j] += t.ac[3 * i + j] * cos(t.omega[i] * time);
         e[i] = -dot(s_i, field);
+        break;
+      }
+      case Term::APPLIED: {
+        const V3 b = applied_b(t, time);
+        e[i] = -(s_i[0] * (sim->mus[i] * b[0]) + s_i[1] * (sim->mus[i] * b[1]) + s_i[2] * (sim->mus[i] * b[2]));
         break;
       }
     }

@@ -84,7 +84,12 @@ def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
             terms[module] = sim.add_zeeman(dc, ac, om)
         elif module == "applied-field":
             B = np.asarray(hs["field"], float)
-            terms[module] = sim.add_zeeman(lat.mus()[:, None] * B[None, :])
+            kind = str(hs.get("type", "static")).lower()
+            if kind == "static":
+                terms[module] = sim.add_zeeman(lat.mus()[:, None] * B[None, :])
+            else:   # applied_field.cc:37-38,66-68: seconds -> ps, Hz -> THz
+                terms[module] = sim.add_applied_field(B, kind, float(hs["time_center"]) / 1e-12, float(hs["freq_bandwidth"]) / 1e12,
+                                                      float(hs.get("freq_center", 0.0)) / 1e12)
         else:
             raise RuntimeError(module)
     sim.init_solver(dt_ps, lat.gilbert_prefactor, seed)

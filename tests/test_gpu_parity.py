@@ -523,3 +523,35 @@ def test_exchange_functional_fields_energy_and_trajectory_match_oracle(variant):
     sim.run(30)
     s.run(30)
     assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+
+
+# ---- time-dependent applied field (hamiltonian/applied_field.cc:10-82: static, sinc, sinc-cos) ----
+@pytest.mark.parametrize("kind", ["sinc", "sinc-cos"])
+@pytest.mark.parametrize("variant", ["direct", "tma", "pair", "pair_store_u", "fused", "pairs"])
+def test_applied_field_pulse_fields_energy_and_trajectory_match_oracle(kind, variant):
+    """B(t) = B g(t): both Heun stages see the field at their own time (predictor t, corrector t + dt,
+    cpu_llg_heun.cc:46,103-104); the pulse is centred inside the run so the amplitude changes sign and size over the steps"""
+    w = W.c3_sc(dims=(9, 8, 14), temperature=0.0)
+    hs = dict(module="applied-field", type=kind, field=[0.3, -0.2, 1.5], time_center=2.0e-15, freq_bandwidth=4.0e14)
+    if kind == "sinc-cos":
+        hs["freq_center"] = 9.0e14
+    w["hamiltonians"].append(hs)
+    lat = w["lattice"]
+    s0 = random_unit_spins(lat.num_spins, 31)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    s = make(w, options=KERNELS.get(variant), pairs=(variant == "pairs"))
+    s.set_spins(s0)
+    h = s.hamiltonians[-1]
+    assert h.name == "applied-field-" + kind
+    for t in (0.0, 1.3e-3, 2.0e-3, 3.7e-3):     # ps
+        f, want = h.calculate_fields(t), sim.term_fields(sim.terms["applied-field"], t)
+        assert np.abs(f - want).max() <= 1e-13 * max(np.abs(want).max(), 1e-30)
+        e, want_e = h.calculate_total_energy(t), sim.term_total_energy(sim.terms["applied-field"], t)
+        assert abs(e - want_e) <= 1e-12 * max(abs(want_e), 1.0)
+    amp = [sim.term_fields(sim.terms["applied-field"], n * 1e-4)[0, 2] for n in range(40)]
+    assert max(amp) > 0 and min(amp) < 0                              # the pulse really varies over the run
+    sim.run(40)
+    s.run(25)
+    s.run(15)                                                         # time is carried across calls
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
