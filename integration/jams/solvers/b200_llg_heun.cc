@@ -12,6 +12,7 @@
 #include "jams/core/lattice.h"
 #include "jams/core/physics.h"
 #include "jams/core/thermostat.h"
+#include "jams/hamiltonian/applied_field.h"
 #include "jams/hamiltonian/exchange.h"
 #include "jams/hamiltonian/uniaxial_anisotropy.h"   // + `friend class B200HeunLLGSolver;`
 #include "jams/hamiltonian/zeeman.h"                // + `friend class B200HeunLLGSolver;`
@@ -57,7 +58,9 @@ void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
 
 void B200HeunLLGSolver::build() {
   check(jb_set_materials(ctx_, globals::mus.data(), globals::gyro.data(), globals::alpha.data()));
+  int ham_index = -1;   // hamiltonians_ are registered in config order (core/jams++.cc:284-288)
   for (auto &h : hamiltonians_) {
+    ++ham_index;
     if (auto *ex = dynamic_cast<ExchangeHamiltonian *>(h.get())) {
       // ExchangeHamiltonian::neighbour_list() (hamiltonian/exchange.h:13): sorted {i,j} pairs + unique tensors.
       // The library recognises a translation-invariant list and switches to its template kernel.
@@ -83,7 +86,25 @@ void B200HeunLLGSolver::build() {
       check(jb_set_zeeman(ctx_, ze->dc_local_field_.data(),
                           ze->has_ac_local_field_ ? ze->ac_local_field_.data() : nullptr,
                           ze->has_ac_local_field_ ? ze->ac_local_frequency_.data() : nullptr));
+    } else if (dynamic_cast<AppliedFieldHamiltonian *>(h.get())) {
+      // the TimeDependentField member is protected and opaque (hamiltonian/applied_field.h:20-43): re-read the Hamiltonian's own
+      // settings group with the conversions of applied_field.cc:13,35-38,63-68 (seconds -> ps, Hz -> THz)
+      const libconfig::Setting &hs = globals::config->lookup("hamiltonians")[ham_index];
+      const auto type = lowercase(jams::config_optional<std::string>(hs, "type", "static"));
+      const Vec3 B = jams::config_required<Vec3>(hs, "field");
+      const double Bv[3] = {B[0], B[1], B[2]};
+      if (type == "static") {
+        check(jb_set_applied_field(ctx_, Bv, 1));
+      } else if (type == "sinc" || type == "sinc-cos") {
+        check(jb_set_applied_field_pulse(ctx_, Bv, type == "sinc" ? JB_FIELD_SINC : JB_FIELD_SINC_COS,
+                                         jams::config_required<double>(hs, "time_center") / 1e-12,
+                                         jams::config_required<double>(hs, "freq_bandwidth") / 1e12,
+                                         type == "sinc-cos" ? jams::config_required<double>(hs, "freq_center") / 1e12 : 0.0));
+      } else {
+        throw std::runtime_error("Unknown field pulse type " + type);
+      }
     } else {
+      // exchange-functional / exchange-neartree keep their matrix private (hamiltonian/sparse_interaction.h:45-49): INTEGRATION.md
       throw std::runtime_error("llg-heun-b200-gpu: hamiltonian '" + h->name() + "' is not fused; use llg-heun-gpu");
     }
   }
