@@ -12,7 +12,8 @@ kernel = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 T = float(sys.argv[4]) if len(sys.argv) > 4 else 100.0
 import json
 extra = json.loads(sys.argv[5]) if len(sys.argv) > 5 else {}
-w = W.c3_sc(dims=(n, n, n), temperature=T)
+dims = tuple(int(v) for v in os.environ["JB_QB_DIMS"].split("x")) if os.environ.get("JB_QB_DIMS") else (n, n, n)
+w = W.c3_sc(dims=dims, temperature=T)
 s = W.make_solver(w, options=dict(extra, kernel=kernel), random_spins_seed=1, seed=3)
 s.run(steps)
 s.ctx.synchronize()
