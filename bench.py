@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--kernel", type=int, default=None, help="0 = direct gathers, 1 = TMA plane ring, 2 = pair kernel (two launches per step), 3 = fused step kernel (default)")
+    ap.add_argument("--kernel", type=int, default=None, help="0 = direct gathers, 1 = TMA plane ring (one site per thread), 2 = pair kernel, two launches per step (the library default), 3 = fused step kernel")
     ap.add_argument("--temperature", type=float, default=None, help="thermostat temperature of the workload in K (default 100; 0 = the deterministic T = 0 variant, a profile artefact and not the headline)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: BASELINE config 5 (sc 512^3, 134 M spins) cut into --gpus x-slabs instead of 256^3 per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
