@@ -586,7 +586,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) 
   else JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the tile kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
-  const int G = per_sm * c->num_sms;
+  int G = per_sm * c->num_sms;
+  if (c->opt_grid > 0) G = std::min(G, c->opt_grid);   // experiments: fewer resident CTAs than the occupancy calculation allows
   const JbGeom &g = c->g;
   int best_c = 1;
   if (c->opt_chunks > 0) {
@@ -1448,6 +1449,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "ring_u") c->opt_RU = (int)value;
   else if (k == "chunks") c->opt_chunks = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
+  else if (k == "grid") c->opt_grid = (int)value;
   else if (k == "u_tma") c->opt_u_tma = (int)value;
   else if (k == "smem_pad") c->opt_smem_pad = (int)value;
   else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }   // experiments: unused dynamic shared memory (KB) per CTA

@@ -248,6 +248,7 @@ struct jb_ctx {
   int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
   int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0, opt_load_hint = 0, opt_reverse_b = 0;
   int opt_smem_pad = 0;
+  int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernels (0 = occupancy x SMs)
   int opt_noise_warp = 0;     // pair kernel: see JbTileParams::noise_warp
   int opt_recover_u = 2;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B), 2 = 1 at T = 0, 0 at T > 0
   int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows
