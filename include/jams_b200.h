@@ -227,6 +227,14 @@ JB_API int jb_synchronize(jb_ctx *ctx);
 JB_API void *jb_stream(jb_ctx *ctx);
 /* tuning knobs (tile shape etc.); unknown keys return JB_ERR_INVALID */
 JB_API int jb_set_option(jb_ctx *ctx, const char *key, int64_t value);
+/* Host-only helper (needs no GPU): the work-item plan the stage kernel's queue uses for a slab of nx_local planes with x ghost
+ * depth ghost_x, n_columns yz-column tiles and n_ctas resident CTAs: chunks (x0[k], xc[k]) in queue order (face chunks first,
+ * long chunks, a taper of short ones); capacity >= 160.  Exposed so that tests can check coverage and ordering on the CPU. */
+JB_API int jb_plan_work_items(int32_t nx_local, int32_t ghost_x, int32_t n_columns, int32_t n_ctas, int32_t capacity,
+                              int32_t *n_chunks, int32_t *x0, int32_t *xc);
+/* with option "trace" = 1: per resident CTA of the most recent stage-kernel launch {SM id, first / last device clock in ns,
+ * work items taken} (4 x uint64 per CTA, at most `capacity` CTAs) -- the load-balance evidence in profiles/.  Synchronises. */
+JB_API int jb_last_stage_trace(jb_ctx *ctx, uint64_t *out4, int32_t capacity, int32_t *n_ctas);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,8 @@ SIGNATURES = {
     "jb_synchronize": (C.c_int, [C.c_void_p]),
     "jb_stream": (C.c_void_p, [C.c_void_p]),
     "jb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "jb_plan_work_items": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _ip, _ip]),
+    "jb_last_stage_trace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
 }
 
 _lib = None
@@ -114,6 +116,17 @@ def detect_exchange_template(dims, num_motif, periodic, i, j, value_id, values9,
         return None
     k = n.value
     return dict(mi=mi[:k].copy(), mj=mj[:k].copy(), T=T[:3 * k].reshape(k, 3).copy(), J9=J9[:9 * k].reshape(k, 9).copy())
+
+
+def plan_work_items(nx_local, ghost_x, n_columns, n_ctas):
+    """jb_plan_work_items: the stage kernel's x-chunk plan in queue order, as a list of (x0, xc).  Host only."""
+    lib = load()
+    x0 = np.zeros(160, np.int32); xc = np.zeros(160, np.int32)
+    n = C.c_int32(0)
+    rc = lib.jb_plan_work_items(int(nx_local), int(ghost_x), int(n_columns), int(n_ctas), 160, C.byref(n), x0, xc)
+    if rc != JB_OK:
+        raise JamsB200Error(rc, "jb_plan_work_items: invalid arguments")
+    return [(int(x0[k]), int(xc[k])) for k in range(n.value)]
 
 
 class Context:
@@ -289,6 +302,13 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.jb_synchronize(self.h))
+
+    def last_stage_trace(self, capacity=4096):
+        """option trace = 1: per resident CTA of the last stage launch (SM id, first clock ns, last clock ns, items taken)"""
+        out = np.zeros((capacity, 4), dtype=np.uint64)
+        n = C.c_int32(0)
+        self._ck(self.lib.jb_last_stage_trace(self.h, _ptr(out), int(capacity), C.byref(n)))
+        return out[:n.value].copy()
 
     def stream(self):
         return self.lib.jb_stream(self.h)

@@ -90,6 +90,20 @@ int ensure_aos(jb_ctx *c) {
   return JB_OK;
 }
 
+// work-queue counters + face counters of the stage kernel, and the optional per-CTA trace buffer
+int ensure_queue(jb_ctx *c) {
+  if (!c->d_queue) {
+    JB_CUDA(c, cudaMalloc(&c->d_queue, 8 * sizeof(unsigned int)));
+    JB_CUDA(c, cudaMemsetAsync(c->d_queue, 0, 8 * sizeof(unsigned int), c->stream));
+    c->stage_launches = 0;
+  }
+  if (c->opt_trace && !c->d_trace) {
+    JB_CUDA(c, cudaMalloc(&c->d_trace, 4096 * 4 * sizeof(unsigned long long)));
+    JB_CUDA(c, cudaMemsetAsync(c->d_trace, 0, 4096 * 4 * sizeof(unsigned long long), c->stream));
+  }
+  return JB_OK;
+}
+
 // ---- geometry --------------------------------------------------------------------------------------
 void compute_geometry(jb_ctx *c, int gx, int gy, int gz) {
   JbGeom &g = c->g;
@@ -353,89 +367,38 @@ void choose_tiling(jb_ctx *c) {
   c->tiling_valid = true;
   c->tmap_valid = false;
   const int n_nbr = (int)c->t_mi.size();
-  if (!c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
+  if (c->opt_kernel < 1 || !c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
-  const bool fused = c->opt_kernel == 3 && c->fused_geometry && g.gx == 2 * c->reach[0] && c->reach[0] == 1;
-  const bool pair = c->opt_kernel >= 2;
-  t.pair = pair ? 1 : 0;
-  if (fused) {
-    // fused step kernel: one CTA per SM; the s_n ring (TMA) and four s* planes share the SM's shared memory.  Tile
-    // candidates in order of preference (less redundant predictor work first); a thread owns the pair (z, z + 1) of
-    // every motif site of one (y) row, consumer threads <= 256.
-    const int rx = c->reach[0], ry = c->reach[1], rz = c->reach[2];
-    const int cand[][2] = {{8, 64}, {4, 64}, {8, 32}, {4, 32}, {8, 16}, {4, 16}, {2, 16}, {2, 8}, {1, 8}, {1, 4}, {1, 2}};
-    const size_t budget = 220 * 1024;
-    bool found = false;
-    for (const auto &cd : cand) {
-      int TY = c->opt_TY ? c->opt_TY : cd[0], TZ = c->opt_TZ ? c->opt_TZ : cd[1];
-      TY = std::max(1, std::min(TY, g.Ny));
-      TZ = std::max(1, std::min(TZ, g.Nz));
-      if (TZ < g.Nz && (TZ & 1)) TZ++;
-      const int HZ = (TZ + 1) / 2;
-      t.TY = TY; t.TZ = TZ; t.SPT = 1;
-      t.e1z = rz > 0 ? 2 : 0; t.e2z = rz > 0 ? 4 : 0;
-      t.gzb = t.e2z;
-      t.BY = TY + 4 * ry; t.BZ = 2 * HZ + 2 * t.e2z;
-      t.UZ = 2 * HZ;
-      t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
-      t.slotU = 16;
-      t.threads = HZ * TY;
-      t.u_tma = 0; t.RU = 2;
-      const int n_ct = (t.threads + 31) / 32 * 32;
-      const int n_halo = 2 * ry * g.M * (HZ + t.e1z) + TY * g.M * t.e1z;
-      const size_t slot_bytes = (size_t)3 * t.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);
-      const size_t fixed = 512 + 4 * slot_bytes;   // four s* planes + their entry-table phases + barriers
-      int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
-      R = std::min(R, JB_PAIR_MAX_RING);
-      if (!c->opt_R) R = std::min(R, 2 * rx + 1 + 3);
-      t.R = t.Rs[0] = t.Rs[1] = R;
-      t.smem[0] = t.smem[1] = fixed + (size_t)R * slot_bytes;
-      t.halo_warps = (n_halo + 31) / 32;
-      const bool fits = R >= 2 * rx + 2 && t.smem[0] <= budget && n_ct + 32 * t.halo_warps + 32 <= 384 &&
-                        t.BY * g.M <= 256 && t.BZ <= 256 && g.oz >= t.e2z;
-      if (fits) { found = true; break; }
-      if (c->opt_TY && c->opt_TZ) break;
-    }
-    if (found) t.fused = 1;
-    for (const JbClass &cl : c->h_classes) if (cl.power != 0) t.uni = 1;
-  }
-  if (t.fused) {
-    // shape chosen above
-  } else if (pair) {
-    // pair kernel: a thread owns the sites (z, z + 1) of every motif site of its y rows; consumer threads =
-    // ceil(TZ / 2) x ceil(TY / SPT) <= 256 so that two CTAs share an SM.  Tile choice: among z extents 128 / 64 / 32 (long
-    // contiguous runs along z serve DRAM best: 4 x 128 beats 8 x 64 beats 16 x 32 on C3, profiles/README.md) take, for
-    // each, the tallest tile whose rings fit the shared-memory budget, and keep the candidate with the most sites per
-    // plane (a shorter z extent only if it brings 1.5 x the sites).  Motifs with several sites multiply the slot size, so they end up with shorter tiles
-    // (bcc: 4 x 64) instead of degenerate one-row tiles.
-    int SPT = c->opt_SPT ? c->opt_SPT : 1;
-    if (!(SPT == 1 || SPT == 2)) return;
+  {
+    // a thread owns the sites (z, z + 1) of every motif site of its y row; consumer threads = ceil(TZ / 2) x TY <= 256 so
+    // that two CTAs share an SM.  Tile choice: among z extents 128 / 64 / 32 (long contiguous runs along z serve DRAM best:
+    // 4 x 128 beats 8 x 64 beats 16 x 32 on C3, profiles/README.md) take, for each, the tallest tile whose rings fit the
+    // shared-memory budget, and keep the candidate with the most sites per plane (a shorter z extent only if it brings
+    // 1.5 x the sites).  Motifs with several sites multiply the slot size, so they end up with shorter tiles (bcc: 4 x 64)
+    // instead of degenerate one-row tiles.
     const size_t budget = c->opt_ctas_per_sm == 1 ? 220 * 1024 : 113 * 1024;   // per CTA
     const int rmin = 2 * g.gx + 2;
     auto shape = [&](int TY, int TZ, jb_ctx::Tiling &q) -> bool {   // fills q; true if the tile fits
       const int HZ = (TZ + 1) / 2;
-      q.TY = TY; q.TZ = TZ; q.SPT = (SPT > TY) ? 1 : SPT;
+      q.TY = TY; q.TZ = TZ;
       q.gzb = (g.gz + 1) & ~1;
       q.BY = TY + 2 * g.gy; q.BZ = ((TZ + 1) & ~1) + 2 * q.gzb;
       q.UZ = (TZ + 1) & ~1;
       q.slotS = (q.BY * g.M * q.BZ + 15) / 16 * 16;
       q.slotU = (q.TY * g.M * q.UZ + 15) / 16 * 16;
-      q.threads = HZ * ((TY + q.SPT - 1) / q.SPT);
-      q.u_tma = 1;
+      q.threads = HZ * TY;
       q.RU = c->opt_RU ? c->opt_RU : 2;
       const size_t slot_bytes = (size_t)3 * q.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
       const size_t u_bytes = (size_t)q.RU * 3 * q.slotU * 8;
-      // noise ring of the noise warp (one-site motifs, SPT 1): two slots of three fp32 per site of the tile
-      const size_t n_bytes = (g.M == 1 && q.SPT == 1 && c->opt_noise_warp) ? (size_t)2 * 3 * q.slotU * 4 : 0;
       for (int st = 0; st < 2; ++st) {
-        const size_t fixed = 512 + (st == 1 ? u_bytes : 0) + n_bytes;
+        const size_t fixed = 512 + (st == 1 ? u_bytes : 0);   // barriers + item ring
         int R = c->opt_R ? c->opt_R : (budget > fixed ? (int)((budget - fixed) / slot_bytes) : 0);
         R = std::min(R, JB_PAIR_MAX_RING);
         // one plane in flight per CTA is the measured optimum: with the stores in the mix, more outstanding plane loads
         // lower the DRAM efficiency (ring 5 / 6: -8 % / -15 %, profiles/README.md r01f)
         if (!c->opt_R) R = std::min(R, rmin);
         q.Rs[st] = R;
-        q.smem[st] = fixed + (size_t)R * slot_bytes + (size_t)c->opt_smem_pad * 1024;
+        q.smem[st] = fixed + (size_t)R * slot_bytes;
       }
       q.R = q.Rs[1];
       return q.Rs[0] >= rmin && q.Rs[1] >= rmin && q.threads <= 256 && q.smem[0] <= 220 * 1024 && q.smem[1] <= 220 * 1024 &&
@@ -452,7 +415,7 @@ void choose_tiling(jb_ctx *c) {
       prev_TZ = TZ;
       if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
       const int HZ = (TZ + 1) / 2;
-      int TY = c->opt_TY ? c->opt_TY : std::max(SPT, (256 * SPT) / HZ);
+      int TY = c->opt_TY ? c->opt_TY : std::max(1, 256 / HZ);
       TY = std::max(1, std::min(TY, std::min(g.Ny, 64)));
       jb_ctx::Tiling q = t;
       bool ok = false;
@@ -460,8 +423,7 @@ void choose_tiling(jb_ctx *c) {
       for (; TY >= 1; TY = c->opt_TY ? 0 : TY - 1) { if (shape(TY, TZ, q)) { ok = true; break; } }
       if (ok) {
         const long long sites = (long long)q.TY * q.TZ * g.M;
-        if (2 * sites > 3 * best_sites) { best_sites = sites; shrunk = q.TY < ty_max;   // a shorter z extent must bring 1.5 x the sites per plane
-          const int pair_flag = t.pair; t = q; t.pair = pair_flag; found = true; }
+        if (2 * sites > 3 * best_sites) { best_sites = sites; shrunk = q.TY < ty_max; t = q; found = true; }   // a shorter z extent must bring 1.5 x the sites per plane
       }
       if (c->opt_TZ) break;   // fixed by the caller
     }
@@ -472,38 +434,6 @@ void choose_tiling(jb_ctx *c) {
       const double interior = (double)t.TY * t.TZ / ((double)t.BY * t.BZ);
       if (interior < 0.4) return;
     }
-  } else {
-  int TZ = c->opt_TZ ? c->opt_TZ : (g.Nz >= 64 ? 64 : (g.Nz >= 32 ? 32 : g.Nz));
-  TZ = std::max(1, std::min(TZ, g.Nz));
-  if (TZ < g.Nz && (TZ & 1)) TZ++;   // several z tiles: their first column must stay 16-byte aligned for TMA
-  int SPT = c->opt_SPT ? c->opt_SPT : 1;
-  // consumer threads per CTA: <= 480 (+ the producer warp = 512 threads at 64 registers, two CTAs per SM) for SPT 1, 256 for SPT 2
-  int TY = c->opt_TY ? c->opt_TY : std::max(SPT, ((SPT == 1 ? 480 : 256) * SPT) / TZ);
-  TY = std::max(1, std::min(TY, g.Ny));
-  if (TY > 64) TY = 64;
-  while (SPT > 1 && (SPT > TY)) SPT /= 2;
-  if (!(SPT == 1 || SPT == 2)) return;
-  t.R = c->opt_R ? c->opt_R : 2 * g.gx + 2;
-  t.RU = c->opt_RU ? c->opt_RU : 2;
-  if (t.R < 2 * g.gx + 2 || t.R > 8 || t.RU < 2 || t.RU > 8) return;
-  for (;;) {
-    t.TY = TY; t.TZ = TZ; t.SPT = SPT;
-    t.gzb = (g.gz + 1) & ~1;
-    t.BY = TY + 2 * g.gy; t.BZ = TZ + 2 * t.gzb; if (t.BZ & 1) t.BZ++;
-    t.UZ = (TZ + 1) & ~1;
-    t.slotS = (t.BY * g.M * t.BZ + 15) / 16 * 16;
-    t.slotU = (t.TY * g.M * t.UZ + 15) / 16 * 16;
-    t.threads = TZ * ((TY + SPT - 1) / SPT);
-    t.smem[0] = (size_t)t.R * 3 * t.slotS * 8 + 512 + (size_t)t.R * n_nbr * sizeof(JbTileNbr);
-    t.u_tma = c->opt_u_tma ? 1 : 0;
-    t.smem[1] = t.smem[0] + (t.u_tma ? (size_t)t.RU * 3 * t.slotU * 8 : 0);
-    // wanted: two CTAs per SM in stage B
-    if ((t.smem[1] <= 110 * 1024 && t.threads <= (SPT == 1 ? 480 : 256)) || c->opt_TY || TY <= SPT) break;
-    TY = std::max(SPT, TY / 2);
-  }
-  if (t.threads > (t.SPT == 1 ? 480 : 256) || t.BY * g.M > 256 || t.BZ > 256 || t.UZ > 256 || t.TY * g.M > 256) return;
-  if (t.smem[1] > 220 * 1024) return;
-  t.Rs[0] = t.Rs[1] = t.R;
   }
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
@@ -517,11 +447,10 @@ void choose_tiling(jb_ctx *c) {
   // pair kernel: within a motif site the entries with an even z offset come first (their neighbour pair is 16-byte
   // aligned in shared memory), then the odd ones; both groups keep the CSR column order
   std::vector<int> order(c->tile_order.begin(), c->tile_order.end());
-  if (t.pair)
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
       if (c->t_mi[a] != c->t_mi[b]) return c->t_mi[a] < c->t_mi[b];
-      return (c->t_T[3 * a + 2] & 1) < (c->t_T[3 * b + 2] & 1);
-    });
+    return (c->t_T[3 * a + 2] & 1) < (c->t_T[3 * b + 2] & 1);
+  });
   c->tile_nbr_odd.assign(g.M + 1, 0);
   for (int pos = 0; pos < n_nbr; ++pos) {
     const int k = order[pos];
@@ -531,7 +460,7 @@ void choose_tiling(jb_ctx *c) {
     if (!(Tz & 1)) c->tile_nbr_odd[mi]++;   // number of even entries for now
     JbTileNbr e{};
     e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
-    e.d = Tx + (t.fused ? c->reach[0] : g.gx);
+    e.d = Tx + g.gx;
     e.J = c->t_J9[9 * k] * inv_mu;
     for (int q = 0; q < 9; ++q) J9T[9 * (size_t)pos + q] = c->t_J9[9 * (size_t)k + q] * inv_mu;
     c->tile_nbr[pos] = e;
@@ -556,61 +485,166 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   p.g = c->g;
   p.J9T = c->d_tile_J9T;
   p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
-  p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols; p.u_tma = t.u_tma;
+  p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
-  for (int q = 0; q < c->g.M; ++q) p.nbr_odd[q] = t.pair ? c->tile_nbr_odd[q] : c->tile_nbr_begin[q + 1];
+  for (int q = 0; q < c->g.M; ++q) p.nbr_odd[q] = c->tile_nbr_odd[q];
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
-  p.rx = c->reach[0]; p.ry = c->reach[1]; p.rz = c->reach[2]; p.e1z = t.e1z; p.e2z = t.e2z;
-  p.producer_sleep_ns = c->opt_producer_sleep;
-  p.split_wait = c->opt_split_wait;
-  p.debug_skip = c->opt_debug_skip;
-  p.early_release = c->opt_early_release;
-  p.store_hint = c->opt_store_hint;
-  p.load_hint = c->opt_load_hint;
-  for (int m = 0; m < c->g.M; ++m) {
-    int n = c->tile_nbr_begin[m];
-    while (n < c->tile_nbr_begin[m + 1] && c->tile_nbr[n].d < 2 * c->g.gx) ++n;
-    p.nbr_split[m] = n;
+}
+
+// The x-chunk plan of one launch: `n` chunks (x0, xc) in QUEUE order.  Work items are (chunk, column) pairs handed out by an
+// atomic counter, chunk-major, so CTAs that run at the same time work on neighbouring columns of the same x-range and share
+// tile halos through the 126 MB L2.  Order: the two face chunks of the slab first (in a slab-decomposed run their ghost-plane
+// stores and the epoch flags travel while the interior is computed), then the long chunks, then a taper of ever shorter chunks
+// that evens out the finishing times of the resident CTAs.
+//
+// Measured on C3 (profiles/README.md r02a): an item boundary costs a CTA next to nothing (the co-resident CTA of the SM uses
+// the bandwidth meanwhile: 2048 instead of 1152 items changed the mean CTA busy time by 0.2 %), but a launch lasts as long as
+// its slowest CTA: the plan is everything.  So the plan is chosen by SIMULATING the queue: list scheduling of the items over G
+// CTAs whose speeds differ by a few per cent (as the per-CTA traces show), cost = planes + a small per-item overhead, over a
+// family of (long length, taper share, shortest length) candidates; the candidate with the shortest makespan wins.
+struct ChunkPlanCandidate { std::vector<std::pair<int, int>> xs; std::vector<int> taper; };
+
+static ChunkPlanCandidate make_candidate(int nx, int gx, int L, int S, int tail_pct) {
+  ChunkPlanCandidate cd;
+  const int lmin = std::max(gx, 1);
+  L = std::max(lmin, std::min(L, nx));
+  S = std::max(lmin, std::min(S, L));
+  int tail = (int)((long long)nx * tail_pct / 100);
+  if (nx - tail < std::max(L, 2 * lmin)) tail = 0;
+  // taper: lengths L/2, L/4, ... >= S, every level the same share of the tail planes
+  std::vector<int> tl;
+  for (int l = L / 2; l >= S && l >= lmin; l /= 2) tl.push_back(l);
+  if (tl.empty() && tail > 0) tl.push_back(S);
+  std::vector<int> taper_len;
+  int used = 0;
+  for (size_t k = 0; k < tl.size() && tail > 0; ++k) {
+    const int share = (int)((long long)tail * (k + 1) / tl.size()) - used;
+    const int cnt = share / tl[k];
+    for (int q = 0; q < cnt; ++q) taper_len.push_back(tl[k]);
+    used += cnt * tl[k];
+  }
+  const int body = nx - used;
+  const int nl = std::max(1, (int)std::lround((double)body / L));
+  // x layout: long chunks, with the taper just before the last long chunk (so both faces of the slab are long chunks)
+  int x = 0;
+  for (int k = 0; k < nl; ++k) {
+    const int len = (int)((long long)(k + 1) * body / nl) - (int)((long long)k * body / nl);
+    if (k == nl - 1 && nl > 1) for (int l : taper_len) { cd.xs.push_back({x, l}); cd.taper.push_back(1); x += l; }
+    cd.xs.push_back({x, len}); cd.taper.push_back(0); x += len;
+    if (k == nl - 1 && nl == 1) for (int l : taper_len) { cd.xs.push_back({x, l}); cd.taper.push_back(1); x += l; }
+  }
+  return cd;
+}
+
+// queue order of a candidate: face chunks, long chunks, taper (longest first)
+static std::vector<int> queue_order(const ChunkPlanCandidate &cd, int nx, int gx) {
+  const int n = (int)cd.xs.size();
+  std::vector<int> order;
+  auto face = [&](int k) { return cd.xs[k].first < gx || cd.xs[k].first + cd.xs[k].second > nx - gx; };
+  for (int k = 0; k < n; ++k) if (face(k)) order.push_back(k);
+  for (int k = 0; k < n; ++k) if (!face(k) && !cd.taper[k]) order.push_back(k);
+  std::vector<int> tp;
+  for (int k = 0; k < n; ++k) if (!face(k) && cd.taper[k]) tp.push_back(k);
+  std::stable_sort(tp.begin(), tp.end(), [&](int a, int b) { return cd.xs[a].second > cd.xs[b].second; });
+  order.insert(order.end(), tp.begin(), tp.end());
+  return order;
+}
+
+static double simulate_queue(const ChunkPlanCandidate &cd, const std::vector<int> &order, int n_cols, int G, double overhead) {
+  // CTA g runs at speed 1 + 4 % * (a fixed pseudo-random number in [-1, 1]); a binary heap of finishing times
+  std::vector<std::pair<double, int>> heap(G);
+  for (int g = 0; g < G; ++g) heap[g] = {0.0, g};
+  auto cmp = [](const std::pair<double, int> &a, const std::pair<double, int> &b) { return a.first > b.first; };
+  std::make_heap(heap.begin(), heap.end(), cmp);
+  auto slow = [](int g) { uint32_t h = (uint32_t)g * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; return 1.0 + 0.04 * ((double)(h & 0xffff) / 32767.5 - 1.0); };
+  for (int q : order) {
+    const double cost = cd.xs[q].second + overhead;
+    for (int col = 0; col < n_cols; ++col) {
+      std::pop_heap(heap.begin(), heap.end(), cmp);
+      std::pair<double, int> &w = heap.back();
+      w.first += cost * slow(w.second);
+      std::push_heap(heap.begin(), heap.end(), cmp);
+    }
+  }
+  double end = 0.0;
+  for (const auto &w : heap) end = std::max(end, w.first);
+  return end;
+}
+
+struct ChunkPlanOptions { int chunks = 0, chunk_long = 0, chunk_short = 0, tail_pct = -1; };
+
+// result in queue order; returns the number of chunks
+static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOptions &o, int *x0_out, int *xc_out) {
+  const ChunkPlanOptions *c = &o;
+  ChunkPlanCandidate best;
+  if (o.chunks > 0) {
+    const int nc = std::max(1, std::min(std::min(o.chunks, nx), JB_TILE_MAX_CHUNKS));
+    for (int k = 0; k < nc; ++k) {
+      const int x0 = (int)((long long)k * nx / nc), x1 = (int)((long long)(k + 1) * nx / nc);
+      best.xs.push_back({x0, x1 - x0}); best.taper.push_back(0);
+    }
+  } else if (c->chunk_long > 0) {
+    best = make_candidate(nx, gx, c->chunk_long, c->chunk_short > 0 ? c->chunk_short : std::max(gx, 2), c->tail_pct >= 0 ? c->tail_pct : 25);
+  } else {
+    const double per_cta = (double)nx * n_cols / std::max(1, G);   // planes of work per resident CTA
+    double best_t = 1e300;
+    const int Ls[] = {8, 10, 12, 14, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128};
+    const int tails[] = {0, 10, 20, 30, 40, 50};
+    const int Ss[] = {2, 4, 8};
+    for (int L : Ls) {
+      if (L > nx || (3 * L > per_cta && L != Ls[0])) continue;   // a CTA takes at least three long items: robust against speed differences the model does not know
+      for (int tp : tails) for (int S : Ss) {
+        if (tp == 0 && S != Ss[0]) continue;
+        if (c->tail_pct >= 0 && tp != tails[0]) continue;
+        ChunkPlanCandidate cd = make_candidate(nx, gx, L, std::max(S, gx), c->tail_pct >= 0 ? c->tail_pct : tp);
+        if ((int)cd.xs.size() > JB_TILE_MAX_CHUNKS || (long long)cd.xs.size() * n_cols > 200000) continue;
+        const double t = simulate_queue(cd, queue_order(cd, nx, gx), n_cols, G, 0.35) * (1.0 + 1e-4 * cd.xs.size());
+        if (t < best_t) { best_t = t; best = cd; }
+      }
+    }
+    if (best.xs.empty()) best = make_candidate(nx, gx, nx, nx, 0);
+  }
+  if ((int)best.xs.size() > JB_TILE_MAX_CHUNKS) best = make_candidate(nx, gx, (nx + JB_TILE_MAX_CHUNKS - 1) / JB_TILE_MAX_CHUNKS, nx, 0);
+  const std::vector<int> order = queue_order(best, nx, gx);
+  const int n = (int)best.xs.size();
+  for (int q = 0; q < n; ++q) { x0_out[q] = best.xs[order[q]].first; xc_out[q] = best.xs[order[q]].second; }
+  return n;
+}
+
+void plan_chunks(jb_ctx *c, int G, int n_cols, jb_ctx::Tiling::Shape &sh) {
+  const int nx = c->g.nx, gx = c->g.gx;
+  ChunkPlanOptions o;
+  o.chunks = c->opt_chunks; o.chunk_long = c->opt_chunk_long; o.chunk_short = c->opt_chunk_short; o.tail_pct = c->opt_tail_pct;
+  sh.n_chunks = plan_chunks_core(nx, gx, n_cols, G, o, sh.x0, sh.xc);
+  sh.face_items[0] = sh.face_items[1] = 0;
+  for (int q = 0; q < sh.n_chunks; ++q) {
+    if (sh.x0[q] < gx) sh.face_items[0] += n_cols;
+    if (sh.x0[q] + sh.xc[q] > nx - gx) sh.face_items[1] += n_cols;
   }
 }
 
-// grid size (resident CTAs) and number of x-chunks for one kernel variant
-int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal) {
+// grid size (resident CTAs) and the x-chunk plan for one kernel variant
+int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, int recu) {
   jb_ctx::Tiling &t = c->tiling;
-  if (t.grid[stage][thermal] > 0) return JB_OK;
+  jb_ctx::Tiling::Shape &sh = t.shape[stage][thermal][recu];
+  if (sh.grid > 0) return JB_OK;
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
-  if (t.fused) JB_CUDA(c, jbk_step_fused_occupancy(p, thermal, c->iso ? 1 : 0, t.uni, t.threads, t.halo_warps, t.smem[stage], &per_sm));
-  else if (t.pair) JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
-  else JB_CUDA(c, jbk_stage_tile_occupancy(p, stage, thermal, c->iso ? 1 : 0, t.SPT, t.threads, t.smem[stage], &per_sm));
-  if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the tile kernel does not fit on an SM with this tiling");
+  JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, recu, t.threads, t.smem[stage], &per_sm));
+  if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the stage kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
   int G = per_sm * c->num_sms;
   if (c->opt_grid > 0) G = std::min(G, c->opt_grid);   // experiments: fewer resident CTAs than the occupancy calculation allows
-  const JbGeom &g = c->g;
-  int best_c = 1;
-  if (c->opt_chunks > 0) {
-    best_c = std::min(c->opt_chunks, g.nx);
-  } else {
-    // cost model: time ~ (items per CTA, rounded up) x (planes marched per item + load-only halo planes)
-    double best = 1e300;
-    for (int nc = 1; nc <= g.nx; ++nc) {
-      const long long items = (long long)nc * t.n_cols;
-      const long long per_cta = (items + G - 1) / G;
-      const int xc = (g.nx + nc - 1) / nc;
-      // planes marched per item + what an item costs on top: halo planes that are only loaded (two-launch kernels) or
-      // the extra predictor planes of the fused kernel
-      const double cost = (double)per_cta * (xc + (t.fused ? 2.0 * c->reach[0] + 0.6 : 0.7 * 2 * g.gx + 0.3));
-      if (cost < best * 0.999) { best = cost; best_c = nc; }
-    }
+  plan_chunks(c, G, t.n_cols, sh);
+  sh.grid = (int)std::min<long long>(G, (long long)sh.n_chunks * t.n_cols);
+  if (c->opt_verbose) {
+    fprintf(stderr, "jams_b200: stage kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads, ring %d/%d, smem %zu B, "
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", stage, thermal, recu, t.TY, t.TZ, t.threads, t.Rs[stage], t.RU,
+            t.smem[stage], per_sm, sh.grid, sh.n_chunks, t.n_cols);
+    for (int q = 0; q < sh.n_chunks; ++q) fprintf(stderr, " %d+%d", sh.x0[q], sh.xc[q]);
+    fprintf(stderr, "\n");
   }
-  t.n_chunks[stage][thermal] = best_c;
-  t.grid[stage][thermal] = (int)std::min<long long>(G, (long long)best_c * t.n_cols);
-  if (c->opt_verbose)
-    fprintf(stderr, "jams_b200: %s kernel stage %d thermal %d: tile %dx%d (y,z) spt %d, %d consumer threads, ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns\n", t.fused ? "fused step" : (t.pair ? "pair" : "tile"), stage, thermal, t.TY, t.TZ, t.SPT, t.threads, t.Rs[stage], t.RU,
-            t.smem[stage], per_sm, t.grid[stage][thermal], best_c, t.n_cols);
   return JB_OK;
 }
 
@@ -653,17 +687,7 @@ int ensure_ready(jb_ctx *c) {
     }
   }
   const JbGeom &g = c->g;
-  // the fused step kernel (jb_step_fused.cu) needs ghost zones twice as deep as the template reaches; it handles reach 1
-  // along x, reach <= 1 along y and z and motifs of one or two sites.  A periodic axis must then be at least 2 x ghost
-  // depth long (no site may sit on both faces) and the slab at least a ghost depth thick.
   const int reach[3] = {gx, gy, gz};
-  bool fused = c->opt_kernel == 3 && c->has_template && !c->has_pairs && gx == 1 && gy <= 1 && gz <= 1 && c->d.num_motif <= 2;
-  {
-    const int ext[3] = {c->d.dims[0], c->d.dims[1], c->d.dims[2]};
-    for (int d = 0; d < 3; ++d) if (reach[d] > 0 && c->d.periodic[d] && ext[d] < 4 * reach[d]) fused = false;
-    if (c->d.nx_local < 2 * gx || (c->d.n_ranks == 1 && c->d.periodic[0] && c->d.nx_local < 4 * gx)) fused = false;
-  }
-  if (fused) { gx *= 2; gy *= 2; gz *= 2; }
   const bool geom_changed = !c->state_allocated || gx != g.gx || gy != g.gy || gz != g.gz || c->state_relayout;
   c->state_relayout = false;
   if (geom_changed) {
@@ -687,7 +711,6 @@ int ensure_ready(jb_ctx *c) {
       JB_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     compute_geometry(c, gx, gy, gz);
-    c->fused_geometry = fused;
     int rc = allocate_state(c); if (rc) return rc;
     if (had_state) {
       double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
@@ -773,6 +796,7 @@ void jb_destroy(jb_ctx *c) {
   p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
+  p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p);
   for (int r = 0; r < JB_MAX_REGIONS; ++r) { p = c->d_region[r]; free_dev(p); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto ev : c->ev) cudaEventDestroy(ev);
@@ -1017,10 +1041,11 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
   const bool multi = c->d.n_ranks > 1 && c->g.gx > 0;
 
   choose_tiling(c);
-  const bool use_tile = c->opt_kernel >= 1 && c->tiling.ok && !c->has_pairs;
+  const bool use_tile = c->tiling.ok && !c->has_pairs;
   JbTileParams tp{};
   if (use_tile) {
     rc = build_tmaps(c); if (rc) return rc;
+    rc = ensure_queue(c); if (rc) return rc;
     fill_tile_params(c, tp);
     for (int r = 0; r < 10; ++r) {   // Philox4x32-10 key schedule (Salmon et al.)
       tp.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
@@ -1028,6 +1053,15 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
     }
   }
   const int thermal = T > 0.0 ? 1 : 0;
+  // data flow of the TMA kernel (option recover_u): 1 = the corrector rebuilds the Heun intermediate from s_n and s* (120 B per
+  // update; at T > 0 it then draws the site's noise a second time), 0 = the predictor stores it with the noise part of the
+  // corrector folded in (144 B), 2 = 1 at T = 0 and 0 at T > 0
+  const bool recu = use_tile && (c->opt_recover_u == 1 || (c->opt_recover_u == 2 && !thermal));
+  // the epoch handshake of a slab-decomposed run happens inside the TMA kernel; the other kernels bracket each launch with
+  // wait / signal launches
+  // (a neighbour slab that lives on THIS device shares its SMs with me: a resident kernel that polls for its flags could keep
+  // it from ever running, so that set-up -- only tests use it -- keeps the separate launches unless fold_halo = 2 insists)
+  const bool fold = multi && use_tile && (c->opt_fold_halo == 2 || (c->opt_fold_halo == 1 && !c->peer_on_my_device));
 
   const int max_chunk = time_dependent(c) ? 2048 : nsteps;
   for (int done = 0; done < nsteps;) {
@@ -1040,47 +1074,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
     }
     rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
 
-    for (int n = 0; n < chunk && use_tile && c->tiling.fused; ++n) {
-      // ---- fused step kernel: one launch per Heun step, reads S0 (s_n) and writes S1 (s_{n+1}); then the roles swap ----
-      for (int k = 0; k < 3; ++k) {
-        tp.out[k] = c->S1[k]; tp.u[k] = nullptr;
-        if (multi) { tp.out_lo[k] = c->peer_lo_S1[k]; tp.out_hi[k] = c->peer_hi_S1[k]; }
-        else if (c->g.per[0] && c->g.gx > 0) { tp.out_lo[k] = c->S1[k]; tp.out_hi[k] = c->S1[k]; }
-        else { tp.out_lo[k] = nullptr; tp.out_hi[k] = nullptr; }
-      }
-      tp.step = first_step + (uint64_t)(done + n);
-      const size_t nc = c->h_classes.size();
-      const JbClass *cls0 = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n : 0) * nc;       // fields at t      (cpu_llg_heun.cc:66)
-      const JbClass *cls1 = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n + 1 : 0) * nc;   // fields at t + dt (:103-106)
-      for (int m = 0; m < c->g.M; ++m) {
-        tp.cls[m] = cls0[c->class_of_motif[m]];
-        const JbClass &b = cls1[c->class_of_motif[m]];
-        tp.fT1[m][0] = b.fTx; tp.fT1[m][1] = b.fTy; tp.fT1[m][2] = b.fTz;
-      }
-      tp.R = c->tiling.Rs[0];
-      rc = tile_launch_shape(c, tp, 0, thermal); if (rc) return rc;
-      tp.n_chunks = c->tiling.n_chunks[0][thermal];
-      tp.n_items = tp.n_chunks * tp.n_cols;
-      if (multi) { JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++; }
-      record_event(c, 0);
-      const CUtensorMap tm[3] = {c->tmap[0][0], c->tmap[0][1], c->tmap[0][2]};
-      JB_CUDA(c, jbk_step_fused(tp, tm, thermal, c->iso ? 1 : 0, c->tiling.uni, c->tiling.threads, c->tiling.halo_warps, c->tiling.grid[0][thermal],
-                                c->tiling.smem[0], c->stream));
-      c->launches++;
-      record_event(c, 1);
-      if (multi) {
-        c->epoch++;
-        JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
-      }
-      for (int k = 0; k < 3; ++k) {   // s_{n+1} becomes the current state
-        std::swap(c->S0[k], c->S1[k]);
-        std::swap(c->tmap[0][k], c->tmap[1][k]);
-        std::swap(c->tmap[3][k], c->tmap[4][k]);
-        std::swap(c->peer_lo_S0[k], c->peer_lo_S1[k]);
-        std::swap(c->peer_hi_S0[k], c->peer_hi_S1[k]);
-      }
-    }
-    for (int n = 0; n < chunk && !(use_tile && c->tiling.fused); ++n) {
+    for (int n = 0; n < chunk; ++n) {
       for (int stage = 0; stage < 2; ++stage) {
         JbStageParams p{};
         p.g = c->g;
@@ -1099,13 +1093,11 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           }
         }
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
-        // the corrector needs no noise: the predictor folds the noise part of its right-hand side into u (jb_device.cuh)
-        // (with recover_u the pair kernel stores no u, and its corrector draws the noise itself)
-        // (option recover_u: 2 = where it is measured faster, i.e. at T = 0 -- at T > 0 the second noise draw costs what the 24 B save)
-        const bool recu = use_tile && c->tiling.pair && !c->has_pairs && (c->opt_recover_u == 1 || (c->opt_recover_u == 2 && !thermal));
+        // stored-u data flow: the corrector needs no noise, the predictor folds the noise part of its right-hand side into u
+        // (jb_device.cuh); recover_u: the corrector draws the noise itself
         const int th = (stage == 0 || recu) ? thermal : 0;
         p.thermal = th;
-        if (multi) {
+        if (multi && !fold) {
           // ghosts I read were written by the neighbours' previous stage; the boxes I write into were
           // last read by the neighbours' previous stage: both are covered by their last signal
           JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++;
@@ -1116,23 +1108,35 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         } else if (use_tile) {
           for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
           tp.step = p.step;
-          tp.recover_u = recu ? 1 : 0;
-          tp.noise_warp = (c->tiling.pair && c->g.M == 1 && c->tiling.SPT == 1) ? c->opt_noise_warp : 0;
           const JbClass *cls = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n + stage : 0) * c->h_classes.size();
           for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
           tp.R = c->tiling.Rs[stage];
-          rc = tile_launch_shape(c, tp, stage, th); if (rc) return rc;
-          tp.n_chunks = c->tiling.n_chunks[stage][th];
-          tp.n_items = tp.n_chunks * tp.n_cols;
+          rc = tile_launch_shape(c, tp, stage, th, recu ? 1 : 0); if (rc) return rc;
+          const jb_ctx::Tiling::Shape &sh = c->tiling.shape[stage][th][recu ? 1 : 0];
+          tp.n_chunks = sh.n_chunks;
+          tp.n_items = sh.n_chunks * tp.n_cols;
+          for (int q = 0; q < sh.n_chunks; ++q) { tp.chunk_x0[q] = sh.x0[q]; tp.chunk_xc[q] = sh.xc[q]; }
+          tp.queue = c->d_queue + (c->stage_launches & 1ull);          // this launch's item counter (zero: see queue_next)
+          tp.queue_next = c->d_queue + ((c->stage_launches + 1) & 1ull);   // ... and the one it zeroes for the next launch
+          c->stage_launches++;
+          tp.trace = c->opt_trace ? c->d_trace : nullptr;
+          tp.halo = JbHalo{};
+          if (fold) {
+            JbHalo &h = tp.halo;
+            h.enabled = (c->peer_lo_flags ? 1 : 0) | (c->peer_hi_flags ? 2 : 0);
+            h.flags = c->flags;
+            h.sig_lo = c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr;
+            h.sig_hi = c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr;
+            h.wait_epoch = c->epoch; h.signal_epoch = c->epoch + 1;
+            h.face_count = c->d_queue + 2;
+            const unsigned int n_cw = (unsigned int)((c->tiling.threads + 31) / 32);
+            h.face_target[0] = n_cw * (unsigned int)sh.face_items[0];
+            h.face_target[1] = n_cw * (unsigned int)sh.face_items[1];
+          }
           const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
-          tp.reverse_items = (c->tiling.pair && stage == 1 && c->opt_reverse_b) ? 1 : 0;
-          if (c->tiling.pair)
-            JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
-                                      c->tiling.grid[stage][th], c->tiling.smem[stage], c->stream));
-          else
-            JB_CUDA(c, jbk_stage_tile(tp, tm, stage, th, c->iso ? 1 : 0, c->tiling.SPT, c->tiling.threads,
-                                      c->tiling.grid[stage][th], c->tiling.smem[stage], c->stream));
+          JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+          c->trace_ctas = sh.grid;
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
         }
@@ -1140,7 +1144,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         record_event(c, 2 * stage + 1);
         if (multi) {
           c->epoch++;
-          JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+          if (!fold) { JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++; }
         }
       }
     }
@@ -1266,7 +1270,8 @@ int jb_magnetisation(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin, 
   if (!c || !M4 || n_groups < 1) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
-  if (c->d_classes == nullptr) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
+  // mu comes from the class table: make sure it is the current one (upload_classes skips the copy when nothing changed)
+  if (c->d_classes == nullptr || c->class_sig.empty()) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
   JbTables t; fill_tables(c, t, 0);
   const size_t need = (size_t)(4096 + 4 * n_groups) * sizeof(double) + (group_of_spin ? (size_t)c->N * sizeof(int) : 0);
   rc = ensure_scratch(c, need + 64); if (rc) return rc;
@@ -1303,7 +1308,7 @@ int jb_region_moment(jb_ctx *c, int32_t region, double *M4) {
   if (!c || !M4 || region < 0 || region >= JB_MAX_REGIONS) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
-  if (c->d_classes == nullptr) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
+  if (c->d_classes == nullptr || c->class_sig.empty()) { std::vector<double> times{0.0}; rc = upload_classes(c, times, 0.0, 0.0, 0, -1); if (rc) return rc; }
   if (c->region_n[region] == 0) { M4[0] = M4[1] = M4[2] = M4[3] = 0.0; return JB_OK; }
   JbTables t; fill_tables(c, t, 0);
   rc = ensure_scratch(c, (size_t)(4096 + 8) * sizeof(double)); if (rc) return rc;
@@ -1360,6 +1365,7 @@ static int map_peer(jb_ctx *c, const Blob &b, void **base_out) {
     JB_FAIL(c, JB_ERR_PEER, "neighbour slab has a different shape (equal slabs are required)");
   if (b.pid == (int32_t)getpid()) {
     // same process (several contexts driven by one host thread): plain pointers, peer access if needed
+    if (b.device == c->device) c->peer_on_my_device = true;
     if (b.device != c->device) {
       int can = 0;
       JB_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, b.device));
@@ -1441,31 +1447,46 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   const std::string k(key);
   if (k == "kernel") c->opt_kernel = (int)value;
   else if (k == "recover_u") c->opt_recover_u = (int)value;
-  else if (k == "noise_warp") c->opt_noise_warp = (int)value;
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
-  else if (k == "spt") c->opt_SPT = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
   else if (k == "ring_u") c->opt_RU = (int)value;
   else if (k == "chunks") c->opt_chunks = (int)value;
+  else if (k == "chunk_long") c->opt_chunk_long = (int)value;
+  else if (k == "chunk_short") c->opt_chunk_short = (int)value;
+  else if (k == "tail_pct") c->opt_tail_pct = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
   else if (k == "grid") c->opt_grid = (int)value;
-  else if (k == "u_tma") c->opt_u_tma = (int)value;
-  else if (k == "smem_pad") c->opt_smem_pad = (int)value;
-  else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }   // experiments: unused dynamic shared memory (KB) per CTA
-  else if (k == "producer_sleep") { c->opt_producer_sleep = (int)value; return JB_OK; }
-  else if (k == "split_wait") { c->opt_split_wait = (int)value; return JB_OK; }
+  else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }
+  else if (k == "fold_halo") { c->opt_fold_halo = (int)value; return JB_OK; }
+  else if (k == "trace") { c->opt_trace = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
-  else if (k == "debug_skip") { c->opt_debug_skip = (int)value; return JB_OK; }
-  else if (k == "early_release") { c->opt_early_release = (int)value; return JB_OK; }
-  else if (k == "store_hint") { c->opt_store_hint = (int)value; return JB_OK; }
-  else if (k == "load_hint") { c->opt_load_hint = (int)value; return JB_OK; }
-  else if (k == "reverse_b") { c->opt_reverse_b = (int)value; return JB_OK; }
   else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }
   else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
   c->tiling_valid = false;
   c->tmap_valid = false;
+  return JB_OK;
+}
+
+int jb_plan_work_items(int32_t nx_local, int32_t ghost_x, int32_t n_columns, int32_t n_ctas, int32_t capacity, int32_t *n_chunks,
+                       int32_t *x0, int32_t *xc) {
+  if (nx_local < 1 || ghost_x < 0 || n_columns < 1 || n_ctas < 1 || !n_chunks || !x0 || !xc || capacity < JB_TILE_MAX_CHUNKS) return JB_ERR_INVALID;
+  int bx0[JB_TILE_MAX_CHUNKS], bxc[JB_TILE_MAX_CHUNKS];
+  const int n = plan_chunks_core(nx_local, ghost_x, n_columns, n_ctas, ChunkPlanOptions{}, bx0, bxc);
+  for (int q = 0; q < n; ++q) { x0[q] = bx0[q]; xc[q] = bxc[q]; }
+  *n_chunks = n;
+  return JB_OK;
+}
+
+int jb_last_stage_trace(jb_ctx *c, uint64_t *out4, int32_t capacity, int32_t *n_ctas) {
+  if (!c || !out4 || !n_ctas || capacity < 0) return JB_ERR_INVALID;
+  *n_ctas = 0;
+  if (!c->d_trace) return JB_OK;
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = std::min(std::min((int)capacity, c->trace_ctas), 4096);
+  JB_CUDA(c, cudaMemcpy(out4, c->d_trace, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  *n_ctas = n;
   return JB_OK;
 }
 

@@ -1,4 +1,4 @@
-// jb_device.cuh — device-side building blocks shared by the stage kernels (jb_kernels.cu, jb_stage_tile.cu):
+// jb_device.cuh — device-side building blocks shared by the stage kernels (jb_kernels.cu, jb_stage_pair.cu):
 // ghosted-box indexing, the Philox4x32-10 Langevin noise, the per-spin LLG-Heun stage update and the
 // ghost-image stores.  Reference formulas are cited next to each piece (paths relative to
 // /root/reference/src/jams/).
@@ -16,7 +16,22 @@ __device__ __forceinline__ long long gidx(const JbGeom &g, int xp, int yp, int m
   return (long long)xp * g.sX + (long long)yp * g.sY + (long long)m * g.PZ + zp;
 }
 
-// ---- Philox4x32-10 (Salmon et al., SC'11) counter-based generator, all in registers -------------
+// ---- Langevin white noise: Philox4x32-10 (Salmon et al., SC'11) in registers + Box-Muller on the SFU ----------
+// One draw per step and site, used by both Heun stages (solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64), as a function of
+// (seed, step, global site id) only -- any slab decomposition, tiling or kernel gives the same numbers.
+//
+// Stream definition (round 2): ONE Philox call per z-PAIR of sites.  counter = (global id of the pair's even-z site, step),
+// key = seed; the 128 output bits w0..w3 feed three Box-Muller transforms k = 0, 1, 2:
+//     radius  u_k = 2 - float(1.mantissa = w_k >> 9)   in (0, 1], 23 bits      r_k = sqrt(-2 ln u_k)
+//     angle   b_0 = w3 & 0xffff, b_1 = w3 >> 16, b_2 = (w0 & 0xff) | (w1 & 0xff) << 8      theta_k = 2 pi (b_k + 1/2) / 65536
+//     even-z site: ( r0 cos th0, r0 sin th0, r1 cos th1 )      odd-z site: ( r1 sin th1, r2 cos th2, r2 sin th2 )
+// No output bit is used twice.  Six normals cost one Philox call (was: two calls for six normals and two discarded ones), which
+// removes about 50 of the 145 noise instructions a pair of sites cost in round 1.
+// Quality notes: |n| <= sqrt(2 * 23 ln 2) = 5.65 (the tail beyond has probability 1e-7 per draw and is lumped at the edge);
+// the 65536 equidistant angles make every mixed moment E[n_a^p n_b^q] with p + q < 65536 exactly that of the continuous
+// transform (the trapezoidal rule is exact for trigonometric polynomials below the number of nodes); lg2 / sqrt / sin / cos are
+// the SFU approximations (absolute error ~1e-6), far below the statistical resolution of any observable -- the reference's two
+// backends, pcg + std::normal_distribution on the CPU and cuRAND XORWOW on the GPU, already differ stream for stream.
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1, uint32_t out[4]) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -31,30 +46,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-
-// Box-Muller in fp32 on the SFU (MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS); the result is widened to
-// double by the caller.  u = (a + 0.5) 2^-32 lies in (0,1], so the log is finite; |n| <= 6.8.
-// The approximate SFU functions have absolute errors ~1e-6 on their outputs, far below the statistical
-// resolution of any observable (the reference's two backends, pcg+std::normal_distribution on the CPU
-// and cuRAND XORWOW on the GPU, already differ stream for stream: SURVEY.md 8c).
-__device__ __forceinline__ float bm_radius(uint32_t a) {
-  const float u = __fmaf_rn((float)a, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  float l2;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));  // sqrt(-2 ln u), ln u = ln2 * lg2 u
-  return r;
-}
-__device__ __forceinline__ void box_muller2(uint32_t a, uint32_t b, float &n0, float &n1) {
-  const float r = bm_radius(a);
-  const float ang = (float)b * 1.4629180792671596e-09f;  // 2 pi 2^-32 b
-  n0 = r * __cosf(ang);
-  n1 = r * __sinf(ang);
-}
-__device__ __forceinline__ float box_muller1(uint32_t a, uint32_t b) {
-  return bm_radius(a) * __cosf((float)b * 1.4629180792671596e-09f);
-}
-
 // the same generator with the 20 round keys precomputed (rk[2r] = k0 + r W0, rk[2r+1] = k1 + r W1): when rk lives
 // in the kernel-parameter bank the keys are constant-bank operands of the LOP3s and cost no instructions
 __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
@@ -71,42 +62,59 @@ __device__ __forceinline__ void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint3
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__device__ __forceinline__ void normals_from_words(const uint32_t r[4], double &n0, double &n1, double &n2) {
-  float a, b;
-  box_muller2(r[0], r[1], a, b);
-  const float c = box_muller1(r[2], r[3]);
+// Box-Muller pieces in fp32 on the SFU (MUFU.LG2 / MUFU.SQRT / MUFU.SIN / MUFU.COS); results are exact fp32 values that the
+// callers widen to double
+__device__ __forceinline__ float bm_radius(uint32_t w) {   // sqrt(-2 ln u), u = 2 - 1.(w >> 9) in (0, 1]
+  const float u = 2.0f - __uint_as_float(0x3f800000u | (w >> 9));
+  float l2, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));   // ln u = ln 2 * lg2 u
+  return r;
+}
+__device__ __forceinline__ float bm_angle(uint32_t b16) {   // 2 pi (b + 1/2) / 65536
+  return __fmaf_rn((float)b16, 9.587379924285257e-05f, 4.7936899621426287e-05f);
+}
+struct PairNormals { float e0, e1, e2, o0, o1, o2; };   // the three draws of the even-z and of the odd-z site of a pair
+__device__ __forceinline__ void pair_normals_from_words(const uint32_t w[4], PairNormals &n) {
+  const float r0 = bm_radius(w[0]), r1 = bm_radius(w[1]), r2 = bm_radius(w[2]);
+  const float t0 = bm_angle(w[3] & 0xffffu), t1 = bm_angle(w[3] >> 16), t2 = bm_angle(__byte_perm(w[0], w[1], 0x7740) & 0xffffu);
+  n.e0 = r0 * __cosf(t0); n.e1 = r0 * __sinf(t0);
+  n.e2 = r1 * __cosf(t1); n.o0 = r1 * __sinf(t1);
+  n.o1 = r2 * __cosf(t2); n.o2 = r2 * __sinf(t2);
+}
+// all six draws of the pair whose even-z site has global id `gpair` (pair kernel: a thread owns both sites)
+__device__ __forceinline__ void pair_normals_rk(const unsigned int *__restrict__ rk, unsigned long long step,
+                                                unsigned long long gpair, PairNormals &n) {
+  uint32_t w[4];
+  philox4x32_10_rk((uint32_t)gpair, (uint32_t)(gpair >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, w);
+  pair_normals_from_words(w, n);
+}
+// the three draws of ONE site (kernels with one site per thread, jb_noise): the same Philox call, only this site's half of
+// the transforms.  gpair = global id of the pair's even-z site, odd = this is the pair's odd-z site
+__device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step, unsigned long long gpair, bool odd,
+                                             double &n0, double &n1, double &n2) {
+  uint32_t w[4];
+  philox4x32_10((uint32_t)gpair, (uint32_t)(gpair >> 32), (uint32_t)step, (uint32_t)(step >> 32),
+                (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const float r1 = bm_radius(w[1]), t1 = bm_angle(w[3] >> 16);
+  float a, b, c;
+  if (!odd) {
+    const float r0 = bm_radius(w[0]), t0 = bm_angle(w[3] & 0xffffu);
+    a = r0 * __cosf(t0); b = r0 * __sinf(t0); c = r1 * __cosf(t1);
+  } else {
+    const float r2 = bm_radius(w[2]), t2 = bm_angle(__byte_perm(w[0], w[1], 0x7740) & 0xffffu);
+    a = r1 * __sinf(t1); b = r2 * __cosf(t2); c = r2 * __sinf(t2);
+  }
   n0 = (double)a; n1 = (double)b; n2 = (double)c;
-}
-// the same three draws left in fp32 (they are exact fp32 values; widening later gives identical doubles)
-__device__ __forceinline__ void site_normals_rk_f(const unsigned int *__restrict__ rk, unsigned long long step,
-                                                  unsigned long long gsite, float &n0, float &n1, float &n2);
-
-// three N(0,1) draws for (global site, step): the Langevin white noise of one spin for one Heun step
-// (one draw per step, reused by both stages: solvers/cuda_llg_heun.cu:79, cpu_llg_heun.cc:53-64)
-__device__ __forceinline__ void site_normals(unsigned long long seed, unsigned long long step,
-                                             unsigned long long gsite, double &n0, double &n1, double &n2) {
-  uint32_t r[4];
-  philox4x32_10((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32),
-                (uint32_t)seed, (uint32_t)(seed >> 32), r);
-  normals_from_words(r, n0, n1, n2);
-}
-__device__ __forceinline__ void site_normals_rk(const unsigned int *__restrict__ rk, unsigned long long step,
-                                                unsigned long long gsite, double &n0, double &n1, double &n2) {
-  uint32_t r[4];
-  philox4x32_10_rk((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, r);
-  normals_from_words(r, n0, n1, n2);
-}
-
-__device__ __forceinline__ void site_normals_rk_f(const unsigned int *__restrict__ rk, unsigned long long step,
-                                                  unsigned long long gsite, float &n0, float &n1, float &n2) {
-  uint32_t r[4];
-  philox4x32_10_rk((uint32_t)gsite, (uint32_t)(gsite >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, r);
-  box_muller2(r[0], r[1], n0, n1);
-  n2 = box_muller1(r[2], r[3]);
 }
 
 __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
   return (((unsigned long long)(g.x_begin + x) * g.Ny + y) * g.Nz + z) * g.M + m;
+}
+// the site's three draws through the z-pair it belongs to
+__device__ __forceinline__ void site_normals_at(const JbGeom &g, unsigned long long seed, unsigned long long step, int x, int y, int m, int z,
+                                                double &n0, double &n1, double &n2) {
+  site_normals(seed, step, global_site(g, x, y, m, z & ~1), (z & 1) != 0, n0, n1, n2);
 }
 
 // ---- the per-spin physics ---------------------------------------------------------------------------
@@ -116,7 +124,8 @@ __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x
 // performs the stage update with the step folded into the class constants c_full = -gyro dt, c_half = -gyro dt/2:
 //   STAGE 0 (predictor, :84-101): u = s + dt/2 rhs ; s* = unit(s + dt rhs)   [+ the noise part of rhs*, see corrector_noise_part]
 //   STAGE 1 (corrector, :124-144): s' = unit(u + dt/2 rhs*)       [ = unit(s_old + dt (rhs/2 + rhs*/2)) ]
-//   (stage 1 is always instantiated with THERMAL = false: the predictor has already put the noise part of rhs* into u)
+//   (stored-u data flow: stage 1 runs with THERMAL = false, the predictor has already put the noise part of rhs* into u;
+//    recover_u data flow: stage 1 adds the noise itself)
 // unit() keeps vectors of length <= DBL_EPSILON unchanged (containers/vec3.h:276-283): vacancies stay 0.
 // The LLG right-hand side is linear in the field: rhs(s*, H* + xi) = rhs(s*, H*) + rhs(s*, xi), and rhs(s*, xi) needs only
 // the site's own predictor spin s* and its own noise draw -- both at hand at the end of the predictor.  So the predictor
@@ -155,7 +164,9 @@ __device__ __forceinline__ void recover_u(double px, double py, double pz, doubl
   const double hl = (d > 4.930380657631324e-32) ? 0.5 * nn * r * r : 0.0;   // lambda / 2
   ux = fma(hl, px, 0.5 * ux); uy = fma(hl, py, 0.5 * uy); uz = fma(hl, pz, 0.5 * uz);
 }
-template <int STAGE, bool THERMAL>
+// FOLD: the predictor folds the noise part of the corrector's right-hand side into v (stored-u data flow); without it v is
+// the plain Heun intermediate (and dead code when the caller does not store it: option recover_u)
+template <int STAGE, bool THERMAL, bool FOLD = true>
 __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy, double sz,
                                          double hx, double hy, double hz,
                                          double n0, double n1, double n2,
@@ -187,42 +198,7 @@ __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy,
   const double r = rsqrt_nobranch(n2_);
   const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;
   ox = px * inv; oy = py * inv; oz = pz * inv;
-  if (STAGE == 0 && THERMAL) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
-}
-
-// branch-free variant for kernels that interleave several independent site updates in one basic block
-// (jb_step_fused.cu): UNI selects the uniaxial term at compile time.
-template <int STAGE, bool THERMAL, bool UNI>
-__device__ __forceinline__ void llg_site_nb(const JbClass &c, double sx, double sy, double sz,
-                                            double hx, double hy, double hz,
-                                            double n0, double n1, double n2,
-                                            double ux, double uy, double uz,
-                                            double &ox, double &oy, double &oz, double &vx, double &vy, double &vz) {
-  if (UNI) {  // uniaxial: H = K p (s.a)^(p-1) a   (uniaxial_anisotropy.cc:155-163), here / mu; KpT = 0 when the class has none
-    const double d = c.ax * sx + c.ay * sy + c.az * sz;
-    const double d2 = d * d;
-    double pw = d;
-    pw = (c.power >= 4) ? pw * d2 : pw;
-    pw = (c.power >= 6) ? pw * d2 : pw;
-    const double f = c.KpT * pw;
-    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
-  }
-  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }
-  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;
-  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;
-  const double tx = fma(c.alpha, bx_, ax_), ty = fma(c.alpha, by_, ay_), tz = fma(c.alpha, bz_, az_);
-  double px, py, pz;
-  if (STAGE == 0) {
-    vx = fma(c.c_half, tx, sx); vy = fma(c.c_half, ty, sy); vz = fma(c.c_half, tz, sz);
-    px = fma(c.c_full, tx, sx); py = fma(c.c_full, ty, sy); pz = fma(c.c_full, tz, sz);
-  } else {
-    px = fma(c.c_half, tx, ux); py = fma(c.c_half, ty, uy); pz = fma(c.c_half, tz, uz);
-  }
-  const double n2_ = px * px + py * py + pz * pz;
-  const double r = rsqrt_nobranch(n2_);
-  const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;   // |p| <= DBL_EPSILON: unchanged (containers/vec3.h:276-283)
-  ox = px * inv; oy = py * inv; oz = pz * inv;
-  if (STAGE == 0 && THERMAL) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
+  if (STAGE == 0 && THERMAL && FOLD) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
 }
 
 // store the ghost images of a freshly computed spin (the value for its own cell has been stored by the

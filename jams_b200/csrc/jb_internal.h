@@ -5,7 +5,7 @@
 //   spins are stored SoA in double, one array per component, in a GHOSTED box
 //       index(xp, yp, m, zp) = ((xp * PY + yp) * M + m) * PZ + zp
 //   with xp = x + gx, yp = y + gy, zp = z + oz and ghost depths gx,gy,gz = max |T| of the exchange
-//   template along each axis (twice that for the fused step kernel).  oz (4 by default; 8 / 16 selectable) >= gz keeps every
+//   template along each axis.  oz (4 by default; 8 / 16 selectable) >= gz keeps every
 //   interior run on a 32-byte sector boundary (all stores write whole sectors) with the shortest possible gap between rows, and
 //   TMA boxes start on even columns (a box whose first element is not 16-byte aligned faults).  z is the fastest index (lanes of a warp run along z), the motif index
 //   m sits between y and z so that a warp never mixes motif sites.  Ghost cells hold the periodic
@@ -103,20 +103,35 @@ struct JbStageParams {
   double dt;
 };
 
-// ---- parameter block of the persistent TMA tile kernel (jb_stage_tile.cu) ------------------------------
-// The per-class constants, the template's group offsets and the tiling live in the kernel parameter (constant)
-// bank (kept under the classic 4 KB limit together with the six tensor maps); the exchange template itself
-// (16 B per entry) is copied from global to shared memory once per resident CTA.  "Matrix" data therefore costs
-// 0 B of HBM traffic per spin (the reference streams 12 B per non-zero, containers/sparse_matrix.h:366-379).
+// ---- parameter block of the persistent TMA stage kernel (jb_stage_pair.cu) ------------------------------
+// The per-class constants, the template's group offsets, the x-chunk plan and the tiling live in the kernel parameter
+// (constant) bank; the exchange template itself (16 B per entry) is copied from global to shared memory once per
+// resident CTA.  "Matrix" data therefore costs 0 B of HBM traffic per spin (the reference streams 12 B per non-zero,
+// containers/sparse_matrix.h:366-379).
 #define JB_TILE_MAX_NBR 1024
 #define JB_TILE_MAX_CLASSES 8
 #define JB_TILE_MAX_MOTIF 16
 #define JB_TILE_MAX_GX 3
-#define JB_PAIR_MAX_RING 12   // ring depth limit of the pair kernel (jb_stage_pair.cu)
+#define JB_PAIR_MAX_RING 12   // ring depth limit of the stage kernel
+#define JB_TILE_MAX_CHUNKS 160// x-chunks of the work-item plan
+#define JB_ITEM_RING 16       // item ids in flight between the producer warp and the consumer warps (> JB_PAIR_MAX_RING)
 struct __align__(16) JbTileNbr {
   int delta;   // offset inside a plane of the smem tile: (dy*M + (mj - mi))*BZ + dz
   int d;       // dx + gx: which of the 2 gx + 1 resident planes
   double J;    // scalar coupling divided by mu of the owning motif site: Tesla
+};
+// halo handshake of a slab-decomposed run, done INSIDE the stage kernel (no separate wait / signal launches): the producer
+// thread of an item that loads ghost planes polls this rank's flag for the neighbour's previous stage, and the last consumer
+// warp that finishes the face items of a side publishes this stage's epoch in the neighbour's flag (jb_stage_pair.cu)
+struct JbHalo {
+  unsigned long long *flags;      // this rank's flags: [0] written by the lo neighbour, [1] by the hi neighbour, [2] error
+  unsigned long long *sig_lo;     // the lo neighbour's flag that I write (its [1]), or null
+  unsigned long long *sig_hi;     // the hi neighbour's flag that I write (its [0]), or null
+  unsigned long long wait_epoch;  // both neighbours must have published this epoch before I touch ghost planes
+  unsigned long long signal_epoch;
+  unsigned int *face_count;       // [0] lo, [1] hi: consumer warps that have finished a face item (reset by the last one)
+  unsigned int face_target[2];    // consumer warps x face items per side
+  int enabled;
 };
 struct JbTileParams {
   JbGeom g;
@@ -131,24 +146,15 @@ struct JbTileParams {
   int BY, BZ, gzb;       // tile + halo extent; gzb = gz rounded up to even = z halo of the box (BZ = TZ + 2 gzb)
   int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
   int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
-  int u_tma;             // stage B: u arrives through the TMA ring (1) or by plain global loads (0)
-  int producer_sleep_ns; // back-off of the producer thread while a slot is still in use (0 = poll)
-  int early_release;     // hand the oldest S slot back to the producer right after the gathers instead of at the end of the plane
-  int store_hint;        // 0 = default stores, 1 = st.global.cs (streaming), 2 = st.global.wt, 3 / 4 = L2 evict_first / evict_last policy (pair kernel)
-  int reverse_items;     // walk the work items from the last to the first (stage B: the data stage A wrote last is still in L2)
-  int load_hint;         // pair kernel, TMA loads: 0 = none, 1 = evict_first on u, 2 = + evict_last on S, 3 = evict_first on both
-  int debug_skip;        // timing experiments only: 1 = no compute (TMA pipeline alone), 2 = no stores
-  int noise_warp;        // pair kernel, one-site motifs at T > 0: 0 = every consumer thread draws its own noise, 1 = a dedicated warp draws it one
-                         // plane ahead into a shared-memory ring, 2 = that warp draws the odd-z site of every pair only
-  int recover_u;         // pair kernel: the Heun intermediate is rebuilt from s_n and s* instead of stored (120 B per update)
-  int split_wait;        // wait for the newest S plane only before its first template entry (hides part of the TMA latency)
-  int nbr_split[JB_TILE_MAX_MOTIF];  // [m] -> first entry of nbr[] that reads the newest plane (d == 2 gx)
-  int nbr_odd[JB_TILE_MAX_MOTIF];    // pair kernel: [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
-  // fused step kernel (jb_step_fused.cu): reach of the exchange template per axis (the ghost depths g.gx.. are twice
-  // that), z halo (even) of the s* extent / of the s_n tile, constant field of the corrector stage (time t + dt), Tesla
-  int rx, ry, rz, e1z, e2z;
-  double fT1[JB_TILE_MAX_MOTIF][3];
+  int nbr_odd[JB_TILE_MAX_MOTIF];    // [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
   int n_yt, n_zt, n_cols, n_chunks, n_items;
+  // work queue: items are handed out by an atomic counter in the order of this plan; item = chunk * n_cols + column.  The plan
+  // lists the slab's two face chunks first (their halo traffic and flags go out early), then long chunks, then short ones (tail)
+  int chunk_x0[JB_TILE_MAX_CHUNKS], chunk_xc[JB_TILE_MAX_CHUNKS];
+  unsigned int *queue;        // next item of this launch
+  unsigned int *queue_next;   // the counter the next launch on the stream will use: zeroed by this one
+  JbHalo halo;
+  unsigned long long *trace;   // optional: per CTA {smid, first clock, last clock, items} (option "trace")
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
   int nbr_begin[JB_TILE_MAX_MOTIF + 1];  // [m] -> first entry of nbr[]
@@ -203,18 +209,16 @@ struct jb_ctx {
   bool iso = true;
   bool tables_built = false;
 
-  // tiling of the persistent TMA kernel (jb_capi.cu choose_tiling) and its parameter-bank tables
+  // tiling of the persistent TMA stage kernel (jb_capi.cu choose_tiling) and its parameter-bank tables
   struct Tiling {
     bool ok = false;
-    int TY = 0, TZ = 0, UZ = 0, SPT = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
-    int pair = 0;                         // 1 = pair kernel (jb_stage_pair.cu): a thread owns two z-adjacent sites
-    int fused = 0;                        // 1 = fused step kernel (jb_step_fused.cu): predictor + corrector in one launch
-    int e1z = 0, e2z = 0, halo_warps = 0, uni = 0;
-    int Rs[2] = {0, 0};                   // ring depth per stage (the pair kernel spends the shared memory stage B needs for u on a deeper ring in stage A)
-    int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, u_tma = 1;
+    int TY = 0, TZ = 0, UZ = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
+    int Rs[2] = {0, 0};                   // ring depth per stage
+    int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0;
     size_t smem[2] = {0, 0};              // per stage
-    int grid[2][2] = {{0, 0}, {0, 0}};    // [stage][thermal], 0 = not determined yet
-    int n_chunks[2][2] = {{0, 0}, {0, 0}};
+    // launch shape per kernel variant [stage][thermal][recover_u]: resident CTAs and the x-chunk plan (0 = not determined yet)
+    struct Shape { int grid = 0, n_chunks = 0, face_items[2] = {0, 0}; int x0[JB_TILE_MAX_CHUNKS], xc[JB_TILE_MAX_CHUNKS]; };
+    Shape shape[2][2][2];
   } tiling;
   bool tiling_valid = false;
   std::vector<int> tile_order, tile_jidx;   // template entries in table order / their unique-tensor ids
@@ -236,21 +240,21 @@ struct jb_ctx {
   double *h_pinned = nullptr; size_t h_pinned_bytes = 0;
 
   // TMA descriptors: [0] = S0 x,y,z  [1] = S1 x,y,z (tile + halo boxes)  [2] = U x,y,z (tile boxes)
-  // [3] = S0, [4] = S1 with the tile box of U (pair kernel, recover_u: the corrector reads the site's own s_n)
+  // [3] = S0, [4] = S1 with the tile box of U (recover_u: the corrector reads the site's own s_n)
   CUtensorMap tmap[5][3];
   bool tmap_valid = false;
 
   // options
-  int opt_kernel = 2;      // 0 = direct global gathers, 1 = persistent TMA tile kernel (one site per thread), 2 = pair kernel (default),
-                           // 3 = fused step kernel where the template allows it (else 2)
+  int opt_kernel = 2;      // 0 = direct global gathers, 2 = TMA pair kernel where the template allows it (default)
   int reach[3] = {0, 0, 0};   // max |T| of the exchange template per axis
-  bool fused_geometry = false; // ghost depths are 2 x reach (what the fused step kernel needs)
-  int opt_TY = 0, opt_TZ = 0, opt_SPT = 0, opt_R = 0, opt_RU = 0, opt_chunks = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
-  int opt_u_tma = 1, opt_producer_sleep = 0, opt_split_wait = 0, opt_verbose = 0, opt_debug_skip = 0, opt_early_release = 1, opt_store_hint = 0, opt_load_hint = 0, opt_reverse_b = 0;
-  int opt_smem_pad = 0;
-  int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernels (0 = occupancy x SMs)
-  int opt_noise_warp = 0;     // pair kernel: see JbTileParams::noise_warp
-  int opt_recover_u = 2;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B), 2 = 1 at T = 0, 0 at T > 0
+  int opt_TY = 0, opt_TZ = 0, opt_R = 0, opt_RU = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
+  int opt_chunks = 0;         // x-chunk plan: 0 = heuristic (long chunks + a tail of short ones), n > 0 = n equal chunks
+  int opt_chunk_long = 0, opt_chunk_short = 0, opt_tail_pct = -1;   // heuristic overrides: planes per long / short chunk, share of the planes in short chunks
+  int opt_verbose = 0;
+  int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernel (0 = occupancy x SMs)
+  int opt_recover_u = 1;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B)
+  int opt_trace = 0;          // per-CTA {SM, first clock, last clock, items} of the last stage launch (jb_last_trace)
+  int opt_fold_halo = 1;      // slab-decomposed runs: epoch handshake inside the stage kernel (1; 2 = even when a neighbour shares this GPU) or as separate wait / signal launches (0)
   int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows
   bool state_relayout = false; // an option that changes the box layout was set: re-layout at the next ensure_ready
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
@@ -267,9 +271,15 @@ struct jb_ctx {
   void *slab = nullptr; size_t slab_bytes = 0;   // single allocation holding S0,S1 and flags (one IPC handle)
   unsigned long long epoch = 0;
   bool halo_connected = false;
+  bool peer_on_my_device = false;   // a neighbour slab of this process lives on the same GPU (tests)
 
   // regions of spins (jb_set_region): device copies of the site lists
   int *d_region[JB_MAX_REGIONS] = {nullptr}; int region_n[JB_MAX_REGIONS] = {0};
+
+  // work queue and face counters of the stage kernel: {queue[2], face_count[2]} unsigned ints, zeroed once
+  unsigned int *d_queue = nullptr;
+  unsigned long long stage_launches = 0;   // parity selects which of the two queue counters a launch uses
+  unsigned long long *d_trace = nullptr; int trace_ctas = 0;
 
   // bookkeeping
   long long launches = 0;
@@ -285,21 +295,11 @@ cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t str
 // one of the four RK4 stages (stage 0..3), direct gathers: in = stage input (with neighbours), out = next stage input
 // (stages 0-2) or the new spins (stage 3), u = running sum of the k's, s_old = spins at the start of the step
 cudaError_t jbk_rk4_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
-// persistent TMA tile kernel: tmaps = {S.x, S.y, S.z, U.x, U.y, U.z}; spt in {1,2,4}; grid = number of CTAs
-// `threads` counts the consumer threads; the launch adds one producer warp
-cudaError_t jbk_stage_tile(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
+// persistent TMA stage kernel (jb_stage_pair.cu): tmaps = {S.x, S.y, S.z, U.x, U.y, U.z}; grid = number of resident CTAs;
+// `threads` = consumer threads = ceil(TZ/2) x TY (the launch adds the producer warp); recu = recover_u data flow
+cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int recu,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
-cudaError_t jbk_stage_tile_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
-                                     size_t smem_bytes, int *blocks_per_sm);
-// fused step kernel (jb_step_fused.cu): tmaps3 = {S_in.x, S_in.y, S_in.z}; one launch = one Heun step
-cudaError_t jbk_step_fused(const JbTileParams &p, const CUtensorMap *tmaps3, int thermal, int iso, int uni, int threads, int halo_warps,
-                           int grid, size_t smem_bytes, cudaStream_t stream);
-cudaError_t jbk_step_fused_occupancy(const JbTileParams &p, int thermal, int iso, int uni, int threads, int halo_warps, size_t smem_bytes,
-                                     int *blocks_per_sm);
-// pair kernel (jb_stage_pair.cu): same contract; `threads` = consumer threads = ceil(TZ/2) x ceil(TY/spt)
-cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int iso, int spt,
-                           int threads, int grid, size_t smem_bytes, cudaStream_t stream);
-cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int spt, int threads,
+cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int recu, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
                             int iso, int stage, cudaStream_t stream);

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
   const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
-  if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+  if (THERMAL) site_normals_at(g, p.seed, p.step, x, y, m, z, n0, n1, n2);
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) rk4_direct_kernel(const __grid_constant__
   }
   if (THERMAL) {   // one draw per step, all four stages (cuda_rk4_base.cu:65)
     double n0, n1, n2;
-    site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+    site_normals_at(g, p.seed, p.step, x, y, m, z, n0, n1, n2);
     hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz);
   }
   // cuda_llg_rk4_kernel.cuh:36-56
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
   const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
-  if (THERMAL) site_normals(p.seed, p.step, global_site(g, x, y, m, z), n0, n1, n2);
+  if (THERMAL) site_normals_at(g, p.seed, p.step, x, y, m, z, n0, n1, n2);
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
@@ -515,7 +515,7 @@ __global__ void noise_kernel(const JbGeom g, const JbTables t, unsigned long lon
   int x, y, m, z;
   decode_site(g, q, x, y, m, z);
   double n0, n1, n2;
-  site_normals(seed, step, global_site(g, x, y, m, z), n0, n1, n2);
+  site_normals_at(g, seed, step, x, y, m, z, n0, n1, n2);
   double sc = 1.0;
   if (!normals_only) {
     const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];

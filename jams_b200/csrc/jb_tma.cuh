@@ -1,5 +1,4 @@
-// jb_tma.cuh — sm_100a building blocks shared by the persistent stage kernels (jb_stage_tile.cu, jb_stage_pair.cu,
-// jb_step_fused.cu): mbarrier full/empty handshakes, 3-D TMA loads (cp.async.bulk.tensor), shared-memory accesses by
+// jb_tma.cuh — sm_100a building blocks of the persistent stage kernel (jb_stage_pair.cu): mbarrier full/empty handshakes, 3-D TMA loads (cp.async.bulk.tensor), shared-memory accesses by
 // 32-bit shared address (always LDS / STS, never a generic LD), 16-byte global stores and the work-item geometry.
 #ifndef JB_TMA_CUH
 #define JB_TMA_CUH
@@ -22,21 +21,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// wait with a software back-off between polls (jb_stage_tile.cu)
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  uint32_t ok = 0;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (ns) __nanosleep(ns);
-  }
-}
 // wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires) instead of
 // returning after a short default time-out.  A spinning try_wait + branch pair was 18 % of all issued instructions in the
 // T = 100 K profile of the pair kernel (profiles/README.md r01g).
@@ -57,18 +41,6 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar, unsigned long long pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(pol)
-      : "memory");
-}
-__device__ __forceinline__ unsigned long long make_policy(int kind) {   // 0 evict_first, 1 evict_last
-  unsigned long long pol;
-  if (kind == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
 }
 __device__ __forceinline__ double2 lds128(uint32_t a) {
   double2 v;
@@ -96,15 +68,6 @@ __device__ __forceinline__ void sts128(uint32_t a, double x, double y) {
 __device__ __forceinline__ void stg128(double *ptr, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
 }
-// store with a cache hint (experiments on how the write-back stream reaches DRAM): 1 = streaming (.cs), 2 = write-through
-// (.wt), 3 = L2 evict_first policy, 4 = L2 evict_last policy; pol = the createpolicy value for 3 / 4
-__device__ __forceinline__ void stg128_hint(double *ptr, double a, double b, int hint, unsigned long long pol) {
-  if (hint == 1) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
-  else if (hint == 2) asm volatile("st.global.wt.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
-  else if (hint >= 3) asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(ptr), "d"(a), "d"(b), "l"(pol) : "memory");
-  else stg128(ptr, a, b);
-}
-
 // ghost images of a boundary site, general case (x / y faces and their edges; rare, out of line).  The parameter block
 // is __grid_constant__, so its address can be handed over without a local copy: no stack frame in the kernels.
 static __device__ __noinline__ void tile_store_images(const JbTileParams &p, int x, int y, int m, int z, double vx, double vy, double vz) {
@@ -114,7 +77,7 @@ static __device__ __noinline__ void tile_store_images(const JbTileParams &p, int
   store_images_inline(p.g, boxes, x, y, m, z, vx, vy, vz);
 }
 
-// work item = (x-chunk, yz-column tile)
+// work item = (x-chunk, yz-column tile); the chunk plan lives in the parameter bank (jb_capi.cu plan_chunks)
 struct ItemGeom { int y0, z0, x0, xc; };
 
 __device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
@@ -122,8 +85,8 @@ __device__ __forceinline__ ItemGeom item_geom(const JbTileParams &p, int item) {
   const int chunk = item / p.n_cols, col = item - chunk * p.n_cols;
   const int yt = col / p.n_zt, zt = col - yt * p.n_zt;
   it.y0 = yt * p.TY; it.z0 = zt * p.TZ;
-  it.x0 = (int)(((long long)chunk * p.g.nx) / p.n_chunks);
-  it.xc = (int)(((long long)(chunk + 1) * p.g.nx) / p.n_chunks) - it.x0;
+  it.x0 = p.chunk_x0[chunk];
+  it.xc = p.chunk_xc[chunk];
   return it;
 }
 
