@@ -232,9 +232,11 @@ JB_API int jb_set_option(jb_ctx *ctx, const char *key, int64_t value);
  * long chunks, a taper of short ones); capacity >= 160.  Exposed so that tests can check coverage and ordering on the CPU. */
 JB_API int jb_plan_work_items(int32_t nx_local, int32_t ghost_x, int32_t n_columns, int32_t n_ctas, int32_t capacity,
                               int32_t *n_chunks, int32_t *x0, int32_t *xc);
-/* with option "trace" = 1: per resident CTA of the most recent stage-kernel launch {SM id, first / last device clock in ns,
- * work items taken} (4 x uint64 per CTA, at most `capacity` CTAs) -- the load-balance evidence in profiles/.  Synchronises. */
-JB_API int jb_last_stage_trace(jb_ctx *ctx, uint64_t *out4, int32_t capacity, int32_t *n_ctas);
+/* with option "trace" = 1: per resident CTA of the most recent stage-kernel launch 32 x uint64: {SM id, first / last device
+ * clock in ns, work items taken, then per item (item id << 40 | start in ns after the CTA's first clock)}, at most
+ * `capacity` CTAs -- the load-balance evidence in profiles/.  Synchronises. */
+#define JB_TRACE_WORDS_PER_CTA 32
+JB_API int jb_last_stage_trace(jb_ctx *ctx, uint64_t *out, int32_t capacity, int32_t *n_ctas);
 
 #ifdef __cplusplus
 }

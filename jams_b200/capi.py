@@ -304,8 +304,9 @@ class Context:
         self._ck(self.lib.jb_synchronize(self.h))
 
     def last_stage_trace(self, capacity=4096):
-        """option trace = 1: per resident CTA of the last stage launch (SM id, first clock ns, last clock ns, items taken)"""
-        out = np.zeros((capacity, 4), dtype=np.uint64)
+        """option trace = 1: per resident CTA of the last stage launch (SM id, first clock ns, last clock ns, items taken, then per
+        item: item id << 40 | start ns after the CTA's first clock)"""
+        out = np.zeros((capacity, 32), dtype=np.uint64)
         n = C.c_int32(0)
         self._ck(self.lib.jb_last_stage_trace(self.h, _ptr(out), int(capacity), C.byref(n)))
         return out[:n.value].copy()

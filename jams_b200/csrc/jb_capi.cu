@@ -98,8 +98,8 @@ int ensure_queue(jb_ctx *c) {
     c->stage_launches = 0;
   }
   if (c->opt_trace && !c->d_trace) {
-    JB_CUDA(c, cudaMalloc(&c->d_trace, 4096 * 4 * sizeof(unsigned long long)));
-    JB_CUDA(c, cudaMemsetAsync(c->d_trace, 0, 4096 * 4 * sizeof(unsigned long long), c->stream));
+    JB_CUDA(c, cudaMalloc(&c->d_trace, 4096 * JB_TRACE_WORDS * sizeof(unsigned long long)));
+    JB_CUDA(c, cudaMemsetAsync(c->d_trace, 0, 4096 * JB_TRACE_WORDS * sizeof(unsigned long long), c->stream));
   }
   return JB_OK;
 }
@@ -366,7 +366,7 @@ void choose_tiling(jb_ctx *c) {
   c->tiling = t;
   c->tiling_valid = true;
   c->tmap_valid = false;
-  const int n_nbr = (int)c->t_mi.size();
+  int n_nbr = (int)c->t_mi.size();
   if (c->opt_kernel < 1 || !c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
   {
@@ -441,7 +441,6 @@ void choose_tiling(jb_ctx *c) {
   c->tiling = t;
 
   // tile-relative neighbour table, per motif site in the reference's CSR column order; couplings in Tesla
-  c->tile_nbr.assign(n_nbr, JbTileNbr{});
   c->tile_nbr_begin.assign(g.M + 1, 0);
   std::vector<double> J9T(9 * (size_t)std::max(1, n_nbr));
   // pair kernel: within a motif site the entries with an even z offset come first (their neighbour pair is 16-byte
@@ -452,20 +451,28 @@ void choose_tiling(jb_ctx *c) {
     return (c->t_T[3 * a + 2] & 1) < (c->t_T[3 * b + 2] & 1);
   });
   c->tile_nbr_odd.assign(g.M + 1, 0);
+  c->tile_zself.assign(2 * (size_t)g.M, 0.0);
+  c->tile_nbr.clear();
   for (int pos = 0; pos < n_nbr; ++pos) {
     const int k = order[pos];
     const int mi = c->t_mi[k], mj = c->t_mj[k];
     const int Tx = c->t_T[3 * k], Ty = c->t_T[3 * k + 1], Tz = c->t_T[3 * k + 2];
     const double inv_mu = c->h_classes[c->class_of_motif[mi]].inv_mu;
+    if (c->iso && Tx == 0 && Ty == 0 && mi == mj && (Tz == 1 || Tz == -1)) {   // the other site of the pair / its z neighbour: no table entry
+      c->tile_zself[2 * mi + (Tz > 0 ? 1 : 0)] = c->t_J9[9 * k] * inv_mu;
+      continue;
+    }
     if (!(Tz & 1)) c->tile_nbr_odd[mi]++;   // number of even entries for now
     JbTileNbr e{};
     e.delta = (Ty * g.M + (mj - mi)) * t.BZ + Tz;
     e.d = Tx + g.gx;
     e.J = c->t_J9[9 * k] * inv_mu;
-    for (int q = 0; q < 9; ++q) J9T[9 * (size_t)pos + q] = c->t_J9[9 * (size_t)k + q] * inv_mu;
-    c->tile_nbr[pos] = e;
+    const size_t at = c->tile_nbr.size();
+    for (int q = 0; q < 9; ++q) J9T[9 * at + q] = c->t_J9[9 * (size_t)k + q] * inv_mu;
+    c->tile_nbr.push_back(e);
     c->tile_nbr_begin[mi + 1]++;
   }
+  n_nbr = (int)c->tile_nbr.size();
   for (int q = 0; q < g.M; ++q) c->tile_nbr_begin[q + 1] += c->tile_nbr_begin[q];
   for (int q = 0; q < g.M; ++q) c->tile_nbr_odd[q] += c->tile_nbr_begin[q];   // -> first odd entry
   if (c->d_tile_nbr) cudaFree(c->d_tile_nbr);
@@ -487,7 +494,11 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
-  for (int q = 0; q < c->g.M; ++q) p.nbr_odd[q] = c->tile_nbr_odd[q];
+  for (int q = 0; q < c->g.M; ++q) {
+    p.nbr_odd[q] = c->tile_nbr_odd[q];
+    p.zself[q][0] = c->tile_zself[2 * q]; p.zself[q][1] = c->tile_zself[2 * q + 1];
+    p.has_zself[q] = (p.zself[q][0] != 0.0 || p.zself[q][1] != 0.0) ? 1 : 0;
+  }
   p.nbr = c->d_tile_nbr;
   p.n_nbr = (int)c->tile_nbr.size();
 }
@@ -1479,13 +1490,14 @@ int jb_plan_work_items(int32_t nx_local, int32_t ghost_x, int32_t n_columns, int
   return JB_OK;
 }
 
-int jb_last_stage_trace(jb_ctx *c, uint64_t *out4, int32_t capacity, int32_t *n_ctas) {
+int jb_last_stage_trace(jb_ctx *c, uint64_t *out, int32_t capacity, int32_t *n_ctas) {
+  uint64_t *out4 = out;
   if (!c || !out4 || !n_ctas || capacity < 0) return JB_ERR_INVALID;
   *n_ctas = 0;
   if (!c->d_trace) return JB_OK;
   JB_CUDA(c, cudaStreamSynchronize(c->stream));
   const int n = std::min(std::min((int)capacity, c->trace_ctas), 4096);
-  JB_CUDA(c, cudaMemcpy(out4, c->d_trace, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  JB_CUDA(c, cudaMemcpy(out4, c->d_trace, (size_t)n * JB_TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   *n_ctas = n;
   return JB_OK;
 }

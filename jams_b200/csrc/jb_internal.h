@@ -114,6 +114,8 @@ struct JbStageParams {
 #define JB_TILE_MAX_GX 3
 #define JB_PAIR_MAX_RING 12   // ring depth limit of the stage kernel
 #define JB_TILE_MAX_CHUNKS 160// x-chunks of the work-item plan
+#define JB_TRACE_WORDS 32     // per-CTA trace record: {SM, first ns, last ns, items, then (item << 40 | start ns - first) per item}
+#define JB_TRACE_ITEMS (JB_TRACE_WORDS - 4)
 #define JB_ITEM_RING 16       // item ids in flight between the producer warp and the consumer warps (> JB_PAIR_MAX_RING)
 struct __align__(16) JbTileNbr {
   int delta;   // offset inside a plane of the smem tile: (dy*M + (mj - mi))*BZ + dz
@@ -147,6 +149,10 @@ struct JbTileParams {
   int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
   int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
   int nbr_odd[JB_TILE_MAX_MOTIF];    // [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
+  // isotropic templates: the couplings (Tesla) of the entries (0, 0, -1) and (0, 0, +1) to the same motif site are taken out of
+  // the table -- one of the two neighbours of each site of a pair is the other site of the pair, already in registers
+  double zself[JB_TILE_MAX_MOTIF][2];
+  int has_zself[JB_TILE_MAX_MOTIF];
   int n_yt, n_zt, n_cols, n_chunks, n_items;
   // work queue: items are handed out by an atomic counter in the order of this plan; item = chunk * n_cols + column.  The plan
   // lists the slab's two face chunks first (their halo traffic and flags go out early), then long chunks, then short ones (tail)
@@ -154,7 +160,7 @@ struct JbTileParams {
   unsigned int *queue;        // next item of this launch
   unsigned int *queue_next;   // the counter the next launch on the stream will use: zeroed by this one
   JbHalo halo;
-  unsigned long long *trace;   // optional: per CTA {smid, first clock, last clock, items} (option "trace")
+  unsigned long long *trace;   // optional: per CTA JB_TRACE_WORDS words (option "trace")
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
   int nbr_begin[JB_TILE_MAX_MOTIF + 1];  // [m] -> first entry of nbr[]
@@ -227,6 +233,7 @@ struct jb_ctx {
   JbTileNbr *d_tile_nbr = nullptr;
   double *d_tile_J9T = nullptr;
   std::vector<int> tile_nbr_begin, tile_nbr_odd;
+  std::vector<double> tile_zself;   // [m][2], see JbTileParams::zself
   int num_sms = 0;
 
   // state: ghosted SoA arrays

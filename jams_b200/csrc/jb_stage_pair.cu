@@ -73,6 +73,35 @@ __device__ __noinline__ void halo_face_done(const JbHalo &h, int side) {
   }
 }
 
+// store a freshly computed pair (sites z, z + 1 of one row) at element index `idx` of a box, together with the periodic z
+// images of its sites (zsh0 / zsh1: index shift of the image inside the row, 0 = none)
+__device__ __forceinline__ void put_pair(double *const *box, long long idx, bool ok0, bool ok1, int zsh0, int zsh1,
+                                         const double2 &ox, const double2 &oy, const double2 &oz) {
+  if (ok1) {          // both sites: 16-byte stores
+    stg128(&box[0][idx], ox.x, ox.y); stg128(&box[1][idx], oy.x, oy.y); stg128(&box[2][idx], oz.x, oz.y);
+  } else if (ok0) {   // odd Nz: the last pair of a row holds one site
+    box[0][idx] = ox.x; box[1][idx] = oy.x; box[2][idx] = oz.x;
+  }
+  if (zsh0 != 0) { box[0][idx + zsh0] = ox.x; box[1][idx + zsh0] = oy.x; box[2][idx + zsh0] = oz.x; }
+  if (zsh1 != 0) { box[0][idx + 1 + zsh1] = ox.y; box[1][idx + 1 + zsh1] = oy.y; box[2][idx + 1 + zsh1] = oz.y; }
+}
+
+// x-face planes (two per slab and stage): the pair and all its y / z images once more, into the box that holds the x image --
+// this slab's own box on one GPU, the neighbour's box (peer memory over NVLink) in a slab-decomposed run
+static __device__ __noinline__ void put_pair_x_images(const JbTileParams &p, int x, long long idx, long long ysh, bool ok0, bool ok1,
+                                                      int zsh0, int zsh1, double2 ox, double2 oy, double2 oz) {
+  const JbGeom &g = p.g;
+  const long long span = (long long)g.nx * g.sX;
+  if (x < g.gx && p.out_lo[0] != nullptr) {
+    put_pair(p.out_lo, idx + span, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+    if (ysh != 0) put_pair(p.out_lo, idx + span + ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+  }
+  if (x >= g.nx - g.gx && p.out_hi[0] != nullptr) {
+    put_pair(p.out_hi, idx - span, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+    if (ysh != 0) put_pair(p.out_hi, idx - span + ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+  }
+}
+
 template <int STAGE, bool THERMAL, bool ISO, bool MOTIF1, bool RECU>
 __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
@@ -211,13 +240,17 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
     const int item = items[qi];
     qi = (qi + 1) & (JB_ITEM_RING - 1);
     if (item < 0) break;
+    if (p.trace && tid == 0 && n_done < JB_TRACE_ITEMS)   // item id and start time relative to the CTA's first clock
+      p.trace[(unsigned long long)JB_TRACE_WORDS * blockIdx.x + 4 + n_done] = ((unsigned long long)item << 40) | ((global_timer_ns() - t_first) & 0xffffffffffull);
     ++n_done;
     const ItemGeom it = item_geom(p, item);
     const int z = it.z0 + 2 * zp;                         // first site of the pair; the second is z + 1
     const int y = it.y0 + ty;
     const bool row = !padding && y < g.Ny;
     const bool ok0 = row && z < g.Nz, ok1 = row && z + 1 < g.Nz;
-    const bool ygen = g.per[1] && ((y < g.gy) | (y >= g.Ny - g.gy));
+    // periodic y image of the row: index shift, 0 = none (ensure_ready guarantees Ny >= 2 gy + 1 for periodic y)
+    int ysh = 0;
+    if (g.per[1] && row) ysh = (y < g.gy) ? g.Ny * (int)g.sY : ((y >= g.Ny - g.gy) ? -g.Ny * (int)g.sY : 0);
     // periodic z image of each site of the pair: index shift inside the row, 0 = none (ensure_ready guarantees
     // Nz >= 2 gz + 1 for periodic z, so a site is never on both faces)
     int zsh0 = 0, zsh1 = 0;
@@ -303,6 +336,16 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
             hz.x += J6 * a0 + J7 * b0 + J8 * d0; hz.y += J6 * a1 + J7 * b1 + J8 * d1;
           }
         }
+        if (ISO && p.has_zself[MOTIF1 ? 0 : m]) {
+          // the z neighbours inside the row: site z + 1 is the pair's other site (registers), likewise z for site z + 1; only
+          // z - 1 and z + 2 come from shared memory (one LDS.64 per component each instead of two)
+          const double Jm = p.zself[MOTIF1 ? 0 : m][0], Jp = p.zself[MOTIF1 ? 0 : m][1];
+          const double lx = lds64(a - 8u), ly = lds64(a + cs8 - 8u), lz = lds64(a + 2 * cs8 - 8u);
+          const double rx = lds64(a + 16u), ry = lds64(a + cs8 + 16u), rz = lds64(a + 2 * cs8 + 16u);
+          hx.x = fma(Jm, lx, hx.x); hx.x = fma(Jp, sx.y, hx.x); hx.y = fma(Jm, sx.x, hx.y); hx.y = fma(Jp, rx, hx.y);
+          hy.x = fma(Jm, ly, hy.x); hy.x = fma(Jp, sy.y, hy.x); hy.y = fma(Jm, sy.x, hy.y); hy.y = fma(Jp, ry, hy.y);
+          hz.x = fma(Jm, lz, hz.x); hz.x = fma(Jp, sz.y, hz.x); hz.y = fma(Jm, sz.x, hz.y); hz.y = fma(Jp, rz, hz.y);
+        }
         // early release: the oldest S plane (at the end of an item: all resident planes) is only read by the gathers
         // above, so its slot can go back to the producer while this warp still does the per-site physics
         if (m == M - 1) {
@@ -331,21 +374,15 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         llg_site<STAGE, THERMAL, !RECU>(c, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, THERMAL ? (double)nz.o0 : 0.0, THERMAL ? (double)nz.o1 : 0.0,
                                         THERMAL ? (double)nz.o2 : 0.0, ux.y, uy.y, uz.y, ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
         const int idx = ic + m * g.PZ;
-        if (ok1) {          // both sites: 16-byte stores
-          if (STAGE == 0 && !RECU) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
-          stg128(&p.out[0][idx], ox.x, ox.y); stg128(&p.out[1][idx], oy.x, oy.y); stg128(&p.out[2][idx], oz.x, oz.y);
-        } else if (ok0) {   // odd Nz: the last pair of a row holds one site
-          if (STAGE == 0 && !RECU) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
-          p.out[0][idx] = ox.x; p.out[1][idx] = oy.x; p.out[2][idx] = oz.x;
+        if (STAGE == 0 && !RECU) {   // the Heun intermediate: interior only, no images
+          if (ok1) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
+          else if (ok0) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
         }
-        if (!(xb | ygen)) {
-          // only a z face: its periodic image sits in the same row
-          if (zsh0 != 0) { p.out[0][idx + zsh0] = ox.x; p.out[1][idx + zsh0] = oy.x; p.out[2][idx + zsh0] = oz.x; }
-          if (zsh1 != 0) { p.out[0][idx + 1 + zsh1] = ox.y; p.out[1][idx + 1 + zsh1] = oy.y; p.out[2][idx + 1 + zsh1] = oz.y; }
-        } else {
-          if (ok0) tile_store_images(p, x, y, m, z, ox.x, oy.x, oz.x);
-          if (ok1) tile_store_images(p, x, y, m, z + 1, ox.y, oy.y, oz.y);
-        }
+        // the new spins and their ghost images: z images sit in the same row, the y image of a face row one lattice height away,
+        // x images (two planes per slab) in the lo / hi box
+        put_pair(p.out, idx, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+        if (ysh != 0) put_pair(p.out, idx + ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
+        if (xb) put_pair_x_images(p, x, idx, ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
       }
       if (STAGE == 1) {   // this warp is done with the u plane
         __syncwarp();
@@ -368,7 +405,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
   if (p.trace && tid == 0) {
     unsigned int smid;
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    unsigned long long *t = p.trace + 4ull * blockIdx.x;
+    unsigned long long *t = p.trace + (unsigned long long)JB_TRACE_WORDS * blockIdx.x;
     t[0] = smid; t[1] = t_first; t[2] = global_timer_ns(); t[3] = (unsigned long long)n_done;
   }
 }

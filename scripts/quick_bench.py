@@ -20,10 +20,12 @@ except Exception:
     pass
 
 
-def trace_summary(ctx, tag):
+def trace_summary(ctx, tag, dump=None):
     t = ctx.last_stage_trace()
     if len(t) == 0:
         return
+    if dump:
+        np.save(dump, t)
     busy = (t[:, 2] - t[:, 1]).astype(np.float64) * 1e-3   # us
     span = float(t[:, 2].max() - t[:, 1].min()) * 1e-3
     items = t[:, 3].astype(np.int64)
@@ -53,7 +55,10 @@ def run(dims, options, T, steps, label, trace):
     print(f"{label:60s} T={T:5.0f}: A {ms[0]/steps:.4f} ms  B {ms[1]/steps:.4f} ms  wall/step {wall/steps*1e3:.4f} ms "
           f"-> {rate/1e9:6.2f} G upd/s = {rate*144/PEAK*100:5.1f}% of HBM roofline (144 B model)", flush=True)
     if trace:
-        trace_summary(s.ctx, "last launch (stage B)")
+        dump = None
+        if os.environ.get("JB_TRACE_DUMP"):
+            dump = os.path.join(os.environ["JB_TRACE_DUMP"], "trace_T%d_%s.npy" % (int(T), "".join(ch if ch.isalnum() else "_" for ch in label)[:60]))
+        trace_summary(s.ctx, "last launch (stage B)", dump)
     s.ctx.close()
 
 

@@ -1,5 +1,6 @@
-"""Development helper: tile kernel vs direct kernel on a small lattice (each option set in its own process)."""
-import json, os, subprocess, sys
+"""Development helper for compute-sanitizer runs: TMA stage kernel vs direct kernel on a small ragged lattice.
+    python scripts/sanity_tile.py '<json options>' <T>"""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
@@ -16,10 +17,4 @@ def one(opts, T):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
-        one(json.loads(sys.argv[1]), float(sys.argv[2]))
-        sys.exit(0)
-    for opts in (dict(kernel=3, row_offset=4), dict(kernel=3, row_offset=8), dict(kernel=2, row_offset=4), dict(kernel=2, row_offset=8), dict(kernel=1, row_offset=8), dict(kernel=3), dict(kernel=3, tile_y=4, tile_z=32), dict(kernel=3, tile_y=3, tile_z=8, ring=4), dict(kernel=2), dict(kernel=2, spt=2), dict(kernel=2, tile_y=3, tile_z=8, ring=4), dict(kernel=2, spt=2, tile_y=8, tile_z=32, ring=9, ring_u=4), dict(kernel=1)):
-        for T in (0.0, 50.0):
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), json.dumps(opts), str(T)], capture_output=True, text=True, timeout=300)
-            print((r.stdout or "").strip() or f"opts {opts} T {T} CRASHED: {(r.stderr or '').strip()[-400:]}", flush=True)
+    one(json.loads(sys.argv[1]), float(sys.argv[2]))
