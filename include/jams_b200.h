@@ -191,6 +191,9 @@ JB_API int jb_energies(jb_ctx *ctx, int32_t term, double time_ps, double *e, int
  * M4[4g..4g+3] = { sum_i mu_i s_i (x,y,z), sum_i mu_i } over the spins of group g in this slab.
  * group_of_spin (N, values in [0,n_groups)) or NULL for a single group. */
 JB_API int jb_magnetisation(jb_ctx *ctx, int32_t n_groups, const int32_t *group_of_spin, double *M4);
+/* The monitor builds its groups once, in its constructor (monitors/magnetisation.cc:21-60): register them here and call
+ * jb_magnetisation with group_of_spin = NULL and the same n_groups afterwards -- no N-long array crosses PCIe per update. */
+JB_API int jb_set_magnetisation_groups(jb_ctx *ctx, int32_t n_groups, const int32_t *group_of_spin);
 
 /* ---- physics hooks that rewrite spins on the device ------------------------------------------ */
 /* PinnedBoundariesPhysics (physics/pinned_boundaries.cc:12-46) keeps the magnetisation direction of an edge region by

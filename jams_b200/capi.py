@@ -57,6 +57,7 @@ SIGNATURES = {
     "jb_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32]),
     "jb_energies": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "jb_magnetisation": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, _dp]),
+    "jb_set_magnetisation_groups": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "jb_halo_export_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jb_halo_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_kernel_launches": (C.c_int64, [C.c_void_p]),
@@ -279,6 +280,11 @@ class Context:
         out = np.zeros((n_groups, 4))
         self._ck(self.lib.jb_magnetisation(self.h, int(n_groups), _ptr(g), out))
         return out
+
+    def set_magnetisation_groups(self, group_of_spin, n_groups):
+        """register the monitor's groups once; afterwards ``magnetisation(None, n_groups)`` uses them"""
+        g = None if group_of_spin is None else np.ascontiguousarray(group_of_spin, np.int32)
+        self._ck(self.lib.jb_set_magnetisation_groups(self.h, int(n_groups), _ptr(g)))
 
     # ---- halo plumbing
     def halo_export_handle(self) -> bytes:

@@ -90,6 +90,13 @@ int ensure_aos(jb_ctx *c) {
   return JB_OK;
 }
 
+int ensure_copy_stream(jb_ctx *c) {
+  if (c->copy_stream) return JB_OK;
+  JB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k <= JB_COPY_CHUNKS; ++k) JB_CUDA(c, cudaEventCreateWithFlags(&c->copy_ev[k], cudaEventDisableTiming));
+  return JB_OK;
+}
+
 // work-queue counters + face counters of the stage kernel, and the optional per-CTA trace buffer
 int ensure_queue(jb_ctx *c) {
   if (!c->d_queue) {
@@ -807,10 +814,12 @@ void jb_destroy(jb_ctx *c) {
   p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
-  p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p);
+  p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p); p = c->d_groups; free_dev(p);
   for (int r = 0; r < JB_MAX_REGIONS; ++r) { p = c->d_region[r]; free_dev(p); }
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   for (auto ev : c->ev) cudaEventDestroy(ev);
+  for (int k = 0; k <= JB_COPY_CHUNKS; ++k) if (c->copy_ev[k]) cudaEventDestroy(c->copy_ev[k]);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1006,14 +1015,29 @@ int jb_set_applied_field_pulse(jb_ctx *c, const double B[3], int32_t type, doubl
 int jb_import_spins(jb_ctx *c, const double *s_aos, int32_t on_device) {
   if (!c || !s_aos) return JB_ERR_INVALID;
   int rc = ensure_ready(c); if (rc) return rc;
-  const double *src = s_aos;
-  if (!on_device) {
-    rc = ensure_aos(c); if (rc) return rc;
-    JB_CUDA(c, cudaMemcpyAsync(c->d_aos, s_aos, (size_t)c->N * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    src = c->d_aos;
-  }
   double *dst[3] = {c->S0[0], c->S0[1], c->S0[2]};
-  JB_CUDA(c, jbk_import(c->g, src, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
+  if (!on_device) {
+    // host memory: x-chunks travel on the copy stream (cudaMemcpyAsync: the copy engine, full PCIe rate from pinned memory)
+    // while the layout kernel of the previous chunk runs on the context's stream; the x ghost planes (periodic images of the
+    // far end of the slab) come last.  globals::s of the reference is exactly such an AoS array (core/lattice.cc:688).
+    rc = ensure_aos(c); if (rc) return rc;
+    rc = ensure_copy_stream(c); if (rc) return rc;
+    const JbGeom &g = c->g;
+    const size_t per_plane = (size_t)g.Ny * g.Nz * g.M * 3;
+    const int nchunk = std::min(JB_COPY_CHUNKS, g.nx);
+    JB_CUDA(c, cudaEventRecord(c->copy_ev[JB_COPY_CHUNKS], c->stream));          // earlier kernels may still read the staging buffer
+    JB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[JB_COPY_CHUNKS], 0));
+    for (int k = 0; k < nchunk; ++k) {
+      const int x0 = (int)((long long)k * g.nx / nchunk), x1 = (int)((long long)(k + 1) * g.nx / nchunk);
+      JB_CUDA(c, cudaMemcpyAsync(c->d_aos + per_plane * x0, s_aos + per_plane * x0, per_plane * (x1 - x0) * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+      JB_CUDA(c, cudaEventRecord(c->copy_ev[k], c->copy_stream));
+      JB_CUDA(c, cudaStreamWaitEvent(c->stream, c->copy_ev[k], 0));
+      JB_CUDA(c, jbk_import_planes(g, c->d_aos, dst, x0, x1, c->stream)); c->launches++;
+    }
+    JB_CUDA(c, jbk_fill_ghosts(g, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
+  } else {
+    JB_CUDA(c, jbk_import(c->g, s_aos, dst, c->d.n_ranks == 1, c->stream)); c->launches += 2;
+  }
   if (c->d.n_ranks > 1 && c->g.gx > 0) {
     if (!c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: call jb_halo_connect before jb_import_spins");
     // neighbours may still be reading my previous ghosts: exchange happens inside an epoch handshake
@@ -1038,8 +1062,19 @@ int jb_export_spins(jb_ctx *c, double *s_aos, int32_t on_device) {
     return JB_OK;
   }
   int rc = ensure_aos(c); if (rc) return rc;
-  JB_CUDA(c, jbk_export(c->g, src, c->d_aos, c->stream)); c->launches++;
-  JB_CUDA(c, cudaMemcpyAsync(s_aos, c->d_aos, (size_t)c->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  rc = ensure_copy_stream(c); if (rc) return rc;
+  // x-chunks: the layout kernel of chunk k + 1 runs while chunk k crosses PCIe on the copy stream
+  const JbGeom &g = c->g;
+  const size_t per_plane = (size_t)g.Ny * g.Nz * g.M * 3;
+  const int nchunk = std::min(JB_COPY_CHUNKS, g.nx);
+  for (int k = 0; k < nchunk; ++k) {
+    const int x0 = (int)((long long)k * g.nx / nchunk), x1 = (int)((long long)(k + 1) * g.nx / nchunk);
+    JB_CUDA(c, jbk_export_planes(g, src, c->d_aos, x0, x1, c->stream)); c->launches++;
+    JB_CUDA(c, cudaEventRecord(c->copy_ev[k], c->stream));
+    JB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[k], 0));
+    JB_CUDA(c, cudaMemcpyAsync(s_aos + per_plane * x0, c->d_aos + per_plane * x0, per_plane * (x1 - x0) * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  JB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   JB_CUDA(c, cudaStreamSynchronize(c->stream));
   return JB_OK;
 }
@@ -1277,6 +1312,19 @@ int jb_energies(jb_ctx *c, int32_t term, double time_ps, double *e, int32_t on_d
   return JB_OK;
 }
 
+int jb_set_magnetisation_groups(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin) {
+  if (!c || n_groups < 1 || (n_groups > 1 && !group_of_spin)) return JB_ERR_INVALID;
+  JB_CUDA(c, cudaSetDevice(c->device));
+  JB_CUDA(c, cudaStreamSynchronize(c->stream));
+  void *p = c->d_groups; free_dev(p); c->d_groups = nullptr; c->n_groups_set = 0;
+  if (n_groups == 1) return JB_OK;
+  for (int i = 0; i < c->N; ++i) if (group_of_spin[i] < 0 || group_of_spin[i] >= n_groups) JB_FAIL(c, JB_ERR_INVALID, "jb_set_magnetisation_groups: group index out of range");
+  JB_CUDA(c, cudaMalloc(&c->d_groups, (size_t)c->N * sizeof(int)));
+  JB_CUDA(c, cudaMemcpy(c->d_groups, group_of_spin, (size_t)c->N * sizeof(int), cudaMemcpyHostToDevice));
+  c->n_groups_set = n_groups;
+  return JB_OK;
+}
+
 int jb_magnetisation(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin, double *M4) {
   if (!c || !M4 || n_groups < 1) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
@@ -1288,6 +1336,10 @@ int jb_magnetisation(jb_ctx *c, int32_t n_groups, const int32_t *group_of_spin, 
   rc = ensure_scratch(c, need + 64); if (rc) return rc;
   double *partial = c->d_scratch, *out4 = c->d_scratch + 4096;
   int *d_groups = nullptr;
+  if (!group_of_spin && n_groups > 1) {   // the groups the monitor registered once (jb_set_magnetisation_groups)
+    if (n_groups != c->n_groups_set) JB_FAIL(c, JB_ERR_INVALID, "jb_magnetisation: no group array given and jb_set_magnetisation_groups was not called for this number of groups");
+    d_groups = c->d_groups;
+  }
   if (group_of_spin) {
     d_groups = reinterpret_cast<int *>(c->d_scratch + 4096 + 4 * n_groups + 2);
     JB_CUDA(c, cudaMemcpyAsync(d_groups, group_of_spin, (size_t)c->N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -1344,8 +1396,18 @@ int jb_rotate_region(jb_ctx *c, int32_t region, const double *R9) {
     else if (c->g.per[0] && c->g.gx > 0) { lo[k] = c->S0[k]; hi[k] = c->S0[k]; }
     else { lo[k] = nullptr; hi[k] = nullptr; }
   }
-  JB_CUDA(c, jbk_region_rotate(c->g, c->S0, lo, hi, c->d_region[region], c->region_n[region], R9, c->stream));
-  c->launches++;
+  // slab-decomposed runs: the rotated ghost images go into the neighbours' boxes, so the call is one more epoch of the halo
+  // handshake -- wait for the neighbours' last stage, rotate, publish.  Every rank calls it for every region (an empty local
+  // region still takes part), exactly as every rank runs every stage.
+  if (multi) { JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++; }
+  if (c->region_n[region] > 0) {
+    JB_CUDA(c, jbk_region_rotate(c->g, c->S0, lo, hi, c->d_region[region], c->region_n[region], R9, c->stream));
+    c->launches++;
+  }
+  if (multi) {
+    c->epoch++;
+    JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+  }
   return JB_OK;
 }
 

@@ -28,6 +28,7 @@
 #define JB_MAX_MOTIF 32
 #define JB_MAX_CLASSES 255
 #define JB_MAX_RING 8
+#define JB_COPY_CHUNKS 8   // x-chunks of the pipelined host <-> device spin transfer
 
 // ---- geometry of the ghosted box ---------------------------------------------------------------
 struct JbGeom {
@@ -245,6 +246,8 @@ struct jb_ctx {
   double *d_aos = nullptr; size_t d_aos_bytes = 0;     // staging for host <-> device AoS
   double *d_scratch = nullptr; size_t d_scratch_bytes = 0;  // per-spin scalars / reductions
   double *h_pinned = nullptr; size_t h_pinned_bytes = 0;
+  cudaStream_t copy_stream = nullptr;      // host <-> device copies of jb_import_spins / jb_export_spins, overlapped with the layout kernels
+  cudaEvent_t copy_ev[JB_COPY_CHUNKS + 1] = {nullptr};
 
   // TMA descriptors: [0] = S0 x,y,z  [1] = S1 x,y,z (tile + halo boxes)  [2] = U x,y,z (tile boxes)
   // [3] = S0, [4] = S1 with the tile box of U (recover_u: the corrector reads the site's own s_n)
@@ -280,6 +283,8 @@ struct jb_ctx {
   bool halo_connected = false;
   bool peer_on_my_device = false;   // a neighbour slab of this process lives on the same GPU (tests)
 
+  int *d_groups = nullptr; int n_groups_set = 0;   // jb_set_magnetisation_groups
+
   // regions of spins (jb_set_region): device copies of the site lists
   int *d_region[JB_MAX_REGIONS] = {nullptr}; int region_n[JB_MAX_REGIONS] = {0};
 
@@ -297,6 +302,11 @@ struct jb_ctx {
 // ---- launchers implemented in jb_kernels.cu (all enqueue on `stream`) -----------------------------
 cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream);
 cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream);
+// the same for the interior planes [x_begin, x_end) only (the host path pipelines x-chunks with the PCIe copies); jbk_import =
+// all planes + jbk_fill_ghosts (ghost cells <- the interior cells they are periodic images of)
+cudaError_t jbk_import_planes(const JbGeom &g, const double *aos, double *const dst[3], int x_begin, int x_end, cudaStream_t stream);
+cudaError_t jbk_fill_ghosts(const JbGeom &g, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream);
+cudaError_t jbk_export_planes(const JbGeom &g, const double *const src[3], double *aos, int x_begin, int x_end, cudaStream_t stream);
 cudaError_t jbk_push_x_ghosts(const JbGeom &g, const double *const src[3], double *const lo[3], double *const hi[3], cudaStream_t stream);
 cudaError_t jbk_stage_direct(const JbStageParams &p, int stage, cudaStream_t stream);
 // one of the four RK4 stages (stage 0..3), direct gathers: in = stage input (with neighbours), out = next stage input

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "jb_device.cuh"
 
 namespace {
@@ -49,46 +51,79 @@ __device__ __forceinline__ long long ref_site_local(const JbGeom &g, int x, int 
 // =================================================================================================
 // import / export between the reference's AoS site order and the ghosted SoA box
 // =================================================================================================
-__global__ void import_kernel(const JbGeom g, const double *__restrict__ aos, double *__restrict__ dx,
-                              double *__restrict__ dy, double *__restrict__ dz, int fill_x_ghosts) {
-  const long long total = g.elems;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    long long r = t;
-    const int zp = (int)(r % g.PZ); r /= g.PZ;
-    const int m = (int)(r % g.M); r /= g.M;
-    const int yp = (int)(r % g.PY);
-    const int xp = (int)(r / g.PY);
-    int x = xp - g.gx, y = yp - g.gy, z = zp - g.oz;
-    bool ok = true;
-    if (x < 0 || x >= g.nx) {
-      // multi-rank: the x ghost planes belong to the neighbours (they push into them); do not touch
-      if (!fill_x_ghosts) continue;
-      if (g.per[0]) x = (x + g.nx) % g.nx; else ok = false;
-    }
-    if (y < 0 || y >= g.Ny) {
-      if (g.per[1] && yp < g.Ny + 2 * g.gy) y = (y + g.Ny) % g.Ny; else ok = false;
-    }
-    if (z < 0 || z >= g.Nz) {
-      if (g.per[2] && z >= -g.gz && z < g.Nz + g.gz) z = (z + g.Nz) % g.Nz; else ok = false;   // padding columns stay 0
-    }
-    double vx = 0.0, vy = 0.0, vz = 0.0;
-    if (ok) {
-      const long long s = ref_site_local(g, x, y, m, z);
-      vx = aos[3 * s]; vy = aos[3 * s + 1]; vz = aos[3 * s + 2];
-    }
-    dx[t] = vx; dy[t] = vy; dz[t] = vz;
+// One block per (x, y, z-chunk of ZC cells): the (z, m) block of a lattice column is contiguous in the reference's AoS order
+// (3 M ZC doubles) and M x 3 contiguous runs of ZC doubles in the SoA box, so both sides of the transposition are coalesced and
+// the permutation happens in shared memory.  Planes [x_begin, x_end) only: the host path pipelines x-chunks with the PCIe copies.
+__global__ void __launch_bounds__(256) import_rows_kernel(const JbGeom g, const double *__restrict__ aos, double *__restrict__ dx,
+                                                          double *__restrict__ dy, double *__restrict__ dz, int x_begin, int n_zc, int ZC) {
+  extern __shared__ double tile[];   // [zz][m][c]
+  const int zc = blockIdx.x % n_zc;
+  const int y = (blockIdx.x / n_zc) % g.Ny;
+  const int x = x_begin + blockIdx.x / (n_zc * g.Ny);
+  const int z0 = zc * ZC, nz = min(ZC, g.Nz - z0);
+  const int n = 3 * g.M * nz;
+  const double *src = aos + 3 * ((((long long)x * g.Ny + y) * g.Nz + z0) * g.M);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = src[i];
+  __syncthreads();
+  double *const d3[3] = {dx, dy, dz};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / (g.M * nz), r = i - c * (g.M * nz);
+    const int m = r / nz, zz = r - m * nz;
+    d3[c][gidx(g, x + g.gx, y + g.gy, m, z0 + zz + g.oz)] = tile[(zz * g.M + m) * 3 + c];
   }
 }
 
-__global__ void export_kernel(const JbGeom g, const double *__restrict__ sx, const double *__restrict__ sy,
-                              const double *__restrict__ sz, double *__restrict__ aos) {
-  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
-  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    int x, y, m, z;
-    decode_site(g, q, x, y, m, z);
-    const long long i = gidx(g, x + g.gx, y + g.gy, m, z + g.oz);
-    const long long s = ref_site_local(g, x, y, m, z);
-    aos[3 * s] = sx[i]; aos[3 * s + 1] = sy[i]; aos[3 * s + 2] = sz[i];
+__global__ void __launch_bounds__(256) export_rows_kernel(const JbGeom g, const double *__restrict__ sx, const double *__restrict__ sy,
+                                                          const double *__restrict__ sz, double *__restrict__ aos, int x_begin, int n_zc, int ZC) {
+  extern __shared__ double tile[];   // [zz][m][c]
+  const int zc = blockIdx.x % n_zc;
+  const int y = (blockIdx.x / n_zc) % g.Ny;
+  const int x = x_begin + blockIdx.x / (n_zc * g.Ny);
+  const int z0 = zc * ZC, nz = min(ZC, g.Nz - z0);
+  const int n = 3 * g.M * nz;
+  const double *const s3[3] = {sx, sy, sz};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i / (g.M * nz), r = i - c * (g.M * nz);
+    const int m = r / nz, zz = r - m * nz;
+    tile[(zz * g.M + m) * 3 + c] = s3[c][gidx(g, x + g.gx, y + g.gy, m, z0 + zz + g.oz)];
+  }
+  __syncthreads();
+  double *dst = aos + 3 * ((((long long)x * g.Ny + y) * g.Nz + z0) * g.M);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = tile[i];
+}
+
+// ghost cells of a freshly imported box: every ghost cell takes the value of the interior cell it is the periodic image of (zero
+// across an open boundary: Lattice::apply_boundary_conditions, core/lattice.cc:987-1007); padding columns are zeroed.  One warp
+// per (xp, yp, m) row.  x ghost planes only with fill_x (on several ranks they belong to the neighbours, who push into them).
+__global__ void __launch_bounds__(256) fill_ghosts_kernel(const JbGeom g, double *__restrict__ dx, double *__restrict__ dy,
+                                                          double *__restrict__ dz, int fill_x) {
+  const long long n_rows = (long long)g.PX * g.PY * g.M;
+  const int lane = threadIdx.x & 31;
+  for (long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; row < n_rows; row += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int m = (int)(row % g.M);
+    const int yp = (int)((row / g.M) % g.PY);
+    const int xp = (int)(row / ((long long)g.M * g.PY));
+    int x = xp - g.gx, y = yp - g.gy;
+    const bool xg = x < 0 || x >= g.nx, yg = y < 0 || y >= g.Ny;
+    if (xg && !fill_x) continue;
+    bool ok = true;
+    if (xg) { if (g.per[0]) x = (x + g.nx) % g.nx; else ok = false; }
+    if (yg) { if (g.per[1]) y = (y + g.Ny) % g.Ny; else ok = false; }
+    const long long dst0 = gidx(g, xp, yp, m, 0);
+    const long long src0 = ok ? gidx(g, x + g.gx, y + g.gy, m, g.oz) : 0;   // z = 0 of the source row
+    const bool ghost_row = xg || yg;
+    for (int zp = lane; zp < g.PZ; zp += 32) {
+      int z = zp - g.oz;
+      const bool zin = z >= 0 && z < g.Nz;
+      if (zin && !ghost_row) continue;   // interior cell: imported
+      bool okz = ok;
+      if (!zin) {
+        if (g.per[2] && z >= -g.gz && z < g.Nz + g.gz) z = (z + g.Nz) % g.Nz; else okz = false;
+      }
+      double vx = 0.0, vy = 0.0, vz = 0.0;
+      if (okz) { vx = dx[src0 + z]; vy = dy[src0 + z]; vz = dz[src0 + z]; }
+      dx[dst0 + zp] = vx; dy[dst0 + zp] = vy; dz[dst0 + zp] = vz;
+    }
   }
 }
 
@@ -560,18 +595,39 @@ cudaError_t launch1d(K kernel, long long total, int threads, cudaStream_t stream
 // =================================================================================================
 // launchers
 // =================================================================================================
+static int rows_zc(const JbGeom &g) { return std::max(1, std::min(g.Nz, 2048 / std::max(1, g.M))); }   // 3 M ZC doubles <= 48 KB of shared memory
+
 cudaError_t jbk_import(const JbGeom &g, const double *aos, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream) {
-  long long blocks = (g.elems + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  import_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, aos, dst[0], dst[1], dst[2], fill_x_ghosts ? 1 : 0);
+  cudaError_t e = jbk_import_planes(g, aos, dst, 0, g.nx, stream);
+  if (e != cudaSuccess) return e;
+  return jbk_fill_ghosts(g, dst, fill_x_ghosts, stream);
+}
+
+cudaError_t jbk_import_planes(const JbGeom &g, const double *aos, double *const dst[3], int x_begin, int x_end, cudaStream_t stream) {
+  if (x_end <= x_begin) return cudaSuccess;
+  const int ZC = rows_zc(g), n_zc = (g.Nz + ZC - 1) / ZC;
+  const long long blocks = (long long)(x_end - x_begin) * g.Ny * n_zc;
+  import_rows_kernel<<<(unsigned)blocks, 256, (size_t)3 * g.M * ZC * sizeof(double), stream>>>(g, aos, dst[0], dst[1], dst[2], x_begin, n_zc, ZC);
+  return cudaGetLastError();
+}
+
+cudaError_t jbk_fill_ghosts(const JbGeom &g, double *const dst[3], bool fill_x_ghosts, cudaStream_t stream) {
+  const long long n_rows = (long long)g.PX * g.PY * g.M;
+  long long blocks = (n_rows + 7) / 8;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  fill_ghosts_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, dst[0], dst[1], dst[2], fill_x_ghosts ? 1 : 0);
   return cudaGetLastError();
 }
 
 cudaError_t jbk_export(const JbGeom &g, const double *const src[3], double *aos, cudaStream_t stream) {
-  const long long total = (long long)g.nx * g.Ny * g.Nz * g.M;
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  export_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, src[0], src[1], src[2], aos);
+  return jbk_export_planes(g, src, aos, 0, g.nx, stream);
+}
+
+cudaError_t jbk_export_planes(const JbGeom &g, const double *const src[3], double *aos, int x_begin, int x_end, cudaStream_t stream) {
+  if (x_end <= x_begin) return cudaSuccess;
+  const int ZC = rows_zc(g), n_zc = (g.Nz + ZC - 1) / ZC;
+  const long long blocks = (long long)(x_end - x_begin) * g.Ny * n_zc;
+  export_rows_kernel<<<(unsigned)blocks, 256, (size_t)3 * g.M * ZC * sizeof(double), stream>>>(g, src[0], src[1], src[2], aos, x_begin, n_zc, ZC);
   return cudaGetLastError();
 }
 

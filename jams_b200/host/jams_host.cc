@@ -937,7 +937,11 @@ std::string MagnetisationMonitor::tsv_header() const {   // monitors/magnetisati
 
 void MagnetisationMonitor::update(B200HeunLLGSolver &solver) {   // monitors/magnetisation.cc:77-104
   std::vector<double> M4(4 * static_cast<size_t>(n_groups_));
-  solver.check(jb_magnetisation(solver.ctx(), n_groups_, group_of_spin_.empty() ? nullptr : group_of_spin_.data(), M4.data()));
+  if (registered_ctx_ != solver.ctx()) {   // the groups are fixed at construction: one upload, not one per update
+    solver.check(jb_set_magnetisation_groups(solver.ctx(), n_groups_, group_of_spin_.empty() ? nullptr : group_of_spin_.data()));
+    registered_ctx_ = solver.ctx();
+  }
+  solver.check(jb_magnetisation(solver.ctx(), n_groups_, nullptr, M4.data()));
   tsv_file_.width(12);
   tsv_file_ << fmt_sci << solver.time();
   tsv_file_ << fmt_sci << solver.physics()->temperature();

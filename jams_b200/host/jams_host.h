@@ -263,6 +263,7 @@ class MagnetisationMonitor : public Monitor {   // monitors/magnetisation.cc:21-
   bool normalize_ = true;
   int n_groups_ = 1;
   std::vector<int32_t> group_of_spin_;
+  const jb_ctx *registered_ctx_ = nullptr;   // context that holds the device copy of group_of_spin_
   std::ofstream tsv_file_;
 };
 

@@ -407,6 +407,7 @@ class MagnetisationMonitor(Monitor):
         if self.grouping not in ("none", "materials", "positions"):
             raise RuntimeError("unknown magnetisation grouping: " + self.grouping)
         self.normalize = bool(settings.get("normalize", True))
+        self._registered = None   # the context whose device copy of the group array is current
 
     def groups(self, solver):
         lat = solver.lattice
@@ -418,8 +419,12 @@ class MagnetisationMonitor(Monitor):
 
     def update(self, solver):
         solver._build()
-        g, ng = self.groups(solver)
-        M4 = solver.reduce_sum(solver.ctx.magnetisation(g, ng))
+        if self._registered is not solver.ctx:   # the groups are fixed at construction (monitors/magnetisation.cc:21-60): upload once
+            g, ng = self.groups(solver)
+            solver.ctx.set_magnetisation_groups(g, ng)
+            self._registered, self._ng = solver.ctx, ng
+        ng = self._ng
+        M4 = solver.reduce_sum(solver.ctx.magnetisation(None, ng))
         row = [solver.time, solver.temperature]
         for n in range(ng):
             mag = M4[n, :3]

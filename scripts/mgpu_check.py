@@ -15,16 +15,60 @@ from jams_b200.distributed import TorchComm
 from jams_b200.solver import MagnetisationMonitor
 
 
+def pinned_boundaries_case(rank, world, local):
+    """pinned_boundaries on a slab-decomposed open-x wall: jb_rotate_region stores rotated ghost images into the neighbours'
+    boxes and must be ordered by the same epoch handshake as the stages; front / back regions span every slab face"""
+    from jams_b200.solver import PinnedBoundariesPhysics
+    w = W.c1_bloch_wall((16 * world, 8, 12))
+    lat = w["lattice"]
+    settings = dict(module="pinned_boundaries", left_pinned_magnetisation=[0, 0, 1.0], right_pinned_magnetisation=[0, 0, -1.0],
+                    front_pinned_magnetisation=[0, 1.0, 0], back_pinned_cells=2, back_pinned_magnetisation=[1.0, 0, 0])
+    comm = TorchComm(periodic_x=False, device=f"cuda:{local}")
+    s = W.make_solver(w, comm=comm, seed=3, device=local)
+    s0 = lat.initial_spins(seed=9)
+    per = lat.num_spins // world
+    s.set_spins(s0[rank * per:(rank + 1) * per])
+    s.register_physics_module(PinnedBoundariesPhysics(settings, lat))
+    for _ in range(8):
+        s.update_physics_module()
+        s.run(1)
+    mine = torch.from_numpy(s.spins()).to(f"cuda:{local}")
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    comm.barrier(s.ctx)
+    ok = True
+    if rank == 0:
+        got = torch.cat(parts).cpu().numpy()
+        single = W.make_solver(w, seed=3, device=local)
+        single.set_spins(s0)
+        single.register_physics_module(PinnedBoundariesPhysics(settings, lat))
+        for _ in range(8):
+            single.update_physics_module()
+            single.run(1)
+        diff = float(np.abs(single.spins() - got).max())
+        ok = diff <= 1e-13   # the all-reduced region moment sums the slabs' partial sums in a different order
+        print(f"mgpu_check[{world} ranks] pinned_boundaries (left/right/front/back) on an open-x wall: max diff = {diff:.3e}, ok = {ok}", flush=True)
+        single.ctx.close()
+    comm.barrier(s.ctx)
+    s.ctx.close()
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    # the T = 0 cases run the pair kernel's recover_u data flow (no stored Heun intermediate, corrector in place); the last case forces it at T > 0
+    # default options: the recover_u data flow with the epoch handshake folded into the stage kernels (two launches per step);
+    # the other cases force the stored-u data flow, the separate wait / signal launches, and a lattice large enough for several
+    # x-chunks, a taper and more work items than resident CTAs per slab
     for name, make, periodic_x, T, steps, opts in (("bcc NN+NNN periodic T=50", lambda: W.c2_bcc_fe(8 * world, temperature=50.0), True, 50.0, 12, None),
                                                    ("sc open-x wall T=0", lambda: W.c1_bloch_wall((16 * world, 8, 40)), False, 0.0, 15, None),
                                                    ("sc periodic T=0", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=0.0), True, 0.0, 15, None),
-                                                   ("sc periodic T=30 recover_u", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(recover_u=1))):
+                                                   ("sc periodic T=30 stored u", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(recover_u=0)),
+                                                   ("sc periodic T=30 separate wait/signal launches", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(fold_halo=0)),
+                                                   ("sc 64/rank x 96 x 256 periodic T=80, many items", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, None),
+                                                   ("sc 64/rank x 96 x 256 periodic T=80, short chunks", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, dict(chunk_long=6, chunk_short=2, tail_pct=50))):
         w = make()
         lat = w["lattice"]
         comm = TorchComm(periodic_x=periodic_x, device=f"cuda:{local}")
@@ -53,6 +97,7 @@ def main():
             single.ctx.close()
         comm.barrier(s.ctx)
         s.ctx.close()
+    ok = pinned_boundaries_case(rank, world, local) and ok
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -1,15 +1,76 @@
 """Test glue: build the CPU oracle for the same workload definition the GPU solver gets.
 
-The oracle side goes from the raw config-level settings through the ORACLE's own template expansion and
-neighbour-list construction (oracle/jams_oracle.cpp); the product side goes through jams_b200.lattice.
-Nothing here is imported by the product."""
+The oracle side goes from the RAW config-level settings (material table, motif, `anisotropies`, `dc_local_field`, ...)
+through this file's own restatement of the reference's parameter handling and the ORACLE's own template expansion and
+neighbour-list construction (oracle/jams_oracle.cpp); the product side goes through jams_b200.lattice / jams_b200.solver.
+Nothing of the product's parser is used on the checker's side: a unit-conversion or material-indexing
+bug in jams_b200 shows up as a parity failure.  Nothing here is imported by the product."""
 from __future__ import annotations
 
 import numpy as np
 
 import oracle
-from jams_b200.consts import ENERGY_UNITS
-from jams_b200.solver import create_hamiltonian
+
+# reference helpers/consts.h:29-36 and core/units.h:15-26, typed in again here on purpose
+REF_HBAR_IU = 0.6582119569              # meV ps
+REF_BOHR_MAGNETON_IU = 0.0578838181     # meV / T
+REF_ELECTRON_G = 2.0023193043625
+REF_GYRO_IU = REF_ELECTRON_G * REF_BOHR_MAGNETON_IU / REF_HBAR_IU   # rad / (ps T)
+REF_BOLTZMANN_IU = 0.0861733326         # meV / K
+REF_JOULE_TO_MEV = 6.24150907e21
+REF_MRYD_TO_MEV = 13.605693123
+ENERGY_UNITS = {"joules": REF_JOULE_TO_MEV, "J": REF_JOULE_TO_MEV, "milli_electron_volts": 1.0, "meV": 1.0,
+                "milli_rydbergs": REF_MRYD_TO_MEV, "mRyd": REF_MRYD_TO_MEV, "rydbergs": REF_MRYD_TO_MEV * 1e3, "Ryd": REF_MRYD_TO_MEV * 1e3,
+                "Kelvin": REF_BOLTZMANN_IU, "K": REF_BOLTZMANN_IU}
+
+
+def ref_site_tables(lat):
+    """per-site (material id, motif position) in the reference's site order ((i Ny + j) Nz + k) M + m (core/lattice.cc:622-657)"""
+    cells = int(lat.dims[0]) * int(lat.dims[1]) * int(lat.dims[2])
+    M = len(lat.motif_material)
+    return np.tile(np.asarray(lat.motif_material, dtype=np.int64), cells), np.tile(np.arange(M, dtype=np.int64), cells)
+
+
+def ref_material_arrays(lat):
+    """globals::mus / gyro / alpha from the raw material table (containers/material.h:30-34, core/lattice.cc:91-97,703-713)"""
+    mat, _ = ref_site_tables(lat)
+    moment = np.array([m.moment * REF_BOHR_MAGNETON_IU for m in lat.materials])
+    alpha = np.array([float(m.alpha) for m in lat.materials])
+    gyro = np.array([m.gyro * REF_GYRO_IU for m in lat.materials])
+    if lat.gilbert_prefactor:
+        gyro = gyro / (1.0 + alpha * alpha)
+    return moment[mat], gyro[mat], alpha[mat]
+
+
+def ref_uniaxial_arrays(lat, settings):
+    """power_, magnitude_ (meV), axis_ of UniaxialAnisotropyHamiltonian (hamiltonian/uniaxial_anisotropy.cc:40-114)"""
+    power = {"K1": 2, "K2": 4, "K3": 6}[settings["order"]]
+    unit = ENERGY_UNITS[settings.get("energy_units", "joules")]
+    mat, motif = ref_site_tables(lat)
+    names = [m.name for m in lat.materials]
+    K = np.zeros(mat.size)
+    axis = np.zeros((mat.size, 3))
+    for who, ax, energy in settings["anisotropies"]:
+        a = np.asarray(ax, dtype=np.float64)
+        a = a / np.sqrt(a @ a)
+        sel = (motif == int(who) - 1) if isinstance(who, (int, np.integer)) else (mat == names.index(who))
+        K[sel] = float(energy) * unit
+        axis[sel] = a
+    return power, K, axis
+
+
+def ref_zeeman_arrays(lat, settings):
+    """dc_local_field_, ac_local_field_ (meV), ac_local_frequency_ (rad / ps) of ZeemanHamiltonian (hamiltonian/zeeman.cc:26-71)"""
+    mat, _ = ref_site_tables(lat)
+    mus = ref_material_arrays(lat)[0]
+    dc = np.zeros((mat.size, 3))
+    if "dc_local_field" in settings:
+        dc = np.asarray(settings["dc_local_field"], dtype=np.float64).reshape(-1, 3)[mat] * mus[:, None]
+    if "ac_local_field" in settings:
+        ac = np.asarray(settings["ac_local_field"], dtype=np.float64).reshape(-1, 3)[mat] * mus[:, None]
+        om = 2.0 * np.pi * np.asarray(settings["ac_local_frequency"], dtype=np.float64)[mat]
+        return dc, ac, om
+    return dc, None, None
 
 
 def oracle_exchange_pairs(lat, settings):
@@ -27,7 +88,7 @@ def oracle_exchange_pairs(lat, settings):
                                   use_symops=settings.get("symops", True), symops=(lat.symops[0].reshape(-1, 9), lat.symops[1]),
                                   energy_cutoff=settings.get("energy_cutoff", 0.0), radius_cutoff=settings.get("radius_cutoff", 100.0),
                                   distance_tolerance=settings.get("distance_tolerance", 1e-4))
-    i, j, v, vals = oracle.neighbour_list(lat.dims, lat.periodic, lat.M, lat.site_material(), tmpl, motif_type=lat.motif_material)
+    i, j, v, vals = oracle.neighbour_list(lat.dims, lat.periodic, lat.M, ref_site_tables(lat)[0].astype(np.int32), tmpl, motif_type=lat.motif_material)
     prefactor = settings.get("interaction_prefactor", 1.0)
     J9 = (prefactor * unit * vals)[v]                      # Jij = prefactor * unit * J   (exchange.cc:165)
     keep = np.max(np.abs(J9), axis=1) > settings.get("energy_cutoff", 0.0) * unit  # (exchange.cc:166)
@@ -40,7 +101,7 @@ def brute_force_functional_pairs(lat, functionals, tol=1e-4):
     ``functionals``: {(name_i, name_j): (r_cutoff, J(r_ij) in meV)}; lengths in lattice parameters.  Returns i, j, J9."""
     pos = lat.positions()
     names = [m.name for m in lat.materials]
-    mat = lat.site_material()
+    mat = ref_site_tables(lat)[0].astype(np.int32)
     A = [lat.cell[:, k] * lat.dims[k] for k in range(3)]
     shifts = [sx * A[0] * lat.periodic[0] + sy * A[1] * lat.periodic[1] + sz * A[2] * lat.periodic[2]
               for sx in (-1, 0, 1) for sy in (-1, 0, 1) for sz in (-1, 0, 1)]
@@ -64,7 +125,8 @@ def brute_force_functional_pairs(lat, functionals, tol=1e-4):
 
 def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
     lat = workload["lattice"]
-    sim = oracle.CpuSim(lat.mus(), lat.gyro(), lat.alpha(), which)
+    mus, gyro, alpha = ref_material_arrays(lat)
+    sim = oracle.CpuSim(mus, gyro, alpha, which)
     terms = {}
     for hs in workload["hamiltonians"]:
         module = hs["module"].lower()
@@ -75,18 +137,16 @@ def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
             i, j, J9 = workload["functional_pairs"]   # brute-force list built by the test (brute_force_functional_pairs)
             terms[module] = sim.add_exchange(i, j, J9)
         elif module == "uniaxial":
-            h = create_hamiltonian(hs, lat)   # parameter parsing only (no numerics)
-            K, axis = h.site_arrays()
-            terms[module] = sim.add_uniaxial(h.power, K, axis)
+            power, K, axis = ref_uniaxial_arrays(lat, hs)
+            terms[module] = sim.add_uniaxial(power, K, axis)
         elif module == "zeeman":
-            h = create_hamiltonian(hs, lat)
-            dc, ac, om = h.site_arrays()
+            dc, ac, om = ref_zeeman_arrays(lat, hs)
             terms[module] = sim.add_zeeman(dc, ac, om)
         elif module == "applied-field":
             B = np.asarray(hs["field"], float)
             kind = str(hs.get("type", "static")).lower()
             if kind == "static":
-                terms[module] = sim.add_zeeman(lat.mus()[:, None] * B[None, :])
+                terms[module] = sim.add_zeeman(mus[:, None] * B[None, :])
             else:   # applied_field.cc:37-38,66-68: seconds -> ps, Hz -> THz
                 terms[module] = sim.add_applied_field(B, kind, float(hs["time_center"]) / 1e-12, float(hs["freq_bandwidth"]) / 1e12,
                                                       float(hs.get("freq_center", 0.0)) / 1e12)

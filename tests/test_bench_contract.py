@@ -21,6 +21,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["gpu_launches"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sc 96^3" in cb["sample"]
+    # 1 OpenMP thread and all host threads were probed; the faster one produced the value
+    assert "1" in cb["threads_tried"] and str(cb["cores"]) in cb["threads_tried"]
+    assert d["steps"] == 1 and d["warmup"] == 3   # the requested counts, not a capped run
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 
