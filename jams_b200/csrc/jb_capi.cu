@@ -836,6 +836,19 @@ int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int3
   for (int k = 0; k < n; ++k) {
     if (mi[k] < 0 || mi[k] >= c->d.num_motif || mj[k] < 0 || mj[k] >= c->d.num_motif) JB_FAIL(c, JB_ERR_INVALID, "motif index out of range in exchange template");
   }
+  if (c->opt_check_symmetry) {
+    // SparseInteractionHamiltonian::finalize (hamiltonian/sparse_interaction.cc:114-118) refuses a 3N x 3N matrix that is not
+    // symmetric (SparseMatrix::Builder::is_symmetric, containers/sparse_matrix_builder.h:320-362: element (3i+a, 3j+b) must
+    // equal (3j+b, 3i+a) exactly).  In template terms: entry (mi, mj, T, J) needs the entry (mj, mi, -T, J^T).
+    std::map<std::array<int, 5>, int> where;
+    for (int k = 0; k < n; ++k) where[{mi[k], mj[k], T3[3 * k], T3[3 * k + 1], T3[3 * k + 2]}] = k;
+    for (int k = 0; k < n; ++k) {
+      auto it = where.find({mj[k], mi[k], -T3[3 * k], -T3[3 * k + 1], -T3[3 * k + 2]});
+      bool ok = it != where.end();
+      for (int a = 0; a < 3 && ok; ++a) for (int b = 0; b < 3; ++b) if (J9[9 * (size_t)k + 3 * a + b] != J9[9 * (size_t)it->second + 3 * b + a]) ok = false;
+      if (!ok) JB_FAIL(c, JB_ERR_INVALID, "sparse matrix for exchange is not symmetric");
+    }
+  }
   c->t_mi.assign(mi, mi + n); c->t_mj.assign(mj, mj + n); c->t_T.assign(T3, T3 + 3 * n); c->t_J9.assign(J9, J9 + 9 * (size_t)n);
   c->has_template = n > 0;
   c->has_pairs = false;
@@ -924,6 +937,25 @@ int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const i
     if (nt > 0) return jb_set_exchange_template(c, nt, mi.data(), mj.data(), T3.data(), J9t.data());
   }
   if (c->d.n_ranks != 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_set_exchange_pairs is single-rank only in this version");
+  if (c->opt_check_symmetry) {
+    // the same symmetry requirement on the explicit list: every (i, j, J) needs (j, i, J^T).  Sort-based, no hash of the list
+    std::vector<int64_t> order(n_pairs);
+    for (int64_t p = 0; p < n_pairs; ++p) order[p] = p;
+    auto key = [&](int64_t p) { return ((uint64_t)(uint32_t)pi[p] << 32) | (uint32_t)pj[p]; };
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return key(a) < key(b); });
+    for (int64_t p = 0; p < n_pairs; ++p) {
+      if (vid[p] < 0 || vid[p] >= n_values) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
+      const uint64_t want = ((uint64_t)(uint32_t)pj[p] << 32) | (uint32_t)pi[p];
+      auto it = std::lower_bound(order.begin(), order.end(), want, [&](int64_t a, uint64_t k) { return key(a) < k; });
+      bool ok = it != order.end() && key(*it) == want;
+      if (ok) {
+        if (vid[*it] < 0 || vid[*it] >= n_values) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
+        const double *A = J9 + 9 * (size_t)vid[p], *B = J9 + 9 * (size_t)vid[*it];
+        for (int a = 0; a < 3 && ok; ++a) for (int b = 0; b < 3; ++b) if (A[3 * a + b] != B[3 * b + a]) ok = false;
+      }
+      if (!ok) JB_FAIL(c, JB_ERR_INVALID, "sparse matrix for exchange is not symmetric");
+    }
+  }
   JB_CUDA(c, cudaSetDevice(c->device));
   c->has_template = false; c->t_mi.clear(); c->t_mj.clear(); c->t_T.clear(); c->t_J9.clear();
   c->has_pairs = false;
@@ -1532,6 +1564,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "grid") c->opt_grid = (int)value;
   else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }
   else if (k == "fold_halo") { c->opt_fold_halo = (int)value; return JB_OK; }
+  else if (k == "check_symmetry") { c->opt_check_symmetry = (int)value; return JB_OK; }   // check_sparse_matrix_symmetry (hamiltonian/exchange.cc:104-110)
   else if (k == "trace") { c->opt_trace = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
   else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }

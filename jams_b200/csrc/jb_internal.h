@@ -263,6 +263,7 @@ struct jb_ctx {
   int opt_verbose = 0;
   int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernel (0 = occupancy x SMs)
   int opt_recover_u = 1;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B)
+  int opt_check_symmetry = 1; // refuse an exchange matrix that is not symmetric, like the reference (settings key check_sparse_matrix_symmetry)
   int opt_trace = 0;          // per-CTA {SM, first clock, last clock, items} of the last stage launch (jb_last_trace)
   int opt_fold_halo = 1;      // slab-decomposed runs: epoch handshake inside the stage kernel (1; 2 = even when a neighbour shares this GPU) or as separate wait / signal launches (0)
   int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows

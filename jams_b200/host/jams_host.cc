@@ -132,6 +132,57 @@ std::vector<Mat3> cubic_point_group() {   // the 48 signed permutation matrices 
   return rots;
 }
 
+// The rotations R of the crystal's symmetry operations {R|t} with t = 0, in the basis of the given cell: what the reference takes
+// from spglib's dataset (core/lattice.cc:783-822) and filters in lattice_site_point_group_symops (:1127-1153).  R runs over the
+// integer matrices that preserve the cell's metric (candidate columns in [-2, 2]^3, the lattice holohedry: at most 48); R is kept
+// if the motif maps onto itself, type by type, without any translation (cartesian tolerance symprec in lattice parameters).
+// Same enumeration order as jams_b200.lattice.find_space_group_operations.
+std::vector<Mat3> find_point_operations(const Mat3 &cell, const std::vector<Vec3> &motif_frac, const std::vector<int> &types, double symprec) {
+  double G[3][3], lens[3], gmax = 0.0;
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    G[i][j] = 0.0;
+    for (int k = 0; k < 3; ++k) G[i][j] += cell[k][i] * cell[k][j];
+    gmax = std::max(gmax, G[i][j]);
+  }
+  for (int k = 0; k < 3; ++k) lens[k] = std::sqrt(G[k][k]);
+  const double tol = symprec * std::max(1.0, std::sqrt(gmax));
+  const double lmax = std::max(lens[0], std::max(lens[1], lens[2]));
+  std::vector<Vec3> cols[3];
+  for (int a = -2; a <= 2; ++a) for (int b = -2; b <= 2; ++b) for (int c = -2; c <= 2; ++c) {
+    const Vec3 v{{double(a), double(b), double(c)}};
+    const double len = norm(matvec(cell, v));
+    for (int k = 0; k < 3; ++k) if (std::abs(len - lens[k]) <= tol) cols[k].push_back(v);
+  }
+  auto dotc = [&](const Vec3 &u, const Vec3 &v) { const Vec3 a = matvec(cell, u), b = matvec(cell, v); return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  std::vector<Mat3> out;
+  const size_t n = motif_frac.size();
+  for (const Vec3 &c0 : cols[0]) for (const Vec3 &c1 : cols[1]) {
+    if (std::abs(dotc(c0, c1) - G[0][1]) > tol * lmax) continue;
+    for (const Vec3 &c2 : cols[2]) {
+      if (std::abs(dotc(c0, c2) - G[0][2]) > tol * lmax || std::abs(dotc(c1, c2) - G[1][2]) > tol * lmax) continue;
+      Mat3 R;
+      for (int r = 0; r < 3; ++r) { R[r][0] = c0[r]; R[r][1] = c1[r]; R[r][2] = c2[r]; }
+      const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                         R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+      if (std::abs(std::abs(det) - 1.0) > 1e-9) continue;
+      bool ok = true;
+      for (size_t a = 0; a < n && ok; ++a) {
+        const Vec3 q = matvec(R, motif_frac[a]);
+        bool found = false;
+        for (size_t b = 0; b < n && !found; ++b) {
+          if (types[b] != types[a]) continue;
+          Vec3 d;
+          for (int k = 0; k < 3; ++k) { d[k] = q[k] - motif_frac[b][k]; d[k] -= std::nearbyint(d[k]); }
+          if (norm(matvec(cell, d)) <= symprec) found = true;
+        }
+        ok = found;
+      }
+      if (ok) out.push_back(R);
+    }
+  }
+  return out;
+}
+
 // jams::fmt::sci / decimal (helpers/output.h:32-42)
 std::ostream &fmt_sci(std::ostream &os) { return os << std::setprecision(8) << std::setw(16) << std::scientific << std::right; }
 std::ostream &fmt_decimal(std::ostream &os) { return os << std::setprecision(6) << std::setw(16) << std::fixed << std::right; }
@@ -217,7 +268,10 @@ Lattice::Lattice(const Setting &config) {
   num_spins = static_cast<int>(n);
 
   if (const Setting *solver = config.find("solver")) gilbert_prefactor = solver->get("gilbert_prefactor", false);   // core/lattice.cc:696-697
-  rotations = cubic_point_group();
+  {   // the reference asks spglib here (core/lattice.cc:783-822)
+    std::vector<int> types(motif_material.begin(), motif_material.end());
+    rotations = find_point_operations(cell, motif_frac, types, kLatticeTolerance);
+  }
 }
 
 int Lattice::material_index(const std::string &name) const {
@@ -496,6 +550,7 @@ static std::vector<InteractionInput> read_interaction_file(const std::string &pa
 }
 
 ExchangeHamiltonian::ExchangeHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
+  check_symmetry_ = s.get("check_sparse_matrix_symmetry", true);
   const bool use_symops = s.get("symops", true);
   const double energy_cutoff = s.get("energy_cutoff", 0.0), radius_cutoff = s.get("radius_cutoff", 100.0);
   const double distance_tolerance = s.get("distance_tolerance", kLatticeTolerance), prefactor = s.get("interaction_prefactor", 1.0);
@@ -902,6 +957,7 @@ Monitor *Monitor::create(const Setting &settings, const Lattice &lattice, const 
   const std::string module = lowercase(settings.required("module").as_string());
   if (module == "magnetisation") return new MagnetisationMonitor(settings, lattice, prefix + "mag.tsv");
   if (module == "energy") return new EnergyMonitor(settings, prefix + "eng.tsv");
+  if (module == "magnetisation-layers") return new MagnetisationLayersMonitor(settings, lattice, prefix + "mag_layers.tsv");
   if (module == "hdf5" || module == "spins-tsv") return new SpinsTsvMonitor(settings, prefix);
   throw std::runtime_error("unknown monitor " + module + " (not supported by the llg-heun-b200-gpu host layer)");
 }
@@ -953,6 +1009,84 @@ void MagnetisationMonitor::update(B200HeunLLGSolver &solver) {   // monitors/mag
               << fmt_sci << std::sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) * factor;
   }
   tsv_file_ << std::endl;
+}
+
+MagnetisationLayersMonitor::MagnetisationLayersMonitor(const Setting &settings, const Lattice &lattice, const std::string &filename)
+    : Monitor(settings), lattice_(lattice), tsv_file_(filename) {   // monitors/magnetisation_layers.cc:15-206
+  if (!tsv_file_) throw std::runtime_error("cannot open " + filename);
+  const Setting &ns = settings.required("layer_normal");
+  const Vec3 layer_normal{{ns[0].as_double(), ns[1].as_double(), ns[2].as_double()}};
+  const double layer_thickness = settings.get("layer_thickness", 0.0);
+  const double distance_tolerance = settings.get("distance_tolerance", 1e-4);   // jams::defaults::lattice_tolerance
+  const std::string grouping = lowercase(settings.get("grouping", "materials"));
+  const int N = lattice.num_spins;
+  std::vector<std::vector<int>> groups;
+  if (grouping == "none") {
+    groups.emplace_back(N);
+    for (int i = 0; i < N; ++i) groups[0][i] = i;
+    group_names_.push_back("total");
+  } else if (grouping == "materials") {
+    groups.resize(lattice.materials.size());
+    for (int i = 0; i < N; ++i) groups[lattice.motif_material[i % lattice.M]].push_back(i);
+    for (const auto &m : lattice.materials) group_names_.push_back(m.name);
+  } else if (grouping == "positions") {
+    groups.resize(lattice.M);
+    for (int i = 0; i < N; ++i) groups[i % lattice.M].push_back(i);
+    for (int n = 0; n < lattice.M; ++n) group_names_.push_back(std::to_string(n));
+  } else {
+    throw std::runtime_error("unknown magnetisation grouping: " + grouping);
+  }
+  mus_ = lattice.mus();
+  const std::vector<double> pos = lattice.positions();
+  const Mat3 R = rotation_matrix_between_vectors(layer_normal, Vec3{{0.0, 0.0, 1.0}});
+  const double to_nm = lattice.lattice_parameter * 1e9;   // kMeterToNanometer
+  group_layer_spins_.resize(groups.size());
+  layer_positions_.resize(groups.size());
+  tsv_file_ << "# magnetisation-layers: layer_normal " << layer_normal[0] << " " << layer_normal[1] << " " << layer_normal[2]
+            << " layer_thickness_nm " << layer_thickness << "\n";
+  for (size_t g = 0; g < groups.size(); ++g) {
+    std::vector<double> z(N, 0.0);
+    double z_min = std::numeric_limits<double>::max();
+    for (int i : groups[g]) {
+      z[i] = (R[2][0] * pos[3 * i] + R[2][1] * pos[3 * i + 1] + R[2][2] * pos[3 * i + 2]) * to_nm;
+      z_min = std::min(z_min, z[i]);
+    }
+    auto comp_less = [&](double a, double b) -> bool {
+      if (layer_thickness == 0.0) return definately_less_than(a, b, distance_tolerance);
+      return definately_less_than(std::floor((a - z_min) / layer_thickness), std::floor((b - z_min) / layer_thickness), distance_tolerance);
+    };
+    std::map<double, std::vector<int>, decltype(comp_less)> unique_positions(comp_less);
+    for (int i : groups[g]) unique_positions[z[i]].push_back(i);
+    int counter = 0;
+    for (const auto &kv : unique_positions) {
+      double z_layer = kv.first;
+      if (layer_thickness != 0.0) {
+        const double bin_index = std::floor((kv.first - (z_min - 0.5 * layer_thickness)) / layer_thickness);
+        z_layer = z_min + (bin_index + 0.5) * layer_thickness;
+      }
+      double sat = 0.0;
+      for (int i : kv.second) sat += mus_[i] / kBohrMagnetonIU;
+      layer_positions_[g].push_back(z_layer);
+      group_layer_spins_[g].push_back(kv.second);
+      tsv_file_ << "# group " << group_names_[g] << " layer " << counter << " position_nm " << std::setprecision(12) << z_layer
+                << " saturation_moment_muB " << sat << " spins " << kv.second.size() << "\n";
+      ++counter;
+    }
+  }
+  tsv_file_ << "# iteration time_ps group layer mx my mz (Bohr magnetons)" << std::endl;
+}
+
+void MagnetisationLayersMonitor::update(B200HeunLLGSolver &solver) {   // monitors/magnetisation_layers.cc:208-242
+  const std::vector<double> s = solver.spins();
+  for (size_t g = 0; g < group_layer_spins_.size(); ++g) {
+    for (size_t l = 0; l < group_layer_spins_[g].size(); ++l) {
+      double m[3] = {0.0, 0.0, 0.0};   // jams::sum_spins_moments (helpers/spinops.cc:55-67)
+      for (int i : group_layer_spins_[g][l]) for (int n = 0; n < 3; ++n) m[n] += mus_[i] * s[3 * static_cast<size_t>(i) + n];
+      tsv_file_ << solver.iteration() << " " << std::scientific << std::setprecision(9) << solver.time() << " " << group_names_[g] << " " << l
+                << std::setprecision(15) << " " << m[0] / kBohrMagnetonIU << " " << m[1] / kBohrMagnetonIU << " " << m[2] / kBohrMagnetonIU << "\n";
+    }
+  }
+  tsv_file_.flush();
 }
 
 EnergyMonitor::EnergyMonitor(const Setting &settings, const std::string &filename) : Monitor(settings), filename_(filename), tsv_file_(filename) {
@@ -1094,6 +1228,8 @@ double Hamiltonian::calculate_total_energy(double time) {
 }
 
 void ExchangeHamiltonian::attach(jb_ctx *ctx) {
+  // check_sparse_matrix_symmetry = false switches the symmetry check off (hamiltonian/exchange.cc:104-110); default: checked
+  solver->check(jb_set_option(ctx, "check_symmetry", check_symmetry_ ? 1 : 0));
   solver->check(jb_set_exchange_template(ctx, template_.size(), template_.mi.data(), template_.mj.data(), template_.T3.data(), template_.J9.data()));
 }
 void UniaxialAnisotropyHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_uniaxial(ctx, power_, magnitude_.data(), axis_.data())); }

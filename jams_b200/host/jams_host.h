@@ -95,7 +95,7 @@ class Lattice {
   Mat3 cell{}, cell_inv{};                 // columns are the lattice vectors a, b, c (core/lattice.cc:356-367)
   std::vector<int> motif_material;
   std::vector<Vec3> motif_frac;
-  std::vector<Mat3> rotations;             // point-group rotations in the fractional basis (O_h generated here; spglib in JAMS)
+  std::vector<Mat3> rotations;             // rotations of the crystal's zero-translation symmetry operations, fractional basis (find_point_operations; spglib in JAMS)
 
   int material_index(const std::string &name) const;   // throws if unknown
   bool material_exists(const std::string &name) const;
@@ -153,8 +153,11 @@ class ExchangeHamiltonian : public Hamiltonian {   // hamiltonian/exchange.cc:12
   NeighbourList neighbour_list() const { return lattice_.neighbour_list(template_); }
  protected:
   struct NoParse {};
-  ExchangeHamiltonian(const Setting &settings, const Lattice &lattice, NoParse) : Hamiltonian(settings, lattice) {}
+  ExchangeHamiltonian(const Setting &settings, const Lattice &lattice, NoParse) : Hamiltonian(settings, lattice) {
+    check_symmetry_ = settings.get("check_sparse_matrix_symmetry", true);
+  }
   InteractionTemplate template_;
+  bool check_symmetry_ = true;
 };
 
 // hamiltonian/exchange_functional.{h,cc}: isotropic J(r_ij) from a closed form inside a cutoff radius per ordered material pair
@@ -285,6 +288,26 @@ class SpinsTsvMonitor : public Monitor {
   int last_iteration_ = 0;
   double last_time_ = 0.0;
   B200HeunLLGSolver *final_from_ = nullptr;   // the final snapshot is taken from the solver that was last seen
+};
+
+// monitors/magnetisation_layers.{h,cc}: the moment of every layer of spins along `layer_normal` (Bohr magnetons), per group, every
+// output_steps -- what examples/bloch_domain_wall uses for the wall profile.  The reference writes the groups' layer tables and
+// the time series into monitors.h5; HDF5 is not available to this build, so the same data go to <name>_mag_layers.tsv:
+//   "# group <name> layer <k> position_nm <z> saturation_moment_muB <m> spins <n>"   once per layer, then per update
+//   "<iteration> <time_ps> <group> <layer> <mx> <my> <mz>"
+class MagnetisationLayersMonitor : public Monitor {
+ public:
+  MagnetisationLayersMonitor(const Setting &settings, const Lattice &lattice, const std::string &filename);
+  void update(B200HeunLLGSolver &solver) override;
+  // layer tables of group g (tests read them back through jbh_* or the file)
+  const std::vector<double> &layer_positions(size_t g) const { return layer_positions_[g]; }
+ private:
+  const Lattice &lattice_;
+  std::vector<std::string> group_names_;
+  std::vector<std::vector<std::vector<int>>> group_layer_spins_;   // [group][layer] -> site ids
+  std::vector<std::vector<double>> layer_positions_;
+  std::vector<double> mus_;
+  std::ofstream tsv_file_;
 };
 
 class EnergyMonitor : public Monitor {   // monitors/energy.cc:16-46

@@ -7,8 +7,8 @@ Mirrors what JAMS does before the solver ever runs, so that the exchange templat
 * boundary wrap / open-boundary rejection               — core/lattice.cc:987-1007
 * interaction template processing                        — core/interactions.cc:24-124,292-347
 * point-group expansion                                  — core/lattice.cc:1015-1035,1127-1153
-  (spglib is replaced by an explicit operation list; ``cubic_point_group()`` gives the 48 O_h
-  operations, sufficient for the sc / bcc / fcc cells of the BASELINE configs)
+  (spglib's operation list is replaced by ``find_space_group_operations``: metric-preserving integer
+  rotations of the cell x translations that map the motif onto itself)
 * neighbour list                                          — core/interactions.cc:349-395
 
 Everything here is setup code; none of it is on the per-step path.
@@ -59,6 +59,54 @@ def cubic_point_group():
                 R[r, perm[r]] = signs[r]
             rots.append(R)
     return np.array(rots), np.zeros((len(rots), 3))
+
+
+def find_space_group_operations(cell, motif_frac, motif_types, symprec=LATTICE_TOLERANCE):
+    """The symmetry operations {R|t} of the crystal in the basis of the given cell -- what the reference asks spglib for
+    (spg_get_dataset, core/lattice.cc:783-822: rotations / translations of the INPUT cell).  R runs over the integer matrices
+    that preserve the cell's metric (the lattice holohedry, at most 48); for each, every translation that maps the first atom
+    onto an atom of its type is tried and kept if the whole motif maps onto itself type by type (cartesian tolerance
+    ``symprec`` in lattice parameters, like spglib's symprec).  Returns (rotations (n,3,3), translations (n,3) in [0,1))."""
+    A = np.asarray(cell, dtype=np.float64).reshape(3, 3)
+    P = np.asarray(motif_frac, dtype=np.float64).reshape(-1, 3)
+    types = np.asarray(motif_types)
+    G = A.T @ A
+    tol = symprec * max(1.0, float(np.sqrt(G.max())))
+    lens = np.sqrt(np.diag(G))
+    cand = np.array(list(itertools.product(range(-2, 3), repeat=3)), dtype=np.float64)
+    clen = np.linalg.norm(cand @ A.T, axis=1)
+    cols = [cand[np.abs(clen - lens[k]) <= tol] for k in range(3)]
+    rots = []
+    for c0 in cols[0]:
+        for c1 in cols[1]:
+            if abs((A @ c0) @ (A @ c1) - G[0, 1]) > tol * max(lens):
+                continue
+            for c2 in cols[2]:
+                if abs((A @ c0) @ (A @ c2) - G[0, 2]) > tol * max(lens) or abs((A @ c1) @ (A @ c2) - G[1, 2]) > tol * max(lens):
+                    continue
+                R = np.column_stack([c0, c1, c2])
+                if abs(abs(np.linalg.det(R)) - 1.0) < 1e-9:
+                    rots.append(R)
+    out_R, out_t = [], []
+    same = [np.nonzero(types == types[a])[0] for a in range(len(P))]
+    for R in rots:
+        RP = P @ R.T
+        for j in same[0]:
+            t = P[j] - RP[0]
+            t = t - np.floor(t)
+            ok = True
+            for a in range(len(P)):
+                d = RP[a] + t - P[same[a]]
+                d = d - np.rint(d)
+                if np.min(np.linalg.norm(d @ A.T, axis=1)) > symprec:
+                    ok = False
+                    break
+            if ok:
+                t = np.where(np.abs(t - 1.0) <= symprec, 0.0, t)
+                if not any(np.array_equal(R, r) and np.allclose(t, u, atol=symprec) for r, u in zip(out_R, out_t)):
+                    out_R.append(R)
+                    out_t.append(t)
+    return np.array(out_R), np.array(out_t)
 
 
 def normalise_fractional_coordinate(r, eps=LATTICE_TOLERANCE):
@@ -150,7 +198,7 @@ class Lattice:
     dims: tuple
     periodic: tuple = (True, True, True)
     gilbert_prefactor: bool = False
-    symops: tuple | None = None       # (rotations (n,3,3) fractional, translations (n,3)); None = cubic O_h
+    symops: tuple | None = None       # (rotations (n,3,3) fractional, translations (n,3)); None = found from the cell and motif
 
     def __post_init__(self):
         self.cell = np.asarray(self.cell, dtype=np.float64).reshape(3, 3)
@@ -160,8 +208,8 @@ class Lattice:
         self.motif_frac = np.array([normalise_fractional_coordinate(p) for _, p in self.motif], dtype=np.float64)
         self.dims = tuple(int(d) for d in self.dims)
         self.periodic = tuple(bool(p) for p in self.periodic)
-        if self.symops is None:
-            self.symops = cubic_point_group()
+        if self.symops is None:   # the reference asks spglib (core/lattice.cc:783-822); here: find_space_group_operations
+            self.symops = find_space_group_operations(self.cell, self.motif_frac, self.motif_material)
 
     # -- sizes
     @property

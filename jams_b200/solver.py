@@ -95,6 +95,8 @@ class ExchangeHamiltonian(Hamiltonian):
         return self._nbr
 
     def attach(self, ctx, x0, nx):
+        # check_sparse_matrix_symmetry = false switches the symmetry check off (hamiltonian/exchange.cc:104-110); default: checked
+        ctx.set_option("check_symmetry", 0 if self.settings.get("check_sparse_matrix_symmetry", True) is False else 1)
         if self.use_pairs:
             i, j, v, vals = self.neighbour_list()
             ctx.set_exchange_pairs(i, j, v, vals)

@@ -555,3 +555,150 @@ def test_applied_field_pulse_fields_energy_and_trajectory_match_oracle(kind, var
     s.run(25)
     s.run(15)                                                         # time is carried across calls
     assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+
+
+# ---- round 2 hardening (VERDICT r01 "what's weak" 1-6) --------------------------------------------------------------------
+_ORACLE_CACHE = {}
+
+
+def _oracle_run(dims, T, steps, seed, normals):
+    """the oracle on the bench workload's Hamiltonian at a size it does in a few seconds per case"""
+    w = W.c3_sc(dims=dims, temperature=T)
+    sim = build_cpu_sim(w)
+    s0 = w["lattice"].initial_spins(seed=3)
+    sim.set_spins(s0)
+    sim.run(steps, normals)
+    return s0, sim.get_spins()
+
+
+@pytest.mark.parametrize("dims", [(96, 96, 96), (64, 32, 256), (24, 256, 256)])
+@pytest.mark.parametrize("T", [0.0, 100.0])
+def test_bench_code_path_matches_oracle(dims, T):
+    """The configuration the headline runs -- 4 x 128 tiles (128 columns at 256 x 256), more work items than resident CTAs, several
+    x-chunks plus the taper, the TMA ring wrapping across item boundaries -- compared with the oracle directly, T = 0 and T > 0
+    with the kernels' own noise handed to the oracle; both data flows of the stage kernel and the direct kernel."""
+    steps, seed = 5, 97
+    w = W.c3_sc(dims=dims, temperature=T)
+    lat = w["lattice"]
+    normals = None
+    if T > 0:
+        probe = make(w, seed=seed)
+        probe.spins()
+        normals = np.stack([probe.ctx.noise(probe.step_size, T, seed, n, normals_only=True) for n in range(steps)])
+        probe.ctx.close()
+    s0, want = _oracle_run(dims, T, steps, seed, normals)
+    for variant in ("pair", "pair_store_u", "direct"):
+        s = make(w, options=dict(KERNELS[variant], verbose=0), seed=seed)
+        s.set_spins(s0)
+        s.run(steps)
+        got = s.spins()
+        assert np.abs(got - want).max() <= TRAJ_TOL, (variant, dims, T)
+        s.ctx.close()
+
+
+def test_exchange_symmetry_guard_mirrors_the_reference():
+    """SparseInteractionHamiltonian::finalize throws "sparse matrix for exchange is not symmetric" (hamiltonian/sparse_interaction.cc:114-118,
+    containers/sparse_matrix_builder.h:320-362) unless check_sparse_matrix_symmetry = false (hamiltonian/exchange.cc:104-110)"""
+    c = capi.Context((6, 6, 6))
+    c.set_materials(np.full(216, 0.1), np.full(216, 0.17), np.full(216, 0.1))
+    eye = np.eye(3).reshape(9)
+    mi, mj = np.zeros(2, np.int32), np.zeros(2, np.int32)
+    T = np.array([[1, 0, 0], [-1, 0, 0]], np.int32)
+    c.set_exchange_template(mi, mj, T, np.stack([eye, eye]))                        # symmetric: accepted
+    with pytest.raises(capi.JamsB200Error, match="sparse matrix for exchange is not symmetric"):
+        c.set_exchange_template(mi, mj, T, np.stack([eye, 2 * eye]))               # J_ij != J_ji
+    with pytest.raises(capi.JamsB200Error, match="not symmetric"):
+        c.set_exchange_template(mi[:1], mj[:1], T[:1], eye[None, :])                # (j, i) missing
+    dm = np.array([0, 1.0, 0, -1.0, 0, 0, 0, 0, 0])                                  # antisymmetric (DM-like) tensor: J_ji = J_ij^T is symmetric overall
+    c.set_exchange_template(mi, mj, T, np.stack([dm, -dm]))
+    with pytest.raises(capi.JamsB200Error, match="not symmetric"):
+        c.set_exchange_template(mi, mj, T, np.stack([dm, dm]))
+    c.set_option("check_symmetry", 0)
+    c.set_exchange_template(mi, mj, T, np.stack([eye, 2 * eye]))                    # the reference's check_sparse_matrix_symmetry = false
+    c.set_option("check_symmetry", 1)
+    # the general list (no translation invariance -> ELL path): a one-way bond is refused too
+    c.set_option("detect_template", 0)
+    i = np.array([0, 1, 5], np.int32); j = np.array([1, 0, 7], np.int32)
+    with pytest.raises(capi.JamsB200Error, match="not symmetric"):
+        c.set_exchange_pairs(i, j, np.zeros(3, np.int32), eye[None, :])
+    c.set_exchange_pairs(i[:2], j[:2], np.zeros(2, np.int32), eye[None, :])
+    # through the plugin surface: the setting reaches the library
+    lat = Lattice([Material("A", 1.0)], np.eye(3), [("A", (0, 0, 0))], (6, 6, 6))
+    hs = dict(module="exchange", symops=False, interactions=[("A", "A", [1.0, 0.0, 0.0], 1e-21), ("A", "A", [-1.0, 0.0, 0.0], 2e-21)])
+    with pytest.raises(capi.JamsB200Error, match="not symmetric"):
+        make(dict(lattice=lat, hamiltonians=[hs], temperature=0.0)).run(1)
+    make(dict(lattice=lat, hamiltonians=[dict(hs, check_sparse_matrix_symmetry=False)], temperature=0.0)).run(1)
+
+
+def test_device_pointer_abi_path():
+    """`on_device = 1`: what the JAMS adapter passes (MultiArray::device_data(), containers/multiarray.h:239-253) -- import, export,
+    fields and noise with device pointers of another owner (a torch tensor) against the host-pointer path"""
+    import torch
+    w = W.c2_bcc_fe(6, temperature=0.0)
+    w["hamiltonians"].append(dict(module="uniaxial", order="K1", anisotropies=[("Fe", [0.0, 0.6, 0.8], 3e-23)]))
+    lat = w["lattice"]
+    s = make(w, seed=11)
+    s0 = random_unit_spins(lat.num_spins, 4)
+    d_in = torch.from_numpy(s0).cuda()
+    torch.cuda.synchronize()
+    s._build()
+    s.ctx.import_spins_ptr(d_in.data_ptr(), 1)
+    s.ctx.synchronize()
+    assert np.array_equal(s.ctx.export_spins(), s0)
+    d_out = torch.zeros_like(d_in)
+    s.ctx.export_spins_ptr(d_out.data_ptr(), 1)
+    s.ctx.synchronize()
+    assert np.array_equal(d_out.cpu().numpy(), s0)
+    # jb_fields into a device array (globals::h on the device)
+    import ctypes as C
+    d_h = torch.zeros_like(d_in)
+    s.ctx._ck(s.ctx.lib.jb_fields(s.ctx.h, capi.TERM_TOTAL, 0.0, C.c_void_p(d_h.data_ptr()), 1))
+    s.ctx.synchronize()
+    assert np.array_equal(d_h.cpu().numpy(), s.ctx.fields(capi.TERM_TOTAL, 0.0))
+    # Thermostat::device_data
+    d_n = torch.zeros_like(d_in)
+    s.ctx._ck(s.ctx.lib.jb_noise(s.ctx.h, 1e-4, 50.0, 11, 3, 0, 0, C.c_void_p(d_n.data_ptr()), 1))
+    s.ctx.synchronize()
+    assert np.array_equal(d_n.cpu().numpy(), s.ctx.noise(1e-4, 50.0, 11, 3))
+    # a trajectory started from the device import equals one started from the host import
+    s.run(10)
+    a = s.spins()
+    s2 = make(w, seed=11)
+    s2.set_spins(s0)
+    s2.run(10)
+    assert np.array_equal(a, s2.spins())
+
+
+def test_noise_distribution_in_depth():
+    """6.3 M draws of the pair-keyed Philox / Box-Muller stream (jb_device.cuh): Kolmogorov-Smirnov and chi-square against N(0,1),
+    moments to order 8, the hard cap of the 23-bit radius, and the independence structure inside a pair of sites -- the two
+    members of a Box-Muller pair share their radius, so besides their correlation the correlation of their SQUARES must vanish"""
+    from scipy import stats
+    lat = Lattice([Material("A", 1.0)], np.eye(3), [("A", (0, 0, 0))], (128, 128, 128))
+    w = dict(lattice=lat, hamiltonians=[dict(module="zeeman", dc_local_field=[[0, 0, 1.0]])], temperature=10.0)
+    s = make(w, seed=2026)
+    s.spins()
+    x = s.ctx.noise(1e-4, 10.0, 2026, 17, normals_only=True)      # (N, 3)
+    flat = x.ravel()
+    n = flat.size
+    assert stats.kstest(flat[::3], "norm").pvalue > 1e-3 and stats.kstest(flat[1::5], "norm").pvalue > 1e-3
+    edges = np.linspace(-4.0, 4.0, 81)
+    obs, _ = np.histogram(flat, bins=np.concatenate([[-np.inf], edges, [np.inf]]))
+    exp = np.diff(stats.norm.cdf(np.concatenate([[-np.inf], edges, [np.inf]]))) * n
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    assert chi2 < stats.chi2.ppf(1 - 1e-4, df=len(obs) - 1), chi2
+    for k, mk, var in ((1, 0.0, 1.0), (2, 1.0, 2.0), (3, 0.0, 15.0), (4, 3.0, 96.0), (6, 15.0, 10170.0), (8, 105.0, 2016000.0)):
+        assert abs((flat ** k).mean() - mk) < 5 * np.sqrt(var / n), k
+    assert 4.9 < np.abs(flat).max() <= np.sqrt(2 * 23 * np.log(2)) + 1e-6      # radius uniform has 23 bits
+    pairs = x.reshape(-1, 2, 3)                                      # (z even, z odd) of every row: one Philox call each
+    e, o = pairs[:, 0, :], pairs[:, 1, :]
+    m = e.shape[0]
+    bm = ((e[:, 0], e[:, 1]), (e[:, 2], o[:, 0]), (o[:, 1], o[:, 2]))   # the three Box-Muller pairs
+    other = ((e[:, 0], e[:, 2]), (e[:, 1], o[:, 1]), (e[:, 0], o[:, 2]), (o[:, 0], o[:, 1]))
+    for a, b in bm + other:
+        assert abs(np.mean(a * b)) < 5 / np.sqrt(m)
+        assert abs(np.mean((a * a - 1) * (b * b - 1))) < 5 * 2 / np.sqrt(m)
+    # neighbouring pairs / rows / steps are independent calls
+    assert abs(np.mean(e[:-1, 0] * e[1:, 0])) < 5 / np.sqrt(m)
+    y = s.ctx.noise(1e-4, 10.0, 2026, 18, normals_only=True).ravel()
+    assert abs(np.mean(flat * y)) < 5 / np.sqrt(n)

@@ -382,3 +382,142 @@ hamiltonians = ( %s );
         create_hamiltonian(dict(module="exchange-neartree", shell_width=0.3, interactions=[("Fe", "Fe", 0.8660254037844386, 3.2e-21), ("Fe", "Fe", 1.0, 1.6e-21)]), lat)
     dropped = host.exchange_template(str(shells), 'hamiltonians = ( { energy_cutoff = 2e-21; } );', ham_index=0)
     assert len(dropped["mi"]) == 16      # only the 8 + 8 nearest-neighbour entries survive
+
+
+# ---- the reference's own known answers and shipped configuration files (copies under tests/golden/reference_cfg/, made by
+# ---- tests/golden/make_reference_cfg_fixtures.py) ----------------------------------------------------------------------
+REF_CFG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_cfg")
+
+
+def _python_exchange_from_cfg(cfg, ham, base_dir):
+    """the Python mirror fed from the parsed configuration (so both host layers see the same text)"""
+    from jams_b200.lattice import Lattice, Material, read_interaction_file
+    mats = [Material(m["name"], m["moment"], m.get("gyro", 1.0), m.get("alpha", 0.01)) for m in cfg["materials"]]
+    lat = Lattice(mats, np.array(cfg["unitcell"]["basis"], float), [(p[0], tuple(p[1])) for p in cfg["unitcell"]["positions"]],
+                  tuple(cfg["lattice"]["size"]), periodic=tuple(cfg["lattice"]["periodic"]))
+    hs = dict(ham)
+    if "exc_file" in hs:
+        hs["interactions"] = read_interaction_file(os.path.join(base_dir, hs.pop("exc_file")))
+    else:
+        hs["interactions"] = [tuple(x) for x in hs["interactions"]]
+    return create_hamiltonian(hs, lat)
+
+
+def test_known_answer_crps4_local_point_groups_give_1536_interactions():
+    """/root/reference/test/test_exchange_symops.py:14 ("computed interactions: 1536") on test/test_exchange_symops.cfg, unchanged:
+    CrPS4 4^3, a low-symmetry cell where the crystal point group (with inversion) would invent interactions.  Needs the symmetry
+    operations of the crystal itself (jams_host.cc find_point_operations / lattice.py find_space_group_operations)."""
+    path = os.path.join(REF_CFG, "test_exchange_symops.cfg")
+    t = host.exchange_template(path, ham_index=1)
+    assert t["n_pairs"] == 1536 and len(t["mi"]) == 24
+    cfg = host.config_to_dict(path)
+    h = _python_exchange_from_cfg(cfg, cfg["hamiltonians"][1], REF_CFG)
+    assert len(h.neighbour_list()[0]) == 1536
+    for a, b in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(a, b)
+
+
+def test_known_answer_yig_8_cubed_gives_217088_interactions():
+    """src/jams/test/interactions.h:255-757 (generate_interactions_yig): 424 interactions per primitive cell x 8^3.  That (stale)
+    gtest hands the complete list to generate_neighbour_list without the symmetry expansion, so `symops = false` here -- with
+    symops the current reference would copy entry (i, j, r) to the images of r while keeping j (core/interactions.cc:24-37) and
+    report 'Multiple interactions', which this host layer reproduces."""
+    patch = 'hamiltonians = ( { module = "exchange"; exc_file = "yig_princep_exc.in"; symops = false; } );'
+    cwd = os.getcwd()
+    os.chdir(REF_CFG)   # exc_file is relative to the working directory, as in JAMS
+    try:
+        t = host.exchange_template("yig_8x8x8.cfg", patch, ham_index=0)
+        with pytest.raises(host.HostError, match="Multiple interactions"):
+            host.exchange_template("yig_8x8x8.cfg", ham_index=0)
+    finally:
+        os.chdir(cwd)
+    assert t["n_pairs"] == 424 * 8 * 8 * 8 == 217088 and len(t["mi"]) == 424
+    cfg = host.config_to_dict(os.path.join(REF_CFG, "yig_8x8x8.cfg"), patch)
+    h = _python_exchange_from_cfg(cfg, cfg["hamiltonians"][0], REF_CFG)
+    assert len(h.template["mi"]) == 424
+    for a, b in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(a, b)
+
+
+def test_shipped_bloch_domain_wall_example_parses_unchanged():
+    """examples/bloch_domain_wall/bloch_domain_wall.cfg as shipped: 256 x 16 x 16 sc, open along x -> 6 N - 2 * 16 * 16 pairs"""
+    path = os.path.join(REF_CFG, "bloch_domain_wall.cfg")
+    la = host.lattice_arrays(path)
+    assert la["num_spins"] == 65536 and la["dims"] == (256, 16, 16) and la["periodic"] == (False, True, True)
+    t = host.exchange_template(path, ham_index=1)
+    assert len(t["mi"]) == 6 and t["n_pairs"] == 6 * 65536 - 2 * 16 * 16
+    cfg = host.config_to_dict(path)
+    assert cfg["solver"]["module"] == "llg-rk4-gpu" and cfg["physics"]["module"] == "pinned_boundaries" and cfg["monitors"][0]["module"] == "magnetisation-layers"
+    assert cfg["initializer"] == {"module": "bloch_domain_wall", "width": 41.56, "center": 128.0}
+
+
+def test_space_group_search_known_answers():
+    """find_space_group_operations against textbook counts: sc O_h (48), conventional bcc (48 x 2 centring translations), the
+    bcc-primitive YIG cell (Ia-3d: 48 operations, 6 of them without translation: the -3 axis through the origin)"""
+    from jams_b200.lattice import cubic_point_group, find_space_group_operations
+    R, T = find_space_group_operations(np.eye(3), [[0, 0, 0]], [0])
+    assert sorted(tuple(r.ravel()) for r in R) == sorted(tuple(r.ravel()) for r in cubic_point_group()[0]) and np.all(T == 0)
+    R, T = find_space_group_operations(np.eye(3), [[0, 0, 0], [0.5, 0.5, 0.5]], [0, 0])
+    assert len(R) == 96 and sum(bool(np.allclose(t, 0)) for t in T) == 48
+    R, T = find_space_group_operations(np.eye(3), [[0, 0, 0], [0.5, 0.5, 0.5]], [0, 1])   # CsCl: the centring is gone
+    assert len(R) == 48
+    cfg = host.config_to_dict(os.path.join(REF_CFG, "yig_8x8x8.cfg"))
+    pos = [p[1] for p in cfg["unitcell"]["positions"]]
+    types = [0 if p[0] == "FeA" else 1 for p in cfg["unitcell"]["positions"]]
+    R, T = find_space_group_operations(np.array(cfg["unitcell"]["basis"], float), pos, types)
+    assert len(R) == 48 and sum(bool(np.allclose(t, 0)) for t in T) == 6
+
+
+def _read_mag_layers(path):
+    layers, rows = {}, []
+    for line in open(path):
+        t = line.split()
+        if line.startswith("# group"):
+            layers[int(t[4])] = float(t[6])
+        elif not line.startswith("#") and t:
+            rows.append((int(t[0]), float(t[1]), t[2], int(t[3]), float(t[4]), float(t[5]), float(t[6])))
+    return layers, rows
+
+
+@pytest.mark.gpu
+def test_shipped_bloch_domain_wall_example_runs_unchanged(tmp_path):
+    """examples/bloch_domain_wall/bloch_domain_wall.cfg exactly as shipped (llg-rk4-gpu + pinned_boundaries at T = 1 K +
+    bloch_domain_wall initializer + magnetisation-layers monitor, N = 65 536); only t_max is shortened by a command-line
+    patch, the way a JAMS user would (core/jams++.cc:48-84)"""
+    cfg = os.path.join(REF_CFG, "bloch_domain_wall.cfg")
+    got, done = host.run(cfg, "solver : { t_max = 2.0e-12; };", name="wall", output_dir=str(tmp_path))
+    assert done == 2000 and got.shape == (65536, 3)
+    assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() < 1e-12
+    layers, rows = _read_mag_layers(tmp_path / "wall_mag_layers.tsv")
+    assert len(layers) == 256 and abs(layers[1] - layers[0] - 0.3) < 1e-9        # layer spacing = lattice parameter 0.3 nm
+    assert sorted({r[0] for r in rows}) == [0, 1000] or sorted({r[0] for r in rows}) == [0, 1000, 2000]
+    last = [r for r in rows if r[0] == max(q[0] for q in rows)]
+    mz = np.array([r[6] for r in sorted(last, key=lambda r: r[3])]) / (3.0 * 256)   # moment 3 mu_B x 256 spins per layer
+    x = np.arange(256)
+    assert np.abs(mz - np.tanh(np.pi * (x - 128.0) / 41.56)).max() < 0.05          # 1 K: the profile stays where the initializer put it
+    assert mz[0] < -0.99 and mz[-1] > 0.99                                         # pinned ends
+
+
+@pytest.mark.gpu
+def test_bloch_wall_relaxes_to_the_analytic_width(tmp_path):
+    """BASELINE.md 1 / bloch_domain_wall.cfg:84-106: w/a = pi sqrt(J / 2k) = 41.56 at T = 0.  Start the shipped example's wall 28 %
+    too narrow (width 30), relax it with the llg-heun path at T = 0 (alpha = 1 to get there in 60 ps; the fixed point does not
+    depend on alpha) and fit m_z(x) = tanh(pi (x - c) / w) to the final state."""
+    from scipy.optimize import curve_fit
+    cfg = os.path.join(REF_CFG, "bloch_domain_wall.cfg")
+    patch = ('lattice : { size = [256, 4, 4]; }; initializer : { width = 30.0; }; physics : { module = "empty"; temperature = 0.0; }; '
+             'materials = ( { name = "A"; moment = 3.0; alpha = 1.0; spin = [0.0, 0.0, 1.0]; } ); '
+             'solver : { module = "llg-heun-gpu"; t_step = 5.0e-16; t_max = 6.0e-11; }; '
+             'monitors = ( { module = "magnetisation-layers"; output_steps = 40000; layer_normal = [1, 0, 0]; } );')
+    got, done = host.run(cfg, patch, name="relax", output_dir=str(tmp_path))
+    assert done == 120000
+    mz = got.reshape(256, 4, 4, 3)[..., 2].mean(axis=(1, 2))
+    x = np.arange(256, dtype=float)
+    (c, wfit), _ = curve_fit(lambda xx, c, w: np.tanh(np.pi * (xx - c) / w), x, mz, p0=(128.0, 30.0))
+    assert abs(wfit - 41.56) <= 0.01 * 41.56, wfit
+    assert abs(c - 127.5) < 1.0 or abs(c - 128.0) < 1.0
+    # the first output of the layers monitor holds the narrow initial wall, the last one the relaxed wall
+    layers, rows = _read_mag_layers(tmp_path / "relax_mag_layers.tsv")
+    first = np.array([r[6] for r in sorted([r for r in rows if r[0] == 0], key=lambda r: r[3])]) / (3.0 * 16)
+    (c0, w0), _ = curve_fit(lambda xx, c, w: np.tanh(np.pi * (xx - c) / w), x, first, p0=(128.0, 30.0))
+    assert abs(w0 - 30.0) < 0.05
