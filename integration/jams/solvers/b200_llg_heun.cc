@@ -43,6 +43,7 @@ void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
   max_steps_ = static_cast<int>(t_max / step_size_);
   min_steps_ = static_cast<int>(t_min / step_size_);
   gilbert_prefactor_ = jams::config_optional<bool>(settings, "gilbert_prefactor", false);  // core/lattice.cc:696-697
+  rk4_ = lowercase(jams::config_required<std::string>(settings, "module")).find("rk4") != std::string::npos;   // "llg-rk4-b200-gpu"
   seed_ = static_cast<std::uint64_t>(jams::config_optional<int>(globals::config->lookup("sim"), "seed", 0));
   register_thermostat(new PassThroughThermostat(step_size_, globals::num_spins));
 
@@ -108,9 +109,51 @@ void B200HeunLLGSolver::build() {
       throw std::runtime_error("llg-heun-b200-gpu: hamiltonian '" + h->name() + "' is not fused; use llg-heun-gpu");
     }
   }
-  physics_rewrites_spins_ = (lowercase(jams::config_optional<std::string>(globals::config->lookup("physics"), "module", "empty")) == "pinned_boundaries");
+  // The first Solver::update_physics_module() of the main loop (core/jams++.cc:334) has already run: globals::s carries the
+  // first pinning rotation.  From here on the state lives in the library and the pinning is applied to it there.
   import_spins();
+  if (lowercase(jams::config_optional<std::string>(globals::config->lookup("physics"), "module", "empty")) == "pinned_boundaries")
+    setup_pinned_boundaries();
   built_ = true;
+}
+
+// PinnedBoundariesPhysics::update (physics/pinned_boundaries.cc:34-46) rotates globals::s in place between steps, and
+// Solver::update_physics_module() is not virtual (core/solver.h:57), so the adapter cannot redirect it.  Re-importing globals::s
+// before every step would throw away the library's progress on every iteration without a monitor export, and
+// exporting after every step would add 96 B per spin to a 120 B step.  Instead the adapter registers the same edge regions with
+// the library and applies the same operation -- sum of mu_i s_i over the region, rotation_matrix_between_vectors, s_i <- R s_i --
+// to the library's state at the end of run(), i.e. at the point of the main loop where the physics module acts.  The module's own
+// rotation of globals::s then only touches a copy that the next export overwrites.
+void B200HeunLLGSolver::setup_pinned_boundaries() {
+  const libconfig::Setting &ps = globals::config->lookup("physics");
+  static const char *names[6] = {"left", "right", "front", "back", "bottom", "top"};   // pinned_boundaries.h:91-107: dimension, upper
+  const Vec3i size = globals::lattice->size();
+  for (int k = 0; k < 6; ++k) {
+    const std::string name = names[k];
+    if (!ps.exists(name + "_pinned_magnetisation")) continue;
+    const Vec3 target = jams::config_required<Vec3>(ps, name + "_pinned_magnetisation");
+    const int cells = jams::config_optional<int>(ps, name + "_pinned_cells", 1);
+    const int dim = k / 2;
+    const bool upper = (k % 2) == 1;
+    std::vector<int32_t> sites;
+    for (int i = 0; i < globals::num_spins; ++i) {
+      const Vec3i cell = globals::lattice->cell_offset(i);
+      if (upper ? cell[dim] >= size[dim] - cells : cell[dim] < cells) sites.push_back(i);
+    }
+    const int region = static_cast<int>(pinned_.size());
+    check(jb_set_region(ctx_, region, static_cast<int32_t>(sites.size()), sites.data()));
+    pinned_.push_back({region, {target[0], target[1], target[2]}});
+  }
+}
+
+void B200HeunLLGSolver::apply_pinned_boundaries() {
+  for (const auto &b : pinned_) {
+    double M4[4];
+    check(jb_region_moment(ctx_, b.region, M4));
+    const Mat3 R = rotation_matrix_between_vectors(Vec3{M4[0], M4[1], M4[2]}, Vec3{b.magnetisation[0], b.magnetisation[1], b.magnetisation[2]});
+    const double R9[9] = {R[0][0], R[0][1], R[0][2], R[1][0], R[1][1], R[1][2], R[2][0], R[2][1], R[2][2]};
+    check(jb_rotate_region(ctx_, b.region, R9));
+  }
 }
 
 void B200HeunLLGSolver::import_spins() {
@@ -128,13 +171,13 @@ void B200HeunLLGSolver::export_spins() {
 
 void B200HeunLLGSolver::run() {
   if (!built_) build();
-  if (physics_rewrites_spins_) import_spins();       // physics/pinned_boundaries.cc:34-46 rotates spins between steps
   update_thermostat();                               // T is re-read every step (core/solver.cc:94-97)
-  check(jb_step(ctx_, 1, step_size_, time_, thermostat_->temperature(), seed_, static_cast<std::uint64_t>(iteration_),
-                gilbert_prefactor_ ? 1 : 0));
+  check((rk4_ ? jb_step_rk4 : jb_step)(ctx_, 1, step_size_, time_, thermostat_->temperature(), seed_,
+                                       static_cast<std::uint64_t>(iteration_), gilbert_prefactor_ ? 1 : 0));
   spins_exported_ = false;
   iteration_++;
   time_ = iteration_ * step_size_;                   // solvers/cuda_llg_heun.cu:120-121
+  apply_pinned_boundaries();                         // what update_physics_module() does next in the main loop (core/jams++.cc:334)
 }
 
 void B200HeunLLGSolver::notify_monitors() {

@@ -8,6 +8,7 @@
 
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "jams/cuda/cuda_solver.h"
 #include "jams_b200.h"
@@ -31,12 +32,16 @@ class B200HeunLLGSolver : public CudaSolver {
   void check(int status) const; // jb_status -> std::runtime_error, like CHECK_CUDA_STATUS (cuda/cuda_common.h:43-77)
   void import_spins();          // globals::s (device AoS) -> library SoA
   void export_spins();          // library SoA -> globals::s (device AoS); marks the host copy stale
+  void setup_pinned_boundaries();   // physics/pinned_boundaries.cc:12-31 -> jb_set_region
+  void apply_pinned_boundaries();   // physics/pinned_boundaries.cc:34-46 on the library's own state
 
   jb_ctx *ctx_ = nullptr;
   bool built_ = false;
   bool spins_exported_ = true;  // globals::s currently equals the library's state
   bool gilbert_prefactor_ = false;
-  bool physics_rewrites_spins_ = false;
+  bool rk4_ = false;            // registered as "llg-rk4-b200-gpu": jb_step_rk4 instead of jb_step
+  struct PinnedRegion { int region; double magnetisation[3]; };
+  std::vector<PinnedRegion> pinned_;   // physics.module = "pinned_boundaries": the edge regions, held by the library
   std::uint64_t seed_ = 0;
 };
 
