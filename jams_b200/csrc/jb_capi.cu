@@ -377,8 +377,11 @@ void choose_tiling(jb_ctx *c) {
   if (c->opt_kernel < 1 || !c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
   {
-    // a thread owns the sites (z, z + 1) of every motif site of its y row; consumer threads = ceil(TZ / 2) x TY <= 256 so
-    // that two CTAs share an SM.  Tile choice: among z extents 128 / 64 / 32 (long contiguous runs along z serve DRAM best:
+    // a thread owns the sites (z, z + 1) of one y row and of the motif sites ms, ms + msplit, ...; consumer threads =
+    // ceil(TZ / 2) x TY x msplit <= 256 so that two CTAs share an SM.  Multi-site motifs get short tiles (the ring slots hold M
+    // rows per y), so the motif index is spread over threads as far as the 256 allow: bcc 4 x 64 runs 256 consumer threads with
+    // msplit = 2 instead of 128 looping over both sites (8 -> 16 consumer warps per SM: the kernel was latency-bound at 15 %
+    // active warps, profiles/r02j_c2_T300_ncu_full.txt).  Tile choice: among z extents 128 / 64 / 32 (long contiguous runs along z serve DRAM best:
     // 4 x 128 beats 8 x 64 beats 16 x 32 on C3, profiles/README.md) take, for each, the tallest tile whose rings fit the
     // shared-memory budget, and keep the candidate with the most sites per plane (a shorter z extent only if it brings
     // 1.5 x the sites).  Motifs with several sites multiply the slot size, so they end up with shorter tiles (bcc: 4 x 64)
@@ -393,7 +396,10 @@ void choose_tiling(jb_ctx *c) {
       q.UZ = (TZ + 1) & ~1;
       q.slotS = (q.BY * g.M * q.BZ + 15) / 16 * 16;
       q.slotU = (q.TY * g.M * q.UZ + 15) / 16 * 16;
-      q.threads = HZ * TY;
+      q.msplit = 1;
+      if (!c->opt_msplit) { for (int d = g.M; d >= 1; --d) if (g.M % d == 0 && HZ * TY * d <= 256) { q.msplit = d; break; } }
+      else if (c->opt_msplit > 0 && g.M % c->opt_msplit == 0) q.msplit = c->opt_msplit;
+      q.threads = HZ * TY * q.msplit;
       q.RU = c->opt_RU ? c->opt_RU : 2;
       const size_t slot_bytes = (size_t)3 * q.slotS * 8 + (size_t)n_nbr * sizeof(JbTileNbr);   // ring slot + its phase of the entry table
       const size_t u_bytes = (size_t)q.RU * 3 * q.slotU * 8;
@@ -498,7 +504,7 @@ void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   const jb_ctx::Tiling &t = c->tiling;
   p.g = c->g;
   p.J9T = c->d_tile_J9T;
-  p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU;
+  p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU; p.msplit = t.msplit;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols;
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
   for (int q = 0; q < c->g.M; ++q) {
@@ -657,8 +663,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, 
   plan_chunks(c, G, t.n_cols, sh);
   sh.grid = (int)std::min<long long>(G, (long long)sh.n_chunks * t.n_cols);
   if (c->opt_verbose) {
-    fprintf(stderr, "jams_b200: stage kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads, ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", stage, thermal, recu, t.TY, t.TZ, t.threads, t.Rs[stage], t.RU,
+    fprintf(stderr, "jams_b200: stage kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads (motif split %d), ring %d/%d, smem %zu B, "
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", stage, thermal, recu, t.TY, t.TZ, t.threads, t.msplit, t.Rs[stage], t.RU,
             t.smem[stage], per_sm, sh.grid, sh.n_chunks, t.n_cols);
     for (int q = 0; q < sh.n_chunks; ++q) fprintf(stderr, " %d+%d", sh.x0[q], sh.xc[q]);
     fprintf(stderr, "\n");
@@ -1554,6 +1560,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "recover_u") c->opt_recover_u = (int)value;
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
+  else if (k == "motif_split") c->opt_msplit = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
   else if (k == "ring_u") c->opt_RU = (int)value;
   else if (k == "chunks") c->opt_chunks = (int)value;

@@ -149,6 +149,7 @@ struct JbTileParams {
   int BY, BZ, gzb;       // tile + halo extent; gzb = gz rounded up to even = z halo of the box (BZ = TZ + 2 gzb)
   int slotS, slotU;      // doubles per component per ring slot (multiples of 16 = 128 B)
   int R, RU;             // ring depths: S planes (>= 2 gx + 2), U planes (>= 2)
+  int msplit;            // consumer threads per z pair of a y row: thread (ty, ms, zp) owns the motif sites ms, ms + msplit, ... (a divisor of M)
   int nbr_odd[JB_TILE_MAX_MOTIF];    // [m] -> first entry of nbr[] with an odd z offset (entries are even-first per motif site)
   // isotropic templates: the couplings (Tesla) of the entries (0, 0, -1) and (0, 0, +1) to the same motif site are taken out of
   // the table -- one of the two neighbours of each site of a pair is the other site of the pair, already in registers
@@ -221,7 +222,7 @@ struct jb_ctx {
     bool ok = false;
     int TY = 0, TZ = 0, UZ = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
     int Rs[2] = {0, 0};                   // ring depth per stage
-    int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0;
+    int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, msplit = 1;
     size_t smem[2] = {0, 0};              // per stage
     // launch shape per kernel variant [stage][thermal][recover_u]: resident CTAs and the x-chunk plan (0 = not determined yet)
     struct Shape { int grid = 0, n_chunks = 0, face_items[2] = {0, 0}; int x0[JB_TILE_MAX_CHUNKS], xc[JB_TILE_MAX_CHUNKS]; };
@@ -257,7 +258,7 @@ struct jb_ctx {
   // options
   int opt_kernel = 2;      // 0 = direct global gathers, 2 = TMA pair kernel where the template allows it (default)
   int reach[3] = {0, 0, 0};   // max |T| of the exchange template per axis
-  int opt_TY = 0, opt_TZ = 0, opt_R = 0, opt_RU = 0, opt_ctas_per_sm = 0;  // 0 = heuristic
+  int opt_TY = 0, opt_TZ = 0, opt_R = 0, opt_RU = 0, opt_ctas_per_sm = 0, opt_msplit = 0;  // 0 = heuristic
   int opt_chunks = 0;         // x-chunk plan: 0 = heuristic (long chunks + a tail of short ones), n > 0 = n equal chunks
   int opt_chunk_long = 0, opt_chunk_short = 0, opt_tail_pct = -1;   // heuristic overrides: planes per long / short chunk, share of the planes in short chunks
   int opt_verbose = 0;

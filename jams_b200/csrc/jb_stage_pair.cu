@@ -18,7 +18,8 @@
 //     shared memory and streams the item's planes-with-halo through 3-D TMA boxes into a ring of R slots (full / empty
 //     mbarriers per slot).  Consumers never meet at a CTA-wide barrier.
 //   * a consumer thread owns the sites (z, z + 1) of one (y, m) row: every gather of an even z offset is one LDS.128 for both
-//     sites, results leave as STG.128, two independent LLG evaluations per thread (ILP 2).
+//     sites, results leave as STG.128, two independent LLG evaluations per thread (ILP 2).  Multi-site motifs: the motif index is
+//     spread over the threads (JbTileParams::msplit), so that a bcc tile of 4 x 64 cells still runs 256 consumer threads.
 //   * RECU ("recover u"): the Heun intermediate is not stored.  k1 is perpendicular to s_n, so
 //     s_n + dt k1 = lambda s* with lambda = (s_n.s_n) / (s*.s_n) and u = (s_n + lambda s*) / 2: the predictor writes only s*
 //     (48 instead of 72 B per site), the corrector reads the site's own s_n through the second ring, rebuilds u in registers and
@@ -209,7 +210,9 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
 
   // =========================== consumers: M motif sites x one z pair of one y row each ===========================
   const int HZ = (p.TZ + 1) >> 1;                        // pairs per tile row
-  const int zp = tid % HZ, tyr = tid / HZ;
+  const int MS = MOTIF1 ? 1 : p.msplit;                  // threads per (y row, z pair): this one owns motif sites m0, m0 + MS, ...
+  const int zp = tid % HZ, trow = tid / HZ;
+  const int tyr = MOTIF1 ? trow : trow / MS, m0 = MOTIF1 ? 0 : trow - tyr * MS;
   const bool padding = tyr >= p.TY;                      // threads that only fill up the last consumer warp
   const int ty = padding ? 0 : tyr;
   const uint32_t cs8 = (uint32_t)slotS * 8u;             // component stride inside a slot, bytes
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
       const uint32_t uplane = uown + (uint32_t)uslot * uslot8;
 
 #pragma unroll 1
-      for (int m = 0; m < M; ++m) {
+      for (int m = m0; m < M; m += MS) {
         const JbClass &c = p.cls[MOTIF1 ? 0 : m];
         const uint32_t mo = (uint32_t)(m * p.BZ) * 8u;
         const uint32_t a = cen + mo;
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         }
         // early release: the oldest S plane (at the end of an item: all resident planes) is only read by the gathers
         // above, so its slot can go back to the producer while this warp still does the per-site physics
-        if (m == M - 1) {
+        if (m + MS >= M) {   // this thread's last motif site of the plane (msplit divides M: the same iteration for every lane)
           __syncwarp();
           if (lane0) {
             mbar_arrive(emptyS0 + 8u * oslot);

@@ -5,6 +5,7 @@ Tolerances: neighbour structure / import-export are bit-exact; fp64 fields agree
 (different summation instruction mix: FMA on the GPU, separate mul+add in the reference build);
 T = 0 (and fixed-noise T > 0) trajectories agree to 1e-10 per spin component after N steps, the bar
 BASELINE.json states."""
+import gc
 import os
 
 import numpy as np
@@ -264,21 +265,30 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     step(single, steps, dt, 0.0, T, seed, 0)
     want = single.export_spins()
 
-    ctxs = [new_ctx(r, n_slabs) for r in range(n_slabs)]
-    blobs = [c.halo_export_handle() for c in ctxs]
-    for r, c in enumerate(ctxs):
-        lo = r - 1 if r > 0 else (n_slabs - 1 if periodic_x else None)
-        hi = r + 1 if r < n_slabs - 1 else (0 if periodic_x else None)
-        c.halo_connect(blobs[lo] if lo is not None else None, blobs[hi] if hi is not None else None)
-    per = lat.num_spins // n_slabs
-    for r, c in enumerate(ctxs):
-        c.import_spins(s0[r * per:(r + 1) * per])
-    for n in range(steps):
+    # The slabs share ONE GPU and one host thread here, so a slab's stage may sit in its halo wait until the host has launched the
+    # neighbour's stage.  Anything that makes the host wait for the device in between deadlocks until the 10 s peer timeout --
+    # in particular the cudaFree of an earlier test's context when Python's cyclic collector happens to run inside the loop.
+    # (One process per GPU, the product's multi-GPU form, has no such coupling.)
+    gc.collect()
+    gc.disable()
+    try:
+        ctxs = [new_ctx(r, n_slabs) for r in range(n_slabs)]
+        blobs = [c.halo_export_handle() for c in ctxs]
+        for r, c in enumerate(ctxs):
+            lo = r - 1 if r > 0 else (n_slabs - 1 if periodic_x else None)
+            hi = r + 1 if r < n_slabs - 1 else (0 if periodic_x else None)
+            c.halo_connect(blobs[lo] if lo is not None else None, blobs[hi] if hi is not None else None)
+        per = lat.num_spins // n_slabs
+        for r, c in enumerate(ctxs):
+            c.import_spins(s0[r * per:(r + 1) * per])
+        for n in range(steps):
+            for c in ctxs:
+                step(c, 1, dt, n * dt, T, seed, n)
+        got = np.concatenate([c.export_spins() for c in ctxs])
         for c in ctxs:
-            step(c, 1, dt, n * dt, T, seed, n)
-    got = np.concatenate([c.export_spins() for c in ctxs])
-    for c in ctxs:
-        c.synchronize()
+            c.synchronize()
+    finally:
+        gc.enable()
     assert np.array_equal(got, want)
 
 
