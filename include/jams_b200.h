@@ -224,6 +224,14 @@ JB_API int64_t jb_kernel_launches(const jb_ctx *ctx);
 /* device time in ms of the stage kernels of the most recent jb_step, measured with CUDA events on the
  * context's stream; out2[0] = stage A total, out2[1] = stage B total.  Synchronises. */
 JB_API int jb_last_step_kernel_ms(jb_ctx *ctx, double *out2);
+/* which stage kernel the most recent jb_step ran: JB_KERNEL_DIRECT (one thread per spin, gathers through L1 / L2), JB_KERNEL_PAIR
+ * (TMA plane ring, a z pair of sites per thread: jb_stage_pair.cu), JB_KERNEL_ROWS (TMA plane ring, four y rows per thread with
+ * register reuse, deep isotropic templates: jb_stage_rows.cu), JB_KERNEL_ELL (general neighbour list); -1 before the first step */
+#define JB_KERNEL_DIRECT 0
+#define JB_KERNEL_PAIR 2
+#define JB_KERNEL_ROWS 4
+#define JB_KERNEL_ELL 5
+JB_API int jb_stage_kernel(const jb_ctx *ctx);
 /* block until all enqueued work of this context has finished */
 JB_API int jb_synchronize(jb_ctx *ctx);
 /* the cudaStream_t the context launches on (so callers can record events on it) */

@@ -61,6 +61,7 @@ SIGNATURES = {
     "jb_halo_export_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jb_halo_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_kernel_launches": (C.c_int64, [C.c_void_p]),
+    "jb_stage_kernel": (C.c_int, [C.c_void_p]),
     "jb_last_step_kernel_ms": (C.c_int, [C.c_void_p, _dp]),
     "jb_synchronize": (C.c_int, [C.c_void_p]),
     "jb_stream": (C.c_void_p, [C.c_void_p]),
@@ -300,6 +301,10 @@ class Context:
     # ---- introspection
     def kernel_launches(self):
         return int(self.lib.jb_kernel_launches(self.h))
+
+    def stage_kernel(self):
+        """jb_stage_kernel: 0 direct, 2 pair, 4 rows, 5 general neighbour list (-1 before the first step)"""
+        return int(self.lib.jb_stage_kernel(self.h))
 
     def last_step_kernel_ms(self):
         out = np.zeros(2)

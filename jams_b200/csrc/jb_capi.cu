@@ -14,6 +14,7 @@
 #include <map>
 #include <unordered_map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "jb_internal.h"
@@ -366,15 +367,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // shape of the tiles; grid size and x-chunking are decided per kernel variant in tile_launch_shape()
-void choose_tiling(jb_ctx *c) {
-  if (c->tiling_valid) return;
+static void choose_pair_tiling(jb_ctx *c) {
   const JbGeom &g = c->g;
   jb_ctx::Tiling t;
-  c->tiling = t;
-  c->tiling_valid = true;
-  c->tmap_valid = false;
   int n_nbr = (int)c->t_mi.size();
-  if (c->opt_kernel < 1 || !c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
+  if (c->opt_kernel < 1 || c->opt_kernel == 4 || !c->has_template || !c->motif_uniform || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF || n_nbr > JB_TILE_MAX_NBR)
     return;
   {
     // a thread owns the sites (z, z + 1) of one y row and of the motif sites ms, ms + msplit, ...; consumer threads =
@@ -500,12 +497,128 @@ void choose_tiling(jb_ctx *c) {
   }
 }
 
+// ---- rows kernel (jb_stage_rows.cu): deep isotropic templates ---------------------------------------------------------
+// Segments: the entries of a motif site that share (dx, dz, mj) and differ only in dy, cut into runs of at most five consecutive
+// offsets; sorted by motif site and length.  delta needs the row pitch BZ of the tile.
+static void build_row_segments(jb_ctx *c, int BZ) {
+  const JbGeom &g = c->g;
+  const int n_nbr = (int)c->t_mi.size();
+  struct Key { int mi, dx, dz, mj; bool operator<(const Key &o) const { return std::tie(mi, dx, dz, mj) < std::tie(o.mi, o.dx, o.dz, o.mj); } };
+  std::map<Key, std::map<int, double>> rows;   // -> dy -> J (meV); duplicate entries add up like the CSR builder merges them
+  for (int k = 0; k < n_nbr; ++k)
+    rows[Key{c->t_mi[k], c->t_T[3 * k], c->t_T[3 * k + 2], c->t_mj[k]}][c->t_T[3 * k + 1]] += c->t_J9[9 * (size_t)k];
+  std::vector<std::pair<int, JbRowSeg>> segs;   // (mi, segment)
+  for (const auto &kv : rows) {
+    const Key &key = kv.first;
+    const double inv_mu = c->h_classes[c->class_of_motif[key.mi]].inv_mu;
+    auto it = kv.second.begin();
+    while (it != kv.second.end()) {
+      const int dy0 = it->first;
+      JbRowSeg sg{};
+      sg.d = key.dx + g.gx;
+      sg.delta = ((dy0 * g.M + (key.mj - key.mi)) * BZ + key.dz) * (int)sizeof(double);
+      int last = dy0;
+      for (; it != kv.second.end() && it->first < dy0 + JB_ROWS_MAX_L; ++it) { sg.c[it->first - dy0] = it->second * inv_mu; last = it->first; }
+      sg.L = last - dy0 + 1;
+      segs.push_back({key.mi, sg});
+    }
+  }
+  std::stable_sort(segs.begin(), segs.end(), [](const std::pair<int, JbRowSeg> &a, const std::pair<int, JbRowSeg> &b) {
+    if (a.first != b.first) return a.first < b.first;
+    if (a.second.L != b.second.L) return a.second.L < b.second.L;
+    return a.second.d < b.second.d;
+  });
+  c->row_segs.clear();
+  for (int m = 0; m < JB_TILE_MAX_MOTIF; ++m) for (int l = 0; l <= JB_ROWS_MAX_L; ++l) c->row_begin[m][l] = 0;
+  for (const auto &ms : segs) c->row_segs.push_back(ms.second);
+  size_t at = 0;
+  for (int m = 0; m < g.M; ++m) {
+    for (int l = 1; l <= JB_ROWS_MAX_L; ++l) {
+      c->row_begin[m][l - 1] = (int)at;
+      while (at < segs.size() && segs[at].first == m && segs[at].second.L == l) ++at;
+      c->row_begin[m][l] = (int)at;
+    }
+  }
+}
+
+static void choose_rows_tiling(jb_ctx *c) {
+  const JbGeom &g = c->g;
+  if (c->opt_kernel < 1 || !c->has_template || !c->motif_uniform || !c->iso || g.gx > JB_TILE_MAX_GX || g.M > JB_TILE_MAX_MOTIF) return;
+  jb_ctx::Tiling t;
+  t.rows = true;
+  t.TZ = std::min(32, g.Nz);
+  if (t.TZ < g.Nz && (t.TZ & 1)) return;
+  t.gzb = (g.gz + 1) & ~1;
+  t.BZ = ((t.TZ + 1) & ~1) + 2 * t.gzb;
+  t.UZ = (t.TZ + 1) & ~1;
+  build_row_segments(c, t.BZ);
+  const int n_rows = (int)c->row_segs.size();
+  const int R = 2 * g.gx + 2;
+  const size_t limit = 227 * 1024;
+  int best_threads = 0;
+  for (int TY = 16; TY >= JB_ROWS_Q; TY -= JB_ROWS_Q) {
+    if (c->opt_TY && TY != c->opt_TY) continue;
+    if (TY - JB_ROWS_Q >= g.Ny && !c->opt_TY) continue;   // taller than the lattice
+    const int BY = TY + 2 * g.gy;
+    const int slotS = (BY * g.M * t.BZ + 15) / 16 * 16;
+    const size_t smem = (size_t)R * 3 * slotS * 8 + 448 + (size_t)n_rows * sizeof(JbRowSeg);
+    if (smem > limit || BY * g.M > 256 || t.BZ > 256) continue;
+    int ms = 0;
+    const int max_warps = c->opt_rows_warps > 0 ? std::min(c->opt_rows_warps, JB_ROWS_MAX_WARPS) : JB_ROWS_MAX_WARPS;
+    for (int d = g.M; d >= 1; --d) if (g.M % d == 0 && (TY / JB_ROWS_Q) * d <= max_warps) { ms = d; break; }
+    if (c->opt_msplit > 0 && g.M % c->opt_msplit == 0 && (TY / JB_ROWS_Q) * c->opt_msplit <= max_warps) ms = c->opt_msplit;
+    if (!ms) continue;
+    const int threads = 32 * (TY / JB_ROWS_Q) * ms;
+    if (threads > best_threads) {
+      best_threads = threads;
+      t.TY = TY; t.BY = BY; t.slotS = slotS; t.slotU = 16; t.R = R; t.Rs[0] = t.Rs[1] = R; t.RU = 2; t.msplit = ms; t.threads = threads;
+      t.smem[0] = t.smem[1] = smem;
+    }
+  }
+  if (!best_threads) return;
+  t.rows_mode = t.threads <= 32 * JB_ROWS_PIPE_WARPS ? 2 : 1;
+  if (c->opt_rows_mode >= 0 && c->opt_rows_mode <= 2 && (c->opt_rows_mode != 2 || t.threads <= 32 * JB_ROWS_PIPE_WARPS)) t.rows_mode = c->opt_rows_mode;
+  t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
+  t.n_cols = t.n_yt * t.n_zt;
+  if (c->d_rows) cudaFree(c->d_rows);
+  c->d_rows = nullptr;
+  if (cudaMalloc(&c->d_rows, std::max(1, n_rows) * sizeof(JbRowSeg)) != cudaSuccess ||
+      cudaMemcpy(c->d_rows, c->row_segs.data(), n_rows * sizeof(JbRowSeg), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  t.ok = true;
+  c->tiling = t;
+}
+
+// kernel choice for a translation-invariant template (option kernel: 0 = direct gathers, 2 = default, 4 = rows kernel where it
+// applies): isotropic templates that reach three or more cells along an axis, or two with 40 or more neighbours per site, go to the rows kernel (the pair kernel's tiles
+// would be mostly halo, and with that many neighbours the gather is bound by shared-memory bandwidth, which the rows kernel
+// halves); everything else to the pair kernel; the direct kernel takes what neither can tile
+void choose_tiling(jb_ctx *c) {
+  if (c->tiling_valid) return;
+  c->tiling = jb_ctx::Tiling();
+  c->tiling_valid = true;
+  c->tmap_valid = false;
+  const int reach = std::max(c->g.gx, std::max(c->g.gy, c->g.gz));
+  const bool deep = c->iso && c->has_template && (reach >= 3 || (reach >= 2 && c->t_mi.size() >= (size_t)40 * c->g.M));
+  if (c->opt_kernel == 4 || deep) choose_rows_tiling(c);
+  if (!c->tiling.ok) choose_pair_tiling(c);
+  if (!c->tiling.ok && !deep) choose_rows_tiling(c);
+}
+
 void fill_tile_params(jb_ctx *c, JbTileParams &p) {
   const jb_ctx::Tiling &t = c->tiling;
   p.g = c->g;
   p.J9T = c->d_tile_J9T;
   p.TY = t.TY; p.TZ = t.TZ; p.UZ = t.UZ; p.BY = t.BY; p.BZ = t.BZ; p.gzb = t.gzb; p.slotS = t.slotS; p.slotU = t.slotU; p.R = t.R; p.RU = t.RU; p.msplit = t.msplit;
   p.n_yt = t.n_yt; p.n_zt = t.n_zt; p.n_cols = t.n_cols;
+  if (t.rows) {
+    p.rows = c->d_rows; p.n_rows = (int)c->row_segs.size();
+    for (int m = 0; m < JB_TILE_MAX_MOTIF; ++m) for (int l = 0; l <= JB_ROWS_MAX_L; ++l) p.row_begin[m][l] = c->row_begin[m][l];
+    p.nbr = nullptr; p.n_nbr = 0;
+    return;
+  }
   for (size_t q = 0; q < c->tile_nbr_begin.size(); ++q) p.nbr_begin[q] = c->tile_nbr_begin[q];
   for (int q = 0; q < c->g.M; ++q) {
     p.nbr_odd[q] = c->tile_nbr_odd[q];
@@ -655,7 +768,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, 
   if (sh.grid > 0) return JB_OK;
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
-  JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, recu, t.threads, t.smem[stage], &per_sm));
+  if (t.rows) JB_CUDA(c, jbk_stage_rows_occupancy(stage, thermal, t.rows_mode, t.threads, t.smem[stage], &per_sm));
+  else JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, recu, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the stage kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
   int G = per_sm * c->num_sms;
@@ -663,8 +777,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, 
   plan_chunks(c, G, t.n_cols, sh);
   sh.grid = (int)std::min<long long>(G, (long long)sh.n_chunks * t.n_cols);
   if (c->opt_verbose) {
-    fprintf(stderr, "jams_b200: stage kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads (motif split %d), ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", stage, thermal, recu, t.TY, t.TZ, t.threads, t.msplit, t.Rs[stage], t.RU,
+    fprintf(stderr, "jams_b200: %s kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads (motif split %d), ring %d/%d, smem %zu B, "
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", t.rows ? "rows" : "pair", stage, thermal, recu, t.TY, t.TZ, t.threads, t.msplit, t.Rs[stage], t.RU,
             t.smem[stage], per_sm, sh.grid, sh.n_chunks, t.n_cols);
     for (int q = 0; q < sh.n_chunks; ++q) fprintf(stderr, " %d+%d", sh.x0[q], sh.xc[q]);
     fprintf(stderr, "\n");
@@ -817,7 +931,7 @@ void jb_destroy(jb_ctx *c) {
   release_state(c);
   void *p;
   p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
-  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p);
+  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p); p = c->d_rows; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
   p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p); p = c->d_groups; free_dev(p);
@@ -1136,11 +1250,12 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
       tp.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
     }
   }
+  c->last_stage_kernel = c->has_pairs ? JB_KERNEL_ELL : (use_tile ? (c->tiling.rows ? JB_KERNEL_ROWS : JB_KERNEL_PAIR) : JB_KERNEL_DIRECT);
   const int thermal = T > 0.0 ? 1 : 0;
   // data flow of the TMA kernel (option recover_u): 1 = the corrector rebuilds the Heun intermediate from s_n and s* (120 B per
   // update; at T > 0 it then draws the site's noise a second time), 0 = the predictor stores it with the noise part of the
   // corrector folded in (144 B), 2 = 1 at T = 0 and 0 at T > 0
-  const bool recu = use_tile && (c->opt_recover_u == 1 || (c->opt_recover_u == 2 && !thermal));
+  const bool recu = use_tile && (c->tiling.rows || c->opt_recover_u == 1 || (c->opt_recover_u == 2 && !thermal));   // the rows kernel has no other data flow
   // the epoch handshake of a slab-decomposed run happens inside the TMA kernel; the other kernels bracket each launch with
   // wait / signal launches
   // (a neighbour slab that lives on THIS device shares its SMs with me: a resident kernel that polls for its flags could keep
@@ -1219,7 +1334,8 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
           }
           const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
-          JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+          if (c->tiling.rows) JB_CUDA(c, jbk_stage_rows(tp, tm, stage, th, c->tiling.rows_mode, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+          else JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
           c->trace_ctas = sh.grid;
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
@@ -1525,6 +1641,7 @@ int jb_halo_connect(jb_ctx *c, const void *blob_lo, const void *blob_hi) {
 
 // ---- introspection ---------------------------------------------------------------------------------------
 int64_t jb_kernel_launches(const jb_ctx *c) { return c ? c->launches : 0; }
+int jb_stage_kernel(const jb_ctx *c) { return c ? c->last_stage_kernel : -1; }
 
 int jb_synchronize(jb_ctx *c) {
   if (!c) return JB_ERR_INVALID;
@@ -1561,6 +1678,8 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
   else if (k == "motif_split") c->opt_msplit = (int)value;
+  else if (k == "rows_mode") c->opt_rows_mode = (int)value;
+  else if (k == "rows_warps") c->opt_rows_warps = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
   else if (k == "ring_u") c->opt_RU = (int)value;
   else if (k == "chunks") c->opt_chunks = (int)value;

@@ -108,6 +108,20 @@ __device__ __forceinline__ void site_normals(unsigned long long seed, unsigned l
   n0 = (double)a; n1 = (double)b; n2 = (double)c;
 }
 
+// the same with the round keys precomputed (stage kernels: rk in the kernel-parameter bank)
+__device__ __forceinline__ void site_normals_rk(const unsigned int *__restrict__ rk, unsigned long long step, unsigned long long gpair, bool odd,
+                                                double &n0, double &n1, double &n2) {
+  uint32_t w[4];
+  philox4x32_10_rk((uint32_t)gpair, (uint32_t)(gpair >> 32), (uint32_t)step, (uint32_t)(step >> 32), rk, w);
+  const float r1 = bm_radius(w[1]), t1 = bm_angle(w[3] >> 16);
+  const uint32_t wr = odd ? w[2] : w[0];
+  const uint32_t wa = odd ? (__byte_perm(w[0], w[1], 0x7740) & 0xffffu) : (w[3] & 0xffffu);
+  const float r = bm_radius(wr), t = bm_angle(wa);
+  const float c1 = __cosf(t1), s1 = __sinf(t1), cc = r * __cosf(t), ss = r * __sinf(t);
+  // even-z site: (r0 cos t0, r0 sin t0, r1 cos t1); odd-z site: (r1 sin t1, r2 cos t2, r2 sin t2)
+  n0 = (double)(odd ? r1 * s1 : cc); n1 = (double)(odd ? cc : ss); n2 = (double)(odd ? ss : r1 * c1);
+}
+
 __device__ __forceinline__ unsigned long long global_site(const JbGeom &g, int x, int y, int m, int z) {
   return (((unsigned long long)(g.x_begin + x) * g.Ny + y) * g.Nz + z) * g.M + m;
 }

@@ -136,6 +136,19 @@ struct JbHalo {
   unsigned int face_target[2];    // consumer warps x face items per side
   int enabled;
 };
+// one segment of the exchange template as the rows kernel (jb_stage_rows.cu) sees it: up to five entries of a motif site that
+// differ only in their y offset, dy = dy0 ... dy0 + L - 1 (absent offsets carry a zero coupling)
+struct __align__(16) JbRowSeg {
+  int delta;    // byte offset of the neighbour of the thread's FIRST site at dy0 (component x) relative to that site, inside a slot
+  int d;        // dx + gx: which of the 2 gx + 1 resident planes
+  int L;        // 1 ... 5
+  int pad;
+  double c[6];  // couplings / mu_i (Tesla) of dy0 + t, t < L; the rest zero
+};
+#define JB_ROWS_MAX_L 5
+#define JB_ROWS_Q 4           // sites (consecutive y rows) per consumer thread
+#define JB_ROWS_MAX_WARPS 8   // consumer warps per CTA (+ the producer warp: 288 threads, 168 registers per thread)
+#define JB_ROWS_PIPE_WARPS 4  // up to here five warps per CTA, at most two per scheduler: 255 registers, room for double-buffered segments
 struct JbTileParams {
   JbGeom g;
   double *out[3];        // spins written (S1 in stage A, S0 in stage B), own box
@@ -163,6 +176,11 @@ struct JbTileParams {
   unsigned int *queue_next;   // the counter the next launch on the stream will use: zeroed by this one
   JbHalo halo;
   unsigned long long *trace;   // optional: per CTA JB_TRACE_WORDS words (option "trace")
+  // rows kernel: the segments in global memory (copied to shared memory once per CTA), sorted by motif site and length:
+  // segments of motif site m with L entries are row_begin[m][L - 1] ... row_begin[m][L] - 1
+  const JbRowSeg *rows;
+  int n_rows;
+  int row_begin[JB_TILE_MAX_MOTIF][JB_ROWS_MAX_L + 1];
   int n_nbr;
   const JbTileNbr *nbr;  // n_nbr entries in global memory, copied to shared memory once per CTA
   int nbr_begin[JB_TILE_MAX_MOTIF + 1];  // [m] -> first entry of nbr[]
@@ -220,6 +238,8 @@ struct jb_ctx {
   // tiling of the persistent TMA stage kernel (jb_capi.cu choose_tiling) and its parameter-bank tables
   struct Tiling {
     bool ok = false;
+    bool rows = false;                    // the rows kernel (jb_stage_rows.cu) instead of the pair kernel
+    int rows_mode = 0;                    // its variant (jbk_stage_rows)
     int TY = 0, TZ = 0, UZ = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
     int Rs[2] = {0, 0};                   // ring depth per stage
     int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, msplit = 1;
@@ -235,6 +255,9 @@ struct jb_ctx {
   JbTileNbr *d_tile_nbr = nullptr;
   double *d_tile_J9T = nullptr;
   std::vector<int> tile_nbr_begin, tile_nbr_odd;
+  std::vector<JbRowSeg> row_segs;           // rows kernel: the template cut into y segments (build_row_segments)
+  JbRowSeg *d_rows = nullptr;
+  int row_begin[JB_TILE_MAX_MOTIF][JB_ROWS_MAX_L + 1] = {{0}};
   std::vector<double> tile_zself;   // [m][2], see JbTileParams::zself
   int num_sms = 0;
 
@@ -263,6 +286,8 @@ struct jb_ctx {
   int opt_chunk_long = 0, opt_chunk_short = 0, opt_tail_pct = -1;   // heuristic overrides: planes per long / short chunk, share of the planes in short chunks
   int opt_verbose = 0;
   int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernel (0 = occupancy x SMs)
+  int opt_rows_mode = -1;     // rows kernel variant: -1 = by the number of consumer warps
+  int opt_rows_warps = 0;     // rows kernel: upper limit of consumer warps per CTA (0 = JB_ROWS_MAX_WARPS)
   int opt_recover_u = 1;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B)
   int opt_check_symmetry = 1; // refuse an exchange matrix that is not symmetric, like the reference (settings key check_sparse_matrix_symmetry)
   int opt_trace = 0;          // per-CTA {SM, first clock, last clock, items} of the last stage launch (jb_last_trace)
@@ -297,6 +322,7 @@ struct jb_ctx {
 
   // bookkeeping
   long long launches = 0;
+  int last_stage_kernel = -1;   // jb_stage_kernel
   std::vector<cudaEvent_t> ev; size_t ev_used = 0;
   std::vector<int> ev_kind;
 };
@@ -320,6 +346,11 @@ cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int recu, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
+// rows kernel (jb_stage_rows.cu): tmaps = {S.x, S.y, S.z}; threads = 32 x (TY / 4) x msplit consumer threads
+// mode: 2 = double-buffered segments (at most JB_ROWS_PIPE_WARPS consumer warps), 0 / 1 = single buffer, unrolled once / twice
+cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tmaps3, int stage, int thermal, int mode, int threads, int grid,
+                           size_t smem_bytes, cudaStream_t stream);
+cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int mode, int threads, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
                             int iso, int stage, cudaStream_t stream);
 // term field (meV) into AoS N x 3 (device); term as jb_term; pairs path when ell_idx != nullptr

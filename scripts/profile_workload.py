@@ -14,6 +14,9 @@ T = float(sys.argv[4]) if len(sys.argv) > 4 else 300.0
 extra = json.loads(sys.argv[5]) if len(sys.argv) > 5 else {}
 w = {"c2": W.c2_bcc_fe, "c4": W.c4_bcc_long_range, "c3": W.c3_sc}[which[:2]](n, temperature=T)
 s = W.make_solver(w, options=dict(extra, verbose=1, time_kernels=1), random_spins_seed=1, seed=3)
+s.run(2)   # warm-up: lazy module loading, first-launch attribute calls
+s.ctx.synchronize()
+s.ctx.last_step_kernel_ms()
 s.run(steps)
 s.ctx.synchronize()
 ms = s.ctx.last_step_kernel_ms() / steps

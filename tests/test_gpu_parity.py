@@ -26,8 +26,11 @@ KERNELS = {"direct": dict(kernel=0), "pair": dict(kernel=2),
            "pair_store_u": dict(kernel=2, recover_u=0), "pair_recover_u": dict(kernel=2, recover_u=1),
            # other tilings / work-item plans of the same kernel: small tiles (many columns), equal chunks, short chunks only
            "pair_small_tile": dict(kernel=2, tile_y=2, tile_z=16, chunks=3), "pair_small_tile_store_u": dict(kernel=2, tile_y=2, tile_z=16, chunks=3, recover_u=0),
-           "pair_short_chunks": dict(kernel=2, tile_y=3, tile_z=32, chunk_long=4, chunk_short=2, tail_pct=50)}
-ALL_TMA = ["pair", "pair_store_u", "pair_recover_u", "pair_small_tile", "pair_small_tile_store_u", "pair_short_chunks"]
+           "pair_short_chunks": dict(kernel=2, tile_y=3, tile_z=32, chunk_long=4, chunk_short=2, tail_pct=50),
+           # the rows kernel (four y rows per thread, deep isotropic templates; forced here on every isotropic template; tensor
+           # couplings fall through to the direct kernel), default tile and the smallest tile with equal chunks
+           "rows": dict(kernel=4), "rows_small_tile": dict(kernel=4, tile_y=4, chunks=3)}
+ALL_TMA = ["pair", "pair_store_u", "pair_recover_u", "pair_small_tile", "pair_small_tile_store_u", "pair_short_chunks", "rows", "rows_small_tile"]
 
 
 def gold(name):
@@ -233,7 +236,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rk4"])
+@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -250,7 +253,7 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
         nx = dims[0] // n
         c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
         if kernel != "rk4":
-            c.set_option("kernel", 2)
+            c.set_option("kernel", 4 if kernel.startswith("rows") else 2)
             c.set_option("recover_u", 0 if kernel.startswith("2u") else 1)   # two launches per step, two halo exchanges
             # fold: the epoch handshake inside the stage kernel (what multi-GPU runs use); the slabs share this GPU here, which
             # works because these lattices leave most of the SMs free for the neighbour's kernel
@@ -290,6 +293,43 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     finally:
         gc.enable()
     assert np.array_equal(got, want)
+
+
+def test_kernel_choice_deep_templates_go_to_the_rows_kernel():
+    for w, opts, want in ((W.c3_sc(dims=(12, 10, 40)), None, 2), (W.c3_sc(dims=(12, 10, 40)), dict(kernel=4), 4), (W.c3_sc(dims=(12, 10, 40)), dict(kernel=0), 0),
+                          (W.c4_bcc_long_range(8), None, 4), (W.c4_bcc_long_range(8), dict(kernel=0), 0)):
+        s = make(w, options=opts, random_spins_seed=1)
+        assert s.ctx.stage_kernel() == -1
+        s.run(1)
+        assert s.ctx.stage_kernel() == want, (w["name"], opts)
+
+
+@pytest.mark.parametrize("dims,periodic", [((8, 9, 40), (True, True, True)), ((7, 13, 33), (True, True, True)), ((9, 8, 70), (False, True, False)),
+                                           ((8, 21, 8), (True, False, True))])
+@pytest.mark.parametrize("T", [0.0, 200.0])
+def test_deep_template_rows_kernel_matches_oracle(dims, periodic, T):
+    """BASELINE config 4's template (bcc, eight shells, 112 neighbours per spin, ghost depth 3) on small lattices with ragged
+    tiles, short z rows and open faces: the rows kernel against the oracle, T = 0 and T > 0 with the kernels' own noise"""
+    w = W.c4_bcc_long_range(8, temperature=T)
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], dims, periodic=periodic)
+    w["lattice"] = lat
+    steps, seed = 8, 77
+    s0 = random_unit_spins(lat.num_spins, 21)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    normals = None
+    res = {}
+    for variant in ("rows", "rows_small_tile", "direct"):
+        s = make(w, options=KERNELS[variant], seed=seed)
+        s.set_spins(s0)
+        if T > 0 and normals is None:
+            normals = np.stack([s.ctx.noise(s.step_size, T, seed, n, normals_only=True) for n in range(steps)])
+        s.run(steps)
+        assert s.ctx.stage_kernel() == (0 if variant == "direct" else 4)
+        res[variant] = s.spins()
+    sim.run(steps, normals)
+    for variant, got in res.items():
+        assert np.abs(got - sim.get_spins()).max() <= TRAJ_TOL, variant
 
 
 def test_error_behaviour_mirrors_the_reference():
