@@ -53,7 +53,8 @@ typedef enum jb_term {
   JB_TERM_UNIAXIAL = 1,  /* "uniaxial"      hamiltonian/uniaxial_anisotropy.cc */
   JB_TERM_ZEEMAN = 2,    /* "zeeman"        hamiltonian/zeeman.cc */
   JB_TERM_APPLIED = 3,   /* "applied-field" hamiltonian/applied_field.cc */
-  JB_TERM_TOTAL = 4      /* sum of the registered terms = globals::h after Solver::compute_fields */
+  JB_TERM_TOTAL = 4,     /* sum of the registered terms = globals::h after Solver::compute_fields */
+  JB_TERM_BIQUADRATIC = 5 /* "biquadratic-exchange" hamiltonian/cuda_biquadratic_exchange.cu */
 } jb_term;
 
 /* Lattice + slab description.  Replaces what the solver reads from globals::lattice
@@ -95,6 +96,14 @@ JB_API int jb_set_materials(jb_ctx *ctx, const double *mus, const double *gyro, 
  * without impurities. */
 JB_API int jb_set_exchange_template(jb_ctx *ctx, int32_t n, const int32_t *motif_i, const int32_t *motif_j,
                              const int32_t *T3, const double *J9);
+
+/* Biquadratic exchange (CudaBiquadraticExchangeHamiltonian, hamiltonian/cuda_biquadratic_exchange.cu:9-156): field
+ * h_i = sum_j 2 B_ij s_j (s_i . s_j) (cuda_biquadratic_exchange_kernel.cuh:5-30), per-spin energy -1/2 s_i . h_i (:235-240), total
+ * energy 1/2 sum_i -s_i . (h_i / 2) (:185-201).  Translation-invariant form like jb_set_exchange_template with one scalar B (meV,
+ * already converted; the reference keeps only values above energy_cutoff, :127-134 -- the caller filters) per entry.  n = 0 removes
+ * the term.  A step with this term runs on the direct-gather stage kernel. */
+JB_API int jb_set_biquadratic_template(jb_ctx *ctx, int32_t n, const int32_t *motif_i, const int32_t *motif_j,
+                                       const int32_t *T3, const double *B);
 
 /* Exchange, general form: the neighbour list itself, as
  * ExchangeHamiltonian::neighbour_list() exposes it (hamiltonian/exchange.h:13,

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libjams_b200.so")
 
 JB_OK, JB_ERR_INVALID, JB_ERR_CUDA, JB_ERR_UNSUPPORTED, JB_ERR_PEER = range(5)
-TERM_EXCHANGE, TERM_UNIAXIAL, TERM_ZEEMAN, TERM_APPLIED, TERM_TOTAL = range(5)
+TERM_EXCHANGE, TERM_UNIAXIAL, TERM_ZEEMAN, TERM_APPLIED, TERM_TOTAL, TERM_BIQUADRATIC = range(6)
 HALO_HANDLE_BYTES = 256
 
 
@@ -39,6 +39,7 @@ SIGNATURES = {
     "jb_abi_version": (C.c_int, []),
     "jb_set_materials": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "jb_set_exchange_template": (C.c_int, [C.c_void_p, C.c_int32, _ip, _ip, _ip, _dp]),
+    "jb_set_biquadratic_template": (C.c_int, [C.c_void_p, C.c_int32, _ip, _ip, _ip, _dp]),
     "jb_set_exchange_pairs": (C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, _ip, C.c_int32, _dp]),
     "jb_detect_exchange_template": (C.c_int, [C.POINTER(LatticeDesc), C.c_int64, _ip, _ip, _ip, C.c_int32, _dp, C.c_int32,
                                                C.POINTER(C.c_int32), _ip, _ip, _ip, _dp]),
@@ -184,6 +185,12 @@ class Context:
         T = np.ascontiguousarray(T, np.int32).reshape(-1); J9 = _f64(J9).reshape(-1)
         assert T.size == 3 * mi.size and J9.size == 9 * mi.size
         self._ck(self.lib.jb_set_exchange_template(self.h, mi.size, mi, mj, T, J9))
+
+    def set_biquadratic_template(self, mi, mj, T, B):
+        mi = np.ascontiguousarray(mi, np.int32); mj = np.ascontiguousarray(mj, np.int32)
+        T = np.ascontiguousarray(T, np.int32).reshape(-1); B = _f64(B).reshape(-1)
+        assert T.size == 3 * mi.size and B.size == mi.size
+        self._ck(self.lib.jb_set_biquadratic_template(self.h, mi.size, mi, mj, T, B))
 
     def set_exchange_pairs(self, i, j, value_id, values9):
         i = np.ascontiguousarray(i, np.int32); j = np.ascontiguousarray(j, np.int32)

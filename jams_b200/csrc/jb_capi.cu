@@ -351,6 +351,38 @@ int upload_classes(jb_ctx *c, const std::vector<double> &times, double dt, doubl
   return JB_OK;
 }
 
+// biquadratic template -> device table in ghosted-box terms, per motif site in the reference's CSR column order
+int build_biquadratic_tables(jb_ctx *c) {
+  const JbGeom &g = c->g;
+  const int n = (int)c->bq_mi.size(), M = g.M;
+  std::vector<int> order(n);
+  for (int k = 0; k < n; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (c->bq_mi[a] != c->bq_mi[b]) return c->bq_mi[a] < c->bq_mi[b];
+    for (int d = 0; d < 3; ++d) if (c->bq_T[3 * a + d] != c->bq_T[3 * b + d]) return c->bq_T[3 * a + d] < c->bq_T[3 * b + d];
+    return c->bq_mj[a] < c->bq_mj[b];
+  });
+  std::vector<JbNbr> glob(n);
+  for (int m = 0; m <= M; ++m) c->bq_begin[m] = 0;
+  for (int pos = 0; pos < n; ++pos) {
+    const int k = order[pos];
+    JbNbr e{};
+    e.dx = c->bq_T[3 * k]; e.J = c->bq_B[k];
+    e.delta = (c->bq_T[3 * k + 1] * M + (c->bq_mj[k] - c->bq_mi[k])) * g.PZ + c->bq_T[3 * k + 2];
+    glob[pos] = e;
+    c->bq_begin[c->bq_mi[k] + 1]++;
+  }
+  for (int m = 0; m < M; ++m) c->bq_begin[m + 1] += c->bq_begin[m];
+  if (c->d_bq_global) cudaFree(c->d_bq_global);
+  c->d_bq_global = nullptr;
+  if (n > 0) {
+    JB_CUDA(c, cudaMalloc(&c->d_bq_global, n * sizeof(JbNbr)));
+    JB_CUDA(c, cudaMemcpy(c->d_bq_global, glob.data(), n * sizeof(JbNbr), cudaMemcpyHostToDevice));
+  }
+  c->bq_built = true;
+  return JB_OK;
+}
+
 void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
   t.nbr_global = c->d_nbr_global; t.Jtab = c->d_Jtab;
   t.classes = c->d_classes + (size_t)class_table_index * c->h_classes.size();
@@ -359,6 +391,8 @@ void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
   for (int m = 0; m < JB_MAX_MOTIF; ++m) t.class_of_motif[m] = c->class_of_motif[m];
   t.n_classes = (int)c->h_classes.size();
   t.iso = c->iso ? 1 : 0;
+  t.bq_global = c->has_bq ? c->d_bq_global : nullptr;
+  for (int m = 0; m <= JB_MAX_MOTIF; ++m) t.bq_begin[m] = (m <= c->g.M && c->has_bq) ? c->bq_begin[m] : 0;
 }
 
 // ---- tiling of the persistent TMA tile kernel ----------------------------------------------------------
@@ -600,6 +634,7 @@ void choose_tiling(jb_ctx *c) {
   c->tiling = jb_ctx::Tiling();
   c->tiling_valid = true;
   c->tmap_valid = false;
+  if (c->has_bq) return;   // the biquadratic field needs s_i inside the neighbour loop: direct kernel
   const int reach = std::max(c->g.gx, std::max(c->g.gy, c->g.gz));
   const bool deep = c->iso && c->has_template && (reach >= 3 || (reach >= 2 && c->t_mi.size() >= (size_t)40 * c->g.M));
   if (c->opt_kernel == 4 || deep) choose_rows_tiling(c);
@@ -824,6 +859,11 @@ int ensure_ready(jb_ctx *c) {
       gx = std::max(gx, std::abs(c->t_T[3 * k])); gy = std::max(gy, std::abs(c->t_T[3 * k + 1])); gz = std::max(gz, std::abs(c->t_T[3 * k + 2]));
     }
   }
+  if (c->has_bq) {
+    for (size_t k = 0; k < c->bq_mi.size(); ++k) {
+      gx = std::max(gx, std::abs(c->bq_T[3 * k])); gy = std::max(gy, std::abs(c->bq_T[3 * k + 1])); gz = std::max(gz, std::abs(c->bq_T[3 * k + 2]));
+    }
+  }
   const JbGeom &g = c->g;
   const int reach[3] = {gx, gy, gz};
   const bool geom_changed = !c->state_allocated || gx != g.gx || gy != g.gy || gz != g.gz || c->state_relayout;
@@ -855,6 +895,7 @@ int ensure_ready(jb_ctx *c) {
       JB_CUDA(c, jbk_import(c->g, c->d_aos, dst, c->d.n_ranks == 1, c->stream)); c->launches++;
     }
     c->tables_built = false;
+    c->bq_built = false;
     c->tiling_valid = false;
     c->classes_dirty = true;
   }
@@ -863,6 +904,7 @@ int ensure_ready(jb_ctx *c) {
   int rc = build_classes(c); if (rc) return rc;
   if (classes_were_dirty) c->tiling_valid = false;
   if (c->has_template && !c->tables_built) { rc = build_template_tables(c); if (rc) return rc; }
+  if (c->has_bq && !c->bq_built) { rc = build_biquadratic_tables(c); if (rc) return rc; }
   return JB_OK;
 }
 
@@ -931,7 +973,7 @@ void jb_destroy(jb_ctx *c) {
   release_state(c);
   void *p;
   p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
-  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p); p = c->d_rows; free_dev(p);
+  p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p); p = c->d_rows; free_dev(p); p = c->d_bq_global; free_dev(p);
   p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
   p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p); p = c->d_groups; free_dev(p);
@@ -973,6 +1015,30 @@ int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int3
   c->has_template = n > 0;
   c->has_pairs = false;
   c->tables_built = false;
+  c->tiling_valid = false;
+  return JB_OK;
+}
+
+int jb_set_biquadratic_template(jb_ctx *c, int32_t n, const int32_t *mi, const int32_t *mj, const int32_t *T3, const double *B) {
+  if (!c || n < 0 || (n > 0 && (!mi || !mj || !T3 || !B))) return JB_ERR_INVALID;
+  for (int k = 0; k < n; ++k)
+    if (mi[k] < 0 || mi[k] >= c->d.num_motif || mj[k] < 0 || mj[k] >= c->d.num_motif) JB_FAIL(c, JB_ERR_INVALID, "biquadratic template: motif index out of range");
+  if (c->opt_check_symmetry) {   // sparse_matrix_builder_.is_symmetric(), cuda_biquadratic_exchange.cu:136-148
+    std::map<std::array<int, 5>, double> seen;
+    for (int k = 0; k < n; ++k) {
+      const std::array<int, 5> key{mi[k], mj[k], T3[3 * k], T3[3 * k + 1], T3[3 * k + 2]};
+      if (seen.count(key)) JB_FAIL(c, JB_ERR_INVALID, "Multiple interactions for the same motif pair and translation in the biquadratic template");
+      seen[key] = B[k];
+    }
+    for (const auto &kv : seen) {
+      const std::array<int, 5> rev{kv.first[1], kv.first[0], -kv.first[2], -kv.first[3], -kv.first[4]};
+      auto it = seen.find(rev);
+      if (it == seen.end() || it->second != kv.second) JB_FAIL(c, JB_ERR_INVALID, "sparse matrix for biquadratic-exchange is not symmetric");
+    }
+  }
+  c->bq_mi.assign(mi, mi + n); c->bq_mj.assign(mj, mj + n); c->bq_T.assign(T3, T3 + 3 * (size_t)n); c->bq_B.assign(B, B + n);
+  c->has_bq = n > 0;
+  c->bq_built = false;
   c->tiling_valid = false;
   return JB_OK;
 }
@@ -1424,7 +1490,7 @@ int jb_noise(jb_ctx *c, double dt, double T, uint64_t seed, uint64_t step, int32
 }
 
 int jb_fields(jb_ctx *c, int32_t term, double time_ps, double *h_aos, int32_t on_device) {
-  if (!c || !h_aos || term < 0 || term > JB_TERM_TOTAL) return JB_ERR_INVALID;
+  if (!c || !h_aos || term < 0 || term > JB_TERM_BIQUADRATIC) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
   std::vector<double> times{time_ps};
@@ -1444,7 +1510,7 @@ int jb_fields(jb_ctx *c, int32_t term, double time_ps, double *h_aos, int32_t on
 }
 
 int jb_energies(jb_ctx *c, int32_t term, double time_ps, double *e, int32_t on_device, double *total) {
-  if (!c || term < 0 || term >= JB_TERM_TOTAL) return JB_ERR_INVALID;
+  if (!c || term < 0 || term == JB_TERM_TOTAL || term > JB_TERM_BIQUADRATIC) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
   std::vector<double> times{time_ps};

@@ -85,6 +85,9 @@ struct JbTables {
   int class_of_motif[JB_MAX_MOTIF];
   int n_classes;
   int iso;                     // all tensors are scalar multiples of the identity
+  // biquadratic exchange (hamiltonian/cuda_biquadratic_exchange_kernel.cuh): its own template, J = B_ij in meV; null = none
+  const JbNbr *bq_global;
+  int bq_begin[JB_MAX_MOTIF + 1];
 };
 
 // ---- parameter block of the fused stage kernels --------------------------------------------------
@@ -206,6 +209,11 @@ struct jb_ctx {
   // exchange template (host)
   std::vector<int> t_mi, t_mj, t_T; std::vector<double> t_J9;
   bool has_template = false;
+  // biquadratic exchange template (host): scalar B per entry
+  std::vector<int> bq_mi, bq_mj, bq_T; std::vector<double> bq_B;
+  bool has_bq = false, bq_built = false;
+  JbNbr *d_bq_global = nullptr;
+  int bq_begin[JB_MAX_MOTIF + 1] = {0};
   // exchange pairs (host -> device ELL), general path
   bool has_pairs = false;
   int ell_width = 0;

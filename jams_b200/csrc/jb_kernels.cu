@@ -147,6 +147,24 @@ __global__ void push_x_ghosts_kernel(const JbGeom g, const double *__restrict__ 
   }
 }
 
+// biquadratic exchange, field of one site in meV added to (hx, hy, hz): sum_j 2 B_ij s_j (s_i . s_j), accumulated in the
+// reference's order ((2 B) s_j[n]) (s_i . s_j) over ascending neighbour ids (cuda_biquadratic_exchange_kernel.cuh:14-24)
+__device__ __forceinline__ void biquadratic_field_site(const JbGeom &g, const JbTables &t, const double *__restrict__ inx,
+                                                       const double *__restrict__ iny, const double *__restrict__ inz, long long ic, int m,
+                                                       double sx, double sy, double sz, double &hx, double &hy, double &hz) {
+  if (!t.bq_global) return;
+  double bx = 0.0, by = 0.0, bz = 0.0;
+  for (int n = t.bq_begin[m]; n < t.bq_begin[m + 1]; ++n) {
+    const JbNbr e = t.bq_global[n];
+    const long long j = ic + (long long)e.dx * g.sX + e.delta;
+    const double jx = inx[j], jy = iny[j], jz = inz[j];
+    const double d = sx * jx + sy * jy + sz * jz;
+    const double b2 = 2.0 * e.J;
+    bx += b2 * jx * d; by += b2 * jy * d; bz += b2 * jz * d;
+  }
+  hx += bx; hy += by; hz += bz;
+}
+
 // =================================================================================================
 // stage kernel, variant 0: direct gathers from the ghosted box through L1/L2 (one thread per spin)
 // =================================================================================================
@@ -179,6 +197,7 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
       hz += J[6] * jx + J[7] * jy + J[8] * jz;
     }
   }
+  biquadratic_field_site(g, p.t, inx, iny, inz, ic, m, sx, sy, sz, hx, hy, hz);
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
   const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
@@ -231,6 +250,7 @@ __global__ void __launch_bounds__(256) rk4_direct_kernel(const __grid_constant__
       hz += J[6] * jx + J[7] * jy + J[8] * jz;
     }
   }
+  biquadratic_field_site(g, p.t, inx, iny, inz, ic, m, sx, sy, sz, hx, hy, hz);
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
   const JbClass &c = p.t.classes[ci];
   hx = fma(hx, c.inv_mu, c.fTx); hy = fma(hy, c.inv_mu, c.fTy); hz = fma(hz, c.inv_mu, c.fTz);   // Tesla
@@ -308,6 +328,7 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
       hz += J[6] * jx + J[7] * jy + J[8] * jz;
     }
   }
+  biquadratic_field_site(g, p.t, inx, iny, inz, ic, m, sx, sy, sz, hx, hy, hz);
   const int ci = p.t.site_class ? (int)p.t.site_class[q] : p.t.class_of_motif[m];
   const JbClass &c = p.t.classes[ci];
   double n0 = 0, n1 = 0, n2 = 0;
@@ -383,6 +404,8 @@ __global__ void field_kernel(const JbGeom g, const JbTables t, const double *__r
   double hx = 0, hy = 0, hz = 0;
   if (term == JB_TERM_EXCHANGE || term == JB_TERM_TOTAL)
     exchange_field_site(g, t, inx, iny, inz, q, ic, m, ell_idx, ell_val, width, pairJ, pairs_iso, total, hx, hy, hz);
+  if (term == JB_TERM_BIQUADRATIC || term == JB_TERM_TOTAL)
+    biquadratic_field_site(g, t, inx, iny, inz, ic, m, inx[ic], iny[ic], inz[ic], hx, hy, hz);
   const int ci = t.site_class ? (int)t.site_class[q] : t.class_of_motif[m];
   const JbClass c = t.classes[ci];
   if ((term == JB_TERM_UNIAXIAL || term == JB_TERM_TOTAL) && c.power != 0) {
@@ -433,6 +456,10 @@ __global__ void __launch_bounds__(256) energy_kernel(const JbGeom g, const JbTab
       double hx, hy, hz;
       exchange_field_site(g, t, inx, iny, inz, q, ic, m, ell_idx, ell_val, width, pairJ, pairs_iso, total, hx, hy, hz);
       e = -(sx * hx + sy * hy + sz * hz);  // sparse_interaction.cc:79-84
+    } else if (term == JB_TERM_BIQUADRATIC) {
+      double hx = 0.0, hy = 0.0, hz = 0.0;
+      biquadratic_field_site(g, t, inx, iny, inz, ic, m, sx, sy, sz, hx, hy, hz);
+      e = -0.5 * (sx * hx + sy * hy + sz * hz);  // cuda_biquadratic_exchange.cu:235-240
     } else if (term == JB_TERM_UNIAXIAL) {
       if (c.power != 0) {
         const double d = c.ax * sx + c.ay * sy + c.az * sz;
@@ -702,7 +729,7 @@ cudaError_t jbk_energy(const JbGeom &g, const JbTables &t, const double *const s
   energy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(g, t, s[0], s[1], s[2], term, ell_idx, ell_val, width, pairJ, pairs_iso, e_out, scratch);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return err;
-  final_sum_kernel<<<1, 256, 0, stream>>>(scratch, (int)blocks, term == JB_TERM_EXCHANGE ? 0.5 : 1.0, total_out);
+  final_sum_kernel<<<1, 256, 0, stream>>>(scratch, (int)blocks, (term == JB_TERM_EXCHANGE || term == JB_TERM_BIQUADRATIC) ? 0.5 : 1.0, total_out);   // biquadratic: 1/2 sum_i -s_i . (h_i / 2), cuda_biquadratic_exchange.cu:185-201
   return cudaGetLastError();
 }
 

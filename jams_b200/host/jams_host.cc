@@ -324,7 +324,9 @@ std::vector<double> Lattice::positions() const {   // core/lattice.cc:622-657,75
 }
 // load_array_from_tsv_file (helpers/load.h:21-47): whitespace-separated numbers, empty lines and lines starting with '#' or '//'
 // skipped (helpers/utils.h:115-127), the element count must match
-static std::vector<double> load_spins_tsv(const std::string &file_name, size_t expected) {
+// A snapshot written by the spin-snapshot monitor starts with "# spins N x 3   iteration I   time_ps T": I is handed back so that a
+// resumed thermal run continues the noise stream (the Philox counter is the step index) instead of replaying the first segment's.
+static std::vector<double> load_spins_tsv(const std::string &file_name, size_t expected, long long *snapshot_iteration = nullptr) {
   if (file_name.size() > 3 && file_name.substr(file_name.size() - 3) == ".h5")
     throw std::runtime_error("lattice.spins: HDF5 is not available in this build; give the whitespace-separated text form (helpers/load.h:21-61)");
   std::ifstream f(file_name);
@@ -333,6 +335,10 @@ static std::vector<double> load_spins_tsv(const std::string &file_name, size_t e
   out.reserve(expected);
   for (std::string line; std::getline(f, line);) {
     const size_t a = line.find_first_not_of(" \t\r");
+    if (a != std::string::npos && line[a] == '#' && snapshot_iteration) {
+      const size_t k = line.find("iteration ");
+      if (k != std::string::npos) *snapshot_iteration = std::atoll(line.c_str() + k + 10);
+    }
     if (a == std::string::npos || line[a] == '#' || (line[a] == '/' && a + 1 < line.size() && line[a + 1] == '/')) continue;
     std::stringstream is(line);
     for (double v; is >> v;) out.push_back(v);
@@ -343,7 +349,7 @@ static std::vector<double> load_spins_tsv(const std::string &file_name, size_t e
 }
 
 std::vector<double> Lattice::initial_spins(uint64_t seed) const {   // core/lattice.cc:703-748
-  if (!spins_file.empty()) return load_spins_tsv(spins_file, 3 * static_cast<size_t>(num_spins));
+  if (!spins_file.empty()) return load_spins_tsv(spins_file, 3 * static_cast<size_t>(num_spins), &snapshot_iteration);
   std::vector<double> s(3 * static_cast<size_t>(num_spins));
   std::mt19937_64 rng(seed);   // the reference seeds pcg32 from std::random_device here: "random" spins are unpinned by design
   std::normal_distribution<double> nd;
@@ -499,6 +505,7 @@ Hamiltonian *Hamiltonian::create(const Setting &settings, const Lattice &lattice
   if (module == "uniaxial") return new UniaxialAnisotropyHamiltonian(settings, lattice);
   if (module == "zeeman") return new ZeemanHamiltonian(settings, lattice);
   if (module == "applied-field") return new AppliedFieldHamiltonian(settings, lattice);
+  if (module == "biquadratic-exchange") return new BiquadraticExchangeHamiltonian(settings, lattice);
   throw std::runtime_error("unknown hamiltonian " + module + " (not on the llg-heun-b200-gpu path)");
 }
 
@@ -551,9 +558,13 @@ static std::vector<InteractionInput> read_interaction_file(const std::string &pa
 
 ExchangeHamiltonian::ExchangeHamiltonian(const Setting &s, const Lattice &lattice) : Hamiltonian(s, lattice) {
   check_symmetry_ = s.get("check_sparse_matrix_symmetry", true);
+  parse_interactions(s, lattice, s.get("interaction_prefactor", 1.0));
+}
+
+void ExchangeHamiltonian::parse_interactions(const Setting &s, const Lattice &lattice, double prefactor) {
   const bool use_symops = s.get("symops", true);
   const double energy_cutoff = s.get("energy_cutoff", 0.0), radius_cutoff = s.get("radius_cutoff", 100.0);
-  const double distance_tolerance = s.get("distance_tolerance", kLatticeTolerance), prefactor = s.get("interaction_prefactor", 1.0);
+  const double distance_tolerance = s.get("distance_tolerance", kLatticeTolerance);
   const std::string coord = lowercase(s.get("coordinate_format", "cartesian"));
   if (coord != "cartesian" && coord != "fractional") throw std::runtime_error("Unknown coordinate format for exchange interactions");
   std::vector<InteractionInput> inputs;
@@ -958,7 +969,10 @@ Monitor *Monitor::create(const Setting &settings, const Lattice &lattice, const 
   if (module == "magnetisation") return new MagnetisationMonitor(settings, lattice, prefix + "mag.tsv");
   if (module == "energy") return new EnergyMonitor(settings, prefix + "eng.tsv");
   if (module == "magnetisation-layers") return new MagnetisationLayersMonitor(settings, lattice, prefix + "mag_layers.tsv");
-  if (module == "hdf5" || module == "spins-tsv") return new SpinsTsvMonitor(settings, prefix);
+  if (module == "hdf5" || module == "spins-tsv") {
+    if (module == "hdf5") std::fprintf(stderr, "jams-b200: monitor 'hdf5': HDF5 is not available in this build, spin snapshots are written as text (%sNNNNNNN.tsv, %sfinal.tsv)\n", prefix.c_str(), prefix.c_str());
+    return new SpinsTsvMonitor(settings, prefix);
+  }
   throw std::runtime_error("unknown monitor " + module + " (not supported by the llg-heun-b200-gpu host layer)");
 }
 
@@ -1127,6 +1141,7 @@ B200HeunLLGSolver::B200HeunLLGSolver(const Setting &settings, const Lattice &lat
   d.device = settings.get("device", -1);
   if (jb_create(&ctx_, &d) != JB_OK) throw std::runtime_error(std::string("jams_b200: ") + jb_last_error(nullptr));
   spins0_ = lattice.initial_spins(seed);
+  noise_step_offset_ = static_cast<uint64_t>(std::max<long long>(0, lattice.snapshot_iteration));   // resumed run: continue the noise stream
   physics_.reset(new Physics(nullptr));
 }
 
@@ -1165,7 +1180,7 @@ std::vector<double> B200HeunLLGSolver::spins() {
 
 void B200HeunLLGSolver::run_steps(int n) {
   build();
-  check((rk4_ ? jb_step_rk4 : jb_step)(ctx_, n, step_size_, time_, physics_->temperature(), seed_, static_cast<uint64_t>(iteration_),
+  check((rk4_ ? jb_step_rk4 : jb_step)(ctx_, n, step_size_, time_, physics_->temperature(), seed_, noise_step_offset_ + static_cast<uint64_t>(iteration_),
                                        lattice_.gilbert_prefactor ? 1 : 0));
   iteration_ += n;
   time_ = iteration_ * step_size_;   // solvers/cuda_llg_heun.cu:120-121
@@ -1231,6 +1246,26 @@ void ExchangeHamiltonian::attach(jb_ctx *ctx) {
   // check_sparse_matrix_symmetry = false switches the symmetry check off (hamiltonian/exchange.cc:104-110); default: checked
   solver->check(jb_set_option(ctx, "check_symmetry", check_symmetry_ ? 1 : 0));
   solver->check(jb_set_exchange_template(ctx, template_.size(), template_.mi.data(), template_.mj.data(), template_.T3.data(), template_.J9.data()));
+}
+// hamiltonian/cuda_biquadratic_exchange.cu:9-156: the exchange grammar, scalar B = J[0][0] * unit (no interaction_prefactor), only
+// values above energy_cutoff are inserted (:131)
+BiquadraticExchangeHamiltonian::BiquadraticExchangeHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  parse_interactions(s, lattice, 1.0);
+  const double cutoff = s.get("energy_cutoff", 0.0) * input_energy_unit_conversion_;
+  InteractionTemplate kept;
+  for (int k = 0; k < template_.size(); ++k) {
+    const double B = template_.J9[9 * static_cast<size_t>(k)];
+    if (!(B > cutoff)) continue;
+    kept.mi.push_back(template_.mi[k]); kept.mj.push_back(template_.mj[k]);
+    for (int d = 0; d < 3; ++d) kept.T3.push_back(template_.T3[3 * static_cast<size_t>(k) + d]);
+    B_.push_back(B);
+  }
+  kept.J9.clear();
+  template_ = kept;
+}
+void BiquadraticExchangeHamiltonian::attach(jb_ctx *ctx) {
+  solver->check(jb_set_option(ctx, "check_symmetry", check_symmetry_ ? 1 : 0));
+  solver->check(jb_set_biquadratic_template(ctx, static_cast<int32_t>(B_.size()), template_.mi.data(), template_.mj.data(), template_.T3.data(), B_.data()));
 }
 void UniaxialAnisotropyHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_uniaxial(ctx, power_, magnitude_.data(), axis_.data())); }
 void ZeemanHamiltonian::attach(jb_ctx *ctx) {

@@ -107,6 +107,7 @@ class Lattice {
   std::vector<double> initial_spins(uint64_t seed) const;   // N x 3; "random" materials use a seeded uniform-on-sphere draw;
                                                             // lattice.spins = "file" replaces them (core/lattice.cc:738-748)
   std::string spins_file;                                   // lattice.spins
+  mutable long long snapshot_iteration = 0;                 // iteration recorded in the header of a loaded snapshot (0 = none)
   std::vector<double> positions() const;                    // N x 3, lattice constants
   std::vector<int32_t> site_material() const, site_motif() const;
 
@@ -156,8 +157,20 @@ class ExchangeHamiltonian : public Hamiltonian {   // hamiltonian/exchange.cc:12
   ExchangeHamiltonian(const Setting &settings, const Lattice &lattice, NoParse) : Hamiltonian(settings, lattice) {
     check_symmetry_ = settings.get("check_sparse_matrix_symmetry", true);
   }
+  void parse_interactions(const Setting &settings, const Lattice &lattice, double prefactor);   // 'interactions' / 'exc_file' -> template_
   InteractionTemplate template_;
   bool check_symmetry_ = true;
+};
+
+// hamiltonian/cuda_biquadratic_exchange.{h,cu}: E = -1/2 sum_ij B_ij (s_i . s_j)^2, field h_i = sum_j 2 B_ij s_j (s_i . s_j); the
+// exchange grammar with the scalar B_ij = J[0][0]
+class BiquadraticExchangeHamiltonian : public ExchangeHamiltonian {
+ public:
+  BiquadraticExchangeHamiltonian(const Setting &settings, const Lattice &lattice);
+  int term() const override { return JB_TERM_BIQUADRATIC; }
+  void attach(jb_ctx *ctx) override;
+ private:
+  std::vector<double> B_;   // meV per template entry
 };
 
 // hamiltonian/exchange_functional.{h,cc}: isotropic J(r_ij) from a closed form inside a cutoff radius per ordered material pair
@@ -360,6 +373,7 @@ class B200HeunLLGSolver {   // core/solver.h:15-90 + solvers/cuda_llg_heun.cu:21
   bool built_ = false;
   bool rk4_ = false;      // module "llg-rk4-b200-gpu" / "llg-rk4-gpu": CudaRK4BaseSolver::run (solvers/cuda_rk4_base.cu:50-108)
   int iteration_ = 0, max_steps_ = 0, min_steps_ = 0;
+  uint64_t noise_step_offset_ = 0;   // added to the step index of the noise stream (resumed runs)
   double time_ = 0.0, step_size_ = 1.0;
   uint64_t seed_ = 0;
   std::vector<double> spins0_;

@@ -105,6 +105,40 @@ class ExchangeHamiltonian(Hamiltonian):
             ctx.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
 
 
+class BiquadraticExchangeHamiltonian(Hamiltonian):
+    """``module = "biquadratic-exchange"`` (hamiltonian/cuda_biquadratic_exchange.{h,cu}): E = -1/2 sum_ij B_ij (s_i . s_j)^2 with the
+    field h_i = sum_j 2 B_ij s_j (s_i . s_j).  Same ``interactions`` / ``exc_file`` grammar and cutoffs as ``exchange``; the scalar
+    B_ij is element [0][0] of the interaction tensor times the unit conversion (no ``interaction_prefactor``), and only values
+    above ``energy_cutoff`` are kept (cuda_biquadratic_exchange.cu:127-134: negative couplings are dropped at the default cutoff
+    of 0, as in the reference)."""
+    term = capi.TERM_BIQUADRATIC
+    name = "biquadratic-exchange"
+
+    def __init__(self, settings: dict, lattice: Lattice):
+        super().__init__(settings, lattice)
+        s = self.settings
+        if "exc_file" in s:
+            from .lattice import read_interaction_file
+            interactions = read_interaction_file(s["exc_file"])
+        elif "interactions" in s:
+            interactions = s["interactions"]
+        else:
+            raise RuntimeError("'exc_file' or 'interactions' settings are required for exchange hamiltonian")
+        t = lattice.expand_interactions(
+            interactions, energy_units=self.input_energy_unit_name,
+            coordinate_format=s.get("coordinate_format", "cartesian"), use_symops=s.get("symops", True),
+            energy_cutoff=s.get("energy_cutoff", 0.0), radius_cutoff=s.get("radius_cutoff", 100.0),
+            distance_tolerance=s.get("distance_tolerance", 1e-4), interaction_prefactor=1.0)
+        B = np.asarray(t["J9"], dtype=np.float64).reshape(-1, 9)[:, 0]
+        keep = B > s.get("energy_cutoff", 0.0) * self.input_energy_unit_conversion
+        self.template = dict(mi=np.asarray(t["mi"])[keep], mj=np.asarray(t["mj"])[keep], T=np.asarray(t["T"]).reshape(-1, 3)[keep], B=B[keep])
+
+    def attach(self, ctx, x0, nx):
+        ctx.set_option("check_symmetry", 0 if self.settings.get("check_sparse_matrix_symmetry", True) is False else 1)
+        t = self.template
+        ctx.set_biquadratic_template(t["mi"], t["mj"], t["T"], t["B"])
+
+
 class ExchangeFunctionalHamiltonian(ExchangeHamiltonian):
     """``module = "exchange-functional"`` (hamiltonian/exchange_functional.{h,cc}): isotropic exchange J(r_ij) from a closed
     form inside a cutoff radius, one entry per ordered material pair:
@@ -357,7 +391,7 @@ class AppliedFieldHamiltonian(Hamiltonian):
 
 _HAMILTONIANS = {"exchange": ExchangeHamiltonian, "exchange-functional": ExchangeFunctionalHamiltonian,
                  "exchange-neartree": ExchangeNeartreeHamiltonian, "uniaxial": UniaxialAnisotropyHamiltonian,
-                 "zeeman": ZeemanHamiltonian, "applied-field": AppliedFieldHamiltonian}
+                 "zeeman": ZeemanHamiltonian, "applied-field": AppliedFieldHamiltonian, "biquadratic-exchange": BiquadraticExchangeHamiltonian}
 
 
 def create_hamiltonian(settings: dict, lattice: Lattice) -> Hamiltonian:

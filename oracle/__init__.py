@@ -76,6 +76,7 @@ class _Lib:
         self.sim_add_uniaxial = sig("sim_add_uniaxial", C.c_int, C.c_void_p, C.c_int, _c_double_p, _c_double_p)
         self.sim_add_zeeman = sig("sim_add_zeeman", C.c_int, C.c_void_p, _c_double_p, C.c_void_p, C.c_void_p)
         self.sim_add_applied_field = sig("sim_add_applied_field", C.c_int, C.c_void_p, _c_double_p, C.c_int, C.c_double, C.c_double, C.c_double, optional=True)
+        self.sim_add_biquadratic = sig("sim_add_biquadratic", C.c_int, C.c_void_p, C.c_int64, _c_int_p, _c_int_p, _c_double_p, C.c_int, optional=True)
         self.sim_exchange_nnz = sig("sim_exchange_nnz", C.c_int64, C.c_void_p, C.c_int)
         self.sim_exchange_csr = sig("sim_exchange_csr", None, C.c_void_p, C.c_int, _c_int_p, _c_int_p, _c_double_p)
         self.sim_set_spins = sig("sim_set_spins", None, C.c_void_p, _c_double_p)
@@ -304,6 +305,14 @@ class CpuSim:
 
     def add_exchange(self, i, j, J9_per_pair, check_symmetric=True):
         self._check(self.L.sim_add_exchange(self.h, len(i), _i32(i), _i32(j), _f64(J9_per_pair, (-1,)), int(check_symmetric)))
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_biquadratic(self, i, j, B_per_pair, check_symmetric=True):
+        """CudaBiquadraticExchangeHamiltonian (hamiltonian/cuda_biquadratic_exchange.cu): scalar N x N matrix; restatement only"""
+        if getattr(self.L, "sim_add_biquadratic", None) is None:
+            raise RuntimeError("this oracle build has no biquadratic-exchange term")
+        self._check(self.L.sim_add_biquadratic(self.h, len(i), _i32(i), _i32(j), _f64(B_per_pair, (-1,)), int(check_symmetric)))
         self.n_terms += 1
         return self.n_terms - 1
 

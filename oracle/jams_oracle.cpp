@@ -437,7 +437,7 @@ void jo_init_bloch_domain_wall(int64_t N, const double *positions, double width,
 namespace {
 
 struct Term {
-  enum Kind { EXCHANGE, UNIAXIAL, ZEEMAN, APPLIED } kind;
+  enum Kind { EXCHANGE, UNIAXIAL, ZEEMAN, APPLIED, BIQUADRATIC } kind;   // BIQUADRATIC: row / col / val are the N x N scalar CSR
   std::vector<double> field;  // N x 3 (Hamiltonian::field_, core/hamiltonian.h)
   // exchange CSR (containers/sparse_matrix.h:270-275)
   std::vector<int> row, col;
@@ -508,6 +508,20 @@ void calculate_fields(Sim &sim, Term &t, double time) {
       for (int i = 0; i < N; ++i) for (int j = 0; j < 3; ++j) t.field[3 * i + j] = sim.mus[i] * b[j];
       break;
     }
+    case Term::BIQUADRATIC:  // hamiltonian/cuda_biquadratic_exchange_kernel.cuh:5-30 (the only field implementation of this term)
+      for (int idx = 0; idx < N; ++idx) {
+        double h_i[3] = {0.0, 0.0, 0.0};
+        double s_i[3] = {sim.s[3 * idx + 0], sim.s[3 * idx + 1], sim.s[3 * idx + 2]};
+        for (auto m = t.row[idx]; m < t.row[idx + 1]; ++m) {
+          auto j = t.col[m];
+          double s_j[3] = {sim.s[3 * j + 0], sim.s[3 * j + 1], sim.s[3 * j + 2]};
+          double B_ij = t.val[m];
+          double s_i_dot_s_j = s_i[0] * s_j[0] + s_i[1] * s_j[1] + s_i[2] * s_j[2];
+          for (auto n = 0; n < 3; ++n) h_i[n] += 2.0 * B_ij * s_j[n] * s_i_dot_s_j;
+        }
+        for (auto n = 0; n < 3; ++n) t.field[3 * idx + n] = h_i[n];
+      }
+      break;
   }
 }
 
@@ -720,6 +734,52 @@ int jo_sim_add_exchange(void *p, int64_t n_pairs, const int *i, const int *j, co
   });
 }
 
+// CudaBiquadraticExchangeHamiltonian ctor (hamiltonian/cuda_biquadratic_exchange.cu:127-156): insert(i, j, value) for every pair of the
+// neighbour list (the caller applies the value > energy_cutoff filter of :131), Builder sort / merge / is_symmetric / build_csr as for
+// the exchange matrix, here N x N with one scalar per pair
+int jo_sim_add_biquadratic(void *p, int64_t n_pairs, const int *i, const int *j, const double *B, int check_symmetric) {
+  auto *sim = static_cast<Sim *>(p);
+  return guarded([&]() {
+    const int num_rows = sim->N;
+    std::vector<int> row_(i, i + n_pairs), col_(j, j + n_pairs);
+    std::vector<double> val_(B, B + n_pairs);
+    for (int64_t q = 0; q < n_pairs; ++q)
+      if (row_[q] >= num_rows || row_[q] < 0 || col_[q] >= num_rows || col_[q] < 0) throw std::runtime_error("Invalid index for sparse matrix");
+    std::vector<std::size_t> permutation(col_.size());
+    std::iota(permutation.begin(), permutation.end(), 0);
+    std::sort(permutation.begin(), permutation.end(), [&](std::size_t a, std::size_t b) {
+      if (row_[a] < row_[b]) return true;
+      if (row_[a] == row_[b]) return col_[a] < col_[b];
+      return false; });
+    auto apply = [&](auto &v) { auto tmp = v; for (std::size_t n = 0; n < permutation.size(); ++n) tmp[n] = v[permutation[n]]; v.swap(tmp); };
+    apply(row_); apply(col_); apply(val_);
+    for (std::size_t m = 1; m < row_.size(); ++m) {
+      if (row_[m] == row_[m - 1] && col_[m] == col_[m - 1]) {
+        val_[m - 1] += val_[m];
+        val_.erase(val_.begin() + m); row_.erase(row_.begin() + m); col_.erase(col_.begin() + m);
+      }
+    }
+    if (check_symmetric) {
+      for (std::size_t n = 0; n < row_.size(); ++n) {
+        const int ii = row_[n], jj = col_[n];
+        auto lo = std::lower_bound(row_.cbegin(), row_.cend(), jj);
+        if (lo == row_.cend() || *lo != jj) throw std::runtime_error("sparse matrix for biquadratic-exchange is not symmetric");
+        auto hi = std::upper_bound(lo, row_.cend(), jj);
+        auto cb = col_.cbegin() + (lo - row_.cbegin()), ce = col_.cbegin() + (hi - row_.cbegin());
+        auto pos = std::lower_bound(cb, ce, ii);
+        if (pos == ce || *pos != ii || val_[pos - col_.cbegin()] != val_[n]) throw std::runtime_error("sparse matrix for biquadratic-exchange is not symmetric");
+      }
+    }
+    Term t; t.kind = Term::BIQUADRATIC;
+    t.field.assign(3 * sim->N, 0.0);
+    t.row.assign(num_rows + 1, 0);
+    for (std::size_t m = 0; m < row_.size(); ++m) t.row[row_[m] + 1]++;
+    for (int r = 0; r < num_rows; ++r) t.row[r + 1] += t.row[r];
+    t.col = col_; t.val = val_;
+    sim->terms.push_back(std::move(t));
+  });
+}
+
 int jo_sim_add_uniaxial(void *p, int power, const double *magnitude, const double *axis) {
   auto *sim = static_cast<Sim *>(p);
   Term t; t.kind = Term::UNIAXIAL; t.power = power;
@@ -836,6 +896,16 @@ double jo_sim_term_total_energy(void *p, int term, double time) {
       }
       return e_total;
     }
+    case Term::BIQUADRATIC: {  // cuda_biquadratic_exchange.cu:185-201: total += -dot(s_i, 0.5 * h_i); return 0.5 * total
+      calculate_fields(*sim, t, time);
+      double total_energy = 0.0;
+      for (int i = 0; i < N; ++i) {
+        V3 s_i = {sim->s[3 * i], sim->s[3 * i + 1], sim->s[3 * i + 2]};
+        V3 h_i = {0.5 * t.field[3 * i], 0.5 * t.field[3 * i + 1], 0.5 * t.field[3 * i + 2]};
+        total_energy += -dot(s_i, h_i);
+      }
+      return 0.5 * total_energy;
+    }
   }
   return 0.0;
 }
@@ -846,10 +916,13 @@ void jo_sim_term_energies(void *p, int term, double time, double *e) {
   auto *sim = static_cast<Sim *>(p);
   auto &t = sim->terms.at(term);
   const int N = sim->N;
-  if (t.kind == Term::EXCHANGE) calculate_fields(*sim, t, time);
+  if (t.kind == Term::EXCHANGE || t.kind == Term::BIQUADRATIC) calculate_fields(*sim, t, time);
   for (int i = 0; i < N; ++i) {
     V3 s_i = {sim->s[3 * i], sim->s[3 * i + 1], sim->s[3 * i + 2]};
     switch (t.kind) {
+      case Term::BIQUADRATIC:   // calculate_energy (cuda_biquadratic_exchange.cu:235-240): -0.5 * dot(s_i, field)
+        e[i] = -0.5 * dot(s_i, V3{t.field[3 * i], t.field[3 * i + 1], t.field[3 * i + 2]});
+        break;
       case Term::EXCHANGE: e[i] = -dot(s_i, V3{t.field[3 * i], t.field[3 * i + 1], t.field[3 * i + 2]}); break;
       case Term::UNIAXIAL: {
         double d = (t.axis[3 * i] * s_i[0] + t.axis[3 * i + 1] * s_i[1] + t.axis[3 * i + 2] * s_i[2]);

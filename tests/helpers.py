@@ -133,6 +133,12 @@ def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
         if module == "exchange":
             i, j, J9, _ = oracle_exchange_pairs(lat, hs)
             terms[module] = sim.add_exchange(i, j, J9)
+        elif module == "biquadratic-exchange":
+            # cuda_biquadratic_exchange.cu:127-134: value = unit * J[0][0] (no interaction_prefactor), kept only if value > energy_cutoff * unit
+            unit = ENERGY_UNITS[hs.get("energy_units", "joules")]
+            i, j, J9, _ = oracle_exchange_pairs(lat, dict(hs, interaction_prefactor=1.0))
+            keep = J9[:, 0] > hs.get("energy_cutoff", 0.0) * unit
+            terms[module] = sim.add_biquadratic(i[keep], j[keep], J9[keep, 0], hs.get("check_sparse_matrix_symmetry", True))
         elif module == "exchange-functional":
             i, j, J9 = workload["functional_pairs"]   # brute-force list built by the test (brute_force_functional_pairs)
             terms[module] = sim.add_exchange(i, j, J9)

@@ -503,6 +503,37 @@ def test_thermal_equilibrium_statistics_match_the_reference_arithmetic_and_the_t
     assert 0.0 < gm < 1.0
 
 
+def test_MT_sweep_with_chained_temperatures_matches_the_reference_arithmetic():
+    """BASELINE config 3 is an M(T) sweep: one chained run over temperatures (the state of T_k starts T_k+1), GPU with its Philox
+    noise against the oracle with its own generator, through the ordered phase, near and above the Curie temperature
+    (k_B T_c = 1.44 J -> 366 K for J = 3.5e-21 J).  Error bars: block standard errors of both runs + the oracle's seed-to-seed
+    spread (0.002 ordered, ~0.01 near T_c at this size)."""
+    sys_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mt_sweep", os.path.join(sys_path, "mt_sweep.py"))
+    mt = importlib.util.module_from_spec(spec); spec.loader.exec_module(mt)
+    temps, equil, meas, every, dims = [100.0, 200.0, 300.0, 450.0], 1500, 3000, 10, (16, 16, 16)
+    lat, got = mt.sweep(0, temps, equil, meas, every, dims=dims, log=lambda *a: None)
+    w = dict(name="mt", lattice=lat, spins=None, temperature=temps[0],
+             hamiltonians=[dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 3.5e-21)]), dict(module="zeeman", dc_local_field=[[0.0, 0.0, 1.0]])])
+    sim = build_cpu_sim(w, dt_ps=5e-16 / 1e-12, seed=5)
+    sim.set_spins(np.tile([0.0, 0.0, 1.0], (lat.num_spins, 1)))
+    prev = 1.0
+    for T, g in zip(temps, got):
+        sim.set_temperature(T)
+        sim.run(equil)
+        mz = []
+        for _ in range(meas // every):
+            sim.run(every)
+            mz.append(sim.get_spins()[:, 2].mean())
+        cm = float(np.mean(mz))
+        tol = 0.01 if T < 250 else 0.03
+        assert abs(g["mz"] - cm) <= tol + 3 * g["mz_err"], (T, g, cm)
+        assert g["mz"] < prev   # the magnetisation falls monotonically along the sweep
+        prev = g["mz"]
+    assert got[0]["mz"] > 0.85 and got[-1]["mz"] < 0.25
+
+
 # ---- edge cases: vacancies, no exchange at all, empty step counts, sizes beyond one slab ----
 @pytest.mark.parametrize("variant", ["direct", "pair", "pair_store_u", "pair_small_tile"])
 def test_vacancies_stay_zero_and_do_not_act_on_their_neighbours(variant):
@@ -644,6 +675,59 @@ def test_bench_code_path_matches_oracle(dims, T):
         got = s.spins()
         assert np.abs(got - want).max() <= TRAJ_TOL, (variant, dims, T)
         s.ctx.close()
+
+
+@pytest.mark.parametrize("solver_module", ["llg-heun-b200-gpu", "llg-rk4-b200-gpu"])
+def test_biquadratic_exchange_fields_energies_and_trajectory_match_oracle(solver_module):
+    """module = "biquadratic-exchange" (hamiltonian/cuda_biquadratic_exchange.{cu,kernel.cuh}): h_i = sum_j 2 B_ij s_j (s_i . s_j) next
+    to bilinear exchange and a uniaxial term on bcc (NN + NNN biquadratic shells; a negative coupling is dropped by the reference's
+    value > energy_cutoff filter and must be dropped here).  Fields and per-spin energies per term, the reference's total (half the
+    sum of the per-spin energies), T = 0 Heun and RK4 trajectories, a same-noise T > 0 Heun trajectory.  The reference has no test or
+    CPU field implementation of this term: the oracle restates the CUDA kernel, parity is unpinned by reference vectors."""
+    from jams_b200.solver import create_solver
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 7), periodic=(True, True, False))
+    hams = [dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21)]),
+            dict(module="biquadratic-exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 0.8e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 0.3e-21),
+                                                             ("Fe", "Fe", [1.0, 1.0, 0.0], -0.2e-21)]),
+            dict(module="uniaxial", order="K1", anisotropies=[("Fe", [0.0, 0.0, 1.0], 1e-23)])]
+    w = dict(name="bq", lattice=lat, hamiltonians=hams, spins=None, temperature=0.0)
+    s0 = random_unit_spins(lat.num_spins, 31)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    rk4 = "rk4" in solver_module
+    s = create_solver(dict(module=solver_module, t_step=1e-16, t_max=1e-9, seed=3), lat)
+    for h in hams:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    bq = s.hamiltonians[1]
+    assert len(bq.template["B"]) == 2 * (8 + 6) and (bq.template["B"] > 0).all()     # the negative shell is gone
+    s.set_spins(s0)
+    total = np.zeros_like(s0)
+    for h in s.hamiltonians:
+        key = h.settings["module"].lower()
+        ref_f = sim.term_fields(sim.terms[key], 0.0)
+        f = h.calculate_fields(0.0)
+        assert np.abs(f - ref_f).max() <= 1e-13 * np.abs(ref_f).max(), key
+        total += ref_f
+        e, tot = s.ctx.energies(h.term, 0.0)
+        assert np.abs(e - sim.term_energies(sim.terms[key])).max() <= 1e-12 * np.abs(e).max(), key
+        assert abs(tot - sim.term_total_energy(sim.terms[key], 0.0)) <= 1e-12 * abs(tot), key
+    assert np.abs(s.compute_fields() - total).max() <= 1e-13 * np.abs(total).max()
+    steps = 30
+    (sim.run_rk4 if rk4 else sim.run)(steps)
+    s.run(steps)
+    assert s.ctx.stage_kernel() in (-1, 0)    # direct gathers (-1: the RK4 solver does not go through jb_step)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+    if not rk4:   # same-noise T > 0
+        T, seed = 120.0, 3
+        s.set_temperature(T)
+        s.set_spins(s0)
+        it0 = s.iteration
+        normals = np.stack([s.ctx.noise(s.step_size, T, seed, it0 + n, normals_only=True) for n in range(10)])
+        sim2 = build_cpu_sim(dict(w, temperature=T))
+        sim2.set_spins(s0)
+        sim2.run(10, normals)
+        s.run(10)
+        assert np.abs(s.spins() - sim2.get_spins()).max() <= TRAJ_TOL
 
 
 def test_exchange_symmetry_guard_mirrors_the_reference():

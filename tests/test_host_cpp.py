@@ -213,6 +213,15 @@ def test_checkpoint_and_restart_through_the_spin_snapshot_monitor(tmp_path):
                        name="rest", output_dir=str(tmp_path))
     assert n == 20
     assert np.array_equal(rest, full)
+    # T > 0: the snapshot header carries the iteration, the resumed run continues the Philox noise stream (step index = counter) instead
+    # of replaying the first segment's draws -- so it, too, equals the uninterrupted run bit for bit
+    hot = 'physics : { temperature = 50.0; }; '
+    full, _ = host.run(cfg, PATCH_B200, mon, hot, name="fullT", output_dir=str(tmp_path))
+    half, _ = host.run(cfg, PATCH_B200, mon, hot, 'solver : { t_max = 2e-15; };', name="halfT", output_dir=str(tmp_path))
+    rest, n = host.run(cfg, PATCH_B200, hot, 'solver : { t_max = 2e-15; }; lattice : { spins = "%s"; };' % (tmp_path / "halfT_final.tsv"),
+                       name="restT", output_dir=str(tmp_path))
+    assert n == 20 and np.abs(half - full).max() > 1e-9
+    assert np.array_equal(rest, full)
 
 
 @pytest.mark.gpu

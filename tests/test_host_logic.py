@@ -300,3 +300,23 @@ def test_exchange_functional_template_equals_a_brute_force_pair_search():
                      (dict(settings, distance_units="furlongs"), "distance units")):
         with pytest.raises(RuntimeError, match=msg):
             create_hamiltonian(bad, lat)
+
+
+def test_biquadratic_template_keeps_only_couplings_above_the_cutoff_and_matches_the_oracle_pairs():
+    """cuda_biquadratic_exchange.cu:127-134: B_ij = unit * J[0][0], inserted only if it exceeds energy_cutoff * unit"""
+    from helpers import oracle_exchange_pairs
+    lat = Lattice([Material("Fe", 2.2)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (4, 4, 4))
+    hs = dict(module="biquadratic-exchange", energy_units="meV", interaction_prefactor=7.0,   # the prefactor is not a setting of this module
+              interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 0.5), ("Fe", "Fe", [1.0, 0.0, 0.0], 0.2), ("Fe", "Fe", [1.0, 1.0, 0.0], -0.1)])
+    h = create_hamiltonian(hs, lat)
+    t = h.template
+    assert len(t["B"]) == 2 * (8 + 6) and set(np.round(t["B"], 12)) == {0.5, 0.2}
+    i, j, J9, _ = oracle_exchange_pairs(lat, dict(hs, interaction_prefactor=1.0))
+    keep = J9[:, 0] > 0.0
+    # expand the template over the lattice and compare with the oracle's neighbour list as (i, j, B) sets
+    nl = lat.neighbour_list(dict(mi=t["mi"], mj=t["mj"], T=t["T"], J9=np.repeat(t["B"][:, None], 9, axis=1)))
+    got = sorted(zip(nl[0].tolist(), nl[1].tolist(), np.round(nl[3][nl[2]][:, 0], 12).tolist()))
+    want = sorted(zip(i[keep].tolist(), j[keep].tolist(), np.round(J9[keep, 0], 12).tolist()))
+    assert got == want and len(got) == lat.num_spins * 14
+    hs_cut = dict(hs, energy_cutoff=0.3)
+    assert len(create_hamiltonian(hs_cut, lat).template["B"]) == 2 * 8
