@@ -595,7 +595,7 @@ static void choose_rows_tiling(jb_ctx *c) {
     if (TY - JB_ROWS_Q >= g.Ny && !c->opt_TY) continue;   // taller than the lattice
     const int BY = TY + 2 * g.gy;
     const int slotS = (BY * g.M * t.BZ + 15) / 16 * 16;
-    const size_t smem = (size_t)R * 3 * slotS * 8 + 448 + (size_t)n_rows * sizeof(JbRowSeg);
+    const size_t smem = (size_t)R * 3 * slotS * 8 + 512 + (size_t)n_rows * sizeof(JbRowSeg);   // rings + barriers / item ring / face counters + segments
     if (smem > limit || BY * g.M > 256 || t.BZ > 256) continue;
     int ms = 0;
     const int max_warps = c->opt_rows_warps > 0 ? std::min(c->opt_rows_warps, JB_ROWS_MAX_WARPS) : JB_ROWS_MAX_WARPS;
@@ -1394,9 +1394,8 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
             h.sig_hi = c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr;
             h.wait_epoch = c->epoch; h.signal_epoch = c->epoch + 1;
             h.face_count = c->d_queue + 2;
-            const unsigned int n_cw = (unsigned int)((c->tiling.threads + 31) / 32);
-            h.face_target[0] = n_cw * (unsigned int)sh.face_items[0];
-            h.face_target[1] = n_cw * (unsigned int)sh.face_items[1];
+            h.face_target[0] = (unsigned int)sh.face_items[0];   // one CTA-level arrival per face item (halo_face_done)
+            h.face_target[1] = (unsigned int)sh.face_items[1];
           }
           const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
           const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};

@@ -135,8 +135,8 @@ struct JbHalo {
   unsigned long long *sig_hi;     // the hi neighbour's flag that I write (its [0]), or null
   unsigned long long wait_epoch;  // both neighbours must have published this epoch before I touch ghost planes
   unsigned long long signal_epoch;
-  unsigned int *face_count;       // [0] lo, [1] hi: consumer warps that have finished a face item (reset by the last one)
-  unsigned int face_target[2];    // consumer warps x face items per side
+  unsigned int *face_count;       // [0] lo, [1] hi: finished face items, counted once per CTA and item (reset by the last one)
+  unsigned int face_target[2];    // face items per side
   int enabled;
 };
 // one segment of the exchange template as the rows kernel (jb_stage_rows.cu) sees it: up to five entries of a motif site that

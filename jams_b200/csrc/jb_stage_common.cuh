@@ -7,6 +7,8 @@
 #include "jb_tma.cuh"
 
 #define JB_PAIR_BARS JB_PAIR_MAX_RING
+// shared memory after the rings: 4 x JB_PAIR_BARS mbarriers, the item ring (JB_ITEM_RING ints), two face-arrival counters + pad
+#define JB_STAGE_TAIL_WORDS (4 * JB_PAIR_BARS + JB_ITEM_RING / 2 + 2)   // in 8-byte words; the tables (16-byte aligned) follow
 
 namespace jbdev {
 
@@ -30,12 +32,20 @@ static __device__ __noinline__ void halo_poll(unsigned long long *flags, int sid
   asm volatile("fence.proxy.async;" ::: "memory");   // the TMA engine (async proxy) reads what the neighbour's generic stores wrote
 }
 
-// a consumer warp has finished a face item of `side`: the last one of the launch tells the neighbour
-static __device__ __noinline__ void halo_face_done(const JbHalo &h, int side) {
+// a consumer warp has finished a face item of `side`.  The warps of a CTA first meet at a counter in shared memory (acq_rel at
+// CTA scope: whoever completes a multiple of n_cw arrivals has observed the stores of all earlier arrivals), and only that
+// warp pays for the system-scope fence and the global counter; the last CTA-level arrival of the launch tells the neighbour.
+// (Round 2 first did fence + global atomic per WARP: 8 x 256 system fences per stage, face items 22 % slower per plane than
+// interior items, profiles/r02q_mgpu_trace_2gpu.log.)  Warps of one CTA may be on different face items at the same time; the
+// n_cw-th, 2 n_cw-th, ... arrival each stand for one finished item, and the CTA's final arrival is ordered after all of them.
+static __device__ __noinline__ void halo_face_done(const JbHalo &h, int side, uint32_t cta_counter, unsigned int n_cw) {
+  unsigned int seen;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(seen) : "r"(cta_counter + 4u * side) : "memory");
+  if ((seen + 1u) % n_cw != 0u) return;
   __threadfence_system();
   const unsigned int old = atomicAdd(h.face_count + side, 1u);
   if (old + 1u == h.face_target[side]) {
-    h.face_count[side] = 0u;   // every other warp has arrived: ready for the next launch (stream order)
+    h.face_count[side] = 0u;   // every other CTA-level arrival has been counted: ready for the next launch (stream order)
     __threadfence_system();
     unsigned long long *dst = side == 0 ? h.sig_lo : h.sig_hi;
     if (dst) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(h.signal_epoch) : "memory");

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(co
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringS + (size_t)R * 3 * slotS);
   unsigned long long *fullS = bars, *emptyS = bars + JB_PAIR_BARS, *fullU = bars + 2 * JB_PAIR_BARS, *emptyU = bars + 3 * JB_PAIR_BARS;
   volatile int *items = reinterpret_cast<volatile int *>(bars + 4 * JB_PAIR_BARS);
-  JbRowSeg *s_rows = reinterpret_cast<JbRowSeg *>(bars + 4 * JB_PAIR_BARS + JB_ITEM_RING / 2);
+  unsigned int *face_arrivals = reinterpret_cast<unsigned int *>(bars + 4 * JB_PAIR_BARS + JB_ITEM_RING / 2);   // [0] lo, [1] hi
+  JbRowSeg *s_rows = reinterpret_cast<JbRowSeg *>(bars + JB_STAGE_TAIL_WORDS);
 
   const int tid = threadIdx.x;
   const int n_cw = (blockDim.x >> 5) - 1;   // consumer warps; warp n_cw is the producer
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(co
       mbar_init(smem_u32(&fullU[s]), 1); mbar_init(smem_u32(&emptyU[s]), n_cw);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    face_arrivals[0] = face_arrivals[1] = 0u;
     if (blockIdx.x == 0) *p.queue_next = 0u;   // the counter of the NEXT launch on this stream
   }
   {
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(co
     if (p.halo.enabled && (face_lo | face_hi)) {   // this warp's stores into the neighbours' boxes are on their way
       __syncwarp();
       if (lane0) {
-        if (face_lo) halo_face_done(p.halo, 0);
-        if (face_hi) halo_face_done(p.halo, 1);
+        if (face_lo) halo_face_done(p.halo, 0, smem_u32(face_arrivals), (unsigned int)n_cw);
+        if (face_hi) halo_face_done(p.halo, 1, smem_u32(face_arrivals), (unsigned int)n_cw);
       }
     }
   }
