@@ -744,7 +744,7 @@ static double simulate_queue(const ChunkPlanCandidate &cd, const std::vector<int
   return end;
 }
 
-struct ChunkPlanOptions { int chunks = 0, chunk_long = 0, chunk_short = 0, tail_pct = -1; };
+struct ChunkPlanOptions { int chunks = 0, chunk_long = 0, chunk_short = 0, tail_pct = -1, face_after = 0; };
 
 // result in queue order; returns the number of chunks
 static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOptions &o, int *x0_out, int *xc_out) {
@@ -778,8 +778,20 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
     if (best.xs.empty()) best = make_candidate(nx, gx, nx, nx, 0);
   }
   if ((int)best.xs.size() > JB_TILE_MAX_CHUNKS) best = make_candidate(nx, gx, (nx + JB_TILE_MAX_CHUNKS - 1) / JB_TILE_MAX_CHUNKS, nx, 0);
-  const std::vector<int> order = queue_order(best, nx, gx);
+  std::vector<int> order = queue_order(best, nx, gx);
   const int n = (int)best.xs.size();
+  if (o.face_after > 0) {
+    // slab-decomposed runs: the face chunks are queued after `face_after` interior chunks, so that the CTAs reach their face
+    // planes -- 12 KB of P2P stores each -- spread over the finishing times of the first wave instead of all in the same
+    // microsecond (a burst of 1.5 MB per direction that stalls every SM's store path at once); late enough to spread, early
+    // enough for the epoch flag to reach the neighbour long before its next stage starts
+    auto face = [&](int k) { return best.xs[k].first < gx || best.xs[k].first + best.xs[k].second > nx - gx; };
+    std::vector<int> f, rest;
+    for (int k : order) (face(k) ? f : rest).push_back(k);
+    const size_t at = std::min<size_t>(o.face_after, rest.size());
+    rest.insert(rest.begin() + at, f.begin(), f.end());
+    order = rest;
+  }
   for (int q = 0; q < n; ++q) { x0_out[q] = best.xs[order[q]].first; xc_out[q] = best.xs[order[q]].second; }
   return n;
 }
@@ -787,7 +799,7 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
 void plan_chunks(jb_ctx *c, int G, int n_cols, jb_ctx::Tiling::Shape &sh) {
   const int nx = c->g.nx, gx = c->g.gx;
   ChunkPlanOptions o;
-  o.chunks = c->opt_chunks; o.chunk_long = c->opt_chunk_long; o.chunk_short = c->opt_chunk_short; o.tail_pct = c->opt_tail_pct;
+  o.chunks = c->opt_chunks; o.chunk_long = c->opt_chunk_long; o.chunk_short = c->opt_chunk_short; o.tail_pct = c->opt_tail_pct; o.face_after = c->opt_face_after >= 0 ? c->opt_face_after : (c->d.n_ranks > 1 ? 2 : 0);   // measured on 2 GPUs: 0 / 2 / 3 / 5 -> 97.0 / 97.6 / 97.7 / 96.0 % (profiles/README.md r02r)
   sh.n_chunks = plan_chunks_core(nx, gx, n_cols, G, o, sh.x0, sh.xc);
   sh.face_items[0] = sh.face_items[1] = 0;
   for (int q = 0; q < sh.n_chunks; ++q) {
@@ -1751,6 +1763,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "chunk_long") c->opt_chunk_long = (int)value;
   else if (k == "chunk_short") c->opt_chunk_short = (int)value;
   else if (k == "tail_pct") c->opt_tail_pct = (int)value;
+  else if (k == "face_after") c->opt_face_after = (int)value;
   else if (k == "ctas_per_sm") c->opt_ctas_per_sm = (int)value;
   else if (k == "grid") c->opt_grid = (int)value;
   else if (k == "row_offset") { c->opt_oz = (int)value; c->state_relayout = true; }

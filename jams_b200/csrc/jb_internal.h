@@ -291,6 +291,7 @@ struct jb_ctx {
   int reach[3] = {0, 0, 0};   // max |T| of the exchange template per axis
   int opt_TY = 0, opt_TZ = 0, opt_R = 0, opt_RU = 0, opt_ctas_per_sm = 0, opt_msplit = 0;  // 0 = heuristic
   int opt_chunks = 0;         // x-chunk plan: 0 = heuristic (long chunks + a tail of short ones), n > 0 = n equal chunks
+  int opt_face_after = -1;    // queue the slab's face chunks after this many interior chunks (0 = first; -1 = 2 on slab-decomposed runs, else 0)
   int opt_chunk_long = 0, opt_chunk_short = 0, opt_tail_pct = -1;   // heuristic overrides: planes per long / short chunk, share of the planes in short chunks
   int opt_verbose = 0;
   int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernel (0 = occupancy x SMs)
