@@ -809,13 +809,15 @@ void plan_chunks(jb_ctx *c, int G, int n_cols, jb_ctx::Tiling::Shape &sh) {
 }
 
 // grid size (resident CTAs) and the x-chunk plan for one kernel variant
-int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, int recu) {
+// rk4: the stage belongs to the RK4 solver (stage 0..3; the shared-memory layout is that of Heun stage 0 for stage 0, else stage 1)
+int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, int recu, bool rk4 = false) {
   jb_ctx::Tiling &t = c->tiling;
-  jb_ctx::Tiling::Shape &sh = t.shape[stage][thermal][recu];
+  jb_ctx::Tiling::Shape &sh = rk4 ? t.shape_rk4[stage][thermal] : t.shape[stage][thermal][recu];
   if (sh.grid > 0) return JB_OK;
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
-  if (t.rows) JB_CUDA(c, jbk_stage_rows_occupancy(stage, thermal, t.rows_mode, t.threads, t.smem[stage], &per_sm));
+  if (rk4) JB_CUDA(c, jbk_rk4_stage_pair_occupancy(p, stage, thermal, t.threads, t.smem[stage > 0 ? 1 : 0], &per_sm));
+  else if (t.rows) JB_CUDA(c, jbk_stage_rows_occupancy(stage, thermal, t.rows_mode, t.threads, t.smem[stage], &per_sm));
   else JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, recu, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the stage kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
@@ -825,8 +827,8 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, 
   sh.grid = (int)std::min<long long>(G, (long long)sh.n_chunks * t.n_cols);
   if (c->opt_verbose) {
     fprintf(stderr, "jams_b200: %s kernel stage %d thermal %d recover_u %d: tile %dx%d (y,z), %d consumer threads (motif split %d), ring %d/%d, smem %zu B, "
-                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", t.rows ? "rows" : "pair", stage, thermal, recu, t.TY, t.TZ, t.threads, t.msplit, t.Rs[stage], t.RU,
-            t.smem[stage], per_sm, sh.grid, sh.n_chunks, t.n_cols);
+                    "%d CTAs/SM -> grid %d, %d x-chunks x %d columns:", t.rows ? "rows" : "pair", stage, thermal, recu, t.TY, t.TZ, t.threads, t.msplit, t.Rs[rk4 ? (stage > 0 ? 1 : 0) : stage], t.RU,
+            t.smem[rk4 ? (stage > 0 ? 1 : 0) : stage], per_sm, sh.grid, sh.n_chunks, t.n_cols);
     for (int q = 0; q < sh.n_chunks; ++q) fprintf(stderr, " %d+%d", sh.x0[q], sh.xc[q]);
     fprintf(stderr, "\n");
   }
@@ -848,10 +850,11 @@ int build_tmaps(jb_ctx *c) {
   const cuuint64_t dims[3] = {(cuuint64_t)g.PZ, (cuuint64_t)g.PY * g.M, (cuuint64_t)g.PX};
   const cuuint64_t strides[2] = {(cuuint64_t)g.PZ * 8, (cuuint64_t)g.sX * 8};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int a = 0; a < 5; ++a) {
-    const cuuint32_t box[3] = {(cuuint32_t)(a < 2 ? t.BZ : t.UZ), (cuuint32_t)((a < 2 ? t.BY : t.TY) * g.M), 1};
+  for (int a = 0; a < 6; ++a) {
+    const bool halo_box = a < 2 || a == 5;
+    const cuuint32_t box[3] = {(cuuint32_t)(halo_box ? t.BZ : t.UZ), (cuuint32_t)((halo_box ? t.BY : t.TY) * g.M), 1};
     for (int k = 0; k < 3; ++k) {
-      double *base = a == 0 || a == 3 ? c->S0[k] : (a == 1 || a == 4 ? c->S1[k] : c->U[k]);
+      double *base = a == 0 || a == 3 ? c->S0[k] : (a == 1 || a == 4 ? c->S1[k] : (a == 5 ? c->V[k] : c->U[k]));
       CUresult r = encode(&c->tmap[a][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1309,6 +1312,53 @@ int jb_export_spins(jb_ctx *c, double *s_aos, int32_t on_device) {
   return JB_OK;
 }
 
+// one launch of the persistent TMA kernels (pair / rows / the RK4 stages on the pair kernel): output boxes, class constants of
+// this stage, launch shape and work-item plan, queue counters, the in-kernel halo handshake
+static int launch_tile_stage(jb_ctx *c, JbTileParams &tp, const JbStageParams &p, int stage, int th, bool recu, bool rk4, int class_table_index, bool fold) {
+  int rc;
+  for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
+  tp.step = p.step;
+  tp.dt = p.dt;
+  const JbClass *cls = c->h_class_tab.data() + (size_t)class_table_index * c->h_classes.size();
+  for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
+  const int lay = rk4 ? (stage > 0 ? 1 : 0) : stage;   // shared-memory layout: with or without the second ring
+  tp.R = c->tiling.Rs[lay];
+  rc = tile_launch_shape(c, tp, stage, th, recu ? 1 : 0, rk4); if (rc) return rc;
+  const jb_ctx::Tiling::Shape &sh = rk4 ? c->tiling.shape_rk4[stage][th] : c->tiling.shape[stage][th][recu ? 1 : 0];
+  tp.n_chunks = sh.n_chunks;
+  tp.n_items = sh.n_chunks * tp.n_cols;
+  for (int q = 0; q < sh.n_chunks; ++q) { tp.chunk_x0[q] = sh.x0[q]; tp.chunk_xc[q] = sh.xc[q]; }
+  tp.queue = c->d_queue + (c->stage_launches & 1ull);          // this launch's item counter (zero: see queue_next)
+  tp.queue_next = c->d_queue + ((c->stage_launches + 1) & 1ull);   // ... and the one it zeroes for the next launch
+  c->stage_launches++;
+  tp.trace = c->opt_trace ? c->d_trace : nullptr;
+  tp.halo = JbHalo{};
+  if (fold) {
+    JbHalo &h = tp.halo;
+    h.enabled = (c->peer_lo_flags ? 1 : 0) | (c->peer_hi_flags ? 2 : 0);
+    h.flags = c->flags;
+    h.sig_lo = c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr;
+    h.sig_hi = c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr;
+    h.wait_epoch = c->epoch; h.signal_epoch = c->epoch + 1;
+    h.face_count = c->d_queue + 2;
+    h.face_target[0] = (unsigned int)sh.face_items[0];   // one CTA-level arrival per face item (halo_face_done)
+    h.face_target[1] = (unsigned int)sh.face_items[1];
+  }
+  if (rk4) {
+    // S ring: the stage input (S0, S1, V, S1); second ring: the tile's own s_old = S0 (tensor maps [3])
+    const int in_map = stage == 0 ? 0 : (stage == 2 ? 5 : 1);
+    const CUtensorMap tm[6] = {c->tmap[in_map][0], c->tmap[in_map][1], c->tmap[in_map][2], c->tmap[3][0], c->tmap[3][1], c->tmap[3][2]};
+    JB_CUDA(c, jbk_rk4_stage_pair(tp, tm, stage, th, c->tiling.threads, sh.grid, c->tiling.smem[lay], c->stream));
+  } else {
+    const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
+    const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
+    if (c->tiling.rows) JB_CUDA(c, jbk_stage_rows(tp, tm, stage, th, c->tiling.rows_mode, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+    else JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+  }
+  c->trace_ctas = sh.grid;
+  return JB_OK;
+}
+
 int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint64_t seed, uint64_t first_step, int32_t gilbert) {
   if (!c || nsteps < 0 || !(dt > 0.0) || T < 0.0) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
@@ -1383,37 +1433,7 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
         if (c->has_pairs) {
           JB_CUDA(c, jbk_stage_pairs(p, c->d_ell_idx, c->d_ell_val, c->ell_width, c->d_pair_J, c->pairs_iso ? 1 : 0, stage, c->stream));
         } else if (use_tile) {
-          for (int k = 0; k < 3; ++k) { tp.out[k] = p.out[k]; tp.out_lo[k] = p.out_lo[k]; tp.out_hi[k] = p.out_hi[k]; tp.u[k] = p.u[k]; }
-          tp.step = p.step;
-          const JbClass *cls = c->h_class_tab.data() + (size_t)(time_dependent(c) ? 2 * n + stage : 0) * c->h_classes.size();
-          for (int m = 0; m < c->g.M; ++m) tp.cls[m] = cls[c->class_of_motif[m]];
-          tp.R = c->tiling.Rs[stage];
-          rc = tile_launch_shape(c, tp, stage, th, recu ? 1 : 0); if (rc) return rc;
-          const jb_ctx::Tiling::Shape &sh = c->tiling.shape[stage][th][recu ? 1 : 0];
-          tp.n_chunks = sh.n_chunks;
-          tp.n_items = sh.n_chunks * tp.n_cols;
-          for (int q = 0; q < sh.n_chunks; ++q) { tp.chunk_x0[q] = sh.x0[q]; tp.chunk_xc[q] = sh.xc[q]; }
-          tp.queue = c->d_queue + (c->stage_launches & 1ull);          // this launch's item counter (zero: see queue_next)
-          tp.queue_next = c->d_queue + ((c->stage_launches + 1) & 1ull);   // ... and the one it zeroes for the next launch
-          c->stage_launches++;
-          tp.trace = c->opt_trace ? c->d_trace : nullptr;
-          tp.halo = JbHalo{};
-          if (fold) {
-            JbHalo &h = tp.halo;
-            h.enabled = (c->peer_lo_flags ? 1 : 0) | (c->peer_hi_flags ? 2 : 0);
-            h.flags = c->flags;
-            h.sig_lo = c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr;
-            h.sig_hi = c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr;
-            h.wait_epoch = c->epoch; h.signal_epoch = c->epoch + 1;
-            h.face_count = c->d_queue + 2;
-            h.face_target[0] = (unsigned int)sh.face_items[0];   // one CTA-level arrival per face item (halo_face_done)
-            h.face_target[1] = (unsigned int)sh.face_items[1];
-          }
-          const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
-          const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
-          if (c->tiling.rows) JB_CUDA(c, jbk_stage_rows(tp, tm, stage, th, c->tiling.rows_mode, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
-          else JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
-          c->trace_ctas = sh.grid;
+          rc = launch_tile_stage(c, tp, p, stage, th, recu, false, time_dependent(c) ? 2 * n + stage : 0, fold); if (rc) return rc;
         } else {
           JB_CUDA(c, jbk_stage_direct(p, stage, c->stream));
         }
@@ -1439,6 +1459,21 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
   if (multi && !c->halo_connected) JB_FAIL(c, JB_ERR_INVALID, "multi-rank context: jb_halo_connect has not been called");
   if (c->has_pairs) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_step_rk4 needs a translation-invariant exchange template (jb_set_exchange_template, or jb_set_exchange_pairs with template detection)");
   const bool periodic_x = c->g.per[0] && c->g.gx > 0;
+  // the four stages on the persistent TMA kernel (isotropic templates the pair kernel can tile; option kernel = 0: direct gathers)
+  choose_tiling(c);
+  const bool use_tile = c->tiling.ok && !c->tiling.rows && c->iso && !c->has_bq;
+  JbTileParams tp{};
+  if (use_tile) {
+    rc = build_tmaps(c); if (rc) return rc;
+    rc = ensure_queue(c); if (rc) return rc;
+    fill_tile_params(c, tp);
+    for (int r = 0; r < 10; ++r) {   // Philox4x32-10 key schedule
+      tp.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+      tp.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+    }
+  }
+  const bool fold = multi && use_tile && (c->opt_fold_halo == 2 || (c->opt_fold_halo == 1 && !c->peer_on_my_device));
+  c->last_stage_kernel = use_tile ? JB_KERNEL_PAIR : JB_KERNEL_DIRECT;
   for (int done = 0; done < nsteps;) {
     const int chunk = time_dependent(c) ? std::min(nsteps - done, 1024) : nsteps - done;
     std::vector<double> times;
@@ -1466,16 +1501,17 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
         p.seed = seed; p.step = first_step + (uint64_t)(done + n);
         p.thermal = T > 0.0 ? 1 : 0;
         p.dt = dt;
-        if (multi) {   // as in jb_step: the neighbours' previous stage wrote the ghosts this stage reads and read the boxes it writes
+        if (multi && !fold) {   // as in jb_step: the neighbours' previous stage wrote the ghosts this stage reads and read the boxes it writes
           JB_CUDA(c, jbk_wait(c->flags, c->peer_lo_flags != nullptr, c->peer_hi_flags != nullptr, c->epoch, c->stream)); c->launches++;
         }
-        record_event(c, 0);
-        JB_CUDA(c, jbk_rk4_stage_direct(p, stage, c->stream));
+        record_event(c, stage < 2 ? 0 : 2);   // jb_last_step_kernel_ms: out2[0] = stages 1 + 2, out2[1] = stages 3 + 4
+        if (use_tile) { rc = launch_tile_stage(c, tp, p, stage, p.thermal, false, true, time_dependent(c) ? 3 * n + tsel : 0, fold); if (rc) return rc; }
+        else JB_CUDA(c, jbk_rk4_stage_direct(p, stage, c->stream));
         c->launches++;
-        record_event(c, 1);
+        record_event(c, stage < 2 ? 1 : 3);
         if (multi) {
           c->epoch++;
-          JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++;
+          if (!fold) { JB_CUDA(c, jbk_signal(c->peer_lo_flags ? c->peer_lo_flags + 1 : nullptr, c->peer_hi_flags ? c->peer_hi_flags + 0 : nullptr, c->epoch, c->stream)); c->launches++; }
         }
       }
     }

@@ -215,6 +215,44 @@ __device__ __forceinline__ void llg_site(const JbClass &c, double sx, double sy,
   if (STAGE == 0 && THERMAL && FOLD) corrector_noise_part(c, ox, oy, oz, n0, n1, n2, vx, vy, vz);
 }
 
+// One stage of the RK4-LLG solver for one site (cuda_llg_rk4_kernel.cuh:36-56, cuda_rk4_base.cu:66-97, cuda_rk4_base_kernel.cuh:16,
+// cuda/cuda_spin_ops.cu:4-17 with the zero-length guard of Vec3 unit_vector).  In: the stage input s, the field h in Tesla
+// (exchange + constant), the draw, s_old (stages 1-3) and the running sum (ax, ay, az) = k1 + 2 k2 + ... (stages 1-3).  Out: the
+// next stage input -- not normalised, as in the reference -- or the new spin (stage 3), and the updated running sum (stages 0-2).
+template <int STAGE, bool THERMAL>
+__device__ __forceinline__ void rk4_site(const JbClass &c, double dt, double sx, double sy, double sz, double hx, double hy, double hz,
+                                         double n0, double n1, double n2, double s0x, double s0y, double s0z,
+                                         double &ax, double &ay, double &az, double &ox, double &oy, double &oz) {
+  if (c.power != 0) {  // uniaxial (uniaxial_anisotropy.cc:155-163), here / mu
+    const double d = c.ax * sx + c.ay * sy + c.az * sz;
+    double pw = d;
+    if (c.power >= 4) pw = d * d * d;
+    if (c.power >= 6) pw = pw * d * d;
+    const double f = c.KpT * pw;
+    hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
+  }
+  if (THERMAL) { hx = fma(c.sigma, n0, hx); hy = fma(c.sigma, n1, hy); hz = fma(c.sigma, n2, hz); }   // one draw per step, all four stages (cuda_rk4_base.cu:65)
+  const double ax_ = sy * hz - sz * hy, ay_ = sz * hx - sx * hz, az_ = sx * hy - sy * hx;
+  const double bx_ = sy * az_ - sz * ay_, by_ = sz * ax_ - sx * az_, bz_ = sx * ay_ - sy * ax_;
+  const double mg = -c.gyro;
+  const double kx = mg * (ax_ + c.alpha * bx_), ky = mg * (ay_ + c.alpha * by_), kz = mg * (az_ + c.alpha * bz_);
+  if (STAGE == 0) {          // y1 = s_old + dt/2 k1 ; sum = k1
+    const double a = 0.5 * dt;
+    ox = sx + a * kx; oy = sy + a * ky; oz = sz + a * kz;
+    ax = kx; ay = ky; az = kz;
+  } else if (STAGE == 1 || STAGE == 2) {   // y = s_old + a dt k ; sum += 2 k
+    const double a = (STAGE == 1) ? 0.5 * dt : dt;
+    ox = s0x + a * kx; oy = s0y + a * ky; oz = s0z + a * kz;
+    ax = ax + 2 * kx; ay = ay + 2 * ky; az = az + 2 * kz;
+  } else {                   // s = unit(s_old + dt (k1 + 2 k2 + 2 k3 + k4) / 6)
+    const double vx = s0x + dt * (ax + kx) / 6.0, vy = s0y + dt * (ay + ky) / 6.0, vz = s0z + dt * (az + kz) / 6.0;
+    const double n2_ = vx * vx + vy * vy + vz * vz;
+    const double r = rsqrt_nobranch(n2_);
+    const double inv = (n2_ > 4.930380657631324e-32) ? r : 1.0;
+    ox = vx * inv; oy = vy * inv; oz = vz * inv;
+  }
+}
+
 // store the ghost images of a freshly computed spin (the value for its own cell has been stored by the
 // caller): periodic images in y/z inside this box; x images into the lo/hi boxes, which are this box
 // itself on one GPU and the neighbours' boxes -- peer memory over NVLink -- on several.

@@ -160,6 +160,7 @@ struct JbTileParams {
   double *u[3];          // Heun intermediate, written by stage A with plain stores (stage B reads it through TMA)
   const double *J9T;     // n_nbr x 9: tensor of every template entry divided by mu_i, Tesla (anisotropic exchange only)
   unsigned long long step;
+  double dt;             // RK4 stages: the step (the Heun stages have it folded into the class constants)
   unsigned int rk[20];   // Philox4x32-10 round keys of the seed (k0 + r W0, k1 + r W1)
   int TY, TZ, UZ;        // tile extent in y, z; UZ = TZ rounded up to even = inner extent of the u box
   int BY, BZ, gzb;       // tile + halo extent; gzb = gz rounded up to even = z halo of the box (BZ = TZ + 2 gzb)
@@ -255,6 +256,7 @@ struct jb_ctx {
     // launch shape per kernel variant [stage][thermal][recover_u]: resident CTAs and the x-chunk plan (0 = not determined yet)
     struct Shape { int grid = 0, n_chunks = 0, face_items[2] = {0, 0}; int x0[JB_TILE_MAX_CHUNKS], xc[JB_TILE_MAX_CHUNKS]; };
     Shape shape[2][2][2];
+    Shape shape_rk4[4][2];                // the RK4 stages on the pair kernel [stage][thermal]
   } tiling;
   bool tiling_valid = false;
   std::vector<int> tile_order, tile_jidx;   // template entries in table order / their unique-tensor ids
@@ -282,8 +284,8 @@ struct jb_ctx {
   cudaEvent_t copy_ev[JB_COPY_CHUNKS + 1] = {nullptr};
 
   // TMA descriptors: [0] = S0 x,y,z  [1] = S1 x,y,z (tile + halo boxes)  [2] = U x,y,z (tile boxes)
-  // [3] = S0, [4] = S1 with the tile box of U (recover_u: the corrector reads the site's own s_n)
-  CUtensorMap tmap[5][3];
+  // [3] = S0, [4] = S1 with the tile box of U (recover_u: the corrector reads the site's own s_n); [5] = V, tile + halo boxes (RK4)
+  CUtensorMap tmap[6][3];
   bool tmap_valid = false;
 
   // options
@@ -355,6 +357,10 @@ cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int recu, int threads,
                                      size_t smem_bytes, int *blocks_per_sm);
+// the four RK4 stages on the same kernel (isotropic couplings): tmaps6 = {stage input x,y,z, S0 (s_old) tile boxes x,y,z}
+cudaError_t jbk_rk4_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6, int stage, int thermal, int threads, int grid,
+                               size_t smem_bytes, cudaStream_t stream);
+cudaError_t jbk_rk4_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm);
 // rows kernel (jb_stage_rows.cu): tmaps = {S.x, S.y, S.z}; threads = 32 x (TY / 4) x msplit consumer threads
 // mode: 2 = double-buffered segments (at most JB_ROWS_PIPE_WARPS consumer warps), 0 / 1 = single buffer, unrolled once / twice
 cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tmaps3, int stage, int thermal, int mode, int threads, int grid,

@@ -69,7 +69,11 @@ static __device__ __noinline__ void put_pair_x_images(const JbTileParams &p, int
   }
 }
 
-template <int STAGE, bool THERMAL, bool ISO, bool MOTIF1, bool RECU>
+// RK4 = true: one of the four stages of the RK4-LLG solver (llg-rk4-gpu: solvers/cuda_rk4_base.cu:50-108, cuda_llg_rk4_kernel.cuh:11-58)
+// on the same machinery -- STAGE 0..3, the S ring streams the stage input (s_old, y1, y2, y3) with halos, the second ring the
+// tile's own s_old (stages 1-3), the running sum k1 + 2 k2 + 2 k3 is read and written in place with 16-byte global accesses
+// issued before the gather; DESIGN.md 3.2b.
+template <int STAGE, bool THERMAL, bool ISO, bool MOTIF1, bool RECU, bool RK4 = false>
 __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
                                                             const __grid_constant__ CUtensorMap tS2,
@@ -78,13 +82,14 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
                                                             const __grid_constant__ CUtensorMap tU2,
                                                             const __grid_constant__ JbTileParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool HAS_U = RK4 ? (STAGE >= 1) : (STAGE == 1);   // a second ring with the tile's own plane of another tensor
   const JbGeom &g = p.g;
   const int M = MOTIF1 ? 1 : g.M, gx = g.gx;
   const int R = p.R, RU = p.RU;
   const int slotS = p.slotS, slotU = p.slotU;
   double *ringS = reinterpret_cast<double *>(smem_raw);
   double *ringU = ringS + (size_t)R * 3 * slotS;
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringU + (STAGE == 1 ? (size_t)RU * 3 * slotU : 0));
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ringU + (HAS_U ? (size_t)RU * 3 * slotU : 0));
   unsigned long long *fullS = bars, *emptyS = bars + JB_PAIR_BARS, *fullU = bars + 2 * JB_PAIR_BARS, *emptyU = bars + 3 * JB_PAIR_BARS;
   volatile int *items = reinterpret_cast<volatile int *>(bars + 4 * JB_PAIR_BARS);
   unsigned int *face_arrivals = reinterpret_cast<unsigned int *>(bars + 4 * JB_PAIR_BARS + JB_ITEM_RING / 2);   // [0] lo, [1] hi
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
   // =========================== producer warp: item ids, the stream of S planes and u planes ===========================
   const int warp_idx = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction
   if (warp_idx == n_cw) {
-    stage_producer<STAGE == 1>(&tS0, &tS1, &tS2, &tU0, &tU1, &tU2, p, M, ringS, ringU, fullS, emptyS, fullU, emptyU, items);
+    stage_producer<HAS_U>(&tS0, &tS1, &tS2, &tU0, &tU1, &tU2, p, M, ringS, ringU, fullS, emptyS, fullU, emptyU, items);
     return;
   }
 
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         mbar_wait(fullS0 + 8u * wslot, wpar);
         if (++wslot == R) { wslot = 0; wpar ^= 1u; }
       }
-      if (STAGE == 1) mbar_wait(fullU0 + 8u * uslot, upar);
+      if (HAS_U) mbar_wait(fullU0 + 8u * uslot, upar);
       const int x = it.x0 + i;
       const bool xb = x_image_needed(g, x);
       const uint32_t cen = own + (uint32_t)cslot * slot8;
@@ -212,6 +217,13 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         const uint32_t mo = (uint32_t)(m * p.BZ) * 8u;
         const uint32_t a = cen + mo;
         const double2 sx = lds128(a), sy = lds128(a + cs8), sz = lds128(a + 2 * cs8);
+        // RK4: the running sum of the k's of this pair, straight from global memory (stages 1-3), in flight during the gather
+        double2 kx = make_double2(0, 0), ky = kx, kz = kx;
+        if (RK4 && STAGE >= 1) {
+          const int idx = ic + m * g.PZ;
+          if (ok1) { kx = *reinterpret_cast<const double2 *>(&p.u[0][idx]); ky = *reinterpret_cast<const double2 *>(&p.u[1][idx]); kz = *reinterpret_cast<const double2 *>(&p.u[2][idx]); }
+          else if (ok0) { kx.x = p.u[0][idx]; ky.x = p.u[1][idx]; kz.x = p.u[2][idx]; }
+        }
         double2 hx = make_double2(c.fTx, c.fTx), hy = make_double2(c.fTy, c.fTy), hz = make_double2(c.fTz, c.fTz);   // constant field (Zeeman dc + ac cos wt + applied), Tesla
         // exchange field in Tesla.  Entries of a motif site: first those with an even z offset (the neighbour pair
         // is 16-byte aligned: LDS.128), then the odd ones (two LDS.64); within each group in the reference's CSR
@@ -278,22 +290,34 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
           }
         }
         double2 ux = make_double2(0, 0), uy = ux, uz = ux;
-        if (STAGE == 1) {
+        if (HAS_U) {
           const uint32_t ua = uplane + (uint32_t)(m * p.UZ) * 8u;
           ux = lds128(ua); uy = lds128(ua + cu8); uz = lds128(ua + 2 * cu8);
-          if (RECU) {   // the ring delivered s_n: rebuild u = (s_n + lambda s*) / 2
+          if (!RK4 && RECU) {   // the ring delivered s_n: rebuild u = (s_n + lambda s*) / 2
             recover_u(sx.x, sy.x, sz.x, ux.x, uy.x, uz.x);
             recover_u(sx.y, sy.y, sz.y, ux.y, uy.y, uz.y);
           }
         }
         if (THERMAL && !MOTIF1) pair_normals_rk(p.rk, p.step, gs + m, nz);
-        double2 ox, oy, oz, vx, vy, vz;
+        double2 ox, oy, oz, vx = make_double2(0, 0), vy = vx, vz = vx;
+        if constexpr (RK4) {
+          rk4_site<STAGE, THERMAL>(c, p.dt, sx.x, sy.x, sz.x, hx.x, hy.x, hz.x, THERMAL ? (double)nz.e0 : 0.0, THERMAL ? (double)nz.e1 : 0.0,
+                                   THERMAL ? (double)nz.e2 : 0.0, ux.x, uy.x, uz.x, kx.x, ky.x, kz.x, ox.x, oy.x, oz.x);
+          rk4_site<STAGE, THERMAL>(c, p.dt, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, THERMAL ? (double)nz.o0 : 0.0, THERMAL ? (double)nz.o1 : 0.0,
+                                   THERMAL ? (double)nz.o2 : 0.0, ux.y, uy.y, uz.y, kx.y, ky.y, kz.y, ox.y, oy.y, oz.y);
+          if (STAGE < 3) {   // the running sum: interior only, no images
+            const int idx = ic + m * g.PZ;
+            if (ok1) { stg128(&p.u[0][idx], kx.x, kx.y); stg128(&p.u[1][idx], ky.x, ky.y); stg128(&p.u[2][idx], kz.x, kz.y); }
+            else if (ok0) { p.u[0][idx] = kx.x; p.u[1][idx] = ky.x; p.u[2][idx] = kz.x; }
+          }
+        } else {
         llg_site<STAGE, THERMAL, !RECU>(c, sx.x, sy.x, sz.x, hx.x, hy.x, hz.x, THERMAL ? (double)nz.e0 : 0.0, THERMAL ? (double)nz.e1 : 0.0,
                                         THERMAL ? (double)nz.e2 : 0.0, ux.x, uy.x, uz.x, ox.x, oy.x, oz.x, vx.x, vy.x, vz.x);
         llg_site<STAGE, THERMAL, !RECU>(c, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, THERMAL ? (double)nz.o0 : 0.0, THERMAL ? (double)nz.o1 : 0.0,
                                         THERMAL ? (double)nz.o2 : 0.0, ux.y, uy.y, uz.y, ox.y, oy.y, oz.y, vx.y, vy.y, vz.y);
+        }
         const int idx = ic + m * g.PZ;
-        if (STAGE == 0 && !RECU) {   // the Heun intermediate: interior only, no images
+        if (!RK4 && STAGE == 0 && !RECU) {   // the Heun intermediate: interior only, no images
           if (ok1) { stg128(&p.u[0][idx], vx.x, vx.y); stg128(&p.u[1][idx], vy.x, vy.y); stg128(&p.u[2][idx], vz.x, vz.y); }
           else if (ok0) { p.u[0][idx] = vx.x; p.u[1][idx] = vy.x; p.u[2][idx] = vz.x; }
         }
@@ -303,7 +327,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         if (ysh != 0) put_pair(p.out, idx + ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
         if (xb) put_pair_x_images(p, x, idx, ysh, ok0, ok1, zsh0, zsh1, ox, oy, oz);
       }
-      if (STAGE == 1) {   // this warp is done with the u plane
+      if (HAS_U) {   // this warp is done with the u plane
         __syncwarp();
         if (lane0) mbar_arrive(emptyU0 + 8u * uslot);
         if (++uslot == RU) { uslot = 0; upar ^= 1u; }
@@ -327,6 +351,17 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
     unsigned long long *t = p.trace + (unsigned long long)JB_TRACE_WORDS * blockIdx.x;
     t[0] = smid; t[1] = t_first; t[2] = global_timer_ns(); t[3] = (unsigned long long)n_done;
   }
+}
+
+template <typename F>
+cudaError_t with_rk4_kernel(int stage, int thermal, int motif1, F &&f) {   // isotropic couplings only (tensor couplings: rk4_direct_kernel)
+#define JB_RK4_CASE(ST, TH, M1) \
+  if (stage == ST && thermal == TH && motif1 == M1) return f(stage_pair_kernel<ST, (TH != 0), true, (M1 != 0), false, true>);
+#define JB_RK4_CASES(ST) JB_RK4_CASE(ST, 0, 0) JB_RK4_CASE(ST, 0, 1) JB_RK4_CASE(ST, 1, 0) JB_RK4_CASE(ST, 1, 1)
+  JB_RK4_CASES(0) JB_RK4_CASES(1) JB_RK4_CASES(2) JB_RK4_CASES(3)
+#undef JB_RK4_CASES
+#undef JB_RK4_CASE
+  return cudaErrorInvalidValue;
 }
 
 template <typename F>
@@ -358,6 +393,24 @@ cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int therm
 cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int iso, int recu,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream) {
   return with_kernel(stage, thermal, iso, p.g.M == 1 ? 1 : 0, recu, [&](auto k) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t jbk_rk4_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm) {
+  return with_rk4_kernel(stage, thermal, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (err != cudaSuccess) return err;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32, smem_bytes);
+  });
+}
+
+cudaError_t jbk_rk4_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int threads, int grid,
+                               size_t smem_bytes, cudaStream_t stream) {
+  return with_rk4_kernel(stage, thermal, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);

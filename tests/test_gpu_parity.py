@@ -236,7 +236,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4"])
+@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4", "rk4_fold", "rk4_direct"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -252,7 +252,10 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     def new_ctx(rank, n):
         nx = dims[0] // n
         c = capi.Context(dims, lat.M, lat.periodic, x_begin=rank * nx, nx_local=nx, rank=rank, n_ranks=n)
-        if kernel != "rk4":
+        if kernel.startswith("rk4"):
+            c.set_option("kernel", 0 if kernel == "rk4_direct" else 2)
+            c.set_option("fold_halo", 2 if kernel.endswith("fold") else 0)
+        else:
             c.set_option("kernel", 4 if kernel.startswith("rows") else 2)
             c.set_option("recover_u", 0 if kernel.startswith("2u") else 1)   # two launches per step, two halo exchanges
             # fold: the epoch handshake inside the stage kernel (what multi-GPU runs use); the slabs share this GPU here, which
@@ -262,7 +265,7 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
         c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
         return c
 
-    step = (lambda c, *a: c.step_rk4(*a)) if kernel == "rk4" else (lambda c, *a: c.step(*a))   # RK4: four exchanges per step
+    step = (lambda c, *a: c.step_rk4(*a)) if kernel.startswith("rk4") else (lambda c, *a: c.step(*a))   # RK4: four exchanges per step
     single = new_ctx(0, 1)
     single.import_spins(s0)
     step(single, steps, dt, 0.0, T, seed, 0)
@@ -358,9 +361,14 @@ def _rk4_solver(w, **kw):
     return s
 
 
+RK4_KERNELS = {"ring": None, "ring_small_tile": dict(tile_y=2, tile_z=16, chunks=3), "direct": dict(kernel=0)}   # the four stages on the TMA pair kernel / direct gathers
+
+
+@pytest.mark.parametrize("variant", list(RK4_KERNELS))
 @pytest.mark.parametrize("make_w,steps", [(lambda: W.c3_sc(dims=(12, 9, 20)), 40), (lambda: W.c2_bcc_fe(6, temperature=0.0), 30),
-                                          (lambda: W.c1_bloch_wall((32, 6, 6)), 40), (lambda: W.c4_bcc_long_range(8), 8)])
-def test_rk4_T0_trajectories_match_oracle(make_w, steps):
+                                          (lambda: W.c1_bloch_wall((32, 6, 6)), 40), (lambda: W.c4_bcc_long_range(8), 8),
+                                          (lambda: W.c3_sc(dims=(7, 13, 70)), 12), (lambda: W.c3_sc(dims=(40, 32, 128)), 6)])
+def test_rk4_T0_trajectories_match_oracle(make_w, steps, variant):
     w = make_w()
     if "sc 12" in w["name"] or w["name"].startswith("C3"):
         w["hamiltonians"].append(dict(module="uniaxial", order="K2", anisotropies=[("A", [0.0, 0.6, 0.8], 2e-23)]))
@@ -369,10 +377,14 @@ def test_rk4_T0_trajectories_match_oracle(make_w, steps):
     sim = build_cpu_sim(w)
     sim.set_spins(s0)
     sim.run_rk4(steps)
-    s = _rk4_solver(w)
+    s = _rk4_solver(w, options=RK4_KERNELS[variant] or {})
     s.set_spins(s0)
     s.run(steps)
     got = s.spins()
+    if variant == "direct" or (variant == "ring" and "C4" in w["name"]):   # C4's deep template is beyond the pair kernel's default tiles: direct gathers
+        assert s.ctx.stage_kernel() == 0
+    elif variant == "ring":
+        assert s.ctx.stage_kernel() == 2
     assert np.abs(got - sim.get_spins()).max() <= TRAJ_TOL
     assert np.abs(np.linalg.norm(got, axis=1) - 1.0).max() < 1e-14
     # a Heun step afterwards continues from the RK4 state (shared device state)
@@ -381,14 +393,15 @@ def test_rk4_T0_trajectories_match_oracle(make_w, steps):
     assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
 
 
-def test_rk4_thermal_trajectory_matches_oracle_given_the_same_noise_and_ac_field():
+@pytest.mark.parametrize("variant", list(RK4_KERNELS))
+def test_rk4_thermal_trajectory_matches_oracle_given_the_same_noise_and_ac_field(variant):
     """one noise draw per step for all four stages (cuda_rk4_base.cu:65); AC Zeeman field evaluated at t0, t0 + dt/2, t0 + dt"""
     lat = Lattice([Material("A", 2.0, alpha=0.05)], np.eye(3), [("A", (0, 0, 0))], (8, 7, 10))
     w = dict(name="sc ac", lattice=lat, temperature=40.0, spins=None,
              hamiltonians=[dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 3.5e-21)]),
                            dict(module="zeeman", dc_local_field=[[0.0, 0.0, 0.5]], ac_local_field=[[2.0, 0.0, 0.0]], ac_local_frequency=[0.5])])
     steps, seed = 20, 4321
-    s = _rk4_solver(w, seed=seed)
+    s = _rk4_solver(w, seed=seed, options=RK4_KERNELS[variant] or {})
     s0 = random_unit_spins(lat.num_spins, 9)
     s.set_spins(s0)
     normals = np.stack([s.ctx.noise(s.step_size, 40.0, seed, n, normals_only=True) for n in range(steps)])
@@ -414,6 +427,11 @@ def test_rk4_full_size_properties_and_fixed_point():
     out = s.spins()
     e1 = sum(h.calculate_total_energy(0.0) for h in s.hamiltonians)
     assert np.abs(np.linalg.norm(out, axis=1) - 1.0).max() < 1e-14 and e1 < e0
+    d = _rk4_solver(w, options=dict(kernel=0))   # the ring and the direct kernels agree to rounding at a size the oracle does not run
+    d.set_spins(s0)
+    d.run(20)
+    assert s.ctx.stage_kernel() == 2 and d.ctx.stage_kernel() == 0
+    assert np.abs(d.spins() - out).max() <= 1e-13
     # Heun from the same start stays within its own (second-order) error of the RK4 trajectory
     h = make(w)
     h.set_spins(s0)
