@@ -387,7 +387,7 @@ def run_b200(args):
 
     # ---- N = 1: the other BASELINE configurations as secondary entries, and the CPU arm ------------------------------------
     if rank == 0 and world == 1 and not args.no_extra:
-        line["other_configs"] = other_configs(min(K, 20))
+        line["other_configs"] = other_configs(min(K, 20), peak)
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             line["cpu_baseline"], _ = cpu_reference_rate(args.cpu_steps, 2, budget_s=20.0)
@@ -427,12 +427,15 @@ def slab_parity(world, rank, local_rank, comm, build):
     return out
 
 
-def other_configs(steps):
-    """BASELINE configs 2 and 4 (parity-test cases, not the headline): stage-kernel rates on this GPU"""
+def other_configs(steps, peak_gbs=None):
+    """BASELINE configs 2 and 4 and the RK4 solver on the bench workload (parity-test cases, not the headline): stage-kernel rates on
+    this GPU.  C4 also reports the gather rate SURVEY.md 8d asks for (neighbour-spin operands delivered per second)."""
     from jams_b200 import workloads as W
+    from jams_b200.solver import create_hamiltonian, create_solver
+    names = {0: "direct gathers", 2: "TMA pair kernel", 4: "TMA rows kernel", 5: "general neighbour list"}
     out = []
-    for name, w in (("C2 bcc Fe 128^3 NN+NNN (z = 14), T = 300 K", W.c2_bcc_fe(128, temperature=300.0)),
-                    ("C4 bcc 128^3, 8 shells (z = 112), T = 0", W.c4_bcc_long_range(128, temperature=0.0))):
+    for name, w, z in (("C2 bcc Fe 128^3 NN+NNN (z = 14), T = 300 K", W.c2_bcc_fe(128, temperature=300.0), 14),
+                       ("C4 bcc 128^3, 8 shells (z = 112), T = 0", W.c4_bcc_long_range(128, temperature=0.0), 112)):
         try:
             s = W.make_solver(w, options=dict(time_kernels=1), random_spins_seed=1)
             s.run(3); s.ctx.synchronize(); s.ctx.last_step_kernel_ms()
@@ -440,10 +443,32 @@ def other_configs(steps):
             st = s.ctx.last_step_kernel_ms() / steps
             n = w["lattice"].num_spins
             out.append({"config": name, "spins": n, "stage_ms": [float(st[0]), float(st[1])], "value": n / (float(st.sum()) * 1e-3), "unit": UNIT,
+                        "kernel": names.get(s.ctx.stage_kernel(), "?"), "gather_TBs": [n * z * 24.0 / (float(t) * 1e-3) / 1e12 for t in st],
                         "timing": "sum of the two stage launches, CUDA events"})
             s.ctx.close()
         except Exception as e:  # noqa: BLE001
             out.append({"config": name, "error": str(e)})
+    try:   # llg-rk4-b200-gpu on the bench workload: four launches per step, 408 B of HBM traffic per spin-update
+        w = W.c3_sc(256, temperature=TEMPERATURE)
+        lat = w["lattice"]
+        s = create_solver(dict(module="llg-rk4-b200-gpu", t_step=W.T_STEP, t_max=1e-9, seed=3, options=dict(time_kernels=1)), lat)
+        for h in w["hamiltonians"]:
+            s.register_hamiltonian(create_hamiltonian(h, lat))
+        s.set_temperature(TEMPERATURE)
+        s.set_spins(lat.initial_spins(seed=1))
+        s.run(3); s.ctx.synchronize(); s.ctx.last_step_kernel_ms()
+        s.run(steps); s.ctx.synchronize()
+        st = s.ctx.last_step_kernel_ms() / steps
+        ms = float(st.sum())
+        rec = {"config": "RK4-LLG on C3 sc 256^3, T = %g K" % TEMPERATURE, "spins": lat.num_spins, "stage_ms": [float(st[0]), float(st[1])],
+               "stage_ms_note": "stages 1 + 2, stages 3 + 4", "value": lat.num_spins / (ms * 1e-3), "unit": UNIT,
+               "kernel": names.get(s.ctx.stage_kernel(), "?"), "bytes_per_update": 408}
+        if peak_gbs:
+            rec["hbm_frac"] = 408.0 * lat.num_spins / (ms * 1e-3) / 1e9 / peak_gbs
+        out.append(rec)
+        s.ctx.close()
+    except Exception as e:  # noqa: BLE001
+        out.append({"config": "RK4-LLG on C3", "error": str(e)})
     return out
 
 

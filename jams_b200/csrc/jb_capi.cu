@@ -788,7 +788,7 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
     auto face = [&](int k) { return best.xs[k].first < gx || best.xs[k].first + best.xs[k].second > nx - gx; };
     std::vector<int> f, rest;
     for (int k : order) (face(k) ? f : rest).push_back(k);
-    const size_t at = std::min<size_t>(o.face_after, rest.size());
+    const size_t at = std::min<size_t>(o.face_after, rest.size() / 3);   // never in the last two thirds of the queue: the flag must travel early
     rest.insert(rest.begin() + at, f.begin(), f.end());
     order = rest;
   }
