@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         // column order (interface/sparse_blas.h:22-25)
         const int nb = p.nbr_begin[MOTIF1 ? 0 : m], no = p.nbr_odd[MOTIF1 ? 0 : m], ne = p.nbr_begin[(MOTIF1 ? 0 : m) + 1];
         const uint32_t base = own + mo;
-#pragma unroll 2
+#pragma unroll 4
         for (int n = nb; n < no; ++n) {
           const int4 raw = lds_entry(tab + (uint32_t)n * 16u);   // {byte offset, d, J}
           const uint32_t q = base + (uint32_t)raw.x;
