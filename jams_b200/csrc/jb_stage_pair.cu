@@ -71,8 +71,8 @@ static __device__ __noinline__ void put_pair_x_images(const JbTileParams &p, int
 
 // RK4 = true: one of the four stages of the RK4-LLG solver (llg-rk4-gpu: solvers/cuda_rk4_base.cu:50-108, cuda_llg_rk4_kernel.cuh:11-58)
 // on the same machinery -- STAGE 0..3, the S ring streams the stage input (s_old, y1, y2, y3) with halos, the second ring the
-// tile's own s_old (stages 1-3), the running sum k1 + 2 k2 + 2 k3 is read and written in place with 16-byte global accesses
-// issued before the gather; DESIGN.md 3.2b.
+// tile's own s_old (stages 1-3); no sum of k's is kept (rk4_site, jb_device.cuh): 48 + 72 + 120 + 96 = 336 B of HBM traffic
+// per spin-update; DESIGN.md 3.2b.
 template <int STAGE, bool THERMAL, bool ISO, bool MOTIF1, bool RECU, bool RK4 = false>
 __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
@@ -217,12 +217,14 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
         const uint32_t mo = (uint32_t)(m * p.BZ) * 8u;
         const uint32_t a = cen + mo;
         const double2 sx = lds128(a), sy = lds128(a + cs8), sz = lds128(a + 2 * cs8);
-        // RK4: the running sum of the k's of this pair, straight from global memory (stages 1-3), in flight during the gather
+        // RK4: stage 2 needs the site's own y1 (it sits in the box this stage overwrites with y3), stage 3 the combination
+        // c = y1 + 2 y2 that stage 2 left in the U box: straight from global memory, in flight during the gather
         double2 kx = make_double2(0, 0), ky = kx, kz = kx;
-        if (RK4 && STAGE >= 1) {
+        if (RK4 && STAGE >= 2) {
           const int idx = ic + m * g.PZ;
-          if (ok1) { kx = *reinterpret_cast<const double2 *>(&p.u[0][idx]); ky = *reinterpret_cast<const double2 *>(&p.u[1][idx]); kz = *reinterpret_cast<const double2 *>(&p.u[2][idx]); }
-          else if (ok0) { kx.x = p.u[0][idx]; ky.x = p.u[1][idx]; kz.x = p.u[2][idx]; }
+          double *const *src = STAGE == 2 ? p.out : p.u;
+          if (ok1) { kx = *reinterpret_cast<const double2 *>(&src[0][idx]); ky = *reinterpret_cast<const double2 *>(&src[1][idx]); kz = *reinterpret_cast<const double2 *>(&src[2][idx]); }
+          else if (ok0) { kx.x = src[0][idx]; ky.x = src[1][idx]; kz.x = src[2][idx]; }
         }
         double2 hx = make_double2(c.fTx, c.fTx), hy = make_double2(c.fTy, c.fTy), hz = make_double2(c.fTz, c.fTz);   // constant field (Zeeman dc + ac cos wt + applied), Tesla
         // exchange field in Tesla.  Entries of a motif site: first those with an even z offset (the neighbour pair
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(288, 2) stage_pair_kernel(const __grid_constan
                                    THERMAL ? (double)nz.e2 : 0.0, ux.x, uy.x, uz.x, kx.x, ky.x, kz.x, ox.x, oy.x, oz.x);
           rk4_site<STAGE, THERMAL>(c, p.dt, sx.y, sy.y, sz.y, hx.y, hy.y, hz.y, THERMAL ? (double)nz.o0 : 0.0, THERMAL ? (double)nz.o1 : 0.0,
                                    THERMAL ? (double)nz.o2 : 0.0, ux.y, uy.y, uz.y, kx.y, ky.y, kz.y, ox.y, oy.y, oz.y);
-          if (STAGE < 3) {   // the running sum: interior only, no images
+          if (STAGE == 2) {   // c = y1 + 2 y2 for the last stage: interior only, no images
             const int idx = ic + m * g.PZ;
             if (ok1) { stg128(&p.u[0][idx], kx.x, kx.y); stg128(&p.u[1][idx], ky.x, ky.y); stg128(&p.u[2][idx], kz.x, kz.y); }
             else if (ok0) { p.u[0][idx] = kx.x; p.u[1][idx] = ky.x; p.u[2][idx] = kz.x; }
