@@ -448,7 +448,7 @@ def other_configs(steps, peak_gbs=None):
             s.ctx.close()
         except Exception as e:  # noqa: BLE001
             out.append({"config": name, "error": str(e)})
-    try:   # llg-rk4-b200-gpu on the bench workload: four launches per step, 408 B of HBM traffic per spin-update
+    try:   # llg-rk4-b200-gpu on the bench workload: four launches per step, 336 B of HBM traffic per spin-update
         w = W.c3_sc(256, temperature=TEMPERATURE)
         lat = w["lattice"]
         s = create_solver(dict(module="llg-rk4-b200-gpu", t_step=W.T_STEP, t_max=1e-9, seed=3, options=dict(time_kernels=1)), lat)
@@ -462,9 +462,11 @@ def other_configs(steps, peak_gbs=None):
         ms = float(st.sum())
         rec = {"config": "RK4-LLG on C3 sc 256^3, T = %g K" % TEMPERATURE, "spins": lat.num_spins, "stage_ms": [float(st[0]), float(st[1])],
                "stage_ms_note": "stages 1 + 2, stages 3 + 4", "value": lat.num_spins / (ms * 1e-3), "unit": UNIT,
-               "kernel": names.get(s.ctx.stage_kernel(), "?"), "bytes_per_update": 408}
+               "kernel": names.get(s.ctx.stage_kernel(), "?"), "bytes_per_update": 336,
+               "bytes_note": "48 + 72 + 120 + 96 B: no stored k-sum (DESIGN.md 3.2b); 408 B with one"}
         if peak_gbs:
-            rec["hbm_frac"] = 408.0 * lat.num_spins / (ms * 1e-3) / 1e9 / peak_gbs
+            rec["hbm_frac"] = 336.0 * lat.num_spins / (ms * 1e-3) / 1e9 / peak_gbs
+            rec["frac_of_408B_model"] = 408.0 * lat.num_spins / (ms * 1e-3) / 1e9 / peak_gbs
         out.append(rec)
         s.ctx.close()
     except Exception as e:  # noqa: BLE001
