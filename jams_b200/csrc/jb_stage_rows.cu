@@ -94,7 +94,9 @@ __device__ __forceinline__ void seg_class(int b, int e, uint32_t tab0, uint32_t 
       }
     }
   } else if (MODE == 1) {
-#pragma unroll 2
+    // short segments hold few registers: unroll further, so that more loads are in flight per warp
+    constexpr int U = L <= 2 ? 4 : (L == 3 ? 3 : 2);
+#pragma unroll U
     for (int n = b; n < e; ++n) {
       SegRegs<L> A;
       seg_load<L>(A, tab0 + (uint32_t)n * 64u, own, oslot, R, slot8, cs8, ys8);
