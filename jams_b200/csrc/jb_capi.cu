@@ -610,8 +610,6 @@ static void choose_rows_tiling(jb_ctx *c) {
     }
   }
   if (!best_threads) return;
-  t.rows_mode = t.threads <= 32 * JB_ROWS_PIPE_WARPS ? 2 : 1;
-  if (c->opt_rows_mode >= 0 && c->opt_rows_mode <= 2 && (c->opt_rows_mode != 2 || t.threads <= 32 * JB_ROWS_PIPE_WARPS)) t.rows_mode = c->opt_rows_mode;
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
   if (c->d_rows) cudaFree(c->d_rows);
@@ -817,7 +815,7 @@ int tile_launch_shape(jb_ctx *c, const JbTileParams &p, int stage, int thermal, 
   if (c->num_sms == 0) JB_CUDA(c, cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, c->device));
   int per_sm = 0;
   if (rk4) JB_CUDA(c, jbk_rk4_stage_pair_occupancy(p, stage, thermal, t.threads, t.smem[stage > 0 ? 1 : 0], &per_sm));
-  else if (t.rows) JB_CUDA(c, jbk_stage_rows_occupancy(stage, thermal, t.rows_mode, t.threads, t.smem[stage], &per_sm));
+  else if (t.rows) JB_CUDA(c, jbk_stage_rows_occupancy(stage, thermal, t.threads, t.smem[stage], &per_sm));
   else JB_CUDA(c, jbk_stage_pair_occupancy(p, stage, thermal, c->iso ? 1 : 0, recu, t.threads, t.smem[stage], &per_sm));
   if (per_sm < 1) JB_FAIL(c, JB_ERR_CUDA, "the stage kernel does not fit on an SM with this tiling");
   if (c->opt_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_ctas_per_sm);
@@ -1352,7 +1350,7 @@ static int launch_tile_stage(jb_ctx *c, JbTileParams &tp, const JbStageParams &p
   } else {
     const int ua = recu ? 3 : 2;   // recover_u: the corrector's second ring carries the tile's own s_n (S0) instead of u
     const CUtensorMap tm[6] = {c->tmap[stage][0], c->tmap[stage][1], c->tmap[stage][2], c->tmap[ua][0], c->tmap[ua][1], c->tmap[ua][2]};
-    if (c->tiling.rows) JB_CUDA(c, jbk_stage_rows(tp, tm, stage, th, c->tiling.rows_mode, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
+    if (c->tiling.rows) JB_CUDA(c, jbk_stage_rows(tp, tm, stage, th, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
     else JB_CUDA(c, jbk_stage_pair(tp, tm, stage, th, c->iso ? 1 : 0, recu ? 1 : 0, c->tiling.threads, sh.grid, c->tiling.smem[stage], c->stream));
   }
   c->trace_ctas = sh.grid;
@@ -1791,7 +1789,6 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "tile_y") c->opt_TY = (int)value;
   else if (k == "tile_z") c->opt_TZ = (int)value;
   else if (k == "motif_split") c->opt_msplit = (int)value;
-  else if (k == "rows_mode") c->opt_rows_mode = (int)value;
   else if (k == "rows_warps") c->opt_rows_warps = (int)value;
   else if (k == "ring") c->opt_R = (int)value;
   else if (k == "ring_u") c->opt_RU = (int)value;

@@ -151,7 +151,6 @@ struct __align__(16) JbRowSeg {
 #define JB_ROWS_MAX_L 5
 #define JB_ROWS_Q 4           // sites (consecutive y rows) per consumer thread
 #define JB_ROWS_MAX_WARPS 8   // consumer warps per CTA (+ the producer warp: 288 threads, 168 registers per thread)
-#define JB_ROWS_PIPE_WARPS 4  // up to here five warps per CTA, at most two per scheduler: 255 registers, room for double-buffered segments
 struct JbTileParams {
   JbGeom g;
   double *out[3];        // spins written (S1 in stage A, S0 in stage B), own box
@@ -248,7 +247,6 @@ struct jb_ctx {
   struct Tiling {
     bool ok = false;
     bool rows = false;                    // the rows kernel (jb_stage_rows.cu) instead of the pair kernel
-    int rows_mode = 0;                    // its variant (jbk_stage_rows)
     int TY = 0, TZ = 0, UZ = 0, BY = 0, BZ = 0, gzb = 0, slotS = 0, slotU = 0, R = 0, RU = 0;
     int Rs[2] = {0, 0};                   // ring depth per stage
     int n_yt = 0, n_zt = 0, n_cols = 0, threads = 0, msplit = 1;
@@ -297,7 +295,6 @@ struct jb_ctx {
   int opt_chunk_long = 0, opt_chunk_short = 0, opt_tail_pct = -1;   // heuristic overrides: planes per long / short chunk, share of the planes in short chunks
   int opt_verbose = 0;
   int opt_grid = 0;           // upper limit of the number of resident CTAs of the persistent kernel (0 = occupancy x SMs)
-  int opt_rows_mode = -1;     // rows kernel variant: -1 = by the number of consumer warps
   int opt_rows_warps = 0;     // rows kernel: upper limit of consumer warps per CTA (0 = JB_ROWS_MAX_WARPS)
   int opt_recover_u = 1;      // pair kernel: 1 = no stored Heun intermediate (120 B per update), 0 = store u (144 B)
   int opt_check_symmetry = 1; // refuse an exchange matrix that is not symmetric, like the reference (settings key check_sparse_matrix_symmetry)
@@ -362,10 +359,9 @@ cudaError_t jbk_rk4_stage_pair(const JbTileParams &p, const CUtensorMap *tmaps6,
                                size_t smem_bytes, cudaStream_t stream);
 cudaError_t jbk_rk4_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm);
 // rows kernel (jb_stage_rows.cu): tmaps = {S.x, S.y, S.z}; threads = 32 x (TY / 4) x msplit consumer threads
-// mode: 2 = double-buffered segments (at most JB_ROWS_PIPE_WARPS consumer warps), 0 / 1 = single buffer, unrolled once / twice
-cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tmaps3, int stage, int thermal, int mode, int threads, int grid,
+cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tmaps3, int stage, int thermal, int threads, int grid,
                            size_t smem_bytes, cudaStream_t stream);
-cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int mode, int threads, size_t smem_bytes, int *blocks_per_sm);
+cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm);
 cudaError_t jbk_stage_pairs(const JbStageParams &p, const int *ell_idx, const int *ell_val, int width, const double *pairJ,
                             int iso, int stage, cudaStream_t stream);
 // term field (meV) into AoS N x 3 (device); term as jb_term; pairs path when ell_idx != nullptr

@@ -20,8 +20,7 @@
 //     i.e. (L + 3) loads for 4 L neighbour terms instead of 4 L loads.  On the bcc eight-shell template (112 entries per site:
 //     40 segments, 224 loads per component for four sites instead of 448) this halves the shared-memory traffic, the bound.
 //     Segments are sorted by length and every length has its own fully unrolled loop (no predicates, registers named at compile
-//     time); the loads of the next segment are issued before the arithmetic of the current one (explicit double buffering: a
-//     CTA has only four to eight consumer warps, so the overlap has to come from inside the thread).
+//     time).
 //   * data flow: recover_u -- the predictor writes only s*, the corrector reads the site's own s_n straight
 //     from global memory (coalesced, issued before the gather so that the latency hides behind it), rebuilds the Heun
 //     intermediate and writes s_{n+1} in place: 120 B of HBM traffic per spin-update.
@@ -73,47 +72,24 @@ __device__ __forceinline__ void seg_fma(const SegRegs<L> &r, double (&h)[JB_ROWS
   }
 }
 
-// all segments [b, e) of one length.  MODE 2 (CTAs with at most four consumer warps, 255 registers per thread): the loads of
-// segment n + 1 are in flight while segment n is accumulated, explicit double buffering.  MODE 0 / 1 (up to eight consumer
-// warps, 168 registers): one buffer, unrolled once / twice; the second warp of the scheduler fills the gaps.
-template <int L, int MODE>
+// all segments [b, e) of one length.  Short segments hold few registers and are unrolled further, so that more loads are in
+// flight per warp (a CTA has at most eight consumer warps; the second warp of a scheduler fills the remaining gaps).  A variant
+// with explicitly double-buffered segments for CTAs of four consumer warps (255 registers) was measured slower (it spilled):
+// profiles/README.md r02n.
+template <int L>
 __device__ __forceinline__ void seg_class(int b, int e, uint32_t tab0, uint32_t own, int oslot, int R, uint32_t slot8, uint32_t cs8, uint32_t ys8,
                                           double (&h)[JB_ROWS_Q][3]) {
-  if (b >= e) return;
-  if (MODE == 2) {
-    SegRegs<L> A, B;
-    seg_load<L>(A, tab0 + (uint32_t)b * 64u, own, oslot, R, slot8, cs8, ys8);
-#pragma unroll 1
-    for (int n = b; n < e; n += 2) {
-      const bool more1 = n + 1 < e, more2 = n + 2 < e;
-      if (more1) seg_load<L>(B, tab0 + (uint32_t)(n + 1) * 64u, own, oslot, R, slot8, cs8, ys8);
-      seg_fma<L>(A, h);
-      if (more1) {
-        if (more2) seg_load<L>(A, tab0 + (uint32_t)(n + 2) * 64u, own, oslot, R, slot8, cs8, ys8);
-        seg_fma<L>(B, h);
-      }
-    }
-  } else if (MODE == 1) {
-    // short segments hold few registers: unroll further, so that more loads are in flight per warp
-    constexpr int U = L <= 2 ? 4 : (L == 3 ? 3 : 2);
+  constexpr int U = L <= 2 ? 4 : (L == 3 ? 3 : 2);
 #pragma unroll U
-    for (int n = b; n < e; ++n) {
-      SegRegs<L> A;
-      seg_load<L>(A, tab0 + (uint32_t)n * 64u, own, oslot, R, slot8, cs8, ys8);
-      seg_fma<L>(A, h);
-    }
-  } else {
-#pragma unroll 1
-    for (int n = b; n < e; ++n) {
-      SegRegs<L> A;
-      seg_load<L>(A, tab0 + (uint32_t)n * 64u, own, oslot, R, slot8, cs8, ys8);
-      seg_fma<L>(A, h);
-    }
+  for (int n = b; n < e; ++n) {
+    SegRegs<L> A;
+    seg_load<L>(A, tab0 + (uint32_t)n * 64u, own, oslot, R, slot8, cs8, ys8);
+    seg_fma<L>(A, h);
   }
 }
 
-template <int STAGE, bool THERMAL, int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(const __grid_constant__ CUtensorMap tS0,
+template <int STAGE, bool THERMAL>
+__global__ void __launch_bounds__(288, 1) stage_rows_kernel(const __grid_constant__ CUtensorMap tS0,
                                                             const __grid_constant__ CUtensorMap tS1,
                                                             const __grid_constant__ CUtensorMap tS2,
                                                             const __grid_constant__ JbTileParams p) {
@@ -232,11 +208,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(co
         for (int s = 0; s < JB_ROWS_Q; ++s) { h[s][0] = c.fTx; h[s][1] = c.fTy; h[s][2] = c.fTz; }   // constant field (Zeeman dc + ac cos wt + applied), Tesla
         const uint32_t ownm = own + (uint32_t)(m * p.BZ) * 8u;
         const int *rb = p.row_begin[m];
-        seg_class<5, MODE>(rb[4], rb[5], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
-        seg_class<4, MODE>(rb[3], rb[4], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
-        seg_class<3, MODE>(rb[2], rb[3], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
-        seg_class<2, MODE>(rb[1], rb[2], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
-        seg_class<1, MODE>(rb[0], rb[1], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
+        seg_class<5>(rb[4], rb[5], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
+        seg_class<4>(rb[3], rb[4], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
+        seg_class<3>(rb[2], rb[3], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
+        seg_class<2>(rb[1], rb[2], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
+        seg_class<1>(rb[0], rb[1], tab0, ownm, oslot, R, slot8, cs8, ys8, h);
         // the thread's own spins (centre plane)
         double sc[JB_ROWS_Q][3];
         {
@@ -301,28 +277,27 @@ __global__ void __launch_bounds__(MODE == 2 ? 160 : 288, 1) stage_rows_kernel(co
 }
 
 template <typename F>
-cudaError_t with_kernel(int stage, int thermal, int mode, F &&f) {
-#define JB_ROWS_CASE(ST, TH, MD) if (stage == ST && thermal == TH && mode == MD) return f(stage_rows_kernel<ST, (TH != 0), MD>);
-#define JB_ROWS_CASES(MD) JB_ROWS_CASE(0, 0, MD) JB_ROWS_CASE(0, 1, MD) JB_ROWS_CASE(1, 0, MD) JB_ROWS_CASE(1, 1, MD)
-  JB_ROWS_CASES(0) JB_ROWS_CASES(1) JB_ROWS_CASES(2)
-#undef JB_ROWS_CASES
-#undef JB_ROWS_CASE
+cudaError_t with_kernel(int stage, int thermal, F &&f) {
+  if (stage == 0 && !thermal) return f(stage_rows_kernel<0, false>);
+  if (stage == 0 && thermal) return f(stage_rows_kernel<0, true>);
+  if (stage == 1 && !thermal) return f(stage_rows_kernel<1, false>);
+  if (stage == 1 && thermal) return f(stage_rows_kernel<1, true>);
   return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
-cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int mode, int threads, size_t smem_bytes, int *blocks_per_sm) {
-  return with_kernel(stage, thermal, mode, [&](auto k) -> cudaError_t {
+cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm) {
+  return with_kernel(stage, thermal, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads + 32, smem_bytes);
   });
 }
 
-cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int mode, int threads, int grid,
+cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int threads, int grid,
                            size_t smem_bytes, cudaStream_t stream) {
-  return with_kernel(stage, thermal, mode, [&](auto k) -> cudaError_t {
+  return with_kernel(stage, thermal, [&](auto k) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, threads + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
