@@ -308,7 +308,7 @@ def test_kernel_choice_deep_templates_go_to_the_rows_kernel():
 
 
 @pytest.mark.parametrize("dims,periodic", [((8, 9, 40), (True, True, True)), ((7, 13, 33), (True, True, True)), ((9, 8, 70), (False, True, False)),
-                                           ((8, 21, 8), (True, False, True))])
+                                           ((8, 21, 8), (True, False, True)), ((16, 36, 70), (True, True, True))])   # the last one: 3 x 3 column tiles, several chunks
 @pytest.mark.parametrize("T", [0.0, 200.0])
 def test_deep_template_rows_kernel_matches_oracle(dims, periodic, T):
     """BASELINE config 4's template (bcc, eight shells, 112 neighbours per spin, ghost depth 3) on small lattices with ragged
