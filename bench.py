@@ -434,7 +434,8 @@ def other_configs(steps, peak_gbs=None):
     from jams_b200.solver import create_hamiltonian, create_solver
     names = {0: "direct gathers", 2: "TMA pair kernel", 4: "TMA rows kernel", 5: "general neighbour list"}
     out = []
-    for name, w, z in (("C2 bcc Fe 128^3 NN+NNN (z = 14), T = 300 K", W.c2_bcc_fe(128, temperature=300.0), 14),
+    for name, w, z in (("C2 bcc Fe 64^3 NN+NNN (z = 14), T = 300 K (BASELINE config 2)", W.c2_bcc_fe(64, temperature=300.0), 14),
+                       ("C2 bcc Fe 128^3 NN+NNN (z = 14), T = 300 K", W.c2_bcc_fe(128, temperature=300.0), 14),
                        ("C4 bcc 128^3, 8 shells (z = 112), T = 0", W.c4_bcc_long_range(128, temperature=0.0), 112)):
         try:
             s = W.make_solver(w, options=dict(time_kernels=1), random_spins_seed=1)

@@ -756,6 +756,24 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
     }
   } else if (c->chunk_long > 0) {
     best = make_candidate(nx, gx, c->chunk_long, c->chunk_short > 0 ? c->chunk_short : std::max(gx, 2), c->tail_pct >= 0 ? c->tail_pct : 25);
+  } else if ((double)nx * n_cols / std::max(1, G) < 24.0) {
+    // small lattices (less than three 8-plane items per resident CTA; BASELINE config 2 at 64^3: 3.5 planes per CTA): the
+    // chunks must be short enough to give every CTA an item -- equal chunks of 1 ... 8 planes, the makespan of the simulated
+    // queue decides; an item pays for its 2 gx halo planes (loads only, from L2 at these sizes) and a fixed overhead.
+    // Measured on C2 64^3: 8-plane chunks (160 of 296 CTAs busy) 7.9 G spin-updates/s, 4-plane chunks 11.8 G.
+    double best_t = 1e300;
+    for (int L : {1, 2, 3, 4, 5, 6, 8, 12, 16}) {
+      if (L > nx || L < std::max(gx, 1)) continue;
+      const int nc = std::min((nx + L - 1) / L, JB_TILE_MAX_CHUNKS);
+      ChunkPlanCandidate cd;
+      for (int k = 0; k < nc; ++k) {
+        const int x0 = (int)((long long)k * nx / nc), x1 = (int)((long long)(k + 1) * nx / nc);
+        cd.xs.push_back({x0, x1 - x0}); cd.taper.push_back(0);
+      }
+      const double t = simulate_queue(cd, queue_order(cd, nx, gx), n_cols, G, 0.35 + 0.5 * 2 * gx);
+      if (t < best_t) { best_t = t; best = cd; }
+    }
+    if (best.xs.empty()) best = make_candidate(nx, gx, nx, nx, 0);
   } else {
     const double per_cta = (double)nx * n_cols / std::max(1, G);   // planes of work per resident CTA
     double best_t = 1e300;
