@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(288, 1) stage_rows_kernel(const __grid_constan
   const uint32_t slot8 = 3u * cs8;                       // slot stride, bytes
   const uint32_t ys8 = (uint32_t)(M * p.BZ) * 8u;        // y stride inside a slot, bytes
   // the thread's first site (row ty0, m = 0, component x) in slot 0 of the ring
-  const uint32_t own = smem_u32(ringS) + (uint32_t)(((ty0 + g.gy) * M) * p.BZ + zl + p.gzb) * 8u;
+  // (lanes beyond a narrow tile, TZ < 32, compute on column 0 and store nothing: their loads stay inside the slot)
+  const uint32_t own = smem_u32(ringS) + (uint32_t)(((ty0 + g.gy) * M) * p.BZ + (zl < p.TZ ? zl : 0) + p.gzb) * 8u;
   const uint32_t tab0 = smem_u32(s_rows);
   const uint32_t fullS0 = smem_u32(fullS), emptyS0 = smem_u32(emptyS);
   const unsigned long long planeSites = (unsigned long long)g.Ny * g.Nz * M;
