@@ -10,6 +10,26 @@
 // shared memory after the rings: 4 x JB_PAIR_BARS mbarriers, the item ring (JB_ITEM_RING ints), two face-arrival counters + pad
 #define JB_STAGE_TAIL_WORDS (4 * JB_PAIR_BARS + JB_ITEM_RING / 2 + 2)   // in 8-byte words; the tables (16-byte aligned) follow
 
+#include <mutex>
+#include <unordered_map>
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a driver call of several microseconds: once per kernel, device and size
+// instead of once per launch (the stage launches of small lattices are host-bound: BASELINE config 1 runs 11 us kernels)
+template <typename K>
+inline cudaError_t jb_ensure_dynamic_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, size_t> done;   // (function, device) -> largest size set so far
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(reinterpret_cast<const void *>(kernel)) * 64ull + (unsigned long long)dev;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (err == cudaSuccess) done[key] = bytes;
+  return err;
+}
+
 namespace jbdev {
 
 static __device__ __forceinline__ unsigned long long global_timer_ns() {

@@ -386,7 +386,7 @@ cudaError_t with_kernel(int stage, int thermal, int iso, int motif1, int recu, F
 cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int iso, int recu, int threads,
                                      size_t smem_bytes, int *blocks_per_sm) {
   return with_kernel(stage, thermal, iso, p.g.M == 1 ? 1 : 0, recu, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32, smem_bytes);
   });
@@ -395,7 +395,7 @@ cudaError_t jbk_stage_pair_occupancy(const JbTileParams &p, int stage, int therm
 cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int iso, int recu,
                            int threads, int grid, size_t smem_bytes, cudaStream_t stream) {
   return with_kernel(stage, thermal, iso, p.g.M == 1 ? 1 : 0, recu, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     return cudaGetLastError();
@@ -404,7 +404,7 @@ cudaError_t jbk_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int sta
 
 cudaError_t jbk_rk4_stage_pair_occupancy(const JbTileParams &p, int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm) {
   return with_rk4_kernel(stage, thermal, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, ((threads + 31) & ~31) + 32, smem_bytes);
   });
@@ -413,7 +413,7 @@ cudaError_t jbk_rk4_stage_pair_occupancy(const JbTileParams &p, int stage, int t
 cudaError_t jbk_rk4_stage_pair(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int threads, int grid,
                                size_t smem_bytes, cudaStream_t stream) {
   return with_rk4_kernel(stage, thermal, p.g.M == 1 ? 1 : 0, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, ((threads + 31) & ~31) + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p);
     return cudaGetLastError();

@@ -290,7 +290,7 @@ cudaError_t with_kernel(int stage, int thermal, F &&f) {
 
 cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int threads, size_t smem_bytes, int *blocks_per_sm) {
   return with_kernel(stage, thermal, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, threads + 32, smem_bytes);
   });
@@ -299,7 +299,7 @@ cudaError_t jbk_stage_rows_occupancy(int stage, int thermal, int threads, size_t
 cudaError_t jbk_stage_rows(const JbTileParams &p, const CUtensorMap *tm, int stage, int thermal, int threads, int grid,
                            size_t smem_bytes, cudaStream_t stream) {
   return with_kernel(stage, thermal, [&](auto k) -> cudaError_t {
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t err = jb_ensure_dynamic_smem(k, smem_bytes);
     if (err != cudaSuccess) return err;
     k<<<grid, threads + 32, smem_bytes, stream>>>(tm[0], tm[1], tm[2], p);
     return cudaGetLastError();
