@@ -138,6 +138,33 @@ def test_cpp_simulation_equals_python_mirror_and_writes_jams_monitor_files(tmp_p
 
 
 @pytest.mark.gpu
+def test_cpp_simulation_with_biquadratic_exchange_equals_python_mirror(tmp_path):
+    """module = "biquadratic-exchange" (hamiltonian/cuda_biquadratic_exchange.cu) through the C++ host: the patch replaces the
+    Hamiltonian list; a negative coupling must be dropped by the value > energy_cutoff filter; the energy monitor writes the
+    reference's total (half the sum of the per-spin energies)"""
+    from jams_b200.solver import create_hamiltonian, create_solver
+    patch = ('hamiltonians = ( { module = "exchange"; interactions = (("A", "A", [1.0, 0.0, 0.0], 3.5e-21)); }, '
+             '{ module = "biquadratic-exchange"; interactions = (("A", "A", [1.0, 0.0, 0.0], 0.7e-21), ("A", "A", [1.0, 1.0, 0.0], -0.2e-21)); } ); ')
+    got, done = host.run(FIXTURE, PATCH_B200, patch, name="bq", output_dir=str(tmp_path))
+    assert done == 40
+    init, _ = host.run(FIXTURE, PATCH_B200, patch, name="bq0", output_dir=str(tmp_path), max_steps=0)
+    lat = W.c1_bloch_wall((32, 4, 4))["lattice"]
+    s = create_solver(dict(module="llg-heun-b200-gpu", t_step=1e-16, t_max=1e-9, seed=0), lat)
+    hs = [dict(module="exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 3.5e-21)]),
+          dict(module="biquadratic-exchange", interactions=[("A", "A", [1.0, 0.0, 0.0], 0.7e-21), ("A", "A", [1.0, 1.0, 0.0], -0.2e-21)])]
+    for h in hs:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    assert len(s.hamiltonians[1].template["B"]) == 6
+    s.set_spins(init)
+    e0 = s.hamiltonians[1].calculate_total_energy(0.0)
+    s.run(40)
+    assert np.array_equal(got, s.spins())
+    eng = open(tmp_path / "bq_eng.tsv").read().splitlines()
+    assert eng[0].split() == ["time", "exchange_E_meV", "biquadratic-exchange_E_meV"]
+    assert float(eng[1].split()[2]) == pytest.approx(e0, rel=1e-12)
+
+
+@pytest.mark.gpu
 def test_cpp_simulation_runs_the_shipped_example_setup_rk4_with_pinned_boundaries(tmp_path):
     """examples/bloch_domain_wall as shipped: solver llg-rk4-gpu + physics pinned_boundaries (bloch_domain_wall.cfg:75-81,132-139),
     through the C++ Simulation and through the Python mirror (main loop order of core/jams++.cc:333-341)"""
