@@ -243,7 +243,8 @@ Lattice::Lattice(const Setting &config) {
   for (int n = 0; n < 3; ++n) dims[n] = static_cast<int>(size[n].as_int());
   if (const Setting *p = lat.find("periodic")) for (int n = 0; n < 3; ++n) periodic[n] = (*p)[n].as_bool();
   if (const Setting *sf = lat.find("spins")) spins_file = sf->as_string();
-  if (lat.exists("impurities")) throw std::runtime_error("lattice.impurities is not supported by the llg-heun-b200-gpu host layer");
+  const Setting *impurity_settings = lat.find("impurities");
+  impurities_seed = static_cast<uint64_t>(lat.get("impurities_seed", 0));   // the reference draws a seed from its global generator if absent
   if (lat.exists("global_rotation") || lat.exists("orientation_axis")) throw std::runtime_error("lattice rotations are not supported by the llg-heun-b200-gpu host layer");
 
   // motif (core/lattice.cc:286-310, 429-470)
@@ -267,6 +268,44 @@ Lattice::Lattice(const Setting &config) {
   if (dims[0] < 1 || dims[1] < 1 || dims[2] < 1 || n >= (1LL << 31)) throw std::runtime_error("invalid lattice size");
   num_spins = static_cast<int>(n);
 
+  if (impurity_settings) {   // read_impurities_from_config (core/lattice.cc:1077-1109) + the substitution loop of generate_supercell (:614-640)
+    std::map<int, std::pair<int, double>> impurity_map;
+    for (int q = 0; q < impurity_settings->length(); ++q) {
+      const Setting &e = (*impurity_settings)[q];
+      const std::string a = e[0].as_string(), b = e[1].as_string();
+      if (!material_exists(a)) throw std::runtime_error("impurity " + std::to_string(q) + " materialA (" + a + ") does not exist");
+      if (!material_exists(b)) throw std::runtime_error("impurity " + std::to_string(q) + " materialB (" + b + ") does not exist");
+      const double fraction = e[2].as_double();
+      if (fraction < 0.0 || fraction >= 1.0) throw std::runtime_error("impurity " + std::to_string(q) + " fraction must be 0 =< x < 1");
+      if (!impurity_map.emplace(material_index(a), std::make_pair(material_index(b), fraction)).second)
+        throw std::runtime_error("impurity " + std::to_string(q) + " redefines a previous impurity");
+    }
+    // pcg32 (setseq_xsh_rr_64_32, default stream) and libstdc++'s generate_canonical<double, 53> over a 32-bit generator, restated from
+    // their published definitions (the reference fetches pcg at configure time): one draw per candidate site, in site order
+    const uint64_t mult = 6364136223846793005ULL, inc = 1442695040888963407ULL;
+    uint64_t state = (impurities_seed + inc) * mult + inc;
+    auto next32 = [&]() -> uint32_t {
+      const uint64_t old = state;
+      state = old * mult + inc;
+      const uint32_t x = static_cast<uint32_t>(((old >> 18u) ^ old) >> 27u), rot = static_cast<uint32_t>(old >> 59u);
+      return (x >> rot) | (x << ((0u - rot) & 31u));
+    };
+    auto uniform = [&]() -> double {
+      double sum = 0.0, tmp = 1.0;
+      for (int k = 0; k < 2; ++k) { sum += static_cast<double>(next32()) * tmp; tmp *= 4294967296.0; }
+      const double r = sum / tmp;
+      return r < 1.0 ? r : std::nextafter(1.0, 0.0);
+    };
+    site_materials_.resize(num_spins);
+    for (int i = 0; i < num_spins; ++i) {
+      int material = motif_material[i % M];
+      const auto it = impurity_map.find(material);
+      if (it != impurity_map.end() && uniform() < it->second.second) material = it->second.first;
+      site_materials_[i] = material;
+    }
+    has_impurities = !impurity_map.empty();
+  }
+
   if (const Setting *solver = config.find("solver")) gilbert_prefactor = solver->get("gilbert_prefactor", false);   // core/lattice.cc:696-697
   {   // the reference asks spglib here (core/lattice.cc:783-822)
     std::vector<int> types(motif_material.begin(), motif_material.end());
@@ -285,7 +324,7 @@ bool Lattice::material_exists(const std::string &name) const {
 
 std::vector<int32_t> Lattice::site_material() const {
   std::vector<int32_t> v(num_spins);
-  for (int i = 0; i < num_spins; ++i) v[i] = motif_material[i % M];
+  for (int i = 0; i < num_spins; ++i) v[i] = material_of_site(i);
   return v;
 }
 std::vector<int32_t> Lattice::site_motif() const {
@@ -295,18 +334,18 @@ std::vector<int32_t> Lattice::site_motif() const {
 }
 std::vector<double> Lattice::mus() const {
   std::vector<double> v(num_spins);
-  for (int i = 0; i < num_spins; ++i) v[i] = materials[motif_material[i % M]].moment;
+  for (int i = 0; i < num_spins; ++i) v[i] = materials[material_of_site(i)].moment;
   return v;
 }
 std::vector<double> Lattice::alpha() const {
   std::vector<double> v(num_spins);
-  for (int i = 0; i < num_spins; ++i) v[i] = materials[motif_material[i % M]].alpha;
+  for (int i = 0; i < num_spins; ++i) v[i] = materials[material_of_site(i)].alpha;
   return v;
 }
 std::vector<double> Lattice::gyro() const {   // core/lattice.cc:91-97,709-713
   std::vector<double> v(num_spins);
   for (int i = 0; i < num_spins; ++i) {
-    const Material &m = materials[motif_material[i % M]];
+    const Material &m = materials[material_of_site(i)];
     v[i] = gilbert_prefactor ? m.gyro / (1.0 + m.alpha * m.alpha) : m.gyro;
   }
   return v;
@@ -354,7 +393,7 @@ std::vector<double> Lattice::initial_spins(uint64_t seed) const {   // core/latt
   std::mt19937_64 rng(seed);   // the reference seeds pcg32 from std::random_device here: "random" spins are unpinned by design
   std::normal_distribution<double> nd;
   for (int i = 0; i < num_spins; ++i) {
-    const Material &m = materials[motif_material[i % M]];
+    const Material &m = materials[material_of_site(i)];
     Vec3 spin = m.spin;
     if (m.randomize) spin = {{nd(rng), nd(rng), nd(rng)}};
     if (m.moment == 0.0) spin = {{0, 0, 0}};   // vacancies
@@ -460,6 +499,20 @@ NeighbourList Lattice::neighbour_list(const InteractionTemplate &t) const {   //
       if (!ok) continue;
       pairs.push_back({site_index(i, j, k, t.mi[n]), site_index(c[0], c[1], c[2], t.mj[n]), n, order});
     }
+  }
+  if (has_impurities) {
+    // the reference looks for duplicate pairs first, then skips pairs whose site materials differ from the entry's types --
+    // those of its motif positions -- "presumably an impurity site" (core/interactions.cc:373-385)
+    std::vector<Pair> sorted(pairs);
+    std::sort(sorted.begin(), sorted.end(), [](const Pair &a, const Pair &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    for (size_t p = 1; p < sorted.size(); ++p)
+      if (sorted[p].i == sorted[p - 1].i && sorted[p].j == sorted[p - 1].j)
+        throw std::runtime_error("Multiple interactions for sites " + std::to_string(sorted[p].i) + " and " + std::to_string(sorted[p].j));
+    std::vector<Pair> kept;
+    kept.reserve(pairs.size());
+    for (const Pair &p : pairs)
+      if (material_of_site(p.i) == motif_material[t.mi[p.entry]] && material_of_site(p.j) == motif_material[t.mj[p.entry]]) kept.push_back(p);
+    pairs.swap(kept);
   }
   // unique values in first-insertion order (containers/unordered_vector_set.h:38-45)
   NeighbourList nl;
@@ -801,7 +854,7 @@ UniaxialAnisotropyHamiltonian::UniaxialAnisotropyHamiltonian(const Setting &s, c
     axis = {{axis[0] / n, axis[1] / n, axis[2] / n}};   // normalize()
     const double energy = e[2].as_double();
     for (int i = 0; i < N; ++i) {
-      if ((motif_position >= 0 && i % lattice.M == motif_position) || (material >= 0 && lattice.motif_material[i % lattice.M] == material)) {
+      if ((motif_position >= 0 && i % lattice.M == motif_position) || (material >= 0 && lattice.material_of_site(i) == material)) {
         magnitude_[i] = energy * input_energy_unit_conversion_;
         for (int k = 0; k < 3; ++k) axis_[3 * static_cast<size_t>(i) + k] = axis[k];
       }
@@ -816,7 +869,7 @@ ZeemanHamiltonian::ZeemanHamiltonian(const Setting &s, const Lattice &lattice) :
   if (const Setting *dc = s.find("dc_local_field")) {
     if (dc->length() != nmat) throw std::runtime_error("dc_local_field: field must be specified for every material");
     for (int i = 0; i < N; ++i) for (int k = 0; k < 3; ++k)
-      dc_local_field_[3 * static_cast<size_t>(i) + k] = (*dc)[lattice.motif_material[i % lattice.M]][k].as_double() * mus[i];
+      dc_local_field_[3 * static_cast<size_t>(i) + k] = (*dc)[lattice.material_of_site(i)][k].as_double() * mus[i];
   }
   if (s.exists("ac_local_field") || s.exists("ac_local_frequency")) {
     if (!(s.exists("ac_local_field") && s.exists("ac_local_frequency"))) throw std::runtime_error("ac_local_field: must have a field and a frequency");
@@ -825,7 +878,7 @@ ZeemanHamiltonian::ZeemanHamiltonian(const Setting &s, const Lattice &lattice) :
     has_ac_local_field_ = true;
     ac_local_field_.assign(3 * static_cast<size_t>(N), 0.0); ac_local_frequency_.assign(N, 0.0);
     for (int i = 0; i < N; ++i) {
-      const int mat = lattice.motif_material[i % lattice.M];
+      const int mat = lattice.material_of_site(i);
       for (int k = 0; k < 3; ++k) ac_local_field_[3 * static_cast<size_t>(i) + k] = f[mat][k].as_double() * mus[i];
       ac_local_frequency_[i] = kTwoPi * w[mat].as_double();
     }
@@ -1041,7 +1094,7 @@ MagnetisationLayersMonitor::MagnetisationLayersMonitor(const Setting &settings, 
     group_names_.push_back("total");
   } else if (grouping == "materials") {
     groups.resize(lattice.materials.size());
-    for (int i = 0; i < N; ++i) groups[lattice.motif_material[i % lattice.M]].push_back(i);
+    for (int i = 0; i < N; ++i) groups[lattice.material_of_site(i)].push_back(i);
     for (const auto &m : lattice.materials) group_names_.push_back(m.name);
   } else if (grouping == "positions") {
     groups.resize(lattice.M);
@@ -1245,6 +1298,12 @@ double Hamiltonian::calculate_total_energy(double time) {
 void ExchangeHamiltonian::attach(jb_ctx *ctx) {
   // check_sparse_matrix_symmetry = false switches the symmetry check off (hamiltonian/exchange.cc:104-110); default: checked
   solver->check(jb_set_option(ctx, "check_symmetry", check_symmetry_ ? 1 : 0));
+  if (lattice_.has_impurities) {   // not translation invariant: the neighbour list itself (general kernel)
+    const NeighbourList nl = lattice_.neighbour_list(template_);
+    solver->check(jb_set_exchange_pairs(ctx, static_cast<int64_t>(nl.i.size()), nl.i.data(), nl.j.data(), nl.value_id.data(),
+                                        static_cast<int32_t>(nl.values9.size() / 9), nl.values9.data()));
+    return;
+  }
   solver->check(jb_set_exchange_template(ctx, template_.size(), template_.mi.data(), template_.mj.data(), template_.T3.data(), template_.J9.data()));
 }
 // hamiltonian/cuda_biquadratic_exchange.cu:9-156: the exchange grammar, scalar B = J[0][0] * unit (no interaction_prefactor), only

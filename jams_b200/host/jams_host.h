@@ -106,7 +106,11 @@ class Lattice {
   std::vector<double> mus() const, gyro() const, alpha() const;
   std::vector<double> initial_spins(uint64_t seed) const;   // N x 3; "random" materials use a seeded uniform-on-sphere draw;
                                                             // lattice.spins = "file" replaces them (core/lattice.cc:738-748)
+  bool has_impurities = false;                              // lattice.impurities (core/lattice.cc:424-427): random substitution of materials
+  uint64_t impurities_seed = 0;
+  int material_of_site(int i) const { return site_materials_.empty() ? motif_material[i % M] : site_materials_[i]; }
   std::string spins_file;                                   // lattice.spins
+  std::vector<int32_t> site_materials_;                     // per site, only with impurities
   mutable long long snapshot_iteration = 0;                 // iteration recorded in the header of a loaded snapshot (0 = none)
   std::vector<double> positions() const;                    // N x 3, lattice constants
   std::vector<int32_t> site_material() const, site_motif() const;

@@ -189,6 +189,31 @@ def read_interaction_file(path):
     return out
 
 
+class Pcg32:
+    """pcg32 = setseq_xsh_rr_64_32 with the default stream (M. O'Neill, pcg-random.org, pcg_random.hpp): 64-bit LCG state,
+    output = rotr32(((old >> 18) ^ old) >> 27, old >> 59) of the state BEFORE the step; seeding state = bump(seed + increment).
+    uniform_real(): libstdc++'s std::generate_canonical<double, 53> over a 32-bit generator: two draws, (g0 + g1 2^32) / 2^64."""
+    MULT, INC, MASK = 6364136223846793005, 1442695040888963407, (1 << 64) - 1
+
+    def __init__(self, seed):
+        self.state = (((int(seed) + self.INC) & self.MASK) * self.MULT + self.INC) & self.MASK
+
+    def __call__(self):
+        old = self.state
+        self.state = (old * self.MULT + self.INC) & self.MASK
+        x = (((old >> 18) ^ old) >> 27) & 0xffffffff
+        rot = old >> 59
+        return ((x >> rot) | (x << ((-rot) & 31))) & 0xffffffff
+
+    def uniform_real(self):
+        total, tmp = 0.0, 1.0
+        for _ in range(2):
+            total += float(self()) * tmp
+            tmp *= 4294967296.0
+        ret = total / tmp
+        return ret if ret < 1.0 else float(np.nextafter(1.0, 0.0))
+
+
 @dataclass
 class Lattice:
     """Materials + unit cell + supercell (reference core/lattice.h)."""
@@ -199,6 +224,8 @@ class Lattice:
     periodic: tuple = (True, True, True)
     gilbert_prefactor: bool = False
     symops: tuple | None = None       # (rotations (n,3,3) fractional, translations (n,3)); None = found from the cell and motif
+    impurities: list | None = None    # lattice.impurities: [(materialA, materialB, fraction), ...] (core/lattice.cc:424-427,1077-1109)
+    impurities_seed: int = 0          # lattice.impurities_seed (the reference draws one from its global generator if absent)
 
     def __post_init__(self):
         self.cell = np.asarray(self.cell, dtype=np.float64).reshape(3, 3)
@@ -210,6 +237,19 @@ class Lattice:
         self.periodic = tuple(bool(p) for p in self.periodic)
         if self.symops is None:   # the reference asks spglib (core/lattice.cc:783-822); here: find_space_group_operations
             self.symops = find_space_group_operations(self.cell, self.motif_frac, self.motif_material)
+        # read_impurities_from_config (core/lattice.cc:1077-1109)
+        self.impurity_map = {}
+        for n, (a, b, fraction) in enumerate(self.impurities or []):
+            if a not in self.material_index:
+                raise RuntimeError(f"impurity {n} materialA ({a}) does not exist")
+            if b not in self.material_index:
+                raise RuntimeError(f"impurity {n} materialB ({b}) does not exist")
+            if fraction < 0.0 or fraction >= 1.0:
+                raise RuntimeError(f"impurity {n} fraction must be 0 =< x < 1")
+            if self.material_index[a] in self.impurity_map:
+                raise RuntimeError(f"impurity {n} redefines a previous impurity")
+            self.impurity_map[self.material_index[a]] = (self.material_index[b], float(fraction))
+        self._site_material_all = None
 
     # -- sizes
     @property
@@ -238,29 +278,56 @@ class Lattice:
         cells = nx * self.dims[1] * self.dims[2]
         return np.tile(np.asarray(per_motif), (cells,) + (1,) * (np.ndim(per_motif) - 1))
 
+    @property
+    def has_impurities(self):   # core/lattice.cc:1115-1117
+        return bool(self.impurity_map)
+
+    def _site_materials(self):
+        """generate_supercell's substitution loop (core/lattice.cc:614-640): sites in the order (i, j, k, m); a site whose motif
+        material has an impurity entry draws one uniform number (std::uniform_real_distribution<> over pcg32(impurity_seed)) and
+        becomes materialB if it is below the fraction.  pcg32 and libstdc++'s generate_canonical are restated from their
+        published definitions (the reference fetches pcg at configure time; it is not in the tree): the STREAM is unpinned, the
+        structure that follows from a given set of site materials is checked against the oracle."""
+        if self._site_material_all is None:
+            mat = self._tile(self.motif_material).astype(np.int32)
+            if self.impurity_map:
+                rng = Pcg32(self.impurities_seed)
+                for site in np.nonzero(np.isin(mat, list(self.impurity_map)))[0]:
+                    b, fraction = self.impurity_map[int(mat[site])]
+                    if rng.uniform_real() < fraction:
+                        mat[site] = b
+            self._site_material_all = mat
+        return self._site_material_all
+
+    def _per_site(self, per_material, x0=0, nx=None):
+        return np.asarray(per_material)[self.site_material(x0, nx)]
+
     def site_material(self, x0=0, nx=None):
-        return self._tile(self.motif_material, x0, nx).astype(np.int32)
+        if not self.impurity_map:
+            return self._tile(self.motif_material, x0, nx).astype(np.int32)
+        nx = self.dims[0] if nx is None else nx
+        per_plane = self.dims[1] * self.dims[2] * self.M
+        return self._site_materials()[x0 * per_plane:(x0 + nx) * per_plane]
 
     def site_motif(self, x0=0, nx=None):
         return self._tile(np.arange(self.M, dtype=np.int32), x0, nx)
 
     def mus(self, x0=0, nx=None):
         """globals::mus = moment * mu_B (containers/material.h:32)"""
-        return self._tile([self.materials[t].moment * kBohrMagnetonIU for t in self.motif_material], x0, nx)
+        return self._per_site([m.moment * kBohrMagnetonIU for m in self.materials], x0, nx)
 
     def alpha(self, x0=0, nx=None):
-        return self._tile([self.materials[t].alpha for t in self.motif_material], x0, nx)
+        return self._per_site([m.alpha for m in self.materials], x0, nx)
 
     def gyro(self, x0=0, nx=None):
         """globals::gyro (containers/material.h:33, core/lattice.cc:91-97,709-713)"""
         vals = []
-        for t in self.motif_material:
-            mat = self.materials[t]
+        for mat in self.materials:
             g = mat.gyro * kGyromagneticRatioIU
             if self.gilbert_prefactor:
                 g = g / (1.0 + mat.alpha * mat.alpha)
             vals.append(g)
-        return self._tile(vals, x0, nx)
+        return self._per_site(vals, x0, nx)
 
     def positions(self, x0=0, nx=None):
         """cartesian site positions in lattice constants (core/lattice.cc:751-756)"""
@@ -276,11 +343,11 @@ class Lattice:
         n = nx * self.dims[1] * self.dims[2] * self.M
         if seed is None:
             per = []
-            for t in self.motif_material:
-                s = np.asarray(self.materials[t].spin, dtype=np.float64)
+            for mat in self.materials:
+                s = np.asarray(mat.spin, dtype=np.float64)
                 nrm = np.sqrt(s @ s)
                 per.append(s / nrm if nrm > np.finfo(float).eps else s)
-            return self._tile(per, x0, nx)
+            return np.ascontiguousarray(self._per_site(per, x0, nx))
         # decomposition-independent: generate the whole lattice stream and slice (test / bench inputs only)
         rng = np.random.default_rng(seed)
         v = rng.standard_normal((self.num_spins, 3))
@@ -462,6 +529,8 @@ class Lattice:
         ii, jj, kk = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
         ii, jj, kk = ii.reshape(-1), jj.reshape(-1), kk.reshape(-1)
         all_i, all_j, all_v = [], [], []
+        smat = self._site_materials() if self.impurity_map else None
+        raw_i, raw_j = [], []   # with impurities: all pairs before the material check (the reference looks for duplicates first)
         n_t = len(template["mi"])
         first_pos = np.full(n_t, -1, np.int64)   # position of each entry's first insertion in generation order
         for n in range(n_t):
@@ -473,6 +542,11 @@ class Lattice:
                 d[l] = (d[l] + size) % size
             local = ((ii * ny + jj) * nz + kk) * M + int(template["mi"][n])
             nbr = ((d[0] * ny + d[1]) * nz + d[2]) * M + int(template["mj"][n])
+            if smat is not None:
+                # "catch if the site has a different material (presumably an impurity site)" (core/interactions.cc:381-385): the
+                # entry's types are those of its motif positions
+                raw_i.append(local[ok]); raw_j.append(nbr[ok])
+                ok = ok & (smat[local] == self.motif_material[int(template["mi"][n])]) & (smat[nbr] == self.motif_material[int(template["mj"][n])])
             all_i.append(local[ok]); all_j.append(nbr[ok])
             all_v.append(np.full(int(ok.sum()), n, np.int64))
             if ok.any():
@@ -490,6 +564,14 @@ class Lattice:
         vid_of_entry = np.array([value_of.get(tuple(template["J9"][n]), -1) for n in range(n_t)], np.int32)
         order = np.lexsort((Jn, I))
         I, Jn, V = I[order], Jn[order], vid_of_entry[E[order]]
+        if smat is not None and raw_i:
+            Ri, Rj = np.concatenate(raw_i), np.concatenate(raw_j)
+            ro = np.lexsort((Rj, Ri))
+            Ri, Rj = Ri[ro], Rj[ro]
+            rdup = (Ri[1:] == Ri[:-1]) & (Rj[1:] == Rj[:-1])
+            if rdup.any():
+                p = int(np.nonzero(rdup)[0][0])
+                raise RuntimeError(f"Multiple interactions for sites {int(Ri[p])} and {int(Rj[p])}")
         dup = (I[1:] == I[:-1]) & (Jn[1:] == Jn[:-1])
         if dup.any():
             p = int(np.nonzero(dup)[0][0])

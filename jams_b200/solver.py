@@ -86,7 +86,7 @@ class ExchangeHamiltonian(Hamiltonian):
             coordinate_format=s.get("coordinate_format", "cartesian"), use_symops=s.get("symops", True),
             energy_cutoff=s.get("energy_cutoff", 0.0), radius_cutoff=s.get("radius_cutoff", 100.0),
             distance_tolerance=s.get("distance_tolerance", 1e-4), interaction_prefactor=s.get("interaction_prefactor", 1.0))
-        self.use_pairs = bool(s.get("use_neighbour_list", False))
+        self.use_pairs = bool(s.get("use_neighbour_list", False)) or lattice.has_impurities   # impurities break translation invariance
         self._nbr = None
 
     def neighbour_list(self):
@@ -304,6 +304,7 @@ class UniaxialAnisotropyHamiltonian(Hamiltonian):
         M = lattice.M
         self.motif_K = np.zeros(M)
         self.motif_axis = np.zeros((M, 3))
+        self.by_material = {}   # material index -> (K, axis): what a site with that material gets when the lattice has impurities
         for who, axis, energy in s["anisotropies"]:
             axis = np.asarray(axis, dtype=np.float64)
             axis = axis / np.sqrt(axis @ axis)  # normalize(), uniaxial_anisotropy.cc:65
@@ -319,9 +320,22 @@ class UniaxialAnisotropyHamiltonian(Hamiltonian):
                 if hit:
                     self.motif_K[m] = energy * self.input_energy_unit_conversion
                     self.motif_axis[m] = axis
+            if not isinstance(who, (int, np.integer)):
+                self.by_material[lattice.material_index[who]] = (energy * self.input_energy_unit_conversion, axis)
 
     def site_arrays(self, x0=0, nx=None):
-        return self.lattice._tile(self.motif_K, x0, nx), self.lattice._tile(self.motif_axis, x0, nx)
+        lat = self.lattice
+        K, axis = lat._tile(self.motif_K, x0, nx), lat._tile(self.motif_axis, x0, nx)
+        if lat.has_impurities:   # by material name: the site's own material decides (uniaxial_anisotropy.cc:89-114)
+            K, axis = np.array(K), np.array(axis)
+            mat = lat.site_material(x0, nx)
+            motif_mat = lat._tile(lat.motif_material, x0, nx)
+            changed = mat != motif_mat
+            K[changed] = 0.0; axis[changed] = 0.0
+            for m_idx, (k, a) in self.by_material.items():
+                sel = changed & (mat == m_idx)
+                K[sel] = k; axis[sel] = a
+        return K, axis
 
     def attach(self, ctx, x0, nx):
         K, axis = self.site_arrays(x0, nx)

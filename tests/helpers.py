@@ -28,7 +28,12 @@ def ref_site_tables(lat):
     """per-site (material id, motif position) in the reference's site order ((i Ny + j) Nz + k) M + m (core/lattice.cc:622-657)"""
     cells = int(lat.dims[0]) * int(lat.dims[1]) * int(lat.dims[2])
     M = len(lat.motif_material)
-    return np.tile(np.asarray(lat.motif_material, dtype=np.int64), cells), np.tile(np.arange(M, dtype=np.int64), cells)
+    mat = np.tile(np.asarray(lat.motif_material, dtype=np.int64), cells)
+    if getattr(lat, "has_impurities", False):
+        # lattice.impurities: which sites were substituted is a random draw (pcg32 stream, unpinned); the checker takes the realised
+        # site materials as an input, like the normals of a thermal run, and derives everything else from the raw settings
+        mat = np.asarray(lat.site_material(), dtype=np.int64)
+    return mat, np.tile(np.arange(M, dtype=np.int64), cells)
 
 
 def ref_material_arrays(lat):

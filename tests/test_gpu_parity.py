@@ -748,6 +748,48 @@ def test_biquadratic_exchange_fields_energies_and_trajectory_match_oracle(solver
         assert np.abs(s.spins() - sim2.get_spins()).max() <= TRAJ_TOL
 
 
+def test_lattice_impurities_random_alloy_matches_oracle():
+    """lattice.impurities (core/lattice.cc:614-640): 30 % of the Fe sites of a bcc lattice become Co.  The neighbour list is no longer
+    translation invariant (pairs with a substituted end are dropped, core/interactions.cc:381-385): general neighbour-list kernel with
+    per-site classes (moment, damping, anisotropy and Zeeman field by the site's own material).  Fields and energies per term, a T = 0
+    trajectory and a same-noise T > 0 trajectory against the oracle, which gets the realised site materials as an input."""
+    from jams_b200.solver import create_solver
+    mats = [Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05)]
+    lat = Lattice(mats, np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (8, 7, 9), periodic=(True, True, False),
+                  impurities=[("Fe", "Co", 0.3)], impurities_seed=5)
+    hams = [dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 1.6e-21)]),
+            dict(module="uniaxial", order="K1", anisotropies=[("Fe", [0.0, 0.0, 1.0], 1e-23), ("Co", [1.0, 0.0, 0.0], 4e-23)]),
+            dict(module="zeeman", dc_local_field=[[0.0, 0.0, 1.0], [0.0, 0.5, 0.0]])]
+    w = dict(name="alloy", lattice=lat, hamiltonians=hams, spins=None, temperature=0.0)
+    assert 0.2 < (lat.site_material() == 1).mean() < 0.4
+    s0 = random_unit_spins(lat.num_spins, 41)
+    sim = build_cpu_sim(w)
+    sim.set_spins(s0)
+    s = create_solver(dict(module="llg-heun-b200-gpu", t_step=1e-16, t_max=1e-9, seed=9), lat)
+    for h in hams:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    s.set_spins(s0)
+    for h in s.hamiltonians:
+        key = h.settings["module"].lower()
+        ref_f = sim.term_fields(sim.terms[key], 0.0)
+        assert np.abs(h.calculate_fields(0.0) - ref_f).max() <= 1e-13 * np.abs(ref_f).max(), key
+        assert abs(h.calculate_total_energy(0.0) - sim.term_total_energy(sim.terms[key], 0.0)) <= 1e-12 * abs(sim.term_total_energy(sim.terms[key], 0.0)), key
+    sim.run(25)
+    s.run(25)
+    assert s.ctx.stage_kernel() == 5   # general neighbour list
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+    T, seed = 80.0, 9
+    s.set_temperature(T)
+    s.set_spins(s0)
+    it0 = s.iteration
+    normals = np.stack([s.ctx.noise(s.step_size, T, seed, it0 + n, normals_only=True) for n in range(10)])
+    sim2 = build_cpu_sim(dict(w, temperature=T))
+    sim2.set_spins(s0)
+    sim2.run(10, normals)
+    s.run(10)
+    assert np.abs(s.spins() - sim2.get_spins()).max() <= TRAJ_TOL
+
+
 def test_exchange_symmetry_guard_mirrors_the_reference():
     """SparseInteractionHamiltonian::finalize throws "sparse matrix for exchange is not symmetric" (hamiltonian/sparse_interaction.cc:114-118,
     containers/sparse_matrix_builder.h:320-362) unless check_sparse_matrix_symmetry = false (hamiltonian/exchange.cc:104-110)"""

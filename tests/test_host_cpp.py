@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from jams_b200 import host, workloads as W
+from jams_b200.lattice import Lattice, Material
 from jams_b200.solver import create_hamiltonian
 
 FIXTURE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "bloch_wall_small.cfg")
@@ -88,6 +89,32 @@ def test_two_material_bcc_template_with_cutoffs_and_tensors():
     assert np.array_equal(la["mus"], lat.mus()) and np.array_equal(la["gyro"], lat.gyro()) and np.array_equal(la["alpha"], lat.alpha())
     assert np.allclose(la["spins"], lat.initial_spins(), rtol=0, atol=1e-16)   # spherical-angle spin setting
     assert np.array_equal(la["positions"], lat.positions())
+
+
+def test_lattice_impurities_cpp_equals_python(tmp_path):
+    """lattice.impurities (core/lattice.cc:424-427,614-640): both host layers restate pcg32 + generate_canonical, so the same seed
+    substitutes the same sites; the neighbour list drops the pairs that touch a substituted site (core/interactions.cc:381-385)"""
+    cfg = BCC_CFG.replace('("Co", [0.5,0.5,0.5])', '("Fe", [0.5,0.5,0.5])').replace(
+        'lattice : { size = [6, 5, 4];', 'lattice : { impurities = ( ("Fe", "Co", 0.35) ); impurities_seed = 21; size = [6, 5, 4];')
+    path = tmp_path / "alloy.cfg"
+    open(path, "w").write(cfg)
+    la = host.lattice_arrays(str(path))
+    mats = [Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05, gyro=1.1, spin=(1.0, 0.0, 0.0))]
+    lat = Lattice(mats, np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 4), periodic=(True, True, False), gilbert_prefactor=True,
+                  impurities=[("Fe", "Co", 0.35)], impurities_seed=21)
+    assert 0.25 < (lat.site_material() == 1).mean() < 0.45
+    assert np.array_equal(la["mus"], lat.mus()) and np.array_equal(la["alpha"], lat.alpha()) and np.array_equal(la["gyro"], lat.gyro())
+    assert np.abs(la["spins"] - lat.initial_spins()).max() <= 1e-15
+    hs = dict(module="exchange", energy_units="meV", energy_cutoff=0.5,
+              interactions=[("Fe", "Co", [0.5, 0.5, 0.5], [20.0, 0, 0, 0, 20.0, 0, 0, 0, 20.0]), ("Co", "Fe", [0.5, 0.5, 0.5], [20.0, 0, 0, 0, 20.0, 0, 0, 0, 20.0]),
+                            ("Fe", "Fe", [1.0, 0, 0], [10.0, 0, 0, 0, 10.0, 0, 0, 0, 10.0]), ("Co", "Co", [1.0, 0, 0], [8.0, 0.1, 0, -0.1, 8.0, 0, 0, 0, 7.5]),
+                            ("Fe", "Fe", [1.0, 1.0, 0], [0.4, 0, 0, 0, 0.4, 0, 0, 0, 0.4])])
+    h = create_hamiltonian(hs, lat)
+    t = host.exchange_template(str(path), ham_index=0)
+    for x, y in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    n_py = len(h.neighbour_list()[0])
+    assert t["n_pairs"] == n_py and 0 < n_py < lat.num_spins * 6
 
 
 def test_known_neighbour_count_sc_8_cubed():

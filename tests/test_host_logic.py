@@ -320,3 +320,52 @@ def test_biquadratic_template_keeps_only_couplings_above_the_cutoff_and_matches_
     assert got == want and len(got) == lat.num_spins * 14
     hs_cut = dict(hs, energy_cutoff=0.3)
     assert len(create_hamiltonian(hs_cut, lat).template["B"]) == 2 * 8
+
+
+def test_pcg32_known_answer_and_impurity_substitution():
+    """lattice.impurities (core/lattice.cc:424-427,614-640,1077-1109): pcg32 restated from its published definition (the demo
+    vector of pcg32(42, stream 54) is the known answer), one uniform draw per candidate site in site order"""
+    from jams_b200.lattice import Pcg32
+
+    class Demo(Pcg32):
+        INC = (54 << 1) | 1
+    r = Demo(42)
+    assert [r() for _ in range(6)] == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+    mats = [Material("A", 2.0), Material("B", 1.0, alpha=0.2), Material("C", 3.0)]
+    motif = [("A", (0, 0, 0)), ("C", (0.5, 0.5, 0.5))]
+    lat = Lattice(mats, np.eye(3), motif, (12, 10, 8), impurities=[("A", "B", 0.25)], impurities_seed=11)
+    mat = lat.site_material()
+    assert set(mat[1::2]) == {2}                                  # C sites are not candidates
+    frac = (mat[0::2] == 1).mean()
+    assert abs(frac - 0.25) < 0.04 and set(mat[0::2]) == {0, 1}
+    assert np.array_equal(mat, Lattice(mats, np.eye(3), motif, (12, 10, 8), impurities=[("A", "B", 0.25)], impurities_seed=11).site_material())
+    assert not np.array_equal(mat, Lattice(mats, np.eye(3), motif, (12, 10, 8), impurities=[("A", "B", 0.25)], impurities_seed=12).site_material())
+    # the draws in site order: site q of the A sublattice is substituted iff the q-th uniform number is below the fraction
+    rng = Pcg32(11)
+    want = np.array([1 if rng.uniform_real() < 0.25 else 0 for _ in range(mat.size // 2)])
+    assert np.array_equal(mat[0::2], want)
+    from jams_b200.consts import kBohrMagnetonIU
+    assert np.array_equal(lat.mus(), np.array([m.moment * kBohrMagnetonIU for m in mats])[mat])
+    x0, nx = 3, 4
+    per_plane = 10 * 8 * 2
+    assert np.array_equal(lat.site_material(x0, nx), mat[x0 * per_plane:(x0 + nx) * per_plane])
+    for bad, msg in (([("Z", "B", 0.1)], "materialA"), ([("A", "Z", 0.1)], "materialB"), ([("A", "B", 1.0)], "fraction"),
+                     ([("A", "B", 0.1), ("A", "C", 0.1)], "redefines")):
+        with pytest.raises(RuntimeError, match=msg):
+            Lattice(mats, np.eye(3), motif, (4, 4, 4), impurities=bad)
+
+
+def test_neighbour_list_with_impurities_bit_exact_with_oracle():
+    """neighbour_list_from_interactions skips pairs whose site materials differ from the entry's types
+    (core/interactions.cc:381-385): the product's list against the oracle's, given the same site materials"""
+    mats = [Material("Fe", 2.2), Material("Co", 1.7)]
+    lat = Lattice(mats, np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 4), periodic=(True, True, False),
+                  impurities=[("Fe", "Co", 0.3)], impurities_seed=3)
+    hs = dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 1.6e-21)])
+    h = create_hamiltonian(hs, lat)
+    assert h.use_pairs
+    i, j, v, vals = h.neighbour_list()
+    oi, oj, oJ9, _ = oracle_exchange_pairs(lat, hs)
+    assert np.array_equal(i, oi) and np.array_equal(j, oj) and np.array_equal(vals[v], oJ9)
+    mat = lat.site_material()
+    assert (mat[i] == 0).all() and (mat[j] == 0).all() and 0 < len(i) < lat.num_spins * 14
