@@ -669,6 +669,7 @@ double Lattice::max_interaction_radius() const {
 }
 
 ExchangeFunctionalHamiltonian::ExchangeFunctionalHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  if (lattice.has_impurities) throw std::runtime_error("exchange-functional is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer");   // the template form assumes translation invariance
   const double tol = kLatticeTolerance, E = input_energy_unit_conversion_;
   const std::string dunit = s.get("distance_units", "lattice_constants");   // core/hamiltonian.cc:140-155
   double D = 1.0;
@@ -768,6 +769,7 @@ ExchangeFunctionalHamiltonian::ExchangeFunctionalHamiltonian(const Setting &s, c
 
 // ---- exchange-neartree (hamiltonian/exchange_neartree.cc:14-156) ----------------------------------------------------
 ExchangeNeartreeHamiltonian::ExchangeNeartreeHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  if (lattice.has_impurities) throw std::runtime_error("exchange-neartree is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer");   // the template form assumes translation invariance
   const double E = input_energy_unit_conversion_;
   const std::string dunit = s.get("distance_units", "lattice_constants");
   double D = 1.0;

@@ -152,6 +152,8 @@ class ExchangeFunctionalHamiltonian(ExchangeHamiltonian):
 
     def __init__(self, settings: dict, lattice: Lattice, lattice_parameter: float | None = None):
         Hamiltonian.__init__(self, settings, lattice)
+        if lattice.has_impurities:   # the template form below assumes a translation-invariant lattice
+            raise RuntimeError(self.name + " is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer")
         s = self.settings
         dunit = s.get("distance_units", "lattice_constants")
         a = lattice_parameter if lattice_parameter is not None else s.get("lattice_parameter", getattr(lattice, "parameter", None))
@@ -255,6 +257,8 @@ class ExchangeNeartreeHamiltonian(ExchangeHamiltonian):
 
     def __init__(self, settings: dict, lattice: Lattice, lattice_parameter: float | None = None):
         Hamiltonian.__init__(self, settings, lattice)
+        if lattice.has_impurities:   # the template form below assumes a translation-invariant lattice
+            raise RuntimeError(self.name + " is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer")
         s = self.settings
         dunit = s.get("distance_units", "lattice_constants")
         a = lattice_parameter if lattice_parameter is not None else s.get("lattice_parameter", getattr(lattice, "parameter", None))
