@@ -1311,6 +1311,7 @@ void ExchangeHamiltonian::attach(jb_ctx *ctx) {
 // hamiltonian/cuda_biquadratic_exchange.cu:9-156: the exchange grammar, scalar B = J[0][0] * unit (no interaction_prefactor), only
 // values above energy_cutoff are inserted (:131)
 BiquadraticExchangeHamiltonian::BiquadraticExchangeHamiltonian(const Setting &s, const Lattice &lattice) : ExchangeHamiltonian(s, lattice, NoParse{}) {
+  if (lattice.has_impurities) throw std::runtime_error("biquadratic-exchange is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer");   // template form only
   parse_interactions(s, lattice, 1.0);
   const double cutoff = s.get("energy_cutoff", 0.0) * input_energy_unit_conversion_;
   InteractionTemplate kept;

@@ -116,6 +116,8 @@ class BiquadraticExchangeHamiltonian(Hamiltonian):
 
     def __init__(self, settings: dict, lattice: Lattice):
         super().__init__(settings, lattice)
+        if lattice.has_impurities:   # the library takes this term as a translation-invariant template only
+            raise RuntimeError(self.name + " is not supported on a lattice with impurities by the llg-heun-b200-gpu host layer")
         s = self.settings
         if "exc_file" in s:
             from .lattice import read_interaction_file
