@@ -110,8 +110,9 @@ JB_API int jb_set_biquadratic_template(jb_ctx *ctx, int32_t n, const int32_t *mo
  * containers/interaction_list.h:45-47): pairs (i,j) in GLOBAL site ids with an index into the table
  * of unique tensors (row-major 3x3, meV, already scaled).  Only pairs whose i lies in this
  * context's slab are used.  A translation-invariant list (jb_detect_exchange_template) is turned into the
- * template form and runs on the TMA tile kernel, on any number of ranks; anything else is kept as an ELL table
- * (explicit int32 indices), single-rank only in this version. */
+ * template form and runs on the TMA kernels; anything else (impurities, vacancies) is kept as an ELL table (explicit int32
+ * indices).  On a slab-decomposed lattice every rank passes the SAME global list: neighbours across a slab face are addressed
+ * through the x ghost planes, whose depth is the largest x distance of any pair of the list. */
 JB_API int jb_set_exchange_pairs(jb_ctx *ctx, int64_t n_pairs, const int32_t *i, const int32_t *j,
                           const int32_t *value_id, int32_t n_values, const double *J9);
 

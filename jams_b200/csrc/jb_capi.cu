@@ -890,6 +890,7 @@ int ensure_ready(jb_ctx *c) {
       gx = std::max(gx, std::abs(c->t_T[3 * k])); gy = std::max(gy, std::abs(c->t_T[3 * k + 1])); gz = std::max(gz, std::abs(c->t_T[3 * k + 2]));
     }
   }
+  gx = std::max(gx, c->pairs_reach_x);   // general neighbour list on several ranks (jb_set_exchange_pairs)
   if (c->has_bq) {
     for (size_t k = 0; k < c->bq_mi.size(); ++k) {
       gx = std::max(gx, std::abs(c->bq_T[3 * k])); gy = std::max(gy, std::abs(c->bq_T[3 * k + 1])); gz = std::max(gz, std::abs(c->bq_T[3 * k + 2]));
@@ -1025,6 +1026,7 @@ int jb_set_materials(jb_ctx *c, const double *mus, const double *gyro, const dou
 }
 
 int jb_set_exchange_template(jb_ctx *c, int32_t n, const int32_t *mi, const int32_t *mj, const int32_t *T3, const double *J9) {
+  if (c) c->pairs_reach_x = 0;
   if (!c || n < 0 || (n > 0 && (!mi || !mj || !T3 || !J9))) return JB_ERR_INVALID;
   for (int k = 0; k < n; ++k) {
     if (mi[k] < 0 || mi[k] >= c->d.num_motif || mj[k] < 0 || mj[k] >= c->d.num_motif) JB_FAIL(c, JB_ERR_INVALID, "motif index out of range in exchange template");
@@ -1153,7 +1155,7 @@ int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const i
     if (rc == JB_ERR_INVALID) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
     if (nt > 0) return jb_set_exchange_template(c, nt, mi.data(), mj.data(), T3.data(), J9t.data());
   }
-  if (c->d.n_ranks != 1) JB_FAIL(c, JB_ERR_UNSUPPORTED, "jb_set_exchange_pairs is single-rank only in this version");
+  const long long n_global = (long long)c->d.dims[0] * c->d.dims[1] * c->d.dims[2] * c->d.num_motif;
   if (c->opt_check_symmetry) {
     // the same symmetry requirement on the explicit list: every (i, j, J) needs (j, i, J^T).  Sort-based, no hash of the list
     std::vector<int64_t> order(n_pairs);
@@ -1174,32 +1176,59 @@ int jb_set_exchange_pairs(jb_ctx *c, int64_t n_pairs, const int32_t *pi, const i
     }
   }
   JB_CUDA(c, cudaSetDevice(c->device));
+  // Geometry: on one rank the list needs no ghost cells (every neighbour is addressed directly, periodic wrap included).  On a
+  // slab-decomposed lattice a neighbour across a slab face is addressed through the x ghost planes, which the neighbouring rank's
+  // stage kernel fills (P2P stores) like for a template; the ghost depth is the largest x distance (minimum image) of ANY pair of
+  // the list, so that every rank lays its box out alike (they store into each other's boxes with their own geometry).
+  const int Nx = c->d.dims[0], Ny = c->d.dims[1], Nz = c->d.dims[2], M = c->d.num_motif;
+  auto decode = [&](int ref, int &x, int &y, int &z, int &m) { m = ref % M; int r = ref / M; z = r % Nz; r /= Nz; y = r % Ny; x = r / Ny; };
+  auto x_distance = [&](int xi, int xj) {   // signed, minimum image along a periodic x
+    int d = xj - xi;
+    if (c->d.periodic[0]) { if (2 * d > Nx) d -= Nx; else if (2 * d < -Nx) d += Nx; }
+    return d;
+  };
+  int reach_x = 0;
+  for (int64_t p = 0; p < n_pairs; ++p) {
+    if (pi[p] < 0 || pi[p] >= n_global || pj[p] < 0 || pj[p] >= n_global || vid[p] < 0 || vid[p] >= n_values) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
+    if (c->d.n_ranks > 1) {
+      int xi, yi, zi, mi, xj, yj, zj, mj;
+      decode(pi[p], xi, yi, zi, mi); decode(pj[p], xj, yj, zj, mj);
+      reach_x = std::max(reach_x, std::abs(x_distance(xi, xj)));
+    }
+  }
+  if (c->d.n_ranks > 1 && reach_x > c->d.nx_local) JB_FAIL(c, JB_ERR_INVALID, "slab thinner than the x range of the neighbour list");
   c->has_template = false; c->t_mi.clear(); c->t_mj.clear(); c->t_T.clear(); c->t_J9.clear();
   c->has_pairs = false;
-  int rc = ensure_ready(c);  // geometry without ghosts
+  c->pairs_reach_x = reach_x;
+  int rc = ensure_ready(c);  // geometry: no y / z ghosts, x ghosts only on several ranks
   if (rc) return rc;
   const JbGeom &g = c->g;
   const int N = c->N;
+  const int x0 = c->d.x_begin, nx = c->d.nx_local;
   std::vector<int> count(N, 0);
-  for (int64_t p = 0; p < n_pairs; ++p) {
-    if (pi[p] < 0 || pi[p] >= N || pj[p] < 0 || pj[p] >= N || vid[p] < 0 || vid[p] >= n_values) JB_FAIL(c, JB_ERR_INVALID, "pair index out of range");
-    count[pi[p]]++;
-  }
+  auto local_ref = [&](int ref) -> long long {   // global reference id -> local reference id, or -1 outside this slab
+    int x, y, z, m; decode(ref, x, y, z, m);
+    if (x < x0 || x >= x0 + nx) return -1;
+    return ((((long long)(x - x0) * Ny + y) * Nz + z) * M + m);
+  };
+  for (int64_t p = 0; p < n_pairs; ++p) { const long long li = local_ref(pi[p]); if (li >= 0) count[li]++; }
   int width = 0;
   for (int i = 0; i < N; ++i) width = std::max(width, count[i]);
-  auto layout_q = [&](int ref) {  // reference site id -> interior layout order q and ghosted index
-    const int m = ref % g.M; int r = ref / g.M; const int z = r % g.Nz; r /= g.Nz; const int y = r % g.Ny; const int x = r / g.Ny;
-    const long long q = (((long long)x * g.Ny + y) * g.M + m) * g.Nz + z;
-    const long long gi = ((long long)(x + g.gx) * g.PY + (y + g.gy)) * g.sY + (long long)m * g.PZ + (z + g.oz);
-    return std::make_pair(q, gi);
-  };
   std::vector<int> idx((size_t)width * N, -1), val((size_t)width * N, 0), fill(N, 0);
   for (int64_t p = 0; p < n_pairs; ++p) {  // pairs arrive sorted by {i,j}: ascending-j order is kept per row
-    const auto qi = layout_q(pi[p]);
-    const auto qj = layout_q(pj[p]);
-    const int e = fill[pi[p]]++;
-    idx[(size_t)e * N + qi.first] = (int)qj.second;
-    val[(size_t)e * N + qi.first] = vid[p];
+    const long long li = local_ref(pi[p]);
+    if (li < 0) continue;
+    int xi, yi, zi, mi, xj, yj, zj, mj;
+    decode(pi[p], xi, yi, zi, mi); decode(pj[p], xj, yj, zj, mj);
+    const long long q = (((long long)(xi - x0) * g.Ny + yi) * g.M + mi) * g.Nz + zi;   // interior layout order of the row
+    // neighbour: inside the slab by its own cell, across a face by the ghost plane at its x distance from the row's cell
+    int xl = xj - x0;
+    if (c->d.n_ranks > 1 && (xj < x0 || xj >= x0 + nx)) xl = (xi - x0) + x_distance(xi, xj);
+    if (xl < -g.gx || xl >= nx + g.gx) JB_FAIL(c, JB_ERR_INVALID, "neighbour list reaches beyond the x ghost planes");
+    const long long gj = ((long long)(xl + g.gx) * g.PY + (yj + g.gy)) * g.sY + (long long)mj * g.PZ + (zj + g.oz);
+    const int e = fill[li]++;
+    idx[(size_t)e * N + q] = (int)gj;
+    val[(size_t)e * N + q] = vid[p];
   }
   bool iso = true;
   for (int v = 0; v < n_values; ++v) {

@@ -216,6 +216,7 @@ struct jb_ctx {
   int bq_begin[JB_MAX_MOTIF + 1] = {0};
   // exchange pairs (host -> device ELL), general path
   bool has_pairs = false;
+  int pairs_reach_x = 0;          // several ranks: largest x distance of a pair = depth of the x ghost planes the list addresses
   int ell_width = 0;
   int *d_ell_idx = nullptr;       // width x N (column-major: entry e of site q at e*N + q), ghosted index or -1
   int *d_ell_val = nullptr;       // value ids

@@ -339,7 +339,9 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
   llg_site<STAGE, THERMAL>(c, sx, sy, sz, fma(hx, c.inv_mu, c.fTx), fma(hy, c.inv_mu, c.fTy), fma(hz, c.inv_mu, c.fTz), n0, n1, n2,
                            ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
-  p.out[0][ic] = ox; p.out[1][ic] = oy; p.out[2][ic] = oz;
+  // one rank: no ghost cells at all (gx = gy = gz = 0: every neighbour is addressed directly); several ranks: the x images of the
+  // face planes go into the neighbours' boxes
+  store_with_images(p, x, y, m, z, ox, oy, oz);
 }
 
 // =================================================================================================

@@ -54,6 +54,17 @@ def pinned_boundaries_case(rank, world, local):
     return ok
 
 
+def alloy(world, temperature):
+    """lattice.impurities: 30 % Co on the Fe sites of a bcc lattice -- not translation invariant, so the exchange travels as the
+    general neighbour list (GLOBAL site ids on every rank, neighbours across a slab face addressed through the x ghost planes)"""
+    from jams_b200.lattice import Lattice, Material
+    lat = Lattice([Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))],
+                  (6 * world, 7, 9), impurities=[("Fe", "Co", 0.3)], impurities_seed=5)
+    hams = [dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 1.6e-21)]),
+            dict(module="uniaxial", order="K1", anisotropies=[("Fe", [0.0, 0.0, 1.0], 1e-23), ("Co", [1.0, 0.0, 0.0], 4e-23)])]
+    return dict(name="alloy", lattice=lat, hamiltonians=hams, spins=None, temperature=temperature)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -67,6 +78,7 @@ def main():
                                                    ("sc periodic T=0", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=0.0), True, 0.0, 15, None),
                                                    ("sc periodic T=30 stored u", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(recover_u=0)),
                                                    ("sc periodic T=30 separate wait/signal launches", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(fold_halo=0)),
+                                                   ("bcc random alloy (lattice.impurities), general neighbour list, T=40", lambda: alloy(world, 40.0), True, 40.0, 12, None),
                                                    ("sc 64/rank x 96 x 256 periodic T=80, many items", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, None),
                                                    ("sc 64/rank x 96 x 256 periodic T=80, short chunks", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, dict(chunk_long=6, chunk_short=2, tail_pct=50))):
         w = make()

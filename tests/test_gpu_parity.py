@@ -236,7 +236,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4", "rk4_fold", "rk4_direct"])
+@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4", "rk4_fold", "rk4_direct", "pairs"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -246,6 +246,7 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
     hs = dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21), ("Fe", "Fe", [1.0, 0.0, 0.0], 1.6e-21)])
     h = create_hamiltonian(hs, lat)
     t = h.template
+    nbr = h.neighbour_list() if kernel == "pairs" else None
     s0 = lat.initial_spins(seed=17)
     dt, T, seed, steps = 1e-4, 50.0, 99, 12
 
@@ -262,7 +263,11 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
             # works because these lattices leave most of the SMs free for the neighbour's kernel
             c.set_option("fold_halo", 2 if kernel.endswith("fold") else 0)
         c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
-        c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
+        if kernel == "pairs":   # the general neighbour list, GLOBAL site ids on every rank: neighbours across a slab face sit in the x ghost planes
+            c.set_option("detect_template", 0)
+            c.set_exchange_pairs(*nbr)
+        else:
+            c.set_exchange_template(t["mi"], t["mj"], t["T"], t["J9"])
         return c
 
     step = (lambda c, *a: c.step_rk4(*a)) if kernel.startswith("rk4") else (lambda c, *a: c.step(*a))   # RK4: four exchanges per step
