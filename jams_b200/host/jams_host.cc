@@ -43,6 +43,9 @@ Vec3 matvec(const Mat3 &A, const Vec3 &v) {
   return {{A[0][0] * v[0] + A[0][1] * v[1] + A[0][2] * v[2], A[1][0] * v[0] + A[1][1] * v[1] + A[1][2] * v[2],
            A[2][0] * v[0] + A[2][1] * v[1] + A[2][2] * v[2]}};
 }
+double determinant(const Mat3 &A) {
+  return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) + A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+}
 Mat3 matmul(const Mat3 &A, const Mat3 &B) {
   Mat3 C{};
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
@@ -245,7 +248,29 @@ Lattice::Lattice(const Setting &config) {
   if (const Setting *sf = lat.find("spins")) spins_file = sf->as_string();
   const Setting *impurity_settings = lat.find("impurities");
   impurities_seed = static_cast<uint64_t>(lat.get("impurities_seed", 0));   // the reference draws a seed from its global generator if absent
-  if (lat.exists("global_rotation") || lat.exists("orientation_axis")) throw std::runtime_error("lattice rotations are not supported by the llg-heun-b200-gpu host layer");
+  {   // "Rotating the system" (core/lattice.cc:434-454,515-575): orientation first, then global_rotation; a_k <- R a_k
+    auto rotate_cell = [&](const Mat3 &R) {
+      const double before = std::abs(determinant(cell));
+      cell = matmul(R, cell);   // columns are a, b, c (containers/cell.cc:62-68)
+      if (std::abs(std::abs(determinant(cell)) - before) > std::max(before, 1.0) * kLatticeTolerance * kLatticeTolerance * kLatticeTolerance)
+        throw std::runtime_error("unitcell volume has changed after rotation");
+      cell_inv = inverse(cell);
+    };
+    if (const Setting *axis = lat.find("orientation_axis")) {
+      const Setting *lv = lat.find("orientation_lattice_vector"), *cv = lat.find("orientation_cartesian_vector");
+      if (lv && cv) throw std::runtime_error("Only one of 'orientation_lattice_vector' or 'orientation_cartesian_vector' can be defined");
+      if (lv || cv) {
+        const Vec3 vec = lv ? read_vec3(*lv) : matvec(cell_inv, read_vec3(*cv));
+        const Vec3 cart = unit_vector(matvec(cell, vec));
+        rotate_cell(rotation_matrix_between_vectors(cart, read_vec3(*axis)));
+      }
+    }
+    if (const Setting *gr = lat.find("global_rotation")) {
+      Mat3 R;
+      for (int r = 0; r < 3; ++r) { const Vec3 row = read_vec3((*gr)[r]); for (int c2 = 0; c2 < 3; ++c2) R[r][c2] = row[c2]; }
+      rotate_cell(R);
+    }
+  }
 
   // motif (core/lattice.cc:286-310, 429-470)
   const std::string fmt_name = uc.get("coordinate_format", "FRACTIONAL");

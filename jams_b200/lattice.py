@@ -226,9 +226,29 @@ class Lattice:
     symops: tuple | None = None       # (rotations (n,3,3) fractional, translations (n,3)); None = found from the cell and motif
     impurities: list | None = None    # lattice.impurities: [(materialA, materialB, fraction), ...] (core/lattice.cc:424-427,1077-1109)
     impurities_seed: int = 0          # lattice.impurities_seed (the reference draws one from its global generator if absent)
+    # "Rotating the system" (core/lattice.cc:434-454,515-575): orientation first (the lattice vector / cartesian vector is turned onto
+    # orientation_axis), then global_rotation; both rotate the unit-cell vectors, a_k <- R a_k
+    orientation_axis: tuple | None = None
+    orientation_lattice_vector: tuple | None = None
+    orientation_cartesian_vector: tuple | None = None
+    global_rotation: np.ndarray | None = None
 
     def __post_init__(self):
         self.cell = np.asarray(self.cell, dtype=np.float64).reshape(3, 3)
+        if self.orientation_axis is not None:
+            if self.orientation_lattice_vector is not None and self.orientation_cartesian_vector is not None:
+                raise RuntimeError("Only one of 'orientation_lattice_vector' or 'orientation_cartesian_vector' can be defined")
+            vec = None
+            if self.orientation_lattice_vector is not None:
+                vec = np.asarray(self.orientation_lattice_vector, dtype=np.float64)
+            elif self.orientation_cartesian_vector is not None:
+                vec = np.linalg.inv(self.cell) @ np.asarray(self.orientation_cartesian_vector, dtype=np.float64)
+            if vec is not None:   # global_reorientation (:535-575)
+                cart = self.cell @ vec
+                cart = cart / np.sqrt(cart @ cart)
+                self._rotate_cell(rotation_matrix_between_vectors(cart, np.asarray(self.orientation_axis, dtype=np.float64)))
+        if self.global_rotation is not None:   # global_rotation (:515-533)
+            self._rotate_cell(np.asarray(self.global_rotation, dtype=np.float64).reshape(3, 3))
         self.cell_inv = np.linalg.inv(self.cell)
         self.material_index = {m.name: i for i, m in enumerate(self.materials)}
         self.motif_material = np.array([self.material_index[name] for name, _ in self.motif], dtype=np.int32)
@@ -250,6 +270,12 @@ class Lattice:
                 raise RuntimeError(f"impurity {n} redefines a previous impurity")
             self.impurity_map[self.material_index[a]] = (self.material_index[b], float(fraction))
         self._site_material_all = None
+
+    def _rotate_cell(self, R):
+        before = abs(np.linalg.det(self.cell))
+        self.cell = R @ self.cell          # columns are a, b, c: a_k <- R a_k (containers/cell.cc:62-68)
+        if abs(abs(np.linalg.det(self.cell)) - before) > max(before, 1.0) * LATTICE_TOLERANCE ** 3:
+            raise RuntimeError("unitcell volume has changed after rotation")
 
     # -- sizes
     @property

@@ -117,6 +117,39 @@ def test_lattice_impurities_cpp_equals_python(tmp_path):
     assert t["n_pairs"] == n_py and 0 < n_py < lat.num_spins * 6
 
 
+def test_lattice_rotations_cpp_equals_python(tmp_path):
+    """lattice.orientation_axis / orientation_lattice_vector and lattice.global_rotation (core/lattice.cc:434-454,515-575): the unit
+    cell vectors are rotated (orientation first), positions follow; interaction vectors are Cartesian in the ROTATED frame, so the bcc
+    template of a lattice whose [111] was turned onto z and then rotated by 90 degrees about z is found with the rotated vectors"""
+    from jams_b200.lattice import rotation_matrix_between_vectors
+    Rz = [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]
+    R1 = rotation_matrix_between_vectors(np.array([1.0, 1.0, 1.0]) / np.sqrt(3.0), np.array([0.0, 0.0, 1.0]))
+    R = np.array(Rz) @ R1
+    nn = R @ np.array([0.5, 0.5, 0.5])
+    cfg = BCC_CFG.replace('("Co", [0.5,0.5,0.5])', '("Fe", [0.5,0.5,0.5])').replace(
+        'lattice : { size = [6, 5, 4];',
+        'lattice : { orientation_axis = [0.0, 0.0, 1.0]; orientation_lattice_vector = [1.0, 1.0, 1.0]; '
+        'global_rotation = ([0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]); size = [6, 5, 4];')
+    cfg = cfg[:cfg.index("hamiltonians")] + ('hamiltonians = ( { module = "exchange"; interactions = ( ("Fe", "Fe", [%.17g, %.17g, %.17g], 3.2e-21) ); } );\n' % tuple(nn)) + cfg[cfg.index("solver :"):]
+    path = tmp_path / "rot.cfg"
+    open(path, "w").write(cfg)
+    mats = [Material("Fe", 2.2, alpha=0.1), Material("Co", 1.7, alpha=0.05, gyro=1.1, spin=(1.0, 0.0, 0.0))]
+    lat = Lattice(mats, np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 4), periodic=(True, True, False), gilbert_prefactor=True,
+                  orientation_axis=(0.0, 0.0, 1.0), orientation_lattice_vector=(1.0, 1.0, 1.0), global_rotation=Rz)
+    assert np.abs(lat.cell - R).max() <= 1e-15
+    la = host.lattice_arrays(str(path))
+    assert np.abs(la["positions"] - lat.positions()).max() <= 1e-14
+    h = create_hamiltonian(dict(module="exchange", interactions=[("Fe", "Fe", list(nn), 3.2e-21)]), lat)
+    assert len(h.template["mi"]) == 16          # 8 nearest neighbours per motif site, as on the unrotated lattice
+    t = host.exchange_template(str(path), ham_index=0)
+    for x, y in zip(_sorted_template(t), _sorted_template(h.template)):
+        assert np.array_equal(x, y)
+    plain = Lattice(mats, np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 4), periodic=(True, True, False))
+    h0 = create_hamiltonian(dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21)]), plain)
+    for x, y in zip(_sorted_template(h.template), _sorted_template(h0.template)):
+        assert np.array_equal(x, y)
+
+
 def test_known_neighbour_count_sc_8_cubed():
     """sc 8^3 NN with symmetry operations -> 8*8*8*6 interactions (reference src/jams/test/interactions.h:241-252)"""
     t = host.exchange_template(FIXTURE, "lattice : { size = [8, 8, 8]; periodic = [true, true, true]; };", ham_index=1)
