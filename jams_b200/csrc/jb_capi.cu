@@ -478,6 +478,18 @@ static void choose_pair_tiling(jb_ctx *c) {
       const double interior = (double)t.TY * t.TZ / ((double)t.BY * t.BZ);
       if (interior < 0.4) return;
     }
+    // Large lattices: half the z extent -- 128 consumer threads per CTA and four CTAs per SM instead of 256 and two.  Twice as many
+    // planes in flight per SM and finer work items outweigh the shorter rows once every CTA has enough planes of work (measured,
+    // profiles/README.md r02ai: C3 256^3 4 x 128 -> 4 x 64: stage A 0.176 -> 0.169 ms, B 0.212 -> 0.210; C2 128^3 4 x 64 -> 4 x 32:
+    // +2 %; on sc 128^3, 14 planes per CTA, the smaller tile loses 2 %).
+    if (!c->opt_TY && !c->opt_TZ && !c->opt_ctas_per_sm && t.threads == 256 && t.TZ >= 64 && !(t.TZ & 3) && t.TZ < 2 * g.Nz) {
+      jb_ctx::Tiling h = t;
+      if (shape(t.TY, t.TZ / 2, h) && h.threads == 128 && std::max(h.smem[0], h.smem[1]) <= 56 * 1024) {
+        const int sms = c->num_sms > 0 ? c->num_sms : 148;
+        const long long cols = (long long)((g.Ny + h.TY - 1) / h.TY) * ((g.Nz + h.TZ - 1) / h.TZ);
+        if ((double)g.nx * cols / (4.0 * sms) >= 24.0) t = h;
+      }
+    }
   }
   t.n_yt = (g.Ny + t.TY - 1) / t.TY; t.n_zt = (g.Nz + t.TZ - 1) / t.TZ;
   t.n_cols = t.n_yt * t.n_zt;
