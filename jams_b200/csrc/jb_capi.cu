@@ -827,7 +827,7 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
 void plan_chunks(jb_ctx *c, int G, int n_cols, jb_ctx::Tiling::Shape &sh) {
   const int nx = c->g.nx, gx = c->g.gx;
   ChunkPlanOptions o;
-  o.chunks = c->opt_chunks; o.chunk_long = c->opt_chunk_long; o.chunk_short = c->opt_chunk_short; o.tail_pct = c->opt_tail_pct; o.face_after = c->opt_face_after >= 0 ? c->opt_face_after : (c->d.n_ranks > 1 ? 2 : 0);   // measured on 2 GPUs: 0 / 2 / 3 / 5 -> 97.0 / 97.6 / 97.7 / 96.0 % (profiles/README.md r02r)
+  o.chunks = c->opt_chunks; o.chunk_long = c->opt_chunk_long; o.chunk_short = c->opt_chunk_short; o.tail_pct = c->opt_tail_pct; o.face_after = c->opt_face_after >= 0 ? c->opt_face_after : (c->d.n_ranks > 1 ? (G + n_cols - 1) / std::max(1, n_cols) : 0);   // the face items follow the first wave of interior items (measured on 2 GPUs, profiles/README.md r02r, r02ak: one chunk too early or too late costs 0.5-2 %)
   sh.n_chunks = plan_chunks_core(nx, gx, n_cols, G, o, sh.x0, sh.xc);
   sh.face_items[0] = sh.face_items[1] = 0;
   for (int q = 0; q < sh.n_chunks; ++q) {
