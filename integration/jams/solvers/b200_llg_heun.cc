@@ -13,6 +13,7 @@
 #include "jams/core/physics.h"
 #include "jams/core/thermostat.h"
 #include "jams/hamiltonian/applied_field.h"
+#include "jams/hamiltonian/cuda_biquadratic_exchange.h"   // + `friend class B200HeunLLGSolver;`
 #include "jams/hamiltonian/exchange.h"
 #include "jams/hamiltonian/uniaxial_anisotropy.h"   // + `friend class B200HeunLLGSolver;`
 #include "jams/hamiltonian/zeeman.h"                // + `friend class B200HeunLLGSolver;`
@@ -47,7 +48,8 @@ void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
   seed_ = static_cast<std::uint64_t>(jams::config_optional<int>(globals::config->lookup("sim"), "seed", 0));
   register_thermostat(new PassThroughThermostat(step_size_, globals::num_spins));
 
-  jb_lattice_desc d{};
+  jb_lattice_desc &d = desc_;
+  d = jb_lattice_desc{};
   for (int n = 0; n < 3; ++n) {
     d.dims[n] = globals::lattice->size(n);
     d.periodic[n] = globals::lattice->is_periodic(n);
@@ -81,6 +83,32 @@ void B200HeunLLGSolver::build() {
         vid[n] = v;
       }
       check(jb_set_exchange_pairs(ctx_, nbr.size(), pi.data(), pj.data(), vid.data(), static_cast<int32_t>(uniq.size()), J9.data()));
+    } else if (auto *bq = dynamic_cast<CudaBiquadraticExchangeHamiltonian *>(h.get())) {
+      // CudaBiquadraticExchangeHamiltonian keeps its neighbour list (hamiltonian/cuda_biquadratic_exchange.h:40) and inserts
+      // B_ij = unit * J[0][0] for every pair whose value exceeds the energy cutoff (cuda_biquadratic_exchange.cu:127-134).  The
+      // library takes this term as a translation-invariant template: jb_detect_exchange_template turns the list into one.
+      const auto &nbr = bq->neighbour_list_;
+      std::vector<int32_t> pi, pj, vid;
+      std::vector<double> J9;
+      for (int n = 0; n < nbr.size(); ++n) {
+        const auto pr = nbr[n];
+        const double value = bq->input_energy_unit_conversion_ * pr.second[0][0];
+        if (!(value > bq->energy_cutoff_ * bq->input_energy_unit_conversion_)) continue;
+        int v = 0;
+        for (; v < static_cast<int>(J9.size() / 9); ++v) if (J9[9 * v] == value) break;
+        if (v == static_cast<int>(J9.size() / 9)) { J9.insert(J9.end(), 9, 0.0); J9[9 * v] = J9[9 * v + 4] = J9[9 * v + 8] = value; }
+        pi.push_back(pr.first[0]); pj.push_back(pr.first[1]); vid.push_back(v);
+      }
+      const int cap = 4096;
+      std::vector<int32_t> mi(cap), mj(cap), T3(3 * cap);
+      std::vector<double> J9t(9 * static_cast<size_t>(cap));
+      int32_t nt = -1;
+      check(jb_detect_exchange_template(&desc_, static_cast<int64_t>(pi.size()), pi.data(), pj.data(), vid.data(), static_cast<int32_t>(J9.size() / 9),
+                                        J9.data(), cap, &nt, mi.data(), mj.data(), T3.data(), J9t.data()));
+      if (nt < 0) throw std::runtime_error("llg-heun-b200-gpu: the biquadratic-exchange list is not translation invariant; use llg-heun-gpu");
+      std::vector<double> B(nt);
+      for (int k = 0; k < nt; ++k) B[k] = J9t[9 * static_cast<size_t>(k)];
+      check(jb_set_biquadratic_template(ctx_, nt, mi.data(), mj.data(), T3.data(), B.data()));
     } else if (auto *un = dynamic_cast<UniaxialAnisotropyHamiltonian *>(h.get())) {
       check(jb_set_uniaxial(ctx_, un->power_, un->magnitude_.data(), un->axis_.data()));
     } else if (auto *ze = dynamic_cast<ZeemanHamiltonian *>(h.get())) {

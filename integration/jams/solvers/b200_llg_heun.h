@@ -36,6 +36,7 @@ class B200HeunLLGSolver : public CudaSolver {
   void apply_pinned_boundaries();   // physics/pinned_boundaries.cc:34-46 on the library's own state
 
   jb_ctx *ctx_ = nullptr;
+  jb_lattice_desc desc_{};   // kept for the host-only helpers (jb_detect_exchange_template)
   bool built_ = false;
   bool spins_exported_ = true;  // globals::s currently equals the library's state
   bool gilbert_prefactor_ = false;
