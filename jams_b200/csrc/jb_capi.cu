@@ -776,7 +776,7 @@ static int plan_chunks_core(int nx, int gx, int n_cols, int G, const ChunkPlanOp
     double best_t = 1e300;
     for (int L : {1, 2, 3, 4, 5, 6, 8, 12, 16}) {
       if (L > nx || L < std::max(gx, 1)) continue;
-      const int nc = std::min((nx + L - 1) / L, JB_TILE_MAX_CHUNKS);
+      const int nc = std::max(1, std::min(std::min((nx + L - 1) / L, nx / std::max(gx, 1)), JB_TILE_MAX_CHUNKS));   // no chunk shorter than the ghost depth
       ChunkPlanCandidate cd;
       for (int k = 0; k < nc; ++k) {
         const int x0 = (int)((long long)k * nx / nc), x1 = (int)((long long)(k + 1) * nx / nc);

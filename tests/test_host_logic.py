@@ -369,3 +369,38 @@ def test_neighbour_list_with_impurities_bit_exact_with_oracle():
     assert np.array_equal(i, oi) and np.array_equal(j, oj) and np.array_equal(vals[v], oJ9)
     mat = lat.site_material()
     assert (mat[i] == 0).all() and (mat[j] == 0).all() and 0 < len(i) < lat.num_spins * 14
+
+
+def test_work_item_plan_covers_the_slab_exactly_once():
+    """jb_plan_work_items (host only): for any slab the x-chunks tile [0, nx) without gaps or overlaps, no chunk is shorter than the
+    ghost depth, the face chunks lead the queue, long chunks come before the taper; small lattices (BASELINE configs 1 and 2) get
+    chunks short enough to give every resident CTA an item"""
+    rng = np.random.default_rng(0)
+    cases = [(256, 1, 128, 296), (256, 1, 256, 592), (128, 1, 64, 296), (128, 2, 32, 148), (64, 1, 16, 296), (64, 1, 512, 592), (256, 1, 4, 296),
+             (16, 1, 4, 296), (8, 1, 2, 296), (5, 2, 3, 148), (1, 0, 7, 296), (3, 3, 1, 148), (512, 1, 512, 296), (2048, 1, 128, 296)]
+    cases += [(int(rng.integers(1, 600)), int(rng.integers(0, 4)), int(rng.integers(1, 300)), int(rng.choice([148, 296, 592]))) for _ in range(200)]
+    for nx, gx, n_cols, G in cases:
+        if nx < max(gx, 1):
+            continue
+        plan = capi.plan_work_items(nx, gx, n_cols, G)
+        assert 1 <= len(plan) <= 160, (nx, gx, n_cols, G)
+        covered = np.zeros(nx, int)
+        for x0, xc in plan:
+            assert xc >= 1 and 0 <= x0 and x0 + xc <= nx, (nx, gx, n_cols, G, plan)
+            covered[x0:x0 + xc] += 1
+        assert (covered == 1).all(), (nx, gx, n_cols, G, plan)
+        if len(plan) > 1:
+            assert min(xc for _, xc in plan) >= max(gx, 1), (nx, gx, n_cols, G, plan)
+        face = [(x0 < gx) or (x0 + xc > nx - gx) for x0, xc in plan]
+        n_face = sum(face)
+        assert all(face[:n_face]) and not any(face[n_face:]), (nx, gx, n_cols, G, plan)     # face chunks first
+    # small lattices: every resident CTA gets an item when there is enough work to go round
+    for nx, gx, n_cols, G in ((64, 1, 16, 296), (256, 1, 4, 296), (32, 1, 16, 296)):
+        plan = capi.plan_work_items(nx, gx, n_cols, G)
+        assert len(plan) * n_cols >= min(G, nx * n_cols) * 0.8, (nx, n_cols, G, len(plan))
+    # the bench workload: long chunks first, then a taper that ends in short chunks
+    plan = capi.plan_work_items(256, 1, 256, 592)
+    inner = [xc for x0, xc in plan if not ((x0 < 1) or (x0 + xc > 255))]
+    long = [xc for xc in inner if xc >= 16]
+    assert inner[:len(long)] == long and max(long) - min(long) <= 1           # equal long chunks lead ...
+    assert inner[len(long):] == sorted(inner[len(long):], reverse=True) and inner[-1] <= 4   # ... the taper ends in short ones
