@@ -65,6 +65,28 @@ def alloy(world, temperature):
     return dict(name="alloy", lattice=lat, hamiltonians=hams, spins=None, temperature=temperature)
 
 
+def deep(world, temperature):
+    """BASELINE config 4's template (bcc, eight shells, reach 2) on a small lattice: the rows kernel over the slabs"""
+    from jams_b200.lattice import Lattice, Material
+    w = W.c4_bcc_long_range(8, temperature=temperature)
+    w["lattice"] = Lattice([Material("Fe", 2.2, alpha=0.1)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (8 * world, 9, 40))
+    return w
+
+
+def solver_of(w, comm, seed, device, options):
+    """options may carry "solver": "rk4" (the RK4 stages on the TMA ring, four exchanges per step)"""
+    options = dict(options or {})
+    if options.pop("solver", "heun") == "rk4":
+        from jams_b200.solver import create_hamiltonian, create_solver
+        lat = w["lattice"]
+        s = create_solver(dict(module="llg-rk4-b200-gpu", t_step=W.T_STEP, t_max=1e-9, seed=seed, options=options, device=device), lat, comm)
+        for h in w["hamiltonians"]:
+            s.register_hamiltonian(create_hamiltonian(h, lat))
+        s.set_temperature(w.get("temperature", 0.0))
+        return s
+    return W.make_solver(w, comm=comm, seed=seed, device=device, options=options or None)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -79,12 +101,14 @@ def main():
                                                    ("sc periodic T=30 stored u", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(recover_u=0)),
                                                    ("sc periodic T=30 separate wait/signal launches", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 15, dict(fold_halo=0)),
                                                    ("bcc random alloy (lattice.impurities), general neighbour list, T=40", lambda: alloy(world, 40.0), True, 40.0, 12, None),
+                                                   ("bcc 8 shells (112 neighbours per spin), rows kernel, T=60", lambda: deep(world, 60.0), True, 60.0, 6, None),
+                                                   ("sc periodic T=30, RK4 on the ring", lambda: W.c3_sc(dims=(12 * world, 10, 36), temperature=30.0), True, 30.0, 8, dict(solver="rk4")),
                                                    ("sc 64/rank x 96 x 256 periodic T=80, many items", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, None),
                                                    ("sc 64/rank x 96 x 256 periodic T=80, short chunks", lambda: W.c3_sc(dims=(64 * world, 96, 256), temperature=80.0), True, 80.0, 10, dict(chunk_long=6, chunk_short=2, tail_pct=50))):
         w = make()
         lat = w["lattice"]
         comm = TorchComm(periodic_x=periodic_x, device=f"cuda:{local}")
-        s = W.make_solver(w, comm=comm, seed=77, device=local, options=opts)
+        s = solver_of(w, comm, 77, local, opts)
         s0 = w["spins"] if w.get("spins") is not None else lat.initial_spins(seed=5)
         per = lat.num_spins // world
         s.set_spins(s0[rank * per:(rank + 1) * per])
@@ -96,7 +120,7 @@ def main():
         comm.barrier(s.ctx)
         if rank == 0:
             got = torch.cat(parts).cpu().numpy()
-            single = W.make_solver(w, seed=77, device=local, options=opts)
+            single = solver_of(w, None, 77, local, opts)
             single.set_spins(s0)
             single.run(steps)
             want = single.spins()
