@@ -72,6 +72,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.mem_samples, self.power_samples = [], []
         self.ok = False
         try:
             import pynvml
@@ -93,6 +94,11 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:   # memory clock and board power: an HBM-bound kernel can slow down under sustained load at the full SM clock
+                    self.mem_samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)))
+                    self.power_samples.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:  # noqa: BLE001
+                    pass
                 try:
                     r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:  # noqa: BLE001
@@ -110,8 +116,13 @@ class ClockSampler(threading.Thread):
             self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        return {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+        out = {"sm_mhz": int(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples), "sm_mhz_min": int(min(self.samples))}
+        if self.mem_samples:
+            out["mem_mhz"] = int(np.median(self.mem_samples)); out["mem_mhz_min"] = int(min(self.mem_samples))
+        if self.power_samples:
+            out["power_w_max"] = float(max(self.power_samples))
+        return out
 
 
 def workload(n_ranks, dims=None):
