@@ -121,20 +121,6 @@ Mat3 rotation_matrix_between_vectors(const Vec3 &a, const Vec3 &b) {   // contai
   return R;
 }
 
-std::vector<Mat3> cubic_point_group() {   // the 48 signed permutation matrices of O_h (fractional basis, zero translations)
-  std::vector<Mat3> rots;
-  int perm[3] = {0, 1, 2};
-  do {
-    for (int s0 = 0; s0 < 2; ++s0) for (int s1 = 0; s1 < 2; ++s1) for (int s2 = 0; s2 < 2; ++s2) {
-      const double sg[3] = {s0 ? -1.0 : 1.0, s1 ? -1.0 : 1.0, s2 ? -1.0 : 1.0};
-      Mat3 R{};
-      for (int r = 0; r < 3; ++r) R[r][perm[r]] = sg[r];
-      rots.push_back(R);
-    }
-  } while (std::next_permutation(perm, perm + 3));
-  return rots;
-}
-
 // The rotations R of the crystal's symmetry operations {R|t} with t = 0, in the basis of the given cell: what the reference takes
 // from spglib's dataset (core/lattice.cc:783-822) and filters in lattice_site_point_group_symops (:1127-1153).  R runs over the
 // integer matrices that preserve the cell's metric (candidate columns in [-2, 2]^3, the lattice holohedry: at most 48); R is kept
