@@ -27,7 +27,9 @@ One "step" = one Heun step (predictor + corrector = two kernel launches) of ever
   cpu_baseline / --impl reference : the reference's CPU path (oracle/_ref: the reference's own SparseMatrix::multiply +
           restated HeunLLGSolver::run) on a bounded sample, timed at 1 OpenMP thread and at all host threads; the faster
           of the two is the value (the reference's small OpenMP loops get slower with many threads on these boxes).
-The oracle (CPU restatement / reference-header build) is executed only in the `cpu_baseline` and `--impl reference` legs.
+  reference_cuda : the reference's own CUDA path (cuSPARSE field + its Heun kernels, oracle/_ref/libjams_ref_cuda.so) on this
+          GPU, on a bounded sample, with the product timed on the same lattice beside it (N = 1 only; a baseline like cpu_baseline)
+The oracle (CPU restatement / reference-header builds) is executed only in the `cpu_baseline`, `reference_cuda` and `--impl reference` legs.
 """
 from __future__ import annotations
 
@@ -160,6 +162,65 @@ def cpu_run(sample_n, steps, warmup, threads):
         if line.startswith("{"):
             return json.loads(line)
     raise RuntimeError("cpu worker failed: " + (r.stderr or "")[-400:])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own CUDA path (llg-heun-gpu: curand normals, cuSPARSE SpMV field, cuda_heun_llg_kernelA/B) on this GPU, from
+# oracle/_ref/libjams_ref_cuda.so (the reference's kernels compiled where they lie, oracle/ref_cuda_wrap.cu).  A second baseline
+# next to cpu_baseline, on a bounded sample: the 3N x 3N CSR of the full 256^3 lattice is 3.6 GB on the device and ~10 GB on
+# the host while the reference's Builder sorts it.  The product is timed on the same lattice in the same process, after it.
+# ---------------------------------------------------------------------------------------------------
+def refcuda_worker(sample_n, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import oracle
+    from helpers import build_cpu_sim
+    from jams_b200 import workloads as W
+    torch.cuda.set_device(0)
+    w = workload(1, dims=(sample_n, sample_n, sample_n))
+    lat = w["lattice"]
+    s0 = lat.initial_spins(seed=1)
+    t0 = time.perf_counter()
+    ref = build_cpu_sim(w, which="reference_cuda", dt_ps=1e-4, seed=1)
+    build_s = time.perf_counter() - t0
+    ref.set_spins(s0)
+    ref_ms = ref.time_heun(steps, warmup)
+    nnz = ref.exchange_nnz(ref.terms["exchange"])
+    ref.close()
+    solver = W.make_solver(w, seed=1, device=0)
+    solver.set_spins(s0)
+    solver.run(warmup)
+    ctx = solver.ctx
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=0)
+    ctx.synchronize(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solver.run(steps)
+    e1.record(stream)
+    e1.synchronize(); ctx.synchronize()
+    own_ms = e0.elapsed_time(e1) / steps
+    print(json.dumps(dict(spins=lat.num_spins, ref_ms=ref_ms, own_ms=own_ms, nnz=nnz, build_s=build_s)), flush=True)
+
+
+def reference_cuda_rate(steps, warmup, sample_n=128):
+    sys.path.insert(0, ROOT)
+    import oracle
+    if not oracle.have_ref_cuda():
+        return {"unavailable": "oracle/_ref/libjams_ref_cuda.so was not built (needs the reference tree at build time)"}
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "refcuda-worker", "--cpu-sample", str(sample_n),
+                        "--steps", str(steps), "--warmup", str(warmup)], capture_output=True, text=True, timeout=900)
+    for line in reversed((r.stdout or "").splitlines()):
+        if line.startswith("{"):
+            res = json.loads(line)
+            n = res["spins"]
+            return {"value": n / (res["ref_ms"] * 1e-3), "unit": UNIT, "ms_per_step": res["ref_ms"], "kind": "reference",
+                    "path": "CUDAHeunLLGSolver::run: curandGenerateNormalDouble + scaling kernel, 2 x (cuSPARSE SpMV on the 3N x 3N CSR "
+                            "+ Zeeman field + daxpy), cuda_heun_llg_kernelA / B; the reference's sources compiled for sm_100a",
+                    "sample": f"sc {sample_n}^3 ({n} spins, {res['nnz']} CSR non-zeros) NN exchange + Zeeman, T={TEMPERATURE} K, {steps} Heun steps "
+                              f"after {warmup} warm-up, CUDA events; device-resident",
+                    "product_same_lattice": {"value": n / (res["own_ms"] * 1e-3), "unit": UNIT, "ms_per_step": res["own_ms"]},
+                    "speedup_same_lattice": res["ref_ms"] / res["own_ms"]}
+    return {"error": "reference CUDA worker failed: " + ((r.stderr or "")[-300:] or "no output")}
 
 
 def host_threads():
@@ -404,6 +465,10 @@ def run_b200(args):
             line["cpu_baseline"], _ = cpu_reference_rate(args.cpu_steps, 2, budget_s=20.0)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"error": str(e)}
+        try:
+            line["reference_cuda"] = reference_cuda_rate(min(K, 20), 3)
+        except Exception as e:  # noqa: BLE001
+            line["reference_cuda"] = {"error": str(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -491,7 +556,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-worker"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-worker", "refcuda-worker"])
     ap.add_argument("--kernel", type=int, default=None, help="0 = direct gathers through L1/L2, 2 = the TMA stage kernel (the library default)")
     ap.add_argument("--temperature", type=float, default=None, help="thermostat temperature of the workload in K (default 100; 0 = the deterministic T = 0 variant, a profile artefact and not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -504,6 +569,8 @@ def main():
         TEMPERATURE = float(args.temperature)
     if args.impl == "cpu-worker":
         cpu_worker(args.cpu_sample, args.steps, args.warmup)
+    elif args.impl == "refcuda-worker":
+        refcuda_worker(args.cpu_sample, args.steps, args.warmup)
     elif args.impl == "reference":
         run_reference(args)
     else:

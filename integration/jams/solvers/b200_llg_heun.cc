@@ -62,8 +62,16 @@ void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
 void B200HeunLLGSolver::build() {
   check(jb_set_materials(ctx_, globals::mus.data(), globals::gyro.data(), globals::alpha.data()));
   int ham_index = -1;   // hamiltonians_ are registered in config order (core/jams++.cc:284-288)
+  int seen[5] = {0, 0, 0, 0, 0};   // exchange, biquadratic, uniaxial, zeeman, applied field: the library holds one term of each kind
+  auto once = [&](int kind, const std::string &hname) {
+    if (seen[kind]++) throw std::runtime_error("llg-heun-b200-gpu: a second hamiltonian of the kind of '" + hname + "'; the fused solver holds one of each kind (merge them, or use llg-heun-gpu)");
+  };
   for (auto &h : hamiltonians_) {
     ++ham_index;
+    const int kind = dynamic_cast<ExchangeHamiltonian *>(h.get()) ? 0 : dynamic_cast<CudaBiquadraticExchangeHamiltonian *>(h.get()) ? 1 :
+                     dynamic_cast<UniaxialAnisotropyHamiltonian *>(h.get()) ? 2 : dynamic_cast<ZeemanHamiltonian *>(h.get()) ? 3 :
+                     dynamic_cast<AppliedFieldHamiltonian *>(h.get()) ? 4 : -1;
+    if (kind >= 0) once(kind, h->name());
     if (auto *ex = dynamic_cast<ExchangeHamiltonian *>(h.get())) {
       // ExchangeHamiltonian::neighbour_list() (hamiltonian/exchange.h:13): sorted {i,j} pairs + unique tensors.
       // The library recognises a translation-invariant list and switches to its template kernel.

@@ -1218,6 +1218,14 @@ void B200HeunLLGSolver::check(int status) const {
 }
 
 void B200HeunLLGSolver::register_hamiltonian(Hamiltonian *h) {
+  // one term of each kind in the fused kernels; the reference sums any number (core/solver.cc:43-57): refuse, do not drop
+  for (const auto &other : hamiltonians_)
+    if (other->term() == h->term()) {
+      const std::string msg = name() + ": hamiltonians '" + other->name() + "' and '" + h->name() +
+                              "' are the same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)";
+      delete h;
+      throw std::runtime_error(msg);
+    }
   h->solver = this;
   hamiltonians_.emplace_back(h);
 }

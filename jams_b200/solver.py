@@ -687,6 +687,12 @@ class Solver:
         return self.iteration < self.max_steps
 
     def register_hamiltonian(self, h: Hamiltonian):
+        # the fused kernels hold ONE term of each kind (one bilinear exchange list, one uniaxial power, one Zeeman field ...);
+        # the reference sums any number of Hamiltonians (core/solver.cc:43-57), so a second one of a kind is refused, not dropped
+        for other in self.hamiltonians:
+            if other.term == h.term:
+                raise RuntimeError(f"{self.name}: hamiltonians '{other.settings.get('module')}' and '{h.settings.get('module')}' are the "
+                                   "same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)")
         h.solver = self
         self.hamiltonians.append(h)
 

@@ -6,6 +6,8 @@ Two libraries, one Python face:
 * ``_ref/libjams_ref.so`` — the reference's own header-only code compiled in place from
   ``/root/reference/src`` (``oracle/ref_wrap.cpp``), prefix ``jref_``.  Exists only if it was built in a
   container that has the reference tree; it then travels to the GPU box as a prebuilt file.
+* ``_ref/libjams_ref_cuda.so`` — the reference's own CUDA kernels and cuSPARSE field path for the same step
+  (``oracle/ref_cuda_wrap.cu``, nvcc for sm_100a from the same tree), prefix ``jrc_``: ``RefCudaSim``.  Needs a GPU to run.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may import this package.  Nothing under ``jams_b200/`` does.
@@ -22,6 +24,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libjams_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libjams_ref.so")
+REF_CUDA_SO = os.path.join(HERE, "_ref", "libjams_ref_cuda.so")
 
 _c_double_p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _c_int_p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
@@ -29,12 +32,16 @@ _c_int_p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(ref: bool = True) -> None:
     """Compile the checkers (``make -C oracle oracle [ref]``)."""
-    targets = ["oracle"] + (["ref"] if ref else [])
+    targets = ["oracle"] + (["ref", "refcuda"] if ref else [])
     subprocess.run(["make", "-C", HERE, "--no-print-directory"] + targets, check=True, stdout=subprocess.DEVNULL)
 
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_ref_cuda() -> bool:
+    return os.path.exists(REF_CUDA_SO)
 
 
 def _f64(a, shape=None):
@@ -144,6 +151,195 @@ def reference() -> _Lib:
         L.jref_have_pcg.restype = C.c_int
         _libs["jref"] = lib
     return _libs["jref"]
+
+
+REF_CUDA_SYMBOLS = ("jrc_last_error", "jrc_device_count", "jrc_sim_create", "jrc_sim_destroy", "jrc_sim_add_exchange",
+                    "jrc_sim_add_uniaxial", "jrc_sim_add_zeeman", "jrc_sim_exchange_nnz", "jrc_sim_set_spins", "jrc_sim_get_spins",
+                    "jrc_sim_get_h", "jrc_sim_init_solver", "jrc_sim_run_heun", "jrc_sim_run_rk4", "jrc_sim_time_heun",
+                    "jrc_biquadratic_field", "jrc_pin_region", "jrc_reduce")
+
+
+def reference_cuda():
+    """ctypes handle of the reference's CUDA path (raises FileNotFoundError where it was never built)."""
+    if "jrc" not in _libs:
+        if not os.path.exists(REF_CUDA_SO):
+            raise FileNotFoundError(f"{REF_CUDA_SO} missing; `make -C oracle refcuda` in a container that has /root/reference")
+        L = C.CDLL(REF_CUDA_SO)
+        L.jrc_last_error.restype = C.c_char_p
+        L.jrc_device_count.restype = C.c_int
+        L.jrc_sim_create.restype = C.c_void_p
+        L.jrc_sim_create.argtypes = [C.c_int, _c_double_p, _c_double_p, _c_double_p]
+        L.jrc_sim_destroy.restype = None
+        L.jrc_sim_destroy.argtypes = [C.c_void_p]
+        L.jrc_sim_add_exchange.restype = C.c_int
+        L.jrc_sim_add_exchange.argtypes = [C.c_void_p, C.c_long, _c_int_p, _c_int_p, _c_double_p, C.c_int]
+        L.jrc_sim_add_uniaxial.restype = C.c_int
+        L.jrc_sim_add_uniaxial.argtypes = [C.c_void_p, C.c_int, _c_double_p, _c_double_p]
+        L.jrc_sim_add_zeeman.restype = C.c_int
+        L.jrc_sim_add_zeeman.argtypes = [C.c_void_p, _c_double_p, C.c_void_p, C.c_void_p]
+        L.jrc_sim_exchange_nnz.restype = C.c_long
+        L.jrc_sim_exchange_nnz.argtypes = [C.c_void_p, C.c_int]
+        for name in ("jrc_sim_set_spins", "jrc_sim_get_spins", "jrc_sim_get_h"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [C.c_void_p, _c_double_p]
+        L.jrc_sim_init_solver.restype = C.c_int
+        L.jrc_sim_init_solver.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_ulonglong]
+        for name in ("jrc_sim_run_heun", "jrc_sim_run_rk4"):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.jrc_sim_time_heun.restype = C.c_double
+        L.jrc_sim_time_heun.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.jrc_biquadratic_field.restype = C.c_int
+        L.jrc_biquadratic_field.argtypes = [C.c_int, C.c_long, _c_int_p, _c_int_p, _c_double_p, _c_double_p, _c_double_p]
+        L.jrc_pin_region.restype = C.c_int
+        L.jrc_pin_region.argtypes = [C.c_int, _c_double_p, _c_double_p, C.c_int, _c_int_p, _c_double_p, _c_double_p]
+        L.jrc_reduce.restype = C.c_int
+        L.jrc_reduce.argtypes = [C.c_int, C.c_int, _c_double_p, C.c_void_p, C.c_int, C.c_void_p, _c_double_p]
+        _libs["jrc"] = L
+    return _libs["jrc"]
+
+
+class RefCudaSim:
+    """The reference's own CUDA step (llg-heun-gpu / llg-rk4-gpu: cuSPARSE field + its kernels) on the current device, with the
+    method names of ``CpuSim`` so that tests/helpers.build_cpu_sim can assemble either."""
+
+    def __init__(self, mus, gyro, alpha):
+        self.L = reference_cuda()
+        if self.L.jrc_device_count() < 1:
+            raise RuntimeError("the reference's CUDA path needs a GPU")
+        self.N = len(mus)
+        self._arrays = (_f64(mus), _f64(gyro), _f64(alpha))
+        self.h = self.L.jrc_sim_create(self.N, *self._arrays)
+        if not self.h:
+            raise RuntimeError(self.error())
+        self.n_terms = 0
+        self.T = 0.0
+        self._solver = None
+
+    def error(self):
+        return (self.L.jrc_last_error() or b"").decode()
+
+    def close(self):
+        if self.h:
+            self.L.jrc_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.error())
+
+    def add_exchange(self, i, j, J9_per_pair, check_symmetric=True):
+        self._check(self.L.jrc_sim_add_exchange(self.h, len(i), _i32(i), _i32(j), _f64(J9_per_pair, (-1,)), int(check_symmetric)))
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_uniaxial(self, power, magnitude, axis):
+        self._check(self.L.jrc_sim_add_uniaxial(self.h, int(power), _f64(magnitude), _f64(axis, (-1,))))
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def add_zeeman(self, dc, ac=None, omega=None):
+        dc = _f64(dc, (-1,))
+        if ac is not None:
+            ac = _f64(ac, (-1,)); omega = _f64(omega)
+            rc = self.L.jrc_sim_add_zeeman(self.h, dc, ac.ctypes.data, omega.ctypes.data)
+        else:
+            rc = self.L.jrc_sim_add_zeeman(self.h, dc, None, None)
+        self._check(rc)
+        self.n_terms += 1
+        return self.n_terms - 1
+
+    def exchange_nnz(self, term=0):
+        return int(self.L.jrc_sim_exchange_nnz(self.h, term))
+
+    def set_spins(self, s):
+        self._check(self.L.jrc_sim_set_spins(self.h, _f64(s, (-1,))))
+
+    def get_spins(self):
+        s = np.zeros(3 * self.N)
+        self._check(self.L.jrc_sim_get_spins(self.h, s))
+        return s.reshape(-1, 3)
+
+    def get_h(self):
+        h = np.zeros(3 * self.N)
+        self._check(self.L.jrc_sim_get_h(self.h, h))
+        return h.reshape(-1, 3)
+
+    def init_solver(self, dt_ps, gilbert_prefactor=False, seed=1):
+        # sigma_(i, j) as CudaThermostatClassical's constructor fills it (cuda_thermostat_classical.cc:34-44 = the CPU solver's
+        # formula, cpu_llg_heun.cc:33-42): taken from the restatement, which test_oracle_cpu.py pins to the reference bit for bit
+        cpu = CpuSim(*self._arrays)
+        cpu.init_solver(dt_ps, gilbert_prefactor, seed)
+        self._sigma = np.ascontiguousarray(np.repeat(cpu.sigma()[:, None], 3, axis=1))
+        cpu.close()
+        self._solver = (float(dt_ps), int(seed))
+        self._check(self.L.jrc_sim_init_solver(self.h, float(dt_ps), self._sigma.ctypes.data, float(self.T), int(seed)))
+
+    def set_temperature(self, T):
+        self.T = float(T)
+        if self._solver is not None:
+            self._check(self.L.jrc_sim_init_solver(self.h, self._solver[0], self._sigma.ctypes.data, self.T, self._solver[1]))
+
+    def _run(self, fn, nsteps, normals):
+        if normals is not None:
+            normals = _f64(normals, (-1,))
+            assert normals.size == nsteps * 3 * self.N
+            self._check(fn(self.h, int(nsteps), normals.ctypes.data))
+        else:
+            self._check(fn(self.h, int(nsteps), None))
+
+    def run(self, nsteps=1, normals=None):
+        """CUDAHeunLLGSolver::run; ``normals`` = None draws them with curand like the reference"""
+        self._run(self.L.jrc_sim_run_heun, nsteps, normals)
+
+    def run_rk4(self, nsteps=1, normals=None):
+        """CudaRK4BaseSolver::run with CUDALLGRK4Solver's function kernel"""
+        self._run(self.L.jrc_sim_run_rk4, nsteps, normals)
+
+    def time_heun(self, steps, warmup):
+        """milliseconds per step of the reference's CUDA Heun step (CUDA events around ``steps`` steps)"""
+        ms = self.L.jrc_sim_time_heun(self.h, int(steps), int(warmup))
+        if ms < 0:
+            raise RuntimeError(self.error())
+        return ms
+
+
+def ref_cuda_biquadratic_field(n, i, j, B, s_aos):
+    h = np.zeros(3 * n)
+    L = reference_cuda()
+    if L.jrc_biquadratic_field(int(n), len(i), _i32(i), _i32(j), _f64(B), _f64(s_aos, (-1,)), h) != 0:
+        raise RuntimeError((L.jrc_last_error() or b"").decode())
+    return h.reshape(-1, 3)
+
+
+def ref_cuda_pin_region(s_aos, mus, indices, target):
+    """PinnedBoundariesPhysics::update's CUDA branch on one region: returns (rotated spins, region moment before the rotation)"""
+    L = reference_cuda()
+    s = _f64(s_aos, (-1,)).copy()
+    mag = np.zeros(3)
+    idx = _i32(indices)
+    if L.jrc_pin_region(len(mus), s, _f64(mus), len(idx), idx, _f64(target, (3,)), mag) != 0:
+        raise RuntimeError((L.jrc_last_error() or b"").decode())
+    return s.reshape(-1, 3), mag
+
+
+def ref_cuda_reduce(kind, s_aos, mus=None, indices=None):
+    L = reference_cuda()
+    out = np.zeros(3)
+    s = _f64(s_aos, (-1,))
+    m = _f64(mus) if mus is not None else None
+    idx = _i32(indices) if indices is not None else None
+    rc = L.jrc_reduce(int(kind), s.size // 3, s, m.ctypes.data if m is not None else None, len(idx) if idx is not None else 0,
+                      idx.ctypes.data if idx is not None else None, out)
+    if rc != 0:
+        raise RuntimeError((L.jrc_last_error() or b"").decode())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

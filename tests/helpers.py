@@ -131,7 +131,8 @@ def brute_force_functional_pairs(lat, functionals, tol=1e-4):
 def build_cpu_sim(workload, which="restatement", dt_ps=1e-4, seed=1):
     lat = workload["lattice"]
     mus, gyro, alpha = ref_material_arrays(lat)
-    sim = oracle.CpuSim(mus, gyro, alpha, which)
+    # "reference_cuda": the reference's own CUDA kernels + cuSPARSE field on the GPU (oracle/ref_cuda_wrap.cu), same assembly
+    sim = oracle.RefCudaSim(mus, gyro, alpha) if which == "reference_cuda" else oracle.CpuSim(mus, gyro, alpha, which)
     terms = {}
     for hs in workload["hamiltonians"]:
         module = hs["module"].lower()

@@ -355,6 +355,22 @@ def test_error_behaviour_mirrors_the_reference():
         create_hamiltonian(dict(module="dipole-fft"), lat)
 
 
+def test_a_second_hamiltonian_of_one_kind_is_refused_not_dropped():
+    """the reference sums any number of Hamiltonians (core/solver.cc:43-57); the fused kernels hold one term of each kind, so a
+    second one must fail loudly instead of silently replacing the first"""
+    from jams_b200.solver import create_solver
+    w = W.c3_sc(dims=(4, 4, 4))
+    lat = w["lattice"]
+    s = create_solver(dict(module="llg-heun-b200-gpu", t_step=1e-16, t_max=1e-12), lat)
+    for h in w["hamiltonians"]:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    with pytest.raises(RuntimeError, match="same kind of term"):
+        s.register_hamiltonian(create_hamiltonian(dict(module="zeeman", dc_local_field=[[0.0, 0.0, 0.5]]), lat))
+    s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order="K1", anisotropies=[("A", [0.0, 0.0, 1.0], 1e-23)]), lat))
+    with pytest.raises(RuntimeError, match="same kind of term"):
+        s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order="K2", anisotropies=[("A", [0.0, 0.0, 1.0], 1e-23)]), lat))
+
+
 # ---- RK4-LLG (SURVEY.md 8f row 3): jb_step_rk4 against the restatement of CudaRK4BaseSolver::run ----
 def _rk4_solver(w, **kw):
     from jams_b200.solver import create_solver

@@ -169,6 +169,19 @@ def test_error_behaviour_mirrors_the_reference():
 
 
 @pytest.mark.gpu
+def test_cpp_a_second_hamiltonian_of_one_kind_is_refused_not_dropped(tmp_path):
+    """the reference sums any number of Hamiltonians (core/solver.cc:43-57); the fused solver holds one term of each kind and must
+    say so instead of letting the later one replace the earlier"""
+    text = open(FIXTURE).read()
+    extra = '{ module = "uniaxial"; order = "K2"; anisotropies = ( ( "A", [ 0.0, 0.0, 1.0 ], 1e-24 ) ); },\n  {\n    module = "exchange";'
+    assert text.count('{\n    module = "exchange";') == 1
+    cfg = tmp_path / "two_uniaxial.cfg"
+    cfg.write_text(text.replace('{\n    module = "exchange";', extra))
+    with pytest.raises(host.HostError, match="same kind of term"):
+        host.run(str(cfg), PATCH_B200, name="dup", output_dir=str(tmp_path))
+
+
+@pytest.mark.gpu
 def test_cpp_simulation_equals_python_mirror_and_writes_jams_monitor_files(tmp_path):
     """the same config through the C++ Simulation (C++ lattice/template/initializer/main loop) and through the Python mirror"""
     steps = 40

@@ -404,3 +404,4 @@ def test_work_item_plan_covers_the_slab_exactly_once():
     long = [xc for xc in inner if xc >= 16]
     assert inner[:len(long)] == long and max(long) - min(long) <= 1           # equal long chunks lead ...
     assert inner[len(long):] == sorted(inner[len(long):], reverse=True) and inner[-1] <= 4   # ... the taper ends in short ones
+
