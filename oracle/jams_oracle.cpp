@@ -12,11 +12,13 @@
 //   (2) the golden vectors in tests/golden/ that were generated from (1) by
 //       tests/golden/make_golden.py, plus the reference's known answers
 //       (sc 8^3 NN -> 3072 interactions, src/jams/test/interactions.h:241-252).
-// PARITY UNPINNED for three restatements of code the reference has only as CUDA kernels and ships no test or vector for:
-//   rk4_run (solvers/cuda_rk4_base.cu), the biquadratic-exchange term (hamiltonian/cuda_biquadratic_exchange_kernel.cuh) and, in
-//   oracle/__init__.py, pin_region (physics/pinned_boundaries.cc).  They are pinned to the mathematics instead: fourth-order
-//   convergence / fixed point / analytic precession (RK4), h = -dE/ds by finite differences (biquadratic), the golden
-//   rotation_matrix_between_vectors vectors (pin_region): tests/test_oracle_cpu.py.
+// Three restatements follow code the reference has only as CUDA kernels and ships no test or vector for: rk4_run
+//   (solvers/cuda_rk4_base.cu), the biquadratic-exchange term (hamiltonian/cuda_biquadratic_exchange_kernel.cuh) and, in
+//   oracle/__init__.py, pin_region (physics/pinned_boundaries.cc).  They are PINNED on the GPU box against those kernels
+//   themselves -- oracle/_ref/libjams_ref_cuda.so, the reference's CUDA sources compiled for sm_100a by oracle/ref_cuda_wrap.cu:
+//   tests/test_gpu_reference_cuda.py (<= 1e-12 RK4 trajectories, field and rotation to rounding) -- and, on the CPU, to the
+//   mathematics: fourth-order convergence / fixed point / analytic precession (RK4), h = -dE/ds by finite differences
+//   (biquadratic), the golden rotation_matrix_between_vectors vectors (pin_region): tests/test_oracle_cpu.py.
 //
 // All citations are file:line under /root/reference/src/jams/.
 // Arithmetic is written out in the same operand order as the reference so that, compiled with

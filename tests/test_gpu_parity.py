@@ -722,7 +722,7 @@ def test_biquadratic_exchange_fields_energies_and_trajectory_match_oracle(solver
     to bilinear exchange and a uniaxial term on bcc (NN + NNN biquadratic shells; a negative coupling is dropped by the reference's
     value > energy_cutoff filter and must be dropped here).  Fields and per-spin energies per term, the reference's total (half the
     sum of the per-spin energies), T = 0 Heun and RK4 trajectories, a same-noise T > 0 Heun trajectory.  The reference has no test or
-    CPU field implementation of this term: the oracle restates the CUDA kernel, parity is unpinned by reference vectors."""
+    CPU field implementation of this term: the oracle restates the CUDA kernel; tests/test_gpu_reference_cuda.py pins both to that kernel itself."""
     from jams_b200.solver import create_solver
     lat = Lattice([Material("Fe", 2.2, alpha=0.1)], np.eye(3), [("Fe", (0, 0, 0)), ("Fe", (0.5, 0.5, 0.5))], (6, 5, 7), periodic=(True, True, False))
     hams = [dict(module="exchange", interactions=[("Fe", "Fe", [0.5, 0.5, 0.5], 3.2e-21)]),
