@@ -251,3 +251,57 @@ def test_magnetisation_monitor_against_the_reference_cuda_reductions():
         want = list(m / mus[idx].sum()) + [np.linalg.norm(m) / mus[idx].sum()]
         assert np.allclose(row[2 + 4 * gidx: 6 + 4 * gidx], want, rtol=0, atol=1e-13)
         assert np.abs(oracle.ref_cuda_reduce(2, x, None, idx) - x[idx].sum(axis=0)).max() <= 1e-11
+
+
+# ---- the product against the committed vectors the reference's CUDA kernels produced (tests/golden/refcuda_*.npz, generated by
+# ---- tests/golden/make_golden_refcuda.py on the GPU box): these need no reference library at run time -----------------------------
+import os
+
+import refcuda_cases as RC
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["sc", "bcc"])
+@pytest.mark.parametrize("solver", ["heun", "rk4", "rk4_direct"])
+def test_product_reproduces_the_reference_cuda_golden_trajectories(name, solver):
+    g = np.load(os.path.join(GOLD, f"refcuda_T0_{name}.npz"))
+    w = RC.sc_three_terms((12, 9, 20)) if name == "sc" else RC.bcc_fe()
+    s = _solver(w, "llg-heun-b200-gpu" if solver == "heun" else "llg-rk4-b200-gpu", options=dict(kernel=0) if solver == "rk4_direct" else None)
+    s.set_spins(g["s0"])
+    h = s.compute_fields()
+    assert np.abs(h - g["h"]).max() <= 1e-13 * np.abs(g["h"]).max()
+    s.run(RC.HEUN_STEPS if solver == "heun" else RC.RK4_STEPS)
+    assert np.abs(s.spins() - g["heun" if solver == "heun" else "rk4"]).max() <= TRAJ_TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver", ["heun", "rk4"])
+def test_product_reproduces_the_reference_cuda_golden_thermal_trajectories(solver):
+    """the fixture's normals are the product's own Philox draws for (seed, step): regenerated here bit for bit, then the trajectory
+    the reference's kernels integrated with them"""
+    g = np.load(os.path.join(GOLD, "refcuda_thermal_sc.npz"))
+    w = RC.sc_three_terms((8, 7, 10), temperature=RC.THERMAL_T)
+    s = _solver(w, "llg-heun-b200-gpu" if solver == "heun" else "llg-rk4-b200-gpu", seed=RC.THERMAL_SEED)
+    s.set_spins(g["s0"])
+    normals = np.stack([s.ctx.noise(s.step_size, RC.THERMAL_T, RC.THERMAL_SEED, n, normals_only=True) for n in range(RC.THERMAL_STEPS)])
+    assert np.array_equal(normals, g["normals"])
+    s.run(RC.THERMAL_STEPS)
+    assert np.abs(s.spins() - g[solver]).max() <= TRAJ_TOL
+
+
+@pytest.mark.gpu
+def test_product_reproduces_the_reference_cuda_golden_biquadratic_field_and_pinned_rotation():
+    g = np.load(os.path.join(GOLD, "refcuda_biquadratic.npz"))
+    s = _solver(RC.biquadratic(), "llg-heun-b200-gpu")
+    s.set_spins(g["s0"])
+    h = s.hamiltonians[0].calculate_fields(0.0)
+    assert np.abs(h - g["h"]).max() <= 1e-13 * np.abs(g["h"]).max()
+    g = np.load(os.path.join(GOLD, "refcuda_pinned.npz"))
+    w, phys = RC.pinned_wall()
+    s = _solver(w, "llg-heun-b200-gpu")
+    s.register_physics_module(create_physics(phys, w["lattice"]))
+    s.set_spins(g["s0"])
+    s.update_physics_module()
+    assert np.abs(s.spins() - g["rotated"]).max() <= 1e-13
