@@ -186,21 +186,32 @@ def refcuda_worker(sample_n, steps, warmup):
     build_s = time.perf_counter() - t0
     ref.set_spins(s0)
     ref_ms = ref.time_heun(steps, warmup)
+    ref_rk4_ms = ref.time_heun(max(steps // 2, 2), 2, rk4=True)
     nnz = ref.exchange_nnz(ref.terms["exchange"])
     ref.close()
-    solver = W.make_solver(w, seed=1, device=0)
-    solver.set_spins(s0)
-    solver.run(warmup)
-    ctx = solver.ctx
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=0)
-    ctx.synchronize(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    solver.run(steps)
-    e1.record(stream)
-    e1.synchronize(); ctx.synchronize()
-    own_ms = e0.elapsed_time(e1) / steps
-    print(json.dumps(dict(spins=lat.num_spins, ref_ms=ref_ms, own_ms=own_ms, nnz=nnz, build_s=build_s)), flush=True)
+
+    def own(module):
+        from jams_b200.solver import create_hamiltonian, create_solver
+        solver = create_solver(dict(module=module, t_step=W.T_STEP, t_max=1e-9, seed=1), lat)
+        for h in w["hamiltonians"]:
+            solver.register_hamiltonian(create_hamiltonian(h, lat))
+        solver.set_temperature(TEMPERATURE)
+        solver.set_spins(s0)
+        solver.run(warmup)
+        ctx = solver.ctx
+        stream = torch.cuda.ExternalStream(ctx.stream(), device=0)
+        ctx.synchronize(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        solver.run(steps)
+        e1.record(stream)
+        e1.synchronize(); ctx.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ctx.close()
+        return ms
+
+    print(json.dumps(dict(spins=lat.num_spins, ref_ms=ref_ms, own_ms=own("llg-heun-b200-gpu"), ref_rk4_ms=ref_rk4_ms, own_rk4_ms=own("llg-rk4-b200-gpu"),
+                          nnz=nnz, build_s=build_s)), flush=True)
 
 
 def reference_cuda_rate(steps, warmup, sample_n=N_CELLS):
@@ -225,7 +236,12 @@ def reference_cuda_rate(steps, warmup, sample_n=N_CELLS):
                     "sample": f"sc {sample_n}^3 ({n} spins, {res['nnz']} CSR non-zeros) NN exchange + Zeeman, T={TEMPERATURE} K, {steps} Heun steps "
                               f"after {warmup} warm-up, CUDA events; device-resident; matrix assembly {res['build_s']:.0f} s on the host, untimed",
                     "product_same_lattice": {"value": n / (res["own_ms"] * 1e-3), "unit": UNIT, "ms_per_step": res["own_ms"]},
-                    "speedup_same_lattice": res["ref_ms"] / res["own_ms"]}
+                    "speedup_same_lattice": res["ref_ms"] / res["own_ms"],
+                    "rk4": {"reference_ms_per_step": res["ref_rk4_ms"], "product_ms_per_step": res["own_rk4_ms"],
+                            "reference_value": n / (res["ref_rk4_ms"] * 1e-3), "product_value": n / (res["own_rk4_ms"] * 1e-3), "unit": UNIT,
+                            "speedup_same_lattice": res["ref_rk4_ms"] / res["own_rk4_ms"],
+                            "path": "CudaRK4BaseSolver::run (llg-rk4-gpu): 4 x (SpMV + Zeeman + daxpy + cuda_llg_rk4_kernel), cublas mid-points, "
+                                    "combination + normalisation kernels"}}
     return {"error": "reference CUDA worker failed: " + ((r.stderr or "")[-300:] or "no output")}
 
 

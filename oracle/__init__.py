@@ -155,7 +155,7 @@ def reference() -> _Lib:
 
 REF_CUDA_SYMBOLS = ("jrc_last_error", "jrc_device_count", "jrc_sim_create", "jrc_sim_destroy", "jrc_sim_add_exchange",
                     "jrc_sim_add_uniaxial", "jrc_sim_add_zeeman", "jrc_sim_exchange_nnz", "jrc_sim_set_spins", "jrc_sim_get_spins",
-                    "jrc_sim_get_h", "jrc_sim_init_solver", "jrc_sim_run_heun", "jrc_sim_run_rk4", "jrc_sim_time_heun",
+                    "jrc_sim_get_h", "jrc_sim_init_solver", "jrc_sim_run_heun", "jrc_sim_run_rk4", "jrc_sim_time_heun", "jrc_sim_time_rk4",
                     "jrc_biquadratic_field", "jrc_pin_region", "jrc_reduce")
 
 
@@ -187,8 +187,9 @@ def reference_cuda():
         for name in ("jrc_sim_run_heun", "jrc_sim_run_rk4"):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p]
-        L.jrc_sim_time_heun.restype = C.c_double
-        L.jrc_sim_time_heun.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for name in ("jrc_sim_time_heun", "jrc_sim_time_rk4"):
+            getattr(L, name).restype = C.c_double
+            getattr(L, name).argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.jrc_biquadratic_field.restype = C.c_int
         L.jrc_biquadratic_field.argtypes = [C.c_int, C.c_long, _c_int_p, _c_int_p, _c_double_p, _c_double_p, _c_double_p]
         L.jrc_pin_region.restype = C.c_int
@@ -302,9 +303,9 @@ class RefCudaSim:
         """CudaRK4BaseSolver::run with CUDALLGRK4Solver's function kernel"""
         self._run(self.L.jrc_sim_run_rk4, nsteps, normals)
 
-    def time_heun(self, steps, warmup):
-        """milliseconds per step of the reference's CUDA Heun step (CUDA events around ``steps`` steps)"""
-        ms = self.L.jrc_sim_time_heun(self.h, int(steps), int(warmup))
+    def time_heun(self, steps, warmup, rk4=False):
+        """milliseconds per step of the reference's CUDA Heun (RK4) step (CUDA events around ``steps`` steps)"""
+        ms = (self.L.jrc_sim_time_rk4 if rk4 else self.L.jrc_sim_time_heun)(self.h, int(steps), int(warmup))
         if ms < 0:
             raise RuntimeError(self.error())
         return ms

@@ -380,20 +380,20 @@ int jrc_sim_run_rk4(void *hdl, int nsteps, const double *normals) {
   });
 }
 
-// `steps` Heun steps timed with CUDA events after `warmup` untimed ones; returns milliseconds per step (< 0 on error).
-// The timed region is CUDAHeunLLGSolver::run as the reference executes it: curand normals, the scaling kernel, two cuSPARSE SpMVs
-// (+ the other terms' kernels and the daxpy sum) and kernels A / B.
-double jrc_sim_time_heun(void *hdl, int steps, int warmup) {
+// `steps` steps timed with CUDA events after `warmup` untimed ones; returns milliseconds per step (< 0 on error).
+// The timed region is CUDAHeunLLGSolver::run (CudaRK4BaseSolver::run for rk4 != 0) as the reference executes it: curand normals, the
+// scaling kernel, two (four) cuSPARSE SpMVs (+ the other terms' kernels and the daxpy sum) and the solver's kernels.
+static double time_steps(void *hdl, int steps, int warmup, int rk4) {
   Sim &sim = *static_cast<Sim *>(hdl);
   double ms_per_step = -1.0;
   int rc = guarded([&] {
     sim.host_normals = nullptr;
-    for (int k = 0; k < warmup; ++k) heun_step(sim);
+    for (int k = 0; k < warmup; ++k) rk4 ? rk4_step(sim) : heun_step(sim);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaDeviceSynchronize();
     cudaEventRecord(e0, nullptr);
-    for (int k = 0; k < steps; ++k) heun_step(sim);
+    for (int k = 0; k < steps; ++k) rk4 ? rk4_step(sim) : heun_step(sim);
     cudaEventRecord(e1, nullptr);
     cudaEventSynchronize(e1);
     float ms = 0.f;
@@ -403,6 +403,8 @@ double jrc_sim_time_heun(void *hdl, int steps, int warmup) {
   });
   return rc ? -1.0 : ms_per_step;
 }
+double jrc_sim_time_heun(void *hdl, int steps, int warmup) { return time_steps(hdl, steps, warmup, 0); }
+double jrc_sim_time_rk4(void *hdl, int steps, int warmup) { return time_steps(hdl, steps, warmup, 1); }
 
 // CudaBiquadraticExchangeHamiltonian: scalar N x N matrix through the Builder (hamiltonian/cuda_biquadratic_exchange.cu:100-157)
 // and calculate_fields (:159-171)
