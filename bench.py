@@ -534,6 +534,7 @@ def other_configs(steps, peak_gbs=None):
     out = []
     for name, w, z in (("C2 bcc Fe 64^3 NN+NNN (z = 14), T = 300 K (BASELINE config 2)", W.c2_bcc_fe(64, temperature=300.0), 14),
                        ("C2 bcc Fe 128^3 NN+NNN (z = 14), T = 300 K", W.c2_bcc_fe(128, temperature=300.0), 14),
+                       ("C2 bcc Fe 256^3 NN+NNN (z = 14), T = 300 K (the same kernel on a lattice that fills the GPU)", W.c2_bcc_fe(256, temperature=300.0), 14),
                        ("C4 bcc 128^3, 8 shells (z = 112), T = 0", W.c4_bcc_long_range(128, temperature=0.0), 112)):
         try:
             s = W.make_solver(w, options=dict(time_kernels=1), random_spins_seed=1)
@@ -543,6 +544,7 @@ def other_configs(steps, peak_gbs=None):
             n = w["lattice"].num_spins
             out.append({"config": name, "spins": n, "stage_ms": [float(st[0]), float(st[1])], "value": n / (float(st.sum()) * 1e-3), "unit": UNIT,
                         "kernel": names.get(s.ctx.stage_kernel(), "?"), "gather_TBs": [n * z * 24.0 / (float(t) * 1e-3) / 1e12 for t in st],
+                        "frac_of_144B_model": (144.0 * n / (float(st.sum()) * 1e-3) / 1e9 / peak_gbs) if peak_gbs else None,
                         "timing": "sum of the two stage launches, CUDA events"})
             s.ctx.close()
         except Exception as e:  # noqa: BLE001

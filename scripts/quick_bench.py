@@ -1,6 +1,6 @@
 """Development helper: time the two stage launches for a list of option sets (not the contract bench; see bench.py).
 
-    python scripts/quick_bench.py [--dims 256x256x256] [--T 0,100] [--steps 20] [--trace] ['{"recover_u": 0}' '{"chunks": 9}' ...]
+    python scripts/quick_bench.py [--workload c3|c2|c4] [--dims 256x256x256] [--T 0,100] [--steps 20] [--trace] ['{"recover_u": 0}' '{"chunks": 9}' ...]
 
 Every option set runs in its own process (a CUDA error is sticky for the process that hit it).  With --trace the per-CTA
 busy times of the last stage-A / stage-B launch are summarised (min / mean / max, items per CTA)."""
@@ -41,7 +41,8 @@ def trace_summary(ctx, tag, dump=None):
 
 def run(dims, options, T, steps, label, trace):
     from jams_b200 import workloads as W
-    w = W.c3_sc(dims=dims, temperature=T)
+    kind = os.environ.get("JB_QB_WORKLOAD", "c3")     # --workload c2 | c4: cubic bcc lattices of dims[0]^3
+    w = W.c3_sc(dims=dims, temperature=T) if kind == "c3" else (W.c2_bcc_fe(dims[0], temperature=T) if kind == "c2" else W.c4_bcc_long_range(dims[0], temperature=T))
     try:
         s = W.make_solver(w, options=dict(options, time_kernels=1, trace=1 if trace else 0), random_spins_seed=1)
         s.run(3); s.ctx.synchronize(); s.ctx.last_step_kernel_ms()
@@ -75,6 +76,7 @@ if __name__ == "__main__":
         elif args[i] == "--T": temps = [float(v) for v in args[i + 1].split(",")]; i += 2
         elif args[i] == "--steps": steps = int(args[i + 1]); i += 2
         elif args[i] == "--trace": trace = True; i += 1
+        elif args[i] == "--workload": os.environ["JB_QB_WORKLOAD"] = args[i + 1]; i += 2
         else: sets.append(args[i]); i += 1
     if not sets:
         sets = ["{}"]
