@@ -54,7 +54,9 @@ typedef enum jb_term {
   JB_TERM_ZEEMAN = 2,    /* "zeeman"        hamiltonian/zeeman.cc */
   JB_TERM_APPLIED = 3,   /* "applied-field" hamiltonian/applied_field.cc */
   JB_TERM_TOTAL = 4,     /* sum of the registered terms = globals::h after Solver::compute_fields */
-  JB_TERM_BIQUADRATIC = 5 /* "biquadratic-exchange" hamiltonian/cuda_biquadratic_exchange.cu */
+  JB_TERM_BIQUADRATIC = 5, /* "biquadratic-exchange" hamiltonian/cuda_biquadratic_exchange.cu */
+  JB_TERM_UNIAXIAL_2 = 6, /* a second and a third "uniaxial" Hamiltonian of the configuration (jb_set_uniaxial_term slots 1, 2) */
+  JB_TERM_UNIAXIAL_3 = 7
 } jb_term;
 
 /* Lattice + slab description.  Replaces what the solver reads from globals::lattice
@@ -131,6 +133,12 @@ JB_API int jb_detect_exchange_template(const jb_lattice_desc *desc, int64_t n_pa
 /* UniaxialAnisotropyHamiltonian: power_ (2,4,6), magnitude_ (N, meV), axis_ (N x 3, unit vectors)
  * (hamiltonian/uniaxial_anisotropy.h:30-32, .cc:89-114). */
 JB_API int jb_set_uniaxial(jb_ctx *ctx, int32_t power, const double *magnitude, const double *axis);
+/* The reference sums any number of Hamiltonians (core/solver.cc:43-57, cuda/cuda_solver.cc:11-26), and K1 + K2 anisotropies are
+ * written as two "uniaxial" modules (one power_ each, uniaxial_anisotropy.cc:89-114).  slot 0 = jb_set_uniaxial (term
+ * JB_TERM_UNIAXIAL); slots 1 and 2 hold a second and a third module (JB_TERM_UNIAXIAL_2 / _3).  A context with a slot > 0 in use
+ * runs its steps on the direct-gather stage kernels (the TMA kernels keep one uniaxial term in their parameter block).
+ * power = 0 or magnitude = NULL clears the slot. */
+JB_API int jb_set_uniaxial_term(jb_ctx *ctx, int32_t slot, int32_t power, const double *magnitude, const double *axis);
 
 /* ZeemanHamiltonian: dc_local_field_ (N x 3, already multiplied by mu_i, meV), optional
  * ac_local_field_ (N x 3, meV) and ac_local_frequency_ (N, rad/ps = 2*pi*f) or NULL

@@ -62,9 +62,11 @@ void B200HeunLLGSolver::initialize(const libconfig::Setting &settings) {
 void B200HeunLLGSolver::build() {
   check(jb_set_materials(ctx_, globals::mus.data(), globals::gyro.data(), globals::alpha.data()));
   int ham_index = -1;   // hamiltonians_ are registered in config order (core/jams++.cc:284-288)
-  int seen[5] = {0, 0, 0, 0, 0};   // exchange, biquadratic, uniaxial, zeeman, applied field: the library holds one term of each kind
+  // exchange, biquadratic, uniaxial, zeeman, applied field: the library holds one term of each kind, except uniaxial terms, which
+  // go into up to three slots (K1 + K2 + K3 as separate modules: jb_set_uniaxial_term)
+  int seen[5] = {0, 0, 0, 0, 0};
   auto once = [&](int kind, const std::string &hname) {
-    if (seen[kind]++) throw std::runtime_error("llg-heun-b200-gpu: a second hamiltonian of the kind of '" + hname + "'; the fused solver holds one of each kind (merge them, or use llg-heun-gpu)");
+    if (seen[kind]++ >= (kind == 2 ? 3 : 1)) throw std::runtime_error("llg-heun-b200-gpu: one hamiltonian too many of the kind of '" + hname + "'; the fused solver holds one of each kind and three uniaxial terms (merge them, or use llg-heun-gpu)");
   };
   for (auto &h : hamiltonians_) {
     ++ham_index;
@@ -118,7 +120,7 @@ void B200HeunLLGSolver::build() {
       for (int k = 0; k < nt; ++k) B[k] = J9t[9 * static_cast<size_t>(k)];
       check(jb_set_biquadratic_template(ctx_, nt, mi.data(), mj.data(), T3.data(), B.data()));
     } else if (auto *un = dynamic_cast<UniaxialAnisotropyHamiltonian *>(h.get())) {
-      check(jb_set_uniaxial(ctx_, un->power_, un->magnitude_.data(), un->axis_.data()));
+      check(jb_set_uniaxial_term(ctx_, seen[2] - 1, un->power_, un->magnitude_.data(), un->axis_.data()));   // slot = how many came before
     } else if (auto *ze = dynamic_cast<ZeemanHamiltonian *>(h.get())) {
       check(jb_set_zeeman(ctx_, ze->dc_local_field_.data(),
                           ze->has_ac_local_field_ ? ze->ac_local_field_.data() : nullptr,

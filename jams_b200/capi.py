@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libjams_b200.so")
 
 JB_OK, JB_ERR_INVALID, JB_ERR_CUDA, JB_ERR_UNSUPPORTED, JB_ERR_PEER = range(5)
-TERM_EXCHANGE, TERM_UNIAXIAL, TERM_ZEEMAN, TERM_APPLIED, TERM_TOTAL, TERM_BIQUADRATIC = range(6)
+TERM_EXCHANGE, TERM_UNIAXIAL, TERM_ZEEMAN, TERM_APPLIED, TERM_TOTAL, TERM_BIQUADRATIC, TERM_UNIAXIAL_2, TERM_UNIAXIAL_3 = range(8)
+UNIAXIAL_TERMS = (TERM_UNIAXIAL, TERM_UNIAXIAL_2, TERM_UNIAXIAL_3)   # jb_set_uniaxial_term slots 0, 1, 2
 HALO_HANDLE_BYTES = 256
 
 
@@ -44,6 +45,7 @@ SIGNATURES = {
     "jb_detect_exchange_template": (C.c_int, [C.POINTER(LatticeDesc), C.c_int64, _ip, _ip, _ip, C.c_int32, _dp, C.c_int32,
                                                C.POINTER(C.c_int32), _ip, _ip, _ip, _dp]),
     "jb_set_uniaxial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "jb_set_uniaxial_term": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "jb_set_zeeman": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_set_applied_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_set_applied_field_pulse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double]),
@@ -197,12 +199,13 @@ class Context:
         v = np.ascontiguousarray(value_id, np.int32); J = _f64(values9).reshape(-1)
         self._ck(self.lib.jb_set_exchange_pairs(self.h, i.size, i, j, v, J.size // 9, J))
 
-    def set_uniaxial(self, power, magnitude, axis):
+    def set_uniaxial(self, power, magnitude, axis, slot=0):
+        """slot 0 = jb_set_uniaxial; slots 1, 2: a second / third uniaxial Hamiltonian (jb_set_uniaxial_term)"""
         if not power:
-            self._ck(self.lib.jb_set_uniaxial(self.h, 0, None, None)); return
+            self._ck(self.lib.jb_set_uniaxial_term(self.h, int(slot), 0, None, None)); return
         K, a = _f64(magnitude), _f64(axis).reshape(-1)
         assert K.size == self.N and a.size == 3 * self.N
-        self._ck(self.lib.jb_set_uniaxial(self.h, int(power), _ptr(K), _ptr(a)))
+        self._ck(self.lib.jb_set_uniaxial_term(self.h, int(slot), int(power), _ptr(K), _ptr(a)))
 
     def set_zeeman(self, dc, ac=None, omega=None):
         dc = None if dc is None else _f64(dc).reshape(-1)

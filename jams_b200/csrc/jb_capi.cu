@@ -227,15 +227,18 @@ int build_classes(jb_ctx *c) {
   const JbGeom &g = c->g;
   const int N = c->N;
   if ((int)c->h_mus.size() != N) JB_FAIL(c, JB_ERR_INVALID, "jb_set_materials has not been called");
-  std::map<std::array<double, 18>, int> seen;
+  std::map<std::array<double, 24>, int> seen;
   c->h_classes.clear(); c->h_class_dc.clear(); c->h_class_ac.clear(); c->h_class_omega.clear(); c->h_class_gyro.clear();
+  c->h_uni_extra.clear();
   std::vector<unsigned char> cls(N);
   for (int i = 0; i < N; ++i) {
-    std::array<double, 18> key{};
+    std::array<double, 24> key{};
     key[0] = c->h_mus[i]; key[1] = c->h_gyro[i]; key[2] = c->h_alpha[i];
     if (c->uni_power) { key[3] = c->h_K[i]; key[4] = c->h_axis[3 * i]; key[5] = c->h_axis[3 * i + 1]; key[6] = c->h_axis[3 * i + 2]; }
     if (c->has_zeeman) { key[7] = c->h_dc[3 * i]; key[8] = c->h_dc[3 * i + 1]; key[9] = c->h_dc[3 * i + 2]; }
     if (c->has_ac) { key[10] = c->h_ac[3 * i]; key[11] = c->h_ac[3 * i + 1]; key[12] = c->h_ac[3 * i + 2]; key[13] = c->h_omega[i]; }
+    for (int q = 0; q < JB_MAX_UNIAXIAL - 1; ++q)
+      if (c->uni_powerx[q]) { key[14 + 4 * q] = c->h_Kx[q][i]; for (int d = 0; d < 3; ++d) key[15 + 4 * q + d] = c->h_axisx[q][3 * i + d]; }
     auto it = seen.find(key);
     int id;
     if (it == seen.end()) {
@@ -249,6 +252,13 @@ int build_classes(jb_ctx *c) {
       k.K = key[3]; k.Kp = key[3] * c->uni_power; k.ax = key[4]; k.ay = key[5]; k.az = key[6];
       k.power = (c->uni_power && key[3] != 0.0) ? c->uni_power : 0;
       c->h_classes.push_back(k);
+      for (int q = 0; q < JB_MAX_UNIAXIAL - 1; ++q) {
+        JbUniExtra u{};
+        u.K = key[14 + 4 * q]; u.Kp = u.K * c->uni_powerx[q]; u.KpT = u.Kp * k.inv_mu;
+        u.ax = key[15 + 4 * q]; u.ay = key[16 + 4 * q]; u.az = key[17 + 4 * q];
+        u.power = (c->uni_powerx[q] && u.K != 0.0) ? c->uni_powerx[q] : 0;
+        c->h_uni_extra.push_back(u);
+      }
       for (int d = 0; d < 3; ++d) { c->h_class_dc.push_back(key[7 + d]); c->h_class_ac.push_back(key[10 + d]); }
       c->h_class_omega.push_back(key[13]);
     } else {
@@ -270,6 +280,12 @@ int build_classes(jb_ctx *c) {
       lay[q++] = cls[(((long long)x * g.Ny + y) * g.Nz + z) * g.M + m];
     JB_CUDA(c, cudaMalloc(&c->d_site_class, N));
     JB_CUDA(c, cudaMemcpy(c->d_site_class, lay.data(), N, cudaMemcpyHostToDevice));
+  }
+  if (c->d_uni_extra) cudaFree(c->d_uni_extra);
+  c->d_uni_extra = nullptr;
+  if (c->has_uni_extra()) {
+    JB_CUDA(c, cudaMalloc(&c->d_uni_extra, c->h_uni_extra.size() * sizeof(JbUniExtra)));
+    JB_CUDA(c, cudaMemcpy(c->d_uni_extra, c->h_uni_extra.data(), c->h_uni_extra.size() * sizeof(JbUniExtra), cudaMemcpyHostToDevice));
   }
   c->classes_dirty = false;
   c->class_sig.clear();
@@ -393,6 +409,7 @@ void fill_tables(jb_ctx *c, JbTables &t, int class_table_index) {
   t.iso = c->iso ? 1 : 0;
   t.bq_global = c->has_bq ? c->d_bq_global : nullptr;
   for (int m = 0; m <= JB_MAX_MOTIF; ++m) t.bq_begin[m] = (m <= c->g.M && c->has_bq) ? c->bq_begin[m] : 0;
+  t.uni_extra = c->has_uni_extra() ? c->d_uni_extra : nullptr;
 }
 
 // ---- tiling of the persistent TMA tile kernel ----------------------------------------------------------
@@ -645,6 +662,7 @@ void choose_tiling(jb_ctx *c) {
   c->tiling_valid = true;
   c->tmap_valid = false;
   if (c->has_bq) return;   // the biquadratic field needs s_i inside the neighbour loop: direct kernel
+  if (c->has_uni_extra()) return;   // a second / third uniaxial term lives in a table only the direct kernels read (JbUniExtra)
   const int reach = std::max(c->g.gx, std::max(c->g.gy, c->g.gz));
   const bool deep = c->iso && c->has_template && (reach >= 3 || (reach >= 2 && c->t_mi.size() >= (size_t)40 * c->g.M));
   if (c->opt_kernel == 4 || deep) choose_rows_tiling(c);
@@ -1018,7 +1036,7 @@ void jb_destroy(jb_ctx *c) {
   void *p;
   p = c->d_aos; free_dev(p); p = c->d_scratch; free_dev(p);
   p = c->d_nbr_global; free_dev(p); p = c->d_Jtab; free_dev(p); p = c->d_tile_nbr; free_dev(p); p = c->d_tile_J9T; free_dev(p); p = c->d_rows; free_dev(p); p = c->d_bq_global; free_dev(p);
-  p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p);
+  p = c->d_classes; free_dev(p); p = c->d_site_class; free_dev(p); p = c->d_uni_extra; free_dev(p);
   p = c->d_ell_idx; free_dev(p); p = c->d_ell_val; free_dev(p); p = c->d_pair_J; free_dev(p);
   p = c->d_queue; free_dev(p); p = c->d_trace; free_dev(p); p = c->d_groups; free_dev(p);
   for (int r = 0; r < JB_MAX_REGIONS; ++r) { p = c->d_region[r]; free_dev(p); }
@@ -1271,6 +1289,21 @@ int jb_set_uniaxial(jb_ctx *c, int32_t power, const double *magnitude, const dou
   return JB_OK;
 }
 
+int jb_set_uniaxial_term(jb_ctx *c, int32_t slot, int32_t power, const double *magnitude, const double *axis) {
+  if (!c) return JB_ERR_INVALID;
+  if (slot == 0) return jb_set_uniaxial(c, power, magnitude, axis);
+  if (slot < 0 || slot >= JB_MAX_UNIAXIAL) JB_FAIL(c, JB_ERR_UNSUPPORTED, "more than three uniaxial Hamiltonians");
+  const int q = slot - 1;
+  if (power == 0 || !magnitude) { c->uni_powerx[q] = 0; c->h_Kx[q].clear(); c->h_axisx[q].clear(); }
+  else {
+    if (!(power == 2 || power == 4 || power == 6) || !axis) JB_FAIL(c, JB_ERR_INVALID, "Unsupported anisotropy power (K1,K2,K3 = 2,4,6)");
+    c->uni_powerx[q] = power; c->h_Kx[q].assign(magnitude, magnitude + c->N); c->h_axisx[q].assign(axis, axis + 3 * (size_t)c->N);
+  }
+  c->classes_dirty = true;
+  c->tiling_valid = false;   // a context with extra uniaxial terms steps on the direct kernels
+  return JB_OK;
+}
+
 int jb_set_zeeman(jb_ctx *c, const double *dc, const double *ac, const double *omega) {
   if (!c) return JB_ERR_INVALID;
   if ((ac == nullptr) != (omega == nullptr)) JB_FAIL(c, JB_ERR_INVALID, "must have a field and a frequency");
@@ -1518,7 +1551,7 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
   const bool periodic_x = c->g.per[0] && c->g.gx > 0;
   // the four stages on the persistent TMA kernel (isotropic templates the pair kernel can tile; option kernel = 0: direct gathers)
   choose_tiling(c);
-  const bool use_tile = c->tiling.ok && !c->tiling.rows && c->iso && !c->has_bq;
+  const bool use_tile = c->tiling.ok && !c->tiling.rows && c->iso && !c->has_bq && !c->has_uni_extra();
   JbTileParams tp{};
   if (use_tile) {
     rc = build_tmaps(c); if (rc) return rc;
@@ -1594,7 +1627,7 @@ int jb_noise(jb_ctx *c, double dt, double T, uint64_t seed, uint64_t step, int32
 }
 
 int jb_fields(jb_ctx *c, int32_t term, double time_ps, double *h_aos, int32_t on_device) {
-  if (!c || !h_aos || term < 0 || term > JB_TERM_BIQUADRATIC) return JB_ERR_INVALID;
+  if (!c || !h_aos || term < 0 || term > JB_TERM_UNIAXIAL_3) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
   std::vector<double> times{time_ps};
@@ -1614,7 +1647,7 @@ int jb_fields(jb_ctx *c, int32_t term, double time_ps, double *h_aos, int32_t on
 }
 
 int jb_energies(jb_ctx *c, int32_t term, double time_ps, double *e, int32_t on_device, double *total) {
-  if (!c || term < 0 || term == JB_TERM_TOTAL || term > JB_TERM_BIQUADRATIC) return JB_ERR_INVALID;
+  if (!c || term < 0 || term == JB_TERM_TOTAL || term > JB_TERM_UNIAXIAL_3) return JB_ERR_INVALID;
   if (!c->state_allocated) JB_FAIL(c, JB_ERR_INVALID, "no spins have been imported");
   int rc = ensure_ready(c); if (rc) return rc;
   std::vector<double> times{time_ps};

@@ -67,6 +67,19 @@ struct JbClass {
   double gyro;        // gyro_i (rad / ps / T): the RK4 stages need k = -gyro (...) without the step folded in
 };
 
+// A second / third uniaxial Hamiltonian of a configuration (the reference sums any number, e.g. K1 and K2 as two modules).  Kept out
+// of JbClass on purpose: the TMA stage kernels take their class constants as kernel parameters and never see these; a context
+// that has any runs its steps on the direct-gather kernels (choose_tiling), which read this table by class id.
+#define JB_MAX_UNIAXIAL 3
+struct JbUniExtra {
+  double Kp;          // K_i * power, meV
+  double K;           // K_i, meV
+  double KpT;         // K_i * power / mu_i, Tesla
+  double ax, ay, az;  // anisotropy axis
+  int power;          // 0 = this class has no such term
+  int pad;
+};
+
 // one entry of the exchange template of a motif site, in ghosted-box terms
 struct JbNbr {
   int delta;   // offset inside a plane of the ghosted box: (dy*M + (mj - mi))*PZ + dz
@@ -88,6 +101,8 @@ struct JbTables {
   // biquadratic exchange (hamiltonian/cuda_biquadratic_exchange_kernel.cuh): its own template, J = B_ij in meV; null = none
   const JbNbr *bq_global;
   int bq_begin[JB_MAX_MOTIF + 1];
+  // uniaxial slots 1 and 2 (jb_set_uniaxial_term): [class * (JB_MAX_UNIAXIAL - 1) + slot - 1]; null = none
+  const JbUniExtra *uni_extra;
 };
 
 // ---- parameter block of the fused stage kernels --------------------------------------------------
@@ -202,6 +217,9 @@ struct jb_ctx {
   // host copies of the caller's per-site parameters (kept to build classes lazily)
   std::vector<double> h_mus, h_gyro, h_alpha;
   std::vector<double> h_K, h_axis; int uni_power = 0;
+  std::vector<double> h_Kx[JB_MAX_UNIAXIAL - 1], h_axisx[JB_MAX_UNIAXIAL - 1]; int uni_powerx[JB_MAX_UNIAXIAL - 1] = {0, 0};   // slots 1, 2
+  std::vector<JbUniExtra> h_uni_extra; JbUniExtra *d_uni_extra = nullptr;
+  bool has_uni_extra() const { return uni_powerx[0] != 0 || uni_powerx[1] != 0; }
   std::vector<double> h_dc, h_ac, h_omega; bool has_zeeman = false, has_ac = false;
   double applied_B[3] = {0, 0, 0}; bool has_applied = false;
   int applied_type = 0; double applied_t0 = 0.0, applied_fbw = 0.0, applied_fc = 0.0;   // jb_set_applied_field_pulse

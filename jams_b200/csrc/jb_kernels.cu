@@ -48,6 +48,24 @@ __device__ __forceinline__ long long ref_site_local(const JbGeom &g, int x, int 
   return (((long long)x * g.Ny + y) * g.Nz + z) * g.M + m;
 }
 
+// a second / third uniaxial Hamiltonian (jb_set_uniaxial_term, JbUniExtra): H = K p (s.a)^(p-1) a of the slots in `slots` (bit
+// q = slot q + 1) added to (hx, hy, hz), in Tesla (K p / mu) or meV (uniaxial_anisotropy.cc:155-163)
+__device__ __forceinline__ void uniaxial_extra_site(const JbTables &t, int ci, int slots, bool tesla, double sx, double sy, double sz,
+                                                    double &hx, double &hy, double &hz) {
+  if (!t.uni_extra) return;
+  for (int q = 0; q < JB_MAX_UNIAXIAL - 1; ++q) {
+    if (!((slots >> q) & 1)) continue;
+    const JbUniExtra u = t.uni_extra[ci * (JB_MAX_UNIAXIAL - 1) + q];
+    if (u.power == 0) continue;
+    const double d = u.ax * sx + u.ay * sy + u.az * sz;
+    double pw = d;
+    if (u.power >= 4) pw = d * d * d;
+    if (u.power >= 6) pw = pw * d * d;
+    const double f = (tesla ? u.KpT : u.Kp) * pw;
+    hx = fma(f, u.ax, hx); hy = fma(f, u.ay, hy); hz = fma(f, u.az, hz);
+  }
+}
+
 // =================================================================================================
 // import / export between the reference's AoS site order and the ghosted SoA box
 // =================================================================================================
@@ -205,8 +223,9 @@ __global__ void __launch_bounds__(256) stage_direct_kernel(const __grid_constant
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
-  llg_site<STAGE, THERMAL>(c, sx, sy, sz, fma(hx, c.inv_mu, c.fTx), fma(hy, c.inv_mu, c.fTy), fma(hz, c.inv_mu, c.fTz), n0, n1, n2,
-                           ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  hx = fma(hx, c.inv_mu, c.fTx); hy = fma(hy, c.inv_mu, c.fTy); hz = fma(hz, c.inv_mu, c.fTz);   // Tesla
+  uniaxial_extra_site(p.t, ci, 3, true, sx, sy, sz, hx, hy, hz);
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
   store_with_images(p, x, y, m, z, ox, oy, oz);
 }
@@ -262,6 +281,7 @@ __global__ void __launch_bounds__(256) rk4_direct_kernel(const __grid_constant__
     const double f = c.KpT * pw;
     hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
   }
+  uniaxial_extra_site(p.t, ci, 3, true, sx, sy, sz, hx, hy, hz);
   if (THERMAL) {   // one draw per step, all four stages (cuda_rk4_base.cu:65)
     double n0, n1, n2;
     site_normals_at(g, p.seed, p.step, x, y, m, z, n0, n1, n2);
@@ -336,8 +356,9 @@ __global__ void __launch_bounds__(256) stage_pairs_kernel(const __grid_constant_
   double ux = 0, uy = 0, uz = 0;
   if (STAGE == 1) { ux = p.u[0][ic]; uy = p.u[1][ic]; uz = p.u[2][ic]; }
   double ox, oy, oz, vx, vy, vz;
-  llg_site<STAGE, THERMAL>(c, sx, sy, sz, fma(hx, c.inv_mu, c.fTx), fma(hy, c.inv_mu, c.fTy), fma(hz, c.inv_mu, c.fTz), n0, n1, n2,
-                           ux, uy, uz, ox, oy, oz, vx, vy, vz);
+  hx = fma(hx, c.inv_mu, c.fTx); hy = fma(hy, c.inv_mu, c.fTy); hz = fma(hz, c.inv_mu, c.fTz);   // Tesla
+  uniaxial_extra_site(p.t, ci, 3, true, sx, sy, sz, hx, hy, hz);
+  llg_site<STAGE, THERMAL>(c, sx, sy, sz, hx, hy, hz, n0, n1, n2, ux, uy, uz, ox, oy, oz, vx, vy, vz);
   if (STAGE == 0) { p.u[0][ic] = vx; p.u[1][ic] = vy; p.u[2][ic] = vz; }
   // one rank: no ghost cells at all (gx = gy = gz = 0: every neighbour is addressed directly); several ranks: the x images of the
   // face planes go into the neighbours' boxes
@@ -419,6 +440,8 @@ __global__ void field_kernel(const JbGeom g, const JbTables t, const double *__r
     const double f = c.Kp * pw;
     hx = fma(f, c.ax, hx); hy = fma(f, c.ay, hy); hz = fma(f, c.az, hz);
   }
+  if (term == JB_TERM_UNIAXIAL_2 || term == JB_TERM_UNIAXIAL_3 || term == JB_TERM_TOTAL)
+    uniaxial_extra_site(t, ci, term == JB_TERM_TOTAL ? 3 : (term == JB_TERM_UNIAXIAL_2 ? 1 : 2), false, inx[ic], iny[ic], inz[ic], hx, hy, hz);
   if (term == JB_TERM_ZEEMAN || term == JB_TERM_APPLIED || term == JB_TERM_TOTAL) { hx += c.fx; hy += c.fy; hz += c.fz; }
   const long long s = ref_site_local(g, x, y, m, z);
   h_aos[3 * s] = hx; h_aos[3 * s + 1] = hy; h_aos[3 * s + 2] = hz;
@@ -466,6 +489,11 @@ __global__ void __launch_bounds__(256) energy_kernel(const JbGeom g, const JbTab
       if (c.power != 0) {
         const double d = c.ax * sx + c.ay * sy + c.az * sz;
         e = -c.K * ipow_even(d, c.power);  // uniaxial_anisotropy.cc:126-133
+      }
+    } else if (term == JB_TERM_UNIAXIAL_2 || term == JB_TERM_UNIAXIAL_3) {
+      if (t.uni_extra) {
+        const JbUniExtra u = t.uni_extra[ci * (JB_MAX_UNIAXIAL - 1) + (term == JB_TERM_UNIAXIAL_2 ? 0 : 1)];
+        if (u.power != 0) e = -u.K * ipow_even(u.ax * sx + u.ay * sy + u.az * sz, u.power);
       }
     } else {  // ZEEMAN / APPLIED: -s . f   (zeeman.cc:82-87, applied_field.cc:150+)
       e = -(sx * c.fx + sy * c.fy + sz * c.fz);

@@ -1218,14 +1218,23 @@ void B200HeunLLGSolver::check(int status) const {
 }
 
 void B200HeunLLGSolver::register_hamiltonian(Hamiltonian *h) {
-  // one term of each kind in the fused kernels; the reference sums any number (core/solver.cc:43-57): refuse, do not drop
-  for (const auto &other : hamiltonians_)
-    if (other->term() == h->term()) {
-      const std::string msg = name() + ": hamiltonians '" + other->name() + "' and '" + h->name() +
-                              "' are the same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)";
-      delete h;
-      throw std::runtime_error(msg);
-    }
+  // The reference sums any number of Hamiltonians (core/solver.cc:43-57).  The fused kernels hold one bilinear exchange list, one
+  // biquadratic list, one Zeeman field and one applied field: a second one of those is refused, not dropped.  Uniaxial terms go
+  // into up to three slots (K1 + K2 + K3 as separate modules, jb_set_uniaxial_term).
+  if (auto *uni = dynamic_cast<UniaxialAnisotropyHamiltonian *>(h)) {
+    int n = 0;
+    for (const auto &other : hamiltonians_) n += dynamic_cast<UniaxialAnisotropyHamiltonian *>(other.get()) != nullptr;
+    if (n >= 3) { delete h; throw std::runtime_error(name() + ": more than three uniaxial hamiltonians (use the reference's solver)"); }
+    uni->set_slot(n);
+  } else {
+    for (const auto &other : hamiltonians_)
+      if (other->term() == h->term()) {
+        const std::string msg = name() + ": hamiltonians '" + other->name() + "' and '" + h->name() +
+                                "' are the same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)";
+        delete h;
+        throw std::runtime_error(msg);
+      }
+  }
   h->solver = this;
   hamiltonians_.emplace_back(h);
 }
@@ -1348,7 +1357,7 @@ void BiquadraticExchangeHamiltonian::attach(jb_ctx *ctx) {
   solver->check(jb_set_option(ctx, "check_symmetry", check_symmetry_ ? 1 : 0));
   solver->check(jb_set_biquadratic_template(ctx, static_cast<int32_t>(B_.size()), template_.mi.data(), template_.mj.data(), template_.T3.data(), B_.data()));
 }
-void UniaxialAnisotropyHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_uniaxial(ctx, power_, magnitude_.data(), axis_.data())); }
+void UniaxialAnisotropyHamiltonian::attach(jb_ctx *ctx) { solver->check(jb_set_uniaxial_term(ctx, slot_, power_, magnitude_.data(), axis_.data())); }
 void ZeemanHamiltonian::attach(jb_ctx *ctx) {
   solver->check(jb_set_zeeman(ctx, dc_local_field_.data(), has_ac_local_field_ ? ac_local_field_.data() : nullptr,
                               has_ac_local_field_ ? ac_local_frequency_.data() : nullptr));

@@ -196,9 +196,11 @@ class ExchangeNeartreeHamiltonian : public ExchangeHamiltonian {
 class UniaxialAnisotropyHamiltonian : public Hamiltonian {   // hamiltonian/uniaxial_anisotropy.cc:79-172
  public:
   UniaxialAnisotropyHamiltonian(const Setting &settings, const Lattice &lattice);
-  int term() const override { return JB_TERM_UNIAXIAL; }
+  int term() const override { return slot_ == 0 ? JB_TERM_UNIAXIAL : (slot_ == 1 ? JB_TERM_UNIAXIAL_2 : JB_TERM_UNIAXIAL_3); }
   void attach(jb_ctx *ctx) override;
+  void set_slot(int slot) { slot_ = slot; }   // the n-th uniaxial Hamiltonian of the configuration (jb_set_uniaxial_term)
  private:
+  int slot_ = 0;
   int power_ = 2;
   std::vector<double> magnitude_, axis_;
 };

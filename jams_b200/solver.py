@@ -296,6 +296,7 @@ class ExchangeNeartreeHamiltonian(ExchangeHamiltonian):
 class UniaxialAnisotropyHamiltonian(Hamiltonian):
     term = capi.TERM_UNIAXIAL
     name = "uniaxial"
+    slot = 0          # the n-th uniaxial Hamiltonian of a configuration (register_hamiltonian): term = capi.UNIAXIAL_TERMS[slot]
     _POWER = {"K1": 2, "K2": 4, "K3": 6}
 
     def __init__(self, settings: dict, lattice: Lattice):
@@ -345,7 +346,7 @@ class UniaxialAnisotropyHamiltonian(Hamiltonian):
 
     def attach(self, ctx, x0, nx):
         K, axis = self.site_arrays(x0, nx)
-        ctx.set_uniaxial(self.power, K, axis)
+        ctx.set_uniaxial(self.power, K, axis, slot=self.slot)
 
 
 class ZeemanHamiltonian(Hamiltonian):
@@ -687,12 +688,19 @@ class Solver:
         return self.iteration < self.max_steps
 
     def register_hamiltonian(self, h: Hamiltonian):
-        # the fused kernels hold ONE term of each kind (one bilinear exchange list, one uniaxial power, one Zeeman field ...);
-        # the reference sums any number of Hamiltonians (core/solver.cc:43-57), so a second one of a kind is refused, not dropped
-        for other in self.hamiltonians:
-            if other.term == h.term:
-                raise RuntimeError(f"{self.name}: hamiltonians '{other.settings.get('module')}' and '{h.settings.get('module')}' are the "
-                                   "same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)")
+        # the reference sums any number of Hamiltonians (core/solver.cc:43-57).  The fused kernels hold ONE bilinear exchange list, one
+        # biquadratic list, one Zeeman field and one applied field -- a second one of those is refused, not dropped -- and up to
+        # three uniaxial terms (K1 + K2 + K3 as separate modules: jb_set_uniaxial_term slots 0, 1, 2)
+        if isinstance(h, UniaxialAnisotropyHamiltonian):
+            n = sum(isinstance(o, UniaxialAnisotropyHamiltonian) for o in self.hamiltonians)
+            if n >= len(capi.UNIAXIAL_TERMS):
+                raise RuntimeError(f"{self.name}: more than {len(capi.UNIAXIAL_TERMS)} uniaxial hamiltonians (use the reference's solver)")
+            h.slot, h.term = n, capi.UNIAXIAL_TERMS[n]
+        else:
+            for other in self.hamiltonians:
+                if other.term == h.term:
+                    raise RuntimeError(f"{self.name}: hamiltonians '{other.settings.get('module')}' and '{h.settings.get('module')}' are the "
+                                       "same kind of term; the fused solver holds one of each kind (merge them, or use the reference's solver)")
         h.solver = self
         self.hamiltonians.append(h)
 

@@ -356,8 +356,8 @@ def test_error_behaviour_mirrors_the_reference():
 
 
 def test_a_second_hamiltonian_of_one_kind_is_refused_not_dropped():
-    """the reference sums any number of Hamiltonians (core/solver.cc:43-57); the fused kernels hold one term of each kind, so a
-    second one must fail loudly instead of silently replacing the first"""
+    """the reference sums any number of Hamiltonians (core/solver.cc:43-57); the fused kernels hold one exchange list, one Zeeman field
+    ... so a second one must fail loudly instead of silently replacing the first.  Uniaxial terms have three slots."""
     from jams_b200.solver import create_solver
     w = W.c3_sc(dims=(4, 4, 4))
     lat = w["lattice"]
@@ -366,9 +366,84 @@ def test_a_second_hamiltonian_of_one_kind_is_refused_not_dropped():
         s.register_hamiltonian(create_hamiltonian(h, lat))
     with pytest.raises(RuntimeError, match="same kind of term"):
         s.register_hamiltonian(create_hamiltonian(dict(module="zeeman", dc_local_field=[[0.0, 0.0, 0.5]]), lat))
-    s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order="K1", anisotropies=[("A", [0.0, 0.0, 1.0], 1e-23)]), lat))
     with pytest.raises(RuntimeError, match="same kind of term"):
-        s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order="K2", anisotropies=[("A", [0.0, 0.0, 1.0], 1e-23)]), lat))
+        s.register_hamiltonian(create_hamiltonian(dict(module="exchange", interactions=[("A", "A", [0.0, 1.0, 0.0], 1e-21)]), lat))
+    for order in ("K1", "K2", "K3"):
+        s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order=order, anisotropies=[("A", [0.0, 0.0, 1.0], 1e-23)]), lat))
+    with pytest.raises(RuntimeError, match="more than 3 uniaxial"):
+        s.register_hamiltonian(create_hamiltonian(dict(module="uniaxial", order="K1", anisotropies=[("A", [1.0, 0.0, 0.0], 1e-23)]), lat))
+
+
+@pytest.mark.parametrize("solver_module", ["llg-heun-b200-gpu", "llg-rk4-b200-gpu"])
+def test_several_uniaxial_hamiltonians_are_summed_like_the_reference(solver_module):
+    """K1 + K2 + K3 written as three "uniaxial" modules (one power each, uniaxial_anisotropy.cc:89-114) on a two-material bcc lattice,
+    different axes, the K2 module on one material only: per-term fields and energies, the total field, T = 0 and same-noise T > 0
+    trajectories against the oracle, which sums its terms like Solver::compute_fields.  Slots 1 and 2 live in a table only the
+    direct-gather kernels read, so the step must not run on a TMA kernel."""
+    from jams_b200.solver import create_solver
+    lat = Lattice([Material("A", 2.0, alpha=0.05), Material("B", 1.2, alpha=0.2)], np.eye(3), [("A", (0, 0, 0)), ("B", (0.5, 0.5, 0.5))], (6, 5, 8))
+    hams = [dict(module="uniaxial", order="K1", anisotropies=[("A", [0.0, 0.0, 1.0], 4e-23), ("B", [1.0, 0.0, 0.0], 2e-23)]),
+            dict(module="exchange", interactions=[("A", "B", [0.5, 0.5, 0.5], 3.0e-21), ("B", "A", [0.5, 0.5, 0.5], 3.0e-21)]),
+            dict(module="uniaxial", order="K2", anisotropies=[("B", [0.0, 0.6, 0.8], 3e-23)]),
+            dict(module="uniaxial", order="K3", anisotropies=[(1, [1.0, 1.0, 1.0], 1e-23), (2, [0.0, 1.0, 0.0], -2e-23)])]
+    w = dict(name="three uniaxial", lattice=lat, hamiltonians=hams, spins=None, temperature=0.0)
+    rk4 = "rk4" in solver_module
+    s0 = random_unit_spins(lat.num_spins, 77)
+    s = create_solver(dict(module=solver_module, t_step=1e-16, t_max=1e-9, seed=5), lat)
+    for h in hams:
+        s.register_hamiltonian(create_hamiltonian(h, lat))
+    assert [h.term for h in s.hamiltonians] == [capi.TERM_UNIAXIAL, capi.TERM_EXCHANGE, capi.TERM_UNIAXIAL_2, capi.TERM_UNIAXIAL_3]
+    s.set_spins(s0)
+    # the oracle takes the terms one by one (helpers.build_cpu_sim keys them by module name: assemble it here)
+    from helpers import ref_material_arrays, ref_uniaxial_arrays, oracle_exchange_pairs
+    mus, gyro, alpha = ref_material_arrays(lat)
+
+    def cpu_sim(T=0.0):
+        sim = oracle.CpuSim(mus, gyro, alpha)
+        ids = []
+        for hs in hams:
+            if hs["module"] == "exchange":
+                i, j, J9, _ = oracle_exchange_pairs(lat, hs)
+                ids.append(sim.add_exchange(i, j, J9))
+            else:
+                ids.append(sim.add_uniaxial(*ref_uniaxial_arrays(lat, hs)))
+        sim.init_solver(1e-4, lat.gilbert_prefactor, 1)
+        sim.set_temperature(T)
+        return sim, ids
+
+    sim, ids = cpu_sim()
+    sim.set_spins(s0)
+    total = np.zeros_like(s0)
+    for h, tid in zip(s.hamiltonians, ids):
+        ref_f = sim.term_fields(tid, 0.0)
+        f = h.calculate_fields(0.0)
+        assert np.abs(f - ref_f).max() <= 1e-13 * np.abs(ref_f).max(), h.settings
+        total += ref_f
+        e, tot = s.ctx.energies(h.term, 0.0)
+        assert np.abs(e - sim.term_energies(tid)).max() <= 1e-12 * np.abs(e).max(), h.settings
+        assert abs(tot - sim.term_total_energy(tid, 0.0)) <= 1e-12 * abs(tot), h.settings
+    assert np.abs(s.compute_fields() - total).max() <= 1e-13 * np.abs(total).max()
+    steps = 30
+    (sim.run_rk4 if rk4 else sim.run)(steps)
+    s.run(steps)
+    assert s.ctx.stage_kernel() in (-1, 0)
+    assert np.abs(s.spins() - sim.get_spins()).max() <= TRAJ_TOL
+    if not rk4:
+        T, seed = 90.0, 5
+        s.set_temperature(T)
+        s.set_spins(s0)
+        it0 = s.iteration
+        normals = np.stack([s.ctx.noise(s.step_size, T, seed, it0 + n, normals_only=True) for n in range(10)])
+        sim2, _ = cpu_sim(T)
+        sim2.set_spins(s0)
+        sim2.run(10, normals)
+        s.run(10)
+        assert np.abs(s.spins() - sim2.get_spins()).max() <= TRAJ_TOL
+    # clearing the extra slots gives the TMA kernel back
+    s.ctx.set_uniaxial(0, None, None, slot=1); s.ctx.set_uniaxial(0, None, None, slot=2)
+    s.ctx.step(1, s.step_size, s.time, 0.0, 0, s.iteration)
+    if not rk4:
+        assert s.ctx.stage_kernel() == 2
 
 
 # ---- RK4-LLG (SURVEY.md 8f row 3): jb_step_rk4 against the restatement of CudaRK4BaseSolver::run ----

@@ -169,16 +169,29 @@ def test_error_behaviour_mirrors_the_reference():
 
 
 @pytest.mark.gpu
-def test_cpp_a_second_hamiltonian_of_one_kind_is_refused_not_dropped(tmp_path):
-    """the reference sums any number of Hamiltonians (core/solver.cc:43-57); the fused solver holds one term of each kind and must
-    say so instead of letting the later one replace the earlier"""
+def test_cpp_several_uniaxial_hamiltonians_and_the_one_of_a_kind_rule(tmp_path):
+    """the reference sums any number of Hamiltonians (core/solver.cc:43-57): two "uniaxial" modules (K1 + K2) run in two slots and
+    give the Python mirror's trajectory bit for bit; a second exchange module is refused instead of replacing the first"""
     text = open(FIXTURE).read()
-    extra = '{ module = "uniaxial"; order = "K2"; anisotropies = ( ( "A", [ 0.0, 0.0, 1.0 ], 1e-24 ) ); },\n  {\n    module = "exchange";'
     assert text.count('{\n    module = "exchange";') == 1
+    k2 = '{ module = "uniaxial"; order = "K2"; anisotropies = ( ( "A", [ 0.0, 0.6, 0.8 ], 3e-23 ) ); },\n  {\n    module = "exchange";'
     cfg = tmp_path / "two_uniaxial.cfg"
-    cfg.write_text(text.replace('{\n    module = "exchange";', extra))
+    cfg.write_text(text.replace('{\n    module = "exchange";', k2))
+    got, done = host.run(str(cfg), PATCH_B200, name="k1k2", output_dir=str(tmp_path))
+    w = W.c1_bloch_wall((32, 4, 4))
+    w["hamiltonians"].insert(1, dict(module="uniaxial", order="K2", anisotropies=[("A", [0.0, 0.6, 0.8], 3e-23)]))
+    assert [h["module"] for h in w["hamiltonians"]] == ["uniaxial", "uniaxial", "exchange"]
+    init, _ = host.run(str(cfg), PATCH_B200, name="init", output_dir=str(tmp_path), max_steps=0)
+    s = W.make_solver(w)
+    s.set_spins(init)
+    s.run(done)
+    assert s.ctx.stage_kernel() == 0 and np.array_equal(got, s.spins())
+    eng = open(tmp_path / "k1k2_eng.tsv").read().splitlines()
+    assert eng[0].split() == ["time", "uniaxial_E_meV", "uniaxial_E_meV", "exchange_E_meV"]
+    two_exchange = tmp_path / "two_exchange.cfg"
+    two_exchange.write_text(text.replace('{\n    module = "exchange";', '{ module = "exchange"; interactions = (("A", "A", [0.0, 1.0, 0.0], 1e-21)); },\n  {\n    module = "exchange";'))
     with pytest.raises(host.HostError, match="same kind of term"):
-        host.run(str(cfg), PATCH_B200, name="dup", output_dir=str(tmp_path))
+        host.run(str(two_exchange), PATCH_B200, name="dup", output_dir=str(tmp_path))
 
 
 @pytest.mark.gpu
