@@ -236,7 +236,7 @@ def test_full_size_properties_sc_128():
 
 @pytest.mark.parametrize("n_slabs", [2, 4])
 @pytest.mark.parametrize("periodic_x", [True, False])
-@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4", "rk4_fold", "rk4_direct", "pairs"])
+@pytest.mark.parametrize("kernel", ["2r", "2u", "2r_fold", "2u_fold", "rows", "rows_fold", "rk4", "rk4_fold", "rk4_direct", "pairs", "direct", "direct_uni3"])
 def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic_x, kernel):
     """several contexts (one per x-slab) on this GPU, halos exchanged by peer stores + epoch flags; thermal noise is
     keyed by the global site so the result must equal the undecomposed run bit for bit"""
@@ -256,6 +256,8 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
         if kernel.startswith("rk4"):
             c.set_option("kernel", 0 if kernel == "rk4_direct" else 2)
             c.set_option("fold_halo", 2 if kernel.endswith("fold") else 0)
+        elif kernel.startswith("direct"):   # the direct-gather Heun stages (what biquadratic exchange and uniaxial slots 1, 2 run on)
+            c.set_option("kernel", 0)
         else:
             c.set_option("kernel", 4 if kernel.startswith("rows") else 2)
             c.set_option("recover_u", 0 if kernel.startswith("2u") else 1)   # two launches per step, two halo exchanges
@@ -263,6 +265,10 @@ def test_slab_decomposition_in_one_process_matches_single_slab(n_slabs, periodic
             # works because these lattices leave most of the SMs free for the neighbour's kernel
             c.set_option("fold_halo", 2 if kernel.endswith("fold") else 0)
         c.set_materials(lat.mus(rank * nx, nx), lat.gyro(rank * nx, nx), lat.alpha(rank * nx, nx))
+        if kernel == "direct_uni3":   # three uniaxial Hamiltonians: slots 1 and 2 force the direct kernels whatever the option says
+            n_loc = nx * dims[1] * dims[2] * lat.M
+            for slot, (power, K, axis) in enumerate([(2, 0.02, (0.0, 0.0, 1.0)), (4, 0.03, (0.0, 0.6, 0.8)), (6, -0.01, (1.0, 0.0, 0.0))]):
+                c.set_uniaxial(power, np.full(n_loc, K), np.tile(np.asarray(axis), (n_loc, 1)), slot=slot)
         if kernel == "pairs":   # the general neighbour list, GLOBAL site ids on every rank: neighbours across a slab face sit in the x ghost planes
             c.set_option("detect_template", 0)
             c.set_exchange_pairs(*nbr)
