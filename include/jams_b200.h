@@ -239,9 +239,13 @@ JB_API int jb_halo_connect(jb_ctx *ctx, const void *blob_lo_neighbour, const voi
 /* ---- introspection for benches and tests -------------------------------------------------------- */
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
 JB_API int64_t jb_kernel_launches(const jb_ctx *ctx);
-/* device time in ms of the stage kernels of the most recent jb_step, measured with CUDA events on the
+/* device time in ms of the stage kernels since the last call (option "time_kernels" > 0), measured with CUDA events on the
  * context's stream; out2[0] = stage A total, out2[1] = stage B total.  Synchronises. */
 JB_API int jb_last_step_kernel_ms(jb_ctx *ctx, double *out2);
+/* how many steps contributed to those totals: with option "time_kernels" = N the launches of every N-th step of a jb_step call are
+ * bracketed by events (N = 1: all of them; an event record between two launches costs about 2 us of stream time, so a bench keeps
+ * N > 1 inside its timed region).  Reset by jb_last_step_kernel_ms. */
+JB_API int64_t jb_timed_steps(const jb_ctx *ctx);
 /* which stage kernel the most recent jb_step ran: JB_KERNEL_DIRECT (one thread per spin, gathers through L1 / L2), JB_KERNEL_PAIR
  * (TMA plane ring, a z pair of sites per thread: jb_stage_pair.cu), JB_KERNEL_ROWS (TMA plane ring, four y rows per thread with
  * register reuse, deep isotropic templates: jb_stage_rows.cu), JB_KERNEL_ELL (general neighbour list); -1 before the first step */

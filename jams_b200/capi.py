@@ -46,6 +46,7 @@ SIGNATURES = {
                                                C.POINTER(C.c_int32), _ip, _ip, _ip, _dp]),
     "jb_set_uniaxial": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "jb_set_uniaxial_term": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "jb_timed_steps": (C.c_int64, [C.c_void_p]),
     "jb_set_zeeman": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "jb_set_applied_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "jb_set_applied_field_pulse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double]),
@@ -317,9 +318,13 @@ class Context:
         return int(self.lib.jb_stage_kernel(self.h))
 
     def last_step_kernel_ms(self):
+        """totals since the last call (option time_kernels > 0); divide by ``timed_steps()`` taken BEFORE this call"""
         out = np.zeros(2)
         self._ck(self.lib.jb_last_step_kernel_ms(self.h, out))
         return out
+
+    def timed_steps(self):
+        return int(self.lib.jb_timed_steps(self.h))
 
     def synchronize(self):
         self._ck(self.lib.jb_synchronize(self.h))

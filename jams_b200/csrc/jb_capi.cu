@@ -971,7 +971,7 @@ int ensure_ready(jb_ctx *c) {
 }
 
 void record_event(jb_ctx *c, int kind) {
-  if (!c->opt_time_kernels) return;
+  if (!c->opt_time_kernels || !c->time_this_step) return;
   if (c->ev_used >= c->ev.size()) {
     if (c->ev.size() >= 16384) return;
     cudaEvent_t e;
@@ -1492,6 +1492,9 @@ int jb_step(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, uint
     rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
 
     for (int n = 0; n < chunk; ++n) {
+      // option time_kernels = N: the launches of every N-th step are bracketed by events (N = 1: every step; a record costs ~2 us)
+      c->time_this_step = c->opt_time_kernels > 0 && (done + n) % c->opt_time_kernels == 0;
+      if (c->time_this_step) c->timed_steps++;
       for (int stage = 0; stage < 2; ++stage) {
         JbStageParams p{};
         p.g = c->g;
@@ -1574,6 +1577,8 @@ int jb_step_rk4(jb_ctx *c, int32_t nsteps, double dt, double time_ps, double T, 
     }
     rc = upload_classes(c, times, dt, T, gilbert, JB_TERM_TOTAL); if (rc) return rc;
     for (int n = 0; n < chunk; ++n) {
+      c->time_this_step = c->opt_time_kernels > 0 && (done + n) % c->opt_time_kernels == 0;
+      if (c->time_this_step) c->timed_steps++;
       for (int stage = 0; stage < 4; ++stage) {
         JbStageParams p{};
         p.g = c->g;
@@ -1870,8 +1875,11 @@ int jb_last_step_kernel_ms(jb_ctx *c, double *out2) {
     out2[c->ev_kind[i] / 2] += ms;
   }
   c->ev_used = 0;
+  c->timed_steps = 0;
   return JB_OK;
 }
+
+int64_t jb_timed_steps(const jb_ctx *c) { return c ? c->timed_steps : 0; }
 
 int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   if (!c || !key) return JB_ERR_INVALID;
@@ -1897,7 +1905,7 @@ int jb_set_option(jb_ctx *c, const char *key, int64_t value) {
   else if (k == "trace") { c->opt_trace = (int)value; return JB_OK; }
   else if (k == "verbose") { c->opt_verbose = (int)value; return JB_OK; }
   else if (k == "detect_template") { c->opt_detect_template = (int)value; return JB_OK; }
-  else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; return JB_OK; }  // no re-tiling
+  else if (k == "time_kernels") { c->opt_time_kernels = (int)value; c->ev_used = 0; c->timed_steps = 0; return JB_OK; }  // no re-tiling
   else JB_FAIL(c, JB_ERR_INVALID, "unknown option " + k);
   c->tiling_valid = false;
   c->tmap_valid = false;

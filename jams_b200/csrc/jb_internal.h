@@ -322,7 +322,8 @@ struct jb_ctx {
   int opt_oz = 4;             // column of z = 0 inside a row (4, 8 or 16 doubles): 4 = 32-byte sectors, the shortest gap between rows
   bool state_relayout = false; // an option that changes the box layout was set: re-layout at the next ensure_ready
   int opt_detect_template = 1;   // jb_set_exchange_pairs: turn translation-invariant lists into a template
-  int opt_time_kernels = 0;
+  int opt_time_kernels = 0;      // N > 0: bracket the stage launches of every N-th step of a jb_step / jb_step_rk4 call with events
+  bool time_this_step = false; long long timed_steps = 0;
 
   // halo peers
   double *peer_lo_S0[3] = {nullptr, nullptr, nullptr}, *peer_lo_S1[3] = {nullptr, nullptr, nullptr};
