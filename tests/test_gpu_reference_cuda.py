@@ -11,10 +11,13 @@ has the reference tree, travels like the other built libraries).  It is what `ll
 These tests pin the three restatements the oracle header lists as "unpinned by reference vectors" -- rk4_run, the biquadratic term
 and pin_region -- to the reference's kernels themselves, and compare the product with the very code it replaces.  Tolerances: the
 fp64 1e-10 trajectory bar of BASELINE.json; fields 1e-13 relative (cuSPARSE sums a row in its own order)."""
+import os
+
 import numpy as np
 import pytest
 
 import oracle
+import refcuda_cases as RC
 from helpers import ENERGY_UNITS, build_cpu_sim, oracle_exchange_pairs, random_unit_spins
 from jams_b200 import workloads as W
 from jams_b200.lattice import Lattice, Material
@@ -255,10 +258,6 @@ def test_magnetisation_monitor_against_the_reference_cuda_reductions():
 
 # ---- the product against the committed vectors the reference's CUDA kernels produced (tests/golden/refcuda_*.npz, generated by
 # ---- tests/golden/make_golden_refcuda.py on the GPU box): these need no reference library at run time -----------------------------
-import os
-
-import refcuda_cases as RC
-
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
