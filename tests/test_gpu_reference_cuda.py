@@ -256,6 +256,38 @@ def test_magnetisation_monitor_against_the_reference_cuda_reductions():
         assert np.abs(oracle.ref_cuda_reduce(2, x, None, idx) - x[idx].sum(axis=0)).max() <= 1e-11
 
 
+@pytest.mark.gpu
+@needs_lib
+@pytest.mark.parametrize("rk4", [False, True])
+def test_three_uniaxial_modules_reference_cuda_kernels_and_product_agree(rk4):
+    """K1 + K2 + K3 as three "uniaxial" modules: the reference launches cuda_uniaxial_field_kernel once per module and sums the
+    fields with daxpy (cuda/cuda_solver.cc:11-26); the product keeps them in three slots (jb_set_uniaxial_term)"""
+    from helpers import ref_material_arrays, ref_uniaxial_arrays
+    lat = Lattice([Material("A", 2.0, alpha=0.05), Material("B", 1.2, alpha=0.2)], np.eye(3), [("A", (0, 0, 0)), ("B", (0.5, 0.5, 0.5))], (6, 5, 8))
+    hams = [dict(module="uniaxial", order="K1", anisotropies=[("A", [0.0, 0.0, 1.0], 4e-23), ("B", [1.0, 0.0, 0.0], 2e-23)]),
+            dict(module="exchange", interactions=[("A", "B", [0.5, 0.5, 0.5], 3.0e-21), ("B", "A", [0.5, 0.5, 0.5], 3.0e-21)]),
+            dict(module="uniaxial", order="K2", anisotropies=[("B", [0.0, 0.6, 0.8], 3e-23)]),
+            dict(module="uniaxial", order="K3", anisotropies=[(1, [1.0, 1.0, 1.0], 1e-23), (2, [0.0, 1.0, 0.0], -2e-23)])]
+    w = dict(name="three uniaxial", lattice=lat, hamiltonians=hams, spins=None, temperature=0.0)
+    s0 = random_unit_spins(lat.num_spins, 77)
+    ref = oracle.RefCudaSim(*ref_material_arrays(lat))
+    for hs in hams:
+        if hs["module"] == "exchange":
+            i, j, J9, _ = oracle_exchange_pairs(lat, hs)
+            ref.add_exchange(i, j, J9)
+        else:
+            ref.add_uniaxial(*ref_uniaxial_arrays(lat, hs))
+    ref.init_solver(1e-4, lat.gilbert_prefactor, 1)
+    ref.set_spins(s0)
+    s = _solver(w, "llg-rk4-b200-gpu" if rk4 else "llg-heun-b200-gpu")
+    s.set_spins(s0)
+    h_ref = ref.get_h()
+    assert np.abs(s.compute_fields() - h_ref).max() <= 1e-13 * np.abs(h_ref).max()
+    (ref.run_rk4 if rk4 else ref.run)(25)
+    s.run(25)
+    assert np.abs(s.spins() - ref.get_spins()).max() <= TRAJ_TOL
+
+
 # ---- the product against the committed vectors the reference's CUDA kernels produced (tests/golden/refcuda_*.npz, generated by
 # ---- tests/golden/make_golden_refcuda.py on the GPU box): these need no reference library at run time -----------------------------
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
