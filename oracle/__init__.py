@@ -156,7 +156,7 @@ def reference() -> _Lib:
 REF_CUDA_SYMBOLS = ("jrc_last_error", "jrc_device_count", "jrc_sim_create", "jrc_sim_destroy", "jrc_sim_add_exchange",
                     "jrc_sim_add_uniaxial", "jrc_sim_add_zeeman", "jrc_sim_exchange_nnz", "jrc_sim_set_spins", "jrc_sim_get_spins",
                     "jrc_sim_get_h", "jrc_sim_init_solver", "jrc_sim_run_heun", "jrc_sim_run_rk4", "jrc_sim_time_heun", "jrc_sim_time_rk4",
-                    "jrc_biquadratic_field", "jrc_pin_region", "jrc_reduce")
+                    "jrc_biquadratic_field", "jrc_pin_region", "jrc_reduce", "jrc_multiarray_contract")
 
 
 def reference_cuda():
@@ -309,6 +309,27 @@ class RefCudaSim:
         if ms < 0:
             raise RuntimeError(self.error())
         return ms
+
+
+def ref_cuda_multiarray_contract(product_lib, product_ctx, s_aos, between):
+    """the JAMS adapter's import -> steps -> export through the reference's own MultiArray (SyncedMemory in CUDA mode).
+    ``product_lib`` / ``product_ctx``: the ctypes library and context handle of the product (jb_import_spins / jb_export_spins are handed
+    over as function pointers); ``between(ctx_handle)`` runs the steps.  Returns (spins a monitor reads after the export, the host
+    copy as it stood before the export)."""
+    L = reference_cuda()
+    IMPORT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+    EXPORT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+    BETWEEN = C.CFUNCTYPE(None, C.c_void_p)
+    imp = C.cast(product_lib.jb_import_spins, IMPORT)
+    exp = C.cast(product_lib.jb_export_spins, EXPORT)
+    cb = BETWEEN(lambda h: between(h))
+    s = _f64(s_aos, (-1,))
+    out, before = np.zeros_like(s), np.zeros_like(s)
+    L.jrc_multiarray_contract.restype = C.c_int
+    L.jrc_multiarray_contract.argtypes = [C.c_int, _c_double_p, _c_double_p, _c_double_p, IMPORT, EXPORT, C.c_void_p, BETWEEN]
+    if L.jrc_multiarray_contract(s.size // 3, s, out, before, imp, exp, product_ctx, cb) != 0:
+        raise RuntimeError((L.jrc_last_error() or b"").decode())
+    return out.reshape(-1, 3), before.reshape(-1, 3)
 
 
 def ref_cuda_biquadratic_field(n, i, j, B, s_aos):

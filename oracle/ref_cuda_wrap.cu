@@ -442,6 +442,27 @@ int jrc_pin_region(int n, double *s, const double *mus, int count, const int *in
   });
 }
 
+// The adapter's data path through the reference's real container (integration/jams/solvers/b200_llg_heun.cc): globals::s is a
+// jams::MultiArray<double, 2>; the adapter imports from its CONST device_data() (host copy stays valid, synced_memory.h const_device_data),
+// steps, and exports into its NON-const device_data(), which marks the host copy stale so that the monitors' next data() call
+// downloads it (synced_memory.h mutable_device_data / const_host_data).  `import_fn` / `export_fn` are jb_import_spins / jb_export_spins
+// of the product (handed over as pointers: this library does not link it), `between` runs the steps.
+int jrc_multiarray_contract(int n, const double *s_in, double *s_out, double *host_copy_before_export,
+                            int (*import_fn)(void *, const double *, int), int (*export_fn)(void *, double *, int), void *ctx,
+                            void (*between)(void *)) {
+  return guarded([&] {
+    Field spins(n, 3);
+    fill(spins, s_in);
+    if (import_fn(ctx, static_cast<const Field &>(spins).device_data(), 1) != 0) throw std::runtime_error("import failed");
+    between(ctx);
+    // the host copy has not been touched by the import
+    std::memcpy(host_copy_before_export, static_cast<const Field &>(spins).data(), sizeof(double) * 3 * n);
+    if (export_fn(ctx, spins.device_data(), 1) != 0) throw std::runtime_error("export failed");
+    cudaDeviceSynchronize();
+    std::memcpy(s_out, static_cast<const Field &>(spins).data(), sizeof(double) * 3 * n);   // what a monitor reads: synced from the device
+  });
+}
+
 // the reductions behind the magnetisation monitor on the CUDA path (cuda/cuda_array_reduction.cu): kind 0 = sum s, 1 = sum mus s,
 // 2 = indexed sum s, 3 = indexed sum mus s
 int jrc_reduce(int kind, int n, const double *s, const double *mus, int count, const int *indices, double *out3) {

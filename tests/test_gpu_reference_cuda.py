@@ -258,6 +258,34 @@ def test_magnetisation_monitor_against_the_reference_cuda_reductions():
 
 @pytest.mark.gpu
 @needs_lib
+def test_adapter_data_path_through_the_reference_multiarray():
+    """row a18: the JAMS adapter hands globals::s.device_data() to jb_import_spins / jb_export_spins with on_device = 1
+    (integration/jams/solvers/b200_llg_heun.cc).  Here globals::s is the reference's real jams::MultiArray (SyncedMemory in CUDA
+    mode): the const device pointer leaves the host copy valid, the non-const one marks it stale, and the next host read -- what a
+    monitor does -- downloads the exported spins."""
+    w = _two_term_sc((10, 8, 12))
+    lat = w["lattice"]
+    s0 = random_unit_spins(lat.num_spins, 3)
+    s = _solver(w, "llg-heun-b200-gpu")
+    s.set_spins(random_unit_spins(lat.num_spins, 99))        # something else, so that the import matters
+    s.run(1)
+    steps = 7
+
+    def between(_handle):
+        s.ctx.step(steps, s.step_size, 0.0, 0.0, 0, 0)
+
+    seen, before = oracle.ref_cuda_multiarray_contract(s.ctx.lib, s.ctx.h, s0, between)
+    assert np.array_equal(before, s0)                          # import through the const pointer: host copy untouched
+    want = s.ctx.export_spins()                                # the product's own host export of the same state
+    assert np.array_equal(seen, want)
+    cpu = build_cpu_sim(w)
+    cpu.set_spins(s0)
+    cpu.run(steps)
+    assert np.abs(seen - cpu.get_spins()).max() <= TRAJ_TOL
+
+
+@pytest.mark.gpu
+@needs_lib
 @pytest.mark.parametrize("rk4", [False, True])
 def test_three_uniaxial_modules_reference_cuda_kernels_and_product_agree(rk4):
     """K1 + K2 + K3 as three "uniaxial" modules: the reference launches cuda_uniaxial_field_kernel once per module and sums the
